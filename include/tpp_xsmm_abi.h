@@ -1,0 +1,238 @@
+/*
+ * tpp_xsmm_abi.h - C-ABI of the B200-native TPP execution backend.
+ *
+ * This is the drop-in boundary: the shared library built from
+ * tpp_mlir_b200/csrc (libtpp_xsmm_runner_utils.so) exports exactly the symbols
+ * that tpp-mlir's JIT-compiled code calls after the ConvertXsmmToFunc lowering.
+ *
+ * Reference interfaces replaced (all paths relative to the tpp-mlir tree):
+ *   runtime/Xsmm/XsmmRunnerUtils.h:22-83     the 13 xsmm_* entry points
+ *   runtime/PerfRunnerUtils.h:22-24          perf_start_timer / perf_stop_timer
+ *   lib/TPP/Transforms/Utils/VNNIUtils.cpp:36 libxsmm_cpuid_dot_pack_factor
+ *   lib/TPP/Conversion/ConvertXsmmToFunc/ConvertXsmmToFunc.cpp:37-101,298-352
+ *                                            argument order / types (all i64)
+ *
+ * Differences from the reference header, on purpose:
+ *   - every integer (including the enums) is declared int64_t, because that is
+ *     what the lowering really passes (MLIR i64); the reference declares 32-bit
+ *     enums and relies on the x86-64 SysV register width.
+ *   - pointers may be DEVICE pointers (fast path, no copies), host pointers that
+ *     were registered with xsmm_cuda_register_host (translated to a device
+ *     mirror), or plain host pointers (strict mode: operands are staged to the
+ *     GPU, the kernel runs, the result is copied back and the call returns
+ *     after the result is visible to the host - the reference's semantics).
+ *   - there is NO CPU fallback: if no CUDA device / sm_100 kernel image is
+ *     available the first dispatch prints a diagnostic and exit(-1)s, the same
+ *     way the reference does when libxsmm cannot JIT a kernel
+ *     (runtime/Xsmm/XsmmRunnerUtils.cpp:132-137).
+ *
+ * Layout notation (row-major view, what tpp-mlir passes):
+ *   A[b][i][p] at A + b*stride_a + i*lda + p      (i<m, p<k)
+ *   B[b][p][j] at B + b*stride_b + p*ldb + j      (j<n)   or VNNI [K/2][N][2]
+ *   C[i][j]    at C + i*ldc + j
+ * All ld and stride values are in ELEMENTS. ptr = alignedPtr + offset*sizeof(T)
+ * (runtime/Xsmm/XsmmRunnerUtils.cpp:63-75).
+ */
+#ifndef TPP_XSMM_ABI_H
+#define TPP_XSMM_ABI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define TPP_XSMM_EXPORT __attribute__((visibility("default")))
+#else
+#define TPP_XSMM_EXPORT
+#endif
+
+/* ---- enum values (include/TPP/Dialect/Xsmm/XsmmEnum.td:13-84) ------------- */
+enum {
+  XSMM_DTYPE_F32 = 1,
+  XSMM_DTYPE_BF16 = 2
+};
+enum {
+  XSMM_BINARY_NONE = 0,
+  XSMM_BINARY_ADD = 1,
+  XSMM_BINARY_MUL = 2,
+  XSMM_BINARY_SUB = 3,
+  XSMM_BINARY_DIV = 4
+};
+enum {
+  XSMM_UNARY_NONE = 0,
+  XSMM_UNARY_IDENTITY = 1,
+  XSMM_UNARY_ZERO = 2,
+  XSMM_UNARY_RELU = 5,
+  XSMM_UNARY_VNNI2 = 28,
+  XSMM_UNARY_TRANSPOSE = 29,
+  /* extension (not in the reference dialect): inverse of VNNI2, [K/2][N][2] -> [K][N] */
+  XSMM_UNARY_UNVNNI2_EXT = 1028
+};
+enum {
+  XSMM_UNARY_FLAG_NONE = 0,
+  XSMM_UNARY_FLAG_BCAST_ROW = 2,
+  XSMM_UNARY_FLAG_BCAST_COL = 4,
+  XSMM_UNARY_FLAG_BCAST_SCALAR = 8
+};
+enum {
+  XSMM_BINARY_FLAG_NONE = 0,
+  XSMM_BINARY_FLAG_BCAST_ROW_IN_0 = 1,
+  XSMM_BINARY_FLAG_BCAST_ROW_IN_1 = 2,
+  XSMM_BINARY_FLAG_BCAST_COL_IN_0 = 4,
+  XSMM_BINARY_FLAG_BCAST_COL_IN_1 = 8,
+  XSMM_BINARY_FLAG_BCAST_SCALAR_IN_0 = 16,
+  XSMM_BINARY_FLAG_BCAST_SCALAR_IN_1 = 32
+};
+/* GEMM flags AS RECEIVED by the C-ABI, i.e. after the lowering swapped the
+ * dialect's vnni_a <-> vnni_b for libxsmm's column-major view
+ * (ConvertXsmmToFunc.cpp:251-265; test/Conversion/XsmmToFunc/xsmm-to-func.mlir:86-116):
+ *   2048 (libxsmm VNNI_A) == dialect vnni_b : row-major B operand is [K/2][N][2]
+ *   4096 (libxsmm VNNI_B) == dialect vnni_a : row-major A operand is [M][K/2][2]
+ *                                             (bit-identical to the flat [M][K]) */
+enum {
+  XSMM_GEMM_FLAG_NONE = 0,
+  XSMM_GEMM_FLAG_BETA_0 = 4,
+  XSMM_GEMM_FLAG_NO_RESET_TILECONFIG = 64,
+  XSMM_GEMM_FLAG_NO_SETUP_TILECONFIG = 128,
+  XSMM_GEMM_FLAG_ROWMAJOR_B_VNNI = 2048,
+  XSMM_GEMM_FLAG_ROWMAJOR_A_VNNI = 4096,
+  XSMM_GEMM_FLAG_VNNI_C = 8192
+};
+
+/* ---- dispatch: build (or look up) a kernel descriptor, return it as i64 ---- */
+
+/* replaces runtime/Xsmm/XsmmRunnerUtils.h:22-24 (XsmmRunnerUtils.cpp:95-140) */
+TPP_XSMM_EXPORT int64_t xsmm_gemm_dispatch(int64_t dtype, int64_t m, int64_t n,
+                                           int64_t k, int64_t lda, int64_t ldb,
+                                           int64_t ldc, int64_t flags);
+
+/* replaces XsmmRunnerUtils.h:26-28 (XsmmRunnerUtils.cpp:142-179) */
+TPP_XSMM_EXPORT int64_t xsmm_unary_dispatch(int64_t kind, int64_t dtype,
+                                            int64_t m, int64_t n, int64_t ldi,
+                                            int64_t ldo, int64_t flags);
+
+/* replaces XsmmRunnerUtils.h:30-32 (XsmmRunnerUtils.cpp:181-211) */
+TPP_XSMM_EXPORT int64_t xsmm_binary_dispatch(int64_t kind, int64_t dtype,
+                                             int64_t m, int64_t n,
+                                             int64_t ldiLhs, int64_t ldiRhs,
+                                             int64_t ldo, int64_t flags);
+
+/* replaces XsmmRunnerUtils.h:34-36 (XsmmRunnerUtils.cpp:308-361) */
+TPP_XSMM_EXPORT int64_t xsmm_brgemm_dispatch(int64_t dtype, int64_t m,
+                                             int64_t n, int64_t k, int64_t lda,
+                                             int64_t ldb, int64_t ldc,
+                                             int64_t stride_a, int64_t stride_b,
+                                             int64_t flags);
+
+/* replaces XsmmRunnerUtils.h:38-45 (XsmmRunnerUtils.cpp:385-457) */
+TPP_XSMM_EXPORT int64_t xsmm_fused_brgemm_dispatch(
+    int64_t dtype, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+    int64_t ldc, int64_t stride_a, int64_t stride_b, int64_t gemm_flags,
+    int64_t unary_flags, int64_t unary_kind, int64_t binary_flags,
+    int64_t binary_kind);
+
+/* replaces XsmmRunnerUtils.h:47-49 (XsmmRunnerUtils.cpp:213-246): AMX tile
+ * configuration has no meaning on a GPU; returns a non-zero dummy handle. */
+TPP_XSMM_EXPORT int64_t xsmm_intel_amx_tile_config_dispatch(
+    int64_t dtype, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+    int64_t ldc, int64_t stride_a, int64_t stride_b, int64_t flags);
+
+/* ---- invoke ---------------------------------------------------------------- */
+
+/* replaces XsmmRunnerUtils.h:51-54 (XsmmRunnerUtils.cpp:79-93) */
+TPP_XSMM_EXPORT void xsmm_gemm_invoke(int64_t dtype, int64_t addr,
+                                      void *alignedPtrA, int64_t offsetA,
+                                      void *alignedPtrB, int64_t offsetB,
+                                      void *alignedPtrC, int64_t offsetC);
+
+/* replaces XsmmRunnerUtils.h:56-59 (XsmmRunnerUtils.cpp:248-259) */
+TPP_XSMM_EXPORT void xsmm_unary_invoke(int64_t dtype, int64_t addr,
+                                       void *alignedPtrIn, int64_t offsetIn,
+                                       void *alignedPtrOut, int64_t offsetOut);
+
+/* replaces XsmmRunnerUtils.h:61-63 (XsmmRunnerUtils.cpp:276-286) */
+TPP_XSMM_EXPORT void xsmm_unary_scalar_invoke(int64_t dtype, int64_t addr,
+                                              float scalar, void *alignedPtrOut,
+                                              int64_t offsetOut);
+
+/* replaces XsmmRunnerUtils.h:65-68 (XsmmRunnerUtils.cpp:261-274) */
+TPP_XSMM_EXPORT void xsmm_binary_invoke(int64_t dtype, int64_t addr,
+                                        void *alignedPtrLhs, int64_t offsetLhs,
+                                        void *alignedPtrRhs, int64_t offsetRhs,
+                                        void *alignedPtrOut, int64_t offsetOut);
+
+/* replaces XsmmRunnerUtils.h:70-74 (XsmmRunnerUtils.cpp:288-306) */
+TPP_XSMM_EXPORT void xsmm_brgemm_invoke(int64_t dtype, int64_t addr,
+                                        void *alignedPtrA, int64_t offsetA,
+                                        void *alignedPtrB, int64_t offsetB,
+                                        void *alignedPtrC, int64_t offsetC,
+                                        int64_t numBatches);
+
+/* replaces XsmmRunnerUtils.h:76-79 (XsmmRunnerUtils.cpp:363-383) */
+TPP_XSMM_EXPORT void xsmm_fused_brgemm_invoke(
+    int64_t dtype, int64_t addr, void *alignedPtrA, int64_t offsetA,
+    void *alignedPtrB, int64_t offsetB, void *alignedPtrC, int64_t offsetC,
+    void *alignedPtrD, int64_t offsetD, int64_t numBatches);
+
+/* replaces XsmmRunnerUtils.h:81-83 (XsmmRunnerUtils.cpp:459-469): no-op. */
+TPP_XSMM_EXPORT void xsmm_intel_amx_tile_config_invoke(int64_t dtype,
+                                                       int64_t addr,
+                                                       void *alignedPtrA,
+                                                       int64_t offset);
+
+/* ---- perf timers (runtime/PerfRunnerUtils.h:22-24, .cpp:23-35) -------------
+ * Same wall-clock semantics; perf_stop_timer first drains every stream this
+ * library launched on, because the timed region is a host loop of asynchronous
+ * invokes (lib/TPP/Conversion/ConvertPerfToLoops/ConvertPerfToLoops.cpp:47-52). */
+TPP_XSMM_EXPORT int64_t perf_start_timer(void);
+TPP_XSMM_EXPORT double perf_stop_timer(int64_t startTimestamp);
+
+/* The one libxsmm symbol the COMPILER links (VNNIUtils.cpp:36): VNNI blocking
+ * factor for a datatype. Returns 2 for bf16 (the VNNI-2 layout is supported by
+ * the BRGEMM kernels) unless TPP_XSMM_VNNI=0 is set in the environment, which
+ * makes the compiler keep flat [K][N] weights (the TMA-native layout). */
+TPP_XSMM_EXPORT int libxsmm_cpuid_dot_pack_factor(int datatype);
+
+/* ---- CUDA-side extensions (new; the reference has no equivalent) ------------
+ * They play the role of the reference GPU path's gpu.alloc/gpu.memcpy argument
+ * offload (lib/TPP/Runner/MLIRBench.cpp:176-205): residency is explicit. */
+
+/* Use this CUDA stream (a cudaStream_t / CUstream as void*) for all subsequent
+ * invokes issued by the calling thread. NULL selects the per-thread default
+ * stream of the library. */
+TPP_XSMM_EXPORT void xsmm_cuda_set_stream(void *stream);
+TPP_XSMM_EXPORT void *xsmm_cuda_get_stream(void);
+
+/* Block until every invoke issued so far (all threads) has completed. */
+TPP_XSMM_EXPORT void xsmm_cuda_sync(void);
+
+/* Register a host range: pins it and creates a device mirror of the same size.
+ * Invokes whose operands lie inside a registered range run on the mirror with no
+ * implicit copies. upload!=0 copies host->mirror now. Returns 0 on success. */
+TPP_XSMM_EXPORT int64_t xsmm_cuda_register_host(void *host, int64_t bytes,
+                                                int64_t upload);
+TPP_XSMM_EXPORT int64_t xsmm_cuda_unregister_host(void *host);
+/* Asynchronous (stream-ordered) host->mirror / mirror->host copies of a
+ * sub-range of a registered range. */
+TPP_XSMM_EXPORT int64_t xsmm_cuda_update_device(void *host, int64_t bytes);
+TPP_XSMM_EXPORT int64_t xsmm_cuda_update_host(void *host, int64_t bytes);
+/* Device address that mirrors a registered host address (NULL if none). */
+TPP_XSMM_EXPORT void *xsmm_cuda_device_ptr(void *host);
+
+/* Introspection used by the tests and by bench.py's "gpu_launches". */
+TPP_XSMM_EXPORT int64_t xsmm_cuda_launch_count(void);
+/* Name of the kernel variant the last invoke on this thread launched
+ * (e.g. "brgemm_tc_bf16_128x128x64"); points to static storage. */
+TPP_XSMM_EXPORT const char *xsmm_cuda_last_kernel(void);
+/* Name of the kernel variant a dispatch handle resolved to. */
+TPP_XSMM_EXPORT const char *xsmm_cuda_handle_kernel(int64_t addr);
+/* ABI version of this header. */
+TPP_XSMM_EXPORT int64_t xsmm_cuda_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* TPP_XSMM_ABI_H */

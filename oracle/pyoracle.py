@@ -1,0 +1,154 @@
+"""ctypes binding of oracle/_build/libxsmm_oracle.so (TEST INFRASTRUCTURE).
+
+Argument names and order mirror the C-ABI of the product (include/tpp_xsmm_abi.h)
+so the parity tests read ``oracle.brgemm(...)`` next to ``xsmm.brgemm(...)``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from ctypes import c_int, c_int64, c_void_p
+
+import numpy as np
+
+F32 = 1
+BF16 = 2
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_lib = None
+_lib_dir = None
+
+
+def build(native: bool = False, force: bool = False) -> str:
+    """Compile the oracle with the Makefile next to this file; returns the .so path.
+
+    native=True builds with -march=native into oracle/_build_native (used by
+    bench.py for the CPU arm on the box it is timed on); the default x86-64-v3
+    build is the one that travels.
+    """
+    out = "_build_native" if native else "_build"
+    so = os.path.join(_HERE, out, "libxsmm_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("xsmm_oracle.c", "xsmm_oracle.h", "tensor_init.cpp", "Makefile")]
+    stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
+    if stale:
+        cmd = ["make", "-C", _HERE, f"OUT={out}"]
+        if native:
+            cmd.append("ARCH=native")
+        subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib(native: bool = False):
+    global _lib, _lib_dir
+    want = "_build_native" if native else "_build"
+    if _lib is not None and _lib_dir == want:
+        return _lib
+    L = ctypes.CDLL(build(native=native))
+    i64 = c_int64
+    L.xo_brgemm.argtypes = [i64] * 10 + [c_void_p, c_void_p, c_void_p, i64]
+    L.xo_brgemm.restype = None
+    L.xo_gemm.argtypes = [i64] * 8 + [c_void_p, c_void_p, c_void_p]
+    L.xo_gemm.restype = None
+    L.xo_fused_brgemm.argtypes = [i64] * 14 + [c_void_p] * 4 + [i64]
+    L.xo_fused_brgemm.restype = None
+    L.xo_unary.argtypes = [i64] * 7 + [c_void_p, c_void_p]
+    L.xo_unary.restype = c_int
+    L.xo_binary.argtypes = [i64] * 8 + [c_void_p, c_void_p, c_void_p]
+    L.xo_binary.restype = c_int
+    L.xo_f32_to_bf16_array.argtypes = [c_void_p, c_void_p, i64]
+    L.xo_f32_to_bf16_array.restype = None
+    L.xo_bf16_to_f32_array.argtypes = [c_void_p, c_void_p, i64]
+    L.xo_bf16_to_f32_array.restype = None
+    L.xo_set_acc_mode.argtypes = [c_int]
+    L.xo_set_num_threads.argtypes = [c_int]
+    L.xo_num_threads.restype = c_int
+    L.ti_create.argtypes = [c_int, c_int, c_int]
+    L.ti_create.restype = c_void_p
+    L.ti_destroy.argtypes = [c_void_p]
+    L.ti_fill.argtypes = [c_void_p, i64, c_void_p]
+    L.ti_fill.restype = None
+    _lib, _lib_dir = L, want
+    return L
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(c_void_p)
+
+
+def np_dtype(dtype: int):
+    return np.float32 if dtype == F32 else np.uint16
+
+
+def f32_to_bf16(a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    out = np.empty(a.shape, dtype=np.uint16)
+    lib().xo_f32_to_bf16_array(_p(a), _p(out), a.size)
+    return out
+
+
+def bf16_to_f32(a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.uint16)
+    out = np.empty(a.shape, dtype=np.float32)
+    lib().xo_bf16_to_f32_array(_p(a), _p(out), a.size)
+    return out
+
+
+def set_acc_mode(mode: int) -> None:
+    lib().xo_set_acc_mode(mode)
+
+
+def set_num_threads(n: int) -> None:
+    lib().xo_set_num_threads(n)
+
+
+def num_threads() -> int:
+    return lib().xo_num_threads()
+
+
+def brgemm(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, flags, A, B, C, batch):
+    lib().xo_brgemm(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, flags, _p(A), _p(B), _p(C), batch)
+
+
+def gemm(dtype, m, n, k, lda, ldb, ldc, flags, A, B, C):
+    lib().xo_gemm(dtype, m, n, k, lda, ldb, ldc, flags, _p(A), _p(B), _p(C))
+
+
+def fused_brgemm(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, gemm_flags, unary_flags, unary_kind,
+                 binary_flags, binary_kind, A, B, C, D, batch):
+    lib().xo_fused_brgemm(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, gemm_flags, unary_flags, unary_kind,
+                          binary_flags, binary_kind, _p(A), _p(B), _p(C), _p(D), batch)
+
+
+def unary(kind, dtype, m, n, ldi, ldo, flags, inp, out):
+    rc = lib().xo_unary(kind, dtype, m, n, ldi, ldo, flags, _p(inp), _p(out))
+    if rc != 0:
+        raise ValueError(f"oracle: unsupported unary kind={kind} dtype={dtype} m={m}")
+
+
+def binary(kind, dtype, m, n, ldl, ldr, ldo, flags, lhs, rhs, out):
+    rc = lib().xo_binary(kind, dtype, m, n, ldl, ldr, ldo, flags, _p(lhs), _p(rhs), _p(out))
+    if rc != 0:
+        raise ValueError(f"oracle: unsupported binary kind={kind}")
+
+
+class TensorInit:
+    """One generator per (type, dtype, seed), filled sequentially, like
+    getTensorInit() (lib/TPP/Transforms/Utils/TensorInit.cpp:75-144)."""
+
+    TYPES = {"const": 0, "simple": 1, "cont": 2, "random": 3, "normal": 4}
+
+    def __init__(self, kind: str, dtype: int, seed: int = 0):
+        self.dtype = dtype
+        self._h = lib().ti_create(self.TYPES[kind], dtype, seed)
+
+    def fill(self, *shape) -> np.ndarray:
+        out = np.empty(shape, dtype=np_dtype(self.dtype))
+        lib().ti_fill(self._h, out.size, _p(out))
+        return out
+
+    def __del__(self):
+        try:
+            lib().ti_destroy(self._h)
+        except Exception:
+            pass
