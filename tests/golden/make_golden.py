@@ -1,0 +1,172 @@
+#!/usr/bin/env python
+"""Extract the known-answer vectors of the reference's own tests into a fixture.
+
+Run in the build container (needs /root/reference, which does not exist on the
+GPU box):
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/reference_vectors.json. Every number in that file is copied
+out of a reference test file (dense<> constants and FileCheck CHECK/RESULT lines);
+nothing is computed here. The dispatch arguments that go with each vector are
+written in tests/golden_cases.py next to the reference file:line they come from.
+"""
+from __future__ import annotations
+
+import json
+import os
+import re
+import sys
+
+REF = os.environ.get("TPP_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_vectors.json")
+
+NUM = r"[-+]?(?:\d+\.\d*|\.\d+|\d+)(?:[eE][-+]?\d+)?"
+
+
+def read(rel):
+    with open(os.path.join(REF, rel)) as f:
+        return f.read()
+
+
+def nums(s):
+    return [float(x) for x in re.findall(NUM, s)]
+
+
+def dense_blocks(text):
+    """All `dense<[ ... ]>` literals of a file, in order, as flat float lists."""
+    out = []
+    i = 0
+    while True:
+        i = text.find("dense<[", i)
+        if i < 0:
+            break
+        depth = 0
+        j = i + len("dense<")
+        start = j
+        while True:
+            c = text[j]
+            if c == "[":
+                depth += 1
+            elif c == "]":
+                depth -= 1
+                if depth == 0:
+                    break
+            j += 1
+        out.append(nums(text[start:j + 1]))
+        i = j
+    return out
+
+
+def check_lines(text, prefix="CHECK"):
+    """Numbers of every `// PREFIX[-SAME|-COUNT-n]: ...` line, one list per line, with the
+    repeat count of CHECK-COUNT-n."""
+    rows = []
+    for line in text.splitlines():
+        m = re.match(r"\s*//\s*" + prefix + r"(-SAME|-COUNT-(\d+))?:\s*(.*)$", line)
+        if not m:
+            continue
+        body = m.group(3)
+        if "(" not in body:
+            continue
+        vals = nums(body)
+        rep = int(m.group(2)) if m.group(2) else 1
+        rows.append({"values": vals, "repeat": rep})
+    return rows
+
+
+def flat_checks(text, prefix="CHECK"):
+    out = []
+    for r in check_lines(text, prefix):
+        out.extend(r["values"] * r["repeat"])
+    return out
+
+
+def main():
+    g = {}
+
+    def add(name, src, **kw):
+        kw["source"] = src
+        g[name] = kw
+
+    t = read("test/Integration/xsmm-brgemm.mlir")
+    add("brgemm_f32_ones", "test/Integration/xsmm-brgemm.mlir:8-20", expected=flat_checks(t))
+
+    t = read("test/BF16/Integration/xsmm-brgemm-bf16.mlir")
+    add("brgemm_bf16_vnni", "test/BF16/Integration/xsmm-brgemm-bf16.mlir:5-20", expected=flat_checks(t))
+
+    t = read("test/BF16/Integration/xsmm-ternary-bf16.mlir")
+    add("brgemm_bf16_vnni_batch64", "test/BF16/Integration/xsmm-ternary-bf16.mlir:5-19", expected=flat_checks(t))
+
+    t = read("test/BF16/Integration/xsmm-gemm-bf16.mlir")
+    add("gemm_bf16_vnni", "test/BF16/Integration/xsmm-gemm-bf16.mlir:5-17", expected=flat_checks(t))
+
+    for name, rel in (("fused_f32", "test/Integration/xsmm-quarternary.mlir"),
+                      ("fused_bf16_vnni", "test/BF16/Integration/xsmm-quarternary-bf16.mlir")):
+        t = read(rel)
+        m = re.search(r"%outVal = arith.constant (" + NUM + ")", t)
+        thr = re.search(r"%threshold = arith.constant (" + NUM + ")", t)
+        add(name, rel + ":4-16", expected_fill=float(m.group(1)), threshold=float(thr.group(1)))
+
+    t = read("test/Integration/xsmm-fusion.mlir")
+    add("fused_f32_seed123", "test/Integration/xsmm-fusion.mlir:5-57", expected=flat_checks(t, "RESULT"))
+
+    t = read("test/Integration/xsmm-transpose.mlir")
+    add("transpose_f32", "test/Integration/xsmm-transpose.mlir:5-41", input=dense_blocks(t)[0], expected=flat_checks(t))
+
+    t = read("test/Integration/transpose-bf16.mlir")
+    add("vnni2_bf16_seed123", "test/Integration/transpose-bf16.mlir:1-35", expected=flat_checks(t))
+
+    t = read("test/BF16/Integration/vnni-packing.mlir")
+    add("vnni2_pack_16x16", "test/BF16/Integration/vnni-packing.mlir:5-41", input=dense_blocks(t)[0],
+        expected_prefix=flat_checks(t))
+
+    t = read("test/BF16/Integration/vnni-packing-chain.mlir")
+    d = dense_blocks(t)
+    add("vnni2_pack_chain", "test/BF16/Integration/vnni-packing-chain.mlir:7-66", input=d[0], expected=d[1])
+
+    t = read("test/Integration/xsmm-unary.mlir")
+    add("unary_relu_f32", "test/Integration/xsmm-unary.mlir:5-13", expected=flat_checks(t))
+    t = read("test/BF16/Integration/xsmm-unary-bf16.mlir")
+    add("unary_relu_bf16", "test/BF16/Integration/xsmm-unary-bf16.mlir", expected=flat_checks(t))
+    t = read("test/Integration/xsmm-zero.mlir")
+    add("unary_zero_f32", "test/Integration/xsmm-zero.mlir:5-15", expected=flat_checks(t))
+    t = read("test/BF16/Integration/xsmm-zero-bf16.mlir")
+    add("unary_zero_bf16", "test/BF16/Integration/xsmm-zero-bf16.mlir", expected=flat_checks(t))
+    t = read("test/Integration/xsmm-binary.mlir")
+    add("binary_add_f32", "test/Integration/xsmm-binary.mlir:5-17", expected=flat_checks(t))
+    t = read("test/BF16/Integration/xsmm-binary-bf16.mlir")
+    add("binary_add_bf16", "test/BF16/Integration/xsmm-binary-bf16.mlir", expected=flat_checks(t))
+
+    for op in ("mul", "sub"):
+        t = read(f"test/Integration/xsmm-{op}.mlir")
+        add(f"binary_{op}_f32", f"test/Integration/xsmm-{op}.mlir", input=dense_blocks(t)[0], expected=flat_checks(t))
+    t = read("test/Integration/xsmm-div.mlir")
+    d = dense_blocks(t)
+    add("binary_div_f32", "test/Integration/xsmm-div.mlir", lhs=d[0], rhs_full=d[1], rhs_col=d[2], rhs_row=d[3],
+        rhs_scalar=d[4], expected_all=flat_checks(t))
+
+    t = read("test/Integration/xsmm-strided-brgemm.mlir")
+    d = dense_blocks(t)
+    add("strided_brgemm", "test/Integration/xsmm-strided-brgemm.mlir:17-109", D=d[0], A=d[1], B=d[2],
+        expected=flat_checks(t))
+    t = read("test/Integration/xsmm-strided-brgemm1.mlir")
+    d = dense_blocks(t)
+    add("strided_gemm1", "test/Integration/xsmm-strided-brgemm1.mlir:15-100", A=d[0], B=d[1], expected=flat_checks(t))
+
+    t = read("test/BF16/Integration/mlp-all-bf16-tpprun.mlir")
+    m = re.search(r"%c4 = arith.constant (" + NUM + ")", t)
+    thr = re.search(r"%threshold = arith.constant (" + NUM + ")", t)
+    add("mlp_all_ones_bf16", "test/BF16/Integration/mlp-all-bf16-tpprun.mlir:4-135", expected_fill=float(m.group(1)),
+        threshold=float(thr.group(1)), batch=128, layers=[256, 512, 1024, 2048, 1000])
+
+    t = read("test/Integration/matmul_64x64x64.mlir")
+    add("matmul_64x64x64_f32", "test/Integration/matmul_64x64x64.mlir:1-16", raw_checks=check_lines(t))
+
+    with open(OUT, "w") as f:
+        json.dump(g, f, indent=1, sort_keys=True)
+    print(f"wrote {OUT}: {len(g)} vectors, {os.path.getsize(OUT)} bytes")
+
+
+if __name__ == "__main__":
+    sys.exit(main())

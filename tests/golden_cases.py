@@ -1,0 +1,269 @@
+"""The reference's known-answer tests, replayed op by op on a backend.
+
+Each case issues the xsmm calls its reference test contains (dispatch arguments
+are copied from the cited .mlir, inputs/expected numbers come from
+tests/golden/reference_vectors.json, which tests/golden/make_golden.py extracted
+from those same files) and returns (result, expected, abs_tol). The same cases
+pin the oracle (tests/test_oracle_golden.py, CPU) and the CUDA path
+(tests/test_parity_gpu.py, through the C-ABI).
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+
+import oracle
+
+F32, BF16 = 1, 2
+_G = None
+
+
+def golden():
+    global _G
+    if _G is None:
+        with open(os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")) as f:
+            _G = json.load(f)
+    return _G
+
+
+def const(dtype, shape, value=1.0):
+    """tpp-run's default input init without --seed: dense<1.0> (TensorInit.cpp:77-82)."""
+    a = np.full(shape, value, dtype=np.float32)
+    return a if dtype == F32 else oracle.f32_to_bf16(a)
+
+
+def to_f32(dtype, a):
+    return a.astype(np.float32) if dtype == F32 else oracle.bf16_to_f32(a)
+
+
+def from_f32(dtype, a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a if dtype == F32 else oracle.f32_to_bf16(a)
+
+
+# ---- cases -----------------------------------------------------------------------
+
+def case_brgemm_f32_ones(be):
+    # test/Integration/xsmm-brgemm.mlir:13: dispatch [32,64,16,16,64,64,512,1024] flags none, batch 2
+    A, B, C = const(F32, (2, 32, 16)), const(F32, (2, 16, 64)), const(F32, (64 * 32,))
+    be.brgemm(F32, 32, 64, 16, 16, 64, 64, 512, 1024, 0, A, 0, B, 0, C, 0, 2)
+    return C, np.array(golden()["brgemm_f32_ones"]["expected"], np.float32), 0.0
+
+
+def case_brgemm_bf16_vnni(be):
+    # test/BF16/Integration/xsmm-brgemm-bf16.mlir:12: [6,6,6,6,6,6,36,36] flags (vnni_b) -> 2048 at the ABI
+    A, B, C = const(BF16, (2, 6, 6)), const(BF16, (2, 3, 6, 2), 3.0), const(BF16, (36,))
+    be.brgemm(BF16, 6, 6, 6, 6, 6, 6, 36, 36, 2048, A, 0, B, 0, C, 0, 2)
+    return to_f32(BF16, C), np.array(golden()["brgemm_bf16_vnni"]["expected"], np.float32), 0.0
+
+
+def case_brgemm_bf16_vnni_batch64(be):
+    # test/BF16/Integration/xsmm-ternary-bf16.mlir:8: [4,4,4,4,4,4,8,8] (vnni_b), batch 64; 257 rounds to 256
+    A, B, C = const(BF16, (64, 4, 4)), const(BF16, (64, 2, 4, 2)), const(BF16, (16,))
+    be.brgemm(BF16, 4, 4, 4, 4, 4, 4, 8, 8, 2048, A, 0, B, 0, C, 0, 64)
+    return to_f32(BF16, C), np.array(golden()["brgemm_bf16_vnni_batch64"]["expected"], np.float32), 0.0
+
+
+def case_gemm_bf16_vnni(be):
+    # test/BF16/Integration/xsmm-gemm-bf16.mlir:10: gemm [6,6,6,6,6,6] (vnni_b)
+    A, B, C = const(BF16, (6, 6)), const(BF16, (3, 6, 2), 3.0), const(BF16, (36,))
+    be.gemm(BF16, 6, 6, 6, 6, 6, 6, 2048, A, 0, B, 0, C, 0)
+    return to_f32(BF16, C), np.array(golden()["gemm_bf16_vnni"]["expected"], np.float32), 0.0
+
+
+def _case_fused(be, dtype, gflags, key):
+    # test/Integration/xsmm-quarternary.mlir:6-9 / BF16 twin: [4,4,4,4,4,4,8,8][add,relu],
+    # binary_flags (bcast_col_in0), batch 16, C accumulated (no beta_0): 16*4 + 1 + 1 = 66
+    A = const(dtype, (64, 4, 4))
+    B = const(dtype, (64, 4, 4)) if dtype == F32 else const(dtype, (64, 2, 4, 2))
+    C, D = const(dtype, (16,)), const(dtype, (4,))
+    be.fused_brgemm(dtype, 4, 4, 4, 4, 4, 4, 8, 8, gflags, 0, 5, 4, 1, A, 0, B, 0, C, 0, D, 0, 16)
+    g = golden()[key]
+    return to_f32(dtype, C), np.full(16, g["expected_fill"], np.float32), g["threshold"]
+
+
+def case_fused_f32(be):
+    return _case_fused(be, F32, 0, "fused_f32")
+
+
+def case_fused_bf16_vnni(be):
+    return _case_fused(be, BF16, 2048, "fused_bf16_vnni")
+
+
+def case_fused_f32_seed123(be):
+    # test/Integration/xsmm-fusion.mlir:51: dispatch (1,4,4,8,8,4,4,32,32,4,0,5,4,1), batch 2, --seed 123:
+    # kernel args are filled in order (A 2x4x8, bias 1x4) from one normal generator; B is dense<2.0>
+    gen = oracle.TensorInit("normal", F32, 123)
+    A, bias = gen.fill(2, 4, 8), gen.fill(1, 4)
+    B, C = const(F32, (2, 8, 4), 2.0), np.zeros(16, np.float32)
+    be.fused_brgemm(F32, 4, 4, 8, 8, 4, 4, 32, 32, 4, 0, 5, 4, 1, A, 0, B, 0, C, 0, bias, 0, 2)
+    return C, np.array(golden()["fused_f32_seed123"]["expected"], np.float32), 6e-6  # 6 printed digits
+
+
+def case_transpose_f32(be):
+    # test/Integration/xsmm-transpose.mlir:6: transpose [4,8,8,4]
+    g = golden()["transpose_f32"]
+    inp, out = np.array(g["input"], np.float32), np.zeros(32, np.float32)
+    be.unary(29, F32, 4, 8, 8, 4, 0, inp, 0, out, 0)
+    return out, np.array(g["expected"], np.float32), 1e-6
+
+
+def case_vnni2_bf16_seed123(be):
+    # test/Integration/transpose-bf16.mlir:10-18 (--seed 123): 4x4 bf16 -> [2][4][2] == vnni_2 [4,4,4,4]
+    gen = oracle.TensorInit("normal", BF16, 123)
+    inp = gen.fill(4, 4)
+    out = np.zeros(16, np.uint16)
+    be.unary(28, BF16, 4, 4, 4, 4, 0, inp, 0, out, 0)
+    return to_f32(BF16, out), np.array(golden()["vnni2_bf16_seed123"]["expected"], np.float32), 1e-6
+
+
+def case_vnni2_pack_16x16(be):
+    # test/BF16/Integration/vnni-packing.mlir:5-8: 16x16 -> 8x16x2, i.e. vnni_2 [16,16,16,16]
+    g = golden()["vnni2_pack_16x16"]
+    inp, out = from_f32(BF16, np.array(g["input"])), np.zeros(256, np.uint16)
+    be.unary(28, BF16, 16, 16, 16, 16, 0, inp, 0, out, 0)
+    pref = np.array(g["expected_prefix"], np.float32)
+    return to_f32(BF16, out)[:pref.size], pref, 0.0
+
+
+def case_vnni2_pack_chain(be):
+    # test/BF16/Integration/vnni-packing-chain.mlir:7-15: 32x32 -> blocks [2][2][16][16] with
+    # outer_dims_perm=[1,0] (a relayout, done here in numpy) -> per block vnni_2 [16,16,16,16]
+    g = golden()["vnni2_pack_chain"]
+    x = np.array(g["input"], np.float32).reshape(32, 32)
+    blocks = x.reshape(2, 16, 2, 16).transpose(2, 0, 1, 3)  # [jb][ib][16][16]
+    inp = from_f32(BF16, np.ascontiguousarray(blocks))
+    out = np.zeros(1024, np.uint16)
+    for blk in range(4):
+        be.unary(28, BF16, 16, 16, 16, 16, 0, inp, blk * 256, out, blk * 256)
+    return to_f32(BF16, out), np.array(g["expected"], np.float32), 0.0
+
+
+def _case_unary(be, dtype, kind, key, fill):
+    # test/Integration/xsmm-unary.mlir:5 relu [3,3,3,3] in place; xsmm-zero.mlir:8 zero [3,3,3,3] on a 5.0 buffer
+    x = const(dtype, (9,), fill)
+    be.unary(kind, dtype, 3, 3, 3, 3, 0, x, 0, x, 0)
+    return to_f32(dtype, x), np.array(golden()[key]["expected"], np.float32), 0.0
+
+
+def case_unary_relu_f32(be):
+    return _case_unary(be, F32, 5, "unary_relu_f32", 1.0)
+
+
+def case_unary_relu_bf16(be):
+    return _case_unary(be, BF16, 5, "unary_relu_bf16", 1.0)
+
+
+def case_unary_zero_f32(be):
+    return _case_unary(be, F32, 2, "unary_zero_f32", 5.0)
+
+
+def case_unary_zero_bf16(be):
+    return _case_unary(be, BF16, 2, "unary_zero_bf16", 5.0)
+
+
+def _case_add(be, dtype, key):
+    # test/Integration/xsmm-binary.mlir:9: add [3,3,3,3,3]
+    a, b, o = const(dtype, (9,)), const(dtype, (9,)), const(dtype, (9,))
+    be.binary(1, dtype, 3, 3, 3, 3, 3, 0, a, 0, b, 0, o, 0)
+    return to_f32(dtype, o), np.array(golden()[key]["expected"], np.float32), 0.0
+
+
+def case_binary_add_f32(be):
+    return _case_add(be, F32, "binary_add_f32")
+
+
+def case_binary_add_bf16(be):
+    return _case_add(be, BF16, "binary_add_bf16")
+
+
+def _case_mulsub(be, kind, key):
+    # test/Integration/xsmm-mul.mlir:6 / xsmm-sub.mlir:6: [4,8,8,8,8], both operands the same constant
+    g = golden()[key]
+    x, o = np.array(g["input"], np.float32), np.zeros(32, np.float32)
+    be.binary(kind, F32, 4, 8, 8, 8, 8, 0, x, 0, x.copy(), 0, o, 0)
+    return o, np.array(g["expected"], np.float32), 1e-5 * 70  # printed with 4-6 significant digits
+
+
+def case_binary_mul_f32(be):
+    return _case_mulsub(be, 2, "binary_mul_f32")
+
+
+def case_binary_sub_f32(be):
+    return _case_mulsub(be, 3, "binary_sub_f32")
+
+
+def case_binary_div_f32(be):
+    # test/Integration/xsmm-div.mlir:6-28: div [4,8,8,8,8] none / (bcast_col_in1) / [4,8,8,1,8] (bcast_row_in1)
+    # / [4,8,8,1,8] (bcast_scalar_in1)
+    g = golden()["binary_div_f32"]
+    lhs = np.array(g["lhs"], np.float32)
+    outs = []
+    for ldr, flags, key in ((8, 0, "rhs_full"), (8, 8, "rhs_col"), (1, 2, "rhs_row"), (1, 32, "rhs_scalar")):
+        rhs, o = np.array(g[key], np.float32), np.zeros(32, np.float32)
+        be.binary(4, F32, 4, 8, 8, ldr, 8, flags, lhs, 0, rhs, 0, o, 0)
+        outs.append(o)
+    return np.concatenate(outs), np.array(g["expected_all"], np.float32), 0.0
+
+
+def case_strided_brgemm(be):
+    # test/Integration/xsmm-strided-brgemm.mlir:34: xsmm_brgemm_dispatch(1,2,2,4,8,16,2,4,64,0):
+    # C_exp[i][ii][j][jj] += sum_{k,kk} A_exp[i][ii][k][kk] * B_exp[k][kk][j][jj]; one invoke per (i,j)
+    # on a 2x2 tile (ldc=2) that starts at zero, then + D (the linalg.generic add)
+    g = golden()["strided_brgemm"]
+    A, B, D = (np.array(g[x], np.float32) for x in ("A", "B", "D"))
+    res = np.zeros((4, 16), np.float32)
+    for i in range(2):
+        for j in range(8):
+            tile = np.zeros(4, np.float32)
+            be.brgemm(F32, 2, 2, 4, 8, 16, 2, 4, 64, 0, A, i * 16, B, j * 2, tile, 0, 2)
+            res[i * 2:(i + 1) * 2, j * 2:(j + 1) * 2] = tile.reshape(2, 2)
+    res += D.reshape(4, 16)
+    return res.reshape(-1), np.array(g["expected"], np.float32), 5e-3  # printed with 2 decimals
+
+
+def case_strided_gemm1(be):
+    # test/Integration/xsmm-strided-brgemm1.mlir:33: xsmm_gemm_dispatch(1,2,2,4,4,16,16,4) (beta_0 folded in):
+    # C[b][i][h][j] = sum_k A[b][h][i][k] * B[b][k][h][j]; one gemm per (b,h) writing a strided 2x2 of C(4x16)
+    g = golden()["strided_gemm1"]
+    A, B = np.array(g["A"], np.float32), np.array(g["B"], np.float32)
+    C = np.zeros(64, np.float32)
+    for b in range(2):
+        for h in range(8):
+            be.gemm(F32, 2, 2, 4, 4, 16, 16, 4, A, (b * 8 + h) * 8, B, b * 64 + h * 2, C, b * 32 + h * 2)
+    return C, np.array(g["expected"], np.float32), 5e-3 * 10
+
+
+def case_matmul_64x64x64_f32(be):
+    # test/Integration/matmul_64x64x64.mlir:11,16 (cfg1): default 32x32x32 packing -> per output block one
+    # xsmm_brgemm_dispatch(1,32,32,32,32,32,32,1024,1024,0) invoke with 2 batches, C initialised to 1 => 65
+    A = const(F32, (2, 2, 32, 32))   # [M/32][K/32][32][32]
+    B = const(F32, (2, 2, 32, 32))   # [N/32][K/32][32][32]
+    C = const(F32, (2, 2, 32, 32))   # [M/32][N/32][32][32]
+    for im in range(2):
+        for jn in range(2):
+            be.brgemm(F32, 32, 32, 32, 32, 32, 32, 1024, 1024, 0, A, im * 2048, B, jn * 2048, C, (im * 2 + jn) * 1024, 2)
+    row = golden()["matmul_64x64x64_f32"]["raw_checks"][0]
+    return C.reshape(-1), np.full(4096, row["values"][0], np.float32), 0.0
+
+
+def case_mlp_all_ones_bf16(be):
+    # test/BF16/Integration/mlp-all-bf16-tpprun.mlir: batch 128, 256->512->1024->2048->1000, VNNI-2 weights,
+    # all inputs/weights/biases 1.0; relu(x*W + b) per layer => 2^38 (expected 2.74878e11, threshold 1.0 bf16)
+    g = golden()["mlp_all_ones_bf16"]
+    batch, layers = g["batch"], g["layers"]
+    x = const(BF16, (batch, layers[0]))
+    for c, k in zip(layers[:-1], layers[1:]):
+        W = const(BF16, (c // 2, k, 2))
+        bias = const(BF16, (k,))
+        y = np.zeros((batch, k), np.uint16)
+        # fused form of the layer (what CombineXsmmOpPass produces): beta_0 | vnni_b, add bcast_col_in0, relu
+        be.fused_brgemm(BF16, batch, k, c, c, k, k, 0, 0, 4 | 2048, 0, 5, 4, 1, x, 0, W, 0, y, 0, bias, 0, 1)
+        x = y
+    expect = to_f32(BF16, from_f32(BF16, np.full(x.size, g["expected_fill"], np.float32)))
+    return to_f32(BF16, x).reshape(-1), expect, g["threshold"]
+
+
+CASES = {name[len("case_"):]: fn for name, fn in sorted(globals().items()) if name.startswith("case_")}

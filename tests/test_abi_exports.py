@@ -1,0 +1,94 @@
+"""CPU-only: the drop-in library builds for sm_100a, loads, and exports every symbol that
+include/tpp_xsmm_abi.h declares (and the 13+2+1 names tpp-mlir binds). No compute calls."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+REFERENCE_SYMBOLS = [  # runtime/Xsmm/XsmmRunnerUtils.h:22-83, runtime/PerfRunnerUtils.h:22-24, VNNIUtils.cpp:36
+    "xsmm_gemm_dispatch", "xsmm_unary_dispatch", "xsmm_binary_dispatch", "xsmm_brgemm_dispatch",
+    "xsmm_fused_brgemm_dispatch", "xsmm_intel_amx_tile_config_dispatch", "xsmm_gemm_invoke", "xsmm_unary_invoke",
+    "xsmm_unary_scalar_invoke", "xsmm_binary_invoke", "xsmm_brgemm_invoke", "xsmm_fused_brgemm_invoke",
+    "xsmm_intel_amx_tile_config_invoke", "perf_start_timer", "perf_stop_timer", "libxsmm_cpuid_dot_pack_factor",
+]
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "tpp_xsmm_abi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"TPP_XSMM_EXPORT\s+[\w\s\*]+?\b(\w+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from tpp_mlir_b200 import _build
+
+    return ctypes.CDLL(_build.build())
+
+
+def test_header_declares_the_reference_abi():
+    decl = declared_symbols()
+    for s in REFERENCE_SYMBOLS:
+        assert s in decl, s
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for s in declared_symbols():
+        assert hasattr(lib, s), f"{s} declared in include/tpp_xsmm_abi.h but not exported"
+
+
+def test_python_binding_table_matches_header():
+    from tpp_mlir_b200 import xsmm
+
+    assert sorted(xsmm.EXPORTS) == declared_symbols()
+
+
+def test_no_cpu_symbols_or_oracle_linked(lib):
+    # the product must not carry the oracle (xo_*) or any host compute fallback
+    from tpp_mlir_b200 import _build
+
+    out = subprocess.run(["nm", "-D", "--defined-only", _build.lib_path()], capture_output=True, text=True).stdout
+    assert "xo_" not in out and "ti_fill" not in out
+
+
+def test_sass_has_blackwell_tensor_and_tma_instructions():
+    from tpp_mlir_b200 import _build
+
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not installed")
+    sass = subprocess.run([cuobjdump, "-sass", _build.lib_path()], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass      # tcgen05.mma
+    assert "LDTM" in sass         # tcgen05.ld
+    assert "UTMALDG" in sass      # cp.async.bulk.tensor
+    assert "HMMA.16816" not in sass  # no legacy mma.sync path
+
+
+def test_pack_factor_and_timers_work_without_gpu(lib):
+    lib.libxsmm_cpuid_dot_pack_factor.restype = ctypes.c_int
+    assert lib.libxsmm_cpuid_dot_pack_factor(2) == 2   # bf16 -> VNNI-2
+    assert lib.libxsmm_cpuid_dot_pack_factor(1) == 1
+    lib.perf_start_timer.restype = ctypes.c_int64
+    lib.perf_stop_timer.restype = ctypes.c_double
+    lib.perf_stop_timer.argtypes = [ctypes.c_int64]
+    t0 = lib.perf_start_timer()
+    assert 0.0 <= lib.perf_stop_timer(t0) < 5.0
+
+
+def test_dispatch_without_gpu_fails_loudly():
+    """No CPU fallback: on a box without a GPU the first dispatch must exit non-zero with a diagnostic."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("this box has a GPU")
+    code = ("from tpp_mlir_b200 import xsmm; "
+            "xsmm.brgemm_dispatch(2, 32, 32, 32, 32, 32, 32, 1024, 1024, 4); print('SURVIVED')")
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT)
+    assert p.returncode != 0
+    assert "SURVIVED" not in p.stdout
+    assert "no CUDA device" in p.stderr

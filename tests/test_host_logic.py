@@ -1,0 +1,57 @@
+"""CPU-only tests of the host-side replay logic (harness) - offsets, flops, layouts."""
+import numpy as np
+import pytest
+import torch
+
+from tpp_mlir_b200 import harness
+
+
+def test_flops_match_reference_convention():
+    # benchmarks/mlir/pytorch/torch-dynamo-mlp-bf16-3x1024.mlir:4 and ...gemm-bf16-3x1024.mlir:4
+    cfg = harness.MlpConfig(batch=256, layers=(1024,) * 4, tiles=(256, 1024, 1024))
+    assert cfg.flops() == 1_612_185_600
+    assert cfg.matmul_flops() == 1_610_612_736
+    cfg8 = harness.MlpConfig(batch=2048, layers=(1024,) * 4, tiles=(256, 1024, 1024))
+    assert cfg8.flops() == 8 * 1_612_185_600
+
+
+def test_config_validation():
+    with pytest.raises(ValueError):
+        harness.MlpConfig(batch=100, tiles=(32, 32, 32))
+    with pytest.raises(ValueError):
+        harness.MlpConfig(batch=256, layers=(1024, 1024, 1024), tiles=(32, 64, 32))
+
+
+def test_pack_unpack_roundtrip_and_block_math():
+    torch.manual_seed(0)
+    mb, c, k, bn, bk, bc = 64, 96, 128, 32, 32, 32
+    x, w = torch.rand(mb, c), torch.rand(c, k)
+    xp, wp = harness.pack_activation(x, bn, bc), harness.pack_weight(w, bk, bc)
+    assert xp.shape == (mb // bn, c // bc, bn, bc) and wp.shape == (k // bk, c // bc, bc, bk)
+    # blocked BRGEMM == flat matmul: out[iN][iK] = sum_iC xp[iN][iC] @ wp[iK][iC]
+    out = torch.einsum("ncab,kcbd->nkad", xp, wp)
+    torch.testing.assert_close(harness.unpack_activation(out), x @ w, rtol=1e-5, atol=1e-5)
+    wv = harness.vnni_pack_weight(wp)
+    assert wv.shape == (k // bk, c // bc, bc // 2, bk, 2)
+    assert wv[1, 2, 3, 4, 1] == wp[1, 2, 7, 4]
+
+
+def test_replay_offsets_follow_appendix_b(monkeypatch):
+    """The invoke stream must be exactly the one the lowered IR issues."""
+    from tpp_mlir_b200 import xsmm
+
+    calls = []
+    monkeypatch.setattr(xsmm, "fused_brgemm_dispatch", lambda *a: calls.append(("dispatch",) + a) or 77)
+    monkeypatch.setattr(xsmm, "intel_amx_tile_config_dispatch", lambda *a: 78)
+    monkeypatch.setattr(xsmm, "fused_brgemm_invoke", lambda *a: calls.append(("invoke",) + a))
+    cfg = harness.MlpConfig(batch=64, layers=(64, 128), tiles=(32, 32, 32))
+    r = harness.MlpReplay(cfg, weights=["W"], biases=["b"], acts=["x", "y"])
+    r.forward()
+    d = calls[0]
+    # dtype, m=bn, n=bk, k=bc, lda=bc, ldb=bk, ldc=bk, stride_a=bn*bc, stride_b=bc*bk, beta_0|64|128, 0, relu, col_in0, add
+    assert d[1:] == (2, 32, 32, 32, 32, 32, 32, 1024, 1024, 4 | 64 | 128, 0, 5, 4, 1)
+    inv = [c for c in calls if c[0] == "invoke"]
+    assert len(inv) == (64 // 32) * (128 // 32) == r.invokes_per_forward
+    # (iN=1, iK=2): offA = iN*(C/bc)*bn*bc, offB = iK*(C/bc)*bc*bk, offC = (iN*(K/bk)+iK)*bn*bk, offD = iK*bk
+    c = inv[1 * 4 + 2]
+    assert c[1:] == (2, 77, "x", 1 * 2 * 1024, "W", 2 * 2 * 1024, "y", (1 * 4 + 2) * 1024, "b", 64, 2)

@@ -1,0 +1,62 @@
+"""Pins the CPU oracle against every known-answer vector the reference's own tests hold
+for this path. CPU only."""
+import numpy as np
+import pytest
+
+import oracle
+from golden_cases import CASES
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference_vector(name, oracle_backend):
+    got, want, tol = CASES[name](oracle_backend)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=0, atol=tol, err_msg=name)
+
+
+def test_bf16_rounding_is_rne():
+    # ties to even, and the 257 -> 256 case the reference relies on (xsmm-ternary-bf16.mlir)
+    x = np.array([257.0, 258.0, 259.0, 1.0 + 2.0 ** -8, 1.0 + 3 * 2.0 ** -8, -257.0], np.float32)
+    got = oracle.bf16_to_f32(oracle.f32_to_bf16(x))
+    np.testing.assert_array_equal(got, np.array([256.0, 258.0, 260.0, 1.0, 1.0 + 2.0 ** -6, -256.0], np.float32))
+
+
+def test_tensor_init_streams_are_sequential():
+    # one generator per (type, dtype, seed), consumed tensor after tensor (TensorInit.cpp:75-86)
+    g1 = oracle.TensorInit("normal", oracle.F32, 123)
+    a, b = g1.fill(8), g1.fill(8)
+    g2 = oracle.TensorInit("normal", oracle.F32, 123)
+    ab = g2.fill(16)
+    np.testing.assert_array_equal(np.concatenate([a, b]), ab)
+    assert (ab >= 0).all() and (ab <= 1).all()
+    c = oracle.TensorInit("cont", oracle.F32).fill(4)
+    np.testing.assert_array_equal(c, np.array([0, 0.25, 0.5, 0.75], np.float32))
+    s = oracle.TensorInit("simple", oracle.F32).fill(4)
+    np.testing.assert_allclose(s, [0.3, 0.6, 0.9, 0.3])
+
+
+def test_oracle_thread_count_does_not_change_results():
+    rng = np.random.default_rng(0)
+    A = oracle.f32_to_bf16(rng.random((4, 40, 24), dtype=np.float32))
+    B = oracle.f32_to_bf16(rng.random((4, 24, 56), dtype=np.float32))
+    outs = []
+    for t in (1, 4):
+        oracle.set_num_threads(t)
+        C = np.zeros((40, 56), np.uint16)
+        oracle.brgemm(2, 40, 56, 24, 24, 56, 56, 40 * 24, 24 * 56, 4, A, B, C, 4)
+        outs.append(C)
+    oracle.set_num_threads(0)
+    np.testing.assert_array_equal(outs[0], outs[1])
+
+
+def test_oracle_vnni_equals_flat():
+    rng = np.random.default_rng(1)
+    m, n, k, batch = 9, 10, 12, 3
+    A = oracle.f32_to_bf16(rng.random((batch, m, k), dtype=np.float32))
+    Bf = rng.random((batch, k, n), dtype=np.float32)
+    B = oracle.f32_to_bf16(Bf)
+    Bv = np.ascontiguousarray(B.reshape(batch, k // 2, 2, n).transpose(0, 1, 3, 2))
+    C0, C1 = np.zeros((m, n), np.uint16), np.zeros((m, n), np.uint16)
+    oracle.brgemm(2, m, n, k, k, n, n, m * k, k * n, 4, A, B, C0, batch)
+    oracle.brgemm(2, m, n, k, k, n, n, m * k, k * n, 4 | 2048, A, Bv, C1, batch)
+    np.testing.assert_array_equal(C0, C1)

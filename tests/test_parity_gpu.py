@@ -1,0 +1,443 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle and the
+reference's known-answer vectors. Tolerances (BASELINE.json north_star): bf16 1e-2 rel,
+f32 1e-5 rel, bit-exact for data movement (identity / zero / transpose / VNNI)."""
+import numpy as np
+import pytest
+
+import oracle
+from backends import BF16, F32, AbiBackend, OracleBackend, np_dtype
+from golden_cases import CASES
+
+pytestmark = pytest.mark.gpu
+
+BF16_RTOL = 1e-2
+F32_RTOL = 1e-5
+
+
+def rnd(rng, dtype, shape, lo=-1.0, hi=1.0):
+    a = rng.uniform(lo, hi, size=shape).astype(np.float32)
+    return a if dtype == F32 else oracle.f32_to_bf16(a)
+
+
+def as_f32(dtype, a):
+    return a.astype(np.float32) if dtype == F32 else oracle.bf16_to_f32(a)
+
+
+def assert_close(dtype, got, want, scale=None):
+    g, w = as_f32(dtype, got).astype(np.float64), as_f32(dtype, want).astype(np.float64)
+    rtol = F32_RTOL if dtype == F32 else BF16_RTOL
+    s = np.abs(w).max() if scale is None else scale
+    np.testing.assert_allclose(g, w, rtol=rtol, atol=rtol * max(s, 1e-30) * 0.5)
+
+
+@pytest.fixture(scope="module")
+def dev():
+    return AbiBackend("device")
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return OracleBackend()
+
+
+# ---- 1. the reference's own known-answer tests, through the ABI ---------------------------
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_golden_vectors_device(name, dev):
+    got, want, tol = CASES[name](dev)
+    np.testing.assert_allclose(got, want, rtol=0, atol=tol, err_msg=name)
+
+
+@pytest.mark.parametrize("placement", ["host", "mirror"])
+@pytest.mark.parametrize("name", ["brgemm_f32_ones", "brgemm_bf16_vnni", "fused_bf16_vnni", "fused_f32_seed123",
+                                  "transpose_f32", "vnni2_pack_chain", "unary_relu_bf16", "binary_div_f32",
+                                  "strided_gemm1", "strided_brgemm", "mlp_all_ones_bf16"])
+def test_golden_vectors_host_pointers(name, placement):
+    got, want, tol = CASES[name](AbiBackend(placement))
+    np.testing.assert_allclose(got, want, rtol=0, atol=tol, err_msg=f"{name}/{placement}")
+
+
+# ---- 2. elementwise TPPs vs oracle --------------------------------------------------------
+UNARY_SHAPES = [(1, 1), (3, 5), (32, 32), (37, 129), (256, 1024), (1, 4096), (513, 8)]
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("kind", [1, 2, 5])
+@pytest.mark.parametrize("flags", [0, 2, 4, 8])
+@pytest.mark.parametrize("shape", UNARY_SHAPES)
+def test_unary_eltwise_bit_exact(dtype, kind, flags, shape, dev, orc):
+    m, n = shape
+    rng = np.random.default_rng(m * 1000 + n + kind)
+    pad = 0 if (m * n) % 2 else 8  # exercise ld > n and the vector / scalar paths
+    ldo = n + pad
+    if flags == 0:
+        ldi, inp = n + pad, rnd(rng, dtype, (m, n + pad))
+    elif flags == 2:
+        ldi, inp = 1, rnd(rng, dtype, (m,))
+    elif flags == 4:
+        ldi, inp = n, rnd(rng, dtype, (n,))
+    else:
+        ldi, inp = 1, rnd(rng, dtype, (1,))
+    sentinel = rnd(rng, dtype, (m, ldo))
+    out_g, out_o = sentinel.copy(), sentinel.copy()
+    dev.unary(kind, dtype, m, n, ldi, ldo, flags, inp, 0, out_g, 0)
+    orc.unary(kind, dtype, m, n, ldi, ldo, flags, inp, 0, out_o, 0)
+    np.testing.assert_array_equal(out_g.view(np.uint32 if dtype == F32 else np.uint16),
+                                  out_o.view(np.uint32 if dtype == F32 else np.uint16))
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_unary_in_place_and_offsets(dtype, dev, orc):
+    rng = np.random.default_rng(7)
+    buf = rnd(rng, dtype, (4, 64, 48))
+    g, o = buf.copy(), buf.copy()
+    for be, b in ((dev, g), (orc, o)):
+        be.unary(5, dtype, 64, 48, 48, 48, 0, b, 2 * 64 * 48, b, 2 * 64 * 48)  # relu(x, x) on the 3rd slice
+    np.testing.assert_array_equal(g, o)
+    assert (g[0] == buf[0]).all() and (g[3] == buf[3]).all()
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+def test_unary_scalar_invoke(dtype, dev, orc):
+    for kind, val in ((2, 7.5), (1, 0.3), (5, -2.0), (5, 1.7)):
+        g = rnd(np.random.default_rng(0), dtype, (33, 40))
+        o = g.copy()
+        dev.unary_scalar(kind, dtype, 33, 40, 1, 40, 8, val, g, 0)
+        orc.unary_scalar(kind, dtype, 33, 40, 1, 40, 8, val, o, 0)
+        np.testing.assert_array_equal(g, o)
+
+
+BIN_FLAGS = [0, 1, 2, 4, 8, 16, 32, 4 | 2, 1 | 8, 16 | 8]
+
+
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("kind", [1, 2, 3, 4])
+@pytest.mark.parametrize("flags", BIN_FLAGS)
+@pytest.mark.parametrize("shape", [(3, 3), (64, 64), (37, 129), (256, 1024)])
+def test_binary_vs_oracle(dtype, kind, flags, shape, dev, orc):
+    m, n = shape
+    rng = np.random.default_rng(kind * 7 + flags)
+
+    def operand(bits_row, bits_col, bits_scalar):
+        if flags & bits_row:
+            return 1, rnd(rng, dtype, (m,), 0.5, 2.0)
+        if flags & bits_col:
+            return n, rnd(rng, dtype, (n,), 0.5, 2.0)
+        if flags & bits_scalar:
+            return 1, rnd(rng, dtype, (1,), 0.5, 2.0)
+        return n, rnd(rng, dtype, (m, n), 0.5, 2.0)
+
+    ldl, lhs = operand(1, 4, 16)
+    ldr, rhs = operand(2, 8, 32)
+    g, o = np.zeros((m, n), np_dtype(dtype)), np.zeros((m, n), np_dtype(dtype))
+    dev.binary(kind, dtype, m, n, ldl, ldr, n, flags, lhs, 0, rhs, 0, g, 0)
+    orc.binary(kind, dtype, m, n, ldl, ldr, n, flags, lhs, 0, rhs, 0, o, 0)
+    if kind == 4:  # division: the GPU's IEEE div and the CPU's agree to the last bit for f32; allow 1 ulp in bf16
+        assert_close(dtype, g, o)
+    else:
+        np.testing.assert_array_equal(g, o)
+
+
+def test_binary_bias_add_in_place(dev, orc):
+    # the unfused MLP epilogue: binary add(bias[bcast_col_in0], C, C) then relu(C, C)
+    rng = np.random.default_rng(3)
+    bias, C = rnd(rng, BF16, (1024,)), rnd(rng, BF16, (256, 1024))
+    g, o = C.copy(), C.copy()
+    for be, c in ((dev, g), (orc, o)):
+        be.binary(1, BF16, 256, 1024, 1024, 1024, 1024, 4, bias, 0, c, 0, c, 0)
+        be.unary(5, BF16, 256, 1024, 1024, 1024, 0, c, 0, c, 0)
+    np.testing.assert_array_equal(g, o)
+
+
+# ---- 3. transforms: bit-exact ----------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [F32, BF16])
+@pytest.mark.parametrize("shape", [(4, 8), (1, 7), (64, 64), (65, 127), (300, 33), (1024, 512)])
+def test_transpose_bit_exact(dtype, shape, dev, orc):
+    m, n = shape
+    rng = np.random.default_rng(m + n)
+    inp = rnd(rng, dtype, (m, n + 3))
+    g, o = np.zeros((n, m + 5), np_dtype(dtype)), np.zeros((n, m + 5), np_dtype(dtype))
+    dev.unary(29, dtype, m, n, n + 3, m + 5, 0, inp, 0, g, 0)
+    orc.unary(29, dtype, m, n, n + 3, m + 5, 0, inp, 0, o, 0)
+    np.testing.assert_array_equal(g, o)
+
+
+@pytest.mark.parametrize("shape", [(2, 1), (16, 16), (32, 32), (64, 1000), (130, 72), (1024, 1024)])
+@pytest.mark.parametrize("pad", [0, 4, 3])
+def test_vnni2_pack_unpack_bit_exact(shape, pad, dev, orc):
+    m, n = shape
+    rng = np.random.default_rng(m * n + pad)
+    inp = rnd(rng, BF16, (m, n + pad))
+    ldo = n + pad
+    g, o = np.zeros((m // 2, ldo, 2), np.uint16), np.zeros((m // 2, ldo, 2), np.uint16)
+    dev.unary(28, BF16, m, n, n + pad, ldo, 0, inp, 0, g, 0)
+    orc.unary(28, BF16, m, n, n + pad, ldo, 0, inp, 0, o, 0)
+    np.testing.assert_array_equal(g, o)
+    # inverse (extension kind): round trip restores the input bits
+    back = np.zeros((m, n + pad), np.uint16)
+    dev.unary(1028, BF16, m, n, ldo, n + pad, 0, g, 0, back, 0)
+    np.testing.assert_array_equal(back[:, :n], inp[:, :n])
+
+
+def test_vnni2_full_size_roundtrip(dev):
+    # BASELINE config 4: 4096 x 4096 bf16; size-independent property: unpack(pack(x)) == x, and the
+    # packed tensor is a permutation (same multiset checksum)
+    rng = np.random.default_rng(4096)
+    x = rng.integers(0, 1 << 16, size=(4096, 4096), dtype=np.uint16)
+    p, back = np.zeros((2048, 4096, 2), np.uint16), np.zeros((4096, 4096), np.uint16)
+    dev.unary(28, BF16, 4096, 4096, 4096, 4096, 0, x, 0, p, 0)
+    dev.unary(1028, BF16, 4096, 4096, 4096, 4096, 0, p, 0, back, 0)
+    np.testing.assert_array_equal(back, x)
+    assert int(p.astype(np.uint64).sum()) == int(x.astype(np.uint64).sum())
+    np.testing.assert_array_equal(p[5, 17], x[10:12, 17])
+
+
+# ---- 4. BRGEMM family ---------------------------------------------------------------------------
+def run_brgemm_pair(dev, orc, dtype, m, n, k, batch, *, lda=None, ldb=None, ldc=None, sa=None, sb=None, flags=4,
+                    vnni=False, fused=None, seed=0, lo=-1.0, hi=1.0):
+    """fused = (unary_kind, binary_flags, binary_kind) or None. Returns (gpu C, oracle C, kernel name)."""
+    lda, ldb, ldc = lda or k, ldb or n, ldc or n
+    sa = m * lda if sa is None else sa
+    sb = k * ldb if sb is None else sb
+    rng = np.random.default_rng(seed)
+    nb = max(batch, 1)
+    A = rnd(rng, dtype, ((nb - 1) * sa + m * lda,), lo, hi)
+    Bflat = rnd(rng, dtype, ((nb - 1) * sb + k * ldb,), lo, hi)
+    B = Bflat
+    if vnni:
+        # repack every batch's [k][ldb] block as [k/2][ldb][2]
+        B = Bflat.copy()
+        for b in range(nb):
+            blk = Bflat[b * sb:b * sb + k * ldb].reshape(k // 2, 2, ldb)
+            B[b * sb:b * sb + k * ldb] = blk.transpose(0, 2, 1).reshape(-1)
+        flags |= 2048
+    C0 = rnd(rng, dtype, (m * ldc,), lo, hi)
+    D = None
+    if fused:
+        bf = fused[1]
+        D = rnd(rng, dtype, (n if bf == 4 else m if bf == 1 else 1 if bf == 16 else m * ldc,), lo, hi)
+    g, o = C0.copy(), C0.copy()
+    for be, c in ((dev, g), (orc, o)):
+        if fused:
+            be.fused_brgemm(dtype, m, n, k, lda, ldb, ldc, sa, sb, flags, 0, fused[0], fused[1], fused[2], A, 0, B, 0,
+                            c, 0, D, 0, batch)
+        else:
+            be.brgemm(dtype, m, n, k, lda, ldb, ldc, sa, sb, flags, A, 0, B, 0, c, 0, batch)
+    return g, o, dev.kernels[-1]
+
+
+TC_SHAPES = [
+    # m, n, k, batch
+    (128, 64, 64, 1), (128, 128, 128, 2), (256, 256, 64, 4), (32, 32, 32, 32), (64, 48, 96, 3),
+    (130, 72, 40, 2), (1, 8, 8, 1), (257, 1000, 136, 2), (256, 1024, 1024, 1), (512, 512, 256, 3),
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+@pytest.mark.parametrize("beta0", [True, False])
+def test_brgemm_bf16_tensor_core_path(shape, beta0, dev, orc):
+    m, n, k, batch = shape
+    g, o, kern = run_brgemm_pair(dev, orc, BF16, m, n, k, batch, flags=4 if beta0 else 0, seed=m + n + k)
+    assert kern.startswith("brgemm_tc_bf16"), kern
+    assert_close(BF16, g, o)
+
+
+@pytest.mark.parametrize("shape", [(128, 128, 64, 2), (256, 1024, 64, 16), (100, 200, 72, 3)])
+def test_brgemm_bf16_padded_leading_dims(shape, dev, orc):
+    m, n, k, batch = shape
+    g, o, kern = run_brgemm_pair(dev, orc, BF16, m, n, k, batch, lda=k + 8, ldb=n + 16, ldc=n + 24,
+                                 sa=m * (k + 8) + 64, sb=k * (n + 16) + 32, seed=11)
+    assert kern.startswith("brgemm_tc_bf16"), kern
+    assert_close(BF16, g, o)
+    # columns >= n of every C row are not written
+    gg, oo = g.reshape(m, n + 24), o.reshape(m, n + 24)
+    np.testing.assert_array_equal(gg[:, n:], oo[:, n:])
+
+
+@pytest.mark.parametrize("fused", [(5, 4, 1), (0, 4, 1), (5, 0, 0), (5, 1, 1), (5, 16, 2), (0, 0, 3)])
+@pytest.mark.parametrize("shape", [(256, 1024, 1024, 1), (64, 64, 32, 8), (129, 65, 72, 2)])
+def test_fused_brgemm_bf16(fused, shape, dev, orc):
+    m, n, k, batch = shape
+    g, o, kern = run_brgemm_pair(dev, orc, BF16, m, n, k, batch, fused=fused, seed=5)
+    assert kern.startswith("brgemm_tc_bf16"), kern
+    assert_close(BF16, g, o)
+    if fused[0] == 5:
+        assert (as_f32(BF16, g) >= 0).all()
+
+
+def test_fused_brgemm_accumulates_into_c(dev, orc):
+    g, o, _ = run_brgemm_pair(dev, orc, BF16, 128, 128, 64, 4, flags=0, fused=(5, 4, 1), seed=9)
+    assert_close(BF16, g, o)
+
+
+def test_cfg3_k64_batch16_equals_k1024_batch1(dev, orc):
+    """the strided view (k=64 x batch 16, lda=1024, stride_a=64, stride_b=65536) and the flat
+    call (k=1024 x batch 1) are the same math and must agree; both vs oracle."""
+    rng = np.random.default_rng(21)
+    A, W, bias = rnd(rng, BF16, (256, 1024), 0, 1), rnd(rng, BF16, (1024, 1024), 0, 0.1), rnd(rng, BF16, (1024,))
+    outs = []
+    for (k, batch, sa, sb) in ((1024, 1, 256 * 1024, 1024 * 1024), (64, 16, 64, 64 * 1024)):
+        c = np.zeros((256, 1024), np.uint16)
+        dev.fused_brgemm(BF16, 256, 1024, k, 1024, 1024, 1024, sa, sb, 4, 0, 5, 4, 1, A, 0, W, 0, c, 0, bias, 0, batch)
+        assert dev.kernels[-1].startswith("brgemm_tc_bf16")
+        outs.append(c)
+    ref = np.zeros((256, 1024), np.uint16)
+    orc.fused_brgemm(BF16, 256, 1024, 1024, 1024, 1024, 1024, 0, 0, 4, 0, 5, 4, 1, A, 0, W, 0, ref, 0, bias, 0, 1)
+    assert_close(BF16, outs[0], ref)
+    assert_close(BF16, outs[1], ref)
+    np.testing.assert_array_equal(outs[0], outs[1])  # same accumulation order inside the kernel
+
+
+def test_brgemm_zero_batches(dev, orc):
+    # numBatches = 0: C = beta*C (+ post-ops); nothing is read from A/B
+    g, o, _ = run_brgemm_pair(dev, orc, BF16, 64, 64, 64, 0, flags=0, fused=(5, 4, 1), seed=2)
+    np.testing.assert_array_equal(g, o)
+    g, o, _ = run_brgemm_pair(dev, orc, F32, 5, 7, 3, 0, flags=4, seed=2)
+    np.testing.assert_array_equal(g, o)
+
+
+@pytest.mark.parametrize("shape", [(4, 4, 4, 64), (6, 6, 6, 2), (32, 32, 32, 2), (64, 64, 64, 1), (33, 65, 17, 3),
+                                   (128, 256, 64, 2)])
+@pytest.mark.parametrize("beta0", [True, False])
+def test_brgemm_f32_simt(shape, beta0, dev, orc):
+    m, n, k, batch = shape
+    oracle.set_acc_mode(1)  # f64 truth: summation order is unspecified in the reference
+    try:
+        g, o, kern = run_brgemm_pair(dev, orc, F32, m, n, k, batch, flags=4 if beta0 else 0, seed=m * k, lo=0, hi=1)
+    finally:
+        oracle.set_acc_mode(0)
+    assert kern.startswith("brgemm_simt_f32"), kern
+    assert_close(F32, g, o)
+
+
+@pytest.mark.parametrize("shape", [(4, 4, 4, 64), (6, 6, 6, 2), (32, 32, 32, 4), (100, 72, 64, 2), (256, 512, 128, 2)])
+def test_brgemm_bf16_vnni_b(shape, dev, orc):
+    m, n, k, batch = shape
+    g, o, kern = run_brgemm_pair(dev, orc, BF16, m, n, k, batch, vnni=True, fused=(5, 4, 1), seed=m)
+    assert_close(BF16, g, o)
+
+
+def test_brgemm_unaligned_falls_back_to_generic_kernel(dev, orc):
+    # lda = 6 elements = 12 bytes: not expressible as a TMA stride -> generic kernel, same answer
+    g, o, kern = run_brgemm_pair(dev, orc, BF16, 6, 6, 6, 2, seed=1)
+    assert kern.startswith("brgemm_simt_bf16"), kern
+    assert_close(BF16, g, o)
+
+
+def test_gemm_is_brgemm_batch1(dev, orc):
+    rng = np.random.default_rng(8)
+    A, B = rnd(rng, BF16, (96, 160)), rnd(rng, BF16, (160, 224))
+    g, o = np.zeros((96, 224), np.uint16), np.zeros((96, 224), np.uint16)
+    dev.gemm(BF16, 96, 224, 160, 160, 224, 224, 4, A, 0, B, 0, g, 0)
+    orc.gemm(BF16, 96, 224, 160, 160, 224, 224, 4, A, 0, B, 0, o, 0)
+    assert_close(BF16, g, o)
+
+
+def test_cfg2_full_size_row_samples(dev, orc):
+    """BASELINE config 2 at full size: bf16 M=N=K=1024, batch 16 (34.4 GFLOP). The oracle checks row slabs
+    (it would need minutes for the whole matrix); a checksum-of-products property covers the rest."""
+    rng = np.random.default_rng(1024)
+    A = rnd(rng, BF16, (16, 1024, 1024), 0, 1)
+    B = rnd(rng, BF16, (16, 1024, 1024), 0, 0.05)
+    C = np.zeros((1024, 1024), np.uint16)
+    dev.brgemm(BF16, 1024, 1024, 1024, 1024, 1024, 1024, 1 << 20, 1 << 20, 4 | 64 | 128, A, 0, B, 0, C, 0, 16)
+    assert dev.kernels[-1].startswith("brgemm_tc_bf16")
+    for r0 in (0, 500, 1016):
+        ref = np.zeros((8, 1024), np.uint16)
+        orc.brgemm(BF16, 8, 1024, 1024, 1024, 1024, 1024, 1 << 20, 1 << 20, 4, A, r0 * 1024, B, 0, ref, 0, 16)
+        assert_close(BF16, C[r0:r0 + 8], ref)
+    # column-sum property: sum_i C[i][j] == sum_b sum_p (sum_i A[b][i][p]) * B[b][p][j]  (f64), within bf16 rounding
+    Af, Bf = as_f32(BF16, A).astype(np.float64), as_f32(BF16, B).astype(np.float64)
+    want = np.einsum("bp,bpj->j", Af.sum(axis=1), Bf)
+    got = as_f32(BF16, C).astype(np.float64).sum(axis=0)
+    np.testing.assert_allclose(got, want, rtol=2e-3)
+
+
+def test_cfg3_mlp_end_to_end(dev, orc):
+    """BASELINE config 3: 3 x fused_brgemm(256 x 1024 x 1024) + bias + relu, TensorInit 'normal' seed 123 data."""
+    gen = oracle.TensorInit("normal", BF16, 123)
+    Ws, bs = [], []
+    for _ in range(3):  # splat constants are replaced first, in op order: W1, b1, W2, b2, W3, b3
+        Ws.append(gen.fill(1024, 1024))
+        bs.append(gen.fill(1024))
+    x = gen.fill(256, 1024)
+    xg, xo = x, x
+    for W, b in zip(Ws, bs):
+        yg, yo = np.zeros((256, 1024), np.uint16), np.zeros((256, 1024), np.uint16)
+        dev.fused_brgemm(BF16, 256, 1024, 1024, 1024, 1024, 1024, 256 * 1024, 1 << 20, 4 | 64 | 128, 0, 5, 4, 1, xg, 0,
+                         W, 0, yg, 0, b, 0, 1)
+        orc.fused_brgemm(BF16, 256, 1024, 1024, 1024, 1024, 1024, 256 * 1024, 1 << 20, 4, 0, 5, 4, 1, xo, 0, W, 0, yo,
+                         0, b, 0, 1)
+        assert_close(BF16, yg, yo)
+        xg, xo = yg, yo
+
+
+# ---- 5. harness replay + residency modes --------------------------------------------------------
+@pytest.mark.parametrize("tiles", [(256, 1024, 1024), (32, 32, 32), (64, 256, 256)])
+@pytest.mark.parametrize("vnni", [False, True])
+def test_mlp_replay_blocked_layouts(tiles, vnni):
+    import torch
+
+    from tpp_mlir_b200 import harness, xsmm
+
+    bn, bk, bc = tiles
+    cfg = harness.MlpConfig(batch=256, layers=(1024, 1024, 1024), tiles=tiles, vnni=vnni)
+    gen = oracle.TensorInit("normal", BF16, 123)
+    Ws = [gen.fill(1024, 1024) for _ in range(2)]
+    bs = [gen.fill(1024) for _ in range(2)]
+    x = gen.fill(256, 1024)
+
+    def t(a):
+        return torch.from_numpy(a.view(np.int16))
+
+    wp = [harness.pack_weight(t(W), bk, bc) for W in Ws]
+    if vnni:
+        wp = [harness.vnni_pack_weight(w) for w in wp]
+    acts = [harness.pack_activation(t(x), bn, bc).cuda()] + [torch.zeros(256 * 1024, dtype=torch.int16).cuda()
+                                                               for _ in range(2)]
+    r = harness.MlpReplay(cfg, [w.cuda() for w in wp], [t(b).cuda() for b in bs], acts)
+    out = r.forward()
+    xsmm.sync()
+    got = harness.unpack_activation(out.reshape(256 // bn, 1024 // bk, bn, bk)).cpu().numpy().view(np.uint16)
+    ref = x
+    for W, b in zip(Ws, bs):
+        y = np.zeros((256, 1024), np.uint16)
+        oracle.fused_brgemm(BF16, 256, 1024, 1024, 1024, 1024, 1024, 0, 0, 4, 0, 5, 4, 1, ref, W, y, b, 1)
+        ref = y
+    assert_close(BF16, got, ref)
+
+
+def test_perf_timer_includes_async_launches():
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    A = torch.ones(16, 1024, 1024, dtype=torch.bfloat16, device="cuda")
+    C = torch.zeros(1024, 1024, dtype=torch.bfloat16, device="cuda")
+    h = xsmm.brgemm_dispatch(BF16, 1024, 1024, 1024, 1024, 1024, 1024, 1 << 20, 1 << 20, 4)
+    xsmm.brgemm_invoke(BF16, h, A, 0, A, 0, C, 0, 16)
+    n0 = xsmm.launch_count()
+    t0 = xsmm.perf_start_timer()
+    for _ in range(5):
+        xsmm.brgemm_invoke(BF16, h, A, 0, A, 0, C, 0, 16)
+    dt = xsmm.perf_stop_timer(t0)
+    assert xsmm.launch_count() - n0 == 5
+    # 5 x 34.4 GFLOP cannot finish faster than the nominal 2.25 PFLOP/s peak allows
+    assert dt > 5 * 34.36e9 / 2.25e15
+    assert float(C[0, 0]) == 16384.0
+
+
+def test_dispatch_is_cached_and_validates():
+    import subprocess
+    import sys
+
+    from tpp_mlir_b200 import xsmm
+
+    h1 = xsmm.brgemm_dispatch(BF16, 64, 64, 64, 64, 64, 64, 4096, 4096, 4)
+    h2 = xsmm.brgemm_dispatch(BF16, 64, 64, 64, 64, 64, 64, 4096, 4096, 4)
+    h3 = xsmm.brgemm_dispatch(BF16, 64, 64, 64, 64, 64, 64, 4096, 4096, 0)
+    assert h1 == h2 and h1 != h3
+    assert xsmm.handle_kernel(h1).startswith("brgemm_tc_bf16")
+    # lda < k violates the op verifier: the reference's dispatch prints and exit(-1)s; so does this one
+    code = "from tpp_mlir_b200 import xsmm; xsmm.brgemm_dispatch(2, 64, 64, 64, 32, 64, 64, 0, 0, 4)"
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    assert p.returncode != 0 and "failed to generate brgemm func" in p.stderr

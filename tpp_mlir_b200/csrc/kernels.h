@@ -1,0 +1,55 @@
+// kernels.h - host-side launch entry points of the sm_100a kernels.
+// Every pointer here is a DEVICE pointer (already offset to the first element).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "kernel_desc.h"
+
+namespace tpp {
+
+// broadcast mode of one eltwise operand
+enum : int { kBcastNone = 0, kBcastRow = 1, kBcastCol = 2, kBcastScalar = 3, kBcastImm = 4 /* scalar passed by value */ };
+// eltwise opcode
+enum : int { kOpIdentity = 0, kOpZero = 1, kOpRelu = 2, kOpAdd = 3, kOpMul = 4, kOpSub = 5, kOpDiv = 6 };
+
+struct EltwiseArgs {
+  const void *in0 = nullptr;
+  const void *in1 = nullptr;
+  void *out = nullptr;
+  int64_t m = 0, n = 0, ld0 = 0, ld1 = 0, ldo = 0;
+  int mode0 = 0, mode1 = 0, op = 0;
+  int64_t dtype = 0;
+  float imm = 0.f; // operand 0 when mode0 == kBcastImm (xsmm_unary_scalar_invoke)
+};
+
+// unary identity/zero/relu and binary add/mul/sub/div, with broadcasts
+void launch_eltwise(const EltwiseArgs &a, cudaStream_t stream);
+// out[j*ldo+i] = in[i*ldi+j], i<m, j<n (bit copy; es = element size 2 or 4)
+void launch_transpose(const void *in, void *out, int64_t m, int64_t n, int64_t ldi, int64_t ldo, int es,
+                      cudaStream_t stream);
+// bf16 [K=m][N=n] (ldi) -> [K/2][N][2] (ldo in pairs), and the inverse
+void launch_vnni2_pack(const void *in, void *out, int64_t m, int64_t n, int64_t ldi, int64_t ldo,
+                       cudaStream_t stream);
+void launch_vnni2_unpack(const void *in, void *out, int64_t m, int64_t n, int64_t ldi, int64_t ldo,
+                         cudaStream_t stream);
+
+struct GemmArgs {
+  const void *A = nullptr;
+  const void *B = nullptr;
+  void *C = nullptr;
+  const void *D = nullptr; // bias vector (fused add, bcast_col_in0) or nullptr
+  int64_t batch = 1;
+};
+
+// generic FFMA BRGEMM (any dtype/ld/stride, VNNI-B), fused epilogue
+void launch_brgemm_simt(const KernelDesc &d, const GemmArgs &g, cudaStream_t stream);
+
+// tcgen05 BRGEMM. Returns false (and launches nothing) if the operands of THIS
+// invoke are not TMA-compatible (pointer alignment); the caller then uses the
+// generic kernel.
+bool brgemm_tc_supported(const KernelDesc &d);
+void brgemm_tc_configure(KernelDesc &d);
+bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t stream);
+
+} // namespace tpp

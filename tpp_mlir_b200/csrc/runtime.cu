@@ -1,0 +1,718 @@
+// runtime.cu - the C-ABI of include/tpp_xsmm_abi.h on top of the sm_100a kernels.
+//
+// B200-native counterpart of runtime/Xsmm/XsmmRunnerUtils.cpp (the libxsmm shim)
+// and runtime/PerfRunnerUtils.cpp. Dispatch validates the shape, picks a kernel
+// family + tile configuration and returns the address of an immortal KernelDesc;
+// invoke resolves the operands to device memory and launches. There is no CPU
+// execution path in this file: every invoke ends in a CUDA kernel launch, and a
+// process without a usable sm_100 device dies in the first dispatch.
+#include "tpp_xsmm_abi.h"
+
+#include <atomic>
+#include <chrono>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <shared_mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "kernel_desc.h"
+#include "kernels.h"
+
+using namespace tpp;
+
+namespace {
+
+// ---- process-wide state -----------------------------------------------------
+std::atomic<int64_t> g_launches{0};
+std::atomic<bool> g_cuda_ready{false};
+std::mutex g_init_mutex;
+
+void fail(const char *what) {
+  fprintf(stderr, "tpp-xsmm-cuda: %s\n", what);
+  exit(-1);
+}
+
+// First CUDA use: there must be an sm_100 device. No fallback of any kind.
+void ensure_cuda() {
+  if (g_cuda_ready.load(std::memory_order_acquire)) return;
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  if (g_cuda_ready.load()) return;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    fprintf(stderr,
+            "tpp-xsmm-cuda: no CUDA device available (%s). This backend has no CPU path; "
+            "run on a B200 (sm_100a).\n",
+            e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    exit(-1);
+  }
+  int dev = 0;
+  if (const char *env = getenv("TPP_XSMM_DEVICE")) {
+    dev = atoi(env);
+    TPP_CUDA_CHECK(cudaSetDevice(dev));
+  } else {
+    TPP_CUDA_CHECK(cudaGetDevice(&dev));
+  }
+  cudaDeviceProp prop;
+  TPP_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    fprintf(stderr, "tpp-xsmm-cuda: device %d (%s) is sm_%d%d; kernels are built for sm_100a only\n", dev, prop.name,
+            prop.major, prop.minor);
+    exit(-1);
+  }
+  g_cuda_ready.store(true, std::memory_order_release);
+}
+
+// ---- per-thread execution context ---------------------------------------------
+struct Staging {
+  void *ptr = nullptr;
+  size_t cap = 0;
+  void *get(size_t bytes) {
+    if (bytes > cap) {
+      if (ptr) TPP_CUDA_CHECK(cudaFree(ptr));
+      size_t want = bytes < (1u << 20) ? (1u << 20) : bytes + bytes / 4;
+      TPP_CUDA_CHECK(cudaMalloc(&ptr, want));
+      cap = want;
+    }
+    return ptr;
+  }
+};
+
+struct ThreadCtx {
+  cudaStream_t stream = nullptr; // legacy default stream unless xsmm_cuda_set_stream was called
+  int device = -1;               // device this thread last launched on
+  const char *last_kernel = "";
+  Staging stage[4];
+};
+thread_local ThreadCtx t_ctx;
+
+// ---- registered host ranges -> device mirrors -----------------------------------
+struct Mirror {
+  char *host;
+  size_t bytes;
+  char *dev;
+  bool pinned_here;
+};
+std::shared_mutex g_mirror_mutex;
+std::map<uintptr_t, Mirror> g_mirrors; // keyed by host start
+std::atomic<int> g_mirror_count{0};
+
+bool find_mirror(const void *p, Mirror *out) {
+  if (g_mirror_count.load(std::memory_order_relaxed) == 0) return false;
+  std::shared_lock<std::shared_mutex> lock(g_mirror_mutex);
+  auto it = g_mirrors.upper_bound(reinterpret_cast<uintptr_t>(p));
+  if (it == g_mirrors.begin()) return false;
+  --it;
+  const Mirror &m = it->second;
+  if (reinterpret_cast<const char *>(p) >= m.host && reinterpret_cast<const char *>(p) < m.host + m.bytes) {
+    *out = m;
+    return true;
+  }
+  return false;
+}
+
+enum class Where { Device, HostMirrored, HostPlain };
+
+struct Resolved {
+  Where where;
+  char *dev;    // device address of the element the host/device pointer designates (Device / HostMirrored)
+  int device;   // owning device ordinal, -1 if unknown
+};
+
+// Classification of a base pointer is cached per thread: the JIT passes the same
+// few memref base pointers over and over.
+struct ClassCacheEntry {
+  const void *base = nullptr;
+  bool is_device = false;
+  int device = -1;
+};
+thread_local ClassCacheEntry t_class_cache[8];
+
+Resolved resolve(const void *base, const void *elem) {
+  Mirror mir;
+  if (find_mirror(elem, &mir)) {
+    return {Where::HostMirrored, mir.dev + (reinterpret_cast<const char *>(elem) - mir.host), -1};
+  }
+  const size_t slot = (reinterpret_cast<uintptr_t>(base) >> 6) & 7;
+  ClassCacheEntry &ce = t_class_cache[slot];
+  if (ce.base != base) {
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, base);
+    bool is_dev = false;
+    int dev = -1;
+    if (e == cudaSuccess) {
+      is_dev = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+      dev = attr.device;
+    } else {
+      cudaGetLastError(); // plain malloc memory on older drivers reports an error: treat as host
+    }
+    ce.base = base;
+    ce.is_device = is_dev;
+    ce.device = dev;
+  }
+  if (ce.is_device) return {Where::Device, const_cast<char *>(reinterpret_cast<const char *>(elem)), ce.device};
+  return {Where::HostPlain, nullptr, -1};
+}
+
+void use_device(int dev) {
+  if (dev >= 0 && dev != t_ctx.device) {
+    TPP_CUDA_CHECK(cudaSetDevice(dev));
+    t_ctx.device = dev;
+  }
+}
+
+inline size_t esize(int64_t dtype) { return dtype == kF32 ? 4 : 2; }
+
+inline char *elem_ptr(int64_t dtype, void *aligned, int64_t offset) {
+  // runtime/Xsmm/XsmmRunnerUtils.cpp:63-75 (get_base_ptr)
+  if (dtype != kF32 && dtype != kBF16) {
+    fprintf(stderr, "Unhandled data type in get_data_pointer_from_memref_desc:%lld", (long long)dtype);
+    return nullptr;
+  }
+  return static_cast<char *>(aligned) + offset * (int64_t)esize(dtype);
+}
+
+// One operand of an invoke: where it lives and, for plain host memory, the 2-D
+// footprint (rows x width elements, pitch ld) that has to be staged.
+struct Operand {
+  void *aligned = nullptr;
+  char *elem = nullptr;
+  int64_t rows = 0, width = 0, ld = 0; // footprint in elements
+  bool is_input = false, is_output = false;
+  char *dev = nullptr; // resolved device address
+  Where where = Where::Device;
+};
+
+struct StagedCall {
+  Operand *ops;
+  int nops;
+  size_t es;
+  bool any_host = false;
+};
+
+void stage_in(StagedCall &sc, cudaStream_t stream) {
+  int known_dev = -1;
+  for (int i = 0; i < sc.nops; ++i) {
+    Operand &o = sc.ops[i];
+    if (!o.elem) continue;
+    Resolved r = resolve(o.aligned, o.elem);
+    o.where = r.where;
+    o.dev = r.dev;
+    if (r.where == Where::Device && r.device >= 0) known_dev = r.device;
+    if (r.where == Where::HostPlain) sc.any_host = true;
+  }
+  use_device(known_dev);
+  if (!sc.any_host) return;
+  for (int i = 0; i < sc.nops; ++i) {
+    Operand &o = sc.ops[i];
+    if (!o.elem || o.where != Where::HostPlain) continue;
+    const size_t pitch = (size_t)o.ld * sc.es;
+    const size_t bytes = o.rows > 0 ? (size_t)(o.rows - 1) * pitch + (size_t)o.width * sc.es : 0;
+    o.dev = static_cast<char *>(t_ctx.stage[i].get(bytes ? bytes : 16));
+    if (o.is_input && bytes) {
+      if (o.rows == 1 || o.ld == o.width)
+        TPP_CUDA_CHECK(cudaMemcpyAsync(o.dev, o.elem, bytes, cudaMemcpyHostToDevice, stream));
+      else
+        TPP_CUDA_CHECK(cudaMemcpy2DAsync(o.dev, pitch, o.elem, pitch, (size_t)o.width * sc.es, (size_t)o.rows,
+                                         cudaMemcpyHostToDevice, stream));
+    }
+  }
+}
+
+void stage_out(StagedCall &sc, cudaStream_t stream) {
+  if (!sc.any_host) return;
+  for (int i = 0; i < sc.nops; ++i) {
+    Operand &o = sc.ops[i];
+    if (!o.elem || o.where != Where::HostPlain || !o.is_output) continue;
+    const size_t pitch = (size_t)o.ld * sc.es;
+    if (o.rows == 1 || o.ld == o.width) {
+      const size_t bytes = (size_t)(o.rows - 1) * pitch + (size_t)o.width * sc.es;
+      TPP_CUDA_CHECK(cudaMemcpyAsync(o.elem, o.dev, bytes, cudaMemcpyDeviceToHost, stream));
+    } else {
+      TPP_CUDA_CHECK(cudaMemcpy2DAsync(o.elem, pitch, o.dev, pitch, (size_t)o.width * sc.es, (size_t)o.rows,
+                                       cudaMemcpyDeviceToHost, stream));
+    }
+  }
+  // strict mode keeps the reference's synchronous semantics: the result is
+  // visible to the host when the invoke returns
+  TPP_CUDA_CHECK(cudaStreamSynchronize(stream));
+}
+
+// ---- dispatch cache -------------------------------------------------------------
+struct Key {
+  int64_t v[16];
+  bool operator==(const Key &o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct KeyHash {
+  size_t operator()(const Key &k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < 16; ++i) {
+      h ^= (uint64_t)k.v[i];
+      h *= 1099511628211ull;
+    }
+    return (size_t)h;
+  }
+};
+std::mutex g_cache_mutex;
+std::unordered_map<Key, KernelDesc *, KeyHash> g_cache;
+
+template <typename Build> int64_t cached(const Key &key, Build build) {
+  std::lock_guard<std::mutex> lock(g_cache_mutex);
+  auto it = g_cache.find(key);
+  if (it != g_cache.end()) return reinterpret_cast<int64_t>(it->second);
+  KernelDesc *d = new KernelDesc(); // immortal, like libxsmm's code registry
+  build(*d);
+  g_cache.emplace(key, d);
+  return reinterpret_cast<int64_t>(d);
+}
+
+const KernelDesc *desc_of(int64_t addr, OpClass a, OpClass b = OpClass::TileConfig, OpClass c = OpClass::TileConfig) {
+  const KernelDesc *d = reinterpret_cast<const KernelDesc *>(addr);
+  if (!d || d->magic != kDescMagic || (d->op != a && d->op != b && d->op != c)) {
+    fail("invoke called with a handle that was not returned by the matching dispatch");
+  }
+  return d;
+}
+
+void print_gemm_shape(const char *what, int64_t dtype, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+                      int64_t ldc, int64_t sa, int64_t sb, int64_t flags) {
+  // same information the reference prints before exit(-1) (XsmmRunnerUtils.cpp:352-358),
+  // in the row-major view
+  fprintf(stderr, "%s\n", what);
+  fprintf(stderr, "dtype: %lld\nM: %lld\nN: %lld\nK: %lld\nlda: %lld\nldb: %lld\nldc: %lld\n", (long long)dtype,
+          (long long)m, (long long)n, (long long)k, (long long)lda, (long long)ldb, (long long)ldc);
+  fprintf(stderr, "stride_a: %lld\nstride_b: %lld\nflags: %lld\n", (long long)sa, (long long)sb, (long long)flags);
+}
+
+int64_t gemm_family_dispatch(OpClass op, int64_t dtype, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+                             int64_t ldc, int64_t sa, int64_t sb, int64_t gflags, int64_t uflags, int64_t ukind,
+                             int64_t bflags, int64_t bkind) {
+  ensure_cuda();
+  const char *what = op == OpClass::Gemm     ? "failed to generate matmul func"
+                     : op == OpClass::Brgemm ? "failed to generate brgemm func"
+                                             : "failed to generate fused brgemm func";
+  bool ok = (dtype == kF32 || dtype == kBF16) && m > 0 && n > 0 && k > 0;
+  const bool vnni_b = (gflags & XSMM_GEMM_FLAG_ROWMAJOR_B_VNNI) != 0;
+  // op verifier rules (lib/TPP/Dialect/Xsmm/XsmmOps.cpp:319-344): lda >= k, ldb >= n, ldc >= n
+  ok = ok && lda >= k && ldb >= n && ldc >= n && sa >= 0 && sb >= 0;
+  if (vnni_b) ok = ok && dtype == kBF16 && (k % 2) == 0;
+  if (gflags & XSMM_GEMM_FLAG_VNNI_C) ok = false; // never produced by the pipeline (XsmmVerify.cpp:91-95)
+  if (op == OpClass::FusedBrgemm) {
+    ok = ok && bkind >= 0 && bkind <= 4 && (ukind == XSMM_UNARY_NONE || ukind == XSMM_UNARY_RELU);
+    ok = ok && (bflags == 0 || bflags == 1 || bflags == 4 || bflags == 16) && uflags == 0;
+  }
+  if (!ok) {
+    print_gemm_shape(what, dtype, m, n, k, lda, ldb, ldc, sa, sb, gflags);
+    exit(-1);
+  }
+  Key key{{(int64_t)op, dtype, m, n, k, lda, ldb, ldc, sa, sb, gflags, uflags, ukind, bflags, bkind, 0}};
+  return cached(key, [&](KernelDesc &d) {
+    d.op = op;
+    d.dtype = dtype;
+    d.m = m; d.n = n; d.k = k; d.lda = lda; d.ldb = ldb; d.ldc = ldc;
+    d.stride_a = sa; d.stride_b = sb;
+    d.gemm_flags = gflags;
+    d.unary_flags = uflags; d.unary_kind = ukind; d.binary_flags = bflags; d.binary_kind = bkind;
+    const char *force = getenv("TPP_XSMM_FORCE_SIMT");
+    if (brgemm_tc_supported(d) && !(force && force[0] == '1')) {
+      d.impl = KernelImpl::BrgemmTC;
+      brgemm_tc_configure(d);
+    } else {
+      d.impl = KernelImpl::BrgemmSimt;
+      snprintf(d.name, sizeof(d.name), "brgemm_simt_%s_64x64x16", dtype == kF32 ? "f32" : "bf16");
+    }
+  });
+}
+
+void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t offA, void *pB, int64_t offB, void *pC,
+                        int64_t offC, void *pD, int64_t offD, int64_t batch) {
+  if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
+  if (batch < 0) batch = 0;
+  const bool vnni_b = (d->gemm_flags & XSMM_GEMM_FLAG_ROWMAJOR_B_VNNI) != 0;
+  const bool beta0 = (d->gemm_flags & XSMM_GEMM_FLAG_BETA_0) != 0;
+  Operand ops[4];
+  // A: batch x (m x k, pitch lda); staged as one row of the whole span
+  const int64_t nb = batch > 0 ? batch : 1;
+  ops[0].aligned = pA; ops[0].elem = elem_ptr(dtype, pA, offA);
+  ops[0].rows = 1; ops[0].width = (nb - 1) * d->stride_a + (d->m - 1) * d->lda + d->k; ops[0].ld = ops[0].width;
+  ops[0].is_input = batch > 0;
+  ops[1].aligned = pB; ops[1].elem = elem_ptr(dtype, pB, offB);
+  ops[1].rows = 1;
+  ops[1].width = vnni_b ? (nb - 1) * d->stride_b + ((d->k / 2 - 1) * d->ldb + d->n) * 2
+                        : (nb - 1) * d->stride_b + (d->k - 1) * d->ldb + d->n;
+  ops[1].ld = ops[1].width;
+  ops[1].is_input = batch > 0;
+  ops[2].aligned = pC; ops[2].elem = elem_ptr(dtype, pC, offC);
+  ops[2].rows = d->m; ops[2].width = d->n; ops[2].ld = d->ldc;
+  ops[2].is_input = !beta0; ops[2].is_output = true;
+  const bool has_d = d->op == OpClass::FusedBrgemm && d->binary_kind != 0 && pD != nullptr;
+  if (has_d) {
+    ops[3].aligned = pD; ops[3].elem = elem_ptr(dtype, pD, offD);
+    const int64_t bf = d->binary_flags;
+    if (bf & 4) { ops[3].rows = 1; ops[3].width = d->n; ops[3].ld = d->n; }
+    else if (bf & 1) { ops[3].rows = 1; ops[3].width = d->m; ops[3].ld = d->m; }
+    else if (bf & 16) { ops[3].rows = 1; ops[3].width = 1; ops[3].ld = 1; }
+    else { ops[3].rows = d->m; ops[3].width = d->n; ops[3].ld = d->ldc; }
+    ops[3].is_input = true;
+  }
+  cudaStream_t stream = t_ctx.stream;
+  StagedCall sc{ops, 4, esize(dtype)};
+  stage_in(sc, stream);
+
+  GemmArgs g;
+  g.A = ops[0].dev; g.B = ops[1].dev; g.C = ops[2].dev; g.D = has_d ? ops[3].dev : nullptr;
+  g.batch = batch;
+  bool launched = false;
+  if (d->impl == KernelImpl::BrgemmTC) {
+    launched = launch_brgemm_tc(*d, g, stream);
+    if (launched) t_ctx.last_kernel = d->name;
+  }
+  if (!launched) {
+    launch_brgemm_simt(*d, g, stream);
+    t_ctx.last_kernel = d->dtype == kF32 ? "brgemm_simt_f32_64x64x16" : "brgemm_simt_bf16_64x64x16";
+  }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  stage_out(sc, stream);
+}
+
+int bcast_mode_unary(int64_t flags) {
+  return flags == XSMM_UNARY_FLAG_BCAST_ROW      ? kBcastRow
+         : flags == XSMM_UNARY_FLAG_BCAST_COL    ? kBcastCol
+         : flags == XSMM_UNARY_FLAG_BCAST_SCALAR ? kBcastScalar
+                                                 : kBcastNone;
+}
+
+void set_footprint(Operand &o, int mode, int64_t m, int64_t n, int64_t ld) {
+  switch (mode) {
+  case kBcastRow: o.rows = m; o.width = 1; o.ld = ld > 0 ? ld : 1; break;
+  case kBcastCol: o.rows = 1; o.width = n; o.ld = n; break;
+  case kBcastScalar: o.rows = 1; o.width = 1; o.ld = 1; break;
+  default: o.rows = m; o.width = n; o.ld = ld; break;
+  }
+}
+
+} // namespace
+
+// ================================ dispatch ========================================
+
+extern "C" int64_t xsmm_gemm_dispatch(int64_t dtype, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+                                      int64_t ldc, int64_t flags) {
+  return gemm_family_dispatch(OpClass::Gemm, dtype, m, n, k, lda, ldb, ldc, 0, 0, flags, 0, 0, 0, 0);
+}
+
+extern "C" int64_t xsmm_brgemm_dispatch(int64_t dtype, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb,
+                                        int64_t ldc, int64_t stride_a, int64_t stride_b, int64_t flags) {
+  return gemm_family_dispatch(OpClass::Brgemm, dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, flags, 0, 0, 0, 0);
+}
+
+extern "C" int64_t xsmm_fused_brgemm_dispatch(int64_t dtype, int64_t m, int64_t n, int64_t k, int64_t lda,
+                                              int64_t ldb, int64_t ldc, int64_t stride_a, int64_t stride_b,
+                                              int64_t gemm_flags, int64_t unary_flags, int64_t unary_kind,
+                                              int64_t binary_flags, int64_t binary_kind) {
+  return gemm_family_dispatch(OpClass::FusedBrgemm, dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, gemm_flags,
+                              unary_flags, unary_kind, binary_flags, binary_kind);
+}
+
+extern "C" int64_t xsmm_unary_dispatch(int64_t kind, int64_t dtype, int64_t m, int64_t n, int64_t ldi, int64_t ldo,
+                                       int64_t flags) {
+  ensure_cuda();
+  bool ok = (dtype == kF32 || dtype == kBF16) && m > 0 && n > 0 && ldi >= 0 && ldo > 0;
+  KernelImpl impl = KernelImpl::Eltwise;
+  const char *name = "";
+  switch (kind) {
+  case XSMM_UNARY_IDENTITY: name = "unary_identity"; break;
+  case XSMM_UNARY_ZERO: name = "unary_zero"; break;
+  case XSMM_UNARY_RELU: name = "unary_relu"; break;
+  case XSMM_UNARY_TRANSPOSE: impl = KernelImpl::Transpose; name = "unary_transpose_64x64"; ok = ok && flags == 0 && ldi >= n && ldo >= m; break;
+  case XSMM_UNARY_VNNI2: impl = KernelImpl::Vnni2Pack; name = "unary_vnni2_pack"; ok = ok && flags == 0 && dtype == kBF16 && (m % 2) == 0 && ldi >= n && ldo >= n; break;
+  case XSMM_UNARY_UNVNNI2_EXT: impl = KernelImpl::Vnni2Unpack; name = "unary_vnni2_unpack"; ok = ok && flags == 0 && dtype == kBF16 && (m % 2) == 0 && ldi >= n && ldo >= n; break;
+  default: ok = false;
+  }
+  if (impl == KernelImpl::Eltwise) {
+    ok = ok && (flags == 0 || flags == 2 || flags == 4 || flags == 8) && ldo >= n;
+    if (flags == 0 && kind != XSMM_UNARY_ZERO) ok = ok && ldi >= n;
+  }
+  if (!ok) {
+    fprintf(stderr, "failed to generate unary func\nop_type: %lld\nflags: %lld\n", (long long)kind, (long long)flags);
+    fprintf(stderr, "M: %lld\nN: %lld\ndtype: %lld\nldi: %lld\nldo: %lld\n", (long long)m, (long long)n,
+            (long long)dtype, (long long)ldi, (long long)ldo);
+    exit(-1);
+  }
+  Key key{{(int64_t)OpClass::Unary, kind, dtype, m, n, ldi, ldo, flags, 0, 0, 0, 0, 0, 0, 0, 0}};
+  return cached(key, [&](KernelDesc &d) {
+    d.op = OpClass::Unary;
+    d.impl = impl;
+    d.dtype = dtype; d.kind = kind; d.m = m; d.n = n; d.ldi = ldi; d.ldo = ldo; d.flags = flags;
+    snprintf(d.name, sizeof(d.name), "%s_%s", name, dtype == kF32 ? "f32" : "bf16");
+  });
+}
+
+extern "C" int64_t xsmm_binary_dispatch(int64_t kind, int64_t dtype, int64_t m, int64_t n, int64_t ldiLhs,
+                                        int64_t ldiRhs, int64_t ldo, int64_t flags) {
+  ensure_cuda();
+  bool ok = (dtype == kF32 || dtype == kBF16) && m > 0 && n > 0 && kind >= 1 && kind <= 4 && ldo >= n;
+  const int64_t f0 = flags & (1 | 4 | 16), f1 = flags & (2 | 8 | 32);
+  ok = ok && (f0 == 0 || f0 == 1 || f0 == 4 || f0 == 16) && (f1 == 0 || f1 == 2 || f1 == 8 || f1 == 32) &&
+       (flags & ~63ll) == 0;
+  if (f0 == 0) ok = ok && ldiLhs >= n;
+  if (f1 == 0) ok = ok && ldiRhs >= n;
+  if (!ok) {
+    fprintf(stderr, "failed to generate binary func\nop_type: %lld\nflags: %lld\n", (long long)kind, (long long)flags);
+    fprintf(stderr, "M: %lld\nN: %lld\ndtype: %lld\nldi: %lld\nldi2: %lld\nldo: %lld\n", (long long)m, (long long)n,
+            (long long)dtype, (long long)ldiLhs, (long long)ldiRhs, (long long)ldo);
+    exit(-1);
+  }
+  Key key{{(int64_t)OpClass::Binary, kind, dtype, m, n, ldiLhs, ldiRhs, ldo, flags, 0, 0, 0, 0, 0, 0, 0}};
+  return cached(key, [&](KernelDesc &d) {
+    static const char *names[] = {"", "add", "mul", "sub", "div"};
+    d.op = OpClass::Binary;
+    d.impl = KernelImpl::Eltwise;
+    d.dtype = dtype; d.kind = kind; d.m = m; d.n = n; d.ldi = ldiLhs; d.ldi2 = ldiRhs; d.ldo = ldo; d.flags = flags;
+    snprintf(d.name, sizeof(d.name), "binary_%s_%s", names[kind], dtype == kF32 ? "f32" : "bf16");
+  });
+}
+
+extern "C" int64_t xsmm_intel_amx_tile_config_dispatch(int64_t dtype, int64_t m, int64_t n, int64_t k, int64_t lda,
+                                                       int64_t ldb, int64_t ldc, int64_t stride_a, int64_t stride_b,
+                                                       int64_t flags) {
+  // AMX tile registers do not exist on a GPU (lib/TPP/Transforms/IntelAMXTileConfig.cpp:32-139
+  // inserts these unconditionally for bf16): one shared no-op descriptor.
+  (void)m; (void)n; (void)k; (void)lda; (void)ldb; (void)ldc; (void)stride_a; (void)stride_b; (void)flags;
+  Key key{{(int64_t)OpClass::TileConfig, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}};
+  return cached(key, [&](KernelDesc &d) {
+    d.op = OpClass::TileConfig;
+    d.impl = KernelImpl::Noop;
+    d.dtype = dtype;
+    snprintf(d.name, sizeof(d.name), "amx_tile_config_noop");
+  });
+}
+
+// ================================= invoke ==========================================
+
+extern "C" void xsmm_gemm_invoke(int64_t dtype, int64_t addr, void *alignedPtrA, int64_t offsetA, void *alignedPtrB,
+                                 int64_t offsetB, void *alignedPtrC, int64_t offsetC) {
+  const KernelDesc *d = desc_of(addr, OpClass::Gemm);
+  gemm_family_invoke(d, dtype, alignedPtrA, offsetA, alignedPtrB, offsetB, alignedPtrC, offsetC, nullptr, 0, 1);
+}
+
+extern "C" void xsmm_brgemm_invoke(int64_t dtype, int64_t addr, void *alignedPtrA, int64_t offsetA, void *alignedPtrB,
+                                   int64_t offsetB, void *alignedPtrC, int64_t offsetC, int64_t numBatches) {
+  const KernelDesc *d = desc_of(addr, OpClass::Brgemm, OpClass::Gemm);
+  gemm_family_invoke(d, dtype, alignedPtrA, offsetA, alignedPtrB, offsetB, alignedPtrC, offsetC, nullptr, 0,
+                     numBatches);
+}
+
+extern "C" void xsmm_fused_brgemm_invoke(int64_t dtype, int64_t addr, void *alignedPtrA, int64_t offsetA,
+                                         void *alignedPtrB, int64_t offsetB, void *alignedPtrC, int64_t offsetC,
+                                         void *alignedPtrD, int64_t offsetD, int64_t numBatches) {
+  const KernelDesc *d = desc_of(addr, OpClass::FusedBrgemm);
+  gemm_family_invoke(d, dtype, alignedPtrA, offsetA, alignedPtrB, offsetB, alignedPtrC, offsetC, alignedPtrD, offsetD,
+                     numBatches);
+}
+
+static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int64_t offIn, bool use_imm, float imm,
+                              void *pOut, int64_t offOut) {
+  if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
+  Operand ops[2];
+  const int mode = bcast_mode_unary(d->flags);
+  const bool reads_input = d->kind != XSMM_UNARY_ZERO && !use_imm;
+  if (reads_input) {
+    ops[0].aligned = pIn; ops[0].elem = elem_ptr(dtype, pIn, offIn);
+    ops[0].is_input = true;
+  }
+  ops[1].aligned = pOut; ops[1].elem = elem_ptr(dtype, pOut, offOut);
+  ops[1].is_output = true;
+  switch (d->impl) {
+  case KernelImpl::Transpose:
+    ops[0].rows = d->m; ops[0].width = d->n; ops[0].ld = d->ldi;
+    ops[1].rows = d->n; ops[1].width = d->m; ops[1].ld = d->ldo;
+    break;
+  case KernelImpl::Vnni2Pack:
+    ops[0].rows = d->m; ops[0].width = d->n; ops[0].ld = d->ldi;
+    ops[1].rows = d->m / 2; ops[1].width = 2 * d->n; ops[1].ld = 2 * d->ldo;
+    break;
+  case KernelImpl::Vnni2Unpack:
+    ops[0].rows = d->m / 2; ops[0].width = 2 * d->n; ops[0].ld = 2 * d->ldi;
+    ops[1].rows = d->m; ops[1].width = d->n; ops[1].ld = d->ldo;
+    break;
+  default:
+    set_footprint(ops[0], mode, d->m, d->n, d->ldi);
+    ops[1].rows = d->m; ops[1].width = d->n; ops[1].ld = d->ldo;
+  }
+  // outputs with gaps (ld > width) are staged with 2-D copies so host bytes in
+  // the gaps are never touched
+  cudaStream_t stream = t_ctx.stream;
+  StagedCall sc{ops, 2, esize(dtype)};
+  stage_in(sc, stream);
+  switch (d->impl) {
+  case KernelImpl::Transpose:
+    launch_transpose(ops[0].dev, ops[1].dev, d->m, d->n, d->ldi, d->ldo, (int)esize(dtype), stream);
+    break;
+  case KernelImpl::Vnni2Pack:
+    launch_vnni2_pack(ops[0].dev, ops[1].dev, d->m, d->n, d->ldi, d->ldo, stream);
+    break;
+  case KernelImpl::Vnni2Unpack:
+    launch_vnni2_unpack(ops[0].dev, ops[1].dev, d->m, d->n, d->ldi, d->ldo, stream);
+    break;
+  default: {
+    EltwiseArgs a;
+    a.in0 = ops[0].dev; a.out = ops[1].dev;
+    a.m = d->m; a.n = d->n; a.ld0 = d->ldi; a.ldo = d->ldo;
+    a.mode0 = use_imm ? kBcastImm : mode;
+    a.imm = imm;
+    a.op = d->kind == XSMM_UNARY_ZERO ? kOpZero : d->kind == XSMM_UNARY_RELU ? kOpRelu : kOpIdentity;
+    a.dtype = dtype;
+    launch_eltwise(a, stream);
+  }
+  }
+  t_ctx.last_kernel = d->name;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  stage_out(sc, stream);
+}
+
+extern "C" void xsmm_unary_invoke(int64_t dtype, int64_t addr, void *alignedPtrIn, int64_t offsetIn,
+                                  void *alignedPtrOut, int64_t offsetOut) {
+  const KernelDesc *d = desc_of(addr, OpClass::Unary);
+  unary_invoke_impl(d, dtype, alignedPtrIn, offsetIn, false, 0.f, alignedPtrOut, offsetOut);
+}
+
+extern "C" void xsmm_unary_scalar_invoke(int64_t dtype, int64_t addr, float scalar, void *alignedPtrOut,
+                                         int64_t offsetOut) {
+  const KernelDesc *d = desc_of(addr, OpClass::Unary);
+  if (d->impl != KernelImpl::Eltwise) fail("xsmm_unary_scalar_invoke: only identity/zero/relu take a scalar input");
+  unary_invoke_impl(d, dtype, nullptr, 0, true, scalar, alignedPtrOut, offsetOut);
+}
+
+extern "C" void xsmm_binary_invoke(int64_t dtype, int64_t addr, void *alignedPtrLhs, int64_t offsetLhs,
+                                   void *alignedPtrRhs, int64_t offsetRhs, void *alignedPtrOut, int64_t offsetOut) {
+  const KernelDesc *d = desc_of(addr, OpClass::Binary);
+  if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
+  const int64_t f = d->flags;
+  const int mode0 = (f & 1) ? kBcastRow : (f & 4) ? kBcastCol : (f & 16) ? kBcastScalar : kBcastNone;
+  const int mode1 = (f & 2) ? kBcastRow : (f & 8) ? kBcastCol : (f & 32) ? kBcastScalar : kBcastNone;
+  Operand ops[3];
+  ops[0].aligned = alignedPtrLhs; ops[0].elem = elem_ptr(dtype, alignedPtrLhs, offsetLhs); ops[0].is_input = true;
+  ops[1].aligned = alignedPtrRhs; ops[1].elem = elem_ptr(dtype, alignedPtrRhs, offsetRhs); ops[1].is_input = true;
+  ops[2].aligned = alignedPtrOut; ops[2].elem = elem_ptr(dtype, alignedPtrOut, offsetOut); ops[2].is_output = true;
+  set_footprint(ops[0], mode0, d->m, d->n, d->ldi);
+  set_footprint(ops[1], mode1, d->m, d->n, d->ldi2);
+  ops[2].rows = d->m; ops[2].width = d->n; ops[2].ld = d->ldo;
+  cudaStream_t stream = t_ctx.stream;
+  StagedCall sc{ops, 3, esize(dtype)};
+  stage_in(sc, stream);
+  EltwiseArgs a;
+  a.in0 = ops[0].dev; a.in1 = ops[1].dev; a.out = ops[2].dev;
+  a.m = d->m; a.n = d->n; a.ld0 = d->ldi; a.ld1 = d->ldi2; a.ldo = d->ldo;
+  a.mode0 = mode0; a.mode1 = mode1;
+  a.op = kOpAdd + (int)(d->kind - 1);
+  a.dtype = dtype;
+  launch_eltwise(a, stream);
+  t_ctx.last_kernel = d->name;
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  stage_out(sc, stream);
+}
+
+extern "C" void xsmm_intel_amx_tile_config_invoke(int64_t dtype, int64_t addr, void *alignedPtrA, int64_t offset) {
+  (void)dtype; (void)addr; (void)alignedPtrA; (void)offset; // nothing to configure on a GPU
+}
+
+// ================================ perf timers ========================================
+
+extern "C" int64_t perf_start_timer(void) {
+  if (g_cuda_ready.load()) TPP_CUDA_CHECK(cudaDeviceSynchronize()); // earlier async work is not ours to time
+  auto timestamp = std::chrono::high_resolution_clock::now();
+  return timestamp.time_since_epoch().count();
+}
+
+extern "C" double perf_stop_timer(int64_t startTimestamp) {
+  if (g_cuda_ready.load()) TPP_CUDA_CHECK(cudaDeviceSynchronize()); // invokes are asynchronous launches
+  auto stop = std::chrono::high_resolution_clock::now();
+  std::chrono::high_resolution_clock::time_point start{std::chrono::high_resolution_clock::duration{startTimestamp}};
+  return std::chrono::duration_cast<std::chrono::duration<double>>(stop - start).count();
+}
+
+extern "C" int libxsmm_cpuid_dot_pack_factor(int datatype) {
+  // libxsmm_datatype: F32 = 1, BF16 = 2 (include/TPP/Dialect/Xsmm/XsmmEnum.td:13-18)
+  if (datatype != (int)kBF16) return 1;
+  const char *env = getenv("TPP_XSMM_VNNI");
+  if (env && env[0] == '0') return 0; // odd factors disable VNNI packing (VNNIUtils.cpp:41-43)
+  return 2;
+}
+
+// ================================ CUDA extensions =====================================
+
+extern "C" void xsmm_cuda_set_stream(void *stream) { t_ctx.stream = static_cast<cudaStream_t>(stream); }
+extern "C" void *xsmm_cuda_get_stream(void) { return t_ctx.stream; }
+
+extern "C" void xsmm_cuda_sync(void) {
+  if (g_cuda_ready.load()) TPP_CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+extern "C" int64_t xsmm_cuda_register_host(void *host, int64_t bytes, int64_t upload) {
+  ensure_cuda();
+  if (!host || bytes <= 0) return -1;
+  Mirror m;
+  m.host = static_cast<char *>(host);
+  m.bytes = (size_t)bytes;
+  m.pinned_here = cudaHostRegister(host, (size_t)bytes, cudaHostRegisterDefault) == cudaSuccess;
+  if (!m.pinned_here) cudaGetLastError(); // already pinned (e.g. by torch) or not pinnable: copies still work
+  void *dev = nullptr;
+  TPP_CUDA_CHECK(cudaMalloc(&dev, (size_t)bytes));
+  m.dev = static_cast<char *>(dev);
+  if (upload) TPP_CUDA_CHECK(cudaMemcpyAsync(m.dev, m.host, m.bytes, cudaMemcpyHostToDevice, t_ctx.stream));
+  {
+    std::unique_lock<std::shared_mutex> lock(g_mirror_mutex);
+    g_mirrors[reinterpret_cast<uintptr_t>(host)] = m;
+    g_mirror_count.store((int)g_mirrors.size());
+  }
+  return 0;
+}
+
+extern "C" int64_t xsmm_cuda_unregister_host(void *host) {
+  Mirror m;
+  {
+    std::unique_lock<std::shared_mutex> lock(g_mirror_mutex);
+    auto it = g_mirrors.find(reinterpret_cast<uintptr_t>(host));
+    if (it == g_mirrors.end()) return -1;
+    m = it->second;
+    g_mirrors.erase(it);
+    g_mirror_count.store((int)g_mirrors.size());
+  }
+  TPP_CUDA_CHECK(cudaDeviceSynchronize());
+  TPP_CUDA_CHECK(cudaFree(m.dev));
+  if (m.pinned_here) cudaHostUnregister(m.host);
+  return 0;
+}
+
+extern "C" int64_t xsmm_cuda_update_device(void *host, int64_t bytes) {
+  Mirror m;
+  if (!find_mirror(host, &m) || static_cast<char *>(host) + bytes > m.host + m.bytes) return -1;
+  TPP_CUDA_CHECK(cudaMemcpyAsync(m.dev + (static_cast<char *>(host) - m.host), host, (size_t)bytes,
+                                 cudaMemcpyHostToDevice, t_ctx.stream));
+  return 0;
+}
+
+extern "C" int64_t xsmm_cuda_update_host(void *host, int64_t bytes) {
+  Mirror m;
+  if (!find_mirror(host, &m) || static_cast<char *>(host) + bytes > m.host + m.bytes) return -1;
+  TPP_CUDA_CHECK(cudaMemcpyAsync(host, m.dev + (static_cast<char *>(host) - m.host), (size_t)bytes,
+                                 cudaMemcpyDeviceToHost, t_ctx.stream));
+  return 0;
+}
+
+extern "C" void *xsmm_cuda_device_ptr(void *host) {
+  Mirror m;
+  if (!find_mirror(host, &m)) return nullptr;
+  return m.dev + (static_cast<char *>(host) - m.host);
+}
+
+extern "C" int64_t xsmm_cuda_launch_count(void) { return g_launches.load(); }
+extern "C" const char *xsmm_cuda_last_kernel(void) { return t_ctx.last_kernel; }
+extern "C" const char *xsmm_cuda_handle_kernel(int64_t addr) {
+  const KernelDesc *d = reinterpret_cast<const KernelDesc *>(addr);
+  return (d && d->magic == kDescMagic) ? d->name : "";
+}
+extern "C" int64_t xsmm_cuda_abi_version(void) { return 1; }

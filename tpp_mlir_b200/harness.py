@@ -1,0 +1,168 @@
+"""Replay of the call sequences tpp-run's JIT-compiled ``main`` executes.
+
+tpp-run / mlir-gen cannot be built here (no LLVM/MLIR), so this module is the
+in-container caller of the C-ABI. It issues exactly the dispatch/invoke stream
+the reference pipeline emits for its benchmark workloads:
+
+* ``MlpReplay``: ``mlir-gen --kernel=const --bias --relu --float-type=bf16
+  --batch=MB --layers=... --tiles=bn,bk,bc [--vnni=2]`` lowered through
+  DefaultTppPasses - one ``xsmm_fused_brgemm_dispatch`` hoisted out of the loops
+  and, per layer, one ``xsmm_fused_brgemm_invoke`` per (iN, iK) output block
+  (tools/mlir-gen/MLIRGen.cpp:632-681, benchmarks/config/omp/mlir-bf16.json:37).
+* ``bench_loop``: tpp-run's timing protocol (lib/TPP/Runner/TppRunnerWrapper.cpp
+  :115-130, lib/TPP/Runner/MLIRBench.cpp:265-300): warm-up clamp(N/100,1,50)
+  calls, then N timed calls between perf_start_timer / perf_stop_timer, mean
+  seconds per call.
+
+Layouts (block-packed, as mlir-gen emits them):
+  input  [MB/bn][C/bc][bn][bc]     weight [K/bk][C/bc][bc][bk]
+  bias   [K/bk][bk]                output [MB/bn][K/bk][bn][bk]
+  VNNI weight: [K/bk][C/bc][bc/2][bk][2]
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+from . import xsmm
+
+
+@dataclass
+class MlpConfig:
+    batch: int = 256
+    layers: tuple = (1024, 1024, 1024, 1024)  # sizes: input, hidden..., output
+    tiles: tuple = (256, 1024, 1024)          # (bn, bk, bc); bk == bc for multi-layer nets
+    dtype: int = xsmm.BF16
+    vnni: bool = False
+    bias: bool = True
+    relu: bool = True
+
+    def __post_init__(self):
+        bn, bk, bc = self.tiles
+        if self.batch % bn:
+            raise ValueError("batch must be a multiple of the bn tile")
+        for c, k in zip(self.layers[:-1], self.layers[1:]):
+            if c % bc or k % bk:
+                raise ValueError("layer sizes must be multiples of the bc / bk tiles")
+        if len(self.layers) > 2 and bk != bc:
+            raise ValueError("multi-layer mlir-gen nets need bk == bc (layer l+1 consumes layer l's blocks)")
+
+    @property
+    def num_layers(self) -> int:
+        return len(self.layers) - 1
+
+    def flops(self) -> int:
+        """BENCH_TOTAL_FLOPS as mlir-gen counts it (MLIRGen.cpp:313-334): 2*M*N*K per
+        matmul plus M*N for the bias add and M*N for the relu."""
+        total = 0
+        for c, k in zip(self.layers[:-1], self.layers[1:]):
+            total += 2 * self.batch * c * k
+            if self.bias:
+                total += self.batch * k
+            if self.relu:
+                total += self.batch * k
+        return total
+
+    def matmul_flops(self) -> int:
+        return sum(2 * self.batch * c * k for c, k in zip(self.layers[:-1], self.layers[1:]))
+
+
+@dataclass
+class MlpReplay:
+    """Holds the dispatched handles and replays one forward pass per ``forward()``.
+
+    ``weights[l]``, ``biases[l]`` and the activation buffers are tensor-likes in the
+    block-packed layouts above (device tensors, or registered / plain host memory).
+    """
+
+    cfg: MlpConfig
+    weights: list
+    biases: list
+    acts: list                       # len == num_layers + 1; acts[0] is the input
+    handles: list = field(default_factory=list)
+    tile_cfg: list = field(default_factory=list)
+
+    def __post_init__(self):
+        cfg = self.cfg
+        bn, bk, bc = cfg.tiles
+        gemm_flags = xsmm.GEMM_FLAG_BETA_0 | (xsmm.GEMM_FLAG_ROWMAJOR_B_VNNI if cfg.vnni else 0)
+        if cfg.dtype == xsmm.BF16:
+            # IntelAMXTileConfig insertion adds these to every bf16 brgemm
+            # (lib/TPP/Transforms/IntelAMXTileConfig.cpp:32-139); ignored on the GPU.
+            gemm_flags |= xsmm.GEMM_FLAG_NO_RESET_TILECONFIG | xsmm.GEMM_FLAG_NO_SETUP_TILECONFIG
+        for _ in range(cfg.num_layers):
+            # dispatches are hoisted out of the loops (LowLevelParallelization.cpp:55-63);
+            # identical arguments return the identical handle
+            if cfg.bias or cfg.relu:
+                h = xsmm.fused_brgemm_dispatch(
+                    cfg.dtype, bn, bk, bc, bc, bk, bk, bn * bc, bc * bk, gemm_flags,
+                    xsmm.UNARY_FLAG_NONE, xsmm.UNARY_RELU if cfg.relu else xsmm.UNARY_NONE,
+                    xsmm.BINARY_FLAG_BCAST_COL_IN_0 if cfg.bias else 0,
+                    xsmm.BINARY_ADD if cfg.bias else xsmm.BINARY_NONE)
+            else:
+                h = xsmm.brgemm_dispatch(cfg.dtype, bn, bk, bc, bc, bk, bk, bn * bc, bc * bk, gemm_flags)
+            self.handles.append(h)
+            if cfg.dtype == xsmm.BF16:
+                self.tile_cfg.append(xsmm.intel_amx_tile_config_dispatch(cfg.dtype, bn, bk, bc, bc, bk, bk, bn * bc,
+                                                                         bc * bk, gemm_flags))
+
+    def forward(self):
+        cfg = self.cfg
+        bn, bk, bc = cfg.tiles
+        fused = cfg.bias or cfg.relu
+        for l in range(cfg.num_layers):
+            c, k = cfg.layers[l], cfg.layers[l + 1]
+            src, dst, w, b, h = self.acts[l], self.acts[l + 1], self.weights[l], self.biases[l], self.handles[l]
+            nb_c, nb_k = c // bc, k // bk
+            for i_n in range(cfg.batch // bn):       # scf.parallel in the reference (OpenMP threads)
+                for i_k in range(nb_k):
+                    off_a = i_n * nb_c * bn * bc
+                    off_b = i_k * nb_c * bc * bk
+                    off_c = (i_n * nb_k + i_k) * bn * bk
+                    if fused:
+                        xsmm.fused_brgemm_invoke(cfg.dtype, h, src, off_a, w, off_b, dst, off_c,
+                                                 b if cfg.bias else None, i_k * bk, nb_c)
+                    else:
+                        xsmm.brgemm_invoke(cfg.dtype, h, src, off_a, w, off_b, dst, off_c, nb_c)
+        return self.acts[-1]
+
+    @property
+    def invokes_per_forward(self) -> int:
+        cfg = self.cfg
+        bn, bk, _ = cfg.tiles
+        return sum((cfg.batch // bn) * (k // bk) for k in cfg.layers[1:])
+
+
+def bench_loop(fn, n: int):
+    """tpp-run's protocol: warm-up clamp(n/100,1,50) calls, n timed calls, mean seconds."""
+    warm = min(max(n // 100, 1), 50)
+    for _ in range(warm):
+        fn()
+    t0 = xsmm.perf_start_timer()
+    for _ in range(n):
+        fn()
+    return xsmm.perf_stop_timer(t0) / n
+
+
+# ---- layout helpers (torch; used by tests / bench to build the packed operands) ---------
+def pack_activation(x, bn, bc):
+    """[MB][C] -> [MB/bn][C/bc][bn][bc]"""
+    mb, c = x.shape
+    return x.reshape(mb // bn, bn, c // bc, bc).permute(0, 2, 1, 3).contiguous()
+
+
+def unpack_activation(xp):
+    """[MB/bn][K/bk][bn][bk] -> [MB][K]"""
+    nb, kb, bn, bk = xp.shape
+    return xp.permute(0, 2, 1, 3).reshape(nb * bn, kb * bk).contiguous()
+
+
+def pack_weight(w, bk, bc):
+    """flat [C][K] (the matmul's B operand) -> [K/bk][C/bc][bc][bk]"""
+    c, k = w.shape
+    return w.reshape(c // bc, bc, k // bk, bk).permute(2, 0, 1, 3).contiguous()
+
+
+def vnni_pack_weight(wp):
+    """[K/bk][C/bc][bc][bk] -> [K/bk][C/bc][bc/2][bk][2]"""
+    kb, cb, bc, bk = wp.shape
+    return wp.reshape(kb, cb, bc // 2, 2, bk).permute(0, 1, 2, 4, 3).contiguous()
