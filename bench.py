@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py - fused-BRGEMM MLP (bf16, 3 x 1024^2, batch 256 per GPU) through the xsmm C-ABI.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is one forward pass of the reference's benchmark workload
+(`mlir-gen --kernel=const --bias --relu --float-type=bf16 --batch=256
+--layers=1024,1024,1024,1024 --tiles=256,1024,1024`, benchmarks/config/omp/mlir-bf16.json:34-62
+with the GPU tile setting of SURVEY.md Appendix B): 3 x xsmm_fused_brgemm_invoke
+(m=256, n=1024, k=1024, bias add + ReLU fused), issued by the native replay loop
+(tpp_mlir_b200/csrc/harness/replay.cpp) exactly as tpp-run's JIT-compiled loop would.
+
+Metric = the reference's own: BENCH_TOTAL_FLOPS / mean seconds / 1e9 (benchmarks/harness/
+controller.py:187-192), FLOPs counted as mlir-gen does (MLIRGen.cpp:313-334).
+
+N > 1: the batch dimension is sharded (weak scaling: 256 rows per GPU, global batch 256*N,
+BASELINE config 5 at N=8); weights/biases are broadcast once from rank 0 over NCCL; there is no
+collective inside the timed loop. Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LAYERS = (1024, 1024, 1024, 1024)
+BATCH_PER_GPU = 256
+TILES = (256, 1024, 1024)
+L2_BYTES = 126 * 1024 * 1024
+METRIC = "fused_brgemm_mlp_bf16_3x1024_b256_gflops"
+UNIT = "GFLOP/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+# ---- clocks sampler (NVML; same counters nvidia-smi prints) -----------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index: int):
+        self.samples = []
+        self._stop = threading.Event()
+        self._thread = None
+        self.max_mhz = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nv = None
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                self.samples.append((time.perf_counter(), mhz, reasons))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
+    def start(self):
+        if self._nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thread:
+            self._thread.join(timeout=1.0)
+
+    def summary(self, t0: float, t1: float):
+        if self._nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"], "samples": 0}
+        inside = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
+        mhz = sorted(s[1] for s in inside)
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        reasons = [name for bit, name in self.REASONS.items() if bits & bit]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(inside)}
+
+
+# ---- workload ------------------------------------------------------------------------------------
+def make_host_data(seed=123):
+    """TensorInit 'normal' seed 123 (tpp-run --seed 123 --splat-to-random --init-type normal): splat
+    constants first in op order (W1,b1,W2,b2,W3,b3), then the kernel argument (the input)."""
+    import oracle
+
+    gen = oracle.TensorInit("normal", oracle.BF16, seed)
+    Ws, bs = [], []
+    for c, k in zip(LAYERS[:-1], LAYERS[1:]):
+        Ws.append(gen.fill(c, k))
+        bs.append(gen.fill(k))
+    return gen, Ws, bs
+
+
+def cpu_arm(steps, warmup, total_budget_s, verbose=False):
+    """The reference's CPU path for this workload, timed on this box's host cores.
+    kind = "port": oracle/ (libxsmm is not buildable offline). Each step is a
+    bounded sample: `rows` of the 256 batch rows through all three layers."""
+    import numpy as np
+
+    import oracle
+
+    oracle.lib(native=True)  # -march=native build for the box it is timed on
+    cores = os.cpu_count() or 1
+    oracle.set_num_threads(cores)
+    gen, Ws, bs = make_host_data()
+    x = gen.fill(BATCH_PER_GPU, LAYERS[0])
+
+    def forward(rows):
+        a = x[:rows]
+        for W, b in zip(Ws, bs):
+            y = np.empty((rows, W.shape[1]), np.uint16)
+            oracle.fused_brgemm(2, rows, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4, 0, 5, 4,
+                                1, a, W, y, b, 1)
+            a = y
+        return a
+
+    t = time.perf_counter()
+    forward(BATCH_PER_GPU)
+    t1 = time.perf_counter() - t
+    rows = BATCH_PER_GPU
+    n_calls = steps + warmup
+    if t1 * n_calls > total_budget_s:
+        rows = int(BATCH_PER_GPU * total_budget_s / (t1 * n_calls)) // 8 * 8
+        rows = max(8, min(BATCH_PER_GPU, rows))
+    for _ in range(warmup):
+        forward(rows)
+    t = time.perf_counter()
+    for _ in range(steps):
+        forward(rows)
+    dt = (time.perf_counter() - t) / steps
+    flops = sum(2 * rows * c * k + 2 * rows * k for c, k in zip(LAYERS[:-1], LAYERS[1:]))
+    return {"value": flops / dt / 1e9, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+            "sample": f"{rows} of {BATCH_PER_GPU} batch rows x 3 layers per step, {steps} steps "
+                      f"(oracle/xsmm_oracle.c, gcc -O3 -march=native -fopenmp)",
+            "ms_per_step": dt * 1e3, "rows": rows}
+
+
+def reference_main(args, rank):
+    if rank != 0:
+        return 0
+    res = cpu_arm(args.steps, args.warmup, total_budget_s=150.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (TensorInit normal, seed 123)",
+        "config": {"workload": "fused_brgemm MLP 3x(256x1024x1024)+bias+relu bf16, batch 256", "layers": list(LAYERS),
+                   "global_batch": BATCH_PER_GPU, "parallelism": "host cores (OpenMP)"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return reference_main(args, rank)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from tpp_mlir_b200 import harness, xsmm
+
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: this backend has no CPU path"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    n_gpus = world
+
+    bn, bk, bc = TILES
+    cfg = harness.MlpConfig(batch=BATCH_PER_GPU, layers=LAYERS, tiles=TILES)
+
+    # ---- data: rank 0 generates, NCCL broadcasts weights/biases; each rank owns its batch shard ----
+    def to_dev(a):
+        return torch.from_numpy(a.view(np.int16)).to(dev)
+
+    if rank == 0:
+        gen, Ws, bs = make_host_data()
+        x_all = gen.fill(BATCH_PER_GPU * n_gpus, LAYERS[0])
+        w_dev = [harness.pack_weight(to_dev(W), bk, bc) for W in Ws]
+        b_dev = [to_dev(b) for b in bs]
+        x_dev_all = to_dev(x_all)
+    else:
+        w_dev = [torch.empty(k // bk, c // bc, bc, bk, dtype=torch.int16, device=dev)
+                 for c, k in zip(LAYERS[:-1], LAYERS[1:])]
+        b_dev = [torch.empty(k, dtype=torch.int16, device=dev) for k in LAYERS[1:]]
+        x_dev_all = torch.empty(BATCH_PER_GPU * n_gpus, LAYERS[0], dtype=torch.int16, device=dev)
+    if n_gpus > 1:
+        for t in w_dev + b_dev + [x_dev_all]:
+            dist.broadcast(t, src=0)  # the one collective of this path: parameters, once, outside the timed loop
+    x_shard = x_dev_all[rank * BATCH_PER_GPU:(rank + 1) * BATCH_PER_GPU].contiguous()
+    x_packed = harness.pack_activation(x_shard, bn, bc)
+
+    # ---- rotate more bytes than the L2 holds so every step streams its operands from HBM ----
+    set_bytes = sum(w.numel() * 2 for w in w_dev) + sum(b.numel() * 2 for b in b_dev) + 4 * BATCH_PER_GPU * 1024 * 2
+    num_sets = L2_BYTES // set_bytes + 2
+    sets = []
+    for s in range(num_sets):
+        acts = [x_packed.clone()] + [torch.zeros(BATCH_PER_GPU * k, dtype=torch.int16, device=dev) for k in LAYERS[1:]]
+        sets.append((acts, [w.clone() for w in w_dev], [b.clone() for b in b_dev]))
+    replay = harness.MlpReplay(cfg, sets[0][1], sets[0][2], sets[0][0])  # dispatches (hoisted, once)
+    loop = harness.NativeMlpLoop(cfg, replay.handles, sets)
+    stream = torch.cuda.current_stream(dev)
+    xsmm.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if n_gpus > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident number ("value") --------------------------------------------------------
+    loop.run(args.warmup)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    loop.run(200)  # keep the GPU busy while the sampler gets going
+    barrier()
+    launches0 = xsmm.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    loop.run(args.steps)
+    ev1.record(stream)
+    barrier()
+    t_wall1 = time.perf_counter()
+    launches = xsmm.launch_count() - launches0
+    sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if n_gpus > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    flops_step_rank = cfg.flops()
+    value = flops_step_rank * n_gpus / (ms_per_step * 1e-3) / 1e9
+
+    # hot-L2 variant (what tpp-run measures: the same buffers every iteration), for information
+    hot = harness.NativeMlpLoop(cfg, replay.handles, sets[:1])
+    hot.run(args.warmup)
+    barrier()
+    ev0.record(stream)
+    hot.run(args.steps)
+    ev1.record(stream)
+    barrier()
+    ms_hot = ev0.elapsed_time(ev1) / args.steps
+
+    # ---- parity of what was just timed (rank-local, against the oracle on a row sample) ----------
+    import oracle
+
+    out = harness.unpack_activation(sets[0][0][-1].reshape(BATCH_PER_GPU // bn, LAYERS[-1] // bk, bn, bk))
+    got = oracle.bf16_to_f32(out[:8].cpu().numpy().view(np.uint16))
+    if rank == 0:
+        a = x_all[:8]
+        for W, b in zip(Ws, bs):
+            y = np.empty((8, W.shape[1]), np.uint16)
+            oracle.fused_brgemm(2, 8, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4, 0, 5, 4, 1,
+                                a, W, y, b, 1)
+            a = y
+        want = oracle.bf16_to_f32(a)
+        rel = float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
+    else:
+        rel = None
+
+    # ---- end-to-end through the C-ABI with HOST buffers (rank-local), H2D + D2H inside the timing ----
+    host_sets = None
+    e2e_steps = min(args.steps, 500)
+    h_w = [w.cpu().contiguous().pin_memory() for w in w_dev]
+    h_b = [b.cpu().contiguous().pin_memory() for b in b_dev]
+    h_acts = [x_packed.cpu().contiguous().pin_memory()] + [torch.zeros(BATCH_PER_GPU * k, dtype=torch.int16).pin_memory()
+                                                           for k in LAYERS[1:]]
+    for tns in h_w + h_b + h_acts:
+        xsmm.register_host(tns, upload=True)  # parameters + activation buffers mirrored once (like gpu.alloc)
+    host_sets = [(h_acts, h_w, h_b)]
+    e2e_loop = harness.NativeMlpLoop(cfg, replay.handles, host_sets)
+    e2e_loop.run_e2e(max(3, args.warmup // 5))
+    barrier()
+    t0 = time.perf_counter()
+    e2e_loop.run_e2e(e2e_steps)
+    torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if n_gpus > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    e2e_value = flops_step_rank * n_gpus / e2e_s / 1e9
+    e2e_out = oracle.bf16_to_f32(harness.unpack_activation(
+        h_acts[-1].reshape(BATCH_PER_GPU // bn, LAYERS[-1] // bk, bn, bk))[:8].numpy().view(np.uint16))
+    e2e_ok = bool(np.array_equal(e2e_out, got))
+    for tns in h_w + h_b + h_acts:
+        xsmm.unregister_host(tns)
+
+    if rank != 0:
+        if n_gpus > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    pk = peaks()
+    launches_per_step = launches / args.steps
+    flops_per_launch = flops_step_rank / launches_per_step
+    avg_launch_s = (ms / args.steps) * 1e-3 / launches_per_step
+    achieved_tflops = flops_per_launch / avg_launch_s / 1e12
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "dominant_kernel.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    cpu = None
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        c = cpu_arm(steps=10, warmup=2, total_budget_s=20.0)
+        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic (TensorInit normal, seed 123; random-init weights)",
+        "config": {"workload": "fused_brgemm MLP 3x(256x1024x1024)+bias+relu bf16, batch 256 per GPU "
+                               "(BASELINE configs[2]; configs[4] at 8 GPUs)",
+                   "layers": list(LAYERS), "tiles": list(TILES), "global_batch": BATCH_PER_GPU * n_gpus,
+                   "parallelism": f"batch-sharded x{n_gpus}, weights broadcast once over NCCL",
+                   "l2": f"rotating {num_sets} operand sets ({num_sets * set_bytes >> 20} MiB > 126 MiB L2), "
+                         "inputs larger than L2",
+                   "timing": "CUDA events on the launch stream, max over ranks",
+                   "flops_per_step": flops_step_rank * n_gpus, "matmul_flops_per_step": cfg.matmul_flops() * n_gpus},
+        "clocks": sampler.summary(t_wall0, t_wall1),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH_PER_GPU * LAYERS[0] * 2,
+                "d2h_bytes_per_step": BATCH_PER_GPU * LAYERS[-1] * 2, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+                "path": "xsmm C-ABI on registered pinned host buffers: update_device(input) -> 3 invokes -> "
+                        "update_host(output) -> sync, every step", "matches_device_run": e2e_ok},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                     "frac": achieved_tflops / pk["bf16_tflops"], "traffic": traffic,
+                     "kernel": xsmm.handle_kernel(replay.handles[0]), "peak_source": pk["source"] + ", burst",
+                     "flops_per_launch": flops_per_launch, "avg_launch_us": avg_launch_s * 1e6},
+        "cpu_baseline": cpu,
+        "extra": {"ms_per_step_hot_l2": ms_hot, "gflops_hot_l2": flops_step_rank * n_gpus / (ms_hot * 1e-3) / 1e9,
+                  "parity_rel_err_vs_oracle": rel, "kernel": xsmm.handle_kernel(replay.handles[0])},
+    }
+    print(json.dumps(line))
+    if n_gpus > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

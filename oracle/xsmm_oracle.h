@@ -18,7 +18,7 @@
  *   lib/TPP/Dialect/Xsmm/XsmmUtils.cpp:90-252       ld / broadcast rules
  *   lib/TPP/Transforms/Utils/VNNIUtils.cpp:75-78    VNNI layouts
  * and is pinned against the known-answer vectors of test/Integration/xsmm-*.mlir
- * and test/BF16/Integration/*.mlir (tests/test_oracle_golden.py).
+ * and the .mlir files under test/BF16/Integration (tests/test_oracle_golden.py).
  *
  * Everything is the ROW-MAJOR view that tpp-mlir passes (the shim's swap to
  * libxsmm's column-major view is an implementation detail of the reference).

@@ -257,7 +257,8 @@ def test_brgemm_bf16_padded_leading_dims(shape, dev, orc):
 @pytest.mark.parametrize("shape", [(256, 1024, 1024, 1), (64, 64, 32, 8), (129, 65, 72, 2)])
 def test_fused_brgemm_bf16(fused, shape, dev, orc):
     m, n, k, batch = shape
-    g, o, kern = run_brgemm_pair(dev, orc, BF16, m, n, k, batch, fused=fused, seed=5)
+    ld = {} if n % 8 == 0 else dict(ldb=n + 8 - n % 8, ldc=n + 8 - n % 8)  # TMA strides are multiples of 16 B
+    g, o, kern = run_brgemm_pair(dev, orc, BF16, m, n, k, batch, fused=fused, seed=5, **ld)
     assert kern.startswith("brgemm_tc_bf16"), kern
     assert_close(BF16, g, o)
     if fused[0] == 5:

@@ -78,5 +78,26 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return so
 
 
+REPLAY_NAME = "libtpp_replay.so"
+
+
+def replay_path() -> str:
+    return os.path.join(LIBDIR, REPLAY_NAME)
+
+
+def build_replay(force: bool = False) -> str:
+    """The native tpp-run stand-in loop (csrc/harness/replay.cpp): plain C++, calls only the C-ABI."""
+    src = os.path.join(CSRC, "harness", "replay.cpp")
+    so = replay_path()
+    lib = build()
+    if force or _stale(so, [src, lib, os.path.join(ROOT, "include", "tpp_xsmm_abi.h")]):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        cmd = [cxx, "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-I", os.path.join(ROOT, "include"),
+               src, "-o", so, "-L", LIBDIR, "-ltpp_xsmm_runner_utils", "-Wl,-rpath,$ORIGIN"]
+        subprocess.run(cmd, check=True)
+    return so
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
+    print(build_replay(force="--force" in sys.argv))

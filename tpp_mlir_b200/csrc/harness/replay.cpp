@@ -1,0 +1,56 @@
+// replay.cpp - native stand-in for the loop tpp-run's JIT-compiled main() executes.
+//
+// tpp-run lowers the benchmark kernel to LLVM IR whose hot loop is a plain native loop of
+// func.call @xsmm_fused_brgemm_invoke(...) (lib/TPP/Runner/MLIRBench.cpp
+// :265-295 wraps it in perf.bench). LLVM/MLIR are not available here, so this file is that loop
+// written by hand: it calls ONLY the C-ABI of include/tpp_xsmm_abi.h, exactly as JIT'd code
+// would, for the block-packed MLP that `mlir-gen --kernel=const --bias --relu` generates
+// (tools/mlir-gen/MLIRGen.cpp:632-681; offsets per SURVEY.md Appendix B).
+#include <cstdint>
+
+#include "tpp_xsmm_abi.h"
+
+extern "C" {
+
+struct TppMlpSet {       // one set of buffers (several sets are rotated to defeat the L2)
+  void *acts[9];         // acts[0] = input, acts[l+1] = output of layer l
+  void *weights[8];
+  void *biases[8];
+};
+
+// Runs `steps` forward passes; step s uses sets[s % num_sets]. Layer l: for every (iN, iK)
+// output block one fused_brgemm invoke with numBatches = C/bc (the scf.parallel loop nest of
+// the reference, serialised on one CUDA stream).
+__attribute__((visibility("default")))
+void tpp_replay_mlp(int64_t dtype, int64_t num_layers, const int64_t *handles, const int64_t *layer_sizes,
+                    int64_t batch, int64_t bn, int64_t bk, int64_t bc, const TppMlpSet *sets, int64_t num_sets,
+                    int64_t first_step, int64_t steps, int64_t has_bias) {
+  for (int64_t s = 0; s < steps; ++s) {
+    const TppMlpSet &set = sets[(first_step + s) % num_sets];
+    for (int64_t l = 0; l < num_layers; ++l) {
+      const int64_t c = layer_sizes[l], k = layer_sizes[l + 1];
+      const int64_t nb_c = c / bc, nb_k = k / bk;
+      for (int64_t in = 0; in < batch / bn; ++in)
+        for (int64_t ik = 0; ik < nb_k; ++ik)
+          xsmm_fused_brgemm_invoke(dtype, handles[l], set.acts[l], in * nb_c * bn * bc, set.weights[l],
+                                   ik * nb_c * bc * bk, set.acts[l + 1], (in * nb_k + ik) * bn * bk,
+                                   has_bias ? set.biases[l] : nullptr, ik * bk, nb_c);
+    }
+  }
+}
+
+// One forward on host buffers that were registered with xsmm_cuda_register_host: upload the
+// step's input, run the layers on the mirrors, download the step's output, wait for it.
+__attribute__((visibility("default")))
+void tpp_replay_mlp_e2e(int64_t dtype, int64_t num_layers, const int64_t *handles, const int64_t *layer_sizes,
+                        int64_t batch, int64_t bn, int64_t bk, int64_t bc, const TppMlpSet *set, int64_t steps,
+                        int64_t has_bias, int64_t elem_size) {
+  for (int64_t s = 0; s < steps; ++s) {
+    xsmm_cuda_update_device(set->acts[0], batch * layer_sizes[0] * elem_size);
+    tpp_replay_mlp(dtype, num_layers, handles, layer_sizes, batch, bn, bk, bc, set, 1, 0, 1, has_bias);
+    xsmm_cuda_update_host(set->acts[num_layers], batch * layer_sizes[num_layers] * elem_size);
+    xsmm_cuda_sync();
+  }
+}
+
+} // extern "C"

@@ -166,3 +166,76 @@ def vnni_pack_weight(wp):
     """[K/bk][C/bc][bc][bk] -> [K/bk][C/bc][bc/2][bk][2]"""
     kb, cb, bc, bk = wp.shape
     return wp.reshape(kb, cb, bc // 2, 2, bk).permute(0, 1, 2, 4, 3).contiguous()
+
+
+# ---- native replay loop (csrc/harness/replay.cpp) ---------------------------------------------
+import ctypes as _ct  # noqa: E402
+
+
+class _TppMlpSet(_ct.Structure):
+    _fields_ = [("acts", _ct.c_void_p * 9), ("weights", _ct.c_void_p * 8), ("biases", _ct.c_void_p * 8)]
+
+
+_replay_lib = None
+
+
+def replay_lib():
+    """libtpp_replay.so: the hand-written equivalent of tpp-run's JIT-compiled hot loop. Pure host
+    C++ that calls only the C-ABI; Python stays out of the timed loop."""
+    global _replay_lib
+    if _replay_lib is None:
+        import os
+
+        from . import _build
+
+        xsmm.LIB  # the ABI library must be loaded (RTLD_GLOBAL) first
+        path = _build.replay_path()
+        if not os.path.exists(path):
+            path = _build.build_replay()
+        lib = _ct.CDLL(path)
+        i64, p = _ct.c_int64, _ct.c_void_p
+        lib.tpp_replay_mlp.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, i64, i64, i64]
+        lib.tpp_replay_mlp.restype = None
+        lib.tpp_replay_mlp_e2e.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, i64, i64]
+        lib.tpp_replay_mlp_e2e.restype = None
+        _replay_lib = lib
+    return _replay_lib
+
+
+class NativeMlpLoop:
+    """K forward passes of an MlpReplay-style net issued from native code.
+
+    ``sets`` is a list of (acts, weights, biases) tuples of tensor-likes; consecutive steps rotate
+    through them (bench.py uses more bytes than the L2 holds)."""
+
+    def __init__(self, cfg: MlpConfig, handles, sets):
+        self.cfg = cfg
+        n = cfg.num_layers
+        assert n <= 8
+        self._handles = (_ct.c_int64 * n)(*handles)
+        self._sizes = (_ct.c_int64 * (n + 1))(*cfg.layers)
+        self._sets = (_TppMlpSet * len(sets))()
+        self._keep = sets
+        for s, (acts, weights, biases) in zip(self._sets, sets):
+            for i, a in enumerate(acts):
+                s.acts[i] = xsmm._ptr(a)
+            for i, w in enumerate(weights):
+                s.weights[i] = xsmm._ptr(w)
+            for i, b in enumerate(biases):
+                s.biases[i] = xsmm._ptr(b)
+        self.num_sets = len(sets)
+        self._step = 0
+
+    def run(self, steps: int) -> None:
+        cfg = self.cfg
+        bn, bk, bc = cfg.tiles
+        replay_lib().tpp_replay_mlp(cfg.dtype, cfg.num_layers, self._handles, self._sizes, cfg.batch, bn, bk, bc,
+                                    self._sets, self.num_sets, self._step, steps, 1 if cfg.bias else 0)
+        self._step += steps
+
+    def run_e2e(self, steps: int, elem_size: int = 2) -> None:
+        """Host buffers registered with xsmm.register_host: per step H2D(input), layers, D2H(output), sync."""
+        cfg = self.cfg
+        bn, bk, bc = cfg.tiles
+        replay_lib().tpp_replay_mlp_e2e(cfg.dtype, cfg.num_layers, self._handles, self._sizes, cfg.batch, bn, bk, bc,
+                                        self._sets, steps, 1 if cfg.bias else 0, elem_size)
