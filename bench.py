@@ -272,6 +272,7 @@ def main():
     t_wall0 = time.perf_counter()
     ev0.record(stream)
     loop.run(args.steps)
+    t_issue = time.perf_counter() - t_wall0   # host time to issue all launches (no sync yet)
     ev1.record(stream)
     barrier()
     t_wall1 = time.perf_counter()
@@ -386,6 +387,7 @@ def main():
                      "flops_per_launch": flops_per_launch, "avg_launch_us": avg_launch_s * 1e6},
         "cpu_baseline": cpu,
         "extra": {"ms_per_step_hot_l2": ms_hot, "gflops_hot_l2": flops_step_rank * n_gpus / (ms_hot * 1e-3) / 1e9,
+                  "host_issue_us_per_launch": t_issue / max(launches, 1) * 1e6,
                   "parity_rel_err_vs_oracle": rel, "kernel": xsmm.handle_kernel(replay.handles[0])},
     }
     print(json.dumps(line))

@@ -85,27 +85,28 @@ static inline void st(int64_t dtype, void *p, int64_t idx, float v) {
 static inline float relu(float x) { return x > 0.0f ? x : 0.0f; }
 
 /* One block of rows [i0,i1): acc[i][j] over all batches and k, f32. */
-#define XO_ROWBLK 8
+#define XO_ROWBLK 16
+#define XO_COLBLK 128
 
-static void brgemm_rows_f32acc(int64_t dtype, int64_t i0, int64_t i1, int64_t n,
-                               int64_t k, int64_t lda, int64_t ldb, int64_t ldc,
-                               int64_t stride_a, int64_t stride_b, int vnni,
-                               int beta0, const void *A, const void *B,
+static void brgemm_rows_f32acc(int64_t dtype, int64_t i0, int64_t i1, int64_t j0,
+                               int64_t j1, int64_t k, int64_t lda, int64_t ldb,
+                               int64_t ldc, int64_t stride_a, int64_t stride_b,
+                               int vnni, int beta0, const void *A, const void *B,
                                const void *C, int64_t batch, float *acc,
                                float *brow) {
-  const int64_t rows = i1 - i0;
+  const int64_t rows = i1 - i0, n = j1 - j0;
   for (int64_t r = 0; r < rows; ++r)
     for (int64_t j = 0; j < n; ++j)
-      acc[r * n + j] = beta0 ? 0.0f : ld(dtype, C, (i0 + r) * ldc + j);
+      acc[r * n + j] = beta0 ? 0.0f : ld(dtype, C, (i0 + r) * ldc + j0 + j);
   for (int64_t b = 0; b < batch; ++b) {
     for (int64_t p = 0; p < k; ++p) {
-      /* expand B row p of batch b into f32 once per row block */
+      /* expand columns [j0,j1) of B row p of batch b into f32 once per tile */
       if (dtype == XO_F32) {
-        const float *Bp = (const float *)B + b * stride_b + p * ldb;
+        const float *Bp = (const float *)B + b * stride_b + p * ldb + j0;
         for (int64_t j = 0; j < n; ++j)
           brow[j] = Bp[j];
       } else if (!vnni) {
-        const uint16_t *Bp = (const uint16_t *)B + b * stride_b + p * ldb;
+        const uint16_t *Bp = (const uint16_t *)B + b * stride_b + p * ldb + j0;
         for (int64_t j = 0; j < n; ++j) {
           uint32_t u = ((uint32_t)Bp[j]) << 16;
           memcpy(&brow[j], &u, 4);
@@ -113,8 +114,8 @@ static void brgemm_rows_f32acc(int64_t dtype, int64_t i0, int64_t i1, int64_t n,
       } else {
         /* B[b][p/2][j][p%2], ldb already divided by the VNNI factor
          * (ConvertLinalgToXsmm.cpp:1143-1148) */
-        const uint16_t *Bp =
-            (const uint16_t *)B + b * stride_b + (p / 2) * ldb * 2 + (p % 2);
+        const uint16_t *Bp = (const uint16_t *)B + b * stride_b +
+                             ((p / 2) * ldb + j0) * 2 + (p % 2);
         for (int64_t j = 0; j < n; ++j) {
           uint32_t u = ((uint32_t)Bp[j * 2]) << 16;
           memcpy(&brow[j], &u, 4);
@@ -183,39 +184,48 @@ void xo_fused_brgemm(int64_t dtype, int64_t m, int64_t n, int64_t k,
     return;
   }
 
+  /* tiles of XO_ROWBLK rows x XO_COLBLK columns; each output element is owned by
+   * exactly one task and summed in a fixed order, so the thread count never
+   * changes a result. */
   const int64_t nblk = (m + XO_ROWBLK - 1) / XO_ROWBLK;
+  const int64_t ncb = (n + XO_COLBLK - 1) / XO_COLBLK;
 #ifdef _OPENMP
   int nthr = xo_num_threads();
 #pragma omp parallel num_threads(nthr)
 #endif
   {
-    float *acc = (float *)malloc(sizeof(float) * XO_ROWBLK * (size_t)n);
-    float *brow = (float *)malloc(sizeof(float) * (size_t)n);
+    float *acc = (float *)malloc(sizeof(float) * XO_ROWBLK * XO_COLBLK);
+    float *brow = (float *)malloc(sizeof(float) * XO_COLBLK);
 #ifdef _OPENMP
-#pragma omp for schedule(static)
+#pragma omp for schedule(static) collapse(2)
 #endif
     for (int64_t blk = 0; blk < nblk; ++blk) {
-      const int64_t i0 = blk * XO_ROWBLK;
-      const int64_t i1 = i0 + XO_ROWBLK < m ? i0 + XO_ROWBLK : m;
-      brgemm_rows_f32acc(dtype, i0, i1, n, k, lda, ldb, ldc, stride_a, stride_b,
-                         vnni, beta0, A, B, C, batch, acc, brow);
-      for (int64_t i = i0; i < i1; ++i)
-        for (int64_t j = 0; j < n; ++j) {
-          float v = acc[(i - i0) * n + j];
-          if (has_bin) {
-            float d = (binary_flags & 4)    ? ld(dtype, D, j)
-                      : (binary_flags & 1)  ? ld(dtype, D, i)
-                      : (binary_flags & 16) ? ld(dtype, D, 0)
-                                            : ld(dtype, D, i * ldc + j);
-            v = binary_kind == 1   ? v + d
-                : binary_kind == 2 ? v * d
-                : binary_kind == 3 ? v - d
-                                   : v / d;
+      for (int64_t cb = 0; cb < ncb; ++cb) {
+        const int64_t i0 = blk * XO_ROWBLK;
+        const int64_t i1 = i0 + XO_ROWBLK < m ? i0 + XO_ROWBLK : m;
+        const int64_t j0 = cb * XO_COLBLK;
+        const int64_t j1 = j0 + XO_COLBLK < n ? j0 + XO_COLBLK : n;
+        const int64_t w = j1 - j0;
+        brgemm_rows_f32acc(dtype, i0, i1, j0, j1, k, lda, ldb, ldc, stride_a,
+                           stride_b, vnni, beta0, A, B, C, batch, acc, brow);
+        for (int64_t i = i0; i < i1; ++i)
+          for (int64_t j = j0; j < j1; ++j) {
+            float v = acc[(i - i0) * w + (j - j0)];
+            if (has_bin) {
+              float d = (binary_flags & 4)    ? ld(dtype, D, j)
+                        : (binary_flags & 1)  ? ld(dtype, D, i)
+                        : (binary_flags & 16) ? ld(dtype, D, 0)
+                                              : ld(dtype, D, i * ldc + j);
+              v = binary_kind == 1   ? v + d
+                  : binary_kind == 2 ? v * d
+                  : binary_kind == 3 ? v - d
+                                     : v / d;
+            }
+            if (has_relu)
+              v = relu(v);
+            st(dtype, C, i * ldc + j, v);
           }
-          if (has_relu)
-            v = relu(v);
-          st(dtype, C, i * ldc + j, v);
-        }
+      }
     }
     free(acc);
     free(brow);

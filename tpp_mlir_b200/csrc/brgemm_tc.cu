@@ -5,8 +5,8 @@
 // C = relu(C_in*beta + sum_b A_b*B_b + bias)) for bf16 operands.
 //
 // Design (B200-first, not a translation of the CPU microkernel):
-//   * one CTA per 128 x BLOCK_N output tile; the WHOLE reduction - every k-block
-//     of every batch element - accumulates into ONE f32 accumulator in TMEM
+//   * one CTA per 128 x BLOCK_N output tile; the reduction - every k-block of
+//     every batch element - accumulates into ONE f32 accumulator in TMEM
 //     ("batch-reduce" == one TMEM tile, many TMA stages);
 //   * A (row-major [b][m][k], K-major for UMMA) and B (row-major [b][k][n],
 //     MN-major for UMMA) are fetched by TMA through 3-D tensor maps
@@ -17,7 +17,16 @@
 //     elected thread) + TMEM allocator, warps 2..5 = epilogue (tcgen05.ld ->
 //     beta / binary(D) / relu in f32 -> one RNE rounding -> 16-byte stores);
 //   * full/empty mbarrier ring of STAGES smem slots between TMA and MMA,
-//     tcgen05.commit releases a slot and finally signals the epilogue.
+//     tcgen05.commit releases a slot and finally signals the epilogue;
+//   * when the output has too few tiles to fill 148 SMs (the 256 x 1024 MLP
+//     layer has 32), the (batch x k) reduction is split across a thread-block
+//     CLUSTER of 2 or 4 CTAs; partial accumulators are exchanged through
+//     distributed shared memory (each CTA owns BLOCK_N/S columns of the tile,
+//     receives the other CTAs' partials with st.shared::cluster pushes) and the
+//     owner applies the fused epilogue - no HBM round trip, no second kernel;
+//   * programmatic dependent launch: everything up to the first global access
+//     (barrier init, TMEM alloc, tensor-map prefetch) overlaps the previous
+//     kernel's tail (griddepcontrol).
 #include <cuda.h>
 
 #include <mutex>
@@ -36,6 +45,7 @@ constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;      // 16 KiB
 constexpr int B_CHUNK_BYTES = BLOCK_K * 64 * 2;           // 64 k-rows x 128 bytes = 8 KiB
 constexpr int NUM_THREADS = 192;
+constexpr int RECV_BYTES = BLOCK_M * 64 * 4;              // split-K exchange: S slots x 128 rows x (64/S) f32 = 32 KiB
 
 struct TcParams {
   void *C;
@@ -43,6 +53,7 @@ struct TcParams {
   int64_t m, n, ldc;
   int32_t k_iters;      // ceil(k / BLOCK_K)
   int32_t total_iters;  // batch * k_iters
+  int32_t split_k;      // cluster size along the reduction (1, 2 or 4)
   int32_t beta0, bin_kind, bin_mode, relu;
   int32_t c_vec_ok;     // C base 16B aligned and ldc % 8 == 0
 };
@@ -52,8 +63,134 @@ template <int BLOCK_N> struct SmemLayout {
   static constexpr int kStageBytes = A_STAGE_BYTES + kBChunks * B_CHUNK_BYTES;
 };
 
-template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// Fused epilogue on NC consecutive f32 accumulator columns of one row: (+C) -> binary(D) -> relu -> bf16.
+template <int NC>
+__device__ __forceinline__ void epilogue_store(float (&v)[NC], const TcParams &p, int64_t row, int64_t col0) {
+  const uint16_t *Dp = static_cast<const uint16_t *>(p.D);
+  uint16_t *crow = static_cast<uint16_t *>(p.C) + row * p.ldc + col0;
+  const bool full = (col0 + NC <= p.n);
+  if (!p.beta0) {
+    if (full && p.c_vec_ok) {
+#pragma unroll
+      for (int g = 0; g < NC / 8; ++g) {
+        const uint4 cv = *reinterpret_cast<const uint4 *>(crow + g * 8);
+        const uint32_t w[4] = {cv.x, cv.y, cv.z, cv.w};
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          v[g * 8 + 2 * h] += __uint_as_float(w[h] << 16);
+          v[g * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xffff0000u);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < NC; ++e)
+        if (col0 + e < p.n) v[e] += bf16_bits_to_f32(crow[e]);
+    }
+  }
+  if (p.bin_kind) {
+    if (p.bin_mode == kBcastCol && p.bin_kind == 1 && full) {   // the MLP case: bias vector add
+#pragma unroll
+      for (int e = 0; e < NC; ++e) v[e] += bf16_bits_to_f32(__ldg(Dp + col0 + e));
+    } else {
+#pragma unroll
+      for (int e = 0; e < NC; ++e) {
+        if (col0 + e < p.n) {
+          const int64_t di = p.bin_mode == kBcastCol   ? col0 + e
+                             : p.bin_mode == kBcastRow ? row
+                             : p.bin_mode == kBcastNone ? row * p.ldc + col0 + e
+                                                        : 0;
+          const float d = bf16_bits_to_f32(__ldg(Dp + di));
+          v[e] = p.bin_kind == 1 ? v[e] + d : p.bin_kind == 2 ? v[e] * d : p.bin_kind == 3 ? v[e] - d : v[e] / d;
+        }
+      }
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int e = 0; e < NC; ++e) v[e] = relu_f32(v[e]);
+  }
+  if (full && p.c_vec_ok) {
+#pragma unroll
+    for (int g = 0; g < NC / 8; ++g) {
+      uint4 o;
+      o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
+      o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
+      o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
+      o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
+      *reinterpret_cast<uint4 *>(crow + g * 8) = o;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < NC; ++e)
+      if (col0 + e < p.n) crow[e] = f32_to_bf16_bits(v[e]);
+  }
+}
+
+// Split-K exchange (BLOCK_N == 64): cluster rank r owns columns [r*NC, (r+1)*NC) of the tile, NC = 64 / S.
+// Every CTA pushes the slices it does not own into the owner's receive buffer, slot = sender rank:
+//   recv[slot][row][NC f32], 16-byte chunks XOR-swizzled by the row so that both the remote stores and
+//   the owner's loads are bank-conflict free.
+template <int NC>
+__device__ __forceinline__ uint32_t recv_offset(int slot, int row, int chunk) {
+  constexpr int NCH = NC / 4;                       // 16-byte chunks per row
+  const int sw = NCH == 4 ? ((row >> 1) & 3) : (row & (NCH - 1));
+  return static_cast<uint32_t>(slot * (BLOCK_M * NC * 4) + row * (NC * 4) + ((chunk ^ sw) << 4));
+}
+
+template <int NC>
+__device__ __forceinline__ void splitk_epilogue(const TcParams &p, uint32_t tmem_acc, uint32_t recv_base, int q,
+                                                int lane, int64_t m0, int64_t n0, uint32_t rank, bool has_acc) {
+  constexpr int S = 64 / NC;
+  constexpr int NCH = NC / 4;
+  const int row_in_tile = q * 32 + lane;
+  float own[NC];
+#pragma unroll
+  for (int c = 0; c < 64; c += 32) {
+    uint32_t r[32];
+    if (has_acc) {
+      ptx::tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      ptx::tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) r[e] = 0u;
+    }
+#pragma unroll
+    for (int part = 0; part < 32 / NC; ++part) {     // the 32-column chunk holds 32/NC owner slices of NC columns
+      const uint32_t owner = static_cast<uint32_t>(c / NC + part);
+      if (owner == rank) {
+#pragma unroll
+        for (int e = 0; e < NC; ++e) own[e] = __uint_as_float(r[part * NC + e]);
+      } else {
+        const uint32_t remote = ptx::mapa(recv_base, owner);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+          ptx::st_cluster_v4(remote + recv_offset<NC>((int)rank, row_in_tile, j),
+                             __uint_as_float(r[part * NC + 4 * j]), __uint_as_float(r[part * NC + 4 * j + 1]),
+                             __uint_as_float(r[part * NC + 4 * j + 2]), __uint_as_float(r[part * NC + 4 * j + 3]));
+      }
+    }
+  }
+  // all partials of this cluster have landed in their owners' shared memory
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    if (static_cast<uint32_t>(s) == rank) continue;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float4 t;
+      const uint32_t a = recv_base + recv_offset<NC>(s, row_in_tile, j);
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(a));
+      own[4 * j] += t.x; own[4 * j + 1] += t.y; own[4 * j + 2] += t.z; own[4 * j + 3] += t.w;
+    }
+  }
+  const int64_t row = m0 + row_in_tile;
+  const int64_t col0 = n0 + (int64_t)rank * NC;
+  if (row < p.m && col0 < p.n) epilogue_store<NC>(own, p, row, col0);
+}
+
+template <int BLOCK_N, int STAGES, bool SPLITK>
+__global__ void __launch_bounds__(NUM_THREADS, SPLITK ? 2 : 1)
 brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   using L = SmemLayout<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -61,7 +198,8 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + STAGES * A_STAGE_BYTES;
-  const uint32_t bar_base = smem_b + STAGES * L::kBChunks * B_CHUNK_BYTES;
+  const uint32_t recv_base = smem_b + STAGES * L::kBChunks * B_CHUNK_BYTES;     // SPLITK only
+  const uint32_t bar_base = recv_base + (SPLITK ? RECV_BYTES : 0);
   const uint32_t full_bar = bar_base;                 // STAGES x 8 bytes
   const uint32_t empty_bar = bar_base + STAGES * 8;   // STAGES x 8 bytes
   const uint32_t accum_bar = bar_base + 2 * STAGES * 8;
@@ -71,6 +209,16 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+
+  // this CTA's share of the (batch x k-block) reduction
+  uint32_t rank = 0;
+  int32_t it_begin = 0, it_end = p.total_iters;
+  if constexpr (SPLITK) {
+    rank = ptx::cluster_ctarank();
+    it_begin = (int32_t)(((int64_t)p.total_iters * rank) / p.split_k);
+    it_end = (int32_t)(((int64_t)p.total_iters * (rank + 1)) / p.split_k);
+  }
+  const int32_t num_iters = it_end - it_begin;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -91,12 +239,18 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::tc_fence_after_sync();
   const uint32_t tmem_acc = *tmem_slot_ptr;
 
+  // PDL: let the next kernel in the stream start its own prologue, then wait until everything the
+  // previous kernel wrote (our A operand is its C) is visible before the first global access.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int32_t it = 0; it < p.total_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
+      for (int32_t i = 0; i < num_iters; ++i) {
+        const int32_t it = it_begin + i;
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
         ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
         ptx::mbar_arrive_expect_tx(full_bar + 8 * s, L::kStageBytes);
         const int32_t b = it / p.k_iters, kb = it - b * p.k_iters;
@@ -111,9 +265,9 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, BLOCK_N, /*A K-major*/ 0, /*B MN-major*/ 1);
-      for (int32_t it = 0; it < p.total_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
+      for (int32_t i = 0; i < num_iters; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
         ptx::mbar_wait(full_bar + 8 * s, ph);
         ptx::tc_fence_after_sync();
         const uint32_t a_addr = smem_a + s * A_STAGE_BYTES;
@@ -125,91 +279,55 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // B: MN-major, 64-column atoms B_CHUNK_BYTES apart (LBO), 8-k-row groups 1024 B apart (SBO);
           // one UMMA_K slice = 16 k-rows = 2048 B
           const uint64_t db = ptx::umma_smem_desc_sw128(b_addr + kk * (UMMA_K * 128), B_CHUNK_BYTES, 1024);
-          ptx::umma_bf16(tmem_acc, da, db, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          ptx::umma_bf16(tmem_acc, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
         }
         ptx::umma_commit(empty_bar + 8 * s);   // frees the slot when these MMAs retire
       }
-      ptx::umma_commit(accum_bar);             // accumulator complete
+      if (num_iters > 0) ptx::umma_commit(accum_bar);   // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
     const int q = warp & 3;
-    const int64_t row = (int64_t)m0 + q * 32 + lane;
-    if (p.total_iters > 0) {
+    if (num_iters > 0) {
       ptx::mbar_wait(accum_bar, 0);
       ptx::tc_fence_after_sync();
     }
-    const uint16_t *Dp = static_cast<const uint16_t *>(p.D);
-    uint16_t *Cp = static_cast<uint16_t *>(p.C);
+    if constexpr (!SPLITK) {
+      const int64_t row = (int64_t)m0 + q * 32 + lane;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 32) {
-      const int64_t col0 = (int64_t)n0 + c;
-      if (col0 >= p.n) break;   // warp-uniform
-      uint32_t r[32];
-      if (p.total_iters > 0) {
-        ptx::tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c, r);
-        ptx::tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) r[e] = 0u;
-      }
-      if (row < p.m) {
-        uint16_t *crow = Cp + row * p.ldc + col0;
-        const bool full = (col0 + 32 <= p.n);
-        float v[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
-        if (!p.beta0) {
-          if (full && p.c_vec_ok) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint4 cv = *reinterpret_cast<const uint4 *>(crow + g * 8);
-              const uint32_t w[4] = {cv.x, cv.y, cv.z, cv.w};
-#pragma unroll
-              for (int h = 0; h < 4; ++h) {
-                v[g * 8 + 2 * h] += __uint_as_float(w[h] << 16);
-                v[g * 8 + 2 * h + 1] += __uint_as_float(w[h] & 0xffff0000u);
-              }
-            }
-          } else {
-#pragma unroll
-            for (int e = 0; e < 32; ++e)
-              if (col0 + e < p.n) v[e] += bf16_bits_to_f32(crow[e]);
-          }
-        }
-        if (p.bin_kind) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            if (col0 + e < p.n) {
-              const int64_t di = p.bin_mode == kBcastCol   ? col0 + e
-                                 : p.bin_mode == kBcastRow ? row
-                                 : p.bin_mode == kBcastNone ? row * p.ldc + col0 + e
-                                                            : 0;
-              const float d = bf16_bits_to_f32(__ldg(Dp + di));
-              v[e] = p.bin_kind == 1 ? v[e] + d : p.bin_kind == 2 ? v[e] * d : p.bin_kind == 3 ? v[e] - d : v[e] / d;
-            }
-          }
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = relu_f32(v[e]);
-        }
-        if (full && p.c_vec_ok) {
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint4 o;
-            o.x = pack_bf16x2(v[g * 8 + 0], v[g * 8 + 1]);
-            o.y = pack_bf16x2(v[g * 8 + 2], v[g * 8 + 3]);
-            o.z = pack_bf16x2(v[g * 8 + 4], v[g * 8 + 5]);
-            o.w = pack_bf16x2(v[g * 8 + 6], v[g * 8 + 7]);
-            *reinterpret_cast<uint4 *>(crow + g * 8) = o;
-          }
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        const int64_t col0 = (int64_t)n0 + c;
+        if (col0 >= p.n) break;   // warp-uniform
+        uint32_t r[32];
+        if (num_iters > 0) {
+          ptx::tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+          ptx::tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (col0 + e < p.n) crow[e] = f32_to_bf16_bits(v[e]);
+          for (int e = 0; e < 32; ++e) r[e] = 0u;
+        }
+        if (row < p.m) {
+          float v[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+          epilogue_store<32>(v, p, row, col0);
         }
       }
+    }
+  }
+
+  if constexpr (SPLITK) {
+    // every thread of every CTA in the cluster reaches the cluster barrier inside / next to the exchange
+    if (warp >= 2) {
+      const int q = warp & 3;
+      if (p.split_k == 4)
+        splitk_epilogue<16>(p, tmem_acc, recv_base, q, lane, m0, n0, rank, num_iters > 0);
+      else
+        splitk_epilogue<32>(p, tmem_acc, recv_base, q, lane, m0, n0, rank, num_iters > 0);
+    } else {
+      __syncwarp();   // lane 0 ran the producer / MMA loop; the cluster barrier is warp-aligned
+      ptx::cluster_arrive();
+      ptx::cluster_wait();
     }
   }
 
@@ -259,20 +377,38 @@ bool encode_map(CUtensorMap *map, const void *base, uint64_t inner, uint64_t row
   return r == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N, int STAGES> constexpr int smem_bytes() {
-  return STAGES * SmemLayout<BLOCK_N>::kStageBytes + (2 * STAGES + 1) * 8 + 16 + 1024;
+template <int BLOCK_N, int STAGES, bool SPLITK> constexpr int smem_bytes() {
+  return STAGES * SmemLayout<BLOCK_N>::kStageBytes + (SPLITK ? RECV_BYTES : 0) + (2 * STAGES + 1) * 8 + 16 + 1024;
 }
 
-template <int BLOCK_N, int STAGES>
+template <int BLOCK_N, int STAGES, bool SPLITK>
 void launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, dim3 grid, cudaStream_t stream) {
-  constexpr int smem = smem_bytes<BLOCK_N, STAGES>();
+  constexpr int smem = smem_bytes<BLOCK_N, STAGES, SPLITK>();
   static std::once_flag once;
   std::call_once(once, [] {
-    TPP_CUDA_CHECK(cudaFuncSetAttribute(brgemm_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        smem));
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(brgemm_tc_kernel<BLOCK_N, STAGES, SPLITK>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   });
-  brgemm_tc_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, smem, stream>>>(tmA, tmB, p);
-  TPP_CUDA_CHECK(cudaGetLastError());
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  int na = 0;
+  attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[na].val.programmaticStreamSerializationAllowed = 1;
+  ++na;
+  if (SPLITK) {
+    attrs[na].id = cudaLaunchAttributeClusterDimension;
+    attrs[na].val.clusterDim.x = 1;
+    attrs[na].val.clusterDim.y = 1;
+    attrs[na].val.clusterDim.z = (unsigned)p.split_k;
+    ++na;
+  }
+  cfg.attrs = attrs;
+  cfg.numAttrs = na;
+  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, brgemm_tc_kernel<BLOCK_N, STAGES, SPLITK>, tmA, tmB, p));
 }
 
 int bin_mode_from_flags(int64_t f) {
@@ -296,7 +432,7 @@ bool brgemm_tc_supported(const KernelDesc &d) {
 
 void brgemm_tc_configure(KernelDesc &d) {
   // Largest BLOCK_N that still yields >= ~3/4 of the SMs worth of CTAs; otherwise the
-  // smallest tile (most CTAs).
+  // smallest tile (most CTAs) and, at launch, a split of the reduction across a cluster.
   const int64_t tiles_m = (d.m + BLOCK_M - 1) / BLOCK_M;
   int bn = 64;
   for (int cand : {256, 128}) {
@@ -304,19 +440,36 @@ void brgemm_tc_configure(KernelDesc &d) {
   }
   d.block_n = bn;
   d.stages = bn == 64 ? 8 : bn == 128 ? 6 : 4;
-  snprintf(d.name, sizeof(d.name), "brgemm_tc_bf16_128x%dx64_s%d", bn, d.stages);
+  snprintf(d.name, sizeof(d.name), "brgemm_tc_bf16_128x%dx64", bn);
 }
 
 bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t stream) {
   if (!aligned16(g.A) || !aligned16(g.B)) return false;
   const int64_t batch = g.batch;
   if (batch > (1ll << 31)) return false;
-  CUtensorMap tmA, tmB;
-  const uint64_t nb = batch > 0 ? (uint64_t)batch : 1;
-  if (!encode_map(&tmA, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, BLOCK_K, BLOCK_M))
-    return false;
-  if (!encode_map(&tmB, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, 64, BLOCK_K))
-    return false;
+  // A tensor map is a pure function of (descriptor, operand address, batch): cache the encoded
+  // pair per thread so steady-state invokes (the same memrefs over and over) skip the driver call.
+  struct MapCacheEntry {
+    const KernelDesc *desc = nullptr;
+    const void *A = nullptr, *B = nullptr;
+    int64_t batch = -1;
+    bool ok = false;
+    CUtensorMap tmA, tmB;
+  };
+  constexpr int kMapCache = 256;
+  thread_local MapCacheEntry t_maps[kMapCache];
+  const uintptr_t ha = reinterpret_cast<uintptr_t>(g.A), hb = reinterpret_cast<uintptr_t>(g.B);
+  MapCacheEntry &e = t_maps[((ha >> 7) ^ (ha >> 19) ^ (hb >> 9) ^ (hb >> 23) ^ (uintptr_t)batch) & (kMapCache - 1)];
+  if (e.desc != &d || e.A != g.A || e.B != g.B || e.batch != batch) {
+    const uint64_t nb = batch > 0 ? (uint64_t)batch : 1;
+    e.desc = &d; e.A = g.A; e.B = g.B; e.batch = batch;
+    e.ok = encode_map(&e.tmA, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, BLOCK_K,
+                      BLOCK_M) &&
+           encode_map(&e.tmB, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, 64,
+                      BLOCK_K);
+  }
+  if (!e.ok) return false;
+  const CUtensorMap &tmA = e.tmA, &tmB = e.tmB;
 
   TcParams p;
   p.C = g.C;
@@ -330,11 +483,28 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   p.relu = d.op == OpClass::FusedBrgemm && d.unary_kind == 5;
   p.c_vec_ok = aligned16(g.C) && (d.ldc % 8) == 0;
 
-  dim3 grid((unsigned)((d.n + d.block_n - 1) / d.block_n), (unsigned)((d.m + BLOCK_M - 1) / BLOCK_M), 1);
+  const int64_t tiles = ((d.n + d.block_n - 1) / d.block_n) * ((d.m + BLOCK_M - 1) / BLOCK_M);
+  // split the reduction across a cluster while the CTA count stays within one wave and every CTA keeps
+  // at least 2 k-blocks
+  int split = 1;
+  if (d.block_n == 64) {
+    const char *env = getenv("TPP_XSMM_SPLITK");
+    if (env) {
+      split = atoi(env);
+    } else {
+      while (split < 4 && tiles * (split * 2) <= 148 && p.total_iters >= 2 * (split * 2)) split *= 2;
+    }
+    if (split != 2 && split != 4) split = 1;
+  }
+  p.split_k = split;
+
+  dim3 grid((unsigned)((d.n + d.block_n - 1) / d.block_n), (unsigned)((d.m + BLOCK_M - 1) / BLOCK_M), (unsigned)split);
   switch (d.block_n) {
-  case 256: launch_cfg<256, 4>(tmA, tmB, p, grid, stream); break;
-  case 128: launch_cfg<128, 6>(tmA, tmB, p, grid, stream); break;
-  default: launch_cfg<64, 8>(tmA, tmB, p, grid, stream); break;
+  case 256: launch_cfg<256, 4, false>(tmA, tmB, p, grid, stream); break;
+  case 128: launch_cfg<128, 6, false>(tmA, tmB, p, grid, stream); break;
+  default:
+    if (split > 1) launch_cfg<64, 3, true>(tmA, tmB, p, grid, stream);   // 105 KiB smem: two CTAs per SM
+    else launch_cfg<64, 8, false>(tmA, tmB, p, grid, stream);
   }
   return true;
 }

@@ -129,14 +129,16 @@ struct ClassCacheEntry {
   bool is_device = false;
   int device = -1;
 };
-thread_local ClassCacheEntry t_class_cache[8];
+constexpr int kClassCacheSize = 256;
+thread_local ClassCacheEntry t_class_cache[kClassCacheSize];
 
 Resolved resolve(const void *base, const void *elem) {
   Mirror mir;
   if (find_mirror(elem, &mir)) {
     return {Where::HostMirrored, mir.dev + (reinterpret_cast<const char *>(elem) - mir.host), -1};
   }
-  const size_t slot = (reinterpret_cast<uintptr_t>(base) >> 6) & 7;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(base);
+  const size_t slot = ((bits >> 8) ^ (bits >> 17) ^ (bits >> 26)) & (kClassCacheSize - 1);
   ClassCacheEntry &ce = t_class_cache[slot];
   if (ce.base != base) {
     cudaPointerAttributes attr;
