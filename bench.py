@@ -193,6 +193,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="graph", choices=["graph", "direct"],
+                    help="graph: replay the captured invoke sequence (one host call per step); "
+                         "direct: one C-ABI invoke per layer per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -261,17 +264,21 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident number ("value") --------------------------------------------------------
-    loop.run(args.warmup)
+    # mode "graph": every operand set's forward pass (3 invokes) is captured once through
+    # xsmm_cuda_graph_begin/end and replayed - one host call per step; mode "direct": one
+    # xsmm_fused_brgemm_invoke (one cudaLaunchKernelEx) per layer per step.
+    run = loop.run_graph if args.mode == "graph" else loop.run
+    run(max(args.warmup, num_sets))   # warm-up also captures every set's graph
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    loop.run(200)  # keep the GPU busy while the sampler gets going
+    run(200)  # keep the GPU busy while the sampler gets going
     barrier()
     launches0 = xsmm.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
     ev0.record(stream)
-    loop.run(args.steps)
+    run(args.steps)
     t_issue = time.perf_counter() - t_wall0   # host time to issue all launches (no sync yet)
     ev1.record(stream)
     barrier()
@@ -289,13 +296,25 @@ def main():
 
     # hot-L2 variant (what tpp-run measures: the same buffers every iteration), for information
     hot = harness.NativeMlpLoop(cfg, replay.handles, sets[:1])
-    hot.run(args.warmup)
+    run_hot = hot.run_graph if args.mode == "graph" else hot.run
+    run_hot(args.warmup)
     barrier()
     ev0.record(stream)
-    hot.run(args.steps)
+    run_hot(args.steps)
     ev1.record(stream)
     barrier()
     ms_hot = ev0.elapsed_time(ev1) / args.steps
+
+    # the other issue mode, for information (same kernels, different host path)
+    other = loop.run if args.mode == "graph" else loop.run_graph
+    other_steps = min(args.steps, 500)
+    other(max(args.warmup, num_sets))
+    barrier()
+    ev0.record(stream)
+    other(other_steps)
+    ev1.record(stream)
+    barrier()
+    ms_other = ev0.elapsed_time(ev1) / other_steps
 
     # ---- parity of what was just timed (rank-local, against the oracle on a row sample) ----------
     import oracle
@@ -374,6 +393,8 @@ def main():
                    "l2": f"rotating {num_sets} operand sets ({num_sets * set_bytes >> 20} MiB > 126 MiB L2), "
                          "inputs larger than L2",
                    "timing": "CUDA events on the launch stream, max over ranks",
+                   "issue_mode": ("CUDA graph replay of the captured xsmm invoke sequence (xsmm_cuda_graph_*)"
+                                  if args.mode == "graph" else "one xsmm_fused_brgemm_invoke per layer"),
                    "flops_per_step": flops_step_rank * n_gpus, "matmul_flops_per_step": cfg.matmul_flops() * n_gpus},
         "clocks": sampler.summary(t_wall0, t_wall1),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH_PER_GPU * LAYERS[0] * 2,
@@ -388,6 +409,7 @@ def main():
         "cpu_baseline": cpu,
         "extra": {"ms_per_step_hot_l2": ms_hot, "gflops_hot_l2": flops_step_rank * n_gpus / (ms_hot * 1e-3) / 1e9,
                   "host_issue_us_per_launch": t_issue / max(launches, 1) * 1e6,
+                  ("ms_per_step_direct_invokes" if args.mode == "graph" else "ms_per_step_graph_replay"): ms_other,
                   "parity_rel_err_vs_oracle": rel, "kernel": xsmm.handle_kernel(replay.handles[0])},
     }
     print(json.dumps(line))

@@ -221,6 +221,19 @@ TPP_XSMM_EXPORT int64_t xsmm_cuda_update_host(void *host, int64_t bytes);
 /* Device address that mirrors a registered host address (NULL if none). */
 TPP_XSMM_EXPORT void *xsmm_cuda_device_ptr(void *host);
 
+/* CUDA-graph capture of a sequence of invokes (the body of a perf.bench loop):
+ *   xsmm_cuda_graph_begin();  ...invokes on device / mirrored operands...;
+ *   g = xsmm_cuda_graph_end();  then  xsmm_cuda_graph_launch(g) any number of times.
+ * Replaying the graph re-runs exactly the captured kernels (same operands) with one
+ * host call instead of one launch per invoke. Capture uses the calling thread's
+ * stream (an internal one if the thread is on the legacy default stream). Plain host
+ * operands cannot be captured (strict mode is synchronous): the invoke exit(-1)s.
+ * graph_end returns 0 if the capture failed. */
+TPP_XSMM_EXPORT int64_t xsmm_cuda_graph_begin(void);
+TPP_XSMM_EXPORT int64_t xsmm_cuda_graph_end(void);
+TPP_XSMM_EXPORT void xsmm_cuda_graph_launch(int64_t graph);
+TPP_XSMM_EXPORT void xsmm_cuda_graph_destroy(int64_t graph);
+
 /* Introspection used by the tests and by bench.py's "gpu_launches". */
 TPP_XSMM_EXPORT int64_t xsmm_cuda_launch_count(void);
 /* Name of the kernel variant the last invoke on this thread launched

@@ -443,3 +443,40 @@ def test_dispatch_is_cached_and_validates():
     code = "from tpp_mlir_b200 import xsmm; xsmm.brgemm_dispatch(2, 64, 64, 64, 32, 64, 64, 0, 0, 4)"
     p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert p.returncode != 0 and "failed to generate brgemm func" in p.stderr
+
+
+def test_graph_capture_replays_the_invoke_sequence():
+    """xsmm_cuda_graph_begin/end: the captured 2-layer invoke chain replays bit-identically."""
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    gen = oracle.TensorInit("normal", BF16, 7)
+
+    def dev_t(a):
+        return torch.from_numpy(a.view(np.int16)).cuda()
+
+    x, W1, b1, W2, b2 = (dev_t(gen.fill(*s)) for s in ((256, 512), (512, 512), (512,), (512, 512), (512,)))
+    y1 = torch.zeros(256, 512, dtype=torch.int16, device="cuda")
+    y2 = torch.zeros(256, 512, dtype=torch.int16, device="cuda")
+    h = xsmm.fused_brgemm_dispatch(BF16, 256, 512, 512, 512, 512, 512, 0, 0, 4, 0, 5, 4, 1)
+
+    def chain():
+        xsmm.fused_brgemm_invoke(BF16, h, x, 0, W1, 0, y1, 0, b1, 0, 1)
+        xsmm.fused_brgemm_invoke(BF16, h, y1, 0, W2, 0, y2, 0, b2, 0, 1)
+
+    chain()
+    xsmm.sync()
+    want = y2.clone()
+    n0 = xsmm.launch_count()
+    with xsmm.graph_capture() as g:
+        chain()
+    assert xsmm.launch_count() == n0  # capture records, it does not execute
+    for _ in range(3):
+        y1.zero_()
+        y2.zero_()
+        g.launch()
+        xsmm.sync()
+        assert torch.equal(y2, want)
+    assert xsmm.launch_count() == n0 + 6
+    g.destroy()

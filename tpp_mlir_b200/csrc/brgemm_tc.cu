@@ -488,7 +488,7 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   // at least 2 k-blocks
   int split = 1;
   if (d.block_n == 64) {
-    const char *env = getenv("TPP_XSMM_SPLITK");
+    static const char *env = getenv("TPP_XSMM_SPLITK");   // tuning override, read once
     if (env) {
       split = atoi(env);
     } else {

@@ -39,6 +39,26 @@ void tpp_replay_mlp(int64_t dtype, int64_t num_layers, const int64_t *handles, c
   }
 }
 
+// Same loop, but each operand set's forward pass is captured once into a CUDA graph
+// (xsmm_cuda_graph_begin/end around the invokes) and replayed: what a perf.bench lowering that
+// captures its body would execute. graphs[i] == 0 means "set i not captured yet".
+__attribute__((visibility("default")))
+int64_t tpp_replay_mlp_graph(int64_t dtype, int64_t num_layers, const int64_t *handles, const int64_t *layer_sizes,
+                             int64_t batch, int64_t bn, int64_t bk, int64_t bc, const TppMlpSet *sets,
+                             int64_t num_sets, int64_t *graphs, int64_t first_step, int64_t steps, int64_t has_bias) {
+  for (int64_t s = 0; s < steps; ++s) {
+    const int64_t idx = (first_step + s) % num_sets;
+    if (!graphs[idx]) {
+      if (xsmm_cuda_graph_begin() != 0) return -1;
+      tpp_replay_mlp(dtype, num_layers, handles, layer_sizes, batch, bn, bk, bc, sets + idx, 1, 0, 1, has_bias);
+      graphs[idx] = xsmm_cuda_graph_end();
+      if (!graphs[idx]) return -1;
+    }
+    xsmm_cuda_graph_launch(graphs[idx]);
+  }
+  return 0;
+}
+
 // One forward on host buffers that were registered with xsmm_cuda_register_host: upload the
 // step's input, run the layers on the mirrors, download the step's output, wait for it.
 __attribute__((visibility("default")))

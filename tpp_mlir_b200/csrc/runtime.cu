@@ -86,8 +86,24 @@ struct ThreadCtx {
   int device = -1;               // device this thread last launched on
   const char *last_kernel = "";
   Staging stage[4];
+  // graph capture (xsmm_cuda_graph_begin/end)
+  bool capturing = false;
+  cudaStream_t capture_stream = nullptr;   // internal stream used when the thread is on the legacy stream
+  cudaStream_t saved_stream = nullptr;
+  int64_t captured_launches = 0;
+};
+
+struct GraphHandle {
+  uint32_t magic = 0x47525048u; // "GRPH"
+  cudaGraphExec_t exec = nullptr;
+  int64_t launches = 0;         // kernels per replay (for xsmm_cuda_launch_count)
 };
 thread_local ThreadCtx t_ctx;
+
+inline void count_launch() {
+  if (t_ctx.capturing) ++t_ctx.captured_launches;   // recorded, not executed yet
+  else g_launches.fetch_add(1, std::memory_order_relaxed);
+}
 
 // ---- registered host ranges -> device mirrors -----------------------------------
 struct Mirror {
@@ -208,6 +224,8 @@ void stage_in(StagedCall &sc, cudaStream_t stream) {
   }
   use_device(known_dev);
   if (!sc.any_host) return;
+  if (t_ctx.capturing)
+    fail("graph capture needs device or registered host operands: plain host pointers are staged synchronously");
   for (int i = 0; i < sc.nops; ++i) {
     Operand &o = sc.ops[i];
     if (!o.elem || o.where != Where::HostPlain) continue;
@@ -329,6 +347,23 @@ int64_t gemm_family_dispatch(OpClass op, int64_t dtype, int64_t m, int64_t n, in
   });
 }
 
+// TPP_XSMM_HOST_PROFILE=1: where the host time of a BRGEMM invoke goes (printed at thread exit)
+const bool g_host_prof = getenv("TPP_XSMM_HOST_PROFILE") != nullptr;
+struct HostProf {
+  uint64_t n = 0, resolve_ns = 0, launch_ns = 0, total_ns = 0;
+  ~HostProf() {
+    if (n)
+      fprintf(stderr, "tpp-xsmm-cuda host profile: %llu brgemm invokes, per invoke: resolve %.2f us, launch %.2f us, "
+                      "total %.2f us\n", (unsigned long long)n, resolve_ns / 1e3 / n, launch_ns / 1e3 / n,
+              total_ns / 1e3 / n);
+  }
+};
+thread_local HostProf t_prof;
+inline uint64_t now_ns() {
+  return (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(
+             std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t offA, void *pB, int64_t offB, void *pC,
                         int64_t offC, void *pD, int64_t offD, int64_t batch) {
   if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
@@ -362,7 +397,9 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
   }
   cudaStream_t stream = t_ctx.stream;
   StagedCall sc{ops, 4, esize(dtype)};
+  const uint64_t t0 = g_host_prof ? now_ns() : 0;
   stage_in(sc, stream);
+  const uint64_t t1 = g_host_prof ? now_ns() : 0;
 
   GemmArgs g;
   g.A = ops[0].dev; g.B = ops[1].dev; g.C = ops[2].dev; g.D = has_d ? ops[3].dev : nullptr;
@@ -376,7 +413,11 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
     launch_brgemm_simt(*d, g, stream);
     t_ctx.last_kernel = d->dtype == kF32 ? "brgemm_simt_f32_64x64x16" : "brgemm_simt_bf16_64x64x16";
   }
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  count_launch();
+  if (g_host_prof) {
+    const uint64_t t2 = now_ns();
+    t_prof.n++; t_prof.resolve_ns += t1 - t0; t_prof.launch_ns += t2 - t1; t_prof.total_ns += t2 - t0;
+  }
   stage_out(sc, stream);
 }
 
@@ -571,7 +612,7 @@ static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int
   }
   }
   t_ctx.last_kernel = d->name;
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  count_launch();
   stage_out(sc, stream);
 }
 
@@ -613,7 +654,7 @@ extern "C" void xsmm_binary_invoke(int64_t dtype, int64_t addr, void *alignedPtr
   a.dtype = dtype;
   launch_eltwise(a, stream);
   t_ctx.last_kernel = d->name;
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  count_launch();
   stage_out(sc, stream);
 }
 
@@ -646,7 +687,13 @@ extern "C" int libxsmm_cpuid_dot_pack_factor(int datatype) {
 
 // ================================ CUDA extensions =====================================
 
-extern "C" void xsmm_cuda_set_stream(void *stream) { t_ctx.stream = static_cast<cudaStream_t>(stream); }
+extern "C" void xsmm_cuda_set_stream(void *stream) {
+  if (t_ctx.capturing) { // keep recording on the capture stream; the new stream takes effect after graph_end
+    t_ctx.saved_stream = static_cast<cudaStream_t>(stream);
+    return;
+  }
+  t_ctx.stream = static_cast<cudaStream_t>(stream);
+}
 extern "C" void *xsmm_cuda_get_stream(void) { return t_ctx.stream; }
 
 extern "C" void xsmm_cuda_sync(void) {
@@ -709,6 +756,59 @@ extern "C" void *xsmm_cuda_device_ptr(void *host) {
   Mirror m;
   if (!find_mirror(host, &m)) return nullptr;
   return m.dev + (static_cast<char *>(host) - m.host);
+}
+
+extern "C" int64_t xsmm_cuda_graph_begin(void) {
+  ensure_cuda();
+  if (t_ctx.capturing) return -1;
+  t_ctx.saved_stream = t_ctx.stream;
+  if (t_ctx.stream == nullptr) { // the legacy default stream cannot be captured
+    if (!t_ctx.capture_stream) TPP_CUDA_CHECK(cudaStreamCreateWithFlags(&t_ctx.capture_stream, cudaStreamNonBlocking));
+    t_ctx.stream = t_ctx.capture_stream;
+  }
+  // relaxed: pointer queries / attribute calls of the first invoke are legal during capture
+  TPP_CUDA_CHECK(cudaStreamBeginCapture(t_ctx.stream, cudaStreamCaptureModeRelaxed));
+  t_ctx.capturing = true;
+  t_ctx.captured_launches = 0;
+  return 0;
+}
+
+extern "C" int64_t xsmm_cuda_graph_end(void) {
+  if (!t_ctx.capturing) return 0;
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(t_ctx.stream, &graph);
+  t_ctx.capturing = false;
+  t_ctx.stream = t_ctx.saved_stream;
+  if (e != cudaSuccess || !graph) {
+    fprintf(stderr, "tpp-xsmm-cuda: graph capture failed: %s\n", cudaGetErrorString(e));
+    cudaGetLastError();
+    return 0;
+  }
+  GraphHandle *gh = new GraphHandle();
+  gh->launches = t_ctx.captured_launches;
+  e = cudaGraphInstantiate(&gh->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    fprintf(stderr, "tpp-xsmm-cuda: graph instantiate failed: %s\n", cudaGetErrorString(e));
+    delete gh;
+    return 0;
+  }
+  return reinterpret_cast<int64_t>(gh);
+}
+
+extern "C" void xsmm_cuda_graph_launch(int64_t graph) {
+  GraphHandle *gh = reinterpret_cast<GraphHandle *>(graph);
+  if (!gh || gh->magic != 0x47525048u) fail("xsmm_cuda_graph_launch: not a graph handle");
+  TPP_CUDA_CHECK(cudaGraphLaunch(gh->exec, t_ctx.stream));
+  g_launches.fetch_add(gh->launches, std::memory_order_relaxed);
+}
+
+extern "C" void xsmm_cuda_graph_destroy(int64_t graph) {
+  GraphHandle *gh = reinterpret_cast<GraphHandle *>(graph);
+  if (!gh || gh->magic != 0x47525048u) return;
+  cudaGraphExecDestroy(gh->exec);
+  gh->magic = 0;
+  delete gh;
 }
 
 extern "C" int64_t xsmm_cuda_launch_count(void) { return g_launches.load(); }

@@ -198,6 +198,8 @@ def replay_lib():
         lib.tpp_replay_mlp.restype = None
         lib.tpp_replay_mlp_e2e.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, i64, i64]
         lib.tpp_replay_mlp_e2e.restype = None
+        lib.tpp_replay_mlp_graph.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, p, i64, i64, i64]
+        lib.tpp_replay_mlp_graph.restype = i64
         _replay_lib = lib
     return _replay_lib
 
@@ -231,6 +233,20 @@ class NativeMlpLoop:
         bn, bk, bc = cfg.tiles
         replay_lib().tpp_replay_mlp(cfg.dtype, cfg.num_layers, self._handles, self._sizes, cfg.batch, bn, bk, bc,
                                     self._sets, self.num_sets, self._step, steps, 1 if cfg.bias else 0)
+        self._step += steps
+
+    def run_graph(self, steps: int) -> None:
+        """Like run(), but each operand set's forward pass is captured once into a CUDA graph
+        (xsmm_cuda_graph_begin/end) and replayed with one host call per step."""
+        cfg = self.cfg
+        bn, bk, bc = cfg.tiles
+        if not hasattr(self, "_graphs"):
+            self._graphs = (_ct.c_int64 * self.num_sets)()
+        rc = replay_lib().tpp_replay_mlp_graph(cfg.dtype, cfg.num_layers, self._handles, self._sizes, cfg.batch, bn,
+                                               bk, bc, self._sets, self.num_sets, self._graphs, self._step, steps,
+                                               1 if cfg.bias else 0)
+        if rc != 0:
+            raise RuntimeError("CUDA graph capture of the MLP forward failed")
         self._step += steps
 
     def run_e2e(self, steps: int, elem_size: int = 2) -> None:

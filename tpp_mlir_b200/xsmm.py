@@ -62,6 +62,10 @@ EXPORTS = {
     "xsmm_cuda_update_device": (c_int64, [c_void_p, c_int64]),
     "xsmm_cuda_update_host": (c_int64, [c_void_p, c_int64]),
     "xsmm_cuda_device_ptr": (c_void_p, [c_void_p]),
+    "xsmm_cuda_graph_begin": (c_int64, []),
+    "xsmm_cuda_graph_end": (c_int64, []),
+    "xsmm_cuda_graph_launch": (None, [c_int64]),
+    "xsmm_cuda_graph_destroy": (None, [c_int64]),
     "xsmm_cuda_launch_count": (c_int64, []),
     "xsmm_cuda_last_kernel": (c_char_p, []),
     "xsmm_cuda_handle_kernel": (c_char_p, [c_int64]),
@@ -191,6 +195,33 @@ def sync() -> None:
 
 def set_stream(stream_ptr: int | None) -> None:
     LIB.xsmm_cuda_set_stream(stream_ptr)
+
+
+class graph_capture:
+    """``with xsmm.graph_capture() as g: ...invokes...`` then ``g.launch()``: the captured invoke
+    sequence (e.g. the body of a perf.bench loop) replays with one host call."""
+
+    def __init__(self):
+        self.handle = 0
+
+    def __enter__(self):
+        if LIB.xsmm_cuda_graph_begin() != 0:
+            raise RuntimeError("xsmm_cuda_graph_begin failed (already capturing?)")
+        return self
+
+    def __exit__(self, exc_type, exc, tb):
+        self.handle = LIB.xsmm_cuda_graph_end()
+        if exc_type is None and not self.handle:
+            raise RuntimeError("CUDA graph capture of the invoke sequence failed")
+        return False
+
+    def launch(self) -> None:
+        LIB.xsmm_cuda_graph_launch(self.handle)
+
+    def destroy(self) -> None:
+        if self.handle:
+            LIB.xsmm_cuda_graph_destroy(self.handle)
+            self.handle = 0
 
 
 def launch_count() -> int:
