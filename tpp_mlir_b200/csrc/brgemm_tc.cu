@@ -30,6 +30,7 @@
 #include <cuda.h>
 
 #include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -56,7 +57,24 @@ struct TcParams {
   int32_t split_k;      // cluster size along the reduction (1, 2 or 4)
   int32_t beta0, bin_kind, bin_mode, relu;
   int32_t c_vec_ok;     // C base 16B aligned and ldc % 8 == 0
+  int32_t b_early;      // B (and D) do not depend on in-flight kernels: fetch B before the PDL wait
+  float *ws;            // split-K exchange through L2: [tile][owner][src][128][64/S] f32 (SPLITK == 2)
+  unsigned long long *trace;   // TPP_XSMM_TC_TRACE: per-CTA clock stamps (nullptr in normal runs)
 };
+
+constexpr int TRACE_SLOTS = 16;
+// stamp slot `slot` of this CTA's trace row with the SM clock (slot 0 additionally gets %globaltimer in slot 15)
+__device__ __forceinline__ void trace_stamp(const TcParams &p, int slot) {
+  if (p.trace) {
+    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    p.trace[(size_t)cta * TRACE_SLOTS + slot] = clock64();
+    if (slot == 0) {
+      unsigned long long gt;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      p.trace[(size_t)cta * TRACE_SLOTS + 15] = gt;
+    }
+  }
+}
 
 template <int BLOCK_N> struct SmemLayout {
   static constexpr int kBChunks = BLOCK_N / 64;
@@ -65,7 +83,8 @@ template <int BLOCK_N> struct SmemLayout {
 
 // Fused epilogue on NC consecutive f32 accumulator columns of one row: (+C) -> binary(D) -> relu -> bf16.
 template <int NC>
-__device__ __forceinline__ void epilogue_store(float (&v)[NC], const TcParams &p, int64_t row, int64_t col0) {
+__device__ __forceinline__ void epilogue_store(float (&v)[NC], const TcParams &p, int64_t row, int64_t col0,
+                                               const float *bias_pref = nullptr) {
   const uint16_t *Dp = static_cast<const uint16_t *>(p.D);
   uint16_t *crow = static_cast<uint16_t *>(p.C) + row * p.ldc + col0;
   const bool full = (col0 + NC <= p.n);
@@ -88,7 +107,10 @@ __device__ __forceinline__ void epilogue_store(float (&v)[NC], const TcParams &p
     }
   }
   if (p.bin_kind) {
-    if (p.bin_mode == kBcastCol && p.bin_kind == 1 && full) {   // the MLP case: bias vector add
+    if (bias_pref) {                                            // bias was prefetched during the main loop
+#pragma unroll
+      for (int e = 0; e < NC; ++e) v[e] += bias_pref[e];
+    } else if (p.bin_mode == kBcastCol && p.bin_kind == 1 && full) {   // the MLP case: bias vector add
 #pragma unroll
       for (int e = 0; e < NC; ++e) v[e] += bf16_bits_to_f32(__ldg(Dp + col0 + e));
     } else {
@@ -170,9 +192,21 @@ __device__ __forceinline__ void splitk_epilogue(const TcParams &p, uint32_t tmem
       }
     }
   }
+  const int64_t row = m0 + row_in_tile;
+  const int64_t col0 = n0 + (int64_t)rank * NC;
+  // bias for the owned columns: requested before the barrier so its latency hides behind it
+  float bias[NC];
+  const bool pref = p.bin_kind == 1 && p.bin_mode == kBcastCol && col0 + NC <= p.n;
+  if (pref) {
+    const uint16_t *Dp = static_cast<const uint16_t *>(p.D) + col0;
+#pragma unroll
+    for (int e = 0; e < NC; ++e) bias[e] = bf16_bits_to_f32(__ldg(Dp + e));
+  }
   // all partials of this cluster have landed in their owners' shared memory
+  if (threadIdx.x == 64) trace_stamp(p, 8);
   ptx::cluster_arrive();
   ptx::cluster_wait();
+  if (threadIdx.x == 64) trace_stamp(p, 9);
 #pragma unroll
   for (int s = 0; s < S; ++s) {
     if (static_cast<uint32_t>(s) == rank) continue;
@@ -184,12 +218,84 @@ __device__ __forceinline__ void splitk_epilogue(const TcParams &p, uint32_t tmem
       own[4 * j] += t.x; own[4 * j + 1] += t.y; own[4 * j + 2] += t.z; own[4 * j + 3] += t.w;
     }
   }
-  const int64_t row = m0 + row_in_tile;
-  const int64_t col0 = n0 + (int64_t)rank * NC;
-  if (row < p.m && col0 < p.n) epilogue_store<NC>(own, p, row, col0);
+  if (row < p.m && col0 < p.n) epilogue_store<NC>(own, p, row, col0, pref ? bias : nullptr);
+  if (threadIdx.x == 64) trace_stamp(p, 10);
 }
 
-template <int BLOCK_N, int STAGES, bool SPLITK>
+// Split-K exchange through L2 (SPLITK == 2). DSMEM moves ~17 B/clk/SM (measured: 24 KiB in + 24 KiB out took
+// ~4400 clk including the barrier), the L2 path moves >60 B/clk/SM each way: every CTA stores the slices it
+// does not own to a small f32 workspace that stays L2-resident ([tile][owner][src][row][NC], a warp writes
+// 32 rows x NC*4 contiguous bytes), fences at gpu scope, meets its cluster at the cluster barrier, and the owner
+// reads its S-1 incoming slices back with ld.global.cg.
+template <int NC>
+__device__ __forceinline__ void splitk_epilogue_l2(const TcParams &p, uint32_t tmem_acc, int q, int lane, int64_t m0,
+                                                   int64_t n0, uint32_t rank, bool has_acc) {
+  constexpr int S = 64 / NC;
+  constexpr int NCH = NC / 4;
+  const int row_in_tile = q * 32 + lane;
+  const int64_t row = m0 + row_in_tile;
+  const int64_t col0 = n0 + (int64_t)rank * NC;
+  const size_t tile = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
+  float *ws_tile = p.ws + tile * (size_t)(S * S * BLOCK_M * NC);
+  float own[NC];
+#pragma unroll
+  for (int c = 0; c < 64; c += 32) {
+    uint32_t r[32];
+    if (has_acc) {
+      ptx::tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+      ptx::tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) r[e] = 0u;
+    }
+#pragma unroll
+    for (int part = 0; part < 32 / NC; ++part) {
+      const uint32_t owner = static_cast<uint32_t>(c / NC + part);
+      if (owner == rank) {
+#pragma unroll
+        for (int e = 0; e < NC; ++e) own[e] = __uint_as_float(r[part * NC + e]);
+      } else {
+        float4 *dst = reinterpret_cast<float4 *>(ws_tile + ((size_t)(owner * S + rank) * BLOCK_M + row_in_tile) * NC);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j)
+          dst[j] = make_float4(__uint_as_float(r[part * NC + 4 * j]), __uint_as_float(r[part * NC + 4 * j + 1]),
+                               __uint_as_float(r[part * NC + 4 * j + 2]), __uint_as_float(r[part * NC + 4 * j + 3]));
+      }
+    }
+  }
+  // bias for the owned columns: issued before the barrier so its latency hides behind it
+  float bias[NC];
+  const bool pref = p.bin_kind == 1 && p.bin_mode == kBcastCol && col0 + NC <= p.n;
+  if (pref) {
+    const uint16_t *Dp = static_cast<const uint16_t *>(p.D) + col0;
+#pragma unroll
+    for (int e = 0; e < NC; ++e) bias[e] = bf16_bits_to_f32(__ldg(Dp + e));
+  }
+  __threadfence();   // partial sums visible device-wide before the cluster barrier releases the readers
+  if (threadIdx.x == 64) trace_stamp(p, 8);
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  if (threadIdx.x == 64) trace_stamp(p, 9);
+#pragma unroll
+  for (int s = 0; s < S; ++s) {
+    if (static_cast<uint32_t>(s) == rank) continue;
+    const float *src = ws_tile + ((size_t)(rank * S + s) * BLOCK_M + row_in_tile) * NC;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      float4 t;
+      asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                   : "l"(src + 4 * j)
+                   : "memory");
+      own[4 * j] += t.x; own[4 * j + 1] += t.y; own[4 * j + 2] += t.z; own[4 * j + 3] += t.w;
+    }
+  }
+  if (row < p.m && col0 < p.n) epilogue_store<NC>(own, p, row, col0, pref ? bias : nullptr);
+  if (threadIdx.x == 64) trace_stamp(p, 10);
+}
+
+// SPLITK: 0 = one CTA per tile, 1 = cluster split-K with DSMEM exchange, 2 = cluster split-K with L2 exchange
+template <int BLOCK_N, int STAGES, int SPLITK>
 __global__ void __launch_bounds__(NUM_THREADS, SPLITK ? 2 : 1)
 brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   using L = SmemLayout<BLOCK_N>;
@@ -199,7 +305,7 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t smem_a = smem_base;
   const uint32_t smem_b = smem_base + STAGES * A_STAGE_BYTES;
   const uint32_t recv_base = smem_b + STAGES * L::kBChunks * B_CHUNK_BYTES;     // SPLITK only
-  const uint32_t bar_base = recv_base + (SPLITK ? RECV_BYTES : 0);
+  const uint32_t bar_base = recv_base + (SPLITK == 1 ? RECV_BYTES : 0);
   const uint32_t full_bar = bar_base;                 // STAGES x 8 bytes
   const uint32_t empty_bar = bar_base + STAGES * 8;   // STAGES x 8 bytes
   const uint32_t accum_bar = bar_base + 2 * STAGES * 8;
@@ -219,6 +325,7 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     it_end = (int32_t)(((int64_t)p.total_iters * (rank + 1)) / p.split_k);
   }
   const int32_t num_iters = it_end - it_begin;
+  if (threadIdx.x == 0) trace_stamp(p, 0);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmA);
@@ -238,11 +345,30 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_acc = *tmem_slot_ptr;
+  if (threadIdx.x == 0) trace_stamp(p, 1);
 
-  // PDL: let the next kernel in the stream start its own prologue, then wait until everything the
-  // previous kernel wrote (our A operand is its C) is visible before the first global access.
+  // PDL: let the next kernel in the stream start its own prologue ...
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // ... and, when the host knows that B was not produced by one of the kernels that may still be
+  // running (MLP weights), fetch the B tiles of the first STAGES k-blocks already now: they overlap
+  // the previous layer's epilogue instead of sitting on this layer's critical path.
+  int32_t b_prefetched = 0;
+  if (p.b_early) b_prefetched = num_iters < STAGES ? num_iters : STAGES;
+  if (warp == 0 && lane == 0) {
+    for (int32_t i = 0; i < b_prefetched; ++i) {
+      const int32_t it = it_begin + i;
+      const int32_t b = it / p.k_iters, kb = it - b * p.k_iters;
+      ptx::mbar_arrive_expect_tx(full_bar + 8 * i, L::kStageBytes);
+#pragma unroll
+      for (int c = 0; c < L::kBChunks; ++c)
+        ptx::tma_load_3d(smem_b + (i * L::kBChunks + c) * B_CHUNK_BYTES, &tmB, full_bar + 8 * i, n0 + c * 64,
+                         kb * BLOCK_K, b);
+    }
+  }
+  // wait until everything the previous kernels wrote (our A operand is the previous layer's C) is
+  // visible before the first dependent global access.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) trace_stamp(p, 2);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -251,15 +377,21 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int32_t it = it_begin + i;
         const int s = i % STAGES;
         const uint32_t ph = (i / STAGES) & 1;
-        ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
-        ptx::mbar_arrive_expect_tx(full_bar + 8 * s, L::kStageBytes);
         const int32_t b = it / p.k_iters, kb = it - b * p.k_iters;
+        if (i >= b_prefetched) {
+          ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
+          ptx::mbar_arrive_expect_tx(full_bar + 8 * s, L::kStageBytes);
+        }
         ptx::tma_load_3d(smem_a + s * A_STAGE_BYTES, &tmA, full_bar + 8 * s, kb * BLOCK_K, m0, b);
+        if (i >= b_prefetched) {
 #pragma unroll
-        for (int c = 0; c < L::kBChunks; ++c)
-          ptx::tma_load_3d(smem_b + (s * L::kBChunks + c) * B_CHUNK_BYTES, &tmB, full_bar + 8 * s, n0 + c * 64,
-                           kb * BLOCK_K, b);
+          for (int c = 0; c < L::kBChunks; ++c)
+            ptx::tma_load_3d(smem_b + (s * L::kBChunks + c) * B_CHUNK_BYTES, &tmB, full_bar + 8 * s, n0 + c * 64,
+                             kb * BLOCK_K, b);
+        }
+        if (i == 0) trace_stamp(p, 3);
       }
+      trace_stamp(p, 4);
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -270,6 +402,7 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t ph = (i / STAGES) & 1;
         ptx::mbar_wait(full_bar + 8 * s, ph);
         ptx::tc_fence_after_sync();
+        if (i == 0) trace_stamp(p, 5);
         const uint32_t a_addr = smem_a + s * A_STAGE_BYTES;
         const uint32_t b_addr = smem_b + s * L::kBChunks * B_CHUNK_BYTES;
 #pragma unroll
@@ -284,6 +417,7 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::umma_commit(empty_bar + 8 * s);   // frees the slot when these MMAs retire
       }
       if (num_iters > 0) ptx::umma_commit(accum_bar);   // accumulator complete
+      trace_stamp(p, 6);
     }
   } else {
     // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
@@ -292,6 +426,7 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       ptx::mbar_wait(accum_bar, 0);
       ptx::tc_fence_after_sync();
     }
+    if (threadIdx.x == 64) trace_stamp(p, 7);
     if constexpr (!SPLITK) {
       const int64_t row = (int64_t)m0 + q * 32 + lane;
 #pragma unroll 1
@@ -320,10 +455,17 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // every thread of every CTA in the cluster reaches the cluster barrier inside / next to the exchange
     if (warp >= 2) {
       const int q = warp & 3;
-      if (p.split_k == 4)
-        splitk_epilogue<16>(p, tmem_acc, recv_base, q, lane, m0, n0, rank, num_iters > 0);
-      else
-        splitk_epilogue<32>(p, tmem_acc, recv_base, q, lane, m0, n0, rank, num_iters > 0);
+      if constexpr (SPLITK == 1) {
+        if (p.split_k == 4)
+          splitk_epilogue<16>(p, tmem_acc, recv_base, q, lane, m0, n0, rank, num_iters > 0);
+        else
+          splitk_epilogue<32>(p, tmem_acc, recv_base, q, lane, m0, n0, rank, num_iters > 0);
+      } else {
+        if (p.split_k == 4)
+          splitk_epilogue_l2<16>(p, tmem_acc, q, lane, m0, n0, rank, num_iters > 0);
+        else
+          splitk_epilogue_l2<32>(p, tmem_acc, q, lane, m0, n0, rank, num_iters > 0);
+      }
     } else {
       __syncwarp();   // lane 0 ran the producer / MMA loop; the cluster barrier is warp-aligned
       ptx::cluster_arrive();
@@ -333,6 +475,7 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) trace_stamp(p, 11);
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_acc, BLOCK_N);
@@ -377,11 +520,11 @@ bool encode_map(CUtensorMap *map, const void *base, uint64_t inner, uint64_t row
   return r == CUDA_SUCCESS;
 }
 
-template <int BLOCK_N, int STAGES, bool SPLITK> constexpr int smem_bytes() {
-  return STAGES * SmemLayout<BLOCK_N>::kStageBytes + (SPLITK ? RECV_BYTES : 0) + (2 * STAGES + 1) * 8 + 16 + 1024;
+template <int BLOCK_N, int STAGES, int SPLITK> constexpr int smem_bytes() {
+  return STAGES * SmemLayout<BLOCK_N>::kStageBytes + (SPLITK == 1 ? RECV_BYTES : 0) + (2 * STAGES + 1) * 8 + 16 + 1024;
 }
 
-template <int BLOCK_N, int STAGES, bool SPLITK>
+template <int BLOCK_N, int STAGES, int SPLITK>
 void launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, dim3 grid, cudaStream_t stream) {
   constexpr int smem = smem_bytes<BLOCK_N, STAGES, SPLITK>();
   static std::once_flag once;
@@ -482,6 +625,14 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   p.bin_mode = bin_mode_from_flags(d.binary_flags);
   p.relu = d.op == OpClass::FusedBrgemm && d.unary_kind == 5;
   p.c_vec_ok = aligned16(g.C) && (d.ldc % 8) == 0;
+  static const bool b_early_off = [] { const char *e = getenv("TPP_XSMM_B_EARLY"); return e && e[0] == '0'; }();
+  p.b_early = (g.b_independent && !b_early_off) ? 1 : 0;
+  // TPP_XSMM_TC_TRACE=1 (debug): synchronous launch with per-CTA clock stamps, summary on stderr
+  static const bool trace_on = getenv("TPP_XSMM_TC_TRACE") != nullptr;
+  static unsigned long long *trace_buf = nullptr;
+  constexpr int kTraceCtas = 1024;
+  if (trace_on && !trace_buf) TPP_CUDA_CHECK(cudaMalloc(&trace_buf, sizeof(unsigned long long) * kTraceCtas * TRACE_SLOTS));
+  p.trace = nullptr;
 
   const int64_t tiles = ((d.n + d.block_n - 1) / d.block_n) * ((d.m + BLOCK_M - 1) / BLOCK_M);
   // split the reduction across a cluster while the CTA count stays within one wave and every CTA keeps
@@ -499,12 +650,59 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   p.split_k = split;
 
   dim3 grid((unsigned)((d.n + d.block_n - 1) / d.block_n), (unsigned)((d.m + BLOCK_M - 1) / BLOCK_M), (unsigned)split);
+  const int n_ctas = (int)(grid.x * grid.y * grid.z);
+  // exchange path of the split-K partials: DSMEM (default, measured faster) or the L2 workspace (TPP_XSMM_XCHG=l)
+  static const bool xchg_dsmem = [] { const char *e = getenv("TPP_XSMM_XCHG"); return !(e && e[0] == 'l'); }();
+  p.ws = nullptr;
+  if (split > 1 && !xchg_dsmem) {
+    // per-thread workspace: kernels of one thread run on one stream, so launches are serialised and may share it
+    thread_local float *ws = nullptr;
+    thread_local size_t ws_bytes = 0;
+    const size_t need = (size_t)n_ctas * BLOCK_M * 64 * sizeof(float);
+    if (need > ws_bytes) {
+      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(stream, &cs);
+      if (cs != cudaStreamCaptureStatusNone && ws_bytes > 0) return false;   // cannot re-allocate inside a capture
+      if (ws) { TPP_CUDA_CHECK(cudaDeviceSynchronize()); TPP_CUDA_CHECK(cudaFree(ws)); }
+      const size_t want = need < (8u << 20) ? (8u << 20) : need;
+      TPP_CUDA_CHECK(cudaMalloc(&ws, want));
+      ws_bytes = want;
+    }
+    p.ws = ws;
+  }
+  if (trace_on && n_ctas <= kTraceCtas) {
+    TPP_CUDA_CHECK(cudaMemsetAsync(trace_buf, 0, sizeof(unsigned long long) * n_ctas * TRACE_SLOTS, stream));
+    p.trace = trace_buf;
+  }
   switch (d.block_n) {
-  case 256: launch_cfg<256, 4, false>(tmA, tmB, p, grid, stream); break;
-  case 128: launch_cfg<128, 6, false>(tmA, tmB, p, grid, stream); break;
+  case 256: launch_cfg<256, 4, 0>(tmA, tmB, p, grid, stream); break;
+  case 128: launch_cfg<128, 6, 0>(tmA, tmB, p, grid, stream); break;
   default:
-    if (split > 1) launch_cfg<64, 3, true>(tmA, tmB, p, grid, stream);   // 105 KiB smem: two CTAs per SM
-    else launch_cfg<64, 8, false>(tmA, tmB, p, grid, stream);
+    if (split > 1 && xchg_dsmem) launch_cfg<64, 3, 1>(tmA, tmB, p, grid, stream);   // 105 KiB smem: two CTAs per SM
+    else if (split > 1) launch_cfg<64, 4, 2>(tmA, tmB, p, grid, stream);            //  97 KiB smem: two CTAs per SM
+    else launch_cfg<64, 8, 0>(tmA, tmB, p, grid, stream);
+  }
+  if (p.trace) {
+    static int dumps = 0;
+    std::vector<unsigned long long> h((size_t)n_ctas * TRACE_SLOTS);
+    TPP_CUDA_CHECK(cudaStreamSynchronize(stream));
+    TPP_CUDA_CHECK(cudaMemcpy(h.data(), trace_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    if (dumps++ % 64 == 40) {   // a steady-state launch
+      double avg[12] = {0};
+      unsigned long long gmin = ~0ull, gmax = 0;
+      for (int c = 0; c < n_ctas; ++c) {
+        const unsigned long long *r = &h[(size_t)c * TRACE_SLOTS];
+        for (int s = 1; s < 12; ++s) avg[s] += r[s] ? (double)(r[s] - r[0]) : 0.0;
+        if (r[15] < gmin) gmin = r[15];
+        if (r[15] > gmax) gmax = r[15];
+      }
+      fprintf(stderr, "tc-trace %s grid=(%u,%u,%u): CTA start spread %llu ns; avg clocks since CTA start:", d.name, grid.x,
+              grid.y, grid.z, gmax - gmin);
+      static const char *names[12] = {"", "setup", "pdl_wait", "tma1", "tma_all", "data1", "mma_issued", "acc_ready",
+                                      "pushed", "cluster", "stored", "end"};
+      for (int s = 1; s < 12; ++s) fprintf(stderr, " %s=%.0f", names[s], avg[s] / n_ctas);
+      fprintf(stderr, "\n");
+    }
   }
   return true;
 }

@@ -40,6 +40,9 @@ struct GemmArgs {
   void *C = nullptr;
   const void *D = nullptr; // bias vector (fused add, bcast_col_in0) or nullptr
   int64_t batch = 1;
+  // true when B (and D) were not written by any of the last few kernels this thread launched: the
+  // kernel may then fetch B before the programmatic-dependent-launch wait (weights of an MLP layer)
+  bool b_independent = false;
 };
 
 // generic FFMA BRGEMM (any dtype/ld/stride, VNNI-B), fused epilogue

@@ -91,6 +91,18 @@ struct ThreadCtx {
   cudaStream_t capture_stream = nullptr;   // internal stream used when the thread is on the legacy stream
   cudaStream_t saved_stream = nullptr;
   int64_t captured_launches = 0;
+  // device ranges written by the last few kernels of this thread (dependency tracking for PDL)
+  struct Range { const char *lo = nullptr, *hi = nullptr; } recent_out[4];
+  int recent_pos = 0;
+  void note_output(const char *lo, size_t bytes) {
+    recent_out[recent_pos & 3] = {lo, lo + bytes};
+    ++recent_pos;
+  }
+  bool recently_written(const char *lo, size_t bytes) const {
+    for (const Range &r : recent_out)
+      if (r.lo && lo < r.hi && r.lo < lo + bytes) return true;
+    return false;
+  }
 };
 
 struct GraphHandle {
@@ -404,6 +416,12 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
   GemmArgs g;
   g.A = ops[0].dev; g.B = ops[1].dev; g.C = ops[2].dev; g.D = has_d ? ops[3].dev : nullptr;
   g.batch = batch;
+  {
+    const size_t es = esize(dtype);
+    g.b_independent = !t_ctx.recently_written(ops[1].dev, (size_t)ops[1].width * es) &&
+                      (!has_d || !t_ctx.recently_written(ops[3].dev, (size_t)((ops[3].rows - 1) * ops[3].ld + ops[3].width) * es));
+    t_ctx.note_output(ops[2].dev, (size_t)((d->m - 1) * d->ldc + d->n) * es);
+  }
   bool launched = false;
   if (d->impl == KernelImpl::BrgemmTC) {
     launched = launch_brgemm_tc(*d, g, stream);
@@ -611,6 +629,7 @@ static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int
     launch_eltwise(a, stream);
   }
   }
+  t_ctx.note_output(ops[1].dev, (size_t)((ops[1].rows - 1) * ops[1].ld + ops[1].width) * esize(dtype));
   t_ctx.last_kernel = d->name;
   count_launch();
   stage_out(sc, stream);
@@ -653,6 +672,7 @@ extern "C" void xsmm_binary_invoke(int64_t dtype, int64_t addr, void *alignedPtr
   a.op = kOpAdd + (int)(d->kind - 1);
   a.dtype = dtype;
   launch_eltwise(a, stream);
+  t_ctx.note_output(ops[2].dev, (size_t)((ops[2].rows - 1) * ops[2].ld + ops[2].width) * esize(dtype));
   t_ctx.last_kernel = d->name;
   count_launch();
   stage_out(sc, stream);
