@@ -294,6 +294,9 @@ def main():
     flops_step_rank = cfg.flops()
     value = flops_step_rank * n_gpus / (ms_per_step * 1e-3) / 1e9
 
+    if os.environ.get("TPP_XSMM_TC_TRACE") == "2":
+        xsmm.LIB.xsmm_cuda_debug_dump_trace()
+
     # hot-L2 variant (what tpp-run measures: the same buffers every iteration), for information
     hot = harness.NativeMlpLoop(cfg, replay.handles, sets[:1])
     run_hot = hot.run_graph if args.mode == "graph" else hot.run

@@ -241,6 +241,9 @@ TPP_XSMM_EXPORT int64_t xsmm_cuda_launch_count(void);
 TPP_XSMM_EXPORT const char *xsmm_cuda_last_kernel(void);
 /* Name of the kernel variant a dispatch handle resolved to. */
 TPP_XSMM_EXPORT const char *xsmm_cuda_handle_kernel(int64_t addr);
+/* Debug: with TPP_XSMM_TC_TRACE=2 in the environment, print the wall-clock timeline of the
+ * most recent BRGEMM launches (kernel overlap under PDL / graph replay) to stderr. */
+TPP_XSMM_EXPORT void xsmm_cuda_debug_dump_trace(void);
 /* ABI version of this header. */
 TPP_XSMM_EXPORT int64_t xsmm_cuda_abi_version(void);
 

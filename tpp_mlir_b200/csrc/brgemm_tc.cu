@@ -29,6 +29,7 @@
 //     kernel's tail (griddepcontrol).
 #include <cuda.h>
 
+#include <algorithm>
 #include <mutex>
 #include <vector>
 
@@ -68,10 +69,10 @@ __device__ __forceinline__ void trace_stamp(const TcParams &p, int slot) {
   if (p.trace) {
     const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
     p.trace[(size_t)cta * TRACE_SLOTS + slot] = clock64();
-    if (slot == 0) {
+    if (slot == 0 || slot == 2 || slot == 11) {   // wall-clock (ns) of CTA start / PDL wait passed / CTA end
       unsigned long long gt;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-      p.trace[(size_t)cta * TRACE_SLOTS + 15] = gt;
+      p.trace[(size_t)cta * TRACE_SLOTS + (slot == 0 ? 15 : slot == 2 ? 13 : 14)] = gt;
     }
   }
 }
@@ -223,10 +224,11 @@ __device__ __forceinline__ void splitk_epilogue(const TcParams &p, uint32_t tmem
 }
 
 // Split-K exchange through L2 (SPLITK == 2). DSMEM moves ~17 B/clk/SM (measured: 24 KiB in + 24 KiB out took
-// ~4400 clk including the barrier), the L2 path moves >60 B/clk/SM each way: every CTA stores the slices it
-// does not own to a small f32 workspace that stays L2-resident ([tile][owner][src][row][NC], a warp writes
-// 32 rows x NC*4 contiguous bytes), fences at gpu scope, meets its cluster at the cluster barrier, and the owner
-// reads its S-1 incoming slices back with ld.global.cg.
+// ~4400 clk including the barrier); the SM<->L2 path is several times wider. Every CTA stores the slices it does
+// not own to a small f32 workspace that stays L2-resident, laid out [tile][owner][src][16-byte chunk][row] so that
+// one warp store / load instruction covers 512 contiguous bytes, meets its cluster at the cluster barrier (its
+// release/acquire at cluster scope orders the global stores for the other CTAs of the cluster; no gpu-scope fence
+// is needed), and the owner reads its S-1 incoming slices back - all loads in flight before the first add.
 template <int NC>
 __device__ __forceinline__ void splitk_epilogue_l2(const TcParams &p, uint32_t tmem_acc, int q, int lane, int64_t m0,
                                                    int64_t n0, uint32_t rank, bool has_acc) {
@@ -236,7 +238,7 @@ __device__ __forceinline__ void splitk_epilogue_l2(const TcParams &p, uint32_t t
   const int64_t row = m0 + row_in_tile;
   const int64_t col0 = n0 + (int64_t)rank * NC;
   const size_t tile = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
-  float *ws_tile = p.ws + tile * (size_t)(S * S * BLOCK_M * NC);
+  float4 *ws_tile = reinterpret_cast<float4 *>(p.ws) + tile * (size_t)(S * S * NCH * BLOCK_M);
   float own[NC];
 #pragma unroll
   for (int c = 0; c < 64; c += 32) {
@@ -255,39 +257,52 @@ __device__ __forceinline__ void splitk_epilogue_l2(const TcParams &p, uint32_t t
 #pragma unroll
         for (int e = 0; e < NC; ++e) own[e] = __uint_as_float(r[part * NC + e]);
       } else {
-        float4 *dst = reinterpret_cast<float4 *>(ws_tile + ((size_t)(owner * S + rank) * BLOCK_M + row_in_tile) * NC);
+        float4 *dst = ws_tile + (size_t)(owner * S + rank) * NCH * BLOCK_M + row_in_tile;
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
-          dst[j] = make_float4(__uint_as_float(r[part * NC + 4 * j]), __uint_as_float(r[part * NC + 4 * j + 1]),
-                               __uint_as_float(r[part * NC + 4 * j + 2]), __uint_as_float(r[part * NC + 4 * j + 3]));
+          dst[j * BLOCK_M] = make_float4(__uint_as_float(r[part * NC + 4 * j]), __uint_as_float(r[part * NC + 4 * j + 1]),
+                                         __uint_as_float(r[part * NC + 4 * j + 2]),
+                                         __uint_as_float(r[part * NC + 4 * j + 3]));
       }
     }
   }
-  // bias for the owned columns: issued before the barrier so its latency hides behind it
-  float bias[NC];
-  const bool pref = p.bin_kind == 1 && p.bin_mode == kBcastCol && col0 + NC <= p.n;
+  // bias for the owned columns: requested before the barrier so its latency hides behind it
+  uint32_t bias_raw[NC / 2];
+  const bool pref = p.bin_kind == 1 && p.bin_mode == kBcastCol && col0 + NC <= p.n &&
+                    ((reinterpret_cast<uintptr_t>(p.D) + col0 * 2) & 15) == 0;
   if (pref) {
-    const uint16_t *Dp = static_cast<const uint16_t *>(p.D) + col0;
+    const uint4 *Dp = reinterpret_cast<const uint4 *>(static_cast<const uint16_t *>(p.D) + col0);
 #pragma unroll
-    for (int e = 0; e < NC; ++e) bias[e] = bf16_bits_to_f32(__ldg(Dp + e));
+    for (int g = 0; g < NC / 8; ++g) {
+      const uint4 w = __ldg(Dp + g);
+      bias_raw[4 * g] = w.x; bias_raw[4 * g + 1] = w.y; bias_raw[4 * g + 2] = w.z; bias_raw[4 * g + 3] = w.w;
+    }
   }
-  __threadfence();   // partial sums visible device-wide before the cluster barrier releases the readers
   if (threadIdx.x == 64) trace_stamp(p, 8);
   ptx::cluster_arrive();
   ptx::cluster_wait();
   if (threadIdx.x == 64) trace_stamp(p, 9);
+  float4 in[(S - 1) * NCH];
 #pragma unroll
-  for (int s = 0; s < S; ++s) {
-    if (static_cast<uint32_t>(s) == rank) continue;
-    const float *src = ws_tile + ((size_t)(rank * S + s) * BLOCK_M + row_in_tile) * NC;
+  for (int k = 0; k < S - 1; ++k) {   // the S-1 other ranks, starting after our own (static register indices)
+    const uint32_t s = (rank + 1 + k) & (S - 1);
+    const float4 *src = ws_tile + (size_t)(rank * S + s) * NCH * BLOCK_M + row_in_tile;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) in[k * NCH + j] = __ldcg(src + j * BLOCK_M);
+  }
+#pragma unroll
+  for (int k = 0; k < S - 1; ++k)
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
-      float4 t;
-      asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
-                   : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-                   : "l"(src + 4 * j)
-                   : "memory");
-      own[4 * j] += t.x; own[4 * j + 1] += t.y; own[4 * j + 2] += t.z; own[4 * j + 3] += t.w;
+      own[4 * j] += in[k * NCH + j].x; own[4 * j + 1] += in[k * NCH + j].y;
+      own[4 * j + 2] += in[k * NCH + j].z; own[4 * j + 3] += in[k * NCH + j].w;
+    }
+  float bias[NC];
+  if (pref) {
+#pragma unroll
+    for (int e = 0; e < NC / 2; ++e) {
+      bias[2 * e] = __uint_as_float(bias_raw[e] << 16);
+      bias[2 * e + 1] = __uint_as_float(bias_raw[e] & 0xffff0000u);
     }
   }
   if (row < p.m && col0 < p.n) epilogue_store<NC>(own, p, row, col0, pref ? bias : nullptr);
@@ -484,6 +499,11 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 // ---- host side ----------------------------------------------------------------
 
+constexpr int kTraceRing = 128, kTraceRingCtas = 256;
+unsigned long long *g_trace_buf = nullptr;
+int g_trace_next = 0;
+int g_trace_ctas[kTraceRing] = {0};
+
 using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -628,10 +648,16 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   static const bool b_early_off = [] { const char *e = getenv("TPP_XSMM_B_EARLY"); return e && e[0] == '0'; }();
   p.b_early = (g.b_independent && !b_early_off) ? 1 : 0;
   // TPP_XSMM_TC_TRACE=1 (debug): synchronous launch with per-CTA clock stamps, summary on stderr
-  static const bool trace_on = getenv("TPP_XSMM_TC_TRACE") != nullptr;
-  static unsigned long long *trace_buf = nullptr;
-  constexpr int kTraceCtas = 1024;
-  if (trace_on && !trace_buf) TPP_CUDA_CHECK(cudaMalloc(&trace_buf, sizeof(unsigned long long) * kTraceCtas * TRACE_SLOTS));
+  // TPP_XSMM_TC_TRACE=2: asynchronous, every launch stamps its own slot of a ring; xsmm_cuda_debug_dump_trace()
+  // prints the wall-clock timeline (kernel overlap under PDL / graph replay)
+  static const int trace_mode = [] { const char *e = getenv("TPP_XSMM_TC_TRACE"); return e ? atoi(e) : 0; }();
+  static const bool trace_on = trace_mode != 0;
+  unsigned long long *&trace_buf = g_trace_buf;
+  constexpr int kTraceCtas = kTraceRingCtas;
+  if (trace_on && !trace_buf) {
+    TPP_CUDA_CHECK(cudaMalloc(&trace_buf, sizeof(unsigned long long) * kTraceRing * kTraceCtas * TRACE_SLOTS));
+    TPP_CUDA_CHECK(cudaMemset(trace_buf, 0, sizeof(unsigned long long) * kTraceRing * kTraceCtas * TRACE_SLOTS));
+  }
   p.trace = nullptr;
 
   const int64_t tiles = ((d.n + d.block_n - 1) / d.block_n) * ((d.m + BLOCK_M - 1) / BLOCK_M);
@@ -651,8 +677,9 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
 
   dim3 grid((unsigned)((d.n + d.block_n - 1) / d.block_n), (unsigned)((d.m + BLOCK_M - 1) / BLOCK_M), (unsigned)split);
   const int n_ctas = (int)(grid.x * grid.y * grid.z);
-  // exchange path of the split-K partials: DSMEM (default, measured faster) or the L2 workspace (TPP_XSMM_XCHG=l)
-  static const bool xchg_dsmem = [] { const char *e = getenv("TPP_XSMM_XCHG"); return !(e && e[0] == 'l'); }();
+  // exchange path of the split-K partials: the L2 workspace (default; 23.1 us per MLP step) or DSMEM
+  // (TPP_XSMM_XCHG=d; 26.7 us: st.shared::cluster moves only ~17 B/clk/SM)
+  static const bool xchg_dsmem = [] { const char *e = getenv("TPP_XSMM_XCHG"); return e && e[0] == 'd'; }();
   p.ws = nullptr;
   if (split > 1 && !xchg_dsmem) {
     // per-thread workspace: kernels of one thread run on one stream, so launches are serialised and may share it
@@ -670,9 +697,13 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
     }
     p.ws = ws;
   }
-  if (trace_on && n_ctas <= kTraceCtas) {
+  if (trace_mode == 1 && n_ctas <= kTraceCtas) {
     TPP_CUDA_CHECK(cudaMemsetAsync(trace_buf, 0, sizeof(unsigned long long) * n_ctas * TRACE_SLOTS, stream));
     p.trace = trace_buf;
+  } else if (trace_mode == 2 && n_ctas <= kTraceCtas) {
+    const int slot = g_trace_next++ % kTraceRing;
+    g_trace_ctas[slot] = n_ctas;
+    p.trace = trace_buf + (size_t)slot * kTraceCtas * TRACE_SLOTS;
   }
   switch (d.block_n) {
   case 256: launch_cfg<256, 4, 0>(tmA, tmB, p, grid, stream); break;
@@ -682,7 +713,7 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
     else if (split > 1) launch_cfg<64, 4, 2>(tmA, tmB, p, grid, stream);            //  97 KiB smem: two CTAs per SM
     else launch_cfg<64, 8, 0>(tmA, tmB, p, grid, stream);
   }
-  if (p.trace) {
+  if (p.trace && trace_mode == 1) {
     static int dumps = 0;
     std::vector<unsigned long long> h((size_t)n_ctas * TRACE_SLOTS);
     TPP_CUDA_CHECK(cudaStreamSynchronize(stream));
@@ -705,6 +736,38 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
     }
   }
   return true;
+}
+
+// Debug (TPP_XSMM_TC_TRACE=2): wall-clock timeline of the traced launches, oldest first.
+void brgemm_tc_dump_trace() {
+  if (!g_trace_buf) return;
+  TPP_CUDA_CHECK(cudaDeviceSynchronize());
+  std::vector<unsigned long long> h((size_t)kTraceRing * kTraceRingCtas * TRACE_SLOTS);
+  TPP_CUDA_CHECK(cudaMemcpy(h.data(), g_trace_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  struct Row { unsigned long long start, wait_min, wait_max, end; int slot; };
+  std::vector<Row> rows;
+  for (int s = 0; s < kTraceRing; ++s) {
+    if (!g_trace_ctas[s]) continue;
+    Row r{~0ull, ~0ull, 0, 0, s};
+    for (int c = 0; c < g_trace_ctas[s]; ++c) {
+      const unsigned long long *t = &h[((size_t)s * kTraceRingCtas + c) * TRACE_SLOTS];
+      if (!t[15]) continue;
+      if (t[15] < r.start) r.start = t[15];
+      if (t[13] && t[13] < r.wait_min) r.wait_min = t[13];
+      if (t[13] > r.wait_max) r.wait_max = t[13];
+      if (t[14] > r.end) r.end = t[14];
+    }
+    if (r.end) rows.push_back(r);
+  }
+  std::sort(rows.begin(), rows.end(), [](const Row &a, const Row &b) { return a.start < b.start; });
+  const size_t first = rows.size() > 12 ? rows.size() - 12 : 0;
+  for (size_t i = first; i < rows.size(); ++i) {
+    const Row &r = rows[i];
+    const unsigned long long t0 = rows[first].start;
+    fprintf(stderr, "tc-timeline slot %3d: first CTA start %+7lld ns, PDL wait passed %lld..%lld, last CTA end %lld ns "
+                    "(kernel span %lld ns)\n", r.slot, (long long)(r.start - t0), (long long)(r.wait_min - t0),
+            (long long)(r.wait_max - t0), (long long)(r.end - t0), (long long)(r.end - r.start));
+  }
 }
 
 } // namespace tpp

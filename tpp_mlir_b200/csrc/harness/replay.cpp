@@ -39,15 +39,31 @@ void tpp_replay_mlp(int64_t dtype, int64_t num_layers, const int64_t *handles, c
   }
 }
 
-// Same loop, but each operand set's forward pass is captured once into a CUDA graph
-// (xsmm_cuda_graph_begin/end around the invokes) and replayed: what a perf.bench lowering that
-// captures its body would execute. graphs[i] == 0 means "set i not captured yet".
+// Same loop, but the invoke sequence is captured once into CUDA graphs (xsmm_cuda_graph_begin/end around
+// the invokes) and replayed: what a perf.bench lowering that captures its body would execute.
+// graphs[i] (i < num_sets) replays one forward pass on operand set i; graphs[num_sets] replays one full
+// rotation (num_sets consecutive forward passes, used when `group` != 0 - the loop body unrolled over the
+// rotating operand sets, so the per-graph-launch latency is paid once per rotation). 0 == not captured yet.
 __attribute__((visibility("default")))
 int64_t tpp_replay_mlp_graph(int64_t dtype, int64_t num_layers, const int64_t *handles, const int64_t *layer_sizes,
                              int64_t batch, int64_t bn, int64_t bk, int64_t bc, const TppMlpSet *sets,
-                             int64_t num_sets, int64_t *graphs, int64_t first_step, int64_t steps, int64_t has_bias) {
-  for (int64_t s = 0; s < steps; ++s) {
+                             int64_t num_sets, int64_t *graphs, int64_t first_step, int64_t steps, int64_t has_bias,
+                             int64_t group) {
+  int64_t s = 0;
+  while (s < steps) {
     const int64_t idx = (first_step + s) % num_sets;
+    if (group && idx == 0 && steps - s >= num_sets) {
+      if (!graphs[num_sets]) {
+        if (xsmm_cuda_graph_begin() != 0) return -1;
+        tpp_replay_mlp(dtype, num_layers, handles, layer_sizes, batch, bn, bk, bc, sets, num_sets, 0, num_sets,
+                       has_bias);
+        graphs[num_sets] = xsmm_cuda_graph_end();
+        if (!graphs[num_sets]) return -1;
+      }
+      xsmm_cuda_graph_launch(graphs[num_sets]);
+      s += num_sets;
+      continue;
+    }
     if (!graphs[idx]) {
       if (xsmm_cuda_graph_begin() != 0) return -1;
       tpp_replay_mlp(dtype, num_layers, handles, layer_sizes, batch, bn, bk, bc, sets + idx, 1, 0, 1, has_bias);
@@ -55,6 +71,7 @@ int64_t tpp_replay_mlp_graph(int64_t dtype, int64_t num_layers, const int64_t *h
       if (!graphs[idx]) return -1;
     }
     xsmm_cuda_graph_launch(graphs[idx]);
+    ++s;
   }
   return 0;
 }

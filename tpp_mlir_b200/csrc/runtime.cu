@@ -838,3 +838,4 @@ extern "C" const char *xsmm_cuda_handle_kernel(int64_t addr) {
   return (d && d->magic == kDescMagic) ? d->name : "";
 }
 extern "C" int64_t xsmm_cuda_abi_version(void) { return 1; }
+extern "C" void xsmm_cuda_debug_dump_trace(void) { brgemm_tc_dump_trace(); }

@@ -198,7 +198,7 @@ def replay_lib():
         lib.tpp_replay_mlp.restype = None
         lib.tpp_replay_mlp_e2e.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, i64, i64]
         lib.tpp_replay_mlp_e2e.restype = None
-        lib.tpp_replay_mlp_graph.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, p, i64, i64, i64]
+        lib.tpp_replay_mlp_graph.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, p, i64, i64, i64, i64]
         lib.tpp_replay_mlp_graph.restype = i64
         _replay_lib = lib
     return _replay_lib
@@ -235,16 +235,17 @@ class NativeMlpLoop:
                                     self._sets, self.num_sets, self._step, steps, 1 if cfg.bias else 0)
         self._step += steps
 
-    def run_graph(self, steps: int) -> None:
-        """Like run(), but each operand set's forward pass is captured once into a CUDA graph
-        (xsmm_cuda_graph_begin/end) and replayed with one host call per step."""
+    def run_graph(self, steps: int, group: bool = True) -> None:
+        """Like run(), but the invoke sequence is captured once into CUDA graphs (xsmm_cuda_graph_begin/end)
+        and replayed: one graph per operand set, plus - with ``group`` - one graph holding a full rotation
+        over all operand sets, so a graph launch covers ``num_sets`` forward passes."""
         cfg = self.cfg
         bn, bk, bc = cfg.tiles
         if not hasattr(self, "_graphs"):
-            self._graphs = (_ct.c_int64 * self.num_sets)()
+            self._graphs = (_ct.c_int64 * (self.num_sets + 1))()
         rc = replay_lib().tpp_replay_mlp_graph(cfg.dtype, cfg.num_layers, self._handles, self._sizes, cfg.batch, bn,
                                                bk, bc, self._sets, self.num_sets, self._graphs, self._step, steps,
-                                               1 if cfg.bias else 0)
+                                               1 if cfg.bias else 0, 1 if group else 0)
         if rc != 0:
             raise RuntimeError("CUDA graph capture of the MLP forward failed")
         self._step += steps

@@ -70,6 +70,7 @@ EXPORTS = {
     "xsmm_cuda_last_kernel": (c_char_p, []),
     "xsmm_cuda_handle_kernel": (c_char_p, [c_int64]),
     "xsmm_cuda_abi_version": (c_int64, []),
+    "xsmm_cuda_debug_dump_trace": (None, []),
 }
 
 
