@@ -209,7 +209,7 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from tpp_mlir_b200 import harness, xsmm
+    from tpp_mlir_b200 import harness, shard, xsmm
 
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device: this backend has no CPU path"}))
@@ -240,10 +240,10 @@ def main():
                  for c, k in zip(LAYERS[:-1], LAYERS[1:])]
         b_dev = [torch.empty(k, dtype=torch.int16, device=dev) for k in LAYERS[1:]]
         x_dev_all = torch.empty(BATCH_PER_GPU * n_gpus, LAYERS[0], dtype=torch.int16, device=dev)
-    if n_gpus > 1:
-        for t in w_dev + b_dev + [x_dev_all]:
-            dist.broadcast(t, src=0)  # the one collective of this path: parameters, once, outside the timed loop
-    x_shard = x_dev_all[rank * BATCH_PER_GPU:(rank + 1) * BATCH_PER_GPU].contiguous()
+    # the one collective of this path: parameters (and the synthetic input), once, outside the timed loop
+    shard.broadcast_parameters(w_dev + b_dev + [x_dev_all], src=0)
+    lo, hi = shard.shard_bounds(BATCH_PER_GPU * n_gpus, rank, n_gpus, tile_m=bn)
+    x_shard = x_dev_all[lo:hi].contiguous()
     x_packed = harness.pack_activation(x_shard, bn, bc)
 
     # ---- rotate more bytes than the L2 holds so every step streams its operands from HBM ----
@@ -286,10 +286,7 @@ def main():
     launches = xsmm.launch_count() - launches0
     sampler.stop()
     ms = ev0.elapsed_time(ev1)
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if n_gpus > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max = shard.max_over_ranks(ms, device=dev)
     ms_per_step = ms_max / args.steps
     flops_step_rank = cfg.flops()
     value = flops_step_rank * n_gpus / (ms_per_step * 1e-3) / 1e9
@@ -353,10 +350,7 @@ def main():
     e2e_loop.run_e2e(e2e_steps)
     torch.cuda.synchronize(dev)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if n_gpus > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    e2e_s = shard.max_over_ranks(e2e_s, device=dev)
     e2e_value = flops_step_rank * n_gpus / e2e_s / 1e9
     e2e_out = oracle.bf16_to_f32(harness.unpack_activation(
         h_acts[-1].reshape(BATCH_PER_GPU // bn, LAYERS[-1] // bk, bn, bk))[:8].numpy().view(np.uint16))
