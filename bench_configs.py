@@ -1,0 +1,197 @@
+#!/usr/bin/env python
+"""bench_configs.py - the BASELINE.json configurations that are NOT the headline line of bench.py,
+measured through the same C-ABI on one B200, each against the roofline that bounds it:
+
+  cfg2   single BRGEMM bf16 M=N=K=1024, batch 16 (34.36 GFLOP)            -> tensor peak
+  cfg3b  MLP layer as the strided view k=64 x batch 16 (same math as cfg3)  -> tensor peak
+  cfg4   unary vnni_2 4096x4096 bf16 (+ inverse, transpose, relu, bias add) -> HBM bandwidth
+  cfg5   MLP 3x1024^2 at batch 2048 on one GPU (what 8 GPUs shard)          -> tensor peak
+
+Writes one JSON line per config to stdout (and to --out). Operands rotate over more bytes than the
+126 MiB L2; time = CUDA events on the launch stream after warm-up.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from bench import peaks  # noqa: E402
+from tpp_mlir_b200 import harness, xsmm  # noqa: E402
+
+L2 = 126 << 20
+BF16 = xsmm.BF16
+
+
+def timed(launchers, iters, warmup=5):
+    """launchers: list of zero-arg callables (one per rotating operand set)."""
+    stream = torch.cuda.current_stream()
+    xsmm.set_stream(stream.cuda_stream)
+    for i in range(warmup):
+        launchers[i % len(launchers)]()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(iters):
+        launchers[i % len(launchers)]()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / iters
+
+
+def rnd(*shape):
+    return (torch.rand(*shape, device="cuda") * 0.5).to(torch.bfloat16)
+
+
+def sets_needed(bytes_per_set):
+    return L2 // bytes_per_set + 2
+
+
+def cfg2(pk):
+    m = n = k = 1024
+    batch = 16
+    h = xsmm.brgemm_dispatch(BF16, m, n, k, k, n, n, m * k, k * n, 4 | 64 | 128)
+    ns = sets_needed(2 * batch * m * k * 2 + m * n * 2)
+    S = [(rnd(batch, m, k), rnd(batch, k, n), torch.empty(m, n, dtype=torch.bfloat16, device="cuda")) for _ in range(ns)]
+    fns = [lambda A=A, B=B, C=C: xsmm.LIB.xsmm_brgemm_invoke(BF16, h, A.data_ptr(), 0, B.data_ptr(), 0, C.data_ptr(), 0, batch)
+           for A, B, C in S]
+    t = timed(fns, 40)
+    # parity on a slab: rows 0..7 against a float64 reduction of the same bf16 data
+    A, B, C = S[0]
+    fns[0]()
+    torch.cuda.synchronize()
+    want = torch.einsum("bik,bkj->ij", A[:, :8].double(), B.double())
+    rel = float(((C[:8].double() - want).abs().max() / want.abs().max()).item())
+    flops = 2.0 * m * n * k * batch
+    return {"config": "cfg2 brgemm bf16 1024x1024x1024 batch 16", "kernel": xsmm.handle_kernel(h), "seconds": t,
+            "gflops": flops / t / 1e9,
+            "roofline": {"bound": "tensor", "achieved": flops / t / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": flops / t / 1e12 / pk["bf16_tflops"], "flops_per_launch": flops,
+                         "algorithmic_bytes": 2 * batch * m * k * 2 + m * n * 2},
+            "rotating_sets": ns, "rel_err_vs_f64": rel}
+
+
+def mlp(pk, batch, name, tiles):
+    layers = (1024,) * 4
+    cfg = harness.MlpConfig(batch=batch, layers=layers, tiles=tiles)
+    bn, bk, bc = tiles
+    set_bytes = 3 * (1024 * 1024 * 2) + 4 * batch * 1024 * 2
+    ns = sets_needed(set_bytes)
+    sets = []
+    for _ in range(ns):
+        acts = [rnd(batch, 1024)] + [torch.empty(batch, 1024, dtype=torch.bfloat16, device="cuda") for _ in range(3)]
+        sets.append((acts, [rnd(1024, 1024) * 0.1 for _ in range(3)], [rnd(1024) for _ in range(3)]))
+    rp = harness.MlpReplay(cfg, sets[0][1], sets[0][2], sets[0][0])
+    loop = harness.NativeMlpLoop(cfg, rp.handles, sets)
+    stream = torch.cuda.current_stream()
+    xsmm.set_stream(stream.cuda_stream)
+    loop.run_graph(2 * ns)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = 20 * ns
+    e0.record(stream)
+    loop.run_graph(steps)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / steps
+    return {"config": name, "kernel": xsmm.handle_kernel(rp.handles[0]), "seconds_per_forward": t,
+            "gflops": cfg.flops() / t / 1e9,
+            "roofline": {"bound": "tensor", "achieved": cfg.flops() / t / 1e12, "peak": pk["bf16_tflops"],
+                         "unit": "TFLOP/s", "frac": cfg.flops() / t / 1e12 / pk["bf16_tflops"]},
+            "rotating_sets": ns, "launches_per_forward": rp.invokes_per_forward}
+
+
+def cfg3b(pk):
+    """One MLP layer issued as the strided BRGEMM view k=64 x batch 16 (lda=1024, stride_a=64, stride_b=65536)."""
+    m, n = 256, 1024
+    h = xsmm.fused_brgemm_dispatch(BF16, m, n, 64, 1024, 1024, 1024, 64, 64 * 1024, 4 | 64 | 128, 0, 5, 4, 1)
+    ns = sets_needed(2 * 1024 * 1024 + 2 * m * 1024 * 2)
+    S = [(rnd(m, 1024), rnd(1024, 1024), torch.empty(m, n, dtype=torch.bfloat16, device="cuda"), rnd(1024)) for _ in range(ns)]
+    fns = [lambda A=A, B=B, C=C, D=D: xsmm.LIB.xsmm_fused_brgemm_invoke(BF16, h, A.data_ptr(), 0, B.data_ptr(), 0,
+                                                                         C.data_ptr(), 0, D.data_ptr(), 0, 16)
+           for A, B, C, D in S]
+    t = timed(fns, 400, warmup=ns)
+    flops = 2.0 * m * n * 1024 + 2 * m * n
+    return {"config": "cfg3b fused_brgemm 256x1024 k=64 x batch 16 (strided view)", "kernel": xsmm.handle_kernel(h),
+            "seconds": t, "gflops": flops / t / 1e9,
+            "roofline": {"bound": "tensor", "achieved": flops / t / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": flops / t / 1e12 / pk["bf16_tflops"]}}
+
+
+def eltwise(pk):
+    out = []
+    m = n = 4096
+    nbytes = m * n * 2
+    ns = sets_needed(2 * nbytes)
+    X = [rnd(m, n) for _ in range(ns)]
+    Y = [torch.empty(m * n, dtype=torch.bfloat16, device="cuda") for _ in range(ns)]
+    bias = rnd(n)
+
+    def run(name, h, invoke, alg_bytes, iters=60):
+        t = timed([lambda i=i: invoke(i) for i in range(ns)], iters, warmup=ns)
+        out.append({"config": name, "kernel": xsmm.handle_kernel(h), "seconds": t, "gbytes_per_s": alg_bytes / t / 1e9,
+                    "reference_convention_gbs(input bytes only)": nbytes / t / 1e9,
+                    "roofline": {"bound": "hbm", "achieved": alg_bytes / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                                 "frac": alg_bytes / t / 1e9 / pk["hbm_gbs"], "algorithmic_bytes": alg_bytes}})
+
+    h = xsmm.unary_dispatch(xsmm.UNARY_VNNI2, BF16, m, n, n, n, 0)
+    run("cfg4 unary vnni_2 pack 4096x4096 bf16", h,
+        lambda i: xsmm.LIB.xsmm_unary_invoke(BF16, h, X[i].data_ptr(), 0, Y[i].data_ptr(), 0), 2 * nbytes)
+    hu = xsmm.unary_dispatch(xsmm.UNARY_UNVNNI2_EXT, BF16, m, n, n, n, 0)
+    run("cfg4 inverse (VNNI2 -> flat) 4096x4096 bf16", hu,
+        lambda i: xsmm.LIB.xsmm_unary_invoke(BF16, hu, X[i].data_ptr(), 0, Y[i].data_ptr(), 0), 2 * nbytes)
+    ht = xsmm.unary_dispatch(xsmm.UNARY_TRANSPOSE, BF16, m, n, n, m, 0)
+    run("unary transpose 4096x4096 bf16", ht,
+        lambda i: xsmm.LIB.xsmm_unary_invoke(BF16, ht, X[i].data_ptr(), 0, Y[i].data_ptr(), 0), 2 * nbytes)
+    hr = xsmm.unary_dispatch(xsmm.UNARY_RELU, BF16, m, n, n, n, 0)
+    run("unary relu 4096x4096 bf16 (out of place)", hr,
+        lambda i: xsmm.LIB.xsmm_unary_invoke(BF16, hr, X[i].data_ptr(), 0, Y[i].data_ptr(), 0), 2 * nbytes)
+    hz = xsmm.unary_dispatch(xsmm.UNARY_ZERO, BF16, m, n, n, n, 0)
+    run("unary zero 4096x4096 bf16", hz,
+        lambda i: xsmm.LIB.xsmm_unary_invoke(BF16, hz, X[i].data_ptr(), 0, Y[i].data_ptr(), 0), nbytes)
+    hb = xsmm.binary_dispatch(xsmm.BINARY_ADD, BF16, m, n, n, n, n, xsmm.BINARY_FLAG_BCAST_COL_IN_0)
+    run("binary add bias(bcast_col_in0) 4096x4096 bf16", hb,
+        lambda i: xsmm.LIB.xsmm_binary_invoke(BF16, hb, bias.data_ptr(), 0, X[i].data_ptr(), 0, Y[i].data_ptr(), 0),
+        2 * nbytes)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=None)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    pk = peaks()
+    torch.cuda.set_device(0)
+    rows = []
+    want = set(args.only.split(",")) if args.only else None
+
+    def on(name):
+        return want is None or name in want
+
+    if on("cfg2"):
+        rows.append(cfg2(pk))
+    if on("cfg3b"):
+        rows.append(cfg3b(pk))
+    if on("cfg4"):
+        rows.extend(eltwise(pk))
+    if on("cfg5"):
+        rows.append(mlp(pk, 2048, "cfg5 MLP 3x1024^2 batch 2048 on ONE GPU (tiles 2048,1024,1024)", (2048, 1024, 1024)))
+        rows.append(mlp(pk, 256, "cfg3 MLP 3x1024^2 batch 256 (graph replay, same as bench.py)", (256, 1024, 1024)))
+    for r in rows:
+        r["peaks"] = pk["source"]
+        print(json.dumps(r))
+    if args.out:
+        with open(args.out, "w") as f:
+            for r in rows:
+                f.write(json.dumps(r) + "\n")
+
+
+if __name__ == "__main__":
+    main()
