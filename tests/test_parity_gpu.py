@@ -229,6 +229,8 @@ TC_SHAPES = [
     # m, n, k, batch
     (128, 64, 64, 1), (128, 128, 128, 2), (256, 256, 64, 4), (32, 32, 32, 32), (64, 48, 96, 3),
     (130, 72, 40, 2), (1, 8, 8, 1), (257, 1000, 136, 2), (256, 1024, 1024, 1), (512, 512, 256, 3),
+    # wide tiles + split-K over a cluster (128x256 split 4, 128x128 split 4, 128x256 split 2, ragged edges)
+    (1024, 1024, 256, 4), (1024, 512, 128, 4), (2048, 1024, 128, 2), (1000, 1000, 264, 3), (1024, 1024, 64, 1),
 ]
 
 
@@ -254,7 +256,8 @@ def test_brgemm_bf16_padded_leading_dims(shape, dev, orc):
 
 
 @pytest.mark.parametrize("fused", [(5, 4, 1), (0, 4, 1), (5, 0, 0), (5, 1, 1), (5, 16, 2), (0, 0, 3)])
-@pytest.mark.parametrize("shape", [(256, 1024, 1024, 1), (64, 64, 32, 8), (129, 65, 72, 2)])
+@pytest.mark.parametrize("shape", [(256, 1024, 1024, 1), (64, 64, 32, 8), (129, 65, 72, 2), (1024, 1024, 128, 4),
+                                   (1024, 520, 192, 2)])
 def test_fused_brgemm_bf16(fused, shape, dev, orc):
     m, n, k, batch = shape
     ld = {} if n % 8 == 0 else dict(ldb=n + 8 - n % 8, ldc=n + 8 - n % 8)  # TMA strides are multiples of 16 B

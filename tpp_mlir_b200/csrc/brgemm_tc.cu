@@ -309,9 +309,86 @@ __device__ __forceinline__ void splitk_epilogue_l2(const TcParams &p, uint32_t t
   if (threadIdx.x == 64) trace_stamp(p, 10);
 }
 
+// Split-K exchange through L2 for the wide tiles (BLOCK_N = 128 / 256, S = 2 or 4, NC = BLOCK_N / S >= 32 columns per
+// owner). Same workspace layout as above. The owner does not keep its own slice in registers across the barrier:
+// after the barrier it re-reads it from TMEM 32 columns at a time, adds the S-1 incoming slices and stores.
+template <int BLOCK_N>
+__device__ __forceinline__ void splitk_epilogue_l2_wide(const TcParams &p, uint32_t tmem_acc, int q, int lane,
+                                                        int64_t m0, int64_t n0, uint32_t rank, bool has_acc) {
+  const int S = p.split_k;
+  const int NC = BLOCK_N / S;          // columns per owner (>= 32)
+  const int NCH = NC / 4;              // 16-byte chunks per owner row
+  const int row_in_tile = q * 32 + lane;
+  const int64_t row = m0 + row_in_tile;
+  const size_t tile = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
+  float4 *ws_tile = reinterpret_cast<float4 *>(p.ws) + tile * (size_t)(S * BLOCK_N / 4 * BLOCK_M);
+  const uint32_t lane_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+  // phase 1: every 32-column chunk this CTA does not own goes to its owner's slot [owner][src = rank]
+#pragma unroll 1
+  for (int c = 0; c < BLOCK_N; c += 32) {
+    const uint32_t owner = static_cast<uint32_t>(c / NC);
+    if (owner == rank) continue;       // warp-uniform
+    uint32_t r[32];
+    if (has_acc) {
+      ptx::tmem_ld_32x32(lane_addr + c, r);
+      ptx::tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) r[e] = 0u;
+    }
+    float4 *dst = ws_tile + ((size_t)(owner * S + rank) * NCH + (c % NC) / 4) * BLOCK_M + row_in_tile;
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      dst[j * BLOCK_M] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+  }
+  if (threadIdx.x == 64) trace_stamp(p, 8);
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  if (threadIdx.x == 64) trace_stamp(p, 9);
+  // phase 2: owned columns, 32 at a time
+#pragma unroll 1
+  for (int c = 0; c < NC; c += 32) {
+    const int64_t col0 = n0 + (int64_t)rank * NC + c;
+    if (col0 >= p.n) break;            // warp-uniform
+    float4 in[3][8];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < S - 1) {
+        const uint32_t src_rank = (rank + 1 + k) & (S - 1);
+        const float4 *src = ws_tile + ((size_t)(rank * S + src_rank) * NCH + c / 4) * BLOCK_M + row_in_tile;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) in[k][j] = __ldcg(src + j * BLOCK_M);
+      }
+    }
+    uint32_t r[32];
+    if (has_acc) {
+      ptx::tmem_ld_32x32(lane_addr + rank * NC + c, r);
+      ptx::tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int e = 0; e < 32; ++e) r[e] = 0u;
+    }
+    float v[32];
+#pragma unroll
+    for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < S - 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[4 * j] += in[k][j].x; v[4 * j + 1] += in[k][j].y; v[4 * j + 2] += in[k][j].z; v[4 * j + 3] += in[k][j].w;
+        }
+      }
+    }
+    if (row < p.m) epilogue_store<32>(v, p, row, col0);
+  }
+  if (threadIdx.x == 64) trace_stamp(p, 10);
+}
+
 // SPLITK: 0 = one CTA per tile, 1 = cluster split-K with DSMEM exchange, 2 = cluster split-K with L2 exchange
 template <int BLOCK_N, int STAGES, int SPLITK>
-__global__ void __launch_bounds__(NUM_THREADS, SPLITK ? 2 : 1)
+__global__ void __launch_bounds__(NUM_THREADS, (SPLITK && BLOCK_N == 64) ? 2 : 1)
 brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   using L = SmemLayout<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
@@ -475,11 +552,13 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           splitk_epilogue<16>(p, tmem_acc, recv_base, q, lane, m0, n0, rank, num_iters > 0);
         else
           splitk_epilogue<32>(p, tmem_acc, recv_base, q, lane, m0, n0, rank, num_iters > 0);
-      } else {
+      } else if constexpr (BLOCK_N == 64) {
         if (p.split_k == 4)
           splitk_epilogue_l2<16>(p, tmem_acc, q, lane, m0, n0, rank, num_iters > 0);
         else
           splitk_epilogue_l2<32>(p, tmem_acc, q, lane, m0, n0, rank, num_iters > 0);
+      } else {
+        splitk_epilogue_l2_wide<BLOCK_N>(p, tmem_acc, q, lane, m0, n0, rank, num_iters > 0);
       }
     } else {
       __syncwarp();   // lane 0 ran the producer / MMA loop; the cluster barrier is warp-aligned
@@ -593,17 +672,40 @@ bool brgemm_tc_supported(const KernelDesc &d) {
   return true;
 }
 
+// Clocks one CTA spends per 64-wide k-block: the MMA itself (M=128: BLOCK_N/2 clk per UMMA_K=16 step) or, more
+// often, the SM's ingest of the A+B stage over the SM<->L2 link (~50 B/clk measured), whichever is larger.
+static double kblock_clocks(int bn) {
+  const double mma = 4.0 * bn / 2.0;
+  const double ingest = (A_STAGE_BYTES + bn * 128.0) / 50.0;
+  return mma > ingest ? mma : ingest;
+}
+static int split_for(int64_t tiles, int64_t total_iters) {
+  int split = 1;
+  while (split < 4 && tiles * (split * 2) <= 148 && total_iters >= 2 * (split * 2)) split *= 2;
+  return split;
+}
+
 void brgemm_tc_configure(KernelDesc &d) {
-  // Largest BLOCK_N that still yields >= ~3/4 of the SMs worth of CTAs; otherwise the
-  // smallest tile (most CTAs) and, at launch, a split of the reduction across a cluster.
+  // Pick BLOCK_N by a small cost model: time ~ waves x (k-blocks per CTA) x clocks per k-block, where the
+  // reduction may be split over a cluster of up to 4 CTAs while the grid stays within one wave (148 SMs).
+  // Wide tiles raise the arithmetic intensity per SM (the SM<->L2 link is the limiter), narrow tiles + split-K
+  // fill the machine when the output has few tiles (the 256 x 1024 MLP layer).
   const int64_t tiles_m = (d.m + BLOCK_M - 1) / BLOCK_M;
-  int bn = 64;
-  for (int cand : {256, 128}) {
-    if (tiles_m * ((d.n + cand - 1) / cand) >= 110) { bn = cand; break; }
+  const int64_t k_iters = (d.k + BLOCK_K - 1) / BLOCK_K;
+  const int64_t iters = k_iters * (d.op == OpClass::Gemm ? 1 : 16);   // batch is a runtime value: assume "many"
+  int best = 64;
+  double best_cost = 1e300;
+  for (int bn : {256, 128, 64}) {
+    if (bn > 64 && d.n <= bn / 2) continue;
+    const int64_t tiles = tiles_m * ((d.n + bn - 1) / bn);
+    const int split = split_for(tiles, iters);
+    const double waves = (double)((tiles * split + 147) / 148);
+    const double cost = waves * kblock_clocks(bn) / split;
+    if (cost < best_cost) { best_cost = cost; best = bn; }
   }
-  d.block_n = bn;
-  d.stages = bn == 64 ? 8 : bn == 128 ? 6 : 4;
-  snprintf(d.name, sizeof(d.name), "brgemm_tc_bf16_128x%dx64", bn);
+  d.block_n = best;
+  d.stages = best == 64 ? 8 : best == 128 ? 6 : 4;
+  snprintf(d.name, sizeof(d.name), "brgemm_tc_bf16_128x%dx64", best);
 }
 
 bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t stream) {
@@ -664,13 +766,9 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   // split the reduction across a cluster while the CTA count stays within one wave and every CTA keeps
   // at least 2 k-blocks
   int split = 1;
-  if (d.block_n == 64) {
+  {
     static const char *env = getenv("TPP_XSMM_SPLITK");   // tuning override, read once
-    if (env) {
-      split = atoi(env);
-    } else {
-      while (split < 4 && tiles * (split * 2) <= 148 && p.total_iters >= 2 * (split * 2)) split *= 2;
-    }
+    split = env ? atoi(env) : split_for(tiles, p.total_iters);
     if (split != 2 && split != 4) split = 1;
   }
   p.split_k = split;
@@ -681,11 +779,11 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   // (TPP_XSMM_XCHG=d; 26.7 us: st.shared::cluster moves only ~17 B/clk/SM)
   static const bool xchg_dsmem = [] { const char *e = getenv("TPP_XSMM_XCHG"); return e && e[0] == 'd'; }();
   p.ws = nullptr;
-  if (split > 1 && !xchg_dsmem) {
+  if (split > 1 && (!xchg_dsmem || d.block_n != 64)) {
     // per-thread workspace: kernels of one thread run on one stream, so launches are serialised and may share it
     thread_local float *ws = nullptr;
     thread_local size_t ws_bytes = 0;
-    const size_t need = (size_t)n_ctas * BLOCK_M * 64 * sizeof(float);
+    const size_t need = (size_t)n_ctas * BLOCK_M * d.block_n * sizeof(float);
     if (need > ws_bytes) {
       cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
       cudaStreamIsCapturing(stream, &cs);
@@ -706,8 +804,14 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
     p.trace = trace_buf + (size_t)slot * kTraceCtas * TRACE_SLOTS;
   }
   switch (d.block_n) {
-  case 256: launch_cfg<256, 4, 0>(tmA, tmB, p, grid, stream); break;
-  case 128: launch_cfg<128, 6, 0>(tmA, tmB, p, grid, stream); break;
+  case 256:
+    if (split > 1) launch_cfg<256, 4, 2>(tmA, tmB, p, grid, stream);
+    else launch_cfg<256, 4, 0>(tmA, tmB, p, grid, stream);
+    break;
+  case 128:
+    if (split > 1) launch_cfg<128, 6, 2>(tmA, tmB, p, grid, stream);
+    else launch_cfg<128, 6, 0>(tmA, tmB, p, grid, stream);
+    break;
   default:
     if (split > 1 && xchg_dsmem) launch_cfg<64, 3, 1>(tmA, tmB, p, grid, stream);   // 105 KiB smem: two CTAs per SM
     else if (split > 1) launch_cfg<64, 4, 2>(tmA, tmB, p, grid, stream);            //  97 KiB smem: two CTAs per SM
