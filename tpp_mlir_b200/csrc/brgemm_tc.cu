@@ -672,6 +672,7 @@ bool brgemm_tc_supported(const KernelDesc &d) {
   return true;
 }
 
+// ---- tile / split selection ----------------------------------------------------------------------------
 // Clocks one CTA spends per 64-wide k-block: the MMA itself (M=128: BLOCK_N/2 clk per UMMA_K=16 step) or, more
 // often, the SM's ingest of the A+B stage over the SM<->L2 link (~50 B/clk measured), whichever is larger.
 static double kblock_clocks(int bn) {
@@ -684,28 +685,39 @@ static int split_for(int64_t tiles, int64_t total_iters) {
   while (split < 4 && tiles * (split * 2) <= 148 && total_iters >= 2 * (split * 2)) split *= 2;
   return split;
 }
-
-void brgemm_tc_configure(KernelDesc &d) {
-  // Pick BLOCK_N by a small cost model: time ~ waves x (k-blocks per CTA) x clocks per k-block, where the
-  // reduction may be split over a cluster of up to 4 CTAs while the grid stays within one wave (148 SMs).
-  // Wide tiles raise the arithmetic intensity per SM (the SM<->L2 link is the limiter), narrow tiles + split-K
-  // fill the machine when the output has few tiles (the 256 x 1024 MLP layer).
+// Small cost model, evaluated per launch (the batch count is a runtime argument):
+//   time ~ waves x [ (k-blocks per CTA) x clocks per k-block + split-K exchange ] ,
+// the reduction may be split over a cluster of up to 4 CTAs while the grid stays within one wave (148 SMs).
+// Wide tiles raise the arithmetic intensity per SM (the SM<->L2 link is the limiter: cfg2 went from 27 % to 61 %
+// of tensor peak with 128x256 tiles), narrow tiles + split-K fill the machine when the output has few tiles
+// (the 256 x 1024 MLP layer).
+static void choose_tile(const KernelDesc &d, int64_t total_iters, int *bn_out, int *split_out) {
   const int64_t tiles_m = (d.m + BLOCK_M - 1) / BLOCK_M;
-  const int64_t k_iters = (d.k + BLOCK_K - 1) / BLOCK_K;
-  const int64_t iters = k_iters * (d.op == OpClass::Gemm ? 1 : 16);   // batch is a runtime value: assume "many"
-  int best = 64;
+  int best = 64, best_split = 1;
   double best_cost = 1e300;
   for (int bn : {256, 128, 64}) {
     if (bn > 64 && d.n <= bn / 2) continue;
     const int64_t tiles = tiles_m * ((d.n + bn - 1) / bn);
-    const int split = split_for(tiles, iters);
+    const int split = split_for(tiles, total_iters);
     const double waves = (double)((tiles * split + 147) / 148);
-    const double cost = waves * kblock_clocks(bn) / split;
-    if (cost < best_cost) { best_cost = cost; best = bn; }
+    const double per_cta_iters = (double)((total_iters + split - 1) / split);
+    double cost = per_cta_iters * kblock_clocks(bn);
+    if (split > 1) cost += 1500.0 + 2.0 * (BLOCK_M * bn * 4.0) * (split - 1) / split / 50.0;   // barrier + ws out/in
+    cost *= waves;
+    if (cost < best_cost) { best_cost = cost; best = bn; best_split = split; }
   }
-  d.block_n = best;
-  d.stages = best == 64 ? 8 : best == 128 ? 6 : 4;
-  snprintf(d.name, sizeof(d.name), "brgemm_tc_bf16_128x%dx64", best);
+  *bn_out = best;
+  *split_out = best_split;
+}
+
+thread_local char t_last_name[64] = "brgemm_tc_bf16";
+const char *brgemm_tc_last_name() { return t_last_name; }
+
+void brgemm_tc_configure(KernelDesc &d) {
+  // the tile shape is chosen per launch (choose_tile); the descriptor only records the family
+  d.block_n = 0;
+  d.stages = 0;
+  snprintf(d.name, sizeof(d.name), "brgemm_tc_bf16_128xNx64");
 }
 
 bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t stream) {
@@ -762,28 +774,33 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   }
   p.trace = nullptr;
 
-  const int64_t tiles = ((d.n + d.block_n - 1) / d.block_n) * ((d.m + BLOCK_M - 1) / BLOCK_M);
+  int block_n = 64, split = 1;
+  choose_tile(d, p.total_iters, &block_n, &split);
   // split the reduction across a cluster while the CTA count stays within one wave and every CTA keeps
   // at least 2 k-blocks
-  int split = 1;
   {
-    static const char *env = getenv("TPP_XSMM_SPLITK");   // tuning override, read once
-    split = env ? atoi(env) : split_for(tiles, p.total_iters);
+    static const char *env_bn = getenv("TPP_XSMM_BLOCK_N");   // tuning overrides, read once
+    static const char *env = getenv("TPP_XSMM_SPLITK");
+    if (env_bn && (atoi(env_bn) == 64 || atoi(env_bn) == 128 || atoi(env_bn) == 256)) {
+      block_n = atoi(env_bn);
+      split = split_for(((d.n + block_n - 1) / block_n) * ((d.m + BLOCK_M - 1) / BLOCK_M), p.total_iters);
+    }
+    if (env) split = atoi(env);
     if (split != 2 && split != 4) split = 1;
   }
   p.split_k = split;
 
-  dim3 grid((unsigned)((d.n + d.block_n - 1) / d.block_n), (unsigned)((d.m + BLOCK_M - 1) / BLOCK_M), (unsigned)split);
+  dim3 grid((unsigned)((d.n + block_n - 1) / block_n), (unsigned)((d.m + BLOCK_M - 1) / BLOCK_M), (unsigned)split);
   const int n_ctas = (int)(grid.x * grid.y * grid.z);
   // exchange path of the split-K partials: the L2 workspace (default; 23.1 us per MLP step) or DSMEM
   // (TPP_XSMM_XCHG=d; 26.7 us: st.shared::cluster moves only ~17 B/clk/SM)
   static const bool xchg_dsmem = [] { const char *e = getenv("TPP_XSMM_XCHG"); return e && e[0] == 'd'; }();
   p.ws = nullptr;
-  if (split > 1 && (!xchg_dsmem || d.block_n != 64)) {
+  if (split > 1 && (!xchg_dsmem || block_n != 64)) {
     // per-thread workspace: kernels of one thread run on one stream, so launches are serialised and may share it
     thread_local float *ws = nullptr;
     thread_local size_t ws_bytes = 0;
-    const size_t need = (size_t)n_ctas * BLOCK_M * d.block_n * sizeof(float);
+    const size_t need = (size_t)n_ctas * BLOCK_M * block_n * sizeof(float);
     if (need > ws_bytes) {
       cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
       cudaStreamIsCapturing(stream, &cs);
@@ -803,7 +820,9 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
     g_trace_ctas[slot] = n_ctas;
     p.trace = trace_buf + (size_t)slot * kTraceCtas * TRACE_SLOTS;
   }
-  switch (d.block_n) {
+  snprintf(t_last_name, sizeof(t_last_name), "brgemm_tc_bf16_128x%dx64%s", block_n,
+           split == 1 ? "" : split == 2 ? "_splitk2" : "_splitk4");
+  switch (block_n) {
   case 256:
     if (split > 1) launch_cfg<256, 4, 2>(tmA, tmB, p, grid, stream);
     else launch_cfg<256, 4, 0>(tmA, tmB, p, grid, stream);

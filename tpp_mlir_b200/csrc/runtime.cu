@@ -425,7 +425,7 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
   bool launched = false;
   if (d->impl == KernelImpl::BrgemmTC) {
     launched = launch_brgemm_tc(*d, g, stream);
-    if (launched) t_ctx.last_kernel = d->name;
+    if (launched) t_ctx.last_kernel = brgemm_tc_last_name();
   }
   if (!launched) {
     launch_brgemm_simt(*d, g, stream);
