@@ -6,10 +6,11 @@
 // lib/TPP/Dialect/Xsmm/XsmmUtils.cpp:90-252).
 //
 // These ops have no data reuse: the design rule is 16-byte vector accesses,
-// fully coalesced on both sides, enough bytes in flight per SM, grid sized in
-// multiples of the SM count. bf16 arithmetic is done in f32 and rounded once
-// (comp_type F32, XsmmRunnerUtils.cpp:161-164,193-195); pure data movement
-// (identity, zero, transpose, vnni) moves bits.
+// fully coalesced on both sides, several independent loads in flight per thread
+// (the first version had one and reached 41-62 % of the HBM copy rate), no integer
+// division in the address path, grids of many small CTAs. bf16 arithmetic is done
+// in f32 and rounded once (comp_type F32, XsmmRunnerUtils.cpp:161-164,193-195); pure
+// data movement (identity, zero, transpose, vnni) moves bits.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -19,8 +20,6 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kNumSMs = 148;
-
-template <typename T> struct Vec16 { uint4 v; };
 
 __device__ __forceinline__ float apply_op(int op, float a, float b) {
   switch (op) {
@@ -74,80 +73,102 @@ __global__ void __launch_bounds__(kThreads) eltwise_scalar_kernel(EltwiseArgs a)
   }
 }
 
-// ---- 16-byte vector path ----------------------------------------------------
-// VEC elements per thread per access (8 bf16 or 4 f32).
-template <typename T, int VEC>
-__device__ __forceinline__ void load_operand(const T *base, int mode, int64_t ld, int64_t i, int64_t j,
-                                             float (&x)[VEC], uint4 &raw) {
-  if (mode == kBcastNone || mode == kBcastCol) {
-    const T *p = mode == kBcastNone ? base + i * ld + j : base + j;
-    raw = *reinterpret_cast<const uint4 *>(p);
-    if constexpr (sizeof(T) == 4) {
-      x[0] = __uint_as_float(raw.x); x[1] = __uint_as_float(raw.y);
-      x[2] = __uint_as_float(raw.z); x[3] = __uint_as_float(raw.w);
-    } else {
-      const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        x[2 * q] = __uint_as_float(w[q] << 16);
-        x[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
-      }
-    }
+// ---- 16-byte vector path ------------------------------------------------------
+// A CTA is 32 column-vectors (32 x 16 B = 512 contiguous bytes per row) x 8 rows; every thread handles
+// ROWS rows (stride 8), so ROWS independent 16-byte loads per operand are in flight before the first use.
+constexpr int ROWS = 4;
+
+template <typename T, int VEC> __device__ __forceinline__ void unpack16(const uint4 &raw, float (&x)[VEC]) {
+  if constexpr (sizeof(T) == 4) {
+    x[0] = __uint_as_float(raw.x); x[1] = __uint_as_float(raw.y);
+    x[2] = __uint_as_float(raw.z); x[3] = __uint_as_float(raw.w);
   } else {
-    const T s = mode == kBcastRow ? base[i * ld] : base[0];
-    float f;
-    uint32_t bits;
-    if constexpr (sizeof(T) == 4) { f = s; bits = __float_as_uint(f); }
-    else { f = bf16_bits_to_f32(s); bits = (uint32_t)s | ((uint32_t)s << 16); }
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) x[q] = f;
-    raw = make_uint4(bits, bits, bits, bits);
+    for (int q = 0; q < 4; ++q) {
+      x[2 * q] = __uint_as_float(w[q] << 16);
+      x[2 * q + 1] = __uint_as_float(w[q] & 0xffff0000u);
+    }
   }
+}
+
+template <typename T> __device__ __forceinline__ uint4 splat16(T s) {
+  uint32_t bits;
+  if constexpr (sizeof(T) == 4) bits = __float_as_uint(s); else bits = (uint32_t)s | ((uint32_t)s << 16);
+  return make_uint4(bits, bits, bits, bits);
+}
+
+// raw 16 bytes of operand `base` for row i, first column j
+template <typename T>
+__device__ __forceinline__ uint4 load16(const T *base, int mode, int64_t ld, int64_t i, int64_t j) {
+  if (mode == kBcastNone) return *reinterpret_cast<const uint4 *>(base + i * ld + j);
+  if (mode == kBcastCol) return *reinterpret_cast<const uint4 *>(base + j);
+  return splat16<T>(mode == kBcastRow ? base[i * ld] : base[0]);
 }
 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads) eltwise_vec_kernel(EltwiseArgs a) {
   const int64_t nv = a.n / VEC;
-  const int64_t total = a.m * nv;
+  const int64_t cv = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  if (cv >= nv) return;
+  const int64_t j = cv * VEC;
+  const int ty = threadIdx.x >> 5;
   const T *in0 = static_cast<const T *>(a.in0);
   const T *in1 = static_cast<const T *>(a.in1);
   T *out = static_cast<T *>(a.out);
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t i = idx / nv, j = (idx - i * nv) * VEC;
-    uint4 *dst = reinterpret_cast<uint4 *>(out + i * a.ldo + j);
-    if (a.op == kOpZero) {
-      *dst = make_uint4(0, 0, 0, 0);
-      continue;
-    }
-    float x[VEC], y[VEC];
-    uint4 raw0, raw1;
-    load_operand<T, VEC>(in0, a.mode0, a.ld0, i, j, x, raw0);
-    if (a.op == kOpIdentity) {
-      *dst = raw0;
-      continue;
-    }
-    if (a.op >= kOpAdd) load_operand<T, VEC>(in1, a.mode1, a.ld1, i, j, y, raw1);
-    float r[VEC];
+  for (int64_t r0 = (int64_t)blockIdx.y * (8 * ROWS) + ty; r0 < a.m; r0 += (int64_t)gridDim.y * (8 * ROWS)) {
+    uint4 raw0[ROWS], raw1[ROWS];
+    if (a.op != kOpZero) {
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) r[q] = apply_op(a.op, x[q], a.op >= kOpAdd ? y[q] : 0.f);
-    uint4 o;
-    if constexpr (sizeof(T) == 4) {
-      o = make_uint4(__float_as_uint(r[0]), __float_as_uint(r[1]), __float_as_uint(r[2]), __float_as_uint(r[3]));
-    } else {
-      o = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
-                     pack_bf16x2(r[6], r[7]));
+      for (int u = 0; u < ROWS; ++u) {
+        const int64_t i = r0 + 8 * u;
+        if (i < a.m) {
+          raw0[u] = load16<T>(in0, a.mode0, a.ld0, i, j);
+          if (a.op >= kOpAdd) raw1[u] = load16<T>(in1, a.mode1, a.ld1, i, j);
+        }
+      }
     }
-    *dst = o;
+#pragma unroll
+    for (int u = 0; u < ROWS; ++u) {
+      const int64_t i = r0 + 8 * u;
+      if (i >= a.m) break;
+      uint4 o;
+      if (a.op == kOpZero) {
+        o = make_uint4(0, 0, 0, 0);
+      } else if (a.op == kOpIdentity) {
+        o = raw0[u];
+      } else {
+        float x[VEC], y[VEC], r[VEC];
+        unpack16<T, VEC>(raw0[u], x);
+        if (a.op >= kOpAdd) unpack16<T, VEC>(raw1[u], y);
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) r[q] = apply_op(a.op, x[q], a.op >= kOpAdd ? y[q] : 0.f);
+        if constexpr (sizeof(T) == 4)
+          o = make_uint4(__float_as_uint(r[0]), __float_as_uint(r[1]), __float_as_uint(r[2]), __float_as_uint(r[3]));
+        else
+          o = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                         pack_bf16x2(r[6], r[7]));
+      }
+      *reinterpret_cast<uint4 *>(out + i * a.ldo + j) = o;
+    }
   }
 }
 
 inline int grid_for(int64_t work_items) {
   int64_t blocks = (work_items + kThreads - 1) / kThreads;
-  const int64_t cap = (int64_t)kNumSMs * 16; // 8 resident 256-thread CTAs per SM x 2 waves, grid-stride beyond
+  const int64_t cap = (int64_t)kNumSMs * 16;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
+}
+
+// 2-D grid of (32 column-vectors) x (8 * rows_per_thread rows) tiles; y is capped, the kernel strides over it
+inline dim3 grid2d(int64_t nvec, int64_t rows, int rows_per_cta) {
+  int64_t gx = (nvec + 31) / 32, gy = (rows + rows_per_cta - 1) / rows_per_cta;
+  const int64_t cap = (int64_t)kNumSMs * 32;
+  if (gx * gy > cap) gy = cap / gx > 0 ? cap / gx : 1;
+  if (gy > 65535) gy = 65535;
+  return dim3((unsigned)gx, (unsigned)gy, 1);
 }
 
 inline bool operand_vec_ok(const void *p, int mode, int64_t ld, int vec) {
@@ -157,8 +178,7 @@ inline bool operand_vec_ok(const void *p, int mode, int64_t ld, int vec) {
 }
 
 // ---- transpose --------------------------------------------------------------
-// 64x64 element tile through shared memory; reads and writes are both coalesced
-// along the contiguous dimension. T is the element type (uint16_t / uint32_t).
+// Generic: 64x64 element tile through shared memory, element-wise (any size / alignment).
 template <typename T>
 __global__ void __launch_bounds__(256) transpose_kernel(const T *__restrict__ in, T *__restrict__ out, int64_t m,
                                                         int64_t n, int64_t ldi, int64_t ldo) {
@@ -184,27 +204,79 @@ __global__ void __launch_bounds__(256) transpose_kernel(const T *__restrict__ in
   }
 }
 
+// bf16, even m / n / ld, 4-byte aligned: every global and shared access is 32 bits wide. A thread loads the
+// 2x2 block (rows 2rp,2rp+1 x cols 2cp,2cp+1) as two words, transposes it in registers with two byte-permutes
+// and stores the two words of the transposed tile; the write phase reads full 128-byte output rows.
+__global__ void __launch_bounds__(256) transpose_bf16_pair_kernel(const uint16_t *__restrict__ in,
+                                                                  uint16_t *__restrict__ out, int64_t m, int64_t n,
+                                                                  int64_t ldi, int64_t ldo) {
+  __shared__ uint32_t tile[64][33];   // [output row within tile (input column)][input row pair]
+  const int64_t tiles_n = (n + 63) / 64;
+  const int64_t i0 = (int64_t)(blockIdx.x / tiles_n) * 64, j0 = (int64_t)(blockIdx.x % tiles_n) * 64;
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  uint32_t w0[4], w1[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {   // all loads first
+    const int rp = y + 8 * u;
+    const int64_t i = i0 + 2 * rp, j = j0 + 2 * x;
+    w0[u] = w1[u] = 0;
+    if (i < m && j < n) {
+      w0[u] = *reinterpret_cast<const uint32_t *>(in + i * ldi + j);
+      w1[u] = *reinterpret_cast<const uint32_t *>(in + (i + 1) * ldi + j);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int rp = y + 8 * u;
+    tile[2 * x][rp] = __byte_perm(w0[u], w1[u], 0x5410);       // (in[2rp][2x],   in[2rp+1][2x])
+    tile[2 * x + 1][rp] = __byte_perm(w0[u], w1[u], 0x7632);   // (in[2rp][2x+1], in[2rp+1][2x+1])
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int c = y + 8 * u;                 // output row within the tile
+    const int64_t jo = j0 + c, io = i0 + 2 * x;
+    if (jo < n && io < m) *reinterpret_cast<uint32_t *>(out + jo * ldo + io) = tile[c][x];
+  }
+}
+
 // ---- VNNI-2 pack / unpack -----------------------------------------------------
 // pack:  out[((p/2)*ldo + j)*2 + p%2] = in[p*ldi + j]   (p<m=K, j<n=N)
-// Each thread owns one row pair (2q, 2q+1) x 8 columns: two 16-byte loads, one
-// 32-byte contiguous interleaved store.
+// A thread owns 8 columns of PAIRS row pairs (stride 8 pairs): 2*PAIRS 16-byte loads in flight, then
+// one 32-byte contiguous interleaved store per pair.
+constexpr int PAIRS = 2;
+
 __global__ void __launch_bounds__(kThreads) vnni2_pack_vec_kernel(const uint16_t *__restrict__ in,
                                                                  uint16_t *__restrict__ out, int64_t m, int64_t n,
                                                                  int64_t ldi, int64_t ldo) {
-  const int64_t nv = n / 8, total = (m / 2) * nv;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t q = idx / nv, j = (idx - q * nv) * 8;
-    const uint4 r0 = *reinterpret_cast<const uint4 *>(in + (2 * q) * ldi + j);
-    const uint4 r1 = *reinterpret_cast<const uint4 *>(in + (2 * q + 1) * ldi + j);
-    uint4 o0, o1;
-    o0.x = __byte_perm(r0.x, r1.x, 0x5410); o0.y = __byte_perm(r0.x, r1.x, 0x7632);
-    o0.z = __byte_perm(r0.y, r1.y, 0x5410); o0.w = __byte_perm(r0.y, r1.y, 0x7632);
-    o1.x = __byte_perm(r0.z, r1.z, 0x5410); o1.y = __byte_perm(r0.z, r1.z, 0x7632);
-    o1.z = __byte_perm(r0.w, r1.w, 0x5410); o1.w = __byte_perm(r0.w, r1.w, 0x7632);
-    uint4 *dst = reinterpret_cast<uint4 *>(out + (q * ldo + j) * 2);
-    dst[0] = o0;
-    dst[1] = o1;
+  const int64_t nv = n / 8, np = m / 2;
+  const int64_t cv = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  if (cv >= nv) return;
+  const int64_t j = cv * 8;
+  const int ty = threadIdx.x >> 5;
+  for (int64_t q0 = (int64_t)blockIdx.y * (8 * PAIRS) + ty; q0 < np; q0 += (int64_t)gridDim.y * (8 * PAIRS)) {
+    uint4 r0[PAIRS], r1[PAIRS];
+#pragma unroll
+    for (int u = 0; u < PAIRS; ++u) {
+      const int64_t q = q0 + 8 * u;
+      if (q < np) {
+        r0[u] = *reinterpret_cast<const uint4 *>(in + (2 * q) * ldi + j);
+        r1[u] = *reinterpret_cast<const uint4 *>(in + (2 * q + 1) * ldi + j);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PAIRS; ++u) {
+      const int64_t q = q0 + 8 * u;
+      if (q >= np) break;
+      uint4 o0, o1;
+      o0.x = __byte_perm(r0[u].x, r1[u].x, 0x5410); o0.y = __byte_perm(r0[u].x, r1[u].x, 0x7632);
+      o0.z = __byte_perm(r0[u].y, r1[u].y, 0x5410); o0.w = __byte_perm(r0[u].y, r1[u].y, 0x7632);
+      o1.x = __byte_perm(r0[u].z, r1[u].z, 0x5410); o1.y = __byte_perm(r0[u].z, r1[u].z, 0x7632);
+      o1.z = __byte_perm(r0[u].w, r1[u].w, 0x5410); o1.w = __byte_perm(r0[u].w, r1[u].w, 0x7632);
+      uint4 *dst = reinterpret_cast<uint4 *>(out + (q * ldo + j) * 2);
+      dst[0] = o0;
+      dst[1] = o1;
+    }
   }
 }
 
@@ -223,19 +295,34 @@ __global__ void __launch_bounds__(kThreads) vnni2_pack_scalar_kernel(const uint1
 __global__ void __launch_bounds__(kThreads) vnni2_unpack_vec_kernel(const uint16_t *__restrict__ in,
                                                                    uint16_t *__restrict__ out, int64_t m, int64_t n,
                                                                    int64_t ldi, int64_t ldo) {
-  const int64_t nv = n / 8, total = (m / 2) * nv;
-  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t q = idx / nv, j = (idx - q * nv) * 8;
-    const uint4 *src = reinterpret_cast<const uint4 *>(in + (q * ldi + j) * 2);
-    const uint4 a = src[0], b = src[1];
-    uint4 r0, r1;
-    r0.x = __byte_perm(a.x, a.y, 0x5410); r1.x = __byte_perm(a.x, a.y, 0x7632);
-    r0.y = __byte_perm(a.z, a.w, 0x5410); r1.y = __byte_perm(a.z, a.w, 0x7632);
-    r0.z = __byte_perm(b.x, b.y, 0x5410); r1.z = __byte_perm(b.x, b.y, 0x7632);
-    r0.w = __byte_perm(b.z, b.w, 0x5410); r1.w = __byte_perm(b.z, b.w, 0x7632);
-    *reinterpret_cast<uint4 *>(out + (2 * q) * ldo + j) = r0;
-    *reinterpret_cast<uint4 *>(out + (2 * q + 1) * ldo + j) = r1;
+  const int64_t nv = n / 8, np = m / 2;
+  const int64_t cv = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  if (cv >= nv) return;
+  const int64_t j = cv * 8;
+  const int ty = threadIdx.x >> 5;
+  for (int64_t q0 = (int64_t)blockIdx.y * (8 * PAIRS) + ty; q0 < np; q0 += (int64_t)gridDim.y * (8 * PAIRS)) {
+    uint4 a[PAIRS], b[PAIRS];
+#pragma unroll
+    for (int u = 0; u < PAIRS; ++u) {
+      const int64_t q = q0 + 8 * u;
+      if (q < np) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(in + (q * ldi + j) * 2);
+        a[u] = src[0];
+        b[u] = src[1];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PAIRS; ++u) {
+      const int64_t q = q0 + 8 * u;
+      if (q >= np) break;
+      uint4 r0, r1;
+      r0.x = __byte_perm(a[u].x, a[u].y, 0x5410); r1.x = __byte_perm(a[u].x, a[u].y, 0x7632);
+      r0.y = __byte_perm(a[u].z, a[u].w, 0x5410); r1.y = __byte_perm(a[u].z, a[u].w, 0x7632);
+      r0.z = __byte_perm(b[u].x, b[u].y, 0x5410); r1.z = __byte_perm(b[u].x, b[u].y, 0x7632);
+      r0.w = __byte_perm(b[u].z, b[u].w, 0x5410); r1.w = __byte_perm(b[u].z, b[u].w, 0x7632);
+      *reinterpret_cast<uint4 *>(out + (2 * q) * ldo + j) = r0;
+      *reinterpret_cast<uint4 *>(out + (2 * q + 1) * ldo + j) = r1;
+    }
   }
 }
 
@@ -252,15 +339,28 @@ __global__ void __launch_bounds__(kThreads) vnni2_unpack_scalar_kernel(const uin
 
 } // namespace
 
-void launch_eltwise(const EltwiseArgs &a, cudaStream_t stream) {
-  if (a.m <= 0 || a.n <= 0) return;
+void launch_eltwise(const EltwiseArgs &a_in, cudaStream_t stream) {
+  if (a_in.m <= 0 || a_in.n <= 0) return;
+  EltwiseArgs a = a_in;
   const bool f32 = a.dtype == kF32;
   const int vec = f32 ? 4 : 8;
+  // fully contiguous operands (no row/col broadcast): re-shape to rows of 8192 elements so that tall-skinny
+  // tensors still give every lane a 16-byte vector
+  auto contiguous = [&](int mode, int64_t ld) { return (mode == kBcastNone && ld == a.n) || mode >= kBcastScalar; };
+  if (a.ldo == a.n && (a.op == kOpZero || contiguous(a.mode0, a.ld0)) && (a.op < kOpAdd || contiguous(a.mode1, a.ld1))) {
+    const int64_t total = a.m * a.n;
+    if (a.n < 2048 && total % 8192 == 0) {
+      a.n = 8192; a.m = total / 8192;
+      a.ldo = 8192;
+      if (a.mode0 == kBcastNone) a.ld0 = 8192;
+      if (a.mode1 == kBcastNone) a.ld1 = 8192;
+    }
+  }
   bool vec_ok = (a.n % vec) == 0 && aligned16(a.out) && (a.ldo % vec) == 0;
   if (a.op != kOpZero) vec_ok = vec_ok && a.mode0 != kBcastImm && operand_vec_ok(a.in0, a.mode0, a.ld0, vec);
   if (a.op >= kOpAdd) vec_ok = vec_ok && operand_vec_ok(a.in1, a.mode1, a.ld1, vec);
   if (vec_ok) {
-    const int grid = grid_for(a.m * (a.n / vec));
+    const dim3 grid = grid2d(a.n / vec, a.m, 8 * ROWS);
     if (f32) eltwise_vec_kernel<float, 4><<<grid, kThreads, 0, stream>>>(a);
     else eltwise_vec_kernel<uint16_t, 8><<<grid, kThreads, 0, stream>>>(a);
   } else {
@@ -275,13 +375,21 @@ void launch_transpose(const void *in, void *out, int64_t m, int64_t n, int64_t l
                       cudaStream_t stream) {
   if (m <= 0 || n <= 0) return;
   const int64_t tiles = ((m + 63) / 64) * ((n + 63) / 64);
-  const int grid = (int)(tiles < (int64_t)kNumSMs * 8 ? tiles : (int64_t)kNumSMs * 8);
-  if (es == 4)
-    transpose_kernel<uint32_t><<<grid, 256, 0, stream>>>(static_cast<const uint32_t *>(in),
-                                                         static_cast<uint32_t *>(out), m, n, ldi, ldo);
-  else
-    transpose_kernel<uint16_t><<<grid, 256, 0, stream>>>(static_cast<const uint16_t *>(in),
-                                                         static_cast<uint16_t *>(out), m, n, ldi, ldo);
+  const bool pair_ok = es == 2 && (m % 2) == 0 && (n % 2) == 0 && (ldi % 2) == 0 && (ldo % 2) == 0 &&
+                       (reinterpret_cast<uintptr_t>(in) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0 &&
+                       tiles < (1ll << 31);
+  if (pair_ok) {
+    transpose_bf16_pair_kernel<<<(unsigned)tiles, 256, 0, stream>>>(static_cast<const uint16_t *>(in),
+                                                                    static_cast<uint16_t *>(out), m, n, ldi, ldo);
+  } else {
+    const int grid = (int)(tiles < (int64_t)kNumSMs * 8 ? tiles : (int64_t)kNumSMs * 8);
+    if (es == 4)
+      transpose_kernel<uint32_t><<<grid, 256, 0, stream>>>(static_cast<const uint32_t *>(in),
+                                                           static_cast<uint32_t *>(out), m, n, ldi, ldo);
+    else
+      transpose_kernel<uint16_t><<<grid, 256, 0, stream>>>(static_cast<const uint16_t *>(in),
+                                                           static_cast<uint16_t *>(out), m, n, ldi, ldo);
+  }
   TPP_CUDA_CHECK(cudaGetLastError());
 }
 
@@ -292,7 +400,7 @@ void launch_vnni2_pack(const void *in, void *out, int64_t m, int64_t n, int64_t 
   uint16_t *dst = static_cast<uint16_t *>(out);
   const bool vec_ok = (n % 8) == 0 && (ldi % 8) == 0 && (ldo % 4) == 0 && aligned16(in) && aligned16(out);
   if (vec_ok)
-    vnni2_pack_vec_kernel<<<grid_for((m / 2) * (n / 8)), kThreads, 0, stream>>>(src, dst, m, n, ldi, ldo);
+    vnni2_pack_vec_kernel<<<grid2d(n / 8, m / 2, 8 * PAIRS), kThreads, 0, stream>>>(src, dst, m, n, ldi, ldo);
   else
     vnni2_pack_scalar_kernel<<<grid_for(m * n), kThreads, 0, stream>>>(src, dst, m, n, ldi, ldo);
   TPP_CUDA_CHECK(cudaGetLastError());
@@ -305,7 +413,7 @@ void launch_vnni2_unpack(const void *in, void *out, int64_t m, int64_t n, int64_
   uint16_t *dst = static_cast<uint16_t *>(out);
   const bool vec_ok = (n % 8) == 0 && (ldo % 8) == 0 && (ldi % 4) == 0 && aligned16(in) && aligned16(out);
   if (vec_ok)
-    vnni2_unpack_vec_kernel<<<grid_for((m / 2) * (n / 8)), kThreads, 0, stream>>>(src, dst, m, n, ldi, ldo);
+    vnni2_unpack_vec_kernel<<<grid2d(n / 8, m / 2, 8 * PAIRS), kThreads, 0, stream>>>(src, dst, m, n, ldi, ldo);
   else
     vnni2_unpack_scalar_kernel<<<grid_for(m * n), kThreads, 0, stream>>>(src, dst, m, n, ldi, ldo);
   TPP_CUDA_CHECK(cudaGetLastError());
