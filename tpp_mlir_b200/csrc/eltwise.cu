@@ -75,8 +75,7 @@ __global__ void __launch_bounds__(kThreads) eltwise_scalar_kernel(EltwiseArgs a)
 
 // ---- 16-byte vector path ------------------------------------------------------
 // A CTA is 32 column-vectors (32 x 16 B = 512 contiguous bytes per row) x 8 rows; every thread handles
-// ROWS rows (stride 8), so ROWS independent 16-byte loads per operand are in flight before the first use.
-constexpr int ROWS = 4;
+// R rows (stride 8), so R independent 16-byte loads per operand are in flight before the first use.
 
 template <typename T, int VEC> __device__ __forceinline__ void unpack16(const uint4 &raw, float (&x)[VEC]) {
   if constexpr (sizeof(T) == 4) {
@@ -106,8 +105,19 @@ __device__ __forceinline__ uint4 load16(const T *base, int mode, int64_t ld, int
   return splat16<T>(mode == kBcastRow ? base[i * ld] : base[0]);
 }
 
-template <typename T, int VEC>
-__global__ void __launch_bounds__(kThreads) eltwise_vec_kernel(EltwiseArgs a) {
+// 2-D grid of (32 column-vectors) x (8 * rows_per_thread rows) tiles; y is capped, the kernel strides over it
+inline dim3 grid2d(int64_t nvec, int64_t rows, int rows_per_cta) {
+  int64_t gx = (nvec + 31) / 32, gy = (rows + rows_per_cta - 1) / rows_per_cta;
+  const int64_t cap = (int64_t)kNumSMs * 32;
+  if (gx * gy > cap) gy = cap / gx > 0 ? cap / gx : 1;
+  if (gy > 65535) gy = 65535;
+  return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
+// NIN = number of tensor inputs (0: zero, 1: identity / relu, 2: binary), R = rows per thread. Specialising on
+// NIN keeps the register count low enough for 5-6 resident CTAs per SM (about 100 KiB of loads in flight per SM).
+template <typename T, int VEC, int NIN, int R>
+__global__ void __launch_bounds__(kThreads, NIN == 2 ? 4 : 5) eltwise_vec_kernel(EltwiseArgs a) {
   const int64_t nv = a.n / VEC;
   const int64_t cv = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
   if (cv >= nv) return;
@@ -116,42 +126,53 @@ __global__ void __launch_bounds__(kThreads) eltwise_vec_kernel(EltwiseArgs a) {
   const T *in0 = static_cast<const T *>(a.in0);
   const T *in1 = static_cast<const T *>(a.in1);
   T *out = static_cast<T *>(a.out);
-  for (int64_t r0 = (int64_t)blockIdx.y * (8 * ROWS) + ty; r0 < a.m; r0 += (int64_t)gridDim.y * (8 * ROWS)) {
-    uint4 raw0[ROWS], raw1[ROWS];
-    if (a.op != kOpZero) {
+  for (int64_t r0 = (int64_t)blockIdx.y * (8 * R) + ty; r0 < a.m; r0 += (int64_t)gridDim.y * (8 * R)) {
+    uint4 raw0[R], raw1[R];
+    if constexpr (NIN >= 1) {
 #pragma unroll
-      for (int u = 0; u < ROWS; ++u) {
+      for (int u = 0; u < R; ++u) {
         const int64_t i = r0 + 8 * u;
         if (i < a.m) {
           raw0[u] = load16<T>(in0, a.mode0, a.ld0, i, j);
-          if (a.op >= kOpAdd) raw1[u] = load16<T>(in1, a.mode1, a.ld1, i, j);
+          if constexpr (NIN == 2) raw1[u] = load16<T>(in1, a.mode1, a.ld1, i, j);
         }
       }
     }
 #pragma unroll
-    for (int u = 0; u < ROWS; ++u) {
+    for (int u = 0; u < R; ++u) {
       const int64_t i = r0 + 8 * u;
-      if (i >= a.m) break;
+      if (i >= a.m) continue;   // (not break: keeps the loop fully unrolled and raw*[] in registers)
       uint4 o;
-      if (a.op == kOpZero) {
+      if constexpr (NIN == 0) {
         o = make_uint4(0, 0, 0, 0);
-      } else if (a.op == kOpIdentity) {
-        o = raw0[u];
       } else {
-        float x[VEC], y[VEC], r[VEC];
-        unpack16<T, VEC>(raw0[u], x);
-        if (a.op >= kOpAdd) unpack16<T, VEC>(raw1[u], y);
+        if (NIN == 1 && a.op == kOpIdentity) {
+          o = raw0[u];
+        } else {
+          float x[VEC], y[VEC], r[VEC];
+          unpack16<T, VEC>(raw0[u], x);
+          if constexpr (NIN == 2) unpack16<T, VEC>(raw1[u], y);
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) r[q] = apply_op(a.op, x[q], a.op >= kOpAdd ? y[q] : 0.f);
-        if constexpr (sizeof(T) == 4)
-          o = make_uint4(__float_as_uint(r[0]), __float_as_uint(r[1]), __float_as_uint(r[2]), __float_as_uint(r[3]));
-        else
-          o = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
-                         pack_bf16x2(r[6], r[7]));
+          for (int q = 0; q < VEC; ++q) r[q] = NIN == 2 ? apply_op(a.op, x[q], y[q]) : relu_f32(x[q]);
+          if constexpr (sizeof(T) == 4)
+            o = make_uint4(__float_as_uint(r[0]), __float_as_uint(r[1]), __float_as_uint(r[2]), __float_as_uint(r[3]));
+          else
+            o = make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]),
+                           pack_bf16x2(r[6], r[7]));
+        }
       }
       *reinterpret_cast<uint4 *>(out + i * a.ldo + j) = o;
     }
   }
+}
+
+template <typename T, int VEC> void launch_vec(const EltwiseArgs &a, dim3 (*g2)(int64_t, int64_t, int), cudaStream_t s) {
+  if (a.op == kOpZero)
+    eltwise_vec_kernel<T, VEC, 0, 4><<<g2(a.n / VEC, a.m, 32), kThreads, 0, s>>>(a);
+  else if (a.op < kOpAdd)
+    eltwise_vec_kernel<T, VEC, 1, 4><<<g2(a.n / VEC, a.m, 32), kThreads, 0, s>>>(a);
+  else
+    eltwise_vec_kernel<T, VEC, 2, 2><<<g2(a.n / VEC, a.m, 16), kThreads, 0, s>>>(a);
 }
 
 inline int grid_for(int64_t work_items) {
@@ -160,15 +181,6 @@ inline int grid_for(int64_t work_items) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return (int)blocks;
-}
-
-// 2-D grid of (32 column-vectors) x (8 * rows_per_thread rows) tiles; y is capped, the kernel strides over it
-inline dim3 grid2d(int64_t nvec, int64_t rows, int rows_per_cta) {
-  int64_t gx = (nvec + 31) / 32, gy = (rows + rows_per_cta - 1) / rows_per_cta;
-  const int64_t cap = (int64_t)kNumSMs * 32;
-  if (gx * gy > cap) gy = cap / gx > 0 ? cap / gx : 1;
-  if (gy > 65535) gy = 65535;
-  return dim3((unsigned)gx, (unsigned)gy, 1);
 }
 
 inline bool operand_vec_ok(const void *p, int mode, int64_t ld, int vec) {
@@ -267,7 +279,7 @@ __global__ void __launch_bounds__(kThreads) vnni2_pack_vec_kernel(const uint16_t
 #pragma unroll
     for (int u = 0; u < PAIRS; ++u) {
       const int64_t q = q0 + 8 * u;
-      if (q >= np) break;
+      if (q >= np) continue;
       uint4 o0, o1;
       o0.x = __byte_perm(r0[u].x, r1[u].x, 0x5410); o0.y = __byte_perm(r0[u].x, r1[u].x, 0x7632);
       o0.z = __byte_perm(r0[u].y, r1[u].y, 0x5410); o0.w = __byte_perm(r0[u].y, r1[u].y, 0x7632);
@@ -314,7 +326,7 @@ __global__ void __launch_bounds__(kThreads) vnni2_unpack_vec_kernel(const uint16
 #pragma unroll
     for (int u = 0; u < PAIRS; ++u) {
       const int64_t q = q0 + 8 * u;
-      if (q >= np) break;
+      if (q >= np) continue;
       uint4 r0, r1;
       r0.x = __byte_perm(a[u].x, a[u].y, 0x5410); r1.x = __byte_perm(a[u].x, a[u].y, 0x7632);
       r0.y = __byte_perm(a[u].z, a[u].w, 0x5410); r1.y = __byte_perm(a[u].z, a[u].w, 0x7632);
@@ -360,9 +372,8 @@ void launch_eltwise(const EltwiseArgs &a_in, cudaStream_t stream) {
   if (a.op != kOpZero) vec_ok = vec_ok && a.mode0 != kBcastImm && operand_vec_ok(a.in0, a.mode0, a.ld0, vec);
   if (a.op >= kOpAdd) vec_ok = vec_ok && operand_vec_ok(a.in1, a.mode1, a.ld1, vec);
   if (vec_ok) {
-    const dim3 grid = grid2d(a.n / vec, a.m, 8 * ROWS);
-    if (f32) eltwise_vec_kernel<float, 4><<<grid, kThreads, 0, stream>>>(a);
-    else eltwise_vec_kernel<uint16_t, 8><<<grid, kThreads, 0, stream>>>(a);
+    if (f32) launch_vec<float, 4>(a, grid2d, stream);
+    else launch_vec<uint16_t, 8>(a, grid2d, stream);
   } else {
     const int grid = grid_for(a.m * a.n);
     if (f32) eltwise_scalar_kernel<float><<<grid, kThreads, 0, stream>>>(a);
