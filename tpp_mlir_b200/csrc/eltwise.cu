@@ -116,8 +116,10 @@ inline dim3 grid2d(int64_t nvec, int64_t rows, int rows_per_cta) {
 
 // NIN = number of tensor inputs (0: zero, 1: identity / relu, 2: binary), R = rows per thread. Specialising on
 // NIN keeps the register count low enough for 5-6 resident CTAs per SM (about 100 KiB of loads in flight per SM).
-template <typename T, int VEC, int NIN, int R>
-__global__ void __launch_bounds__(kThreads, NIN == 2 ? 4 : 5) eltwise_vec_kernel(EltwiseArgs a) {
+// INV (binary only): 1 / 2 = operand 0 / 1 does not depend on the row (bcast_col: the bias vector, or a scalar);
+// it is loaded once per thread instead of once per row, which leaves registers for R = 4 rows in flight.
+template <typename T, int VEC, int NIN, int R, int INV>
+__global__ void __launch_bounds__(kThreads, (NIN == 2 && INV == 0) ? 4 : 5) eltwise_vec_kernel(EltwiseArgs a) {
   const int64_t nv = a.n / VEC;
   const int64_t cv = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
   if (cv >= nv) return;
@@ -126,15 +128,20 @@ __global__ void __launch_bounds__(kThreads, NIN == 2 ? 4 : 5) eltwise_vec_kernel
   const T *in0 = static_cast<const T *>(a.in0);
   const T *in1 = static_cast<const T *>(a.in1);
   T *out = static_cast<T *>(a.out);
+  uint4 inv = make_uint4(0, 0, 0, 0);
+  if constexpr (INV == 1) inv = load16<T>(in0, a.mode0, a.ld0, 0, j);
+  if constexpr (INV == 2) inv = load16<T>(in1, a.mode1, a.ld1, 0, j);
   for (int64_t r0 = (int64_t)blockIdx.y * (8 * R) + ty; r0 < a.m; r0 += (int64_t)gridDim.y * (8 * R)) {
-    uint4 raw0[R], raw1[R];
+    uint4 raw0[R], raw1[INV == 0 ? R : 1];
     if constexpr (NIN >= 1) {
 #pragma unroll
       for (int u = 0; u < R; ++u) {
         const int64_t i = r0 + 8 * u;
         if (i < a.m) {
-          raw0[u] = load16<T>(in0, a.mode0, a.ld0, i, j);
-          if constexpr (NIN == 2) raw1[u] = load16<T>(in1, a.mode1, a.ld1, i, j);
+          // with an invariant operand, raw0[] carries the streaming one
+          if constexpr (INV == 1) raw0[u] = load16<T>(in1, a.mode1, a.ld1, i, j);
+          else raw0[u] = load16<T>(in0, a.mode0, a.ld0, i, j);
+          if constexpr (NIN == 2 && INV == 0) raw1[u] = load16<T>(in1, a.mode1, a.ld1, i, j);
         }
       }
     }
@@ -150,8 +157,13 @@ __global__ void __launch_bounds__(kThreads, NIN == 2 ? 4 : 5) eltwise_vec_kernel
           o = raw0[u];
         } else {
           float x[VEC], y[VEC], r[VEC];
-          unpack16<T, VEC>(raw0[u], x);
-          if constexpr (NIN == 2) unpack16<T, VEC>(raw1[u], y);
+          if constexpr (INV == 1) {          // operand 0 is the invariant one, raw0[] holds operand 1
+            unpack16<T, VEC>(inv, x);
+            unpack16<T, VEC>(raw0[u], y);
+          } else {
+            unpack16<T, VEC>(raw0[u], x);
+            if constexpr (NIN == 2) unpack16<T, VEC>(INV == 2 ? inv : raw1[u], y);
+          }
 #pragma unroll
           for (int q = 0; q < VEC; ++q) r[q] = NIN == 2 ? apply_op(a.op, x[q], y[q]) : relu_f32(x[q]);
           if constexpr (sizeof(T) == 4)
@@ -167,12 +179,18 @@ __global__ void __launch_bounds__(kThreads, NIN == 2 ? 4 : 5) eltwise_vec_kernel
 }
 
 template <typename T, int VEC> void launch_vec(const EltwiseArgs &a, dim3 (*g2)(int64_t, int64_t, int), cudaStream_t s) {
+  const bool inv0 = a.mode0 == kBcastCol || a.mode0 == kBcastScalar;
+  const bool inv1 = a.mode1 == kBcastCol || a.mode1 == kBcastScalar;
   if (a.op == kOpZero)
-    eltwise_vec_kernel<T, VEC, 0, 4><<<g2(a.n / VEC, a.m, 32), kThreads, 0, s>>>(a);
+    eltwise_vec_kernel<T, VEC, 0, 4, 0><<<g2(a.n / VEC, a.m, 32), kThreads, 0, s>>>(a);
   else if (a.op < kOpAdd)
-    eltwise_vec_kernel<T, VEC, 1, 4><<<g2(a.n / VEC, a.m, 32), kThreads, 0, s>>>(a);
+    eltwise_vec_kernel<T, VEC, 1, 4, 0><<<g2(a.n / VEC, a.m, 32), kThreads, 0, s>>>(a);
+  else if (inv0)
+    eltwise_vec_kernel<T, VEC, 2, 4, 1><<<g2(a.n / VEC, a.m, 32), kThreads, 0, s>>>(a);
+  else if (inv1)
+    eltwise_vec_kernel<T, VEC, 2, 4, 2><<<g2(a.n / VEC, a.m, 32), kThreads, 0, s>>>(a);
   else
-    eltwise_vec_kernel<T, VEC, 2, 2><<<g2(a.n / VEC, a.m, 16), kThreads, 0, s>>>(a);
+    eltwise_vec_kernel<T, VEC, 2, 2, 0><<<g2(a.n / VEC, a.m, 16), kThreads, 0, s>>>(a);
 }
 
 inline int grid_for(int64_t work_items) {
