@@ -132,9 +132,8 @@ def cpu_arm(steps, warmup, total_budget_s, verbose=False):
 
     import oracle
 
-    oracle.lib(native=True)  # -march=native build for the box it is timed on
-    cores = os.cpu_count() or 1
-    oracle.set_num_threads(cores)
+    oracle.use_native(True)  # -march=native build for the box it is timed on
+    oracle.lib()
     gen, Ws, bs = make_host_data()
     x = gen.fill(BATCH_PER_GPU, LAYERS[0])
 
@@ -142,14 +141,27 @@ def cpu_arm(steps, warmup, total_budget_s, verbose=False):
         a = x[:rows]
         for W, b in zip(Ws, bs):
             y = np.empty((rows, W.shape[1]), np.uint16)
-            oracle.fused_brgemm(2, rows, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4, 0, 5, 4,
-                                1, a, W, y, b, 1)
+            if not oracle.fused_brgemm_fast(2, rows, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4,
+                                            5, 4, 1, a, W, y, b, 1):
+                oracle.fused_brgemm(2, rows, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4, 0, 5,
+                                    4, 1, a, W, y, b, 1)
             a = y
         return a
 
-    t = time.perf_counter()
-    forward(BATCH_PER_GPU)
-    t1 = time.perf_counter() - t
+    # "all the host threads it can use": the usable count is not os.cpu_count() inside a container with a CPU
+    # quota - try a ladder of thread counts on one forward pass each and keep the fastest
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    ladder = sorted({t for t in (4, 8, 16, 32, 64, 96, 128, avail) if t <= avail} | {min(avail, 8)})
+    best_t, t1 = 1, float("inf")
+    for nt in ladder:
+        oracle.set_num_threads(nt)
+        forward(BATCH_PER_GPU)  # first touch / thread pool spin-up
+        t = time.perf_counter()
+        forward(BATCH_PER_GPU)
+        dt1 = time.perf_counter() - t
+        if dt1 < t1:
+            best_t, t1 = nt, dt1
+    oracle.set_num_threads(best_t)
     rows = BATCH_PER_GPU
     n_calls = steps + warmup
     if t1 * n_calls > total_budget_s:
@@ -164,7 +176,8 @@ def cpu_arm(steps, warmup, total_budget_s, verbose=False):
     flops = sum(2 * rows * c * k + 2 * rows * k for c, k in zip(LAYERS[:-1], LAYERS[1:]))
     return {"value": flops / dt / 1e9, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
             "sample": f"{rows} of {BATCH_PER_GPU} batch rows x 3 layers per step, {steps} steps "
-                      f"(oracle/xsmm_oracle.c, gcc -O3 -march=native -fopenmp)",
+                      f"(oracle/xsmm_oracle_fast.c: {oracle.fast_isa()}, OpenMP {oracle.num_threads()} threads, "
+                      f"gcc -O3 -march=native; libxsmm itself is not buildable offline)",
             "ms_per_step": dt * 1e3, "rows": rows}
 
 

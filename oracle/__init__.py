@@ -13,11 +13,14 @@ from .pyoracle import (  # noqa: F401
     brgemm,
     build,
     f32_to_bf16,
+    fast_isa,
     fused_brgemm,
+    fused_brgemm_fast,
     gemm,
     lib,
     num_threads,
     set_acc_mode,
     set_num_threads,
     unary,
+    use_native,
 )

@@ -18,6 +18,14 @@ BF16 = 2
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _lib = None
 _lib_dir = None
+_native = False
+
+
+def use_native(flag: bool = True) -> None:
+    """Select the -march=native build (oracle/_build_native) for every later call. bench.py's CPU arm uses it on
+    the box it is timed on; tests use the portable x86-64-v3 build that travels with the repo."""
+    global _native
+    _native = bool(flag)
 
 
 def build(native: bool = False, force: bool = False) -> str:
@@ -29,7 +37,8 @@ def build(native: bool = False, force: bool = False) -> str:
     """
     out = "_build_native" if native else "_build"
     so = os.path.join(_HERE, out, "libxsmm_oracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("xsmm_oracle.c", "xsmm_oracle.h", "tensor_init.cpp", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("xsmm_oracle.c", "xsmm_oracle_fast.c", "xsmm_oracle.h", "tensor_init.cpp",
+                                             "Makefile")]
     stale = force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if stale:
         cmd = ["make", "-C", _HERE, f"OUT={out}"]
@@ -39,8 +48,9 @@ def build(native: bool = False, force: bool = False) -> str:
     return so
 
 
-def lib(native: bool = False):
+def lib(native: bool | None = None):
     global _lib, _lib_dir
+    native = _native if native is None else native
     want = "_build_native" if native else "_build"
     if _lib is not None and _lib_dir == want:
         return _lib
@@ -63,6 +73,9 @@ def lib(native: bool = False):
     L.xo_set_acc_mode.argtypes = [c_int]
     L.xo_set_num_threads.argtypes = [c_int]
     L.xo_num_threads.restype = c_int
+    L.xo_fused_brgemm_fast.argtypes = [i64] * 13 + [c_void_p] * 4 + [i64]
+    L.xo_fused_brgemm_fast.restype = c_int
+    L.xo_fast_isa.restype = c_int
     L.ti_create.argtypes = [c_int, c_int, c_int]
     L.ti_create.restype = c_void_p
     L.ti_destroy.argtypes = [c_void_p]
@@ -118,6 +131,18 @@ def fused_brgemm(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, gemm_flags, 
                  binary_flags, binary_kind, A, B, C, D, batch):
     lib().xo_fused_brgemm(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, gemm_flags, unary_flags, unary_kind,
                           binary_flags, binary_kind, _p(A), _p(B), _p(C), _p(D), batch)
+
+
+def fused_brgemm_fast(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, gemm_flags, unary_kind, binary_flags,
+                      binary_kind, A, B, C, D, batch) -> bool:
+    """Vectorised CPU kernel for the timed CPU arm (xsmm_oracle_fast.c). Returns False if the shape is not
+    supported (caller falls back to the plain oracle)."""
+    return lib().xo_fused_brgemm_fast(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, gemm_flags, unary_kind,
+                                      binary_flags, binary_kind, _p(A), _p(B), _p(C), _p(D), batch) == 0
+
+
+def fast_isa() -> str:
+    return {2: "AVX512-BF16 vdpbf16ps 8x32 microkernel", 1: "compiler-vectorised f32 FMA"}[lib().xo_fast_isa()]
 
 
 def unary(kind, dtype, m, n, ldi, ldo, flags, inp, out):

@@ -60,3 +60,32 @@ def test_oracle_vnni_equals_flat():
     oracle.brgemm(2, m, n, k, k, n, n, m * k, k * n, 4, A, B, C0, batch)
     oracle.brgemm(2, m, n, k, k, n, n, m * k, k * n, 4 | 2048, A, Bv, C1, batch)
     np.testing.assert_array_equal(C0, C1)
+
+
+@pytest.mark.parametrize("native", [False, True])
+def test_fast_cpu_kernel_matches_oracle(native):
+    """The vectorised kernel that bench.py times as the CPU arm computes the same operator as the oracle
+    (native=True: the -march=native build, i.e. the vdpbf16ps microkernel where the CPU has AVX512-BF16)."""
+    oracle.use_native(native)
+    try:
+        _check_fast_kernel()
+    finally:
+        oracle.use_native(False)
+        oracle.lib()
+
+
+def _check_fast_kernel():
+    rng = np.random.default_rng(5)
+    m, n, k, batch = 64, 96, 128, 3
+    A = oracle.f32_to_bf16(rng.uniform(-1, 1, (batch, m, k)).astype(np.float32))
+    B = oracle.f32_to_bf16(rng.uniform(-1, 1, (batch, k, n)).astype(np.float32))
+    bias = oracle.f32_to_bf16(rng.uniform(-1, 1, (n,)).astype(np.float32))
+    for gflags in (4, 0):
+        C0 = oracle.f32_to_bf16(rng.uniform(-1, 1, (m, n)).astype(np.float32))
+        c_ref, c_fast = C0.copy(), C0.copy()
+        oracle.fused_brgemm(2, m, n, k, k, n, n, m * k, k * n, gflags, 0, 5, 4, 1, A, B, c_ref, bias, batch)
+        assert oracle.fused_brgemm_fast(2, m, n, k, k, n, n, m * k, k * n, gflags, 5, 4, 1, A, B, c_fast, bias, batch)
+        r, f = oracle.bf16_to_f32(c_ref), oracle.bf16_to_f32(c_fast)
+        np.testing.assert_allclose(f, r, rtol=1e-2, atol=1e-2 * np.abs(r).max())
+    # unsupported shapes are refused, not mis-computed
+    assert not oracle.fused_brgemm_fast(2, 7, n, k, k, n, n, 0, 0, 4, 5, 4, 1, A, B, c_fast, bias, 1)
