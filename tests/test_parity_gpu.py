@@ -314,11 +314,17 @@ def test_brgemm_f32_simt(shape, beta0, dev, orc):
     assert_close(F32, g, o)
 
 
-@pytest.mark.parametrize("shape", [(4, 4, 4, 64), (6, 6, 6, 2), (32, 32, 32, 4), (100, 72, 64, 2), (256, 512, 128, 2)])
+@pytest.mark.parametrize("shape", [(4, 4, 4, 64), (6, 6, 6, 2), (32, 32, 32, 4), (100, 72, 64, 2), (256, 512, 128, 2),
+                                   (256, 1024, 1024, 1), (1024, 1024, 64, 16)])
 def test_brgemm_bf16_vnni_b(shape, dev, orc):
     m, n, k, batch = shape
     g, o, kern = run_brgemm_pair(dev, orc, BF16, m, n, k, batch, vnni=True, fused=(5, 4, 1), seed=m)
     assert_close(BF16, g, o)
+    # VNNI-2 weights reach the tensor cores through an un-interleave pass once the problem is big enough
+    if m * n * k * batch >= 1 << 21:
+        assert kern == "vnni2_unpack+brgemm_tc_bf16", kern
+    else:
+        assert kern.startswith("brgemm_simt_bf16"), kern
 
 
 def test_brgemm_unaligned_falls_back_to_generic_kernel(dev, orc):

@@ -41,6 +41,9 @@ struct KernelDesc {
   int32_t block_n = 0;   // UMMA N (64/128/256)
   int32_t stages = 0;
   int32_t split_k = 1;   // cluster size along the reduction (DSMEM reduce)
+  // VNNI-B descriptors: the same shape with a flat [K][N] B, run on the tcgen05 kernel after B has been
+  // un-interleaved into a scratch buffer (nullptr when the shape is not tensor-core eligible)
+  const KernelDesc *flat_twin = nullptr;
   char name[64] = {0};
 };
 

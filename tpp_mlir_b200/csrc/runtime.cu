@@ -355,6 +355,19 @@ int64_t gemm_family_dispatch(OpClass op, int64_t dtype, int64_t m, int64_t n, in
     } else {
       d.impl = KernelImpl::BrgemmSimt;
       snprintf(d.name, sizeof(d.name), "brgemm_simt_%s_64x64x16", dtype == kF32 ? "f32" : "bf16");
+      if (vnni_b && !(force && force[0] == '1')) {
+        // VNNI-2 B ([K/2][N][2], the reference's default bf16 weight layout) is not a canonical UMMA operand
+        // layout: large shapes un-interleave B into a scratch buffer (one HBM-bound pass) and run the tcgen05
+        // kernel on the flat twin; small ones stay on the generic kernel.
+        KernelDesc twin = d;
+        twin.gemm_flags &= ~(int64_t)XSMM_GEMM_FLAG_ROWMAJOR_B_VNNI;
+        if (brgemm_tc_supported(twin)) {
+          twin.impl = KernelImpl::BrgemmTC;
+          brgemm_tc_configure(twin);
+          d.flat_twin = new KernelDesc(twin);
+          snprintf(d.name, sizeof(d.name), "brgemm_bf16_vnni(unpack+tc | simt)");
+        }
+      }
     }
   });
 }
@@ -426,6 +439,24 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
   if (d->impl == KernelImpl::BrgemmTC) {
     launched = launch_brgemm_tc(*d, g, stream);
     if (launched) t_ctx.last_kernel = brgemm_tc_last_name();
+  } else if (d->flat_twin && batch > 0 && (double)d->m * d->n * d->k * batch >= 2097152.0 &&
+             (batch == 1 || d->stride_b == d->k * d->ldb) && aligned16(g.B)) {
+    // VNNI-B -> flat B in a per-thread scratch (batches are contiguous: one tall [batch*k][ldb] un-interleave)
+    thread_local Staging vnni_scratch;
+    const int64_t rows = batch * d->k;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    const size_t need = (size_t)rows * d->ldb * 2;
+    if (cs == cudaStreamCaptureStatusNone || need <= vnni_scratch.cap) {
+      void *flat = vnni_scratch.get(need);
+      launch_vnni2_unpack(g.B, flat, rows, d->n, d->ldb, d->ldb, stream);
+      count_launch();
+      GemmArgs gf = g;
+      gf.B = flat;
+      gf.b_independent = false;   // produced by the kernel just launched
+      launched = launch_brgemm_tc(*d->flat_twin, gf, stream);
+      if (launched) t_ctx.last_kernel = "vnni2_unpack+brgemm_tc_bf16";
+    }
   }
   if (!launched) {
     launch_brgemm_simt(*d, g, stream);
