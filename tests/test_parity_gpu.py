@@ -489,3 +489,47 @@ def test_graph_capture_replays_the_invoke_sequence():
         assert torch.equal(y2, want)
     assert xsmm.launch_count() == n0 + 6
     g.destroy()
+
+
+def test_concurrent_invokes_from_many_threads(orc):
+    """The reference runs invokes concurrently from OpenMP threads on disjoint C tiles (--def-parallel,
+    lib/TPP/DefaultPipeline.cpp:179-180): dispatch cache, per-thread streams / staging / tensor-map caches must be
+    thread-safe. 8 threads, each with its own stream, mix of tensor-core, generic and eltwise kernels and of
+    device / plain-host operands."""
+    import threading
+
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    errors = []
+
+    def worker(tid):
+        try:
+            rng = np.random.default_rng(100 + tid)
+            stream = torch.cuda.Stream()
+            be = AbiBackend("device" if tid % 2 == 0 else "host")
+            with torch.cuda.stream(stream):
+                for it in range(6):
+                    m, n, k, batch = 64 + 32 * (tid % 3), 128, 64 * (1 + it % 2), 1 + it % 3
+                    A, B = rnd(rng, BF16, (batch, m, k)), rnd(rng, BF16, (batch, k, n))
+                    bias, C0 = rnd(rng, BF16, (n,)), rnd(rng, BF16, (m, n))
+                    g, o = C0.copy(), C0.copy()
+                    be.fused_brgemm(BF16, m, n, k, k, n, n, m * k, k * n, 0, 0, 5, 4, 1, A, 0, B, 0, g, 0, bias, 0, batch)
+                    orc.fused_brgemm(BF16, m, n, k, k, n, n, m * k, k * n, 0, 0, 5, 4, 1, A, 0, B, 0, o, 0, bias, 0, batch)
+                    assert_close(BF16, g, o)
+                    x = rnd(rng, F32, (33, 47))
+                    yg, yo = np.zeros((47, 33), np.float32), np.zeros((47, 33), np.float32)
+                    be.unary(29, F32, 33, 47, 47, 33, 0, x, 0, yg, 0)
+                    orc.unary(29, F32, 33, 47, 47, 33, 0, x, 0, yo, 0)
+                    np.testing.assert_array_equal(yg, yo)
+        except Exception as e:  # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(8)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    xsmm.sync()
+    assert not errors, errors
