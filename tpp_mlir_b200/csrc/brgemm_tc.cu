@@ -387,7 +387,11 @@ __device__ __forceinline__ void splitk_epilogue_l2_wide(const TcParams &p, uint3
 }
 
 // SPLITK: 0 = one CTA per tile, 1 = cluster split-K with DSMEM exchange, 2 = cluster split-K with L2 exchange
-template <int BLOCK_N, int STAGES, int SPLITK>
+// MC = 1: 2 x 2 (x S) thread-block clusters with TMA multicast. The two CTAs of a cluster row (same m-tile) each
+// fetch one 64-row half of the A stage and multicast it to both; the two CTAs of a cluster column (same n-tile)
+// each fetch half of the B chunks and multicast them. Every SM then pulls only half of its operand bytes over its
+// SM<->L2 link, which is what bounds the single-CTA kernel (24 % of tensor peak at 2048 x 1024 x 1024).
+template <int BLOCK_N, int STAGES, int SPLITK, int MC = 0>
 __global__ void __launch_bounds__(NUM_THREADS, (SPLITK && BLOCK_N == 64) ? 2 : 1)
 brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   using L = SmemLayout<BLOCK_N>;
@@ -411,8 +415,19 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // this CTA's share of the (batch x k-block) reduction
   uint32_t rank = 0;
   int32_t it_begin = 0, it_end = p.total_iters;
+  // multicast geometry: cluster = (2 n-tiles, 2 m-tiles, S); rank in cluster = cx + 2*cy + 4*cz
+  uint32_t cx = 0, cy = 0;
+  uint16_t a_mask = 0, b_mask = 0, free_mask = 0;
+  if constexpr (MC) {
+    const uint32_t cr = ptx::cluster_ctarank();
+    cx = cr & 1; cy = (cr >> 1) & 1;
+    const uint32_t zbase = cr & ~3u;
+    a_mask = static_cast<uint16_t>((1u << (zbase + 2 * cy)) | (1u << (zbase + 2 * cy + 1)));   // same m-tile: both cx
+    b_mask = static_cast<uint16_t>((1u << (zbase + cx)) | (1u << (zbase + cx + 2)));           // same n-tile: both cy
+    free_mask = a_mask | b_mask;   // the CTAs whose producers write into this CTA's stages
+  }
   if constexpr (SPLITK) {
-    rank = ptx::cluster_ctarank();
+    rank = blockIdx.z;             // gridDim.z == cluster z extent == split_k
     it_begin = (int32_t)(((int64_t)p.total_iters * rank) / p.split_k);
     it_end = (int32_t)(((int64_t)p.total_iters * (rank + 1)) / p.split_k);
   }
@@ -424,7 +439,9 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::prefetch_tensormap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(full_bar + 8 * s, 1);
-      ptx::mbar_init(empty_bar + 8 * s, 1);
+      // with multicast a stage is refilled by this CTA and by its row / column partner: all three must have
+      // seen their MMAs retire before anyone overwrites it
+      ptx::mbar_init(empty_bar + 8 * s, MC ? 3 : 1);
     }
     ptx::mbar_init(accum_bar, 1);
     ptx::fence_mbar_init();
@@ -434,7 +451,14 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before_sync();
-  __syncthreads();
+  if constexpr (MC) {
+    // partners' barriers must exist before the first multicast / remote arrive
+    __syncwarp();
+    ptx::cluster_arrive();
+    ptx::cluster_wait();
+  } else {
+    __syncthreads();
+  }
   ptx::tc_fence_after_sync();
   const uint32_t tmem_acc = *tmem_slot_ptr;
   if (threadIdx.x == 0) trace_stamp(p, 1);
@@ -445,7 +469,7 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // running (MLP weights), fetch the B tiles of the first STAGES k-blocks already now: they overlap
   // the previous layer's epilogue instead of sitting on this layer's critical path.
   int32_t b_prefetched = 0;
-  if (p.b_early) b_prefetched = num_iters < STAGES ? num_iters : STAGES;
+  if (p.b_early && !MC) b_prefetched = num_iters < STAGES ? num_iters : STAGES;
   if (warp == 0 && lane == 0) {
     for (int32_t i = 0; i < b_prefetched; ++i) {
       const int32_t it = it_begin + i;
@@ -474,12 +498,24 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
           ptx::mbar_arrive_expect_tx(full_bar + 8 * s, L::kStageBytes);
         }
-        ptx::tma_load_3d(smem_a + s * A_STAGE_BYTES, &tmA, full_bar + 8 * s, kb * BLOCK_K, m0, b);
-        if (i >= b_prefetched) {
+        if constexpr (MC) {
+          // my half of A (64 rows) to both CTAs of my cluster row; my half of the B chunks to my cluster column
+          ptx::tma_load_3d_mc(smem_a + s * A_STAGE_BYTES + cx * (A_STAGE_BYTES / 2), &tmA, full_bar + 8 * s,
+                              kb * BLOCK_K, m0 + (int32_t)cx * (BLOCK_M / 2), b, a_mask);
 #pragma unroll
-          for (int c = 0; c < L::kBChunks; ++c)
-            ptx::tma_load_3d(smem_b + (s * L::kBChunks + c) * B_CHUNK_BYTES, &tmB, full_bar + 8 * s, n0 + c * 64,
-                             kb * BLOCK_K, b);
+          for (int c = 0; c < L::kBChunks / 2; ++c) {
+            const int cc = (int)cy * (L::kBChunks / 2) + c;
+            ptx::tma_load_3d_mc(smem_b + (s * L::kBChunks + cc) * B_CHUNK_BYTES, &tmB, full_bar + 8 * s, n0 + cc * 64,
+                                kb * BLOCK_K, b, b_mask);
+          }
+        } else {
+          ptx::tma_load_3d(smem_a + s * A_STAGE_BYTES, &tmA, full_bar + 8 * s, kb * BLOCK_K, m0, b);
+          if (i >= b_prefetched) {
+#pragma unroll
+            for (int c = 0; c < L::kBChunks; ++c)
+              ptx::tma_load_3d(smem_b + (s * L::kBChunks + c) * B_CHUNK_BYTES, &tmB, full_bar + 8 * s, n0 + c * 64,
+                               kb * BLOCK_K, b);
+          }
         }
         if (i == 0) trace_stamp(p, 3);
       }
@@ -506,7 +542,9 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t db = ptx::umma_smem_desc_sw128(b_addr + kk * (UMMA_K * 128), B_CHUNK_BYTES, 1024);
           ptx::umma_bf16(tmem_acc, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
         }
-        ptx::umma_commit(empty_bar + 8 * s);   // frees the slot when these MMAs retire
+        // frees the slot when these MMAs retire (in this CTA and, with multicast, at both partners)
+        if constexpr (MC) ptx::umma_commit_mc(empty_bar + 8 * s, free_mask);
+        else ptx::umma_commit(empty_bar + 8 * s);
       }
       if (num_iters > 0) ptx::umma_commit(accum_bar);   // accumulator complete
       trace_stamp(p, 6);
@@ -568,6 +606,12 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   ptx::tc_fence_before_sync();
+  if constexpr (MC) {
+    // partners may still multicast into / arrive on this CTA's shared memory until their main loops end
+    __syncwarp();
+    ptx::cluster_arrive();
+    ptx::cluster_wait();
+  }
   __syncthreads();
   if (threadIdx.x == 0) trace_stamp(p, 11);
   if (warp == 1) {
@@ -623,12 +667,12 @@ template <int BLOCK_N, int STAGES, int SPLITK> constexpr int smem_bytes() {
   return STAGES * SmemLayout<BLOCK_N>::kStageBytes + (SPLITK == 1 ? RECV_BYTES : 0) + (2 * STAGES + 1) * 8 + 16 + 1024;
 }
 
-template <int BLOCK_N, int STAGES, int SPLITK>
+template <int BLOCK_N, int STAGES, int SPLITK, int MC = 0>
 void launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, dim3 grid, cudaStream_t stream) {
   constexpr int smem = smem_bytes<BLOCK_N, STAGES, SPLITK>();
   static std::once_flag once;
   std::call_once(once, [] {
-    TPP_CUDA_CHECK(cudaFuncSetAttribute(brgemm_tc_kernel<BLOCK_N, STAGES, SPLITK>,
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(brgemm_tc_kernel<BLOCK_N, STAGES, SPLITK, MC>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   });
   cudaLaunchConfig_t cfg{};
@@ -641,16 +685,16 @@ void launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &
   attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[na].val.programmaticStreamSerializationAllowed = 1;
   ++na;
-  if (SPLITK) {
+  if (SPLITK || MC) {
     attrs[na].id = cudaLaunchAttributeClusterDimension;
-    attrs[na].val.clusterDim.x = 1;
-    attrs[na].val.clusterDim.y = 1;
-    attrs[na].val.clusterDim.z = (unsigned)p.split_k;
+    attrs[na].val.clusterDim.x = MC ? 2 : 1;
+    attrs[na].val.clusterDim.y = MC ? 2 : 1;
+    attrs[na].val.clusterDim.z = SPLITK ? (unsigned)p.split_k : 1;
     ++na;
   }
   cfg.attrs = attrs;
   cfg.numAttrs = na;
-  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, brgemm_tc_kernel<BLOCK_N, STAGES, SPLITK>, tmA, tmB, p));
+  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, brgemm_tc_kernel<BLOCK_N, STAGES, SPLITK, MC>, tmA, tmB, p));
 }
 
 int bin_mode_from_flags(int64_t f) {
@@ -691,23 +735,33 @@ static int split_for(int64_t tiles, int64_t total_iters) {
 // Wide tiles raise the arithmetic intensity per SM (the SM<->L2 link is the limiter: cfg2 went from 27 % to 61 %
 // of tensor peak with 128x256 tiles), narrow tiles + split-K fill the machine when the output has few tiles
 // (the 256 x 1024 MLP layer).
-static void choose_tile(const KernelDesc &d, int64_t total_iters, int *bn_out, int *split_out) {
+static void choose_tile(const KernelDesc &d, int64_t total_iters, int *bn_out, int *split_out, int *mc_out) {
   const int64_t tiles_m = (d.m + BLOCK_M - 1) / BLOCK_M;
-  int best = 64, best_split = 1;
+  static const bool mc_off = [] { const char *e = getenv("TPP_XSMM_MULTICAST"); return e && e[0] == '0'; }();
+  int best = 64, best_split = 1, best_mc = 0;
   double best_cost = 1e300;
   for (int bn : {256, 128, 64}) {
     if (bn > 64 && d.n <= bn / 2) continue;
-    const int64_t tiles = tiles_m * ((d.n + bn - 1) / bn);
-    const int split = split_for(tiles, total_iters);
-    const double waves = (double)((tiles * split + 147) / 148);
-    const double per_cta_iters = (double)((total_iters + split - 1) / split);
-    double cost = per_cta_iters * kblock_clocks(bn);
-    if (split > 1) cost += 1500.0 + 2.0 * (BLOCK_M * bn * 4.0) * (split - 1) / split / 50.0;   // barrier + ws out/in
-    cost *= waves;
-    if (cost < best_cost) { best_cost = cost; best = bn; best_split = split; }
+    const int64_t tiles_n = (d.n + bn - 1) / bn;
+    const int64_t tiles = tiles_m * tiles_n;
+    for (int mc = 0; mc <= 1; ++mc) {
+      // 2 x 2 multicast clusters: wide tiles only, even tile counts, and at most 2-way split-K (cluster <= 8)
+      if (mc && (mc_off || bn == 64 || (tiles_m & 1) || (tiles_n & 1))) continue;
+      int split = split_for(tiles, total_iters);
+      if (mc && split > 2) split = 2;
+      const double waves = (double)((tiles * split + 147) / 148);
+      const double per_cta_iters = (double)((total_iters + split - 1) / split);
+      const double mma = 4.0 * bn / 2.0;
+      const double ingest = (A_STAGE_BYTES + bn * 128.0) / (mc ? 2.0 : 1.0) / 50.0;
+      double cost = per_cta_iters * (mma > ingest ? mma : ingest) + (mc ? 1000.0 : 0.0);
+      if (split > 1) cost += 1500.0 + 2.0 * (BLOCK_M * bn * 4.0) * (split - 1) / split / 50.0;   // barrier + ws out/in
+      cost *= waves;
+      if (cost < best_cost) { best_cost = cost; best = bn; best_split = split; best_mc = mc; }
+    }
   }
   *bn_out = best;
   *split_out = best_split;
+  *mc_out = best_mc;
 }
 
 thread_local char t_last_name[64] = "brgemm_tc_bf16";
@@ -724,12 +778,28 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   if (!aligned16(g.A) || !aligned16(g.B)) return false;
   const int64_t batch = g.batch;
   if (batch > (1ll << 31)) return false;
-  // A tensor map is a pure function of (descriptor, operand address, batch): cache the encoded
+  const int32_t k_iters = (int32_t)((d.k + BLOCK_K - 1) / BLOCK_K);
+  int block_n = 64, split = 1, mc = 0;
+  choose_tile(d, batch * k_iters, &block_n, &split, &mc);
+  {
+    static const char *env_bn = getenv("TPP_XSMM_BLOCK_N");   // tuning overrides, read once
+    static const char *env = getenv("TPP_XSMM_SPLITK");
+    if (env_bn && (atoi(env_bn) == 64 || atoi(env_bn) == 128 || atoi(env_bn) == 256)) {
+      block_n = atoi(env_bn);
+      mc = 0;
+      split = split_for(((d.n + block_n - 1) / block_n) * ((d.m + BLOCK_M - 1) / BLOCK_M), batch * k_iters);
+    }
+    if (env) split = atoi(env);
+    if (split != 2 && split != 4) split = 1;
+    if (mc && split > 2) split = 2;
+  }
+  // A tensor map is a pure function of (descriptor, operand address, batch, box): cache the encoded
   // pair per thread so steady-state invokes (the same memrefs over and over) skip the driver call.
   struct MapCacheEntry {
     const KernelDesc *desc = nullptr;
     const void *A = nullptr, *B = nullptr;
     int64_t batch = -1;
+    int mc = -1;
     bool ok = false;
     CUtensorMap tmA, tmB;
   };
@@ -737,11 +807,12 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   thread_local MapCacheEntry t_maps[kMapCache];
   const uintptr_t ha = reinterpret_cast<uintptr_t>(g.A), hb = reinterpret_cast<uintptr_t>(g.B);
   MapCacheEntry &e = t_maps[((ha >> 7) ^ (ha >> 19) ^ (hb >> 9) ^ (hb >> 23) ^ (uintptr_t)batch) & (kMapCache - 1)];
-  if (e.desc != &d || e.A != g.A || e.B != g.B || e.batch != batch) {
+  if (e.desc != &d || e.A != g.A || e.B != g.B || e.batch != batch || e.mc != mc) {
     const uint64_t nb = batch > 0 ? (uint64_t)batch : 1;
-    e.desc = &d; e.A = g.A; e.B = g.B; e.batch = batch;
+    e.desc = &d; e.A = g.A; e.B = g.B; e.batch = batch; e.mc = mc;
+    // with multicast every CTA fetches one 64-row half of the A stage
     e.ok = encode_map(&e.tmA, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, BLOCK_K,
-                      BLOCK_M) &&
+                      mc ? BLOCK_M / 2 : BLOCK_M) &&
            encode_map(&e.tmB, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, 64,
                       BLOCK_K);
   }
@@ -752,7 +823,7 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   p.C = g.C;
   p.D = g.D;
   p.m = d.m; p.n = d.n; p.ldc = d.ldc;
-  p.k_iters = (int32_t)((d.k + BLOCK_K - 1) / BLOCK_K);
+  p.k_iters = k_iters;
   p.total_iters = (int32_t)(batch * p.k_iters);
   p.beta0 = (d.gemm_flags & 4) != 0;
   p.bin_kind = (d.op == OpClass::FusedBrgemm && g.D) ? (int)d.binary_kind : 0;
@@ -774,20 +845,6 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   }
   p.trace = nullptr;
 
-  int block_n = 64, split = 1;
-  choose_tile(d, p.total_iters, &block_n, &split);
-  // split the reduction across a cluster while the CTA count stays within one wave and every CTA keeps
-  // at least 2 k-blocks
-  {
-    static const char *env_bn = getenv("TPP_XSMM_BLOCK_N");   // tuning overrides, read once
-    static const char *env = getenv("TPP_XSMM_SPLITK");
-    if (env_bn && (atoi(env_bn) == 64 || atoi(env_bn) == 128 || atoi(env_bn) == 256)) {
-      block_n = atoi(env_bn);
-      split = split_for(((d.n + block_n - 1) / block_n) * ((d.m + BLOCK_M - 1) / BLOCK_M), p.total_iters);
-    }
-    if (env) split = atoi(env);
-    if (split != 2 && split != 4) split = 1;
-  }
   p.split_k = split;
 
   dim3 grid((unsigned)((d.n + block_n - 1) / block_n), (unsigned)((d.m + BLOCK_M - 1) / BLOCK_M), (unsigned)split);
@@ -820,15 +877,19 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
     g_trace_ctas[slot] = n_ctas;
     p.trace = trace_buf + (size_t)slot * kTraceCtas * TRACE_SLOTS;
   }
-  snprintf(t_last_name, sizeof(t_last_name), "brgemm_tc_bf16_128x%dx64%s", block_n,
-           split == 1 ? "" : split == 2 ? "_splitk2" : "_splitk4");
+  snprintf(t_last_name, sizeof(t_last_name), "brgemm_tc_bf16_128x%dx64%s%s", block_n,
+           split == 1 ? "" : split == 2 ? "_splitk2" : "_splitk4", mc ? "_mc2x2" : "");
   switch (block_n) {
   case 256:
-    if (split > 1) launch_cfg<256, 4, 2>(tmA, tmB, p, grid, stream);
+    if (mc && split > 1) launch_cfg<256, 4, 2, 1>(tmA, tmB, p, grid, stream);
+    else if (mc) launch_cfg<256, 4, 0, 1>(tmA, tmB, p, grid, stream);
+    else if (split > 1) launch_cfg<256, 4, 2>(tmA, tmB, p, grid, stream);
     else launch_cfg<256, 4, 0>(tmA, tmB, p, grid, stream);
     break;
   case 128:
-    if (split > 1) launch_cfg<128, 6, 2>(tmA, tmB, p, grid, stream);
+    if (mc && split > 1) launch_cfg<128, 6, 2, 1>(tmA, tmB, p, grid, stream);
+    else if (mc) launch_cfg<128, 6, 0, 1>(tmA, tmB, p, grid, stream);
+    else if (split > 1) launch_cfg<128, 6, 2>(tmA, tmB, p, grid, stream);
     else launch_cfg<128, 6, 0>(tmA, tmB, p, grid, stream);
     break;
   default:
