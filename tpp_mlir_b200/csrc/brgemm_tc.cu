@@ -737,7 +737,11 @@ static int split_for(int64_t tiles, int64_t total_iters) {
 // (the 256 x 1024 MLP layer).
 static void choose_tile(const KernelDesc &d, int64_t total_iters, int *bn_out, int *split_out, int *mc_out) {
   const int64_t tiles_m = (d.m + BLOCK_M - 1) / BLOCK_M;
-  static const bool mc_off = [] { const char *e = getenv("TPP_XSMM_MULTICAST"); return e && e[0] == '0'; }();
+  // Multicast clusters are implemented and parity-tested but OFF by default: measured on B200 they do not help
+  // (cfg2 990 -> 404 TF/s because the cluster limit caps split-K at 2; cfg5 384 -> 375 TF/s). Multicast saves L2
+  // reads, not the bytes each SM must receive over its own SM<->L2 link, and that link (~50-64 B/clk) is what
+  // bounds this kernel; halving the per-SM bytes needs cta_group::2 MMAs (next step).
+  static const bool mc_off = [] { const char *e = getenv("TPP_XSMM_MULTICAST"); return !(e && e[0] == '1'); }();
   int best = 64, best_split = 1, best_mc = 0;
   double best_cost = 1e300;
   for (int bn : {256, 128, 64}) {
