@@ -314,13 +314,15 @@ __device__ __forceinline__ void splitk_epilogue_l2(const TcParams &p, uint32_t t
 // after the barrier it re-reads it from TMEM 32 columns at a time, adds the S-1 incoming slices and stores.
 template <int BLOCK_N>
 __device__ __forceinline__ void splitk_epilogue_l2_wide(const TcParams &p, uint32_t tmem_acc, int q, int lane,
-                                                        int64_t m0, int64_t n0, uint32_t rank, bool has_acc) {
+                                                        int64_t m0, int64_t n0, uint32_t rank, bool has_acc,
+                                                        unsigned tile_x = blockIdx.x, unsigned tiles_x = gridDim.x,
+                                                        unsigned tile_y = blockIdx.y) {
   const int S = p.split_k;
   const int NC = BLOCK_N / S;          // columns per owner (>= 32)
   const int NCH = NC / 4;              // 16-byte chunks per owner row
   const int row_in_tile = q * 32 + lane;
   const int64_t row = m0 + row_in_tile;
-  const size_t tile = blockIdx.x + (size_t)gridDim.x * blockIdx.y;
+  const size_t tile = tile_x + (size_t)tiles_x * tile_y;
   float4 *ws_tile = reinterpret_cast<float4 *>(p.ws) + tile * (size_t)(S * BLOCK_N / 4 * BLOCK_M);
   const uint32_t lane_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
   // phase 1: every 32-column chunk this CTA does not own goes to its owner's slot [owner][src = rank]
@@ -620,6 +622,166 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+// ---- CTA-pair kernel (cta_group::2) ---------------------------------------------------------------------
+// One 256 x BLOCK_N output tile per pair of CTAs (two SMs of a TPC): CTA r of the pair stages A rows
+// [128r, 128r+128) and B columns [r*BLOCK_N/2, (r+1)*BLOCK_N/2) of every k-block in ITS shared memory; the leader
+// (r = 0) issues tcgen05.mma.cta_group::2 with M = 256, which reads both CTAs' operands and accumulates rows
+// 128r.. into CTA r's TMEM. Each SM therefore receives 16 KiB + BLOCK_N*64 B per k-block instead of
+// 16 KiB + BLOCK_N*128 B: for BLOCK_N = 256 that is 32 KiB per 512 MMA clocks = 62 B/clk, inside what the SM<->L2
+// link delivers, where the single-CTA 128 x 256 tile needs 94 B/clk (measured 61 % of tensor peak, link-bound).
+// Cluster = (2, 1, S): the pair along x, optional split-K along z with the L2 workspace exchange.
+template <int BLOCK_N, int STAGES, int SPLITK>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+brgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
+  constexpr int HALF_N = BLOCK_N / 2;                 // B columns staged by each CTA
+  constexpr int kBChunks = HALF_N / 64;
+  constexpr int kStageBytes = A_STAGE_BYTES + kBChunks * B_CHUNK_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;
+  const uint32_t smem_b = smem_base + STAGES * A_STAGE_BYTES;
+  const uint32_t bar_base = smem_b + STAGES * kBChunks * B_CHUNK_BYTES;
+  const uint32_t full_bar = bar_base;                 // used in the leader only (both CTAs' bytes land on it)
+  const uint32_t empty_bar = bar_base + STAGES * 8;   // one per CTA, released by the pair's MMA commits
+  const uint32_t accum_bar = bar_base + 2 * STAGES * 8;
+  const uint32_t tmem_slot = accum_bar + 8;
+  uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t crank = ptx::cluster_ctarank();      // = peer + 2 * z
+  const uint32_t peer = crank & 1;                    // 0 = leader
+  const uint32_t leader_rank = crank & ~1u;
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << leader_rank);
+  const int32_t m0 = blockIdx.x * BLOCK_M;            // this CTA's 128 rows (blockIdx.x = 2 * pair + peer)
+  const int32_t n0 = blockIdx.y * BLOCK_N;
+
+  uint32_t rank = 0;
+  int32_t it_begin = 0, it_end = p.total_iters;
+  if constexpr (SPLITK) {
+    rank = blockIdx.z;
+    it_begin = (int32_t)(((int64_t)p.total_iters * rank) / p.split_k);
+    it_end = (int32_t)(((int64_t)p.total_iters * (rank + 1)) / p.split_k);
+  }
+  const int32_t num_iters = it_end - it_begin;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmA);
+    ptx::prefetch_tensormap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(full_bar + 8 * s, 1);
+      ptx::mbar_init(empty_bar + 8 * s, 1);
+    }
+    ptx::mbar_init(accum_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, BLOCK_N);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before_sync();
+  __syncwarp();
+  ptx::cluster_arrive();   // both CTAs' barriers and TMEM exist before any remote signal / pair MMA
+  ptx::cluster_wait();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own halves into own smem, bytes counted on the LEADER's full barrier =====
+    if (lane == 0) {
+      const uint32_t leader_full = ptx::mapa(full_bar, leader_rank);
+      for (int32_t i = 0; i < num_iters; ++i) {
+        const int32_t it = it_begin + i;
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        const int32_t b = it / p.k_iters, kb = it - b * p.k_iters;
+        ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
+        if (peer == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2 * kStageBytes);   // both CTAs' bytes
+        ptx::tma_load_3d_pair(smem_a + s * A_STAGE_BYTES, &tmA, leader_full + 8 * s, kb * BLOCK_K, m0, b);
+#pragma unroll
+        for (int c = 0; c < kBChunks; ++c)
+          ptx::tma_load_3d_pair(smem_b + (s * kBChunks + c) * B_CHUNK_BYTES, &tmB, leader_full + 8 * s,
+                                n0 + (int32_t)peer * HALF_N + c * 64, kb * BLOCK_K, b);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader only =====
+    if (lane == 0 && peer == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BLOCK_M, BLOCK_N, /*A K-major*/ 0, /*B MN-major*/ 1);
+      for (int32_t i = 0; i < num_iters; ++i) {
+        const int s = i % STAGES;
+        const uint32_t ph = (i / STAGES) & 1;
+        ptx::mbar_wait(full_bar + 8 * s, ph);
+        ptx::tc_fence_after_sync();
+        const uint32_t a_addr = smem_a + s * A_STAGE_BYTES;
+        const uint32_t b_addr = smem_b + s * kBChunks * B_CHUNK_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+          const uint64_t da = ptx::umma_smem_desc_sw128(a_addr + kk * (UMMA_K * 2), 16, 1024);
+          const uint64_t db = ptx::umma_smem_desc_sw128(b_addr + kk * (UMMA_K * 128), B_CHUNK_BYTES, 1024);
+          ptx::umma_bf16_pair(tmem_acc, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+        }
+        ptx::umma_commit_pair(empty_bar + 8 * s, pair_mask);   // frees the slot in both CTAs
+      }
+      if (num_iters > 0) ptx::umma_commit_pair(accum_bar, pair_mask);   // both epilogues may start
+    }
+  } else {
+    // ===== epilogue (both CTAs, each on its own 128 rows of TMEM) =====
+    const int q = warp & 3;
+    if (num_iters > 0) {
+      ptx::mbar_wait(accum_bar, 0);
+      ptx::tc_fence_after_sync();
+    }
+    if constexpr (!SPLITK) {
+      const int64_t row = (int64_t)m0 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        const int64_t col0 = (int64_t)n0 + c;
+        if (col0 >= p.n) break;
+        uint32_t r[32];
+        if (num_iters > 0) {
+          ptx::tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + c, r);
+          ptx::tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) r[e] = 0u;
+        }
+        if (row < p.m) {
+          float v[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+          epilogue_store<32>(v, p, row, col0);
+        }
+      }
+    }
+  }
+
+  if constexpr (SPLITK) {
+    if (warp >= 2) {
+      const int q = warp & 3;
+      splitk_epilogue_l2_wide<BLOCK_N>(p, tmem_acc, q, lane, m0, n0, rank, num_iters > 0, blockIdx.x, gridDim.x,
+                                       blockIdx.y);
+    } else {
+      __syncwarp();
+      ptx::cluster_arrive();
+      ptx::cluster_wait();
+    }
+  }
+
+  // the peer must not exit (nor free TMEM) while the leader's MMAs still read its shared memory / write its TMEM
+  ptx::tc_fence_before_sync();
+  __syncwarp();
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_pair(tmem_acc, BLOCK_N);
+  }
+}
+
 // ---- host side ----------------------------------------------------------------
 
 constexpr int kTraceRing = 128, kTraceRingCtas = 256;
@@ -697,6 +859,31 @@ void launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &
   TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, brgemm_tc_kernel<BLOCK_N, STAGES, SPLITK, MC>, tmA, tmB, p));
 }
 
+template <int BLOCK_N, int STAGES, int SPLITK>
+void launch_cfg_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, dim3 grid, cudaStream_t stream) {
+  constexpr int smem = STAGES * (A_STAGE_BYTES + (BLOCK_N / 128) * B_CHUNK_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  });
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = 2;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = SPLITK ? (unsigned)p.split_k : 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK>, tmA, tmB, p));
+}
+
 int bin_mode_from_flags(int64_t f) {
   if (f & 4) return kBcastCol;
   if (f & 1) return kBcastRow;
@@ -763,6 +950,25 @@ static void choose_tile(const KernelDesc &d, int64_t total_iters, int *bn_out, i
       if (cost < best_cost) { best_cost = cost; best = bn; best_split = split; best_mc = mc; }
     }
   }
+  // CTA pairs (cta_group::2): one 256 x bn tile per pair, each SM receives A (128 x 64) + half of B per k-block
+  static const bool pair_on = [] { const char *e = getenv("TPP_XSMM_PAIR"); return !(e && e[0] == '0'); }();
+  if (pair_on) {
+    const int64_t tiles_m256 = (d.m + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    for (int bn : {256, 128}) {
+      if (d.n <= bn / 2) continue;
+      const int64_t ctas1 = 2 * tiles_m256 * ((d.n + bn - 1) / bn);
+      int split = 1;
+      while (split < 4 && ctas1 * (split * 2) <= 148 && total_iters >= 2 * (split * 2)) split *= 2;
+      const double waves = (double)((ctas1 * split + 147) / 148);
+      const double per_cta_iters = (double)((total_iters + split - 1) / split);
+      const double mma = 4.0 * bn / 2.0;
+      const double ingest = (A_STAGE_BYTES + bn * 64.0) / 50.0;
+      double cost = per_cta_iters * (mma > ingest ? mma : ingest) + 1000.0;
+      if (split > 1) cost += 1500.0 + 2.0 * (BLOCK_M * bn * 4.0) * (split - 1) / split / 50.0;
+      cost *= waves;
+      if (cost < best_cost) { best_cost = cost; best = bn; best_split = split; best_mc = 2; }
+    }
+  }
   *bn_out = best;
   *split_out = best_split;
   *mc_out = best_mc;
@@ -795,7 +1001,7 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
     }
     if (env) split = atoi(env);
     if (split != 2 && split != 4) split = 1;
-    if (mc && split > 2) split = 2;
+    if (mc == 1 && split > 2) split = 2;
   }
   // A tensor map is a pure function of (descriptor, operand address, batch, box): cache the encoded
   // pair per thread so steady-state invokes (the same memrefs over and over) skip the driver call.
@@ -816,7 +1022,7 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
     e.desc = &d; e.A = g.A; e.B = g.B; e.batch = batch; e.mc = mc;
     // with multicast every CTA fetches one 64-row half of the A stage
     e.ok = encode_map(&e.tmA, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, BLOCK_K,
-                      mc ? BLOCK_M / 2 : BLOCK_M) &&
+                      mc == 1 ? BLOCK_M / 2 : BLOCK_M) &&
            encode_map(&e.tmB, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, 64,
                       BLOCK_K);
   }
@@ -852,6 +1058,9 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   p.split_k = split;
 
   dim3 grid((unsigned)((d.n + block_n - 1) / block_n), (unsigned)((d.m + BLOCK_M - 1) / BLOCK_M), (unsigned)split);
+  if (mc == 2)   // CTA pairs: x = 2 * (256-row tiles) so that the two CTAs of a pair are cluster ranks 2i, 2i+1
+    grid = dim3((unsigned)(2 * ((d.m + 2 * BLOCK_M - 1) / (2 * BLOCK_M))), (unsigned)((d.n + block_n - 1) / block_n),
+                (unsigned)split);
   const int n_ctas = (int)(grid.x * grid.y * grid.z);
   // exchange path of the split-K partials: the L2 workspace (default; 23.1 us per MLP step) or DSMEM
   // (TPP_XSMM_XCHG=d; 26.7 us: st.shared::cluster moves only ~17 B/clk/SM)
@@ -881,18 +1090,27 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
     g_trace_ctas[slot] = n_ctas;
     p.trace = trace_buf + (size_t)slot * kTraceCtas * TRACE_SLOTS;
   }
-  snprintf(t_last_name, sizeof(t_last_name), "brgemm_tc_bf16_128x%dx64%s%s", block_n,
-           split == 1 ? "" : split == 2 ? "_splitk2" : "_splitk4", mc ? "_mc2x2" : "");
+  snprintf(t_last_name, sizeof(t_last_name), "brgemm_tc_bf16_%dx%dx64%s%s", mc == 2 ? 256 : 128, block_n,
+           split == 1 ? "" : split == 2 ? "_splitk2" : "_splitk4", mc == 1 ? "_mc2x2" : mc == 2 ? "_2cta" : "");
+  if (mc == 2) {
+    if (block_n == 256) {
+      if (split > 1) launch_cfg_pair<256, 6, 2>(tmA, tmB, p, grid, stream);
+      else launch_cfg_pair<256, 6, 0>(tmA, tmB, p, grid, stream);
+    } else {
+      if (split > 1) launch_cfg_pair<128, 8, 2>(tmA, tmB, p, grid, stream);
+      else launch_cfg_pair<128, 8, 0>(tmA, tmB, p, grid, stream);
+    }
+  } else
   switch (block_n) {
   case 256:
-    if (mc && split > 1) launch_cfg<256, 4, 2, 1>(tmA, tmB, p, grid, stream);
-    else if (mc) launch_cfg<256, 4, 0, 1>(tmA, tmB, p, grid, stream);
+    if (mc == 1 && split > 1) launch_cfg<256, 4, 2, 1>(tmA, tmB, p, grid, stream);
+    else if (mc == 1) launch_cfg<256, 4, 0, 1>(tmA, tmB, p, grid, stream);
     else if (split > 1) launch_cfg<256, 4, 2>(tmA, tmB, p, grid, stream);
     else launch_cfg<256, 4, 0>(tmA, tmB, p, grid, stream);
     break;
   case 128:
-    if (mc && split > 1) launch_cfg<128, 6, 2, 1>(tmA, tmB, p, grid, stream);
-    else if (mc) launch_cfg<128, 6, 0, 1>(tmA, tmB, p, grid, stream);
+    if (mc == 1 && split > 1) launch_cfg<128, 6, 2, 1>(tmA, tmB, p, grid, stream);
+    else if (mc == 1) launch_cfg<128, 6, 0, 1>(tmA, tmB, p, grid, stream);
     else if (split > 1) launch_cfg<128, 6, 2>(tmA, tmB, p, grid, stream);
     else launch_cfg<128, 6, 0>(tmA, tmB, p, grid, stream);
     break;
