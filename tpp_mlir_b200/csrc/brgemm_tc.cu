@@ -59,6 +59,7 @@ struct TcParams {
   int32_t beta0, bin_kind, bin_mode, relu;
   int32_t c_vec_ok;     // C base 16B aligned and ldc % 8 == 0
   int32_t b_early;      // B (and D) do not depend on in-flight kernels: fetch B before the PDL wait
+  unsigned int *flags;  // split-K arrival counters per tile (flag-synchronised exchange, SPLITK == 3)
   float *ws;            // split-K exchange through L2: [tile][owner][src][128][64/S] f32 (SPLITK == 2)
   unsigned long long *trace;   // TPP_XSMM_TC_TRACE: per-CTA clock stamps (nullptr in normal runs)
 };
@@ -316,7 +317,7 @@ template <int BLOCK_N>
 __device__ __forceinline__ void splitk_epilogue_l2_wide(const TcParams &p, uint32_t tmem_acc, int q, int lane,
                                                         int64_t m0, int64_t n0, uint32_t rank, bool has_acc,
                                                         unsigned tile_x = blockIdx.x, unsigned tiles_x = gridDim.x,
-                                                        unsigned tile_y = blockIdx.y) {
+                                                        unsigned tile_y = blockIdx.y, bool flag_sync = false) {
   const int S = p.split_k;
   const int NC = BLOCK_N / S;          // columns per owner (>= 32)
   const int NCH = NC / 4;              // 16-byte chunks per owner row
@@ -345,8 +346,26 @@ __device__ __forceinline__ void splitk_epilogue_l2_wide(const TcParams &p, uint3
                                      __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
   }
   if (threadIdx.x == 64) trace_stamp(p, 8);
-  ptx::cluster_arrive();
-  ptx::cluster_wait();
+  if (!flag_sync) {
+    ptx::cluster_arrive();
+    ptx::cluster_wait();
+  } else {
+    // The S CTAs of this tile are NOT in one cluster (8-CTA clusters of pairs only fit 15 at a time on a B200,
+    // measured): they meet at a monotonically increasing arrival counter in global memory instead. All of them
+    // are co-resident (the launcher keeps such grids within one wave of 1-CTA-per-SM kernels), so spinning is safe.
+    __threadfence();                                      // my partial sums are visible device-wide ...
+    asm volatile("bar.sync 1, 128;" ::: "memory");        // ... for all 128 epilogue threads of this CTA
+    if (threadIdx.x == 64) {
+      unsigned int *cnt = p.flags + tile;
+      const unsigned int old = atomicAdd(cnt, 1u);
+      const unsigned int target = (old / (unsigned)S + 1u) * (unsigned)S;
+      unsigned int seen;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+      } while (seen < target);
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+  }
   if (threadIdx.x == 64) trace_stamp(p, 9);
   // phase 2: owned columns, 32 at a time
 #pragma unroll 1
@@ -763,8 +782,8 @@ brgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp >= 2) {
       const int q = warp & 3;
       splitk_epilogue_l2_wide<BLOCK_N>(p, tmem_acc, q, lane, m0, n0, rank, num_iters > 0, blockIdx.x, gridDim.x,
-                                       blockIdx.y);
-    } else {
+                                       blockIdx.y, /*flag_sync=*/SPLITK == 3);
+    } else if constexpr (SPLITK != 3) {
       __syncwarp();
       ptx::cluster_arrive();
       ptx::cluster_wait();
@@ -878,7 +897,7 @@ void launch_cfg_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
   attrs[1].id = cudaLaunchAttributeClusterDimension;
   attrs[1].val.clusterDim.x = 2;
   attrs[1].val.clusterDim.y = 1;
-  attrs[1].val.clusterDim.z = SPLITK ? (unsigned)p.split_k : 1;
+  attrs[1].val.clusterDim.z = SPLITK == 2 ? (unsigned)p.split_k : 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 2;
   TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK>, tmA, tmB, p));
@@ -1066,6 +1085,7 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   // (TPP_XSMM_XCHG=d; 26.7 us: st.shared::cluster moves only ~17 B/clk/SM)
   static const bool xchg_dsmem = [] { const char *e = getenv("TPP_XSMM_XCHG"); return e && e[0] == 'd'; }();
   p.ws = nullptr;
+  p.flags = nullptr;
   if (split > 1 && (!xchg_dsmem || block_n != 64)) {
     // per-thread workspace: kernels of one thread run on one stream, so launches are serialised and may share it
     thread_local float *ws = nullptr;
@@ -1081,6 +1101,19 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
       ws_bytes = want;
     }
     p.ws = ws;
+    // arrival counters of the flag-synchronised exchange: zeroed once, only ever incremented; one region per S so
+    // that every counter is a multiple of S between launches
+    thread_local unsigned int *flags = nullptr;
+    constexpr int kFlagTiles = 4096;
+    if (mc == 2) {
+      if (n_ctas / split > kFlagTiles) return false;
+      if (!flags) {
+        TPP_CUDA_CHECK(cudaMalloc(&flags, sizeof(unsigned int) * 2 * kFlagTiles));
+        // stream-ordered (and capturable: re-zeroing at every graph replay keeps the counters multiples of S)
+        TPP_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * 2 * kFlagTiles, stream));
+      }
+      p.flags = flags + (split == 4 ? kFlagTiles : 0);
+    }
   }
   if (trace_mode == 1 && n_ctas <= kTraceCtas) {
     TPP_CUDA_CHECK(cudaMemsetAsync(trace_buf, 0, sizeof(unsigned long long) * n_ctas * TRACE_SLOTS, stream));
@@ -1094,10 +1127,10 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
            split == 1 ? "" : split == 2 ? "_splitk2" : "_splitk4", mc == 1 ? "_mc2x2" : mc == 2 ? "_2cta" : "");
   if (mc == 2) {
     if (block_n == 256) {
-      if (split > 1) launch_cfg_pair<256, 6, 2>(tmA, tmB, p, grid, stream);
+      if (split > 1) launch_cfg_pair<256, 6, 3>(tmA, tmB, p, grid, stream);
       else launch_cfg_pair<256, 6, 0>(tmA, tmB, p, grid, stream);
     } else {
-      if (split > 1) launch_cfg_pair<128, 8, 2>(tmA, tmB, p, grid, stream);
+      if (split > 1) launch_cfg_pair<128, 8, 3>(tmA, tmB, p, grid, stream);
       else launch_cfg_pair<128, 8, 0>(tmA, tmB, p, grid, stream);
     }
   } else
