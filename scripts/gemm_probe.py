@@ -1,5 +1,5 @@
 import sys, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 from tpp_mlir_b200 import xsmm
 def run(m, n, k, b, iters=20):
     A = (torch.rand(b, m, k, device="cuda") - 0.5).bfloat16(); B = (torch.rand(b, k, n, device="cuda") - 0.5).bfloat16()
