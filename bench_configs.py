@@ -69,7 +69,7 @@ def cfg2(pk):
     want = torch.einsum("bik,bkj->ij", A[:, :8].double(), B.double())
     rel = float(((C[:8].double() - want).abs().max() / want.abs().max()).item())
     flops = 2.0 * m * n * k * batch
-    return {"config": "cfg2 brgemm bf16 1024x1024x1024 batch 16", "kernel": xsmm.handle_kernel(h), "seconds": t,
+    return {"config": "cfg2 brgemm bf16 1024x1024x1024 batch 16", "kernel": xsmm.last_kernel(), "seconds": t,
             "gflops": flops / t / 1e9,
             "roofline": {"bound": "tensor", "achieved": flops / t / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": flops / t / 1e12 / pk["bf16_tflops"], "flops_per_launch": flops,
@@ -100,7 +100,7 @@ def mlp(pk, batch, name, tiles):
     e1.record(stream)
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) * 1e-3 / steps
-    return {"config": name, "kernel": xsmm.handle_kernel(rp.handles[0]), "seconds_per_forward": t,
+    return {"config": name, "kernel": xsmm.last_kernel(), "seconds_per_forward": t,
             "gflops": cfg.flops() / t / 1e9,
             "roofline": {"bound": "tensor", "achieved": cfg.flops() / t / 1e12, "peak": pk["bf16_tflops"],
                          "unit": "TFLOP/s", "frac": cfg.flops() / t / 1e12 / pk["bf16_tflops"]},
@@ -118,7 +118,7 @@ def cfg3b(pk):
            for A, B, C, D in S]
     t = timed(fns, 400, warmup=ns)
     flops = 2.0 * m * n * 1024 + 2 * m * n
-    return {"config": "cfg3b fused_brgemm 256x1024 k=64 x batch 16 (strided view)", "kernel": xsmm.handle_kernel(h),
+    return {"config": "cfg3b fused_brgemm 256x1024 k=64 x batch 16 (strided view)", "kernel": xsmm.last_kernel(),
             "seconds": t, "gflops": flops / t / 1e9,
             "roofline": {"bound": "tensor", "achieved": flops / t / 1e12, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": flops / t / 1e12 / pk["bf16_tflops"]}}
