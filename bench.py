@@ -410,7 +410,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH_PER_GPU * LAYERS[0] * 2,
                 "d2h_bytes_per_step": BATCH_PER_GPU * LAYERS[-1] * 2, "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
                 "path": "xsmm C-ABI on registered pinned host buffers: update_device(input) -> 3 invokes -> "
-                        "update_host(output) -> sync, every step", "matches_device_run": e2e_ok},
+                        "update_host(output) -> stream sync, every step (the step is captured once with "
+                        "xsmm_cuda_graph_* and replayed: one host call per step)", "matches_device_run": e2e_ok},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": achieved_tflops / pk["bf16_tflops"], "traffic": traffic,

@@ -207,6 +207,8 @@ TPP_XSMM_EXPORT void *xsmm_cuda_get_stream(void);
 
 /* Block until every invoke issued so far (all threads) has completed. */
 TPP_XSMM_EXPORT void xsmm_cuda_sync(void);
+/* Block until everything issued on the calling thread's stream has completed. */
+TPP_XSMM_EXPORT void xsmm_cuda_stream_sync(void);
 
 /* Register a host range: pins it and creates a device mirror of the same size.
  * Invokes whose operands lie inside a registered range run on the mirror with no

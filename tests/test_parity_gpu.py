@@ -533,3 +533,83 @@ def test_concurrent_invokes_from_many_threads(orc):
         t.join()
     xsmm.sync()
     assert not errors, errors
+
+
+@pytest.mark.parametrize("layers,view", [(3, "flat"), (2, "flat"), (4, "flat"), (3, "k64xb16")])
+def test_captured_mlp_chain_is_fused_and_matches(layers, view):
+    """Graph capture of consecutive layers (C of one = A of the next) launches ONE persistent chain kernel
+    (SURVEY 8f-2); results are bit-identical to the per-layer kernels and within tolerance of the oracle."""
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    gen = oracle.TensorInit("normal", BF16, 11 + layers)
+    Ws = [gen.fill(1024, 1024) for _ in range(layers)]
+    bs = [gen.fill(1024) for _ in range(layers)]
+    x = gen.fill(256, 1024)
+
+    def dev_t(a):
+        return torch.from_numpy(a.view(np.int16)).cuda()
+
+    dW, db = [dev_t(w) for w in Ws], [dev_t(b) for b in bs]
+    acts = [dev_t(x)] + [torch.zeros(256, 1024, dtype=torch.int16, device="cuda") for _ in range(layers)]
+    if view == "flat":
+        h = xsmm.fused_brgemm_dispatch(BF16, 256, 1024, 1024, 1024, 1024, 1024, 256 * 1024, 1 << 20, 4 | 64 | 128, 0, 5, 4, 1)
+        nb = 1
+    else:  # strided view of the same math: k = 64 x batch 16
+        h = xsmm.fused_brgemm_dispatch(BF16, 256, 1024, 64, 1024, 1024, 1024, 64, 64 * 1024, 4 | 64 | 128, 0, 5, 4, 1)
+        nb = 16
+
+    def forward():
+        for l in range(layers):
+            xsmm.fused_brgemm_invoke(BF16, h, acts[l], 0, dW[l], 0, acts[l + 1], 0, db[l], 0, nb)
+
+    forward()
+    xsmm.sync()
+    direct = [a.clone() for a in acts[1:]]
+    n0 = xsmm.launch_count()
+    with xsmm.graph_capture() as g:
+        forward()
+    for a in acts[1:]:
+        a.zero_()
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == 1, "the captured chain must be ONE kernel launch"
+    assert xsmm.last_kernel().startswith(f"mlp_chain_bf16_{layers}layers"), xsmm.last_kernel()
+    for got, want in zip(acts[1:], direct):
+        assert torch.equal(got, want)
+    ref = x
+    for W, b in zip(Ws, bs):
+        y = np.zeros((256, 1024), np.uint16)
+        oracle.fused_brgemm(BF16, 256, 1024, 1024, 1024, 1024, 1024, 0, 0, 4, 0, 5, 4, 1, ref, W, y, b, 1)
+        ref = y
+    assert_close(BF16, acts[-1].cpu().numpy().view(np.uint16), ref)
+    # replay again: the grid-barrier counters are monotonic across launches
+    g.launch()
+    g.launch()
+    xsmm.sync()
+    assert torch.equal(acts[-1], direct[-1])
+    g.destroy()
+
+
+def test_captured_non_chain_sequences_are_not_fused():
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    a = (torch.rand(256, 1024, device="cuda") * 0.1).bfloat16()
+    w = (torch.rand(1024, 1024, device="cuda") * 0.1).bfloat16()
+    c1 = torch.zeros(256, 1024, device="cuda", dtype=torch.bfloat16)
+    c2 = torch.zeros(256, 1024, device="cuda", dtype=torch.bfloat16)
+    h = xsmm.brgemm_dispatch(BF16, 256, 1024, 1024, 1024, 1024, 1024, 0, 0, 4)
+    n0 = xsmm.launch_count()
+    with xsmm.graph_capture() as g:   # two independent GEMMs on the same input: not a chain
+        xsmm.brgemm_invoke(BF16, h, a, 0, w, 0, c1, 0, 1)
+        xsmm.brgemm_invoke(BF16, h, a, 0, w, 0, c2, 0, 1)
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == 2
+    assert torch.equal(c1, c2)
+    ref = (a.float() @ w.float())
+    assert ((c1.float() - ref).abs().max() / ref.abs().max()).item() < 1e-2
+    g.destroy()

@@ -30,6 +30,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstring>
 #include <mutex>
 #include <vector>
 
@@ -801,6 +802,159 @@ brgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
+// ---- fused chain kernel: L consecutive BRGEMM layers in ONE persistent launch ----------------------------
+// SURVEY.md section 8(f) item 2. The batch-256 MLP layer is latency-bound: per layer ~0.9 us of
+// kernel hand-off plus ~4.4 us of kernel, most of it waiting. When a captured invoke sequence (xsmm_cuda_graph_*)
+// contains layers whose C is the next layer's A, the runtime launches this kernel instead: same tiling as the
+// stand-alone kernel (128 x 64 tiles, 4-CTA split-K clusters, L2 exchange), but
+//   * the weight tiles of ALL layers (iters_per_cta x 8 KiB per layer) are fetched at kernel start and stay in
+//     shared memory: no weight traffic on the critical path of layers 1..L-1;
+//   * layers are separated by a grid-wide arrival counter instead of a kernel boundary (all CTAs are co-resident:
+//     <= 148 CTAs, 1 per SM), so there is no launch hand-off and no per-layer setup;
+//   * TMEM, barriers and the A stages are allocated once.
+constexpr int CHAIN_MAX_LAYERS = 4;
+constexpr int CHAIN_IPC = 4;   // (batch x k-block) iterations per CTA and layer == A stages
+
+struct ChainParams {
+  CUtensorMap tmA[CHAIN_MAX_LAYERS], tmB[CHAIN_MAX_LAYERS];
+  TcParams layer[CHAIN_MAX_LAYERS];
+  unsigned int *grid_counter;   // monotonic arrival counter shared by all CTAs of this grid size
+  int num_layers;
+  int weights_early;            // no layer's weights / bias are written by in-flight kernels
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainParams cp) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;                                     // CHAIN_IPC stages x 16 KiB
+  const uint32_t smem_w = smem_base + CHAIN_IPC * A_STAGE_BYTES;         // L x CHAIN_IPC tiles x 8 KiB
+  const uint32_t bar_base = smem_w + CHAIN_MAX_LAYERS * CHAIN_IPC * B_CHUNK_BYTES;
+  const uint32_t a_full = bar_base;                                      // CHAIN_IPC
+  const uint32_t w_full = bar_base + 8 * CHAIN_IPC;                      // CHAIN_MAX_LAYERS
+  const uint32_t acc_bar = w_full + 8 * CHAIN_MAX_LAYERS;
+  const uint32_t layer_bar = acc_bar + 8;
+  const uint32_t tmem_slot = layer_bar + 8;
+  uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * 64;
+  const uint32_t rank = blockIdx.z;                   // k-slice of this CTA (cluster = (1,1,4))
+  const int L = cp.num_layers;
+  const unsigned int G = gridDim.x * gridDim.y * gridDim.z;
+
+  if (warp == 0 && lane == 0) {
+    for (int l = 0; l < L; ++l) {
+      ptx::prefetch_tensormap(&cp.tmA[l]);
+      ptx::prefetch_tensormap(&cp.tmB[l]);
+      ptx::mbar_init(w_full + 8 * l, 1);
+    }
+    for (int s = 0; s < CHAIN_IPC; ++s) ptx::mbar_init(a_full + 8 * s, 1);
+    ptx::mbar_init(acc_bar, 1);
+    ptx::mbar_init(layer_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 64);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  // weights of every layer: this CTA's k-slice (CHAIN_IPC k-blocks) x its 64 columns
+  auto issue_weights = [&]() {
+    for (int l = 0; l < L; ++l) {
+      const TcParams &p = cp.layer[l];
+      ptx::mbar_arrive_expect_tx(w_full + 8 * l, CHAIN_IPC * B_CHUNK_BYTES);
+      for (int i = 0; i < CHAIN_IPC; ++i) {
+        const int32_t it = (int32_t)rank * CHAIN_IPC + i;
+        const int32_t b = it / p.k_iters, kb = it - b * p.k_iters;
+        ptx::tma_load_3d(smem_w + (l * CHAIN_IPC + i) * B_CHUNK_BYTES, &cp.tmB[l], w_full + 8 * l, n0, kb * BLOCK_K, b);
+      }
+    }
+  };
+  if (warp == 0 && lane == 0 && cp.weights_early) issue_weights();
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (warp == 0 && lane == 0 && !cp.weights_early) issue_weights();
+
+  for (int l = 0; l < L; ++l) {
+    const TcParams &p = cp.layer[l];
+    const uint32_t par = l & 1;
+    if (warp == 0) {
+      // ===== producer: this layer's A k-slice (previous layer's output once the whole grid has stored it) =====
+      if (lane == 0) {
+        if (l > 0) {
+          ptx::mbar_wait(layer_bar, (l - 1) & 1);
+          asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of Y(l-1) -> async-proxy (TMA) reads
+        }
+        for (int i = 0; i < CHAIN_IPC; ++i) {
+          const int32_t it = (int32_t)rank * CHAIN_IPC + i;
+          const int32_t b = it / p.k_iters, kb = it - b * p.k_iters;
+          ptx::mbar_arrive_expect_tx(a_full + 8 * i, A_STAGE_BYTES);
+          ptx::tma_load_3d(smem_a + i * A_STAGE_BYTES, &cp.tmA[l], a_full + 8 * i, kb * BLOCK_K, m0, b);
+        }
+      }
+      __syncwarp();
+      ptx::cluster_arrive();   // the split-K exchange barrier of this layer (all threads of the cluster)
+      ptx::cluster_wait();
+    } else if (warp == 1) {
+      // ===== MMA issuer =====
+      if (lane == 0) {
+        constexpr uint32_t idesc = ptx::umma_idesc_bf16(BLOCK_M, 64, 0, 1);
+        ptx::mbar_wait(w_full + 8 * l, 0);
+        for (int i = 0; i < CHAIN_IPC; ++i) {
+          ptx::mbar_wait(a_full + 8 * i, par);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_addr = smem_a + i * A_STAGE_BYTES;
+          const uint32_t b_addr = smem_w + (l * CHAIN_IPC + i) * B_CHUNK_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+            const uint64_t da = ptx::umma_smem_desc_sw128(a_addr + kk * (UMMA_K * 2), 16, 1024);
+            const uint64_t db = ptx::umma_smem_desc_sw128(b_addr + kk * (UMMA_K * 128), B_CHUNK_BYTES, 1024);
+            ptx::umma_bf16(tmem_acc, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        ptx::umma_commit(acc_bar);
+      }
+      __syncwarp();
+      ptx::cluster_arrive();
+      ptx::cluster_wait();
+    } else {
+      // ===== epilogue: split-K exchange + fused bias/ReLU/store, then the grid-wide layer barrier =====
+      const int q = warp & 3;
+      ptx::mbar_wait(acc_bar, par);
+      ptx::tc_fence_after_sync();
+      splitk_epilogue_l2<16>(p, tmem_acc, q, lane, m0, n0, rank, true);
+      if (l + 1 < L) {
+        __threadfence();                                   // this CTA's rows of Y(l) are visible device-wide
+        ptx::tc_fence_before_sync();                       // TMEM reads done before the next layer's MMAs overwrite it
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (threadIdx.x == 64) {
+          const unsigned int old = atomicAdd(cp.grid_counter, 1u);
+          const unsigned int target = (old / G + 1u) * G;
+          unsigned int seen;
+          do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cp.grid_counter) : "memory");
+          } while (seen < target);
+          asm volatile("fence.proxy.async;" ::: "memory");
+          ptx::mbar_arrive(layer_bar);                     // release the producer for layer l+1
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_acc, 64);
+  }
+}
+
 // ---- host side ----------------------------------------------------------------
 
 constexpr int kTraceRing = 128, kTraceRingCtas = 256;
@@ -1174,6 +1328,102 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
       fprintf(stderr, "\n");
     }
   }
+  return true;
+}
+
+// ---- fused chain launch -------------------------------------------------------------------------------------
+// True if layers[0..L) can run in mlp_chain_kernel: every layer is a bf16 tensor-core BRGEMM with beta_0, the same
+// m and n, exactly 4 x CHAIN_IPC (batch x k-block) iterations, and layer l+1 reads layer l's C as its A.
+bool brgemm_chain_supported(const KernelDesc *const *descs, const GemmArgs *args, int L) {
+  static const bool off = [] { const char *e = getenv("TPP_XSMM_CHAIN"); return e && e[0] == '0'; }();
+  if (off || L < 2 || L > CHAIN_MAX_LAYERS) return false;
+  const KernelDesc &d0 = *descs[0];
+  const int64_t tiles = ((d0.n + 63) / 64) * ((d0.m + BLOCK_M - 1) / BLOCK_M);
+  if (tiles * 4 > 128) return false;   // 4-CTA clusters: 33 fit at a time (measured); all CTAs must be co-resident
+  for (int l = 0; l < L; ++l) {
+    const KernelDesc &d = *descs[l];
+    if (d.impl != KernelImpl::BrgemmTC || !(d.gemm_flags & 4) || d.m != d0.m || d.n != d0.n) return false;
+    const int64_t k_iters = (d.k + BLOCK_K - 1) / BLOCK_K;
+    if ((d.k % BLOCK_K) != 0 || args[l].batch * k_iters != 4 * CHAIN_IPC) return false;
+    if (!aligned16(args[l].A) || !aligned16(args[l].B) || !aligned16(args[l].C) || (d.ldc % 8) != 0) return false;
+    if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && !(d.binary_kind == 1 && (d.binary_flags & 4))) return false;
+    if (l > 0) {
+      // the chain link: A(l) is exactly C(l-1), viewed with the same leading dimension
+      if (args[l].A != args[l - 1].C || d.lda != descs[l - 1]->ldc) return false;
+      if (args[l].batch * d.k != descs[l - 1]->n) return false;
+    }
+    for (int j = 0; j < L; ++j) {   // weights / bias must not be produced inside the chain
+      if (args[l].B == args[j].C || (args[l].D && args[l].D == args[j].C)) return false;
+      if (j != l && args[l].C == args[j].C) return false;
+    }
+  }
+  return true;
+}
+
+bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, int L, cudaStream_t stream) {
+  ChainParams cp;
+  memset(&cp, 0, sizeof(cp));
+  const KernelDesc &d0 = *descs[0];
+  dim3 grid((unsigned)((d0.n + 63) / 64), (unsigned)((d0.m + BLOCK_M - 1) / BLOCK_M), 4);
+  const int n_ctas = (int)(grid.x * grid.y * grid.z);
+  // per-thread exchange workspace + grid counters (same life cycle as the stand-alone kernel's workspace)
+  thread_local float *ws = nullptr;
+  thread_local unsigned int *counters = nullptr;
+  if (!ws) {
+    TPP_CUDA_CHECK(cudaMalloc(&ws, (size_t)148 * BLOCK_M * 64 * sizeof(float)));
+    TPP_CUDA_CHECK(cudaMalloc(&counters, sizeof(unsigned int) * 256));
+    TPP_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 256, stream));
+  }
+  cp.grid_counter = counters + n_ctas;   // one counter per grid size: always a multiple of G between launches
+  cp.num_layers = L;
+  cp.weights_early = 1;
+  for (int l = 0; l < L; ++l) {
+    const KernelDesc &d = *descs[l];
+    const GemmArgs &g = args[l];
+    const uint64_t nb = (uint64_t)g.batch;
+    if (!encode_map(&cp.tmA[l], g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, BLOCK_K,
+                    BLOCK_M) ||
+        !encode_map(&cp.tmB[l], g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, 64, BLOCK_K))
+      return false;
+    TcParams &p = cp.layer[l];
+    p.C = g.C; p.D = g.D;
+    p.m = d.m; p.n = d.n; p.ldc = d.ldc;
+    p.k_iters = (int32_t)(d.k / BLOCK_K);
+    p.total_iters = 4 * CHAIN_IPC;
+    p.split_k = 4;
+    p.beta0 = 1;
+    p.bin_kind = (d.op == OpClass::FusedBrgemm && g.D) ? (int)d.binary_kind : 0;
+    p.bin_mode = bin_mode_from_flags(d.binary_flags);
+    p.relu = d.op == OpClass::FusedBrgemm && d.unary_kind == 5;
+    p.c_vec_ok = 1;
+    p.b_early = 0;
+    p.flags = nullptr;
+    p.ws = ws;
+    p.trace = nullptr;
+    if (!g.b_independent) cp.weights_early = 0;
+  }
+  constexpr int smem = CHAIN_IPC * A_STAGE_BYTES + CHAIN_MAX_LAYERS * CHAIN_IPC * B_CHUNK_BYTES +
+                       (CHAIN_IPC + CHAIN_MAX_LAYERS + 2) * 8 + 16 + 1024;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  });
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = 1;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = 4;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_kernel, cp));
+  snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dlayers_128x64x64_splitk4", L);
   return true;
 }
 

@@ -78,16 +78,29 @@ int64_t tpp_replay_mlp_graph(int64_t dtype, int64_t num_layers, const int64_t *h
 
 // One forward on host buffers that were registered with xsmm_cuda_register_host: upload the
 // step's input, run the layers on the mirrors, download the step's output, wait for it.
+// use_graph != 0: the whole step (H2D copy, invokes, D2H copy) is captured once with
+// xsmm_cuda_graph_begin/end and replayed - one host call + one stream wait per step.
 __attribute__((visibility("default")))
-void tpp_replay_mlp_e2e(int64_t dtype, int64_t num_layers, const int64_t *handles, const int64_t *layer_sizes,
-                        int64_t batch, int64_t bn, int64_t bk, int64_t bc, const TppMlpSet *set, int64_t steps,
-                        int64_t has_bias, int64_t elem_size) {
-  for (int64_t s = 0; s < steps; ++s) {
+int64_t tpp_replay_mlp_e2e(int64_t dtype, int64_t num_layers, const int64_t *handles, const int64_t *layer_sizes,
+                           int64_t batch, int64_t bn, int64_t bk, int64_t bc, const TppMlpSet *set, int64_t steps,
+                           int64_t has_bias, int64_t elem_size, int64_t use_graph, int64_t *graph_io) {
+  auto one_step = [&]() {
     xsmm_cuda_update_device(set->acts[0], batch * layer_sizes[0] * elem_size);
     tpp_replay_mlp(dtype, num_layers, handles, layer_sizes, batch, bn, bk, bc, set, 1, 0, 1, has_bias);
     xsmm_cuda_update_host(set->acts[num_layers], batch * layer_sizes[num_layers] * elem_size);
-    xsmm_cuda_sync();
+  };
+  if (use_graph && graph_io && !*graph_io) {
+    if (xsmm_cuda_graph_begin() != 0) return -1;
+    one_step();
+    *graph_io = xsmm_cuda_graph_end();
+    if (!*graph_io) return -1;
   }
+  for (int64_t s = 0; s < steps; ++s) {
+    if (use_graph) xsmm_cuda_graph_launch(*graph_io);
+    else one_step();
+    xsmm_cuda_stream_sync();   // the step's output is in host memory
+  }
+  return 0;
 }
 
 } // extern "C"

@@ -54,6 +54,9 @@ void launch_brgemm_simt(const KernelDesc &d, const GemmArgs &g, cudaStream_t str
 bool brgemm_tc_supported(const KernelDesc &d);
 void brgemm_tc_configure(KernelDesc &d);
 bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t stream);
+// L consecutive layers (C of one is A of the next) in one persistent kernel: see brgemm_tc.cu
+bool brgemm_chain_supported(const KernelDesc *const *descs, const GemmArgs *args, int L);
+bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, int L, cudaStream_t stream);
 const char *brgemm_tc_last_name();   // tile configuration of this thread's last tcgen05 launch
 void brgemm_tc_dump_trace();   // debug, TPP_XSMM_TC_TRACE=2
 

@@ -81,7 +81,15 @@ struct Staging {
   }
 };
 
+struct PendingGemm {
+  const KernelDesc *d;
+  GemmArgs g;
+};
+
 struct ThreadCtx {
+  // BRGEMM invokes recorded during graph capture and not launched yet: consecutive layers whose C is the next
+  // layer's A are fused into one persistent kernel when the sequence is flushed (see flush_pending)
+  std::vector<PendingGemm> pending;
   cudaStream_t stream = nullptr; // legacy default stream unless xsmm_cuda_set_stream was called
   int device = -1;               // device this thread last launched on
   const char *last_kernel = "";
@@ -372,6 +380,68 @@ int64_t gemm_family_dispatch(OpClass op, int64_t dtype, int64_t m, int64_t n, in
   });
 }
 
+// Launch one resolved BRGEMM (tensor-core kernel, VNNI un-interleave + tensor-core twin, or the generic kernel).
+void issue_gemm(const KernelDesc *d, const GemmArgs &g, cudaStream_t stream) {
+  const int64_t batch = g.batch;
+  bool launched = false;
+  if (d->impl == KernelImpl::BrgemmTC) {
+    launched = launch_brgemm_tc(*d, g, stream);
+    if (launched) t_ctx.last_kernel = brgemm_tc_last_name();
+  } else if (d->flat_twin && batch > 0 && (double)d->m * d->n * d->k * batch >= 2097152.0 &&
+             (batch == 1 || d->stride_b == d->k * d->ldb) && aligned16(g.B)) {
+    // VNNI-B -> flat B in a per-thread scratch (batches are contiguous: one tall [batch*k][ldb] un-interleave)
+    thread_local Staging vnni_scratch;
+    const int64_t rows = batch * d->k;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    const size_t need = (size_t)rows * d->ldb * 2;
+    if (cs == cudaStreamCaptureStatusNone || need <= vnni_scratch.cap) {
+      void *flat = vnni_scratch.get(need);
+      launch_vnni2_unpack(g.B, flat, rows, d->n, d->ldb, d->ldb, stream);
+      count_launch();
+      GemmArgs gf = g;
+      gf.B = flat;
+      gf.b_independent = false;   // produced by the kernel just launched
+      launched = launch_brgemm_tc(*d->flat_twin, gf, stream);
+      if (launched) t_ctx.last_kernel = "vnni2_unpack+brgemm_tc_bf16";
+    }
+  }
+  if (!launched) {
+    launch_brgemm_simt(*d, g, stream);
+    t_ctx.last_kernel = d->dtype == kF32 ? "brgemm_simt_f32_64x64x16" : "brgemm_simt_bf16_64x64x16";
+  }
+  count_launch();
+}
+
+// Launch the BRGEMMs recorded during graph capture, in order. Runs of 2..4 consecutive layers that form a chain
+// (C of layer l is A of layer l+1, same m / n, tensor-core eligible) go to the persistent fused kernel
+// ("whole-MLP fusion ... or CUDA-graph capture of the invoke sequence"); everything else is
+// launched exactly as a direct invoke would.
+void flush_pending() {
+  if (t_ctx.pending.empty()) return;
+  std::vector<PendingGemm> list;
+  list.swap(t_ctx.pending);
+  cudaStream_t stream = t_ctx.stream;
+  size_t i = 0;
+  while (i < list.size()) {
+    int fused = 0;
+    for (int L = 4; L >= 2 && !fused; --L) {
+      if (i + L > list.size()) continue;
+      const KernelDesc *descs[4];
+      GemmArgs args[4];
+      for (int l = 0; l < L; ++l) { descs[l] = list[i + l].d; args[l] = list[i + l].g; }
+      if (brgemm_chain_supported(descs, args, L) && launch_brgemm_chain(descs, args, L, stream)) {
+        t_ctx.last_kernel = brgemm_tc_last_name();
+        count_launch();
+        fused = L;
+      }
+    }
+    if (fused) { i += fused; continue; }
+    issue_gemm(list[i].d, list[i].g, stream);
+    ++i;
+  }
+}
+
 // TPP_XSMM_HOST_PROFILE=1: where the host time of a BRGEMM invoke goes (printed at thread exit)
 const bool g_host_prof = getenv("TPP_XSMM_HOST_PROFILE") != nullptr;
 struct HostProf {
@@ -435,34 +505,12 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
                       (!has_d || !t_ctx.recently_written(ops[3].dev, (size_t)((ops[3].rows - 1) * ops[3].ld + ops[3].width) * es));
     t_ctx.note_output(ops[2].dev, (size_t)((d->m - 1) * d->ldc + d->n) * es);
   }
-  bool launched = false;
-  if (d->impl == KernelImpl::BrgemmTC) {
-    launched = launch_brgemm_tc(*d, g, stream);
-    if (launched) t_ctx.last_kernel = brgemm_tc_last_name();
-  } else if (d->flat_twin && batch > 0 && (double)d->m * d->n * d->k * batch >= 2097152.0 &&
-             (batch == 1 || d->stride_b == d->k * d->ldb) && aligned16(g.B)) {
-    // VNNI-B -> flat B in a per-thread scratch (batches are contiguous: one tall [batch*k][ldb] un-interleave)
-    thread_local Staging vnni_scratch;
-    const int64_t rows = batch * d->k;
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(stream, &cs);
-    const size_t need = (size_t)rows * d->ldb * 2;
-    if (cs == cudaStreamCaptureStatusNone || need <= vnni_scratch.cap) {
-      void *flat = vnni_scratch.get(need);
-      launch_vnni2_unpack(g.B, flat, rows, d->n, d->ldb, d->ldb, stream);
-      count_launch();
-      GemmArgs gf = g;
-      gf.B = flat;
-      gf.b_independent = false;   // produced by the kernel just launched
-      launched = launch_brgemm_tc(*d->flat_twin, gf, stream);
-      if (launched) t_ctx.last_kernel = "vnni2_unpack+brgemm_tc_bf16";
-    }
+  if (t_ctx.capturing && !sc.any_host && d->impl == KernelImpl::BrgemmTC) {
+    t_ctx.pending.push_back({d, g});   // launched (possibly fused with its neighbours) by flush_pending()
+    return;
   }
-  if (!launched) {
-    launch_brgemm_simt(*d, g, stream);
-    t_ctx.last_kernel = d->dtype == kF32 ? "brgemm_simt_f32_64x64x16" : "brgemm_simt_bf16_64x64x16";
-  }
-  count_launch();
+  flush_pending();
+  issue_gemm(d, g, stream);
   if (g_host_prof) {
     const uint64_t t2 = now_ns();
     t_prof.n++; t_prof.resolve_ns += t1 - t0; t_prof.launch_ns += t2 - t1; t_prof.total_ns += t2 - t0;
@@ -607,6 +655,7 @@ extern "C" void xsmm_fused_brgemm_invoke(int64_t dtype, int64_t addr, void *alig
 
 static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int64_t offIn, bool use_imm, float imm,
                               void *pOut, int64_t offOut) {
+  flush_pending();
   if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
   Operand ops[2];
   const int mode = bcast_mode_unary(d->flags);
@@ -683,6 +732,7 @@ extern "C" void xsmm_binary_invoke(int64_t dtype, int64_t addr, void *alignedPtr
                                    void *alignedPtrRhs, int64_t offsetRhs, void *alignedPtrOut, int64_t offsetOut) {
   const KernelDesc *d = desc_of(addr, OpClass::Binary);
   if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
+  flush_pending();
   const int64_t f = d->flags;
   const int mode0 = (f & 1) ? kBcastRow : (f & 4) ? kBcastCol : (f & 16) ? kBcastScalar : kBcastNone;
   const int mode1 = (f & 2) ? kBcastRow : (f & 8) ? kBcastCol : (f & 32) ? kBcastScalar : kBcastNone;
@@ -751,6 +801,10 @@ extern "C" void xsmm_cuda_sync(void) {
   if (g_cuda_ready.load()) TPP_CUDA_CHECK(cudaDeviceSynchronize());
 }
 
+extern "C" void xsmm_cuda_stream_sync(void) {
+  if (g_cuda_ready.load()) TPP_CUDA_CHECK(cudaStreamSynchronize(t_ctx.stream));
+}
+
 extern "C" int64_t xsmm_cuda_register_host(void *host, int64_t bytes, int64_t upload) {
   ensure_cuda();
   if (!host || bytes <= 0) return -1;
@@ -790,6 +844,7 @@ extern "C" int64_t xsmm_cuda_unregister_host(void *host) {
 extern "C" int64_t xsmm_cuda_update_device(void *host, int64_t bytes) {
   Mirror m;
   if (!find_mirror(host, &m) || static_cast<char *>(host) + bytes > m.host + m.bytes) return -1;
+  flush_pending();
   TPP_CUDA_CHECK(cudaMemcpyAsync(m.dev + (static_cast<char *>(host) - m.host), host, (size_t)bytes,
                                  cudaMemcpyHostToDevice, t_ctx.stream));
   return 0;
@@ -798,6 +853,7 @@ extern "C" int64_t xsmm_cuda_update_device(void *host, int64_t bytes) {
 extern "C" int64_t xsmm_cuda_update_host(void *host, int64_t bytes) {
   Mirror m;
   if (!find_mirror(host, &m) || static_cast<char *>(host) + bytes > m.host + m.bytes) return -1;
+  flush_pending();
   TPP_CUDA_CHECK(cudaMemcpyAsync(host, m.dev + (static_cast<char *>(host) - m.host), (size_t)bytes,
                                  cudaMemcpyDeviceToHost, t_ctx.stream));
   return 0;
@@ -826,6 +882,7 @@ extern "C" int64_t xsmm_cuda_graph_begin(void) {
 
 extern "C" int64_t xsmm_cuda_graph_end(void) {
   if (!t_ctx.capturing) return 0;
+  flush_pending();
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(t_ctx.stream, &graph);
   t_ctx.capturing = false;

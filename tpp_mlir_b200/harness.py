@@ -196,8 +196,8 @@ def replay_lib():
         i64, p = _ct.c_int64, _ct.c_void_p
         lib.tpp_replay_mlp.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, i64, i64, i64]
         lib.tpp_replay_mlp.restype = None
-        lib.tpp_replay_mlp_e2e.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, i64, i64]
-        lib.tpp_replay_mlp_e2e.restype = None
+        lib.tpp_replay_mlp_e2e.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, i64, i64, i64, p]
+        lib.tpp_replay_mlp_e2e.restype = i64
         lib.tpp_replay_mlp_graph.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, p, i64, i64, i64, i64]
         lib.tpp_replay_mlp_graph.restype = i64
         _replay_lib = lib
@@ -250,9 +250,15 @@ class NativeMlpLoop:
             raise RuntimeError("CUDA graph capture of the MLP forward failed")
         self._step += steps
 
-    def run_e2e(self, steps: int, elem_size: int = 2) -> None:
-        """Host buffers registered with xsmm.register_host: per step H2D(input), layers, D2H(output), sync."""
+    def run_e2e(self, steps: int, elem_size: int = 2, graph: bool = True) -> None:
+        """Host buffers registered with xsmm.register_host: per step H2D(input), layers, D2H(output), stream
+        sync. graph=True replays the captured step (copies included) with one host call per step."""
         cfg = self.cfg
         bn, bk, bc = cfg.tiles
-        replay_lib().tpp_replay_mlp_e2e(cfg.dtype, cfg.num_layers, self._handles, self._sizes, cfg.batch, bn, bk, bc,
-                                        self._sets, steps, 1 if cfg.bias else 0, elem_size)
+        if not hasattr(self, "_e2e_graph"):
+            self._e2e_graph = _ct.c_int64(0)
+        rc = replay_lib().tpp_replay_mlp_e2e(cfg.dtype, cfg.num_layers, self._handles, self._sizes, cfg.batch, bn, bk,
+                                             bc, self._sets, steps, 1 if cfg.bias else 0, elem_size,
+                                             1 if graph else 0, _ct.byref(self._e2e_graph))
+        if rc != 0:
+            raise RuntimeError("e2e replay failed (graph capture)")

@@ -57,6 +57,7 @@ EXPORTS = {
     "xsmm_cuda_set_stream": (None, [c_void_p]),
     "xsmm_cuda_get_stream": (c_void_p, []),
     "xsmm_cuda_sync": (None, []),
+    "xsmm_cuda_stream_sync": (None, []),
     "xsmm_cuda_register_host": (c_int64, [c_void_p, c_int64, c_int64]),
     "xsmm_cuda_unregister_host": (c_int64, [c_void_p]),
     "xsmm_cuda_update_device": (c_int64, [c_void_p, c_int64]),
