@@ -304,7 +304,7 @@ def main():
     flops_step_rank = cfg.flops()
     value = flops_step_rank * n_gpus / (ms_per_step * 1e-3) / 1e9
 
-    if os.environ.get("TPP_XSMM_TC_TRACE") == "2":
+    if os.environ.get("TPP_XSMM_TC_TRACE") in ("2", "3"):
         xsmm.LIB.xsmm_cuda_debug_dump_trace()
 
     # hot-L2 variant (what tpp-run measures: the same buffers every iteration), for information

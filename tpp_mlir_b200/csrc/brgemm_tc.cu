@@ -360,9 +360,10 @@ __device__ __forceinline__ void splitk_epilogue_l2_wide(const TcParams &p, uint3
       unsigned int *cnt = p.flags + tile;
       const unsigned int old = atomicAdd(cnt, 1u);
       const unsigned int target = (old / (unsigned)S + 1u) * (unsigned)S;
-      unsigned int seen;
+      unsigned int seen, spins = 0;
       do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+        if (++spins > (1u << 22)) __trap();   // co-residency assumption broken: fail loudly, never hang
       } while (seen < target);
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -821,7 +822,15 @@ struct ChainParams {
   unsigned int *grid_counter;   // monotonic arrival counter shared by all CTAs of this grid size
   int num_layers;
   int weights_early;            // no layer's weights / bias are written by in-flight kernels
+  unsigned long long *trace;    // TPP_XSMM_TC_TRACE=1: clock stamps of layer 1 (nullptr in normal runs)
 };
+
+__device__ __forceinline__ void chain_stamp(const ChainParams &cp, int slot) {
+  if (cp.trace) {
+    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    cp.trace[(size_t)cta * TRACE_SLOTS + slot] = clock64();
+  }
+}
 
 __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainParams cp) {
   extern __shared__ uint8_t smem_raw[];
@@ -862,6 +871,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_kernel(const __grid_
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_acc = *tmem_slot_ptr;
+  if (threadIdx.x == 0) chain_stamp(cp, 0);
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
@@ -889,7 +899,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_kernel(const __grid_
       if (lane == 0) {
         if (l > 0) {
           ptx::mbar_wait(layer_bar, (l - 1) & 1);
-          asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy stores of Y(l-1) -> async-proxy (TMA) reads
+          // Y(l-1) was written by other SMs with generic-proxy stores, fenced at gpu scope before the arrival
+          // counter moved and acquired by this CTA's thread 64: it is in L2, which is where TMA reads from.
+          if (l == 1) chain_stamp(cp, 1);
         }
         for (int i = 0; i < CHAIN_IPC; ++i) {
           const int32_t it = (int32_t)rank * CHAIN_IPC + i;
@@ -897,6 +909,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_kernel(const __grid_
           ptx::mbar_arrive_expect_tx(a_full + 8 * i, A_STAGE_BYTES);
           ptx::tma_load_3d(smem_a + i * A_STAGE_BYTES, &cp.tmA[l], a_full + 8 * i, kb * BLOCK_K, m0, b);
         }
+        if (l == 1) chain_stamp(cp, 2);
       }
       __syncwarp();
       ptx::cluster_arrive();   // the split-K exchange barrier of this layer (all threads of the cluster)
@@ -909,6 +922,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_kernel(const __grid_
         for (int i = 0; i < CHAIN_IPC; ++i) {
           ptx::mbar_wait(a_full + 8 * i, par);
           ptx::tc_fence_after_sync();
+          if (l == 1 && i == 0) chain_stamp(cp, 3);
+          if (l == 1 && i == CHAIN_IPC - 1) chain_stamp(cp, 4);
           const uint32_t a_addr = smem_a + i * A_STAGE_BYTES;
           const uint32_t b_addr = smem_w + (l * CHAIN_IPC + i) * B_CHUNK_BYTES;
 #pragma unroll
@@ -928,19 +943,24 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_kernel(const __grid_
       const int q = warp & 3;
       ptx::mbar_wait(acc_bar, par);
       ptx::tc_fence_after_sync();
+      if (l == 1 && threadIdx.x == 64) chain_stamp(cp, 7);
       splitk_epilogue_l2<16>(p, tmem_acc, q, lane, m0, n0, rank, true);
       if (l + 1 < L) {
-        __threadfence();                                   // this CTA's rows of Y(l) are visible device-wide
         ptx::tc_fence_before_sync();                       // TMEM reads done before the next layer's MMAs overwrite it
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // all 128 epilogue threads have issued their Y(l) stores
         if (threadIdx.x == 64) {
+          // one gpu-scope fence by the arriving thread: the CTA barrier above ordered the other threads' stores
+          // before it (cumulativity), so they are visible device-wide before the counter moves
+          __threadfence();
           const unsigned int old = atomicAdd(cp.grid_counter, 1u);
           const unsigned int target = (old / G + 1u) * G;
-          unsigned int seen;
+          unsigned int seen, spins = 0;
           do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(cp.grid_counter) : "memory");
+            if (++spins > (1u << 22)) __trap();            // co-residency assumption broken: fail loudly, never hang
           } while (seen < target);
-          asm volatile("fence.proxy.async;" ::: "memory");
+          if (l == 1) chain_stamp(cp, 11);
+          if (l == 0) chain_stamp(cp, 5);
           ptx::mbar_arrive(layer_bar);                     // release the producer for layer l+1
         }
       }
@@ -949,6 +969,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_kernel(const __grid_
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) chain_stamp(cp, 12);
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_acc, 64);
@@ -961,6 +982,7 @@ constexpr int kTraceRing = 128, kTraceRingCtas = 256;
 unsigned long long *g_trace_buf = nullptr;
 int g_trace_next = 0;
 int g_trace_ctas[kTraceRing] = {0};
+int g_chain_trace_ctas = 0, g_chain_trace_layers = 0;
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -1422,6 +1444,20 @@ bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, i
   attrs[1].val.clusterDim.z = 4;
   cfg.attrs = attrs;
   cfg.numAttrs = 2;
+  // TPP_XSMM_TC_TRACE=3: the chain kernels stamp SM clocks of layer 1 into a buffer that is baked into the captured
+  // graph; xsmm_cuda_debug_dump_trace() prints the averages of the last replay (no synchronisation here: this
+  // function runs inside a stream capture)
+  static const bool trace_on = [] { const char *e = getenv("TPP_XSMM_TC_TRACE"); return e && atoi(e) == 3; }();
+  if (trace_on) {
+    if (!g_trace_buf) {
+      TPP_CUDA_CHECK(cudaMalloc(&g_trace_buf, sizeof(unsigned long long) * kTraceRing * kTraceRingCtas * TRACE_SLOTS));
+      TPP_CUDA_CHECK(cudaMemsetAsync(g_trace_buf, 0, sizeof(unsigned long long) * kTraceRing * kTraceRingCtas * TRACE_SLOTS, stream));
+    }
+    cp.trace = g_trace_buf;
+    if (L > 1) cp.layer[1].trace = g_trace_buf;   // splitk_epilogue_l2 stamps slots 8 (pushed) 9 (cluster) 10 (stored)
+    g_chain_trace_ctas = n_ctas;
+    g_chain_trace_layers = L;
+  }
   TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_kernel, cp));
   snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dlayers_128x64x64_splitk4", L);
   return true;
@@ -1431,6 +1467,25 @@ bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, i
 void brgemm_tc_dump_trace() {
   if (!g_trace_buf) return;
   TPP_CUDA_CHECK(cudaDeviceSynchronize());
+  if (g_chain_trace_ctas) {
+    const int n_ctas = g_chain_trace_ctas;
+    std::vector<unsigned long long> h((size_t)n_ctas * TRACE_SLOTS);
+    TPP_CUDA_CHECK(cudaMemcpy(h.data(), g_trace_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    static const char *names[13] = {"", "L1_released", "L1_A_issued", "L1_data1", "L1_data_all", "L0_gridbar_passed", "",
+                                    "L1_acc_ready", "L1_pushed", "L1_cluster", "L1_stored", "L1_gridbar_passed", "end"};
+    fprintf(stderr, "chain-trace %d layers, %d CTAs: avg clocks since CTA start:", g_chain_trace_layers, n_ctas);
+    for (int sl : {5, 1, 2, 3, 4, 7, 8, 9, 10, 11, 12}) {
+      double sum = 0;
+      int cnt = 0;
+      for (int c = 0; c < n_ctas; ++c) {
+        const unsigned long long *r = &h[(size_t)c * TRACE_SLOTS];
+        if (r[sl] && r[0] && r[sl] > r[0]) { sum += (double)(r[sl] - r[0]); ++cnt; }
+      }
+      fprintf(stderr, " %s=%.0f", names[sl], cnt ? sum / cnt : 0.0);
+    }
+    fprintf(stderr, "\n");
+    return;
+  }
   std::vector<unsigned long long> h((size_t)kTraceRing * kTraceRingCtas * TRACE_SLOTS);
   TPP_CUDA_CHECK(cudaMemcpy(h.data(), g_trace_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   struct Row { unsigned long long start, wait_min, wait_max, end; int slot; };
