@@ -204,6 +204,12 @@ TPP_XSMM_EXPORT int libxsmm_cpuid_dot_pack_factor(int datatype);
  * stream of the library. */
 TPP_XSMM_EXPORT void xsmm_cuda_set_stream(void *stream);
 TPP_XSMM_EXPORT void *xsmm_cuda_get_stream(void);
+/* Create / destroy a non-blocking CUDA stream without linking the CUDA runtime (JIT'd callers have only this
+ * library). A thread that software-pipelines independent steps (upload of step i+1 under the kernels of step i under
+ * the download of step i-1) creates one stream per in-flight step and switches with xsmm_cuda_set_stream; every
+ * stream has its own kernel scratch, so work on different streams may overlap. destroy waits for the stream. */
+TPP_XSMM_EXPORT void *xsmm_cuda_stream_create(void);
+TPP_XSMM_EXPORT void xsmm_cuda_stream_destroy(void *stream);
 
 /* Block until every invoke issued so far (all threads) has completed. */
 TPP_XSMM_EXPORT void xsmm_cuda_sync(void);
@@ -221,6 +227,19 @@ TPP_XSMM_EXPORT int64_t xsmm_cuda_unregister_host(void *host);
 TPP_XSMM_EXPORT int64_t xsmm_cuda_update_device(void *host, int64_t bytes);
 TPP_XSMM_EXPORT int64_t xsmm_cuda_update_host(void *host, int64_t bytes);
 /* Device address that mirrors a registered host address (NULL if none). */
+/* Asynchronous forms for software-pipelined callers (independent steps, one buffer set per in-flight step).
+ * upload_async copies host->mirror on a dedicated upload stream: it overlaps kernels already queued, and every invoke
+ * (or graph launch) issued after the call waits for it. download_async copies mirror->host on a dedicated download
+ * stream once the invokes issued before the call are done, and overlaps whatever is issued after it; wait_host blocks
+ * until the latest download_async of that host address has landed (returns -1 if the calling thread has none on
+ * record). The caller must not upload into a mirror that queued invokes still read, nor let invokes overwrite a
+ * mirror whose download has not been waited for - i.e. consume step s before reusing its buffers for step s+depth.
+ * Inside xsmm_cuda_graph_begin/end the copies become parallel branches of the captured graph (a graph that holds
+ * several steps overlaps their copies with each other's kernels); such downloads are complete when the graph
+ * launch is (xsmm_cuda_stream_sync). All return 0 on success, -1 if the range is not registered. */
+TPP_XSMM_EXPORT int64_t xsmm_cuda_upload_async(void *host, int64_t bytes);
+TPP_XSMM_EXPORT int64_t xsmm_cuda_download_async(void *host, int64_t bytes);
+TPP_XSMM_EXPORT int64_t xsmm_cuda_wait_host(void *host);
 TPP_XSMM_EXPORT void *xsmm_cuda_device_ptr(void *host);
 
 /* CUDA-graph capture of a sequence of invokes (the body of a perf.bench loop):

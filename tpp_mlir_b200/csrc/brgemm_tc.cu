@@ -1170,6 +1170,27 @@ static void choose_tile(const KernelDesc &d, int64_t total_iters, int *bn_out, i
 }
 
 thread_local char t_last_name[64] = "brgemm_tc_bf16";
+
+// Device scratch of the split-K exchange and the chain kernel's grid counters. One instance per (host thread, stream):
+// launches of one thread on one stream are serialised and may share it; a thread that pipelines work over several
+// streams (xsmm_cuda_stream_create + xsmm_cuda_set_stream) gets a private copy per stream, so kernels that overlap in
+// time never share a workspace. Graphs bake these pointers in: replay a graph on the stream it was captured for.
+struct StreamScratch {
+  cudaStream_t stream = nullptr;
+  float *ws = nullptr;
+  size_t ws_bytes = 0;
+  unsigned int *flags = nullptr;
+  float *chain_ws = nullptr;
+  unsigned int *chain_counters = nullptr;
+};
+StreamScratch &scratch_for(cudaStream_t stream) {
+  thread_local std::vector<StreamScratch *> all;
+  for (StreamScratch *s : all)
+    if (s->stream == stream) return *s;
+  all.push_back(new StreamScratch());
+  all.back()->stream = stream;
+  return *all.back();
+}
 const char *brgemm_tc_last_name() { return t_last_name; }
 
 void brgemm_tc_configure(KernelDesc &d) {
@@ -1263,9 +1284,10 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   p.ws = nullptr;
   p.flags = nullptr;
   if (split > 1 && (!xchg_dsmem || block_n != 64)) {
-    // per-thread workspace: kernels of one thread run on one stream, so launches are serialised and may share it
-    thread_local float *ws = nullptr;
-    thread_local size_t ws_bytes = 0;
+    // per-(thread, stream) workspace: launches on one stream are serialised and may share it
+    StreamScratch &sc = scratch_for(stream);
+    float *&ws = sc.ws;
+    size_t &ws_bytes = sc.ws_bytes;
     const size_t need = (size_t)n_ctas * BLOCK_M * block_n * sizeof(float);
     if (need > ws_bytes) {
       cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -1279,7 +1301,7 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
     p.ws = ws;
     // arrival counters of the flag-synchronised exchange: zeroed once, only ever incremented; one region per S so
     // that every counter is a multiple of S between launches
-    thread_local unsigned int *flags = nullptr;
+    unsigned int *&flags = sc.flags;
     constexpr int kFlagTiles = 4096;
     if (mc == 2) {
       if (n_ctas / split > kFlagTiles) return false;
@@ -1388,9 +1410,10 @@ bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, i
   const KernelDesc &d0 = *descs[0];
   dim3 grid((unsigned)((d0.n + 63) / 64), (unsigned)((d0.m + BLOCK_M - 1) / BLOCK_M), 4);
   const int n_ctas = (int)(grid.x * grid.y * grid.z);
-  // per-thread exchange workspace + grid counters (same life cycle as the stand-alone kernel's workspace)
-  thread_local float *ws = nullptr;
-  thread_local unsigned int *counters = nullptr;
+  // per-(thread, stream) exchange workspace + grid counters (same life cycle as the stand-alone kernel's workspace)
+  StreamScratch &sc = scratch_for(stream);
+  float *&ws = sc.chain_ws;
+  unsigned int *&counters = sc.chain_counters;
   if (!ws) {
     TPP_CUDA_CHECK(cudaMalloc(&ws, (size_t)148 * BLOCK_M * 64 * sizeof(float)));
     TPP_CUDA_CHECK(cudaMalloc(&counters, sizeof(unsigned int) * 256));

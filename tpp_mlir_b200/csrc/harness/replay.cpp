@@ -103,4 +103,87 @@ int64_t tpp_replay_mlp_e2e(int64_t dtype, int64_t num_layers, const int64_t *han
   return 0;
 }
 
+// Throughput forms of the same end-to-end step: `depth` independent steps in flight, one set of host buffers +
+// mirrors per slot; step s reuses slot s % depth only after that slot's previous output has reached host memory
+// (the point where a caller would consume the result and write the next input). Every step still uploads its input
+// and downloads its output inside the loop.
+//   mode 0  one compute stream + the library's copy streams: upload_async(in) -> replay of the captured layer
+//           sequence -> download_async(out) per step, wait_host(out) before the slot is reused. Kernels of
+//           different steps never overlap (one stream); copies run under them.
+//   mode 1  the loop body unrolled `depth` times inside ONE captured graph (the copies become parallel branches):
+//           one graph launch + one stream wait per `depth` steps.
+//   mode 2  one stream (xsmm_cuda_stream_create) and one captured step graph (copies included) per slot.
+// graphs: depth + 1 entries, streams: depth entries, 0 = not created yet; they persist across calls (one mode per
+// pair of arrays). steps is rounded down to a multiple of depth in mode 1. Returns the number of steps run or -1.
+__attribute__((visibility("default")))
+int64_t tpp_replay_mlp_e2e_pipelined(int64_t dtype, int64_t num_layers, const int64_t *handles,
+                                     const int64_t *layer_sizes, int64_t batch, int64_t bn, int64_t bk, int64_t bc,
+                                     const TppMlpSet *slots, int64_t depth, int64_t steps, int64_t has_bias,
+                                     int64_t elem_size, int64_t mode, int64_t *graphs, void **streams) {
+  const int64_t in_bytes = batch * layer_sizes[0] * elem_size;
+  const int64_t out_bytes = batch * layer_sizes[num_layers] * elem_size;
+  auto layers = [&](int64_t d) {
+    tpp_replay_mlp(dtype, num_layers, handles, layer_sizes, batch, bn, bk, bc, slots + d, 1, 0, 1, has_bias);
+  };
+  if (mode == 0) {
+    for (int64_t d = 0; d < depth; ++d) {
+      if (graphs[d]) continue;
+      if (xsmm_cuda_graph_begin() != 0) return -1;
+      layers(d);
+      if (!(graphs[d] = xsmm_cuda_graph_end())) return -1;
+    }
+    for (int64_t s = 0; s < steps; ++s) {
+      const int64_t d = s % depth;
+      void *out = slots[d].acts[num_layers];
+      if (s >= depth) xsmm_cuda_wait_host(out);   // output of step s - depth consumed; the slot is free again
+      xsmm_cuda_upload_async(slots[d].acts[0], in_bytes);
+      xsmm_cuda_graph_launch(graphs[d]);
+      xsmm_cuda_download_async(out, out_bytes);
+    }
+    xsmm_cuda_stream_sync();   // drain: every step's output has reached the host
+    return steps;
+  }
+  if (mode == 1) {
+    if (!graphs[depth]) {
+      if (xsmm_cuda_graph_begin() != 0) return -1;
+      for (int64_t d = 0; d < depth; ++d) {
+        xsmm_cuda_upload_async(slots[d].acts[0], in_bytes);
+        layers(d);
+        xsmm_cuda_download_async(slots[d].acts[num_layers], out_bytes);
+      }
+      if (!(graphs[depth] = xsmm_cuda_graph_end())) return -1;
+    }
+    const int64_t groups = steps / depth;
+    for (int64_t g = 0; g < groups; ++g) {
+      xsmm_cuda_graph_launch(graphs[depth]);
+      xsmm_cuda_stream_sync();   // the outputs of these `depth` steps are in host memory
+    }
+    return groups * depth;
+  }
+  void *caller_stream = xsmm_cuda_get_stream();
+  for (int64_t d = 0; d < depth; ++d) {
+    if (!streams[d]) streams[d] = xsmm_cuda_stream_create();
+    if (!graphs[d]) {
+      xsmm_cuda_set_stream(streams[d]);
+      if (xsmm_cuda_graph_begin() != 0) return -1;
+      xsmm_cuda_update_device(slots[d].acts[0], in_bytes);
+      layers(d);
+      xsmm_cuda_update_host(slots[d].acts[num_layers], out_bytes);
+      if (!(graphs[d] = xsmm_cuda_graph_end())) return -1;
+    }
+  }
+  for (int64_t s = 0; s < steps; ++s) {
+    const int64_t d = s % depth;
+    xsmm_cuda_set_stream(streams[d]);
+    if (s >= depth) xsmm_cuda_stream_sync();
+    xsmm_cuda_graph_launch(graphs[d]);
+  }
+  for (int64_t d = 0; d < depth; ++d) {
+    xsmm_cuda_set_stream(streams[d]);
+    xsmm_cuda_stream_sync();
+  }
+  xsmm_cuda_set_stream(caller_stream);
+  return steps;
+}
+
 } // extern "C"

@@ -111,6 +111,14 @@ struct ThreadCtx {
       if (r.lo && lo < r.hi && r.lo < lo + bytes) return true;
     return false;
   }
+  // asynchronous residency (xsmm_cuda_upload_async / download_async): copies run on two side streams so that
+  // they overlap kernels; events order them against the compute stream
+  cudaStream_t up_stream = nullptr, down_stream = nullptr;
+  cudaEvent_t ev_up = nullptr, ev_compute = nullptr, ev_fork = nullptr, ev_join = nullptr;
+  bool up_pending = false;       // the compute stream must wait for ev_up before its next launch
+  bool up_in_capture = false, down_in_capture = false;   // side streams forked into the running capture
+  struct Download { void *host = nullptr; cudaEvent_t ev = nullptr; } downloads[16];
+  int download_pos = 0;
 };
 
 struct GraphHandle {
@@ -418,6 +426,10 @@ void issue_gemm(const KernelDesc *d, const GemmArgs &g, cudaStream_t stream) {
 // ("whole-MLP fusion ... or CUDA-graph capture of the invoke sequence"); everything else is
 // launched exactly as a direct invoke would.
 void flush_pending() {
+  if (t_ctx.up_pending) {   // kernels issued from here on see every upload_async issued before them
+    TPP_CUDA_CHECK(cudaStreamWaitEvent(t_ctx.stream, t_ctx.ev_up, 0));
+    t_ctx.up_pending = false;
+  }
   if (t_ctx.pending.empty()) return;
   std::vector<PendingGemm> list;
   list.swap(t_ctx.pending);
@@ -793,16 +805,36 @@ extern "C" void xsmm_cuda_set_stream(void *stream) {
     t_ctx.saved_stream = static_cast<cudaStream_t>(stream);
     return;
   }
+  if (t_ctx.stream != static_cast<cudaStream_t>(stream))
+    for (auto &r : t_ctx.recent_out) r = {};   // dependency tracking is per stream; cross-stream order is the caller's
   t_ctx.stream = static_cast<cudaStream_t>(stream);
 }
 extern "C" void *xsmm_cuda_get_stream(void) { return t_ctx.stream; }
+
+extern "C" void *xsmm_cuda_stream_create(void) {
+  ensure_cuda();
+  cudaStream_t s = nullptr;
+  TPP_CUDA_CHECK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  return s;
+}
+extern "C" void xsmm_cuda_stream_destroy(void *stream) {
+  if (!stream) return;
+  if (t_ctx.stream == static_cast<cudaStream_t>(stream)) t_ctx.stream = nullptr;
+  TPP_CUDA_CHECK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  TPP_CUDA_CHECK(cudaStreamDestroy(static_cast<cudaStream_t>(stream)));
+}
 
 extern "C" void xsmm_cuda_sync(void) {
   if (g_cuda_ready.load()) TPP_CUDA_CHECK(cudaDeviceSynchronize());
 }
 
 extern "C" void xsmm_cuda_stream_sync(void) {
-  if (g_cuda_ready.load()) TPP_CUDA_CHECK(cudaStreamSynchronize(t_ctx.stream));
+  if (!g_cuda_ready.load()) return;
+  TPP_CUDA_CHECK(cudaStreamSynchronize(t_ctx.stream));
+  if (t_ctx.up_stream && !t_ctx.capturing) {   // everything this thread issued, asynchronous copies included
+    TPP_CUDA_CHECK(cudaStreamSynchronize(t_ctx.up_stream));
+    TPP_CUDA_CHECK(cudaStreamSynchronize(t_ctx.down_stream));
+  }
 }
 
 extern "C" int64_t xsmm_cuda_register_host(void *host, int64_t bytes, int64_t upload) {
@@ -859,6 +891,71 @@ extern "C" int64_t xsmm_cuda_update_host(void *host, int64_t bytes) {
   return 0;
 }
 
+namespace {
+void ensure_copy_streams() {
+  if (t_ctx.up_stream) return;
+  TPP_CUDA_CHECK(cudaStreamCreateWithFlags(&t_ctx.up_stream, cudaStreamNonBlocking));
+  TPP_CUDA_CHECK(cudaStreamCreateWithFlags(&t_ctx.down_stream, cudaStreamNonBlocking));
+  for (cudaEvent_t *e : {&t_ctx.ev_up, &t_ctx.ev_compute, &t_ctx.ev_fork, &t_ctx.ev_join})
+    TPP_CUDA_CHECK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  for (auto &d : t_ctx.downloads) TPP_CUDA_CHECK(cudaEventCreateWithFlags(&d.ev, cudaEventDisableTiming));
+}
+} // namespace
+
+// Upload on the thread's upload stream: ordered after earlier uploads only, so it overlaps kernels that are already
+// queued; every invoke issued AFTER this call waits for it. During graph capture the copy becomes a parallel branch
+// of the graph (root node, or behind the previous upload).
+extern "C" int64_t xsmm_cuda_upload_async(void *host, int64_t bytes) {
+  Mirror m;
+  if (!find_mirror(host, &m) || static_cast<char *>(host) + bytes > m.host + m.bytes) return -1;
+  flush_pending();
+  ensure_copy_streams();
+  if (t_ctx.capturing && !t_ctx.up_in_capture) {   // fork: pull the upload stream into the capture
+    TPP_CUDA_CHECK(cudaEventRecord(t_ctx.ev_fork, t_ctx.stream));
+    TPP_CUDA_CHECK(cudaStreamWaitEvent(t_ctx.up_stream, t_ctx.ev_fork, 0));
+    t_ctx.up_in_capture = true;
+  }
+  TPP_CUDA_CHECK(cudaMemcpyAsync(m.dev + (static_cast<char *>(host) - m.host), host, (size_t)bytes,
+                                 cudaMemcpyHostToDevice, t_ctx.up_stream));
+  TPP_CUDA_CHECK(cudaEventRecord(t_ctx.ev_up, t_ctx.up_stream));
+  t_ctx.up_pending = true;
+  return 0;
+}
+
+// Download on the thread's download stream: starts when the invokes issued BEFORE this call have finished and runs
+// under whatever is issued after it. Outside a capture, xsmm_cuda_wait_host(host) blocks until the bytes are in host
+// memory; a captured download is complete when the graph launch is (xsmm_cuda_stream_sync).
+extern "C" int64_t xsmm_cuda_download_async(void *host, int64_t bytes) {
+  Mirror m;
+  if (!find_mirror(host, &m) || static_cast<char *>(host) + bytes > m.host + m.bytes) return -1;
+  flush_pending();
+  ensure_copy_streams();
+  TPP_CUDA_CHECK(cudaEventRecord(t_ctx.ev_compute, t_ctx.stream));
+  TPP_CUDA_CHECK(cudaStreamWaitEvent(t_ctx.down_stream, t_ctx.ev_compute, 0));
+  if (t_ctx.capturing) t_ctx.down_in_capture = true;
+  TPP_CUDA_CHECK(cudaMemcpyAsync(host, m.dev + (static_cast<char *>(host) - m.host), (size_t)bytes,
+                                 cudaMemcpyDeviceToHost, t_ctx.down_stream));
+  if (!t_ctx.capturing) {
+    ThreadCtx::Download &d = t_ctx.downloads[t_ctx.download_pos++ & 15];
+    d.host = host;
+    TPP_CUDA_CHECK(cudaEventRecord(d.ev, t_ctx.down_stream));
+  }
+  return 0;
+}
+
+// Block until the most recent xsmm_cuda_download_async(host, ...) of this thread has delivered its bytes.
+// Returns -1 if the thread has no such download on record (only the last 16 are kept).
+extern "C" int64_t xsmm_cuda_wait_host(void *host) {
+  for (int i = 1; i <= 16; ++i) {
+    ThreadCtx::Download &d = t_ctx.downloads[(t_ctx.download_pos - i) & 15];
+    if (d.host == host && d.ev) {
+      TPP_CUDA_CHECK(cudaEventSynchronize(d.ev));
+      return 0;
+    }
+  }
+  return -1;
+}
+
 extern "C" void *xsmm_cuda_device_ptr(void *host) {
   Mirror m;
   if (!find_mirror(host, &m)) return nullptr;
@@ -877,12 +974,25 @@ extern "C" int64_t xsmm_cuda_graph_begin(void) {
   TPP_CUDA_CHECK(cudaStreamBeginCapture(t_ctx.stream, cudaStreamCaptureModeRelaxed));
   t_ctx.capturing = true;
   t_ctx.captured_launches = 0;
+  t_ctx.up_in_capture = t_ctx.down_in_capture = false;
+  t_ctx.up_pending = false;
   return 0;
 }
 
 extern "C" int64_t xsmm_cuda_graph_end(void) {
   if (!t_ctx.capturing) return 0;
   flush_pending();
+  // join the copy branches back into the capture stream
+  if (t_ctx.up_in_capture) {
+    TPP_CUDA_CHECK(cudaEventRecord(t_ctx.ev_join, t_ctx.up_stream));
+    TPP_CUDA_CHECK(cudaStreamWaitEvent(t_ctx.stream, t_ctx.ev_join, 0));
+  }
+  if (t_ctx.down_in_capture) {
+    TPP_CUDA_CHECK(cudaEventRecord(t_ctx.ev_join, t_ctx.down_stream));
+    TPP_CUDA_CHECK(cudaStreamWaitEvent(t_ctx.stream, t_ctx.ev_join, 0));
+  }
+  t_ctx.up_in_capture = t_ctx.down_in_capture = false;
+  t_ctx.up_pending = false;
   cudaGraph_t graph = nullptr;
   cudaError_t e = cudaStreamEndCapture(t_ctx.stream, &graph);
   t_ctx.capturing = false;
@@ -907,6 +1017,7 @@ extern "C" int64_t xsmm_cuda_graph_end(void) {
 extern "C" void xsmm_cuda_graph_launch(int64_t graph) {
   GraphHandle *gh = reinterpret_cast<GraphHandle *>(graph);
   if (!gh || gh->magic != 0x47525048u) fail("xsmm_cuda_graph_launch: not a graph handle");
+  flush_pending();   // orders the launch after this thread's pending upload_async
   TPP_CUDA_CHECK(cudaGraphLaunch(gh->exec, t_ctx.stream));
   g_launches.fetch_add(gh->launches, std::memory_order_relaxed);
 }

@@ -198,6 +198,8 @@ def replay_lib():
         lib.tpp_replay_mlp.restype = None
         lib.tpp_replay_mlp_e2e.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, i64, i64, i64, p]
         lib.tpp_replay_mlp_e2e.restype = i64
+        lib.tpp_replay_mlp_e2e_pipelined.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, i64, i64, i64, i64, p, p]
+        lib.tpp_replay_mlp_e2e_pipelined.restype = i64
         lib.tpp_replay_mlp_graph.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, p, i64, i64, i64, i64]
         lib.tpp_replay_mlp_graph.restype = i64
         _replay_lib = lib
@@ -262,3 +264,25 @@ class NativeMlpLoop:
                                              1 if graph else 0, _ct.byref(self._e2e_graph))
         if rc != 0:
             raise RuntimeError("e2e replay failed (graph capture)")
+
+    PIPE_MODES = {"async": 0, "grouped": 1, "streams": 2}
+
+    def run_e2e_pipelined(self, steps: int, elem_size: int = 2, mode: str = "async") -> int:
+        """Throughput form of run_e2e: every operand set is a pipeline slot, so uploads, kernels and downloads
+        of neighbouring steps overlap; every step still moves its input and its output across PCIe.
+        mode "async": xsmm_cuda_upload_async / graph replay / download_async per step, wait_host before a slot is
+        reused; "grouped": one captured graph holds num_sets steps (copies are parallel branches);
+        "streams": one stream + one captured step graph per slot. Returns the number of steps run."""
+        cfg = self.cfg
+        bn, bk, bc = cfg.tiles
+        key = "_pipe_" + mode
+        if not hasattr(self, key):
+            setattr(self, key, ((_ct.c_int64 * (self.num_sets + 1))(), (_ct.c_void_p * self.num_sets)()))
+        graphs, streams = getattr(self, key)
+        rc = replay_lib().tpp_replay_mlp_e2e_pipelined(cfg.dtype, cfg.num_layers, self._handles, self._sizes, cfg.batch,
+                                                       bn, bk, bc, self._sets, self.num_sets, steps,
+                                                       1 if cfg.bias else 0, elem_size, self.PIPE_MODES[mode], graphs,
+                                                       streams)
+        if rc < 0:
+            raise RuntimeError("pipelined e2e replay failed (graph capture)")
+        return rc

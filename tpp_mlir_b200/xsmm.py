@@ -56,12 +56,17 @@ EXPORTS = {
     "libxsmm_cpuid_dot_pack_factor": (c_int, [c_int]),
     "xsmm_cuda_set_stream": (None, [c_void_p]),
     "xsmm_cuda_get_stream": (c_void_p, []),
+    "xsmm_cuda_stream_create": (c_void_p, []),
+    "xsmm_cuda_stream_destroy": (None, [c_void_p]),
     "xsmm_cuda_sync": (None, []),
     "xsmm_cuda_stream_sync": (None, []),
     "xsmm_cuda_register_host": (c_int64, [c_void_p, c_int64, c_int64]),
     "xsmm_cuda_unregister_host": (c_int64, [c_void_p]),
     "xsmm_cuda_update_device": (c_int64, [c_void_p, c_int64]),
     "xsmm_cuda_update_host": (c_int64, [c_void_p, c_int64]),
+    "xsmm_cuda_upload_async": (c_int64, [c_void_p, c_int64]),
+    "xsmm_cuda_download_async": (c_int64, [c_void_p, c_int64]),
+    "xsmm_cuda_wait_host": (c_int64, [c_void_p]),
     "xsmm_cuda_device_ptr": (c_void_p, [c_void_p]),
     "xsmm_cuda_graph_begin": (c_int64, []),
     "xsmm_cuda_graph_end": (c_int64, []),
@@ -197,6 +202,23 @@ def sync() -> None:
 
 def set_stream(stream_ptr: int | None) -> None:
     LIB.xsmm_cuda_set_stream(stream_ptr)
+
+
+def get_stream() -> int | None:
+    return LIB.xsmm_cuda_get_stream()
+
+
+def stream_create() -> int:
+    """A new non-blocking CUDA stream (as an integer handle) for set_stream; see xsmm_cuda_stream_create."""
+    return LIB.xsmm_cuda_stream_create()
+
+
+def stream_destroy(stream_ptr: int) -> None:
+    LIB.xsmm_cuda_stream_destroy(stream_ptr)
+
+
+def stream_sync() -> None:
+    LIB.xsmm_cuda_stream_sync()
 
 
 class graph_capture:
