@@ -538,7 +538,10 @@ def test_concurrent_invokes_from_many_threads(orc):
 @pytest.mark.parametrize("layers,view", [(3, "flat"), (2, "flat"), (4, "flat"), (3, "k64xb16")])
 def test_captured_mlp_chain_is_fused_and_matches(layers, view):
     """Graph capture of consecutive layers (C of one = A of the next) launches ONE persistent chain kernel
-    (SURVEY 8f-2); results are bit-identical to the per-layer kernels and within tolerance of the oracle."""
+    (SURVEY 8f-2). Every layer's output is within tolerance of the oracle AND within one bf16 rounding step of the
+    per-layer kernels (the chain accumulates the full reduction in one TMEM tile, the stand-alone kernel adds four
+    split-K partials: the f32 sums may differ in the last bit before the single bf16 rounding); replays are
+    bit-identical to each other."""
     import torch
 
     from tpp_mlir_b200 import xsmm
@@ -577,7 +580,10 @@ def test_captured_mlp_chain_is_fused_and_matches(layers, view):
     assert xsmm.launch_count() - n0 == 1, "the captured chain must be ONE kernel launch"
     assert xsmm.last_kernel().startswith(f"mlp_chain_bf16_{layers}layers"), xsmm.last_kernel()
     for got, want in zip(acts[1:], direct):
-        assert torch.equal(got, want)
+        gi, wi = got.cpu().numpy().view(np.uint16).astype(np.int32), want.cpu().numpy().view(np.uint16).astype(np.int32)
+        assert np.abs(gi - wi).max() <= 1, "chain vs per-layer kernels: more than one bf16 ulp apart"
+        assert (gi != wi).mean() < 1e-3
+    first = [a.clone() for a in acts[1:]]
     ref = x
     for W, b in zip(Ws, bs):
         y = np.zeros((256, 1024), np.uint16)
@@ -585,11 +591,30 @@ def test_captured_mlp_chain_is_fused_and_matches(layers, view):
         ref = y
     assert_close(BF16, acts[-1].cpu().numpy().view(np.uint16), ref)
     # replay again: the grid-barrier counters are monotonic across launches
+    for a in acts[1:]:
+        a.fill_(0x7FC0)  # poison (bf16 NaN): a layer that ran ahead of its producers would propagate it
     g.launch()
     g.launch()
     xsmm.sync()
-    assert torch.equal(acts[-1], direct[-1])
+    for a, f in zip(acts[1:], first):
+        assert torch.equal(a, f)
     g.destroy()
+
+
+def test_split_k_chain_kernel_still_matches():
+    """The first chain design (4-CTA split-K clusters + grid barrier, TPP_XSMM_CHAIN=s) stays available and
+    bit-identical to the per-layer kernels; the option is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TPP_XSMM_CHAIN="s")
+    out = subprocess.run([sys.executable, os.path.join(root, "scripts", "chain_check.py"), "3", "2"], env=env, cwd=root,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "splitk4" in out.stdout and "differing_elems=0" in out.stdout, out.stdout
+    assert "replay determinism: 0 unstable" in out.stdout, out.stdout
 
 
 def test_captured_non_chain_sequences_are_not_fused():

@@ -43,6 +43,9 @@ struct GemmArgs {
   // true when B (and D) were not written by any of the last few kernels this thread launched: the
   // kernel may then fetch B before the programmatic-dependent-launch wait (weights of an MLP layer)
   bool b_independent = false;
+  // same for A: the fused chain kernel may then fetch its first layer's activations (and run that layer's MMAs,
+  // which only touch shared / tensor memory) before the wait; stores always come after it
+  bool a_independent = false;
 };
 
 // generic FFMA BRGEMM (any dtype/ld/stride, VNNI-B), fused epilogue

@@ -100,10 +100,10 @@ struct ThreadCtx {
   cudaStream_t saved_stream = nullptr;
   int64_t captured_launches = 0;
   // device ranges written by the last few kernels of this thread (dependency tracking for PDL)
-  struct Range { const char *lo = nullptr, *hi = nullptr; } recent_out[4];
+  struct Range { const char *lo = nullptr, *hi = nullptr; } recent_out[8];
   int recent_pos = 0;
   void note_output(const char *lo, size_t bytes) {
-    recent_out[recent_pos & 3] = {lo, lo + bytes};
+    recent_out[recent_pos & 7] = {lo, lo + bytes};
     ++recent_pos;
   }
   bool recently_written(const char *lo, size_t bytes) const {
@@ -513,6 +513,7 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
   g.batch = batch;
   {
     const size_t es = esize(dtype);
+    g.a_independent = !t_ctx.recently_written(ops[0].dev, (size_t)ops[0].width * es);
     g.b_independent = !t_ctx.recently_written(ops[1].dev, (size_t)ops[1].width * es) &&
                       (!has_d || !t_ctx.recently_written(ops[3].dev, (size_t)((ops[3].rows - 1) * ops[3].ld + ops[3].width) * es));
     t_ctx.note_output(ops[2].dev, (size_t)((d->m - 1) * d->ldc + d->n) * es);
