@@ -601,6 +601,152 @@ def test_captured_mlp_chain_is_fused_and_matches(layers, view):
     g.destroy()
 
 
+def _mlp_chain_setup(n_chains, layers, seed):
+    import torch
+
+    gen = oracle.TensorInit("normal", BF16, seed)
+
+    def dev_t(a):
+        return torch.from_numpy(a.view(np.int16)).cuda()
+
+    chains = []
+    for _ in range(n_chains):
+        Ws = [dev_t(gen.fill(1024, 1024)) for _ in range(layers)]
+        bs = [dev_t(gen.fill(1024)) for _ in range(layers)]
+        acts = [dev_t(gen.fill(256, 1024))] + [torch.zeros(256, 1024, dtype=torch.int16, device="cuda") for _ in range(layers)]
+        chains.append((acts, Ws, bs))
+    return chains
+
+
+def _ulp_diff(a, b):
+    return np.abs(a.cpu().numpy().view(np.uint16).astype(np.int32) - b.cpu().numpy().view(np.uint16).astype(np.int32)).max()
+
+
+def test_captured_independent_chains_share_one_interleaved_launch():
+    """Several independent forward passes captured in one graph (the benchmark's rotating operand sets) become ONE
+    launch of the chain kernel with the chains interleaved three at a time; every layer of every chain stays within one
+    bf16 rounding step of the per-layer kernels, replays are bit-identical (poisoned intermediates)."""
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    layers, n_chains = 3, 7
+    chains = _mlp_chain_setup(n_chains, layers, 29)
+    h = xsmm.fused_brgemm_dispatch(BF16, 256, 1024, 1024, 1024, 1024, 1024, 0, 0, 4 | 64 | 128, 0, 5, 4, 1)
+
+    def forward(c):
+        acts, Ws, bs = c
+        for l in range(layers):
+            xsmm.fused_brgemm_invoke(BF16, h, acts[l], 0, Ws[l], 0, acts[l + 1], 0, bs[l], 0, 1)
+
+    for c in chains:
+        forward(c)
+    xsmm.sync()
+    direct = [[a.clone() for a in c[0][1:]] for c in chains]
+    with xsmm.graph_capture() as g:
+        for c in chains:
+            forward(c)
+    assert xsmm.last_kernel().startswith(f"mlp_chain_bf16_{n_chains}x{layers}layers"), xsmm.last_kernel()
+    first = None
+    for rep in range(3):
+        for c in chains:
+            for a in c[0][1:]:
+                a.fill_(0x7FC0)
+        n0 = xsmm.launch_count()
+        g.launch()
+        xsmm.sync()
+        assert xsmm.launch_count() - n0 == 1, "independent chains must share one launch"
+        got = [[a.clone() for a in c[0][1:]] for c in chains]
+        if first is None:
+            first = got
+            for gc, dc in zip(got, direct):
+                for a, d in zip(gc, dc):
+                    assert _ulp_diff(a, d) <= 1
+        else:
+            for gc, fc in zip(got, first):
+                for a, f in zip(gc, fc):
+                    assert torch.equal(a, f)
+    g.destroy()
+
+
+def test_captured_dependent_or_aliased_chains_are_not_interleaved():
+    """A chain that reads another chain's output, or writes buffers another chain uses, must not run interleaved with
+    it: such chains get their own launches (stream order), and the results match running them one after the other."""
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    layers = 2
+    (a1, W1, b1), (a2, W2, b2) = _mlp_chain_setup(2, layers, 31)
+    h = xsmm.fused_brgemm_dispatch(BF16, 256, 1024, 1024, 1024, 1024, 1024, 0, 0, 4 | 64 | 128, 0, 5, 4, 1)
+    a2[0] = a1[-1]   # chain 2 consumes chain 1's output ...
+    extra = torch.zeros(256, 1024, dtype=torch.int16, device="cuda")
+
+    def forward():
+        for l in range(layers):
+            xsmm.fused_brgemm_invoke(BF16, h, a1[l], 0, W1[l], 0, a1[l + 1], 0, b1[l], 0, 1)
+        # ... through an unrelated op in between, so that the two chains stay two chains
+        hz = xsmm.unary_dispatch(2, BF16, 256, 1024, 1024, 1024, 0)
+        xsmm.unary_invoke(BF16, hz, extra, 0, extra, 0)
+        for l in range(layers):
+            xsmm.fused_brgemm_invoke(BF16, h, a2[l], 0, W2[l], 0, a2[l + 1], 0, b2[l], 0, 1)
+        # and a third pass over chain 1's buffers again (aliases chain 1 completely)
+        for l in range(layers):
+            xsmm.fused_brgemm_invoke(BF16, h, a1[l], 0, W1[l], 0, a1[l + 1], 0, b1[l], 0, 1)
+
+    forward()
+    xsmm.sync()
+    want = [t.clone() for t in a1[1:] + a2[1:]]
+    with xsmm.graph_capture() as g:
+        forward()
+    for t in a1[1:] + a2[1:]:
+        t.fill_(0x7FC0)
+    n0 = xsmm.launch_count()
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == 4, "three chain launches + the zero kernel"
+    for t, w in zip(a1[1:] + a2[1:], want):
+        assert _ulp_diff(t, w) <= 1
+    g.destroy()
+
+
+def test_chain_with_weights_written_just_before():
+    """Weights / bias produced by a kernel issued right before the chain (here: identity copies through the ABI) must
+    not be fetched before the programmatic-launch wait; the chain still runs fused and matches."""
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    layers = 3
+    ((acts, Ws, bs),) = _mlp_chain_setup(1, layers, 37)
+    h = xsmm.fused_brgemm_dispatch(BF16, 256, 1024, 1024, 1024, 1024, 1024, 0, 0, 4 | 64 | 128, 0, 5, 4, 1)
+    hc = xsmm.unary_dispatch(1, BF16, 1024, 1024, 1024, 1024, 0)
+    W_live = [torch.zeros_like(w) for w in Ws]
+
+    def forward():
+        for l in range(layers):
+            xsmm.unary_invoke(BF16, hc, Ws[l], 0, W_live[l], 0)     # "training step": fresh weights every forward
+        for l in range(layers):
+            xsmm.fused_brgemm_invoke(BF16, h, acts[l], 0, W_live[l], 0, acts[l + 1], 0, bs[l], 0, 1)
+
+    forward()
+    xsmm.sync()
+    want = [a.clone() for a in acts[1:]]
+    with xsmm.graph_capture() as g:
+        forward()
+    assert xsmm.last_kernel().startswith("mlp_chain_bf16_3layers"), xsmm.last_kernel()
+    for rep in range(3):
+        for w in W_live:
+            w.zero_()
+        for a in acts[1:]:
+            a.fill_(0x7FC0)
+        g.launch()
+    xsmm.sync()
+    for a, w in zip(acts[1:], want):
+        assert _ulp_diff(a, w) <= 1
+    g.destroy()
+
+
 def test_split_k_chain_kernel_still_matches():
     """The first chain design (4-CTA split-K clusters + grid barrier, TPP_XSMM_CHAIN=s) stays available and
     bit-identical to the per-layer kernels; the option is read once per process, hence the subprocess."""

@@ -832,13 +832,6 @@ __device__ __forceinline__ void chain_stamp(const ChainParams &cp, int slot) {
   }
 }
 
-__device__ __forceinline__ void chain_stamp_raw(unsigned long long *trace, int slot) {
-  if (trace) {
-    const unsigned cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
-    trace[(size_t)cta * TRACE_SLOTS + slot] = clock64();
-  }
-}
-
 __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_kernel(const __grid_constant__ ChainParams cp) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -996,9 +989,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_kernel(const __grid_
 //   * TMEM lane = feature, so the bias is one scalar per thread and all four epilogue warps have work;
 //   * operands move in few, large TMA boxes: the activation slice through a 4-D map (k-in-block, row, k-block,
 //     batch) whose box covers 4 k-blocks x 32 rows = 16 KiB, the weights in 32 KiB boxes (the measured cost of one
-//     TMA issue + barrier hand-off is ~150-600 clk, far more than the 64-128 clk of MMA work per k-block);
-//   * the 128 KiB weight slice of layer l+1 streams into the weight slots as layer l's MMAs retire them
-//     (tcgen05.commit per group), under the epilogue and barrier latency of layer l, L2-prefetched at kernel start.
+//     TMA issue + barrier hand-off is ~150-600 clk, far more than the 100 clk of MMA work per k-block);
+//   * the kernel runs a list of PASSES (one pass = one layer of one chain). The operands of pass p+1 stream into
+//     the 16 weight / activation slots as pass p's MMAs retire them (tcgen05.commit per group of 4 slots), i.e.
+//     under the MMAs, the epilogue and the barrier latency of pass p;
+//   * several INDEPENDENT chains captured in one graph (the benchmark's rotating operand sets, or any batch of
+//     forward passes on different buffers) become ONE launch whose pass list interleaves two chains (A.L0, B.L0,
+//     A.L1, B.L1, ...): while chain A's layer output travels store -> fence -> counter -> poll (~2500 clk, most of
+//     a layer when one chain runs alone), the tensor pipe works on chain B; there is no kernel boundary (1.5-1.8 us
+//     of programmatic-launch hand-off) between forward passes, and the next chain's first-layer operands load
+//     under the previous chain's last layer.
+// Per pass and CTA the tensor pipe reads 192 KiB of operands from shared memory and TMA writes 192 KiB into it:
+// at 128 B/clk that is ~3000 clk, the bound of this tiling (measured: tcgen05.mma time = operand bytes / 128 B/clk,
+// scripts/probes/umma_rate.cu); L2 -> SM delivery of the same 192 KiB runs at ~53 B/clk per SM with all SMs pulling.
 constexpr int FT_M = 64;                          // features per CTA  (UMMA M)
 constexpr int FT_N = 32;                          // batch rows per CTA (UMMA N)
 constexpr int FT_KB = 16;                         // k-block slots: (batch x k) reduction of at most 16 x 64
@@ -1007,44 +1010,41 @@ constexpr int FT_NG = FT_KB / FT_GROUP;
 constexpr int FT_X_BYTES = FT_N * BLOCK_K * 2;    // 4 KiB
 constexpr int FT_W_BYTES = BLOCK_K * FT_M * 2;    // 8 KiB
 constexpr int FT_CTR_STRIDE = 32;                 // one 128-byte line per batch-tile counter
+constexpr int FT_CTR_SLOT = 160 * FT_CTR_STRIDE;  // counters of chain slot s start at s * FT_CTR_SLOT
+constexpr int FT_MAX_WAYS = 4;                    // chains interleaved in one launch (= counter slots)
+constexpr int FT_MAX_PASSES = 64;
 
-struct ChainFtParams {
-  CUtensorMap tmX[CHAIN_MAX_LAYERS], tmW[CHAIN_MAX_LAYERS];
-  TcParams layer[CHAIN_MAX_LAYERS];   // total_iters = k-block slots of the layer, k_iters = k-blocks per batch element
-  unsigned int *counters;             // [batch tile][FT_CTR_STRIDE]: monotonic, a multiple of gridDim.x between launches
-  int num_layers;
-  int weights_early;
-  int x0_early;                       // layer 0's activations are not produced by in-flight kernels
-  int no_proxy_fence;
+struct alignas(64) FtPass {
+  CUtensorMap tmX, tmW;
+  void *C;
+  const void *D;
+  int64_t ldc;
+  int32_t k_iters;          // k-blocks per batch element
+  int32_t groups;           // (batch x k-blocks) / FT_GROUP
+  uint8_t has_bias, relu;
+  uint8_t arrive;           // a later pass reads this pass's output: arrive on the slot's counter after storing
+  uint8_t x_dep;            // X is the output of an earlier pass of the same chain slot: wait for wait_arrivals
+  uint8_t slot;             // chain slot (< FT_MAX_WAYS) = which counter set this pass's chain uses
+  uint8_t pad[3];
+  uint32_t wait_arrivals;   // arrivals per CTA on the slot's counter (this launch) that must be visible before X loads
+};
+
+struct FtParams {
+  FtPass pass[FT_MAX_PASSES];
+  unsigned int *counters;   // [slot][batch tile][FT_CTR_STRIDE]: monotonic, multiples of gridDim.x between launches
+  int num_passes;
+  int weights_early;        // no weight / bias is produced by in-flight kernels: fetch pass 0's before the PDL wait
+  int x0_early;             // same for pass 0's activations
+  int proxy_fence;
   unsigned long long *trace;
 };
 
-constexpr int FT_TRACE_SLOTS = 64;
+constexpr int FT_TRACE_SLOTS = 64;    // [0] CTA start, [1] PDL wait passed, [2] end, [8 + 6 p + e] events of pass p < 9
 __device__ __forceinline__ void ft_stamp(unsigned long long *trace, int slot) {
   if (trace) trace[(size_t)(blockIdx.x + gridDim.x * blockIdx.y) * FT_TRACE_SLOTS + slot] = clock64();
 }
-
-__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
-  unsigned int v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__device__ __forceinline__ void ft_stamp_wall(unsigned long long *trace, int slot) {
-  if (trace) {
-    unsigned long long gt;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    trace[(size_t)(blockIdx.x + gridDim.x * blockIdx.y) * FT_TRACE_SLOTS + slot] = gt;
-  }
-}
-
-// wall-clock stamps of consecutive launches go to alternating regions behind the clock-stamp region
-__device__ __forceinline__ void ft_stamp_wall2(unsigned long long *trace, unsigned parity, int slot) {
-  if (trace) {
-    unsigned long long gt;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-    trace[(size_t)(1 + parity) * 256 * FT_TRACE_SLOTS + (size_t)(blockIdx.x + gridDim.x * blockIdx.y) * 8 + slot] = gt;
-  }
+__device__ __forceinline__ void ft_stamp_pass(unsigned long long *trace, int p, int e) {
+  if (trace && p < 9) trace[(size_t)(blockIdx.x + gridDim.x * blockIdx.y) * FT_TRACE_SLOTS + 8 + 6 * p + e] = clock64();
 }
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
@@ -1052,47 +1052,50 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 
-constexpr int FT_MMA_WARPS = 2;                  // MMA issuers; issuer w owns k-blocks {2w, 2w+1} of every group
-constexpr int FT_THREADS = 32 * (1 + FT_MMA_WARPS + 4);
-
-__global__ void __launch_bounds__(FT_THREADS, 1) mlp_chain_ft_kernel(const __grid_constant__ ChainFtParams cp) {
+__global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __grid_constant__ FtParams cp) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_x = smem_base;                                   // FT_KB x 4 KiB
   const uint32_t smem_w = smem_base + FT_KB * FT_X_BYTES;              // FT_KB x 8 KiB
   const uint32_t bar_base = smem_w + FT_KB * FT_W_BYTES;
-  const uint32_t x_full = bar_base;
-  const uint32_t w_full = bar_base + 8 * FT_NG;
-  const uint32_t w_empty = bar_base + 16 * FT_NG;
-  const uint32_t acc_bar = bar_base + 24 * FT_NG;
-  const uint32_t tmem_slot = acc_bar + 8;
+  const uint32_t x_full = bar_base;                                    // [FT_NG]
+  const uint32_t w_full = bar_base + 8 * FT_NG;                        // [FT_NG]
+  const uint32_t w_empty = bar_base + 16 * FT_NG;                      // [FT_NG] group's X and W slots consumed
+  const uint32_t acc_full = bar_base + 24 * FT_NG;                     // [2] accumulator (pass parity) complete
+  const uint32_t acc_free = acc_full + 16;                             // [2] accumulator read out by the epilogue
+  const uint32_t tmem_slot = acc_free + 16;
   uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t n0 = blockIdx.x * FT_M;              // first feature of this CTA
   const int32_t m0 = blockIdx.y * FT_N;              // first batch row of this CTA
-  const unsigned int G = gridDim.x;                  // CTAs per batch tile == arrivals per layer
-  unsigned int *counter = cp.counters + (size_t)blockIdx.y * FT_CTR_STRIDE;
-  const int L = cp.num_layers;
-  constexpr uint32_t TMEM_COLS = 2 * FT_MMA_WARPS * FT_N;   // per layer parity: one 32-column accumulator per issuer
+  const unsigned int G = gridDim.x;                  // CTAs per batch tile == arrivals per barrier
+  unsigned int *counter0 = cp.counters + (size_t)blockIdx.y * FT_CTR_STRIDE;
+  const int P = cp.num_passes;
 
   if (warp == 0 && lane == 0) {
-    for (int l = 0; l < L; ++l) {
-      ptx::prefetch_tensormap(&cp.tmX[l]);
-      ptx::prefetch_tensormap(&cp.tmW[l]);
-    }
+    ptx::prefetch_tensormap(&cp.pass[0].tmX);
+    ptx::prefetch_tensormap(&cp.pass[0].tmW);
     for (int g = 0; g < FT_NG; ++g) {
       ptx::mbar_init(x_full + 8 * g, 1);
       ptx::mbar_init(w_full + 8 * g, 1);
-      ptx::mbar_init(w_empty + 8 * g, FT_MMA_WARPS);
+      ptx::mbar_init(w_empty + 8 * g, 1);
     }
-    ptx::mbar_init(acc_bar, FT_MMA_WARPS);
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(acc_full + 8 * b, 1);
+      ptx::mbar_init(acc_free + 8 * b, 4);           // one arrival per epilogue warp
+    }
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_alloc(tmem_slot, 2 * FT_N);            // two 32-column accumulators, alternating by pass
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before_sync();
@@ -1100,125 +1103,125 @@ __global__ void __launch_bounds__(FT_THREADS, 1) mlp_chain_ft_kernel(const __gri
   ptx::tc_fence_after_sync();
   const uint32_t tmem_acc = *tmem_slot_ptr;
   if (threadIdx.x == 0) ft_stamp(cp.trace, 0);
-  unsigned long long wall_start = 0;
-  if (cp.trace) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(wall_start));
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp == 0) {
     // ===== producer: the whole warp walks the (uniform) control flow, one elected lane issues =====
     // box coordinates (batch element, k-block) of group g's first slot, without integer division
-    auto group_coords = [&](int l, int g, int32_t &b, int32_t &kb) {
-      const int32_t k_iters = cp.layer[l].k_iters;
+    auto group_coords = [&](const FtPass &ps, int g, int32_t &b, int32_t &kb) {
       b = 0;
       kb = g * FT_GROUP;
-      while (kb >= k_iters) { kb -= k_iters; ++b; }
+      while (kb >= ps.k_iters) { kb -= ps.k_iters; ++b; }
     };
-    auto issue_w = [&](int l, int g) {
+    auto issue_w = [&](int p, int g) {
+      const FtPass &ps = cp.pass[p];
       int32_t b, kb;
-      group_coords(l, g, b, kb);
+      group_coords(ps, g, b, kb);
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(w_full + 8 * g, FT_GROUP * FT_W_BYTES);
-        ptx::tma_load_3d(smem_w + g * (FT_GROUP * FT_W_BYTES), &cp.tmW[l], w_full + 8 * g, n0, kb * BLOCK_K, b);
+        ptx::tma_load_3d(smem_w + g * (FT_GROUP * FT_W_BYTES), &ps.tmW, w_full + 8 * g, n0, kb * BLOCK_K, b);
       }
       __syncwarp();
     };
-    auto issue_x_group = [&](int l, int g) {
+    auto issue_x = [&](int p, int g) {
+      const FtPass &ps = cp.pass[p];
       int32_t b, kb;
-      group_coords(l, g, b, kb);
+      group_coords(ps, g, b, kb);
       if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(x_full + 8 * g, FT_GROUP * FT_X_BYTES);
-        ptx::tma_load_4d(smem_x + g * (FT_GROUP * FT_X_BYTES), &cp.tmX[l], x_full + 8 * g, 0, m0, kb, b);
+        ptx::tma_load_4d(smem_x + g * (FT_GROUP * FT_X_BYTES), &ps.tmX, x_full + 8 * g, 0, m0, kb, b);
       }
       __syncwarp();
     };
-    const bool x0_early = cp.weights_early && cp.x0_early;
-    auto early_weights = [&]() {
-      const int NG0 = cp.layer[0].total_iters / FT_GROUP;
-      for (int g = 0; g < NG0; ++g) {                // group by group: the MMAs start on the first 48 KiB
+    const bool x0_early = cp.weights_early && cp.x0_early && !cp.pass[0].x_dep;
+    auto early_loads = [&]() {
+      for (int g = 0; g < cp.pass[0].groups; ++g) {  // group by group: the MMAs start on the first 48 KiB
         issue_w(0, g);
-        if (x0_early) issue_x_group(0, g);
+        if (x0_early) issue_x(0, g);
       }
-      // later layers: this CTA's share of the feature tile's weight slice goes to L2 now
-      for (int l = 1; l < L; ++l) {
-        for (int g = (int)blockIdx.y; g < cp.layer[l].total_iters / FT_GROUP; g += (int)gridDim.y) {
+      // the next passes' weights: this CTA's share of the feature tile's slice goes to L2 now
+      for (int p = 1; p < P && p < 3; ++p) {
+        const FtPass &ps = cp.pass[p];
+        for (int g = (int)blockIdx.y; g < ps.groups; g += (int)gridDim.y) {
           int32_t b, kb;
-          group_coords(l, g, b, kb);
-          if (ptx::elect_one()) ptx::tma_prefetch_3d(&cp.tmW[l], n0, kb * BLOCK_K, b);
+          group_coords(ps, g, b, kb);
+          if (ptx::elect_one()) ptx::tma_prefetch_3d(&ps.tmW, n0, kb * BLOCK_K, b);
           __syncwarp();
         }
       }
     };
-    auto issue_x = [&](int l) {
-      const int NG = cp.layer[l].total_iters / FT_GROUP;
-      for (int g = 0; g < NG; ++g) issue_x_group(l, g);
-    };
-    if (cp.weights_early) early_weights();
+    if (cp.weights_early) early_loads();
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (lane == 0) ft_stamp(cp.trace, 62);
-    if (!cp.weights_early) early_weights();
-    // arrivals of this launch so far are < G (nobody passes layer 0's barrier without this CTA)
-    const unsigned int base = (ld_acquire_gpu(counter) / G) * G;
-    if (cp.trace && lane == 0) {
-      const unsigned parity = (base / (G * (unsigned)(L - 1))) & 1u;
-      unsigned long long *t = cp.trace + (size_t)(1 + parity) * 256 * FT_TRACE_SLOTS + (size_t)(blockIdx.x + gridDim.x * blockIdx.y) * 8;
-      t[0] = wall_start;
-      ft_stamp_wall2(cp.trace, parity, 1);
-      t[7] = base;
-    }
-    for (int l = 0; l < L; ++l) {
-      const int NG = cp.layer[l].total_iters / FT_GROUP;
-      if (l > 0) {
-        for (int g = 0; g < NG; ++g) {               // group g's slots are free once layer l-1's MMAs on them retired
-          ptx::mbar_wait(w_empty + 8 * g, (l - 1) & 1);
-          issue_w(l, g);
-          if (l == 1 && lane == 0) ft_stamp(cp.trace, 40 + g);
-        }
-        // Y(l-1) rows [m0, m0+32): all G CTAs of this batch tile have stored and arrived
-        const unsigned int target = base + (unsigned)l * G;
-        unsigned int spins = 0;
+    if (lane == 0) ft_stamp(cp.trace, 1);
+    if (!cp.weights_early) early_loads();
+    // arrivals of this launch so far are < G on either counter (nobody passes a barrier without this CTA)
+    unsigned int base[FT_MAX_WAYS];
+#pragma unroll
+    for (int sl = 0; sl < FT_MAX_WAYS; ++sl) base[sl] = (ld_acquire_gpu(counter0 + sl * FT_CTR_SLOT) / G) * G;
+    for (int p = 0; p < P; ++p) {
+      const FtPass &ps = cp.pass[p];
+      if (p + 1 < P && lane == 0) {
+        ptx::prefetch_tensormap(&cp.pass[p + 1].tmX);
+        ptx::prefetch_tensormap(&cp.pass[p + 1].tmW);
+      }
+      const unsigned int *ctr = counter0 + (int)ps.slot * FT_CTR_SLOT;
+      unsigned int target = ps.wait_arrivals * G;
+#pragma unroll
+      for (int sl = 0; sl < FT_MAX_WAYS; ++sl)
+        if (sl == (int)ps.slot) target += base[sl];
+      bool ready = !ps.x_dep;
+      int x_next = (p == 0 && x0_early) ? ps.groups : 0;     // X groups issued so far
+      for (int g = 0; g < ps.groups; ++g) {
+        if (p > 0) ptx::mbar_wait(w_empty + 8 * g, (p - 1) & 1);   // slots of group g retired by pass p-1's MMAs
+        if (p > 0) issue_w(p, g);                    // pass 0's weights were issued by early_loads()
         // relaxed (L2-coherent) polls: an acquire on every iteration costs a fence per poll. The data this flag
         // guards was fenced to L2 by its writers before they arrived, and it is only read by TMA (L2, never L1),
-        // issued after this loop exits - a control dependency the hardware does not speculate across.
-        while ((int)(ld_relaxed_gpu(counter) - target) < 0) {
+        // issued after the check - a control dependency the hardware does not speculate across.
+        if (!ready) ready = (int)(ld_relaxed_gpu(ctr) - target) >= 0;   // one non-blocking look per group
+        if (ready) {
+          if (x_next == 0 && ps.x_dep) {
+            if (cp.proxy_fence) asm volatile("fence.proxy.async;" ::: "memory");
+            if (lane == 0) ft_stamp_pass(cp.trace, p, 0);
+          }
+          for (; x_next <= g; ++x_next) issue_x(p, x_next);
+        }
+      }
+      if (!ready) {
+        unsigned int spins = 0;
+        while ((int)(ld_relaxed_gpu(ctr) - target) < 0) {
           if (++spins > (1u << 22)) __trap();        // co-residency assumption broken: fail loudly, never hang
         }
-        if (l == 2 && lane == 0) ft_stamp_wall(cp.trace, 38);
-        if (!cp.no_proxy_fence) asm volatile("fence.proxy.async;" ::: "memory");     // generic-proxy stores (other SMs) -> TMA reads
-        if (l == 1 && lane == 0) ft_stamp(cp.trace, 1);
-        if (l == 2 && lane == 0) ft_stamp(cp.trace, 7);
-        if (l == 2 && lane == 0) ft_stamp_wall(cp.trace, 39);
+        if (cp.proxy_fence) asm volatile("fence.proxy.async;" ::: "memory");   // generic stores (other SMs) -> TMA reads
+        if (lane == 0) ft_stamp_pass(cp.trace, p, 0);
       }
-      if (l > 0 || !x0_early) issue_x(l);
-      if (l == 1 && lane == 0) ft_stamp(cp.trace, 2);
+      for (; x_next < ps.groups; ++x_next) issue_x(p, x_next);
+      if (lane == 0) ft_stamp_pass(cp.trace, p, 1);
     }
-    if (cp.trace && lane == 0) ft_stamp_wall2(cp.trace, (base / (G * (unsigned)(L - 1))) & 1u, 2);   // producer done
-  } else if (warp <= FT_MMA_WARPS) {
-    // ===== MMA issuers: uniform control flow, one elected lane issues; issuer w accumulates its k-blocks of every
-    // group into its own 32 TMEM columns (the epilogue adds the issuers' accumulators) =====
-    const int w = warp - 1;
+  } else if (warp == 1) {
+    // ===== MMA issuer: uniform control flow, one elected lane issues =====
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(FT_M, FT_N, 1, 0);     // A (weights) MN-major, B (X) K-major
-    constexpr int KB_PER_W = FT_GROUP / FT_MMA_WARPS;
-    // descriptors of this issuer's first k-block / k-step 0 of group 0; the rest are constants added to the address field
-    const uint64_t da0 = ptx::umma_smem_desc_sw128(smem_w + w * KB_PER_W * FT_W_BYTES, FT_W_BYTES, 1024);
-    const uint64_t db0 = ptx::umma_smem_desc_sw128(smem_x + w * KB_PER_W * FT_X_BYTES, 16, 1024);
-    for (int l = 0; l < L; ++l) {
-      const int NG = cp.layer[l].total_iters / FT_GROUP;
-      const uint32_t par = l & 1;
-      const uint32_t acc = tmem_acc + (uint32_t)((l & 1) * FT_MMA_WARPS + w) * FT_N;
+    // descriptors of slot 0 / k-step 0; every other (slot, k-step) is a constant added to the 14-bit address field
+    const uint64_t da0 = ptx::umma_smem_desc_sw128(smem_w, FT_W_BYTES, 1024);
+    const uint64_t db0 = ptx::umma_smem_desc_sw128(smem_x, 16, 1024);
+    for (int p = 0; p < P; ++p) {
+      const int NG = cp.pass[p].groups;
+      const uint32_t par = p & 1;
+      const uint32_t acc = tmem_acc + par * FT_N;
+      if (p >= 2) {                                  // the epilogue of pass p-2 has read this accumulator out
+        ptx::mbar_wait(acc_free + 8 * par, ((p >> 1) - 1) & 1);
+        ptx::tc_fence_after_sync();
+      }
 #pragma unroll
       for (int g = 0; g < FT_NG; ++g) {
         if (g < NG) {
           ptx::mbar_wait(w_full + 8 * g, par);
-          if (l == 1 && threadIdx.x == 32) ft_stamp(cp.trace, 8 + g);
-          if (l == 0 && threadIdx.x == 32) ft_stamp(cp.trace, 52 + g);
           ptx::mbar_wait(x_full + 8 * g, par);
           ptx::tc_fence_after_sync();
-          if (l == 1 && threadIdx.x == 32) ft_stamp(cp.trace, 24 + g);
-          if (l == 0 && threadIdx.x == 32) ft_stamp(cp.trace, 48 + g);
+          if (g == 0 && lane == 0) ft_stamp_pass(cp.trace, p, 2);
           if (ptx::elect_one()) {
 #pragma unroll
-            for (int j = 0; j < KB_PER_W; ++j) {
+            for (int j = 0; j < FT_GROUP; ++j) {
 #pragma unroll
               for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
                 const uint64_t da = da0 + (uint64_t)(((g * FT_GROUP + j) * FT_W_BYTES + kk * (UMMA_K * 128)) >> 4);
@@ -1226,87 +1229,60 @@ __global__ void __launch_bounds__(FT_THREADS, 1) mlp_chain_ft_kernel(const __gri
                 ptx::umma_bf16(acc, da, db, idesc, (g > 0 || j > 0 || kk > 0) ? 1u : 0u);
               }
             }
-            ptx::umma_commit(w_empty + 8 * g);       // the group's weight slots may be refilled for the next layer
-            if (g == NG - 1) ptx::umma_commit(acc_bar);
+            ptx::umma_commit(w_empty + 8 * g);       // the group's slots may be refilled with the next pass's tiles
+            if (g == NG - 1) ptx::umma_commit(acc_full + 8 * par);
           }
           __syncwarp();
-          if (l == 1 && threadIdx.x == 32) ft_stamp(cp.trace, 28 + g);
         }
       }
-      if (l == 0 && threadIdx.x == 32) ft_stamp(cp.trace, 56);
     }
   } else {
     // ===== epilogue: TMEM lanes 32q + (0..15) hold features 16q + (0..15); columns = the 32 batch rows =====
     const int q = warp & 3;
     const int f = 16 * q + (lane & 15);
     const bool active = lane < 16;
-    const int ep_tid0 = 32 * (1 + FT_MMA_WARPS);     // first epilogue thread: the one that arrives for the CTA
-    // this thread's bias of every layer, requested before the wait when the parameters are not produced in flight
-    uint16_t bias_raw[CHAIN_MAX_LAYERS];
-    auto load_biases = [&]() {
-#pragma unroll
-      for (int l = 0; l < CHAIN_MAX_LAYERS; ++l)
-        bias_raw[l] = (l < L && cp.layer[l].bin_kind) ? __ldg(static_cast<const uint16_t *>(cp.layer[l].D) + n0 + f)
-                                                      : (uint16_t)0;
+    const int ep_tid0 = 64;                          // first epilogue thread: the one that arrives for the CTA
+    auto load_bias = [&](int p) -> uint16_t {
+      return (p < P && cp.pass[p].has_bias) ? __ldg(static_cast<const uint16_t *>(cp.pass[p].D) + n0 + f) : (uint16_t)0;
     };
-    if (cp.weights_early) load_biases();
+    // this thread's bias of the first pass, requested before the wait when the parameters are not produced in flight
+    uint16_t bias_next = 0;
+    if (cp.weights_early) bias_next = load_bias(0);
     // everything before this point only read memory; no store may precede the previous kernel's completion
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (threadIdx.x == ep_tid0) ft_stamp(cp.trace, 34);
-    if (!cp.weights_early) load_biases();
-#pragma unroll
-    for (int l = 0; l < CHAIN_MAX_LAYERS; ++l) {
-      if (l >= L) break;
-      const TcParams &p = cp.layer[l];
-      const float bias = bf16_bits_to_f32(bias_raw[l]);
-      ptx::mbar_wait(acc_bar, l & 1);
+    if (!cp.weights_early) bias_next = load_bias(0);
+    for (int p = 0; p < P; ++p) {
+      const FtPass &ps = cp.pass[p];
+      const float bias = bf16_bits_to_f32(bias_next);
+      bias_next = load_bias(p + 1);                  // in flight while this pass's accumulator completes
+      const uint32_t par = p & 1;
+      ptx::mbar_wait(acc_full + 8 * par, (p >> 1) & 1);
       ptx::tc_fence_after_sync();
-      if (l == 1 && threadIdx.x == ep_tid0) ft_stamp(cp.trace, 3);
-      if (l == 0 && threadIdx.x == ep_tid0) ft_stamp(cp.trace, 57);
-      if (l == 0 && threadIdx.x == ep_tid0 + 32) ft_stamp(cp.trace, 33);
-      if (l == 2 && threadIdx.x == ep_tid0) ft_stamp(cp.trace, 59);
-      const uint32_t t0 = tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + (uint32_t)((l & 1) * FT_MMA_WARPS) * FT_N;
+      if (threadIdx.x == ep_tid0) ft_stamp_pass(cp.trace, p, 3);
       uint32_t r[32];
-      ptx::tmem_ld_32x32(t0, r);
+      ptx::tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + par * FT_N, r);
       ptx::tmem_ld_wait();
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-#pragma unroll
-      for (int w = 1; w < FT_MMA_WARPS; ++w) {
-        ptx::tmem_ld_32x32(t0 + w * FT_N, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(r[j]);
-      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(acc_free + 8 * par);
       if (active) {
-        uint16_t *out = static_cast<uint16_t *>(p.C) + (int64_t)m0 * p.ldc + n0 + f;
-        if (p.relu) {
+        uint16_t *out = static_cast<uint16_t *>(ps.C) + (int64_t)m0 * ps.ldc + n0 + f;
+        if (ps.relu) {
 #pragma unroll
-          for (int j = 0; j < FT_N; ++j) out[(int64_t)j * p.ldc] = f32_to_bf16_bits(relu_f32(v[j] + bias));
+          for (int j = 0; j < FT_N; ++j) out[(int64_t)j * ps.ldc] = f32_to_bf16_bits(relu_f32(__uint_as_float(r[j]) + bias));
         } else {
 #pragma unroll
-          for (int j = 0; j < FT_N; ++j) out[(int64_t)j * p.ldc] = f32_to_bf16_bits(v[j] + bias);
+          for (int j = 0; j < FT_N; ++j) out[(int64_t)j * ps.ldc] = f32_to_bf16_bits(__uint_as_float(r[j]) + bias);
         }
       }
-      if (l == 1 && threadIdx.x == ep_tid0) ft_stamp(cp.trace, 4);
-      if (l == 0 && threadIdx.x == ep_tid0) ft_stamp(cp.trace, 32);
-      if (l == L - 1 && threadIdx.x == ep_tid0 && cp.trace) {   // last store issued: wall clock, parity from the counter
-        const unsigned parity = ((ld_relaxed_gpu(counter) - 1) / (G * (unsigned)(L - 1))) & 1u;
-        ft_stamp_wall2(cp.trace, parity, 3);
-      }
-      if (l + 1 < L) {
-        ptx::tc_fence_before_sync();
-        asm volatile("bar.sync 1, 128;" ::: "memory");     // all epilogue threads have issued their Y(l) stores
+      if (threadIdx.x == ep_tid0) ft_stamp_pass(cp.trace, p, 4);
+      if (ps.arrive) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // all epilogue threads have issued their stores
         if (threadIdx.x == ep_tid0) {
           // one gpu-scope release by the arriving thread; the CTA barrier ordered the other threads' stores before it
-          if (l == 1) ft_stamp(cp.trace, 60);
           asm volatile("fence.acq_rel.gpu;" ::: "memory");
-          if (l == 1) ft_stamp(cp.trace, 61);
-          asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
-          if (l == 1) ft_stamp(cp.trace, 5);
-          if (l == 1) ft_stamp_wall(cp.trace, 63);
-          if (l == 0) ft_stamp(cp.trace, 58);
+          asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter0 + (int)ps.slot * FT_CTR_SLOT) : "memory");
+          ft_stamp_pass(cp.trace, p, 5);
         }
       }
     }
@@ -1314,10 +1290,10 @@ __global__ void __launch_bounds__(FT_THREADS, 1) mlp_chain_ft_kernel(const __gri
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (threadIdx.x == 0) ft_stamp(cp.trace, 6);
+  if (threadIdx.x == 0) ft_stamp(cp.trace, 2);
   if (warp == 1) {
     ptx::tc_fence_after_sync();
-    ptx::tmem_dealloc(tmem_acc, TMEM_COLS);
+    ptx::tmem_dealloc(tmem_acc, 2 * FT_N);
   }
 }
 
@@ -1769,7 +1745,7 @@ bool brgemm_chain_supported(const KernelDesc *const *descs, const GemmArgs *args
   return true;
 }
 
-// Feature-major chain (mlp_chain_ft_kernel): additionally needs m % 32 == 0, n % 64 == 0, a reduction of at most
+// Feature-major chain (mlp_chain_ft_kernel): additionally needs m % 32 == 0, n % 64 == 0, a reduction of exactly
 // FT_KB k-blocks per layer, bias-add (bcast_col) or no binary, and (m/32) x (n/64) <= 148 co-resident CTAs.
 static bool chain_ft_supported(const KernelDesc *const *descs, const GemmArgs *args, int L) {
   static const bool off = [] { const char *e = getenv("TPP_XSMM_CHAIN"); return e && e[0] == 's'; }();
@@ -1780,7 +1756,7 @@ static bool chain_ft_supported(const KernelDesc *const *descs, const GemmArgs *a
   for (int l = 0; l < L; ++l) {
     const KernelDesc &d = *descs[l];
     const int64_t k_iters = d.k / BLOCK_K, iters = args[l].batch * k_iters;
-    if (iters < FT_GROUP || iters > FT_KB || (iters % FT_GROUP) != 0) return false;
+    if (iters != FT_KB) return false;
     // a group of 4 k-block slots must be one TMA box: 4 k-blocks of one batch element, or whole batch elements
     if (!((k_iters % FT_GROUP) == 0 || k_iters == 1 || k_iters == 2)) return false;
     if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && args[l].D == nullptr) return false;
@@ -1788,10 +1764,120 @@ static bool chain_ft_supported(const KernelDesc *const *descs, const GemmArgs *a
   return true;
 }
 
-static bool launch_brgemm_chain_ft(const KernelDesc *const *descs, const GemmArgs *args, int L, cudaStream_t stream) {
-  ChainFtParams cp;
+namespace {
+struct ByteRange { const char *lo, *hi; };
+inline bool overlaps(const ByteRange &a, const ByteRange &b) { return a.lo < b.hi && b.lo < a.hi; }
+// operand footprints of one chain: inputs (first layer's A, every layer's B and D) and outputs (every layer's C)
+void chain_ranges(const KernelDesc *const *descs, const GemmArgs *args, int L, std::vector<ByteRange> &in,
+                  std::vector<ByteRange> &out) {
+  for (int l = 0; l < L; ++l) {
+    const KernelDesc &d = *descs[l];
+    const GemmArgs &g = args[l];
+    const int64_t nb = g.batch > 0 ? g.batch : 1;
+    auto rng = [](const void *p, int64_t elems) {
+      const char *c = static_cast<const char *>(p);
+      return ByteRange{c, c + elems * 2};
+    };
+    if (l == 0) in.push_back(rng(g.A, (nb - 1) * d.stride_a + (d.m - 1) * d.lda + d.k));
+    in.push_back(rng(g.B, (nb - 1) * d.stride_b + (d.k - 1) * d.ldb + d.n));
+    if (g.D) in.push_back(rng(g.D, d.n));
+    out.push_back(rng(g.C, (d.m - 1) * d.ldc + d.n));
+  }
+}
+}  // namespace
+
+// Launch chains [0, num_chains) - chain c is layers [first[c], first[c] + len[c]) of descs / args, each already accepted
+// by brgemm_chain_supported - as ONE feature-major launch, interleaving pairs of chains. Only a prefix of mutually
+// independent, identically tiled chains is taken. Returns the number of chains launched (0: not applicable).
+int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args, const int *first, const int *len,
+                            int num_chains, cudaStream_t stream) {
+  if (num_chains < 1 || !chain_ft_supported(descs + first[0], args + first[0], len[0])) return 0;
+  static const bool multi_off = [] { const char *e = getenv("TPP_XSMM_CHAIN_MULTI"); return e && e[0] == '0'; }();
+  const KernelDesc &d0 = *descs[first[0]];
+  // ---- which chains go into this launch ----
+  int take = 1, passes = len[0];
+  {
+    std::vector<ByteRange> in_all, out_all;
+    chain_ranges(descs + first[0], args + first[0], len[0], in_all, out_all);
+    while (!multi_off && take < num_chains) {
+      const int c = take;
+      const KernelDesc &d = *descs[first[c]];
+      if (d.m != d0.m || d.n != d0.n || passes + len[c] > FT_MAX_PASSES) break;
+      if (!chain_ft_supported(descs + first[c], args + first[c], len[c])) break;
+      std::vector<ByteRange> in, out;
+      chain_ranges(descs + first[c], args + first[c], len[c], in, out);
+      bool indep = true;
+      for (const ByteRange &o : out) {
+        for (const ByteRange &x : in_all) indep = indep && !overlaps(o, x);
+        for (const ByteRange &x : out_all) indep = indep && !overlaps(o, x);
+      }
+      for (const ByteRange &i : in)
+        for (const ByteRange &x : out_all) indep = indep && !overlaps(i, x);
+      if (!indep) break;
+      in_all.insert(in_all.end(), in.begin(), in.end());
+      out_all.insert(out_all.end(), out.begin(), out.end());
+      passes += len[c];
+      ++take;
+    }
+  }
+  // ---- the pass list: `ways` chains at a time interleaved layer by layer; a chain's counter slot is its position in
+  // the tuple. One chain's layer-to-layer latency (store, fence, counter, poll, TMA: ~5000 clk) is longer than one
+  // pass (~3000-4000 clk), so three chains are needed to keep the tensor pipe busy. ----
+  static const int ways = [] {
+    const char *e = getenv("TPP_XSMM_CHAIN_WAYS");
+    const int w = e ? atoi(e) : 3;
+    return w < 1 ? 1 : w > FT_MAX_WAYS ? FT_MAX_WAYS : w;
+  }();
+  static FtParams cp;   // ~20 KiB: too large for the stack of a small thread; launches are serialised per thread anyway
+  static std::mutex cp_mutex;
+  std::lock_guard<std::mutex> lock(cp_mutex);
   memset(&cp, 0, sizeof(cp));
-  const KernelDesc &d0 = *descs[0];
+  uint32_t arrivals[FT_MAX_WAYS] = {0, 0, 0, 0};
+  int np = 0;
+  bool weights_early = true;
+  auto add_pass = [&](int c, int l, int slot) -> bool {
+    const KernelDesc &d = *descs[first[c] + l];
+    const GemmArgs &g = args[first[c] + l];
+    FtPass &ps = cp.pass[np];
+    const uint64_t nb = (uint64_t)g.batch;
+    const uint32_t k_iters = (uint32_t)(d.k / BLOCK_K);
+    const uint32_t gk = k_iters >= FT_GROUP ? FT_GROUP : k_iters, gb = FT_GROUP / gk;   // box = gk k-blocks x gb batches
+    if (!encode_map_x4(&ps.tmX, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, FT_N, gk,
+                       gb) ||
+        !encode_map(&ps.tmW, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, FT_M,
+                    BLOCK_K * gk, gb))
+      return false;
+    ps.C = g.C;
+    ps.D = g.D;
+    ps.ldc = d.ldc;
+    ps.k_iters = (int32_t)k_iters;
+    ps.groups = FT_NG;
+    ps.has_bias = (d.op == OpClass::FusedBrgemm && g.D && d.binary_kind == 1) ? 1 : 0;
+    ps.relu = (d.op == OpClass::FusedBrgemm && d.unary_kind == 5) ? 1 : 0;
+    ps.slot = (uint8_t)slot;
+    ps.x_dep = l > 0 ? 1 : 0;
+    ps.wait_arrivals = arrivals[ps.slot];
+    ps.arrive = l + 1 < len[c] ? 1 : 0;
+    if (ps.arrive) ++arrivals[ps.slot];
+    if (!g.b_independent) weights_early = false;
+    ++np;
+    return true;
+  };
+  bool ok = true;
+  for (int c = 0; c < take && ok; c += ways) {
+    const int nc = std::min(ways, take - c);
+    int maxL = 0;
+    for (int j = 0; j < nc; ++j) maxL = std::max(maxL, len[c + j]);
+    for (int l = 0; l < maxL && ok; ++l)
+      for (int j = 0; j < nc && ok; ++j)
+        if (l < len[c + j]) ok = add_pass(c + j, l, j);
+  }
+  if (!ok) {
+    static bool warned = false;
+    if (!warned) fprintf(stderr, "tpp-xsmm-cuda: feature-major chain: tensor map encode failed, using the split-K chain\n");
+    warned = true;
+    return 0;
+  }
   dim3 grid((unsigned)(d0.n / FT_M), (unsigned)(d0.m / FT_N), 1);
   const int n_ctas = (int)(grid.x * grid.y);
   StreamScratch &sc = scratch_for(stream);
@@ -1800,55 +1886,28 @@ static bool launch_brgemm_chain_ft(const KernelDesc *const *descs, const GemmArg
   for (auto &e : sc.ft_counters)
     if (e.first == (int)grid.x) counters = e.second;
   if (!counters) {
-    const size_t bytes = sizeof(unsigned int) * 148 * FT_CTR_STRIDE;
+    const size_t bytes = sizeof(unsigned int) * FT_MAX_WAYS * FT_CTR_SLOT;
     TPP_CUDA_CHECK(cudaMalloc(&counters, bytes));
     TPP_CUDA_CHECK(cudaMemsetAsync(counters, 0, bytes, stream));
     sc.ft_counters.emplace_back((int)grid.x, counters);
   }
   cp.counters = counters;
-  cp.num_layers = L;
-  cp.weights_early = 1;
+  cp.num_passes = np;
+  cp.weights_early = weights_early ? 1 : 0;
+  static const bool x0_off = [] { const char *e = getenv("TPP_XSMM_CHAIN_X0"); return e && e[0] == '0'; }();
+  cp.x0_early = (args[first[0]].a_independent && !x0_off) ? 1 : 0;
   // fence.proxy.async between the flag observation and the TMA reads costs ~0.3 us per layer and is not needed for
   // data that other SMs fenced to L2 (TMA reads L2); TPP_XSMM_CHAIN_PROXY_FENCE=1 turns it on
   static const bool pf = [] { const char *e = getenv("TPP_XSMM_CHAIN_PROXY_FENCE"); return e && e[0] == '1'; }();
-  cp.no_proxy_fence = pf ? 0 : 1;
-  for (int l = 0; l < L; ++l) {
-    const KernelDesc &d = *descs[l];
-    const GemmArgs &g = args[l];
-    const uint64_t nb = (uint64_t)g.batch;
-    const uint32_t k_iters = (uint32_t)(d.k / BLOCK_K);
-    const uint32_t gk = k_iters >= FT_GROUP ? FT_GROUP : k_iters, gb = FT_GROUP / gk;   // box = gk k-blocks x gb batches
-    if (!encode_map_x4(&cp.tmX[l], g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, FT_N,
-                       gk, gb) ||
-        !encode_map(&cp.tmW[l], g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, FT_M,
-                    BLOCK_K * gk, gb)) {
-      static bool warned = false;
-      if (!warned) fprintf(stderr, "tpp-xsmm-cuda: feature-major chain: tensor map encode failed, using split-K chain\n");
-      warned = true;
-      return false;
-    }
-    TcParams &p = cp.layer[l];
-    memset(&p, 0, sizeof(p));
-    p.C = g.C; p.D = g.D;
-    p.m = d.m; p.n = d.n; p.ldc = d.ldc;
-    p.k_iters = (int32_t)(d.k / BLOCK_K);
-    p.total_iters = (int32_t)(g.batch * p.k_iters);
-    p.beta0 = 1;
-    p.bin_kind = (d.op == OpClass::FusedBrgemm && g.D) ? (int)d.binary_kind : 0;
-    p.bin_mode = bin_mode_from_flags(d.binary_flags);
-    p.relu = d.op == OpClass::FusedBrgemm && d.unary_kind == 5;
-    if (!g.b_independent) cp.weights_early = 0;
-  }
-  static const bool x0_off = [] { const char *e = getenv("TPP_XSMM_CHAIN_X0"); return e && e[0] == '0'; }();
-  cp.x0_early = (args[0].a_independent && !x0_off) ? 1 : 0;
-  constexpr int smem = FT_KB * (FT_X_BYTES + FT_W_BYTES) + (3 * FT_NG + 1) * 8 + 16 + 1024;
+  cp.proxy_fence = pf ? 1 : 0;
+  constexpr int smem = FT_KB * (FT_X_BYTES + FT_W_BYTES) + (3 * FT_NG + 4) * 8 + 16 + 1024;
   static std::once_flag once;
   std::call_once(once, [] {
     TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_ft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   });
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(FT_THREADS);
+  cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[1];
@@ -1864,16 +1923,20 @@ static bool launch_brgemm_chain_ft(const KernelDesc *const *descs, const GemmArg
     }
     cp.trace = g_trace_buf;
     g_chain_trace_ctas = n_ctas;
-    g_chain_trace_layers = L;
+    g_chain_trace_layers = np;
     g_chain_trace_ft = true;
   }
   TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_ft_kernel, cp));
-  snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dlayers_ft64x32_fullk", L);
-  return true;
+  if (take == 1) snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dlayers_ft64x32_fullk", len[0]);
+  else snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dx%dlayers_ft64x32_fullk", take, len[0]);
+  return take;
 }
 
 bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, int L, cudaStream_t stream) {
-  if (chain_ft_supported(descs, args, L) && launch_brgemm_chain_ft(descs, args, L, stream)) return true;
+  {
+    const int first = 0;
+    if (launch_brgemm_chains_ft(descs, args, &first, &L, 1, stream) == 1) return true;
+  }
   ChainParams cp;
   memset(&cp, 0, sizeof(cp));
   const KernelDesc &d0 = *descs[0];
@@ -1963,7 +2026,7 @@ void brgemm_tc_dump_trace() {
     const int n_ctas = g_chain_trace_ctas;
     std::vector<unsigned long long> h((size_t)n_ctas * FT_TRACE_SLOTS);
     TPP_CUDA_CHECK(cudaMemcpy(h.data(), g_trace_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    auto avg = [&](int sl, int ref) {   // median over CTAs (the ~20 CTAs that start early on idle SMs skew a mean)
+    auto med = [&](int sl, int ref) {   // median over CTAs (the ~20 CTAs that start early on idle SMs skew a mean)
       std::vector<double> v;
       for (int c = 0; c < n_ctas; ++c) {
         const unsigned long long *r = &h[(size_t)c * FT_TRACE_SLOTS];
@@ -1973,57 +2036,12 @@ void brgemm_tc_dump_trace() {
       std::sort(v.begin(), v.end());
       return v[v.size() / 2];
     };
-    fprintf(stderr, "ft-chain-trace %d layers, %d CTAs; median clocks relative to L1 released (slot 1):\n", g_chain_trace_layers, n_ctas);
-    fprintf(stderr, "  cta_start=%.0f L0_mma_issued=%.0f X_issued=%.0f acc_ready=%.0f stored=%.0f arrived=%.0f end=%.0f\n",
-            avg(0, 1), avg(56, 1), avg(2, 1), avg(3, 1), avg(4, 1), avg(5, 1), avg(6, 1));
-    fprintf(stderr, "  L0: pdl_wait_passed=%.0f w_full=%.0f %.0f %.0f %.0f x_full=%.0f %.0f %.0f %.0f mma_issued=%.0f acc_ready=%.0f arrived=%.0f | L2: released=%.0f acc_ready=%.0f\n",
-            avg(62, 1), avg(52, 1), avg(53, 1), avg(54, 1), avg(55, 1), avg(48, 1), avg(49, 1), avg(50, 1), avg(51, 1),
-            avg(56, 1), avg(57, 1), avg(58, 1), avg(7, 1), avg(59, 1));
-    {   // wall-clock view of the L1 -> L2 barrier per batch tile: arrival skew and visibility latency
-      const int gx = n_ctas >= 16 ? 16 : n_ctas, gy = n_ctas / gx;
-      double skew = 0, lat = 0, latmax = 0, lat2 = 0;
-      for (int y = 0; y < gy; ++y) {
-        unsigned long long amax = 0;
-        const unsigned long long a0 = h[(size_t)(y * gx) * FT_TRACE_SLOTS + 63];
-        double asum = 0;
-        for (int x = 0; x < gx; ++x) { const unsigned long long a = h[(size_t)(y * gx + x) * FT_TRACE_SLOTS + 63]; asum += (double)((long long)(a - a0)); if (a > amax) amax = a; }
-        skew += (double)((long long)(amax - a0)) - asum / gx;
-        for (int x = 0; x < gx; ++x) { const double d = (double)h[(size_t)(y * gx + x) * FT_TRACE_SLOTS + 39] - (double)amax; lat += d; if (d > latmax) latmax = d; }
-        for (int x = 0; x < gx; ++x) lat2 += (double)h[(size_t)(y * gx + x) * FT_TRACE_SLOTS + 38] - (double)amax;
-      }
-      fprintf(stderr, "  poll exit - last arrival: mean %.0f ns\n", lat2 / n_ctas);
-      fprintf(stderr, "  L1->L2 barrier (ns, globaltimer): last arrival - mean arrival = %.0f; release - last arrival: mean %.0f max %.0f\n",
-              skew / gy, lat / n_ctas, latmax);
-    }
-    {   // wall-clock hand-off between the last two launches (regions 1, 2)
-      std::vector<unsigned long long> w((size_t)2 * 256 * FT_TRACE_SLOTS);
-      TPP_CUDA_CHECK(cudaMemcpy(w.data(), g_trace_buf + (size_t)256 * FT_TRACE_SLOTS, w.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-      const unsigned long long *r0 = w.data(), *r1 = w.data() + (size_t)256 * FT_TRACE_SLOTS;
-      if (r0[7] > r1[7]) std::swap(r0, r1);   // r0 = earlier launch (smaller counter base)
-      unsigned long long end0 = 0;
-      for (int c = 0; c < n_ctas; ++c) if (r0[c * 8 + 3] > end0) end0 = r0[c * 8 + 3];
-      double s_avg = 0, p_avg = 0, e_avg = 0; long long s_min = 1ll << 60, s_max = -(1ll << 60), p_min = 1ll << 60, p_max = -(1ll << 60), e_max = 0;
-      for (int c = 0; c < n_ctas; ++c) {
-        const long long st = (long long)(r1[c * 8 + 0] - end0), pw = (long long)(r1[c * 8 + 1] - end0), en = (long long)(r1[c * 8 + 3] - end0);
-        s_avg += st; p_avg += pw; e_avg += en;
-        if (st < s_min) s_min = st; if (st > s_max) s_max = st;
-        if (pw < p_min) p_min = pw; if (pw > p_max) p_max = pw;
-        if (en > e_max) e_max = en;
-      }
-      fprintf(stderr, "  hand-off (ns after the previous launch's last store): CTA start min %lld avg %.0f max %lld; PDL wait passed min %lld avg %.0f max %lld; "
-                      "last store avg %.0f max %lld\n", s_min, s_avg / n_ctas, s_max, p_min, p_avg / n_ctas, p_max, e_avg / n_ctas, e_max);
-    }
-    fprintf(stderr, "  L0 epilogue: pdl_wait_passed(epi warp)=%.0f acc_ready(warp+1)=%.0f stored=%.0f\n", avg(34, 1), avg(33, 1), avg(32, 1));
-    fprintf(stderr, "  L1 arrive: stored=%.0f bar_sync=%.0f fence=%.0f red=%.0f\n", avg(4, 1), avg(60, 1), avg(61, 1), avg(5, 1));
-    fprintf(stderr, "  W1 issued :");
-    for (int i = 0; i < 4; ++i) fprintf(stderr, " %.0f", avg(40 + i, 1));
-    fprintf(stderr, "\n  W1 full   :");
-    for (int i = 0; i < 4; ++i) fprintf(stderr, " %.0f", avg(8 + i, 1));
-    fprintf(stderr, "\n  X1 full   :");
-    for (int i = 0; i < 4; ++i) fprintf(stderr, " %.0f", avg(24 + i, 1));
-    fprintf(stderr, "\n  MMA issued:");
-    for (int i = 0; i < 4; ++i) fprintf(stderr, " %.0f", avg(28 + i, 1));
-    fprintf(stderr, "\n");
+    fprintf(stderr, "ft-chain-trace %d passes, %d CTAs; median SM clocks since the PDL wait passed: cta_start=%.0f end=%.0f\n",
+            g_chain_trace_layers, n_ctas, med(0, 1), med(2, 1));
+    for (int p = 0; p < 9 && p < g_chain_trace_layers; ++p)
+      fprintf(stderr, "  pass %d: inputs_ready=%.0f x_issued=%.0f mma_start=%.0f acc_ready=%.0f stored=%.0f arrived=%.0f\n", p,
+              med(8 + 6 * p, 1), med(9 + 6 * p, 1), med(10 + 6 * p, 1), med(11 + 6 * p, 1), med(12 + 6 * p, 1),
+              med(13 + 6 * p, 1));
     return;
   }
   if (g_chain_trace_ctas) {

@@ -60,6 +60,11 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
 // L consecutive layers (C of one is A of the next) in one persistent kernel: see brgemm_tc.cu
 bool brgemm_chain_supported(const KernelDesc *const *descs, const GemmArgs *args, int L);
 bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, int L, cudaStream_t stream);
+// several chains (chain c = layers [first[c], first[c] + len[c]), each accepted by brgemm_chain_supported) as ONE launch
+// of the feature-major chain kernel, pairs of mutually independent chains interleaved; returns the number of chains
+// launched (a prefix), 0 if the kernel does not apply
+int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args, const int *first, const int *len,
+                            int num_chains, cudaStream_t stream);
 const char *brgemm_tc_last_name();   // tile configuration of this thread's last tcgen05 launch
 void brgemm_tc_dump_trace();   // debug, TPP_XSMM_TC_TRACE=2
 

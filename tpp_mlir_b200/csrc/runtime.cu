@@ -434,23 +434,45 @@ void flush_pending() {
   std::vector<PendingGemm> list;
   list.swap(t_ctx.pending);
   cudaStream_t stream = t_ctx.stream;
-  size_t i = 0;
-  while (i < list.size()) {
-    int fused = 0;
-    for (int L = 4; L >= 2 && !fused; --L) {
-      if (i + L > list.size()) continue;
-      const KernelDesc *descs[4];
-      GemmArgs args[4];
-      for (int l = 0; l < L; ++l) { descs[l] = list[i + l].d; args[l] = list[i + l].g; }
-      if (brgemm_chain_supported(descs, args, L) && launch_brgemm_chain(descs, args, L, stream)) {
-        t_ctx.last_kernel = brgemm_tc_last_name();
-        count_launch();
-        fused = L;
-      }
+  // segment the list: maximal chains (2..4 layers, C of one = A of the next) and single invokes
+  const size_t n = list.size();
+  std::vector<const KernelDesc *> descs(n);
+  std::vector<GemmArgs> args(n);
+  for (size_t k = 0; k < n; ++k) { descs[k] = list[k].d; args[k] = list[k].g; }
+  std::vector<int> seg_first, seg_len;     // seg_len 1 = not a chain
+  for (size_t i = 0; i < n;) {
+    int L = 1;
+    for (int t = 4; t >= 2; --t)
+      if (i + t <= n && brgemm_chain_supported(descs.data() + i, args.data() + i, t)) { L = t; break; }
+    seg_first.push_back((int)i);
+    seg_len.push_back(L);
+    i += L;
+  }
+  for (size_t sidx = 0; sidx < seg_first.size();) {
+    if (seg_len[sidx] == 1) {
+      issue_gemm(list[seg_first[sidx]].d, list[seg_first[sidx]].g, stream);
+      ++sidx;
+      continue;
     }
-    if (fused) { i += fused; continue; }
-    issue_gemm(list[i].d, list[i].g, stream);
-    ++i;
+    // a run of consecutive chains: as many as possible in one launch of the feature-major kernel
+    size_t run = sidx;
+    while (run < seg_first.size() && seg_len[run] > 1) ++run;
+    int took = launch_brgemm_chains_ft(descs.data(), args.data(), seg_first.data() + sidx, seg_len.data() + sidx,
+                                       (int)(run - sidx), stream);
+    if (took > 0) {
+      t_ctx.last_kernel = brgemm_tc_last_name();
+      count_launch();
+      sidx += took;
+      continue;
+    }
+    const int f = seg_first[sidx], L = seg_len[sidx];
+    if (launch_brgemm_chain(descs.data() + f, args.data() + f, L, stream)) {
+      t_ctx.last_kernel = brgemm_tc_last_name();
+      count_launch();
+    } else {
+      for (int l = 0; l < L; ++l) issue_gemm(list[f + l].d, list[f + l].g, stream);
+    }
+    ++sidx;
   }
 }
 
