@@ -298,6 +298,7 @@ def main():
     barrier()
     t_wall1 = time.perf_counter()
     launches = xsmm.launch_count() - launches0
+    timed_kernel = xsmm.last_kernel()   # the kernel the timed loop launched (graph mode: the fused chain kernel)
     sampler.stop()
     ms = ev0.elapsed_time(ev1)
     ms_max = shard.max_over_ranks(ms, device=dev)
@@ -430,7 +431,9 @@ def main():
                    "l2": f"rotating {num_sets} operand sets ({num_sets * set_bytes >> 20} MiB > 126 MiB L2), "
                          "inputs larger than L2",
                    "timing": "CUDA events on the launch stream, max over ranks",
-                   "issue_mode": ("CUDA graph replay of the captured xsmm invoke sequence (xsmm_cuda_graph_*)"
+                   "issue_mode": ("CUDA graph replay of the captured xsmm invoke sequence (xsmm_cuda_graph_*): one graph = "
+                                  f"one rotation of {num_sets} forward passes on {num_sets} operand sets, which the "
+                                  "runtime fuses into one launch of the chain kernel (3 passes interleaved)"
                                   if args.mode == "graph" else "one xsmm_fused_brgemm_invoke per layer"),
                    "flops_per_step": flops_step_rank * n_gpus, "matmul_flops_per_step": cfg.matmul_flops() * n_gpus},
         "clocks": sampler.summary(t_wall0, t_wall1),
@@ -448,13 +451,17 @@ def main():
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": achieved_tflops / pk["bf16_tflops"], "traffic": traffic,
-                     "kernel": xsmm.handle_kernel(replay.handles[0]), "peak_source": pk["source"] + ", burst",
-                     "flops_per_launch": flops_per_launch, "avg_launch_us": avg_launch_s * 1e6},
+                     "kernel": timed_kernel, "peak_source": pk["source"] + ", burst",
+                     "flops_per_launch": flops_per_launch, "avg_launch_us": avg_launch_s * 1e6,
+                     "forward_passes_per_launch": args.steps / max(launches, 1),
+                     "note": "batch 256 is latency/delivery-bound, not tensor-bound: per pass and SM 192 KiB of operands "
+                             "arrive at ~50 B/clk (DESIGN.md 4.1c); traffic = DRAM bytes of one launch (ncu)"},
         "cpu_baseline": cpu,
         "extra": {"ms_per_step_hot_l2": ms_hot, "gflops_hot_l2": flops_step_rank * n_gpus / (ms_hot * 1e-3) / 1e9,
                   "host_issue_us_per_launch": t_issue / max(launches, 1) * 1e6,
                   ("ms_per_step_direct_invokes" if args.mode == "graph" else "ms_per_step_graph_replay"): ms_other,
-                  "parity_rel_err_vs_oracle": rel, "kernel": xsmm.handle_kernel(replay.handles[0])},
+                  "parity_rel_err_vs_oracle": rel, "kernel": timed_kernel,
+                  "per_layer_kernel": xsmm.handle_kernel(replay.handles[0])},
     }
     print(json.dumps(line))
     if n_gpus > 1:

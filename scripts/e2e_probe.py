@@ -62,6 +62,14 @@ def mlp(depth, mode, steps=960):
     return dt * 1e6
 
 
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "batch":
+    for depth in (1, 2, 4):
+        print(f"raw H2D+D2H 512KiB, depth {depth}: {raw_pcie(depth):7.2f} us/step", flush=True)
+    for mode, depth in (("async", 4), ("async", 8), ("batch2", 4), ("batch2", 8), ("batch3", 6), ("batch3", 9),
+                        ("batch3", 12), ("batch4", 8), ("batch4", 12), ("batch6", 12), ("batch6", 18)):
+        print(f"mlp e2e {mode:8s} depth {depth:2d}: {mlp(depth, mode, steps=1200):7.2f} us/step", flush=True)
+    sys.exit(0)
+
 if __name__ == "__main__":
     for depth in (1, 2, 4, 8):
         print(f"raw H2D+D2H 512KiB, depth {depth}: {raw_pcie(depth):7.2f} us/step", flush=True)

@@ -1036,6 +1036,10 @@ struct FtParams {
   int weights_early;        // no weight / bias is produced by in-flight kernels: fetch pass 0's before the PDL wait
   int x0_early;             // same for pass 0's activations
   int proxy_fence;
+  int w_multicast;          // launched as (1,2,1) clusters: the two batch tiles of a cluster share each weight box
+  // split-K-2 variant only: counter values are derived from a per-slot launch epoch instead of being read back
+  unsigned int *epoch;      // [FT_MAX_WAYS] barriers completed per counter by earlier launches; [FT_MAX_WAYS] exit ticket
+  unsigned int arrivals_total[FT_MAX_WAYS];   // barriers per counter this launch adds to each slot
   unsigned long long *trace;
 };
 
@@ -1086,7 +1090,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
     for (int g = 0; g < FT_NG; ++g) {
       ptx::mbar_init(x_full + 8 * g, 1);
       ptx::mbar_init(w_full + 8 * g, 1);
-      ptx::mbar_init(w_empty + 8 * g, 1);
+      ptx::mbar_init(w_empty + 8 * g, cp.w_multicast ? 2 : 1);   // multicast: both CTAs of the cluster retire a group
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(acc_full + 8 * b, 1);
@@ -1102,6 +1106,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_acc = *tmem_slot_ptr;
+  // weight multicast: the peer's barriers must exist before this CTA's first multicast box can complete on them
+  const uint32_t crank = cp.w_multicast ? ptx::cluster_ctarank() : 0u;
+  if (cp.w_multicast) ptx::cluster_sync();
   if (threadIdx.x == 0) ft_stamp(cp.trace, 0);
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -1119,8 +1126,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
       int32_t b, kb;
       group_coords(ps, g, b, kb);
       if (ptx::elect_one()) {
+        // every CTA expects the whole box on its own barrier; with multicast only cluster rank (g & 1) fetches it,
+        // and the box lands in both CTAs' slots (same offsets) and completes on both CTAs' barriers
         ptx::mbar_arrive_expect_tx(w_full + 8 * g, FT_GROUP * FT_W_BYTES);
-        ptx::tma_load_3d(smem_w + g * (FT_GROUP * FT_W_BYTES), &ps.tmW, w_full + 8 * g, n0, kb * BLOCK_K, b);
+        if (!cp.w_multicast)
+          ptx::tma_load_3d(smem_w + g * (FT_GROUP * FT_W_BYTES), &ps.tmW, w_full + 8 * g, n0, kb * BLOCK_K, b);
+        else if ((uint32_t)(g & 1) == crank)
+          ptx::tma_load_3d_mc(smem_w + g * (FT_GROUP * FT_W_BYTES), &ps.tmW, w_full + 8 * g, n0, kb * BLOCK_K, b,
+                              (uint16_t)0x3);
       }
       __syncwarp();
     };
@@ -1229,7 +1242,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
                 ptx::umma_bf16(acc, da, db, idesc, (g > 0 || j > 0 || kk > 0) ? 1u : 0u);
               }
             }
-            ptx::umma_commit(w_empty + 8 * g);       // the group's slots may be refilled with the next pass's tiles
+            // the group's slots may be refilled with the next pass's tiles (multicast: tell both CTAs of the cluster)
+            if (cp.w_multicast) ptx::umma_commit_mc(w_empty + 8 * g, (uint16_t)0x3);
+            else ptx::umma_commit(w_empty + 8 * g);
             if (g == NG - 1) ptx::umma_commit(acc_full + 8 * par);
           }
           __syncwarp();
@@ -1290,10 +1305,326 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (cp.w_multicast) ptx::cluster_sync();           // the peer may still signal this CTA's barriers until it is done too
   if (threadIdx.x == 0) ft_stamp(cp.trace, 2);
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc(tmem_acc, 2 * FT_N);
+  }
+}
+
+// ---- split-K-2 variant of the pass kernel ------------------------------------------------------------------------
+// A pass of the kernel above is bound by the bytes one SM receives (192 KiB at ~50 B/clk); the tensor pipe and even
+// shared memory have slack. Here a cluster of two CTAs shares a (64 features) x (64 batch rows) tile and splits the
+// reduction in halves: per pass a CTA receives 64 KiB of weights + 64 KiB of activations (-33 %) and the two partial
+// accumulators meet through distributed shared memory: each CTA owns 32 of the 64 rows, pushes the other 32 rows of
+// its partial (8 KiB, st.shared::cluster) into the peer's receive buffer and signals the peer's mbarrier
+// (release.cluster / acquire.cluster) - no global-memory round trip, no cluster-wide barrier. Everything else
+// (pass list, interleaved chains, slot retirement by tcgen05.commit, per-batch-tile arrival counters) is unchanged;
+// a consumer CTA (feature tile, batch tile, k-half z) waits for the 16 CTAs that produce its half of the features.
+constexpr int F2_N = 64;                          // batch rows per tile (UMMA N); a CTA stores 32 of them
+constexpr int F2_KB = 8;                          // k-block slots per CTA: half of the 16-k-block reduction
+constexpr int F2_GROUP = 2;                       // k-blocks per TMA box / barrier
+constexpr int F2_NG = F2_KB / F2_GROUP;
+constexpr int F2_X_BYTES = F2_N * BLOCK_K * 2;    // 8 KiB
+constexpr int F2_RECV_BYTES = FT_M * 32 * 4;      // the peer's partial for my 32 rows: 64 features x 32 f32
+constexpr int F2_THREADS = 352;                   // producer, MMA issuer, 4 finisher warps, 4 sender warps, arriver
+
+__global__ void __launch_bounds__(F2_THREADS, 1) mlp_chain_ft2_kernel(const __grid_constant__ FtParams cp) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_x = smem_base;                                   // F2_KB x 8 KiB
+  const uint32_t smem_w = smem_base + F2_KB * F2_X_BYTES;              // F2_KB x 8 KiB
+  const uint32_t smem_recv = smem_w + F2_KB * FT_W_BYTES;              // 2 x 8 KiB (pass parity)
+  const uint32_t bar_base = smem_recv + 2 * F2_RECV_BYTES;
+  const uint32_t x_full = bar_base;                                    // [F2_NG]
+  const uint32_t w_full = bar_base + 8 * F2_NG;
+  const uint32_t w_empty = bar_base + 16 * F2_NG;
+  const uint32_t acc_full = bar_base + 24 * F2_NG;                     // [2]
+  const uint32_t acc_free = acc_full + 16;                             // [2]
+  const uint32_t xchg_full = acc_free + 16;                            // [2] the peer's partial has landed in recv[parity]
+  const uint32_t recv_free = xchg_full + 16;                           // [2] (local) my finishers are done with recv[parity]
+  const uint32_t tmem_slot = recv_free + 16;
+  uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int32_t n0 = blockIdx.x * FT_M;              // first feature of this CTA
+  const int32_t m0 = blockIdx.y * F2_N;              // first batch row of the pair's tile
+  const uint32_t z = blockIdx.z;                     // k-half of this CTA == its rank in the (1,1,2) cluster
+  const unsigned int G = gridDim.x;                  // arrivals per barrier: gridDim.x/2 feature tiles x 2 k-halves
+  // the counter this CTA waits on: its batch tile, ITS k-half of the next layer's reduction
+  unsigned int *wait_ctr0 = cp.counters + (size_t)(blockIdx.y * 2 + z) * FT_CTR_STRIDE;
+  // the counter this CTA arrives on: its batch tile, the k-half its features belong to
+  unsigned int *arrive_ctr0 = cp.counters + (size_t)(blockIdx.y * 2 + (blockIdx.x >= gridDim.x / 2 ? 1 : 0)) * FT_CTR_STRIDE;
+  const int P = cp.num_passes;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&cp.pass[0].tmX);
+    ptx::prefetch_tensormap(&cp.pass[0].tmW);
+    for (int g = 0; g < F2_NG; ++g) {
+      ptx::mbar_init(x_full + 8 * g, 1);
+      ptx::mbar_init(w_full + 8 * g, 1);
+      ptx::mbar_init(w_empty + 8 * g, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(acc_full + 8 * b, 1);
+      ptx::mbar_init(acc_free + 8 * b, 8);           // one arrival per finisher and per sender warp
+      ptx::mbar_init(xchg_full + 8 * b, 1);          // one expect_tx arrival (mine); the peer's st.async bytes complete it
+      ptx::mbar_init(recv_free + 8 * b, 4);          // one arrival per finisher warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 2 * F2_N);            // two 64-column accumulators, alternating by pass
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+  ptx::cluster_sync();                               // the peer's barriers exist before anything is pushed to it
+  if (threadIdx.x == 0) ft_stamp(cp.trace, 0);
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+  if (warp == 0) {
+    // ===== producer =====
+    // box coordinates (batch element, k-block) of group g's first k-block: global k-block index z * 8 + 2 g
+    auto group_coords = [&](const FtPass &ps, int g, int32_t &b, int32_t &kb) {
+      b = 0;
+      kb = (int32_t)z * F2_KB + g * F2_GROUP;
+      while (kb >= ps.k_iters) { kb -= ps.k_iters; ++b; }
+    };
+    auto issue_w = [&](int p, int g) {
+      const FtPass &ps = cp.pass[p];
+      int32_t b, kb;
+      group_coords(ps, g, b, kb);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(w_full + 8 * g, F2_GROUP * FT_W_BYTES);
+        ptx::tma_load_3d(smem_w + g * (F2_GROUP * FT_W_BYTES), &ps.tmW, w_full + 8 * g, n0, kb * BLOCK_K, b);
+      }
+      __syncwarp();
+    };
+    auto issue_x = [&](int p, int g) {
+      const FtPass &ps = cp.pass[p];
+      int32_t b, kb;
+      group_coords(ps, g, b, kb);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(x_full + 8 * g, F2_GROUP * F2_X_BYTES);
+        ptx::tma_load_4d(smem_x + g * (F2_GROUP * F2_X_BYTES), &ps.tmX, x_full + 8 * g, 0, m0, kb, b);
+      }
+      __syncwarp();
+    };
+    const bool x0_early = cp.weights_early && cp.x0_early && !cp.pass[0].x_dep;
+    auto early_loads = [&]() {
+      for (int g = 0; g < F2_NG; ++g) {
+        issue_w(0, g);
+        if (x0_early) issue_x(0, g);
+      }
+    };
+    if (cp.weights_early) early_loads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (lane == 0) ft_stamp(cp.trace, 1);
+    if (!cp.weights_early) early_loads();
+    unsigned int base[FT_MAX_WAYS];
+#pragma unroll
+    for (int sl = 0; sl < FT_MAX_WAYS; ++sl) base[sl] = ld_acquire_gpu(cp.epoch + sl) * G;
+    for (int p = 0; p < P; ++p) {
+      const FtPass &ps = cp.pass[p];
+      if (p + 1 < P && lane == 0) {
+        ptx::prefetch_tensormap(&cp.pass[p + 1].tmX);
+        ptx::prefetch_tensormap(&cp.pass[p + 1].tmW);
+      }
+      const unsigned int *ctr = wait_ctr0 + (int)ps.slot * FT_CTR_SLOT;
+      unsigned int target = ps.wait_arrivals * G;
+#pragma unroll
+      for (int sl = 0; sl < FT_MAX_WAYS; ++sl)
+        if (sl == (int)ps.slot) target += base[sl];
+      bool ready = !ps.x_dep;
+      int x_next = (p == 0 && x0_early) ? F2_NG : 0;
+      for (int g = 0; g < F2_NG; ++g) {
+        if (p > 0) ptx::mbar_wait(w_empty + 8 * g, (p - 1) & 1);
+        if (p > 0) issue_w(p, g);
+        if (!ready) ready = (int)(ld_relaxed_gpu(ctr) - target) >= 0;
+        if (ready) {
+          if (x_next == 0 && ps.x_dep) {
+            if (cp.proxy_fence) asm volatile("fence.proxy.async;" ::: "memory");
+          }
+          for (; x_next <= g; ++x_next) issue_x(p, x_next);
+        }
+      }
+      if (!ready) {
+        unsigned int spins = 0;
+        while ((int)(ld_relaxed_gpu(ctr) - target) < 0) {
+          if (++spins > (1u << 22)) __trap();        // co-residency assumption broken: fail loudly, never hang
+        }
+        if (cp.proxy_fence) asm volatile("fence.proxy.async;" ::: "memory");
+      }
+      for (; x_next < F2_NG; ++x_next) issue_x(p, x_next);
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(FT_M, F2_N, 1, 0);     // A (weights) MN-major, B (X) K-major
+    const uint64_t da0 = ptx::umma_smem_desc_sw128(smem_w, FT_W_BYTES, 1024);
+    const uint64_t db0 = ptx::umma_smem_desc_sw128(smem_x, 16, 1024);
+    for (int p = 0; p < P; ++p) {
+      const uint32_t par = p & 1;
+      const uint32_t acc = tmem_acc + par * F2_N;
+      if (p >= 2) {
+        ptx::mbar_wait(acc_free + 8 * par, ((p >> 1) - 1) & 1);
+        ptx::tc_fence_after_sync();
+      }
+#pragma unroll
+      for (int g = 0; g < F2_NG; ++g) {
+        ptx::mbar_wait(w_full + 8 * g, par);
+        ptx::mbar_wait(x_full + 8 * g, par);
+        ptx::tc_fence_after_sync();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int j = 0; j < F2_GROUP; ++j) {
+#pragma unroll
+            for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+              const uint64_t da = da0 + (uint64_t)(((g * F2_GROUP + j) * FT_W_BYTES + kk * (UMMA_K * 128)) >> 4);
+              const uint64_t db = db0 + (uint64_t)(((g * F2_GROUP + j) * F2_X_BYTES + kk * (UMMA_K * 2)) >> 4);
+              ptx::umma_bf16(acc, da, db, idesc, (g > 0 || j > 0 || kk > 0) ? 1u : 0u);
+            }
+          }
+          ptx::umma_commit(w_empty + 8 * g);
+          if (g == F2_NG - 1) ptx::umma_commit(acc_full + 8 * par);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===== epilogue: lanes 0..15 of quarter q hold features 16q + lane; columns = the tile's 64 batch rows.
+    // This CTA finishes rows [32z, 32z+32). SENDER warps (6..9) push the other 32 columns of the partial into the
+    // peer's receive buffer and signal it; FINISHER warps (2..5) add the peer's partial to their own 32 columns, apply
+    // bias / ReLU, round once and store. Two warp sets, so that waiting for the peer never delays what the peer waits for.
+    const int q = warp & 3;
+    const int f = 16 * q + (lane & 15);
+    const bool active = lane < 16;
+    const uint32_t peer = z ^ 1u;
+    if (warp == 10) {
+      // ===== arriver: publishes a pass's output for the finishers (they only bar.arrive), so the ~1100-clk gpu-scope
+      // fence is off their critical path =====
+      asm volatile("griddepcontrol.wait;" ::: "memory");
+      for (int p = 0; p < P; ++p) {
+        const FtPass &ps = cp.pass[p];
+        if (!ps.arrive) continue;
+        asm volatile("bar.sync 1, 160;" ::: "memory");     // the 128 finisher threads have issued this pass's stores
+        if (lane == 0) {
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(arrive_ctr0 + (int)ps.slot * FT_CTR_SLOT) : "memory");
+          ft_stamp_pass(cp.trace, p, 5);
+        }
+        __syncwarp();
+      }
+    } else if (warp >= 6) {
+      for (int p = 0; p < P; ++p) {
+        const uint32_t par = p & 1;
+        ptx::mbar_wait(acc_full + 8 * par, (p >> 1) & 1);
+        ptx::tc_fence_after_sync();
+        uint32_t oth[32];
+        ptx::tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + par * F2_N + 32 * peer, oth);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(acc_free + 8 * par);
+        if (threadIdx.x == 192) ft_stamp_pass(cp.trace, p, 1);
+        // Overwriting the peer's recv[par] (last used by pass p-2) needs no signal from the peer: this push waits
+        // until MY finishers have consumed pass p-1, i.e. received the peer's push of pass p-1, which the peer only
+        // sent after ITS finishers had consumed pass p-2 (same rule on its side). All local, no cross-SM release.
+        if (p >= 1) ptx::mbar_wait(recv_free + 8 * ((p - 1) & 1), ((p - 1) >> 1) & 1);
+        if (active) {
+          // st.async: every 16-byte store carries its own completion (complete_tx on the peer's barrier); a
+          // release.cluster arrive after plain st.shared::cluster stores cost ~3000 clk per pass here
+          const uint32_t remote = ptx::mapa(smem_recv + par * F2_RECV_BYTES + (uint32_t)f * 128u, peer);
+          const uint32_t remote_bar = ptx::mapa(xchg_full + 8 * par, peer);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)                  // 16-byte chunks XOR-swizzled by the feature: no bank conflicts
+            ptx::st_async_v4(remote + (uint32_t)((j ^ (f & 7)) << 4), remote_bar, oth[4 * j], oth[4 * j + 1],
+                             oth[4 * j + 2], oth[4 * j + 3]);
+        }
+        if (threadIdx.x == 192) ft_stamp_pass(cp.trace, p, 2);
+      }
+    } else {
+      const int ep_tid0 = 64;
+      auto load_bias = [&](int p) -> uint16_t {
+        return (p < P && cp.pass[p].has_bias) ? __ldg(static_cast<const uint16_t *>(cp.pass[p].D) + n0 + f) : (uint16_t)0;
+      };
+      uint16_t bias_next = 0;
+      if (cp.weights_early) bias_next = load_bias(0);
+      asm volatile("griddepcontrol.wait;" ::: "memory");   // no store before the previous kernel has completed
+      if (!cp.weights_early) bias_next = load_bias(0);
+      for (int p = 0; p < P; ++p) {
+        const FtPass &ps = cp.pass[p];
+        const float bias = bf16_bits_to_f32(bias_next);
+        bias_next = load_bias(p + 1);
+        const uint32_t par = p & 1;
+        ptx::mbar_wait(acc_full + 8 * par, (p >> 1) & 1);
+        ptx::tc_fence_after_sync();
+        if (threadIdx.x == ep_tid0) ft_stamp_pass(cp.trace, p, 3);
+        uint32_t own[32];
+        ptx::tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + par * F2_N + 32 * z, own);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(acc_free + 8 * par);
+        const uint32_t recv = smem_recv + par * F2_RECV_BYTES + (uint32_t)f * 128u;    // this feature's 32 f32
+        if (threadIdx.x == ep_tid0) ptx::mbar_arrive_expect_tx(xchg_full + 8 * par, F2_RECV_BYTES);
+        ptx::mbar_wait(xchg_full + 8 * par, (p >> 1) & 1);
+        if (threadIdx.x == ep_tid0) ft_stamp_pass(cp.trace, p, 0);
+        float v[32];
+        if (active) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 t;
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(recv + (uint32_t)((j ^ (f & 7)) << 4)));
+            // (k-half 0) + (k-half 1): IEEE addition is commutative, so both CTAs of a pair round identically
+            v[4 * j] = __uint_as_float(own[4 * j]) + t.x;
+            v[4 * j + 1] = __uint_as_float(own[4 * j + 1]) + t.y;
+            v[4 * j + 2] = __uint_as_float(own[4 * j + 2]) + t.z;
+            v[4 * j + 3] = __uint_as_float(own[4 * j + 3]) + t.w;
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(recv_free + 8 * par);   // this warp has consumed recv[par] of pass p
+        if (active) {
+          uint16_t *out = static_cast<uint16_t *>(ps.C) + (int64_t)(m0 + 32 * (int32_t)z) * ps.ldc + n0 + f;
+          if (ps.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) out[(int64_t)j * ps.ldc] = f32_to_bf16_bits(relu_f32(v[j] + bias));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) out[(int64_t)j * ps.ldc] = f32_to_bf16_bits(v[j] + bias);
+          }
+        }
+        if (threadIdx.x == ep_tid0) ft_stamp_pass(cp.trace, p, 4);
+        if (ps.arrive) asm volatile("bar.arrive 1, 160;" ::: "memory");   // stores issued; the arriver warp publishes them
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::cluster_sync();                               // the peer may still push to / signal this CTA until it is done too
+  if (threadIdx.x == 0) {
+    ft_stamp(cp.trace, 2);
+    // launch epoch: the last CTA to leave publishes how many barriers every counter has completed
+    const unsigned int n_ctas = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int ticket = atomicAdd(cp.epoch + FT_MAX_WAYS, 1u);
+    if (ticket == n_ctas - 1) {
+#pragma unroll
+      for (int sl = 0; sl < FT_MAX_WAYS; ++sl) cp.epoch[sl] += cp.arrivals_total[sl];
+      cp.epoch[FT_MAX_WAYS] = 0;
+      __threadfence();
+    }
+  }
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc(tmem_acc, 2 * F2_N);
   }
 }
 
@@ -1764,6 +2095,23 @@ static bool chain_ft_supported(const KernelDesc *const *descs, const GemmArgs *a
   return true;
 }
 
+// split-K-2 variant (mlp_chain_ft2_kernel): 64-row batch tiles, an even number of feature tiles, and a reduction whose
+// halves are whole TMA boxes of two k-blocks
+static bool chain_ft2_supported(const KernelDesc *const *descs, const GemmArgs *args, int L) {
+  static const bool off = [] { const char *e = getenv("TPP_XSMM_CHAIN_SPLIT"); return e && e[0] == '1'; }();
+  if (off) return false;
+  const KernelDesc &d0 = *descs[0];
+  if ((d0.m % F2_N) != 0 || (d0.n % (2 * FT_M)) != 0) return false;
+  if ((d0.m / F2_N) * (d0.n / FT_M) * 2 > 148) return false;
+  for (int l = 0; l < L; ++l) {
+    const int64_t k_iters = descs[l]->k / BLOCK_K;
+    if (!(k_iters == 1 || (k_iters % 2) == 0)) return false;
+    if (k_iters > F2_KB && (k_iters % F2_KB) != 0) return false;   // a k-half is whole batch elements or divides one
+    if (k_iters < F2_KB && (F2_KB % k_iters) != 0) return false;
+  }
+  return true;
+}
+
 namespace {
 struct ByteRange { const char *lo, *hi; };
 inline bool overlaps(const ByteRange &a, const ByteRange &b) { return a.lo < b.hi && b.lo < a.hi; }
@@ -1794,6 +2142,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   if (num_chains < 1 || !chain_ft_supported(descs + first[0], args + first[0], len[0])) return 0;
   static const bool multi_off = [] { const char *e = getenv("TPP_XSMM_CHAIN_MULTI"); return e && e[0] == '0'; }();
   const KernelDesc &d0 = *descs[first[0]];
+  const bool split2 = chain_ft2_supported(descs + first[0], args + first[0], len[0]);
   // ---- which chains go into this launch ----
   int take = 1, passes = len[0];
   {
@@ -1804,6 +2153,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
       const KernelDesc &d = *descs[first[c]];
       if (d.m != d0.m || d.n != d0.n || passes + len[c] > FT_MAX_PASSES) break;
       if (!chain_ft_supported(descs + first[c], args + first[c], len[c])) break;
+      if (split2 && !chain_ft2_supported(descs + first[c], args + first[c], len[c])) break;
       std::vector<ByteRange> in, out;
       chain_ranges(descs + first[c], args + first[c], len[c], in, out);
       bool indep = true;
@@ -1841,9 +2191,10 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     FtPass &ps = cp.pass[np];
     const uint64_t nb = (uint64_t)g.batch;
     const uint32_t k_iters = (uint32_t)(d.k / BLOCK_K);
-    const uint32_t gk = k_iters >= FT_GROUP ? FT_GROUP : k_iters, gb = FT_GROUP / gk;   // box = gk k-blocks x gb batches
-    if (!encode_map_x4(&ps.tmX, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, FT_N, gk,
-                       gb) ||
+    const uint32_t grp = split2 ? F2_GROUP : FT_GROUP;
+    const uint32_t gk = k_iters >= grp ? grp : k_iters, gb = grp / gk;   // box = gk k-blocks x gb batch elements
+    if (!encode_map_x4(&ps.tmX, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a,
+                       split2 ? F2_N : FT_N, gk, gb) ||
         !encode_map(&ps.tmW, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, FT_M,
                     BLOCK_K * gk, gb))
       return false;
@@ -1878,20 +2229,24 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     warned = true;
     return 0;
   }
-  dim3 grid((unsigned)(d0.n / FT_M), (unsigned)(d0.m / FT_N), 1);
-  const int n_ctas = (int)(grid.x * grid.y);
+  dim3 grid((unsigned)(d0.n / FT_M), (unsigned)(d0.m / (split2 ? F2_N : FT_N)), split2 ? 2u : 1u);
+  const int n_ctas = (int)(grid.x * grid.y * grid.z);
   StreamScratch &sc = scratch_for(stream);
-  // one counter array per group size G = grid.x: every counter stays a multiple of G between launches
+  // one counter array per (variant, group size G = grid.x): every counter stays a multiple of G between launches;
+  // the split-K-2 variant's launch epoch (+ exit ticket) lives behind its counters
+  const int ctr_key = (int)grid.x | (split2 ? 0x10000 : 0);
   unsigned int *counters = nullptr;
   for (auto &e : sc.ft_counters)
-    if (e.first == (int)grid.x) counters = e.second;
+    if (e.first == ctr_key) counters = e.second;
   if (!counters) {
-    const size_t bytes = sizeof(unsigned int) * FT_MAX_WAYS * FT_CTR_SLOT;
+    const size_t bytes = sizeof(unsigned int) * (FT_MAX_WAYS * FT_CTR_SLOT + 2 * FT_MAX_WAYS);
     TPP_CUDA_CHECK(cudaMalloc(&counters, bytes));
     TPP_CUDA_CHECK(cudaMemsetAsync(counters, 0, bytes, stream));
-    sc.ft_counters.emplace_back((int)grid.x, counters);
+    sc.ft_counters.emplace_back(ctr_key, counters);
   }
   cp.counters = counters;
+  cp.epoch = counters + FT_MAX_WAYS * FT_CTR_SLOT;
+  for (int sl = 0; sl < FT_MAX_WAYS; ++sl) cp.arrivals_total[sl] = arrivals[sl];
   cp.num_passes = np;
   cp.weights_early = weights_early ? 1 : 0;
   static const bool x0_off = [] { const char *e = getenv("TPP_XSMM_CHAIN_X0"); return e && e[0] == '0'; }();
@@ -1900,21 +2255,36 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   // data that other SMs fenced to L2 (TMA reads L2); TPP_XSMM_CHAIN_PROXY_FENCE=1 turns it on
   static const bool pf = [] { const char *e = getenv("TPP_XSMM_CHAIN_PROXY_FENCE"); return e && e[0] == '1'; }();
   cp.proxy_fence = pf ? 1 : 0;
-  constexpr int smem = FT_KB * (FT_X_BYTES + FT_W_BYTES) + (3 * FT_NG + 4) * 8 + 16 + 1024;
+  constexpr int smem1 = FT_KB * (FT_X_BYTES + FT_W_BYTES) + (3 * FT_NG + 4) * 8 + 16 + 1024;
+  constexpr int smem2 = F2_KB * (F2_X_BYTES + FT_W_BYTES) + 2 * F2_RECV_BYTES + (3 * F2_NG + 8) * 8 + 16 + 1024;
+  const int smem = split2 ? smem2 : smem1;
   static std::once_flag once;
   std::call_once(once, [] {
-    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_ft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_ft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_ft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
   });
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(split2 ? F2_THREADS : NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 1;
+  // TPP_XSMM_CHAIN_MC=1: weight multicast across pairs of batch tiles ((1,2,1) clusters). It halves the L2 reads of
+  // the weights but not the bytes each SM receives, and a pass is bound by the latter (~47-53 B/clk per SM):
+  // measured 7.15 us (multicast) vs 7.12 us (unicast) per forward, so it stays off by default.
+  static const bool mc_on = [] { const char *e = getenv("TPP_XSMM_CHAIN_MC"); return e && e[0] == '1'; }();
+  cp.w_multicast = (!split2 && mc_on && (grid.y % 2) == 0) ? 1 : 0;
+  if (cp.w_multicast || split2) {
+    attrs[1].id = cudaLaunchAttributeClusterDimension;
+    attrs[1].val.clusterDim.x = 1;
+    attrs[1].val.clusterDim.y = split2 ? 1 : 2;
+    attrs[1].val.clusterDim.z = split2 ? 2 : 1;
+    cfg.numAttrs = 2;
+  }
   static const bool trace_on = [] { const char *e = getenv("TPP_XSMM_TC_TRACE"); return e && atoi(e) == 3; }();
   if (trace_on) {
     if (!g_trace_buf) {
@@ -1926,9 +2296,11 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     g_chain_trace_layers = np;
     g_chain_trace_ft = true;
   }
-  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_ft_kernel, cp));
-  if (take == 1) snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dlayers_ft64x32_fullk", len[0]);
-  else snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dx%dlayers_ft64x32_fullk", take, len[0]);
+  if (split2) TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_ft2_kernel, cp));
+  else TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_ft_kernel, cp));
+  const char *tile = split2 ? "ft64x64_splitk2" : "ft64x32_fullk";
+  if (take == 1) snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dlayers_%s", len[0], tile);
+  else snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dx%dlayers_%s", take, len[0], tile);
   return take;
 }
 
@@ -2039,7 +2411,7 @@ void brgemm_tc_dump_trace() {
     fprintf(stderr, "ft-chain-trace %d passes, %d CTAs; median SM clocks since the PDL wait passed: cta_start=%.0f end=%.0f\n",
             g_chain_trace_layers, n_ctas, med(0, 1), med(2, 1));
     for (int p = 0; p < 9 && p < g_chain_trace_layers; ++p)
-      fprintf(stderr, "  pass %d: inputs_ready=%.0f x_issued=%.0f mma_start=%.0f acc_ready=%.0f stored=%.0f arrived=%.0f\n", p,
+      fprintf(stderr, "  pass %d: e0(inputs_ready|xchg_done)=%.0f e1(x_issued|sender_start)=%.0f e2(mma_start|pushed)=%.0f acc_ready=%.0f stored=%.0f arrived=%.0f\n", p,
               med(8 + 6 * p, 1), med(9 + 6 * p, 1), med(10 + 6 * p, 1), med(11 + 6 * p, 1), med(12 + 6 * p, 1),
               med(13 + 6 * p, 1));
     return;

@@ -113,6 +113,9 @@ int64_t tpp_replay_mlp_e2e(int64_t dtype, int64_t num_layers, const int64_t *han
 //   mode 1  the loop body unrolled `depth` times inside ONE captured graph (the copies become parallel branches):
 //           one graph launch + one stream wait per `depth` steps.
 //   mode 2  one stream (xsmm_cuda_stream_create) and one captured step graph (copies included) per slot.
+//   mode 2 + g (g >= 1)  groups of g steps: upload_async of the g inputs -> ONE captured graph with the g layer
+//           sequences (independent chains, which the runtime fuses into one interleaved launch) -> download_async of the
+//           g outputs; depth / g groups in flight, wait_host before a slot is reused.
 // graphs: depth + 1 entries, streams: depth entries, 0 = not created yet; they persist across calls (one mode per
 // pair of arrays). steps is rounded down to a multiple of depth in mode 1. Returns the number of steps run or -1.
 __attribute__((visibility("default")))
@@ -159,6 +162,33 @@ int64_t tpp_replay_mlp_e2e_pipelined(int64_t dtype, int64_t num_layers, const in
       xsmm_cuda_stream_sync();   // the outputs of these `depth` steps are in host memory
     }
     return groups * depth;
+  }
+  if (mode >= 3) {
+    // mode 3 + g: like mode 0, but the unit of work is a GROUP of g = mode - 2 ... consecutive steps (slots): their
+    // inputs are uploaded, their layer sequences replay as ONE captured graph (independent chains: the runtime runs
+    // them interleaved in one launch), their outputs are downloaded; depth / g groups are in flight.
+    const int64_t gsz = mode - 2;                 // mode 3 -> 1 (== mode 0), mode 5 -> 3 steps per launch, ...
+    const int64_t ngrp = depth / gsz;
+    if (ngrp < 1) return -1;
+    for (int64_t grp = 0; grp < ngrp; ++grp) {
+      if (graphs[grp]) continue;
+      if (xsmm_cuda_graph_begin() != 0) return -1;
+      for (int64_t j = 0; j < gsz; ++j) layers(grp * gsz + j);
+      if (!(graphs[grp] = xsmm_cuda_graph_end())) return -1;
+    }
+    const int64_t iters = steps / gsz;
+    for (int64_t it = 0; it < iters; ++it) {
+      const int64_t grp = it % ngrp;
+      for (int64_t j = 0; j < gsz; ++j) {
+        const TppMlpSet &sl = slots[grp * gsz + j];
+        if (it >= ngrp) xsmm_cuda_wait_host(sl.acts[num_layers]);   // previous output of this slot consumed
+        xsmm_cuda_upload_async(sl.acts[0], in_bytes);
+      }
+      xsmm_cuda_graph_launch(graphs[grp]);
+      for (int64_t j = 0; j < gsz; ++j) xsmm_cuda_download_async(slots[grp * gsz + j].acts[num_layers], out_bytes);
+    }
+    xsmm_cuda_stream_sync();
+    return iters * gsz;
   }
   void *caller_stream = xsmm_cuda_get_stream();
   for (int64_t d = 0; d < depth; ++d) {

@@ -125,6 +125,7 @@ struct GraphHandle {
   uint32_t magic = 0x47525048u; // "GRPH"
   cudaGraphExec_t exec = nullptr;
   int64_t launches = 0;         // kernels per replay (for xsmm_cuda_launch_count)
+  char last_kernel[96] = {0};   // name of the last kernel captured (what xsmm_cuda_last_kernel reports after a replay)
 };
 thread_local ThreadCtx t_ctx;
 
@@ -1027,6 +1028,7 @@ extern "C" int64_t xsmm_cuda_graph_end(void) {
   }
   GraphHandle *gh = new GraphHandle();
   gh->launches = t_ctx.captured_launches;
+  snprintf(gh->last_kernel, sizeof(gh->last_kernel), "%s", t_ctx.last_kernel ? t_ctx.last_kernel : "");
   e = cudaGraphInstantiate(&gh->exec, graph, 0);
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) {
@@ -1042,6 +1044,11 @@ extern "C" void xsmm_cuda_graph_launch(int64_t graph) {
   if (!gh || gh->magic != 0x47525048u) fail("xsmm_cuda_graph_launch: not a graph handle");
   flush_pending();   // orders the launch after this thread's pending upload_async
   TPP_CUDA_CHECK(cudaGraphLaunch(gh->exec, t_ctx.stream));
+  {
+    thread_local char replayed[96];
+    memcpy(replayed, gh->last_kernel, sizeof(replayed));
+    t_ctx.last_kernel = replayed;
+  }
   g_launches.fetch_add(gh->launches, std::memory_order_relaxed);
 }
 

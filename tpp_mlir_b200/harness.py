@@ -265,14 +265,16 @@ class NativeMlpLoop:
         if rc != 0:
             raise RuntimeError("e2e replay failed (graph capture)")
 
-    PIPE_MODES = {"async": 0, "grouped": 1, "streams": 2}
+    PIPE_MODES = {"async": 0, "grouped": 1, "streams": 2, "batch2": 4, "batch3": 5, "batch4": 6, "batch6": 8}
 
     def run_e2e_pipelined(self, steps: int, elem_size: int = 2, mode: str = "async") -> int:
         """Throughput form of run_e2e: every operand set is a pipeline slot, so uploads, kernels and downloads
         of neighbouring steps overlap; every step still moves its input and its output across PCIe.
         mode "async": xsmm_cuda_upload_async / graph replay / download_async per step, wait_host before a slot is
         reused; "grouped": one captured graph holds num_sets steps (copies are parallel branches);
-        "streams": one stream + one captured step graph per slot. Returns the number of steps run."""
+        "streams": one stream + one captured step graph per slot; "batchG": groups of G steps share one captured graph
+        of G independent layer chains (one interleaved chain-kernel launch), num_sets / G groups in flight.
+        Returns the number of steps run."""
         cfg = self.cfg
         bn, bk, bc = cfg.tiles
         key = "_pipe_" + mode
