@@ -1313,30 +1313,37 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
   }
 }
 
-// ---- split-K-2 variant of the pass kernel ------------------------------------------------------------------------
+// ---- split-K variants (S = 2, 4) of the pass kernel -----------------------------------------------------------------
 // A pass of the kernel above is bound by the bytes one SM receives (192 KiB at ~50 B/clk); the tensor pipe and even
-// shared memory have slack. Here a cluster of two CTAs shares a (64 features) x (64 batch rows) tile and splits the
-// reduction in halves: per pass a CTA receives 64 KiB of weights + 64 KiB of activations (-33 %) and the two partial
-// accumulators meet through distributed shared memory: each CTA owns 32 of the 64 rows, pushes the other 32 rows of
-// its partial (8 KiB, st.shared::cluster) into the peer's receive buffer and signals the peer's mbarrier
-// (release.cluster / acquire.cluster) - no global-memory round trip, no cluster-wide barrier. Everything else
-// (pass list, interleaved chains, slot retirement by tcgen05.commit, per-batch-tile arrival counters) is unchanged;
-// a consumer CTA (feature tile, batch tile, k-half z) waits for the 16 CTAs that produce its half of the features.
-constexpr int F2_N = 64;                          // batch rows per tile (UMMA N); a CTA stores 32 of them
-constexpr int F2_KB = 8;                          // k-block slots per CTA: half of the 16-k-block reduction
-constexpr int F2_GROUP = 2;                       // k-blocks per TMA box / barrier
-constexpr int F2_NG = F2_KB / F2_GROUP;
-constexpr int F2_X_BYTES = F2_N * BLOCK_K * 2;    // 8 KiB
-constexpr int F2_RECV_BYTES = FT_M * 32 * 4;      // the peer's partial for my 32 rows: 64 features x 32 f32
+// shared memory have slack. Here a cluster of S CTAs shares a (64 features) x (32 S batch rows) tile and splits the
+// reduction S ways: per pass a CTA receives 128/S KiB of weights + 64 KiB of activations (S = 2: 128 KiB, S = 4:
+// 96 KiB) and the S partial accumulators meet through distributed shared memory: each CTA owns 32 of the rows and
+// pushes the other rows of its partial (8 KiB per peer) into the peers' receive buffers with st.async, whose bytes
+// complete_tx on the RECEIVER's mbarrier - no global-memory round trip, no cluster-wide barrier, no release/acquire
+// round trip (a release.cluster arrive after plain st.shared::cluster stores cost ~3000 clk per pass). Everything else
+// (pass list, interleaved chains, slot retirement by tcgen05.commit, arrival counters) is unchanged; a consumer CTA
+// (feature tile, batch tile, k-slice z) waits for the 16 CTAs that produce its slice of the features.
+template <int S> struct FS {
+  static constexpr int N = 32 * S;                  // batch rows per tile (UMMA N); a CTA stores 32 of them
+  static constexpr int KB = FT_KB / S;              // k-block slots per CTA
+  static constexpr int NG = 4;                      // groups (TMA boxes / barriers) per pass
+  static constexpr int GROUP = KB / NG;             // k-blocks per group
+  static constexpr int X_BYTES = N * BLOCK_K * 2;   // one k-block of activations
+  static constexpr int RECV_BYTES = FT_M * 32 * 4;  // one peer's partial for my 32 rows: 64 features x 32 f32
+  static constexpr int SMEM = KB * (X_BYTES + FT_W_BYTES) + 2 * (S - 1) * RECV_BYTES + (3 * NG + 8) * 8 + 16 + 1024;
+};
 constexpr int F2_THREADS = 352;                   // producer, MMA issuer, 4 finisher warps, 4 sender warps, arriver
 
-__global__ void __launch_bounds__(F2_THREADS, 1) mlp_chain_ft2_kernel(const __grid_constant__ FtParams cp) {
+template <int S>
+__global__ void __launch_bounds__(F2_THREADS, 1) mlp_chain_fts_kernel(const __grid_constant__ FtParams cp) {
+  constexpr int F2_N = FS<S>::N, F2_KB = FS<S>::KB, F2_NG = FS<S>::NG, F2_GROUP = FS<S>::GROUP;
+  constexpr int F2_X_BYTES = FS<S>::X_BYTES, F2_RECV_BYTES = FS<S>::RECV_BYTES;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_x = smem_base;                                   // F2_KB x 8 KiB
   const uint32_t smem_w = smem_base + F2_KB * F2_X_BYTES;              // F2_KB x 8 KiB
-  const uint32_t smem_recv = smem_w + F2_KB * FT_W_BYTES;              // 2 x 8 KiB (pass parity)
-  const uint32_t bar_base = smem_recv + 2 * F2_RECV_BYTES;
+  const uint32_t smem_recv = smem_w + F2_KB * FT_W_BYTES;              // [pass parity][sender rank slot] x 8 KiB
+  const uint32_t bar_base = smem_recv + 2 * (S - 1) * F2_RECV_BYTES;
   const uint32_t x_full = bar_base;                                    // [F2_NG]
   const uint32_t w_full = bar_base + 8 * F2_NG;
   const uint32_t w_empty = bar_base + 16 * F2_NG;
@@ -1351,12 +1358,12 @@ __global__ void __launch_bounds__(F2_THREADS, 1) mlp_chain_ft2_kernel(const __gr
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int32_t n0 = blockIdx.x * FT_M;              // first feature of this CTA
   const int32_t m0 = blockIdx.y * F2_N;              // first batch row of the pair's tile
-  const uint32_t z = blockIdx.z;                     // k-half of this CTA == its rank in the (1,1,2) cluster
-  const unsigned int G = gridDim.x;                  // arrivals per barrier: gridDim.x/2 feature tiles x 2 k-halves
-  // the counter this CTA waits on: its batch tile, ITS k-half of the next layer's reduction
-  unsigned int *wait_ctr0 = cp.counters + (size_t)(blockIdx.y * 2 + z) * FT_CTR_STRIDE;
-  // the counter this CTA arrives on: its batch tile, the k-half its features belong to
-  unsigned int *arrive_ctr0 = cp.counters + (size_t)(blockIdx.y * 2 + (blockIdx.x >= gridDim.x / 2 ? 1 : 0)) * FT_CTR_STRIDE;
+  const uint32_t z = blockIdx.z;                     // k-slice of this CTA == its rank in the (1,1,S) cluster
+  const unsigned int G = gridDim.x;                  // arrivals per barrier: gridDim.x/S feature tiles x S k-slices
+  // the counter this CTA waits on: its batch tile, ITS k-slice of the next layer's reduction
+  unsigned int *wait_ctr0 = cp.counters + (size_t)(blockIdx.y * S + z) * FT_CTR_STRIDE;
+  // the counter this CTA arrives on: its batch tile, the k-slice its features belong to
+  unsigned int *arrive_ctr0 = cp.counters + (size_t)(blockIdx.y * S + blockIdx.x / (gridDim.x / S)) * FT_CTR_STRIDE;
   const int P = cp.num_passes;
 
   if (warp == 0 && lane == 0) {
@@ -1370,7 +1377,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) mlp_chain_ft2_kernel(const __gr
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(acc_full + 8 * b, 1);
       ptx::mbar_init(acc_free + 8 * b, 8);           // one arrival per finisher and per sender warp
-      ptx::mbar_init(xchg_full + 8 * b, 1);          // one expect_tx arrival (mine); the peer's st.async bytes complete it
+      ptx::mbar_init(xchg_full + 8 * b, 1);          // one expect_tx arrival (mine); the peers' st.async bytes complete it
       ptx::mbar_init(recv_free + 8 * b, 4);          // one arrival per finisher warp
     }
     ptx::fence_mbar_init();
@@ -1504,7 +1511,6 @@ __global__ void __launch_bounds__(F2_THREADS, 1) mlp_chain_ft2_kernel(const __gr
     const int q = warp & 3;
     const int f = 16 * q + (lane & 15);
     const bool active = lane < 16;
-    const uint32_t peer = z ^ 1u;
     if (warp == 10) {
       // ===== arriver: publishes a pass's output for the finishers (they only bar.arrive), so the ~1100-clk gpu-scope
       // fence is off their critical path =====
@@ -1525,8 +1531,11 @@ __global__ void __launch_bounds__(F2_THREADS, 1) mlp_chain_ft2_kernel(const __gr
         const uint32_t par = p & 1;
         ptx::mbar_wait(acc_full + 8 * par, (p >> 1) & 1);
         ptx::tc_fence_after_sync();
-        uint32_t oth[32];
-        ptx::tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + par * F2_N + 32 * peer, oth);
+        uint32_t oth[S - 1][32];
+#pragma unroll
+        for (int r = 1; r < S; ++r)                   // the 32 columns (rows of the tile) owned by cluster rank z ^ r
+          ptx::tmem_ld_32x32(tmem_acc + (static_cast<uint32_t>(q * 32) << 16) + par * F2_N + 32 * (z ^ (uint32_t)r),
+                             oth[r - 1]);
         ptx::tmem_ld_wait();
         ptx::tc_fence_before_sync();
         __syncwarp();
@@ -1539,12 +1548,16 @@ __global__ void __launch_bounds__(F2_THREADS, 1) mlp_chain_ft2_kernel(const __gr
         if (active) {
           // st.async: every 16-byte store carries its own completion (complete_tx on the peer's barrier); a
           // release.cluster arrive after plain st.shared::cluster stores cost ~3000 clk per pass here
-          const uint32_t remote = ptx::mapa(smem_recv + par * F2_RECV_BYTES + (uint32_t)f * 128u, peer);
-          const uint32_t remote_bar = ptx::mapa(xchg_full + 8 * par, peer);
 #pragma unroll
-          for (int j = 0; j < 8; ++j)                  // 16-byte chunks XOR-swizzled by the feature: no bank conflicts
-            ptx::st_async_v4(remote + (uint32_t)((j ^ (f & 7)) << 4), remote_bar, oth[4 * j], oth[4 * j + 1],
-                             oth[4 * j + 2], oth[4 * j + 3]);
+          for (int r = 1; r < S; ++r) {
+            const uint32_t peer = z ^ (uint32_t)r;     // the peer files my partial under slot r - 1 (it sees me as peer ^ r)
+            const uint32_t remote = ptx::mapa(smem_recv + (par * (S - 1) + (r - 1)) * F2_RECV_BYTES + (uint32_t)f * 128u, peer);
+            const uint32_t remote_bar = ptx::mapa(xchg_full + 8 * par, peer);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)                // 16-byte chunks XOR-swizzled by the feature: no bank conflicts
+              ptx::st_async_v4(remote + (uint32_t)((j ^ (f & 7)) << 4), remote_bar, oth[r - 1][4 * j],
+                               oth[r - 1][4 * j + 1], oth[r - 1][4 * j + 2], oth[r - 1][4 * j + 3]);
+          }
         }
         if (threadIdx.x == 192) ft_stamp_pass(cp.trace, p, 2);
       }
@@ -1571,22 +1584,26 @@ __global__ void __launch_bounds__(F2_THREADS, 1) mlp_chain_ft2_kernel(const __gr
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(acc_free + 8 * par);
-        const uint32_t recv = smem_recv + par * F2_RECV_BYTES + (uint32_t)f * 128u;    // this feature's 32 f32
-        if (threadIdx.x == ep_tid0) ptx::mbar_arrive_expect_tx(xchg_full + 8 * par, F2_RECV_BYTES);
+        const uint32_t recv = smem_recv + par * (S - 1) * F2_RECV_BYTES + (uint32_t)f * 128u;   // this feature's 32 f32
+        if (threadIdx.x == ep_tid0) ptx::mbar_arrive_expect_tx(xchg_full + 8 * par, (S - 1) * F2_RECV_BYTES);
         ptx::mbar_wait(xchg_full + 8 * par, (p >> 1) & 1);
         if (threadIdx.x == ep_tid0) ft_stamp_pass(cp.trace, p, 0);
         float v[32];
         if (active) {
+          // partial of k-slice z ^ r sits in slot r - 1; summation order own + (z^1) + (z^2) + (z^3): fixed per CTA,
+          // hence deterministic (S = 2: IEEE addition is commutative, both CTAs of a pair even round identically)
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 t;
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(recv + (uint32_t)((j ^ (f & 7)) << 4)));
-            // (k-half 0) + (k-half 1): IEEE addition is commutative, so both CTAs of a pair round identically
-            v[4 * j] = __uint_as_float(own[4 * j]) + t.x;
-            v[4 * j + 1] = __uint_as_float(own[4 * j + 1]) + t.y;
-            v[4 * j + 2] = __uint_as_float(own[4 * j + 2]) + t.z;
-            v[4 * j + 3] = __uint_as_float(own[4 * j + 3]) + t.w;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(own[j]);
+#pragma unroll
+          for (int r = 1; r < S; ++r) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 t;
+              asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                           : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                           : "r"(recv + (uint32_t)((r - 1) * F2_RECV_BYTES) + (uint32_t)((j ^ (f & 7)) << 4)));
+              v[4 * j] += t.x; v[4 * j + 1] += t.y; v[4 * j + 2] += t.z; v[4 * j + 3] += t.w;
+            }
           }
         }
         __syncwarp();
@@ -2095,21 +2112,29 @@ static bool chain_ft_supported(const KernelDesc *const *descs, const GemmArgs *a
   return true;
 }
 
-// split-K-2 variant (mlp_chain_ft2_kernel): 64-row batch tiles, an even number of feature tiles, and a reduction whose
-// halves are whole TMA boxes of two k-blocks
-static bool chain_ft2_supported(const KernelDesc *const *descs, const GemmArgs *args, int L) {
-  static const bool off = [] { const char *e = getenv("TPP_XSMM_CHAIN_SPLIT"); return e && e[0] == '1'; }();
-  if (off) return false;
+// split-K variants (mlp_chain_fts_kernel<S>): 32 S-row batch tiles, a multiple of S feature tiles, and a reduction
+// whose S slices are made of whole TMA boxes. Returns the largest usable S in {4, 2}, or 1.
+static int chain_ft_split(const KernelDesc *const *descs, const GemmArgs *args, int L) {
+  // S = 4 is implemented and parity-clean but slower than S = 2 (7.97 vs 5.71 us per forward): its 24 KiB of st.async
+  // pushes per pass move at ~8 B/clk and become the bound. TPP_XSMM_CHAIN_SPLIT=4 enables it, =1 disables split-K.
+  static const int max_split = [] { const char *e = getenv("TPP_XSMM_CHAIN_SPLIT"); return e ? atoi(e) : 2; }();
   const KernelDesc &d0 = *descs[0];
-  if ((d0.m % F2_N) != 0 || (d0.n % (2 * FT_M)) != 0) return false;
-  if ((d0.m / F2_N) * (d0.n / FT_M) * 2 > 148) return false;
-  for (int l = 0; l < L; ++l) {
-    const int64_t k_iters = descs[l]->k / BLOCK_K;
-    if (!(k_iters == 1 || (k_iters % 2) == 0)) return false;
-    if (k_iters > F2_KB && (k_iters % F2_KB) != 0) return false;   // a k-half is whole batch elements or divides one
-    if (k_iters < F2_KB && (F2_KB % k_iters) != 0) return false;
+  for (int S = 4; S >= 2; S /= 2) {
+    if (S > max_split) continue;
+    const int rows = 32 * S, kb = FT_KB / S, group = kb / 4;
+    if ((d0.m % rows) != 0 || ((d0.n / FT_M) % S) != 0) continue;
+    if ((d0.m / rows) * (d0.n / FT_M) * S > 148) continue;
+    bool ok = true;
+    for (int l = 0; l < L && ok; ++l) {
+      const int64_t k_iters = descs[l]->k / BLOCK_K;
+      if (!(k_iters == 1 || (k_iters % group) == 0)) ok = false;            // a box = `group` k-blocks of one batch element
+      if (k_iters > kb && (k_iters % kb) != 0) ok = false;                   // a k-slice divides a batch element ...
+      if (k_iters < kb && (kb % k_iters) != 0) ok = false;                   // ... or is whole batch elements
+    }
+    (void)args;
+    if (ok) return S;
   }
-  return true;
+  return 1;
 }
 
 namespace {
@@ -2142,7 +2167,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   if (num_chains < 1 || !chain_ft_supported(descs + first[0], args + first[0], len[0])) return 0;
   static const bool multi_off = [] { const char *e = getenv("TPP_XSMM_CHAIN_MULTI"); return e && e[0] == '0'; }();
   const KernelDesc &d0 = *descs[first[0]];
-  const bool split2 = chain_ft2_supported(descs + first[0], args + first[0], len[0]);
+  int split = chain_ft_split(descs + first[0], args + first[0], len[0]);
   // ---- which chains go into this launch ----
   int take = 1, passes = len[0];
   {
@@ -2153,7 +2178,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
       const KernelDesc &d = *descs[first[c]];
       if (d.m != d0.m || d.n != d0.n || passes + len[c] > FT_MAX_PASSES) break;
       if (!chain_ft_supported(descs + first[c], args + first[c], len[c])) break;
-      if (split2 && !chain_ft2_supported(descs + first[c], args + first[c], len[c])) break;
+      if (chain_ft_split(descs + first[c], args + first[c], len[c]) != split) break;
       std::vector<ByteRange> in, out;
       chain_ranges(descs + first[c], args + first[c], len[c], in, out);
       bool indep = true;
@@ -2170,6 +2195,10 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
       ++take;
     }
   }
+  // one or two chains per launch have nothing to hide the exchange latency behind: the full-K kernel is faster there
+  // (11.0 vs 14.7 us for a single forward); every split-K shape is also a full-K shape
+  if (take < 3) split = 1;
+  const bool split2 = split > 1;
   // ---- the pass list: `ways` chains at a time interleaved layer by layer; a chain's counter slot is its position in
   // the tuple. One chain's layer-to-layer latency (store, fence, counter, poll, TMA: ~5000 clk) is longer than one
   // pass (~3000-4000 clk), so three chains are needed to keep the tensor pipe busy. ----
@@ -2191,10 +2220,10 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     FtPass &ps = cp.pass[np];
     const uint64_t nb = (uint64_t)g.batch;
     const uint32_t k_iters = (uint32_t)(d.k / BLOCK_K);
-    const uint32_t grp = split2 ? F2_GROUP : FT_GROUP;
+    const uint32_t grp = split == 4 ? FS<4>::GROUP : split == 2 ? FS<2>::GROUP : FT_GROUP;
     const uint32_t gk = k_iters >= grp ? grp : k_iters, gb = grp / gk;   // box = gk k-blocks x gb batch elements
     if (!encode_map_x4(&ps.tmX, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a,
-                       split2 ? F2_N : FT_N, gk, gb) ||
+                       32 * split, gk, gb) ||
         !encode_map(&ps.tmW, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, FT_M,
                     BLOCK_K * gk, gb))
       return false;
@@ -2229,12 +2258,12 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     warned = true;
     return 0;
   }
-  dim3 grid((unsigned)(d0.n / FT_M), (unsigned)(d0.m / (split2 ? F2_N : FT_N)), split2 ? 2u : 1u);
+  dim3 grid((unsigned)(d0.n / FT_M), (unsigned)(d0.m / (32 * split)), (unsigned)split);
   const int n_ctas = (int)(grid.x * grid.y * grid.z);
   StreamScratch &sc = scratch_for(stream);
   // one counter array per (variant, group size G = grid.x): every counter stays a multiple of G between launches;
   // the split-K-2 variant's launch epoch (+ exit ticket) lives behind its counters
-  const int ctr_key = (int)grid.x | (split2 ? 0x10000 : 0);
+  const int ctr_key = (int)grid.x | (split << 16);
   unsigned int *counters = nullptr;
   for (auto &e : sc.ft_counters)
     if (e.first == ctr_key) counters = e.second;
@@ -2256,12 +2285,12 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   static const bool pf = [] { const char *e = getenv("TPP_XSMM_CHAIN_PROXY_FENCE"); return e && e[0] == '1'; }();
   cp.proxy_fence = pf ? 1 : 0;
   constexpr int smem1 = FT_KB * (FT_X_BYTES + FT_W_BYTES) + (3 * FT_NG + 4) * 8 + 16 + 1024;
-  constexpr int smem2 = F2_KB * (F2_X_BYTES + FT_W_BYTES) + 2 * F2_RECV_BYTES + (3 * F2_NG + 8) * 8 + 16 + 1024;
-  const int smem = split2 ? smem2 : smem1;
+  const int smem = split == 4 ? FS<4>::SMEM : split == 2 ? FS<2>::SMEM : smem1;
   static std::once_flag once;
   std::call_once(once, [] {
     TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_ft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
-    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_ft2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_fts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS<2>::SMEM));
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_fts_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS<4>::SMEM));
   });
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
@@ -2282,7 +2311,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     attrs[1].id = cudaLaunchAttributeClusterDimension;
     attrs[1].val.clusterDim.x = 1;
     attrs[1].val.clusterDim.y = split2 ? 1 : 2;
-    attrs[1].val.clusterDim.z = split2 ? 2 : 1;
+    attrs[1].val.clusterDim.z = split2 ? (unsigned)split : 1;
     cfg.numAttrs = 2;
   }
   static const bool trace_on = [] { const char *e = getenv("TPP_XSMM_TC_TRACE"); return e && atoi(e) == 3; }();
@@ -2296,9 +2325,10 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     g_chain_trace_layers = np;
     g_chain_trace_ft = true;
   }
-  if (split2) TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_ft2_kernel, cp));
+  if (split == 4) TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_fts_kernel<4>, cp));
+  else if (split == 2) TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_fts_kernel<2>, cp));
   else TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_ft_kernel, cp));
-  const char *tile = split2 ? "ft64x64_splitk2" : "ft64x32_fullk";
+  const char *tile = split == 4 ? "ft64x128_splitk4" : split == 2 ? "ft64x64_splitk2" : "ft64x32_fullk";
   if (take == 1) snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dlayers_%s", len[0], tile);
   else snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dx%dlayers_%s", take, len[0], tile);
   return take;
