@@ -298,7 +298,8 @@ def main():
     barrier()
     t_wall1 = time.perf_counter()
     launches = xsmm.launch_count() - launches0
-    timed_kernel = xsmm.last_kernel()   # the kernel the timed loop launched (graph mode: the fused chain kernel)
+    run(num_sets)                       # exactly one rotation: the name of the kernel the timed loop is made of
+    timed_kernel = xsmm.last_kernel()   # (graph mode: the fused multi-chain kernel; leftover steps run single chains)
     sampler.stop()
     ms = ev0.elapsed_time(ev1)
     ms_max = shard.max_over_ranks(ms, device=dev)
@@ -454,8 +455,9 @@ def main():
                      "kernel": timed_kernel, "peak_source": pk["source"] + ", burst",
                      "flops_per_launch": flops_per_launch, "avg_launch_us": avg_launch_s * 1e6,
                      "forward_passes_per_launch": args.steps / max(launches, 1),
-                     "note": "batch 256 is latency/delivery-bound, not tensor-bound: per pass and SM 192 KiB of operands "
-                             "arrive at ~50 B/clk (DESIGN.md 4.1c); traffic = DRAM bytes of one launch (ncu)"},
+                     "note": "batch 256 is delivery-bound, not tensor-bound: per layer pass every SM has to receive "
+                             "128 KiB of operands at ~50 B/clk (DESIGN.md 4.1c); traffic = DRAM bytes of one launch "
+                             "(ncu, profiles/ncu_mlp_chain_fts_r1.json)"},
         "cpu_baseline": cpu,
         "extra": {"ms_per_step_hot_l2": ms_hot, "gflops_hot_l2": flops_step_rank * n_gpus / (ms_hot * 1e-3) / 1e9,
                   "host_issue_us_per_launch": t_issue / max(launches, 1) * 1e6,
