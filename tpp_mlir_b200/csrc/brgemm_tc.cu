@@ -1645,6 +1645,259 @@ __global__ void __launch_bounds__(F2_THREADS, 1) mlp_chain_fts_kernel(const __gr
   }
 }
 
+// ---- pair-per-chain kernel: one CTA pair runs a whole layer chain, many chains side by side ---------------------------
+// Third design of the fused chain, for launches that carry MANY independent chains (a captured graph of the
+// benchmark's rotating operand sets, a batch of requests, or the 256-row blocks of a large-batch MLP: rows are
+// independent through all layers). The pass kernels above spread ONE layer over 128 SMs in 64 x 64 tiles: every SM then
+// receives 128 KiB of operands per layer pass, 16 MiB per layer over all SMs for 2.5 MiB of unique data, and the
+// chip-wide L2 -> SM throughput (~6300 B/clk) bounds a pass at ~2700 clk no matter how the latencies are hidden.
+// Here a work item (one chain x one block of 256 batch rows) belongs to ONE pair of CTAs (two SMs of a TPC,
+// tcgen05.mma.cta_group::2, M = 256) which walks the layers and, per layer, the 256-column output tiles:
+//   * per tile and k-block each CTA stages its 128 activation rows (16 KiB) and HALF of the 256 weight columns (16 KiB);
+//     a layer costs 4 MiB of L2 -> SM traffic per item instead of 16 MiB, every weight byte is fetched exactly once;
+//   * CTA r only ever reads the activation rows it wrote itself (rows 128 r .. 128 r + 127 of the item), so a layer
+//     boundary needs no cross-SM synchronisation at all: the CTA's epilogue warps fence their stores and arrive on a
+//     LOCAL mbarrier, the CTA's producer waits on it before the next layer's first activation box. No counters, no
+//     co-residency assumption, nothing to spin on across SMs;
+//   * the next layer's weights do not depend on anything: their boxes for the first ring slots are issued BEFORE that
+//     wait (same mbarrier, expect_tx covers both operands), so the HBM latency of the weights hides behind the last
+//     epilogue of the previous layer;
+//   * TMEM holds two 256-column accumulators: the epilogue of tile t (tcgen05.ld -> bias -> ReLU -> bf16 -> 16-byte
+//     stores) runs under the MMAs of tile t + 1;
+//   * pairs are independent: the grid is min(items, 74) pairs, pair p takes items p, p + pairs, ...
+// Layer descriptors (two tensor maps + epilogue parameters per layer) live in a device table written once at capture.
+constexpr int PC_STAGES = 6;
+constexpr int PC_BLOCK_N = 256;                       // output columns per tile (UMMA N)
+constexpr int PC_HALF_N = PC_BLOCK_N / 2;             // weight columns staged by each CTA
+constexpr int PC_W_CHUNKS = PC_HALF_N / 64;           // 64-column TMA boxes per CTA and k-block
+constexpr int PC_STAGE_BYTES = A_STAGE_BYTES + PC_W_CHUNKS * B_CHUNK_BYTES;   // 32 KiB
+constexpr int PC_ROWS = 2 * BLOCK_M;                  // batch rows per work item
+constexpr int PC_SMEM = PC_STAGES * PC_STAGE_BYTES + (2 * PC_STAGES + 5) * 8 + 16 + 1024;
+
+struct alignas(128) PcLayer {
+  CUtensorMap tmX;          // activations: (k, row, batch element), box 64 x 128
+  CUtensorMap tmW;          // weights: (n, k, batch element), box 64 x 64
+  void *C;
+  const void *D;            // bias vector or nullptr
+  int64_t ldc;
+  int32_t k_iters;          // k-blocks per batch element
+  int32_t total_iters;      // batch x k_iters
+  int32_t n_tiles;          // n / 256
+  int32_t n;
+  int32_t relu;
+  int32_t pad[3];
+};
+struct PcItem {
+  int32_t layer0, num_layers, row0, pad;
+};
+struct PcParams {
+  const PcLayer *layers;
+  const PcItem *items;
+  int32_t num_items;
+};
+
+__device__ __forceinline__ void tensormap_acquire(const void *map) {
+  // the table was written by a host copy: make it visible to the tensor-map proxy of this SM before the first use
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const PcParams cp) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;                                       // PC_STAGES x 16 KiB
+  const uint32_t smem_w = smem_base + PC_STAGES * A_STAGE_BYTES;           // PC_STAGES x 2 x 8 KiB
+  const uint32_t bar_base = smem_w + PC_STAGES * PC_W_CHUNKS * B_CHUNK_BYTES;
+  const uint32_t full_bar = bar_base;                                      // leader's: both CTAs' bytes land on it
+  const uint32_t empty_bar = bar_base + PC_STAGES * 8;                     // per CTA, released by the pair's MMA commits
+  const uint32_t acc_full = bar_base + 2 * PC_STAGES * 8;                  // [2] per CTA: accumulator complete
+  const uint32_t acc_free = acc_full + 16;                                 // [2] leader's: both epilogues have read it out
+  const uint32_t layer_done = acc_free + 16;                               // per CTA: my rows of the layer output are stored
+  const uint32_t tmem_slot = layer_done + 8;
+  uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t peer = ptx::cluster_ctarank();       // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < PC_STAGES; ++s) {
+      ptx::mbar_init(full_bar + 8 * s, 1);
+      ptx::mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(acc_full + 8 * b, 1);
+      ptx::mbar_init(acc_free + 8 * b, 8);            // one arrival per epilogue warp of both CTAs
+    }
+    ptx::mbar_init(layer_done, 4);                    // one arrival per epilogue warp
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, 2 * PC_BLOCK_N);  // all 512 columns: two accumulators
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before_sync();
+  __syncwarp();
+  ptx::cluster_arrive();   // both CTAs' barriers and TMEM exist before any remote signal / pair MMA
+  ptx::cluster_wait();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own rows / own weight columns into own smem, bytes counted on the LEADER =====
+    if (lane == 0) {
+      const uint32_t leader_full = ptx::mapa(full_bar, 0);
+      int s = 0;
+      uint32_t ph = 0, layer_ph = 0;
+      for (int item = pair; item < cp.num_items; item += num_pairs) {
+        const PcItem it = cp.items[item];
+        const int32_t row0 = it.row0 + (int32_t)peer * BLOCK_M;
+        for (int l = 0; l < it.num_layers; ++l) {
+          const PcLayer *L = cp.layers + it.layer0 + l;
+          tensormap_acquire(&L->tmX);
+          tensormap_acquire(&L->tmW);
+          const int32_t k_iters = L->k_iters, total = L->total_iters, n_tiles = L->n_tiles;
+          const int32_t pre = total < PC_STAGES ? total : PC_STAGES;
+          for (int32_t j = 0; j < n_tiles; ++j) {
+            const int32_t wcol = j * PC_BLOCK_N + (int32_t)peer * PC_HALF_N;
+            const bool defer = (l > 0 && j == 0);     // the activations are the previous layer's output
+            int32_t b = 0, kb = 0;
+            for (int32_t i = 0; i < total; ++i) {
+              ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
+              if (peer == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2 * PC_STAGE_BYTES);   // both CTAs' bytes
+#pragma unroll
+              for (int c = 0; c < PC_W_CHUNKS; ++c)
+                ptx::tma_load_3d_pair(smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES, &L->tmW, leader_full + 8 * s,
+                                      wcol + c * 64, kb * BLOCK_K, b);
+              if (!(defer && i < pre))
+                ptx::tma_load_3d_pair(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, kb * BLOCK_K, row0, b);
+              if (defer && i == pre - 1) {
+                // my rows of the previous layer's output are stored and fenced: now the activation boxes of the
+                // `pre` slots whose weights are already in flight
+                ptx::mbar_wait(layer_done, layer_ph);
+                layer_ph ^= 1;
+                int ss = s - (pre - 1);
+                if (ss < 0) ss += PC_STAGES;
+                int32_t bb = 0, kk = 0;
+                for (int32_t t = 0; t < pre; ++t) {
+                  ptx::tma_load_3d_pair(smem_a + ss * A_STAGE_BYTES, &L->tmX, leader_full + 8 * ss, kk * BLOCK_K, row0, bb);
+                  if (++ss == PC_STAGES) ss = 0;
+                  if (++kk == k_iters) { kk = 0; ++bb; }
+                }
+              }
+              if (++kb == k_iters) { kb = 0; ++b; }
+              if (++s == PC_STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader only =====
+    if (lane == 0 && peer == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(PC_ROWS, PC_BLOCK_N, /*A K-major*/ 0, /*B MN-major*/ 1);
+      const uint16_t pair_mask = 3;
+      int s = 0;
+      uint32_t ph = 0, t = 0;
+      for (int item = pair; item < cp.num_items; item += num_pairs) {
+        const PcItem it = cp.items[item];
+        for (int l = 0; l < it.num_layers; ++l) {
+          const PcLayer *L = cp.layers + it.layer0 + l;
+          const int32_t total = L->total_iters, n_tiles = L->n_tiles;
+          for (int32_t j = 0; j < n_tiles; ++j, ++t) {
+            const uint32_t buf = t & 1;
+            if (t >= 2) {                              // both epilogues have read tile t - 2 out of this accumulator
+              ptx::mbar_wait_cluster(acc_free + 8 * buf, ((t >> 1) - 1) & 1);
+              ptx::tc_fence_after_sync();
+            }
+            const uint32_t acc = tmem_acc + buf * PC_BLOCK_N;
+            for (int32_t i = 0; i < total; ++i) {
+              ptx::mbar_wait(full_bar + 8 * s, ph);
+              ptx::tc_fence_after_sync();
+              const uint32_t a_addr = smem_a + s * A_STAGE_BYTES;
+              const uint32_t b_addr = smem_w + s * PC_W_CHUNKS * B_CHUNK_BYTES;
+#pragma unroll
+              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                const uint64_t da = ptx::umma_smem_desc_sw128(a_addr + kk * (UMMA_K * 2), 16, 1024);
+                const uint64_t db = ptx::umma_smem_desc_sw128(b_addr + kk * (UMMA_K * 128), B_CHUNK_BYTES, 1024);
+                ptx::umma_bf16_pair(acc, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+              }
+              ptx::umma_commit_pair(empty_bar + 8 * s, pair_mask);   // frees the slot in both CTAs
+              if (++s == PC_STAGES) { s = 0; ph ^= 1; }
+            }
+            ptx::umma_commit_pair(acc_full + 8 * buf, pair_mask);    // both epilogues may start
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs, each on its own 128 rows / TMEM lanes) =====
+    const int q = warp & 3;
+    const uint32_t leader_acc_free = ptx::mapa(acc_free, 0);
+    const uint32_t lane_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t t = 0;
+    for (int item = pair; item < cp.num_items; item += num_pairs) {
+      const PcItem it = cp.items[item];
+      const int64_t row = (int64_t)it.row0 + (int64_t)peer * BLOCK_M + q * 32 + lane;
+      for (int l = 0; l < it.num_layers; ++l) {
+        const PcLayer *L = cp.layers + it.layer0 + l;
+        TcParams p;
+        p.C = L->C;
+        p.D = L->D;
+        p.ldc = L->ldc;
+        p.n = L->n;
+        p.m = row + 1;
+        p.beta0 = 1;
+        p.bin_kind = L->D ? 1 : 0;
+        p.bin_mode = kBcastCol;
+        p.relu = L->relu;
+        p.c_vec_ok = 1;
+        const int32_t n_tiles = L->n_tiles;
+        for (int32_t j = 0; j < n_tiles; ++j, ++t) {
+          const uint32_t buf = t & 1;
+          ptx::mbar_wait(acc_full + 8 * buf, (t >> 1) & 1);
+          ptx::tc_fence_after_sync();
+#pragma unroll 1
+          for (int c = 0; c < PC_BLOCK_N; c += 32) {
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(lane_addr + buf * PC_BLOCK_N + c, r);
+            ptx::tmem_ld_wait();
+            if (c == PC_BLOCK_N - 32) {               // the accumulator is in registers: hand it back to the MMA issuer
+              ptx::tc_fence_before_sync();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive_remote(leader_acc_free + 8 * buf);
+            }
+            float v[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+            epilogue_store<32>(v, p, row, (int64_t)j * PC_BLOCK_N + c);
+          }
+        }
+        if (l + 1 < it.num_layers) {
+          // this warp's rows of the layer output: visible at L2 (where TMA reads) before the producer is told
+          __threadfence();
+          asm volatile("fence.proxy.async;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(layer_done);
+        }
+      }
+    }
+  }
+
+  // the peer must not exit (nor free TMEM) while the leader's MMAs still read its shared memory / write its TMEM
+  ptx::tc_fence_before_sync();
+  __syncwarp();
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_pair(tmem_acc, 2 * PC_BLOCK_N);
+  }
+}
+
 // ---- host side ----------------------------------------------------------------
 
 constexpr int kTraceRing = 128, kTraceRingCtas = 256;
@@ -2331,6 +2584,146 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   const char *tile = split == 4 ? "ft64x128_splitk4" : split == 2 ? "ft64x64_splitk2" : "ft64x32_fullk";
   if (take == 1) snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dlayers_%s", len[0], tile);
   else snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dx%dlayers_%s", take, len[0], tile);
+  return take;
+}
+
+// ---- pair-per-chain launch ---------------------------------------------------------------------------------------------
+namespace {
+thread_local std::vector<void *> t_capture_allocs;   // device tables baked into the graph being captured
+cudaStream_t table_stream() {
+  thread_local cudaStream_t st = nullptr;
+  if (!st) TPP_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  return st;
+}
+bool chain_pair_supported(const KernelDesc *const *descs, const GemmArgs *args, int L) {
+  const KernelDesc &d0 = *descs[0];
+  if ((d0.m % PC_ROWS) != 0 || (d0.n % PC_BLOCK_N) != 0 || d0.m > (1 << 30) || d0.n > (1 << 30)) return false;
+  for (int l = 0; l < L; ++l) {
+    const KernelDesc &d = *descs[l];
+    if ((d.k % BLOCK_K) != 0 || args[l].batch < 1 || (d.ldc % 8) != 0) return false;
+    if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && args[l].D == nullptr) return false;
+    if (d.op == OpClass::FusedBrgemm && d.unary_kind != 0 && d.unary_kind != 5) return false;
+  }
+  return true;
+}
+}  // namespace
+
+void brgemm_tc_take_capture_allocs(std::vector<void *> &out) {
+  out.insert(out.end(), t_capture_allocs.begin(), t_capture_allocs.end());
+  t_capture_allocs.clear();
+}
+
+// Launch a prefix of chains [0, num_chains) as ONE launch of mlp_chain_pair_kernel: every chain is cut into blocks of
+// 256 batch rows, every block is a work item of one CTA pair. Taken only when the launch carries enough items to
+// occupy a useful share of the 74 pairs (a single pair needs ~50 us for a 3 x 1024^2 chain; the pass kernels above
+// finish a lone chain in ~11 us). Returns the number of chains launched (0: not applicable).
+int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *args, const int *first, const int *len,
+                              int num_chains, cudaStream_t stream) {
+  static const int min_items = [] {
+    const char *e = getenv("TPP_XSMM_CHAIN_PAIR_MIN");   // 0 disables the kernel
+    return e ? atoi(e) : 12;
+  }();
+  if (min_items <= 0 || num_chains < 1) return 0;
+  int take = 0;
+  int64_t items = 0, layers = 0;
+  {
+    std::vector<ByteRange> in_all, out_all;
+    while (take < num_chains) {
+      const int c = take;
+      if (!chain_pair_supported(descs + first[c], args + first[c], len[c])) break;
+      std::vector<ByteRange> in, out;
+      chain_ranges(descs + first[c], args + first[c], len[c], in, out);
+      bool indep = true;
+      for (const ByteRange &o : out) {
+        for (const ByteRange &x : in_all) indep = indep && !overlaps(o, x);
+        for (const ByteRange &x : out_all) indep = indep && !overlaps(o, x);
+      }
+      for (const ByteRange &i : in)
+        for (const ByteRange &x : out_all) indep = indep && !overlaps(i, x);
+      if (!indep) break;
+      in_all.insert(in_all.end(), in.begin(), in.end());
+      out_all.insert(out_all.end(), out.begin(), out.end());
+      items += descs[first[c]]->m / PC_ROWS;
+      layers += len[c];
+      ++take;
+    }
+  }
+  if (take == 0 || items < min_items) return 0;
+  std::vector<PcLayer> hl((size_t)layers);
+  std::vector<PcItem> hi((size_t)items);
+  size_t nl = 0, ni = 0;
+  for (int c = 0; c < take; ++c) {
+    const int32_t layer0 = (int32_t)nl;
+    for (int l = 0; l < len[c]; ++l) {
+      const KernelDesc &d = *descs[first[c] + l];
+      const GemmArgs &g = args[first[c] + l];
+      PcLayer &pl = hl[nl++];
+      memset(&pl, 0, sizeof(pl));
+      const uint64_t nb = (uint64_t)g.batch;
+      if (!encode_map(&pl.tmX, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, BLOCK_K,
+                      BLOCK_M) ||
+          !encode_map(&pl.tmW, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, 64, BLOCK_K))
+        return 0;
+      pl.C = g.C;
+      pl.D = (d.op == OpClass::FusedBrgemm && g.D && d.binary_kind == 1) ? g.D : nullptr;
+      pl.ldc = d.ldc;
+      pl.k_iters = (int32_t)(d.k / BLOCK_K);
+      pl.total_iters = (int32_t)(g.batch * (d.k / BLOCK_K));
+      pl.n_tiles = (int32_t)(d.n / PC_BLOCK_N);
+      pl.n = (int32_t)d.n;
+      pl.relu = (d.op == OpClass::FusedBrgemm && d.unary_kind == 5) ? 1 : 0;
+    }
+    for (int64_t r = 0; r < descs[first[c]]->m; r += PC_ROWS) {
+      PcItem &pi = hi[ni++];
+      pi.layer0 = layer0;
+      pi.num_layers = len[c];
+      pi.row0 = (int32_t)r;
+      pi.pad = 0;
+    }
+  }
+  // the table is written now (not captured): a graph replay only launches the kernel that reads it
+  const size_t lbytes = hl.size() * sizeof(PcLayer), ibytes = (hi.size() * sizeof(PcItem) + 127) & ~(size_t)127;
+  char *table = nullptr;
+  TPP_CUDA_CHECK(cudaMalloc(&table, lbytes + ibytes));
+  TPP_CUDA_CHECK(cudaMemcpyAsync(table, hl.data(), lbytes, cudaMemcpyHostToDevice, table_stream()));
+  TPP_CUDA_CHECK(cudaMemcpyAsync(table + lbytes, hi.data(), hi.size() * sizeof(PcItem), cudaMemcpyHostToDevice, table_stream()));
+  TPP_CUDA_CHECK(cudaStreamSynchronize(table_stream()));
+  t_capture_allocs.push_back(table);
+  PcParams cp;
+  cp.layers = reinterpret_cast<const PcLayer *>(table);
+  cp.items = reinterpret_cast<const PcItem *>(table + lbytes);
+  cp.num_items = (int32_t)items;
+  static const int max_pairs = [] {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char *e = getenv("TPP_XSMM_CHAIN_PAIRS");
+    const int p = e ? atoi(e) : sms / 2;
+    return p < 1 ? 1 : p;
+  }();
+  // balanced: the fewest pairs that still need the minimal number of rounds
+  const int rounds = (int)((items + max_pairs - 1) / max_pairs);
+  const int pairs = (int)((items + rounds - 1) / rounds);
+  static std::once_flag once;
+  std::call_once(once, [] {
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM));
+  });
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = PC_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = 2;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_pair_kernel, cp));
+  snprintf(t_last_name, sizeof(t_last_name), "mlp_chain_bf16_%dx%dlayers_pair256x256", (int)items, len[0]);
   return take;
 }
 

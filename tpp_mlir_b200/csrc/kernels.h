@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <vector>
 
 #include "kernel_desc.h"
 
@@ -65,6 +66,12 @@ bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, i
 // launched (a prefix), 0 if the kernel does not apply
 int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args, const int *first, const int *len,
                             int num_chains, cudaStream_t stream);
+// same contract, for launches that carry many independent chains: one CTA pair (cta_group::2, 256 x 256 tiles) walks a
+// whole chain for a block of 256 batch rows; taken when the prefix has at least TPP_XSMM_CHAIN_PAIR_MIN (12) such blocks
+int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *args, const int *first, const int *len,
+                              int num_chains, cudaStream_t stream);
+// device tables allocated by chain launches since the last call (owned by the graph being captured)
+void brgemm_tc_take_capture_allocs(std::vector<void *> &out);
 const char *brgemm_tc_last_name();   // tile configuration of this thread's last tcgen05 launch
 void brgemm_tc_dump_trace();   // debug, TPP_XSMM_TC_TRACE=2
 

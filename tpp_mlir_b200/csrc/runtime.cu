@@ -126,6 +126,7 @@ struct GraphHandle {
   cudaGraphExec_t exec = nullptr;
   int64_t launches = 0;         // kernels per replay (for xsmm_cuda_launch_count)
   char last_kernel[96] = {0};   // name of the last kernel captured (what xsmm_cuda_last_kernel reports after a replay)
+  std::vector<void *> device_allocs;   // descriptor tables the captured kernels read (freed with the graph)
 };
 thread_local ThreadCtx t_ctx;
 
@@ -458,8 +459,12 @@ void flush_pending() {
     // a run of consecutive chains: as many as possible in one launch of the feature-major kernel
     size_t run = sidx;
     while (run < seg_first.size() && seg_len[run] > 1) ++run;
-    int took = launch_brgemm_chains_ft(descs.data(), args.data(), seg_first.data() + sidx, seg_len.data() + sidx,
-                                       (int)(run - sidx), stream);
+    // many independent chains: one CTA pair per chain (4x less L2 -> SM traffic per layer than the pass kernels)
+    int took = launch_brgemm_chains_pair(descs.data(), args.data(), seg_first.data() + sidx, seg_len.data() + sidx,
+                                         (int)(run - sidx), stream);
+    if (took == 0)
+      took = launch_brgemm_chains_ft(descs.data(), args.data(), seg_first.data() + sidx, seg_len.data() + sidx,
+                                     (int)(run - sidx), stream);
     if (took > 0) {
       t_ctx.last_kernel = brgemm_tc_last_name();
       count_launch();
@@ -1021,18 +1026,23 @@ extern "C" int64_t xsmm_cuda_graph_end(void) {
   cudaError_t e = cudaStreamEndCapture(t_ctx.stream, &graph);
   t_ctx.capturing = false;
   t_ctx.stream = t_ctx.saved_stream;
+  std::vector<void *> tables;
+  brgemm_tc_take_capture_allocs(tables);
   if (e != cudaSuccess || !graph) {
     fprintf(stderr, "tpp-xsmm-cuda: graph capture failed: %s\n", cudaGetErrorString(e));
     cudaGetLastError();
+    for (void *t : tables) cudaFree(t);
     return 0;
   }
   GraphHandle *gh = new GraphHandle();
+  gh->device_allocs.swap(tables);
   gh->launches = t_ctx.captured_launches;
   snprintf(gh->last_kernel, sizeof(gh->last_kernel), "%s", t_ctx.last_kernel ? t_ctx.last_kernel : "");
   e = cudaGraphInstantiate(&gh->exec, graph, 0);
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) {
     fprintf(stderr, "tpp-xsmm-cuda: graph instantiate failed: %s\n", cudaGetErrorString(e));
+    for (void *t : gh->device_allocs) cudaFree(t);
     delete gh;
     return 0;
   }
@@ -1056,6 +1066,7 @@ extern "C" void xsmm_cuda_graph_destroy(int64_t graph) {
   GraphHandle *gh = reinterpret_cast<GraphHandle *>(graph);
   if (!gh || gh->magic != 0x47525048u) return;
   cudaGraphExecDestroy(gh->exec);
+  for (void *t : gh->device_allocs) cudaFree(t);   // callers destroy a graph only after its replays have completed
   gh->magic = 0;
   delete gh;
 }
