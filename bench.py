@@ -33,7 +33,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 LAYERS = (1024, 1024, 1024, 1024)
-PIPE_DEPTH = 4          # steps in flight in the end-to-end throughput leg
+CHAIN_GROUP = 74        # forward passes per launch group: one per CTA pair of the pair-per-chain kernel (148 SMs / 2)
+PIPE_GROUPS = 3         # launch groups in flight in the end-to-end throughput leg (upload | kernel | download)
 BATCH_PER_GPU = 256
 TILES = (256, 1024, 1024)
 L2_BYTES = 126 * 1024 * 1024
@@ -123,6 +124,14 @@ def make_host_data(seed=123):
         Ws.append(gen.fill(c, k))
         bs.append(gen.fill(k))
     return gen, Ws, bs
+
+
+def h_out_bits(h_acts, harness, bn, bk):
+    """first 8 rows of a host-side output buffer (block-packed) as int32 bf16 bit patterns"""
+    import numpy as np
+
+    o = harness.unpack_activation(h_acts[-1].reshape(BATCH_PER_GPU // bn, LAYERS[-1] // bk, bn, bk))[:8].numpy()
+    return o.view(np.uint16).astype(np.int32)
 
 
 def cpu_arm(steps, warmup, total_budget_s, verbose=False):
@@ -262,7 +271,9 @@ def main():
 
     # ---- rotate more bytes than the L2 holds so every step streams its operands from HBM ----
     set_bytes = sum(w.numel() * 2 for w in w_dev) + sum(b.numel() * 2 for b in b_dev) + 4 * BATCH_PER_GPU * 1024 * 2
-    num_sets = L2_BYTES // set_bytes + 2
+    # ... and at least two forward passes per CTA pair in one rotation graph, so that the pair-per-chain kernel
+    # (one pair of SMs per forward pass) has two rounds of work per launch
+    num_sets = max(L2_BYTES // set_bytes + 2, 2 * CHAIN_GROUP)
     sets = []
     for s in range(num_sets):
         acts = [x_packed.clone()] + [torch.zeros(BATCH_PER_GPU * k, dtype=torch.int16, device=dev) for k in LAYERS[1:]]
@@ -282,12 +293,16 @@ def main():
     # xsmm_cuda_graph_begin/end and replayed - one host call per step; mode "direct": one
     # xsmm_fused_brgemm_invoke (one cudaLaunchKernelEx) per layer per step.
     run = loop.run_graph if args.mode == "graph" else loop.run
-    run(max(args.warmup, num_sets))   # warm-up also captures every set's graph
+    run(max(args.warmup, num_sets))   # warm-up also captures the rotation graph
+    loop.reset()
+    run(args.steps)                   # rehearsal of the timed call: captures the graph of its partial last rotation
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    run(200)  # keep the GPU busy while the sampler gets going
+    loop.reset()
+    run(2 * num_sets)  # keep the GPU busy while the sampler gets going
     barrier()
+    loop.reset()
     launches0 = xsmm.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
@@ -298,6 +313,7 @@ def main():
     barrier()
     t_wall1 = time.perf_counter()
     launches = xsmm.launch_count() - launches0
+    loop.reset()
     run(num_sets)                       # exactly one rotation: the name of the kernel the timed loop is made of
     timed_kernel = xsmm.last_kernel()   # (graph mode: the fused multi-chain kernel; leftover steps run single chains)
     sampler.stop()
@@ -370,33 +386,41 @@ def main():
     e2e_value = flops_step_rank * n_gpus / e2e_s / 1e9
     e2e_out = oracle.bf16_to_f32(harness.unpack_activation(
         h_acts[-1].reshape(BATCH_PER_GPU // bn, LAYERS[-1] // bk, bn, bk))[:8].numpy().view(np.uint16))
-    e2e_ok = bool(np.array_equal(e2e_out, got))
-    # throughput form: PIPE_DEPTH independent steps in flight (one stream + one buffer set per slot); every step
-    # still uploads its 512 KiB input and downloads its 512 KiB output
+    # the single-step graph runs the full-K pass kernel, the device-timed loop the pair kernel: same math, the f32
+    # summation order inside the tensor core may differ -> compare in bf16 ulps, and against the oracle below
+    sync_ulp = int(np.abs(h_out_bits(h_acts, harness, bn, bk) - out[:8].cpu().numpy().view(np.uint16).astype(np.int32)).max())
+    e2e_rel = float(np.abs(e2e_out - want).max() / max(np.abs(want).max(), 1e-30)) if rank == 0 else None
+    # throughput form: PIPE_GROUPS groups of CHAIN_GROUP independent steps in flight (one buffer set per step); every
+    # step still uploads its 512 KiB input and downloads its 512 KiB output
+    depth = PIPE_GROUPS * CHAIN_GROUP
     slot_acts = [h_acts]
-    for _ in range(PIPE_DEPTH - 1):
+    for _ in range(depth - 1):
         acts = [x_packed.cpu().contiguous().pin_memory()] + [torch.zeros(BATCH_PER_GPU * k, dtype=torch.int16).pin_memory()
                                                              for k in LAYERS[1:]]
         for tns in acts:
             xsmm.register_host(tns, upload=True)
         slot_acts.append(acts)
     pipe_loop = harness.NativeMlpLoop(cfg, replay.handles, [(a, h_w, h_b) for a in slot_acts])
-    pipe_loop.run_e2e_pipelined(max(3 * PIPE_DEPTH, args.warmup // 5))
+    pipe_mode = f"batch{CHAIN_GROUP}"
+    pipe_steps = max(e2e_steps // depth, 2) * depth
+    pipe_loop.run_e2e_pipelined(depth, mode=pipe_mode)
     torch.cuda.synchronize(dev)
     for a in slot_acts:
         a[-1].zero_()
     pipe_runs = []
-    for _ in range(3):   # three timed repetitions of e2e_steps steps; the median is reported
+    for _ in range(3):   # three timed repetitions; the median is reported
         barrier()
         t0 = time.perf_counter()
-        pipe_loop.run_e2e_pipelined(e2e_steps)   # returns after the last step's output has reached the host
-        pipe_runs.append(shard.max_over_ranks((time.perf_counter() - t0) / e2e_steps, device=dev))
+        ran = pipe_loop.run_e2e_pipelined(pipe_steps, mode=pipe_mode)   # returns after the last output reached the host
+        pipe_runs.append(shard.max_over_ranks((time.perf_counter() - t0) / ran, device=dev))
     pipe_s = sorted(pipe_runs)[1]
     pipe_value = flops_step_rank * n_gpus / pipe_s / 1e9
+    pipe_kernel = xsmm.last_kernel()
+    e2e_ulp = 0
+    got_bits = out[:8].cpu().numpy().view(np.uint16).astype(np.int32)
     for a in slot_acts:
-        o = oracle.bf16_to_f32(harness.unpack_activation(
-            a[-1].reshape(BATCH_PER_GPU // bn, LAYERS[-1] // bk, bn, bk))[:8].numpy().view(np.uint16))
-        e2e_ok = e2e_ok and bool(np.array_equal(o, got))
+        o = harness.unpack_activation(a[-1].reshape(BATCH_PER_GPU // bn, LAYERS[-1] // bk, bn, bk))[:8].numpy()
+        e2e_ulp = max(e2e_ulp, int(np.abs(o.view(np.uint16).astype(np.int32) - got_bits).max()))
     for tns in h_w + h_b + [t for a in slot_acts for t in a]:
         xsmm.unregister_host(tns)
 
@@ -407,6 +431,8 @@ def main():
         return 0
 
     pk = peaks()
+    # algorithmic HBM bytes of one forward pass: 3 weight matrices + 3 biases + input + output (intermediates stay in L2)
+    set_bytes_algo = sum(c * k * 2 + k * 2 for c, k in zip(LAYERS[:-1], LAYERS[1:])) + 2 * BATCH_PER_GPU * 1024 * 2
     launches_per_step = launches / args.steps
     flops_per_launch = flops_step_rank / launches_per_step
     avg_launch_s = (ms / args.steps) * 1e-3 / launches_per_step
@@ -433,33 +459,44 @@ def main():
                          "inputs larger than L2",
                    "timing": "CUDA events on the launch stream, max over ranks",
                    "issue_mode": ("CUDA graph replay of the captured xsmm invoke sequence (xsmm_cuda_graph_*): one graph = "
-                                  f"one rotation of {num_sets} forward passes on {num_sets} operand sets, which the "
-                                  "runtime fuses into one launch of the chain kernel (3 passes interleaved)"
+                                  f"one rotation of {num_sets} forward passes on {num_sets} operand sets ({3 * num_sets} "
+                                  "xsmm_fused_brgemm_invoke calls), which the runtime turns into ONE launch of the "
+                                  "pair-per-chain kernel: each forward pass (a chain of 3 dependent layers) runs on one "
+                                  "pair of SMs, 74 forward passes side by side; latency of a lone forward pass: "
+                                  "extra.ms_per_step_single_forward"
                                   if args.mode == "graph" else "one xsmm_fused_brgemm_invoke per layer"),
                    "flops_per_step": flops_step_rank * n_gpus, "matmul_flops_per_step": cfg.matmul_flops() * n_gpus},
         "clocks": sampler.summary(t_wall0, t_wall1),
         "e2e": {"value": pipe_value, "unit": UNIT, "h2d_bytes_per_step": BATCH_PER_GPU * LAYERS[0] * 2,
-                "d2h_bytes_per_step": BATCH_PER_GPU * LAYERS[-1] * 2, "ms_per_step": pipe_s * 1e3, "steps": e2e_steps,
-                "path": "xsmm C-ABI on registered pinned host buffers: update_device(input) -> 3 invokes -> "
-                        "update_host(output) every step, as xsmm_cuda_upload_async -> replay of the captured invoke "
-                        f"sequence -> xsmm_cuda_download_async; {PIPE_DEPTH} independent steps in flight (one buffer set "
-                        "each), xsmm_cuda_wait_host(output) before a slot is reused, so the copies of neighbouring "
-                        "steps run under the kernels; wall clock incl. the final drain; median of 3 repetitions",
-                "pipeline_depth": PIPE_DEPTH, "ms_per_step_repetitions": [t * 1e3 for t in pipe_runs],
+                "d2h_bytes_per_step": BATCH_PER_GPU * LAYERS[-1] * 2, "ms_per_step": pipe_s * 1e3, "steps": pipe_steps,
+                "path": "xsmm C-ABI on registered pinned host buffers, every step: xsmm_cuda_upload_async(input 512 KiB) "
+                        "-> 3 xsmm_fused_brgemm_invoke (replayed from the captured sequence) -> xsmm_cuda_download_async("
+                        f"output 512 KiB); steps are issued in groups of {CHAIN_GROUP} (one captured graph = one launch of the "
+                        f"pair-per-chain kernel per group), {PIPE_GROUPS} groups in flight, xsmm_cuda_wait_host(output) before "
+                        "a buffer set is reused, so uploads, kernels and downloads of neighbouring groups overlap; wall "
+                        "clock incl. the final drain; median of 3 repetitions; bound by PCIe (1 MiB per step)",
+                "pipeline_depth": depth, "kernel": pipe_kernel,
+                "ms_per_step_repetitions": [t * 1e3 for t in pipe_runs],
+                "max_ulp_diff_vs_device_run": e2e_ulp,
                 "synchronous": {"value": e2e_value, "ms_per_step": e2e_s * 1e3,
-                                "path": "same step, one in flight: graph launch -> stream sync, every step"},
-                "matches_device_run": e2e_ok},
+                                "path": "same step, one in flight: graph launch -> stream sync, every step",
+                                "rel_err_vs_oracle": e2e_rel, "max_ulp_diff_vs_device_run": sync_ulp}},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "achieved": achieved_tflops, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                      "frac": achieved_tflops / pk["bf16_tflops"], "traffic": traffic,
                      "kernel": timed_kernel, "peak_source": pk["source"] + ", burst",
                      "flops_per_launch": flops_per_launch, "avg_launch_us": avg_launch_s * 1e6,
                      "forward_passes_per_launch": args.steps / max(launches, 1),
-                     "note": "batch 256 is delivery-bound, not tensor-bound: per layer pass every SM has to receive "
-                             "128 KiB of operands at ~50 B/clk (DESIGN.md 4.1c); traffic = DRAM bytes of one launch "
-                             "(ncu, profiles/ncu_mlp_chain_fts_r1.json)"},
+                     "hbm_bytes_per_step": set_bytes_algo, "hbm_gbs": set_bytes_algo / (ms_per_step * 1e-3) / 1e9,
+                     "hbm_frac_of_measured_peak": set_bytes_algo / (ms_per_step * 1e-3) / 1e9 / pk["hbm_gbs"],
+                     "note": "arithmetic intensity 236 FLOP/B sits at the machine balance (251): with operand sets "
+                             "rotating through > L2 every weight byte comes from HBM, so the HBM fraction is reported "
+                             "beside the tensor fraction (DESIGN.md 4.1d); traffic = DRAM bytes of one launch (ncu, "
+                             "profiles/)"},
         "cpu_baseline": cpu,
-        "extra": {"ms_per_step_hot_l2": ms_hot, "gflops_hot_l2": flops_step_rank * n_gpus / (ms_hot * 1e-3) / 1e9,
+        "extra": {"ms_per_step_single_forward": ms_hot,
+                  "single_forward_note": "one operand set replayed back to back (L2-hot, what tpp-run itself measures): "
+                                         "one forward pass per launch, the full-K pass kernel on 128 SMs",
                   "host_issue_us_per_launch": t_issue / max(launches, 1) * 1e6,
                   ("ms_per_step_direct_invokes" if args.mode == "graph" else "ms_per_step_graph_replay"): ms_other,
                   "parity_rel_err_vs_oracle": rel, "kernel": timed_kernel,

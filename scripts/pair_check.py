@@ -92,3 +92,6 @@ for N in COUNTS:
     g.destroy()
     del sets, got
     torch.cuda.empty_cache()
+    import os
+    if os.environ.get("TPP_XSMM_TC_TRACE") == "4":
+        xsmm.LIB.xsmm_cuda_debug_dump_trace()

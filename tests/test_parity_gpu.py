@@ -840,3 +840,170 @@ def test_pipelined_steps_keep_apart(mode):
         xsmm.sync()
         for t in regs:
             xsmm.unregister_host(t)
+
+
+# ---- pair-per-chain kernel (mlp_chain_pair_kernel): many independent chains in one captured graph -----------------
+def _oracle_mlp(x, Ws, bs, m=256, relu=5, bias=True):
+    ref = x
+    for W, b in zip(Ws, bs):
+        y = np.zeros((m, W.shape[1]), np.uint16)
+        oracle.fused_brgemm(BF16, m, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4, 0, relu,
+                            4 if bias else 0, 1 if bias else 0, ref, W, y, b if bias else None, 1)
+        ref = y
+    return ref
+
+
+@pytest.mark.parametrize("n_chains,layers,view", [(13, 3, "flat"), (20, 2, "flat"), (16, 4, "k64xb16"), (80, 3, "flat")])
+def test_many_captured_chains_run_on_cta_pairs(n_chains, layers, view):
+    """>= 12 independent forward passes captured in one graph become ONE launch of the pair-per-chain kernel (one CTA
+    pair per chain, cta_group::2 256 x 256 tiles). Every layer of every chain is within one bf16 rounding step of the
+    per-layer kernels, sampled chains match the oracle within the bf16 tolerance, replays with poisoned intermediates
+    are bit-identical (a layer that ran ahead of its own output would propagate the poison). 80 chains > 74 pairs:
+    pairs take a second chain."""
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    gen = oracle.TensorInit("normal", BF16, 100 + n_chains)
+    hW = [gen.fill(1024, 1024) for _ in range(layers)]
+    hb = [gen.fill(1024) for _ in range(layers)]
+
+    def dev_t(a):
+        return torch.from_numpy(a.view(np.int16)).cuda()
+
+    chains, xs = [], []
+    for c in range(n_chains):
+        x = gen.fill(256, 1024)
+        xs.append(x)
+        # per-chain parameters: the base matrices rolled by c rows (a chain reading another chain's table entry fails)
+        Ws = [torch.roll(dev_t(w), shifts=c, dims=0).contiguous() for w in hW]
+        bs = [torch.roll(dev_t(b), shifts=c, dims=0).contiguous() for b in hb]
+        acts = [dev_t(x)] + [torch.zeros(256, 1024, dtype=torch.int16, device="cuda") for _ in range(layers)]
+        chains.append((acts, Ws, bs))
+    if view == "flat":
+        h = xsmm.fused_brgemm_dispatch(BF16, 256, 1024, 1024, 1024, 1024, 1024, 0, 0, 4 | 64 | 128, 0, 5, 4, 1)
+        nb = 1
+    else:
+        h = xsmm.fused_brgemm_dispatch(BF16, 256, 1024, 64, 1024, 1024, 1024, 64, 64 * 1024, 4 | 64 | 128, 0, 5, 4, 1)
+        nb = 16
+
+    def forward(c):
+        acts, Ws, bs = c
+        for l in range(layers):
+            xsmm.fused_brgemm_invoke(BF16, h, acts[l], 0, Ws[l], 0, acts[l + 1], 0, bs[l], 0, nb)
+
+    for c in chains:
+        forward(c)
+    xsmm.sync()
+    direct = [[a.clone() for a in c[0][1:]] for c in chains]
+    with xsmm.graph_capture() as g:
+        for c in chains:
+            forward(c)
+    assert xsmm.last_kernel() == f"mlp_chain_bf16_{n_chains}x{layers}layers_pair256x256", xsmm.last_kernel()
+    first = None
+    for rep in range(3):
+        for c in chains:
+            for a in c[0][1:]:
+                a.fill_(0x7FC0)
+        n0 = xsmm.launch_count()
+        g.launch()
+        xsmm.sync()
+        assert xsmm.launch_count() - n0 == 1, "all chains must share one launch"
+        got = [[a.clone() for a in c[0][1:]] for c in chains]
+        if first is None:
+            first = got
+            for gc, dc in zip(got, direct):
+                for a, d in zip(gc, dc):
+                    assert _ulp_diff(a, d) <= 1
+        else:
+            for gc, fc in zip(got, first):
+                for a, f in zip(gc, fc):
+                    assert torch.equal(a, f)
+    for c in (0, n_chains // 2, n_chains - 1):
+        Wc = [np.roll(w, c, axis=0) for w in hW]
+        bc = [np.roll(b, c, axis=0) for b in hb]
+        assert_close(BF16, first[c][-1].cpu().numpy().view(np.uint16), _oracle_mlp(xs[c], Wc, bc))
+    g.destroy()
+
+
+def test_large_batch_chain_is_cut_into_row_blocks_for_the_pairs():
+    """One chain with m = 2048 batch rows per layer (BASELINE configs[4] on one GPU) plus one with m = 1024: rows are
+    independent through the layers, so the runtime cuts the chains into 8 + 4 blocks of 256 rows, one CTA pair each."""
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    layers = 3
+    gen = oracle.TensorInit("normal", BF16, 77)
+
+    def dev_t(a):
+        return torch.from_numpy(a.view(np.int16)).cuda()
+
+    specs = []
+    for m in (2048, 1024):
+        hW = [gen.fill(1024, 1024) for _ in range(layers)]
+        hb = [gen.fill(1024) for _ in range(layers)]
+        x = gen.fill(m, 1024)
+        acts = [dev_t(x)] + [torch.zeros(m, 1024, dtype=torch.int16, device="cuda") for _ in range(layers)]
+        h = xsmm.fused_brgemm_dispatch(BF16, m, 1024, 1024, 1024, 1024, 1024, 0, 0, 4, 0, 5, 4, 1)
+        specs.append((m, h, x, hW, hb, acts, [dev_t(w) for w in hW], [dev_t(b) for b in hb]))
+    with xsmm.graph_capture() as g:
+        for m, h, x, hW, hb, acts, dW, db in specs:
+            for l in range(layers):
+                xsmm.fused_brgemm_invoke(BF16, h, acts[l], 0, dW[l], 0, acts[l + 1], 0, db[l], 0, 1)
+    assert xsmm.last_kernel() == "mlp_chain_bf16_12x3layers_pair256x256", xsmm.last_kernel()
+    n0 = xsmm.launch_count()
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == 1
+    for m, h, x, hW, hb, acts, dW, db in specs:
+        want = _oracle_mlp(x, hW, hb, m=m)
+        assert_close(BF16, acts[-1].cpu().numpy().view(np.uint16), want)
+    g.destroy()
+
+
+def test_pair_kernel_without_bias_or_relu_and_with_padded_leading_dims():
+    """Plain brgemm chains (no bias, no ReLU) and fused chains whose activations live in wider buffers (ld > n): the
+    tensor maps carry lda / ldc, the epilogue must not touch the padding."""
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    layers, n_chains, ld = 2, 12, 1024 + 64
+    gen = oracle.TensorInit("normal", BF16, 5150)
+
+    def dev_t(a):
+        return torch.from_numpy(a.view(np.int16)).cuda()
+
+    hW = [gen.fill(1024, 1024) for _ in range(layers)]
+    dW = [dev_t(w) for w in hW]
+    h = xsmm.brgemm_dispatch(BF16, 256, 1024, 1024, ld, 1024, ld, 0, 0, 4)
+    xs, chains = [], []
+    for c in range(n_chains):
+        x = gen.fill(256, 1024)
+        xs.append(x)
+        acts = []
+        for l in range(layers + 1):
+            t = torch.full((256, ld), 0x1234, dtype=torch.int16, device="cuda")
+            if l == 0:
+                t[:, :1024] = dev_t(x)
+            acts.append(t)
+        chains.append(acts)
+    with xsmm.graph_capture() as g:
+        for acts in chains:
+            for l in range(layers):
+                xsmm.brgemm_invoke(BF16, h, acts[l], 0, dW[l], 0, acts[l + 1], 0, 1)
+    assert xsmm.last_kernel() == f"mlp_chain_bf16_{n_chains}x{layers}layers_pair256x256", xsmm.last_kernel()
+    g.launch()
+    xsmm.sync()
+    for x, acts in zip(xs, chains):
+        ref = x
+        for W in hW:
+            y = np.zeros((256, 1024), np.uint16)
+            oracle.brgemm(BF16, 256, 1024, 1024, 1024, 1024, 1024, 0, 0, 4, ref, W, y, 1)
+            ref = y
+        out = acts[-1].cpu().numpy().view(np.uint16)
+        assert_close(BF16, out[:, :1024].copy(), ref)
+        for a in acts[1:]:
+            assert (a[:, 1024:] == 0x1234).all(), "padding columns were overwritten"
+    g.destroy()

@@ -1672,11 +1672,15 @@ constexpr int PC_HALF_N = PC_BLOCK_N / 2;             // weight columns staged b
 constexpr int PC_W_CHUNKS = PC_HALF_N / 64;           // 64-column TMA boxes per CTA and k-block
 constexpr int PC_STAGE_BYTES = A_STAGE_BYTES + PC_W_CHUNKS * B_CHUNK_BYTES;   // 32 KiB
 constexpr int PC_ROWS = 2 * BLOCK_M;                  // batch rows per work item
-constexpr int PC_SMEM = PC_STAGES * PC_STAGE_BYTES + (2 * PC_STAGES + 5) * 8 + 16 + 1024;
+constexpr int PC_OUT_COLS = 64;                       // columns per TMA store box (128 bytes: one swizzle row)
+constexpr int PC_OUT_BYTES = BLOCK_M * PC_OUT_COLS * 2;   // 16 KiB staging buffer, two of them
+constexpr int PC_BIAS_BYTES = PC_BLOCK_N * 2;         // one tile's bias slice, two of them
+constexpr int PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 2 * PC_OUT_BYTES + 2 * PC_BIAS_BYTES + (2 * PC_STAGES + 5) * 8 + 16 + 1024;
 
 struct alignas(128) PcLayer {
   CUtensorMap tmX;          // activations: (k, row, batch element), box 64 x 128
   CUtensorMap tmW;          // weights: (n, k, batch element), box 64 x 64
+  CUtensorMap tmC;          // output: (n, row, 1), box 64 x 128 (TMA store from the swizzled staging buffer)
   void *C;
   const void *D;            // bias vector or nullptr
   int64_t ldc;
@@ -1694,7 +1698,13 @@ struct PcParams {
   const PcLayer *layers;
   const PcItem *items;
   int32_t num_items;
+  unsigned long long *trace;   // TPP_XSMM_TC_TRACE=4: clock stamps of each CTA's first item (nullptr in normal runs)
 };
+constexpr int PC_TRACE_SLOTS = 64;   // [4t+0] MMA tile start, [4t+1] MMAs issued, [4t+2] accumulator ready, [4t+3] tile stored
+                                     // (t < 12); [48+2l], [49+2l] producer waits for / has layer l's input; [60] start, [61] end
+__device__ __forceinline__ void pc_stamp(const PcParams &cp, int slot) {
+  if (cp.trace) cp.trace[(size_t)blockIdx.x * PC_TRACE_SLOTS + slot] = clock64();
+}
 
 __device__ __forceinline__ void tensormap_acquire(const void *map) {
   // the table was written by a host copy: make it visible to the tensor-map proxy of this SM before the first use
@@ -1706,7 +1716,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;                                       // PC_STAGES x 16 KiB
   const uint32_t smem_w = smem_base + PC_STAGES * A_STAGE_BYTES;           // PC_STAGES x 2 x 8 KiB
-  const uint32_t bar_base = smem_w + PC_STAGES * PC_W_CHUNKS * B_CHUNK_BYTES;
+  const uint32_t smem_out = smem_w + PC_STAGES * PC_W_CHUNKS * B_CHUNK_BYTES;   // 2 x 16 KiB output staging
+  const uint32_t smem_bias = smem_out + 2 * PC_OUT_BYTES;                  // 2 x 512 B: bias slice of tile t / t + 1
+  const uint32_t bar_base = smem_bias + 2 * PC_BIAS_BYTES;
   const uint32_t full_bar = bar_base;                                      // leader's: both CTAs' bytes land on it
   const uint32_t empty_bar = bar_base + PC_STAGES * 8;                     // per CTA, released by the pair's MMA commits
   const uint32_t acc_full = bar_base + 2 * PC_STAGES * 8;                  // [2] per CTA: accumulator complete
@@ -1729,7 +1741,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
       ptx::mbar_init(acc_full + 8 * b, 1);
       ptx::mbar_init(acc_free + 8 * b, 8);            // one arrival per epilogue warp of both CTAs
     }
-    ptx::mbar_init(layer_done, 4);                    // one arrival per epilogue warp
+    ptx::mbar_init(layer_done, 1);                    // the epilogue thread that issues (and waits for) the TMA stores
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -1745,6 +1757,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
 
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) pc_stamp(cp, 60);
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): own rows / own weight columns into own smem, bytes counted on the LEADER =====
@@ -1777,7 +1790,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
               if (defer && i == pre - 1) {
                 // my rows of the previous layer's output are stored and fenced: now the activation boxes of the
                 // `pre` slots whose weights are already in flight
+                if (item == pair) pc_stamp(cp, 48 + 2 * l);
                 ptx::mbar_wait(layer_done, layer_ph);
+                asm volatile("fence.proxy.async;" ::: "memory");
+                if (item == pair) pc_stamp(cp, 49 + 2 * l);
                 layer_ph ^= 1;
                 int ss = s - (pre - 1);
                 if (ss < 0) ss += PC_STAGES;
@@ -1814,6 +1830,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
               ptx::tc_fence_after_sync();
             }
             const uint32_t acc = tmem_acc + buf * PC_BLOCK_N;
+            if (t < 12) pc_stamp(cp, 4 * t);
             for (int32_t i = 0; i < total; ++i) {
               ptx::mbar_wait(full_bar + 8 * s, ph);
               ptx::tc_fence_after_sync();
@@ -1829,62 +1846,118 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
               if (++s == PC_STAGES) { s = 0; ph ^= 1; }
             }
             ptx::umma_commit_pair(acc_full + 8 * buf, pair_mask);    // both epilogues may start
+            if (t < 12) pc_stamp(cp, 4 * t + 1);
           }
         }
       }
     }
   } else {
     // ===== epilogue (both CTAs, each on its own 128 rows / TMEM lanes) =====
+    // TMEM lane = row: a thread owns one output row. Its bf16 results go to a 128-byte-swizzled staging buffer
+    // (64 columns x 128 rows), which one thread hands to TMA as a store box: full 128-byte lines leave the SM instead of
+    // 16-byte pieces of 32 different lines per warp instruction (measured: direct stores cost 15.7k clk per tile, twice
+    // the tile's MMA time).
     const int q = warp & 3;
+    const int r_in = q * 32 + lane;                   // row within this CTA's 128
     const uint32_t leader_acc_free = ptx::mapa(acc_free, 0);
     const uint32_t lane_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
-    uint32_t t = 0;
+    const bool issuer = threadIdx.x == 64;
+    const uint32_t row_off = (uint32_t)r_in * 128u;
+    const uint32_t sw = (uint32_t)(r_in & 7);
+    uint32_t t = 0, g = 0;                            // tiles / store boxes handled so far
+    // The bias slice of a tile (256 bf16) is staged in shared memory one tile ahead: thread i fetches columns 2i, 2i+1
+    // of the NEXT tile into a register before it starts on the current one and parks it in the other half of the
+    // buffer afterwards, so no global-load latency (an L2 / HBM miss every time: bias slices are never reused by an SM)
+    // sits inside the column loop. Measured before: 8 exposed misses per tile, epilogue 10-20k clk for 8k clk of MMAs.
+    auto fetch_bias = [&](const void *D, int32_t j) -> uint32_t {
+      return D ? __ldg(reinterpret_cast<const uint32_t *>(static_cast<const uint16_t *>(D) + (size_t)j * PC_BLOCK_N) + r_in) : 0u;
+    };
+    if (pair < cp.num_items) {
+      const PcItem it0 = cp.items[pair];
+      const uint32_t b0 = fetch_bias(cp.layers[it0.layer0].D, 0);
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_bias + (uint32_t)r_in * 4u), "r"(b0) : "memory");
+    }
     for (int item = pair; item < cp.num_items; item += num_pairs) {
       const PcItem it = cp.items[item];
-      const int64_t row = (int64_t)it.row0 + (int64_t)peer * BLOCK_M + q * 32 + lane;
+      const int32_t row0 = it.row0 + (int32_t)peer * BLOCK_M;
       for (int l = 0; l < it.num_layers; ++l) {
         const PcLayer *L = cp.layers + it.layer0 + l;
-        TcParams p;
-        p.C = L->C;
-        p.D = L->D;
-        p.ldc = L->ldc;
-        p.n = L->n;
-        p.m = row + 1;
-        p.beta0 = 1;
-        p.bin_kind = L->D ? 1 : 0;
-        p.bin_mode = kBcastCol;
-        p.relu = L->relu;
-        p.c_vec_ok = 1;
+        if (issuer) tensormap_acquire(&L->tmC);
+        const void *Dp = L->D;
+        const bool relu = L->relu != 0;
         const int32_t n_tiles = L->n_tiles;
         for (int32_t j = 0; j < n_tiles; ++j, ++t) {
           const uint32_t buf = t & 1;
+          // next tile's bias: same layer / next layer / first layer of this pair's next item
+          uint32_t bias_next = 0;
+          if (j + 1 < n_tiles) bias_next = fetch_bias(Dp, j + 1);
+          else if (l + 1 < it.num_layers) bias_next = fetch_bias(L[1].D, 0);
+          else if (item + num_pairs < cp.num_items) bias_next = fetch_bias(cp.layers[cp.items[item + num_pairs].layer0].D, 0);
           ptx::mbar_wait(acc_full + 8 * buf, (t >> 1) & 1);
           ptx::tc_fence_after_sync();
+          if (t < 12 && issuer) pc_stamp(cp, 4 * t + 2);
+          const uint32_t bias_s = smem_bias + buf * PC_BIAS_BYTES;
 #pragma unroll 1
-          for (int c = 0; c < PC_BLOCK_N; c += 32) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32(lane_addr + buf * PC_BLOCK_N + c, r);
-            ptx::tmem_ld_wait();
-            if (c == PC_BLOCK_N - 32) {               // the accumulator is in registers: hand it back to the MMA issuer
-              ptx::tc_fence_before_sync();
-              __syncwarp();
-              if (lane == 0) ptx::mbar_arrive_remote(leader_acc_free + 8 * buf);
-            }
-            float v[32];
+          for (int c = 0; c < PC_BLOCK_N; c += PC_OUT_COLS, ++g) {
+            const uint32_t sbuf = smem_out + (g & 1) * PC_OUT_BYTES;
+            // the store box issued two boxes ago has been read out of this staging buffer
+            if (issuer) ptx::bulk_wait_group_read<1>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
-            epilogue_store<32>(v, p, row, (int64_t)j * PC_BLOCK_N + c);
+            for (int h = 0; h < PC_OUT_COLS; h += 32) {
+              uint32_t r[32];
+              ptx::tmem_ld_32x32(lane_addr + buf * PC_BLOCK_N + c + h, r);
+              uint32_t bw[16];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)             // warp-uniform address: a broadcast read
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(bw[4 * u]), "=r"(bw[4 * u + 1]), "=r"(bw[4 * u + 2]), "=r"(bw[4 * u + 3])
+                             : "r"(bias_s + (uint32_t)((c + h) * 2 + u * 16)));
+              ptx::tmem_ld_wait();
+              if (c + h == PC_BLOCK_N - 32) {         // the accumulator is in registers: hand it back to the MMA issuer
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_remote(leader_acc_free + 8 * buf);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                uint32_t o[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                  float lo = __uint_as_float(r[8 * u + 2 * w]), hi = __uint_as_float(r[8 * u + 2 * w + 1]);
+                  if (Dp) {
+                    lo += __uint_as_float(bw[4 * u + w] << 16);
+                    hi += __uint_as_float(bw[4 * u + w] & 0xffff0000u);
+                  }
+                  if (relu) { lo = relu_f32(lo); hi = relu_f32(hi); }
+                  o[w] = pack_bf16x2(lo, hi);
+                }
+                const uint32_t chunk = (uint32_t)(h / 8 + u);   // 16-byte chunk of the 128-byte row
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                             ::"r"(sbuf + row_off + ((chunk ^ sw) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                             : "memory");
+              }
+            }
+            ptx::fence_proxy_async();                 // my shared-memory writes -> the async proxy (TMA store)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (issuer) {
+              ptx::tma_store_3d(&L->tmC, sbuf, j * PC_BLOCK_N + c, row0, 0);
+              ptx::bulk_commit_group();
+            }
           }
+          // the other half of the bias buffer was last read during tile t - 1: every thread is past that
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_bias + (buf ^ 1u) * PC_BIAS_BYTES + (uint32_t)r_in * 4u), "r"(bias_next)
+                       : "memory");
+          if (t < 12 && issuer) pc_stamp(cp, 4 * t + 3);
         }
-        if (l + 1 < it.num_layers) {
-          // this warp's rows of the layer output: visible at L2 (where TMA reads) before the producer is told
-          __threadfence();
-          asm volatile("fence.proxy.async;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(layer_done);
+        if (l + 1 < it.num_layers && issuer) {
+          // my rows of the layer output have been written (TMA stores complete): the producer may fetch them
+          ptx::bulk_wait_group<0>();
+          ptx::mbar_arrive(layer_done);
         }
       }
     }
+    if (issuer) ptx::bulk_wait_group<0>();
   }
 
   // the peer must not exit (nor free TMEM) while the leader's MMAs still read its shared memory / write its TMEM
@@ -1892,6 +1965,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
   __syncwarp();
   ptx::cluster_arrive();
   ptx::cluster_wait();
+  if (threadIdx.x == 0) pc_stamp(cp, 61);
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc_pair(tmem_acc, 2 * PC_BLOCK_N);
@@ -1906,6 +1980,8 @@ int g_trace_next = 0;
 int g_trace_ctas[kTraceRing] = {0};
 int g_chain_trace_ctas = 0, g_chain_trace_layers = 0;
 bool g_chain_trace_ft = false;
+unsigned long long *g_pc_trace = nullptr;   // pair-per-chain kernel stamps (TPP_XSMM_TC_TRACE=4)
+int g_pc_trace_ctas = 0;
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -2320,6 +2396,32 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
 // ---- fused chain launch -------------------------------------------------------------------------------------
 // True if layers[0..L) can run in mlp_chain_kernel: every layer is a bf16 tensor-core BRGEMM with beta_0, the same
 // m and n, exactly 4 x CHAIN_IPC (batch x k-block) iterations, and layer l+1 reads layer l's C as its A.
+// Kernel-independent part: layers[0..L) form a chain - every layer a bf16 tensor-core BRGEMM with beta_0 on the same m
+// rows, layer l+1 reads exactly layer l's C as its A, no weight / bias / output buffer is written inside the chain.
+// Each chain kernel adds its own shape constraints on top (brgemm_chain_supported, chain_ft_supported,
+// chain_pair_supported); a linked chain that no kernel takes is launched layer by layer.
+bool brgemm_chain_linked(const KernelDesc *const *descs, const GemmArgs *args, int L) {
+  static const bool off = [] { const char *e = getenv("TPP_XSMM_CHAIN"); return e && e[0] == '0'; }();
+  if (off || L < 2 || L > CHAIN_MAX_LAYERS) return false;
+  const KernelDesc &d0 = *descs[0];
+  for (int l = 0; l < L; ++l) {
+    const KernelDesc &d = *descs[l];
+    if (d.impl != KernelImpl::BrgemmTC || !(d.gemm_flags & 4) || d.m != d0.m) return false;
+    if ((d.k % BLOCK_K) != 0 || args[l].batch < 1) return false;
+    if (!aligned16(args[l].A) || !aligned16(args[l].B) || !aligned16(args[l].C) || (d.ldc % 8) != 0) return false;
+    if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && !(d.binary_kind == 1 && (d.binary_flags & 4))) return false;
+    if (l > 0) {
+      if (args[l].A != args[l - 1].C || d.lda != descs[l - 1]->ldc) return false;
+      if (args[l].batch * d.k != descs[l - 1]->n) return false;
+    }
+    for (int j = 0; j < L; ++j) {
+      if (args[l].B == args[j].C || (args[l].D && args[l].D == args[j].C)) return false;
+      if (j != l && args[l].C == args[j].C) return false;
+    }
+  }
+  return true;
+}
+
 bool brgemm_chain_supported(const KernelDesc *const *descs, const GemmArgs *args, int L) {
   static const bool off = [] { const char *e = getenv("TPP_XSMM_CHAIN"); return e && e[0] == '0'; }();
   if (off || L < 2 || L > CHAIN_MAX_LAYERS) return false;
@@ -2417,7 +2519,9 @@ void chain_ranges(const KernelDesc *const *descs, const GemmArgs *args, int L, s
 // independent, identically tiled chains is taken. Returns the number of chains launched (0: not applicable).
 int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args, const int *first, const int *len,
                             int num_chains, cudaStream_t stream) {
-  if (num_chains < 1 || !chain_ft_supported(descs + first[0], args + first[0], len[0])) return 0;
+  if (num_chains < 1 || !brgemm_chain_supported(descs + first[0], args + first[0], len[0]) ||
+      !chain_ft_supported(descs + first[0], args + first[0], len[0]))
+    return 0;
   static const bool multi_off = [] { const char *e = getenv("TPP_XSMM_CHAIN_MULTI"); return e && e[0] == '0'; }();
   const KernelDesc &d0 = *descs[first[0]];
   int split = chain_ft_split(descs + first[0], args + first[0], len[0]);
@@ -2430,7 +2534,9 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
       const int c = take;
       const KernelDesc &d = *descs[first[c]];
       if (d.m != d0.m || d.n != d0.n || passes + len[c] > FT_MAX_PASSES) break;
-      if (!chain_ft_supported(descs + first[c], args + first[c], len[c])) break;
+      if (!brgemm_chain_supported(descs + first[c], args + first[c], len[c]) ||
+          !chain_ft_supported(descs + first[c], args + first[c], len[c]))
+        break;
       if (chain_ft_split(descs + first[c], args + first[c], len[c]) != split) break;
       std::vector<ByteRange> in, out;
       chain_ranges(descs + first[c], args + first[c], len[c], in, out);
@@ -2597,12 +2703,14 @@ cudaStream_t table_stream() {
 }
 bool chain_pair_supported(const KernelDesc *const *descs, const GemmArgs *args, int L) {
   const KernelDesc &d0 = *descs[0];
-  if ((d0.m % PC_ROWS) != 0 || (d0.n % PC_BLOCK_N) != 0 || d0.m > (1 << 30) || d0.n > (1 << 30)) return false;
+  if ((d0.m % PC_ROWS) != 0 || d0.m > (1 << 30)) return false;
   for (int l = 0; l < L; ++l) {
     const KernelDesc &d = *descs[l];
+    if ((d.n % PC_BLOCK_N) != 0 || d.n > (1 << 30)) return false;
     if ((d.k % BLOCK_K) != 0 || args[l].batch < 1 || (d.ldc % 8) != 0) return false;
     if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && args[l].D == nullptr) return false;
     if (d.op == OpClass::FusedBrgemm && d.unary_kind != 0 && d.unary_kind != 5) return false;
+    if (args[l].D && !aligned16(args[l].D)) return false;   // the epilogue reads the bias in 16-byte words
   }
   return true;
 }
@@ -2662,7 +2770,8 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
       const uint64_t nb = (uint64_t)g.batch;
       if (!encode_map(&pl.tmX, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, BLOCK_K,
                       BLOCK_M) ||
-          !encode_map(&pl.tmW, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, 64, BLOCK_K))
+          !encode_map(&pl.tmW, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, 64, BLOCK_K) ||
+          !encode_map(&pl.tmC, g.C, (uint64_t)d.n, (uint64_t)d.m, 1, (uint64_t)d.ldc, 0, PC_OUT_COLS, BLOCK_M))
         return 0;
       pl.C = g.C;
       pl.D = (d.op == OpClass::FusedBrgemm && g.D && d.binary_kind == 1) ? g.D : nullptr;
@@ -2693,6 +2802,15 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   cp.layers = reinterpret_cast<const PcLayer *>(table);
   cp.items = reinterpret_cast<const PcItem *>(table + lbytes);
   cp.num_items = (int32_t)items;
+  cp.trace = nullptr;
+  static const bool pc_trace_on = [] { const char *e = getenv("TPP_XSMM_TC_TRACE"); return e && atoi(e) == 4; }();
+  if (pc_trace_on) {
+    if (!g_pc_trace) {
+      TPP_CUDA_CHECK(cudaMalloc(&g_pc_trace, sizeof(unsigned long long) * 2 * 148 * PC_TRACE_SLOTS));
+      TPP_CUDA_CHECK(cudaMemset(g_pc_trace, 0, sizeof(unsigned long long) * 2 * 148 * PC_TRACE_SLOTS));
+    }
+    cp.trace = g_pc_trace;
+  }
   static const int max_pairs = [] {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -2710,6 +2828,7 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   });
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * pairs));
+  g_pc_trace_ctas = 2 * pairs;
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = PC_SMEM;
   cfg.stream = stream;
@@ -2728,6 +2847,7 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
 }
 
 bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, int L, cudaStream_t stream) {
+  if (!brgemm_chain_supported(descs, args, L)) return false;
   {
     const int first = 0;
     if (launch_brgemm_chains_ft(descs, args, &first, &L, 1, stream) == 1) return true;
@@ -2815,6 +2935,31 @@ bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, i
 
 // Debug (TPP_XSMM_TC_TRACE=2): wall-clock timeline of the traced launches, oldest first.
 void brgemm_tc_dump_trace() {
+  if (g_pc_trace && g_pc_trace_ctas) {
+    TPP_CUDA_CHECK(cudaDeviceSynchronize());
+    const int n = g_pc_trace_ctas;
+    std::vector<unsigned long long> h((size_t)n * PC_TRACE_SLOTS);
+    TPP_CUDA_CHECK(cudaMemcpy(h.data(), g_pc_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    auto med = [&](int sl, int parity) {   // median over the CTAs of one parity (0 = leaders, 1 = peers, 2 = all)
+      std::vector<double> v;
+      for (int c = 0; c < n; ++c) {
+        if (parity < 2 && (c & 1) != parity) continue;
+        const unsigned long long *r = &h[(size_t)c * PC_TRACE_SLOTS];
+        if (r[sl] && r[60]) v.push_back((double)((long long)r[sl] - (long long)r[60]));
+      }
+      if (v.empty()) return 0.0;
+      std::sort(v.begin(), v.end());
+      return v[v.size() / 2];
+    };
+    fprintf(stderr, "pair-chain-trace %d CTAs; median SM clocks since CTA start; end=%.0f\n", n, med(61, 2));
+    for (int t = 0; t < 12; ++t)
+      fprintf(stderr, "  tile %2d: mma_start=%.0f mma_issued=%.0f acc_ready=%.0f stored=%.0f (peer: acc_ready=%.0f stored=%.0f)\n",
+              t, med(4 * t, 0), med(4 * t + 1, 0), med(4 * t + 2, 0), med(4 * t + 3, 0), med(4 * t + 2, 1), med(4 * t + 3, 1));
+    for (int l = 1; l < 4; ++l)
+      if (med(48 + 2 * l, 2) > 0)
+        fprintf(stderr, "  layer %d input: producer waits from %.0f to %.0f\n", l, med(48 + 2 * l, 2), med(49 + 2 * l, 2));
+    return;
+  }
   if (!g_trace_buf) return;
   TPP_CUDA_CHECK(cudaDeviceSynchronize());
   if (g_chain_trace_ctas && g_chain_trace_ft) {

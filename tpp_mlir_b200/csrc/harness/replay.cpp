@@ -6,7 +6,10 @@
 // written by hand: it calls ONLY the C-ABI of include/tpp_xsmm_abi.h, exactly as JIT'd code
 // would, for the block-packed MLP that `mlir-gen --kernel=const --bias --relu` generates
 // (tools/mlir-gen/MLIRGen.cpp:632-681; offsets per SURVEY.md Appendix B).
+#include <algorithm>
 #include <cstdint>
+#include <map>
+#include <tuple>
 
 #include "tpp_xsmm_abi.h"
 
@@ -44,6 +47,8 @@ void tpp_replay_mlp(int64_t dtype, int64_t num_layers, const int64_t *handles, c
 // graphs[i] (i < num_sets) replays one forward pass on operand set i; graphs[num_sets] replays one full
 // rotation (num_sets consecutive forward passes, used when `group` != 0 - the loop body unrolled over the
 // rotating operand sets, so the per-graph-launch latency is paid once per rotation). 0 == not captured yet.
+// With `group`, the steps before the first rotation boundary and after the last one are replayed as ONE graph each
+// (captured per (first set, length) on first use), single steps only when one step is left.
 __attribute__((visibility("default")))
 int64_t tpp_replay_mlp_graph(int64_t dtype, int64_t num_layers, const int64_t *handles, const int64_t *layer_sizes,
                              int64_t batch, int64_t bn, int64_t bk, int64_t bc, const TppMlpSet *sets,
@@ -62,6 +67,22 @@ int64_t tpp_replay_mlp_graph(int64_t dtype, int64_t num_layers, const int64_t *h
       }
       xsmm_cuda_graph_launch(graphs[num_sets]);
       s += num_sets;
+      continue;
+    }
+    // a partial rotation (the head up to the next rotation boundary, or the tail of the run): one captured graph per
+    // (first set, length), so that a run of any length is still a handful of graph launches
+    const int64_t chunk = std::min(steps - s, num_sets - idx);
+    if (group && chunk >= 2) {
+      static std::map<std::tuple<const void *, const void *, int64_t, int64_t>, int64_t> partial;
+      int64_t &g = partial[std::make_tuple((const void *)sets, (const void *)graphs, idx, chunk)];
+      if (!g) {
+        if (xsmm_cuda_graph_begin() != 0) return -1;
+        tpp_replay_mlp(dtype, num_layers, handles, layer_sizes, batch, bn, bk, bc, sets + idx, chunk, 0, chunk, has_bias);
+        g = xsmm_cuda_graph_end();
+        if (!g) return -1;
+      }
+      xsmm_cuda_graph_launch(g);
+      s += chunk;
       continue;
     }
     if (!graphs[idx]) {

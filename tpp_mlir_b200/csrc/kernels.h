@@ -59,7 +59,8 @@ bool brgemm_tc_supported(const KernelDesc &d);
 void brgemm_tc_configure(KernelDesc &d);
 bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t stream);
 // L consecutive layers (C of one is A of the next) in one persistent kernel: see brgemm_tc.cu
-bool brgemm_chain_supported(const KernelDesc *const *descs, const GemmArgs *args, int L);
+bool brgemm_chain_linked(const KernelDesc *const *descs, const GemmArgs *args, int L);      // the layers form a chain
+bool brgemm_chain_supported(const KernelDesc *const *descs, const GemmArgs *args, int L);   // ... the pass kernels can run
 bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, int L, cudaStream_t stream);
 // several chains (chain c = layers [first[c], first[c] + len[c]), each accepted by brgemm_chain_supported) as ONE launch
 // of the feature-major chain kernel, pairs of mutually independent chains interleaved; returns the number of chains

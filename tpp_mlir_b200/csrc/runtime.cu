@@ -445,7 +445,7 @@ void flush_pending() {
   for (size_t i = 0; i < n;) {
     int L = 1;
     for (int t = 4; t >= 2; --t)
-      if (i + t <= n && brgemm_chain_supported(descs.data() + i, args.data() + i, t)) { L = t; break; }
+      if (i + t <= n && brgemm_chain_linked(descs.data() + i, args.data() + i, t)) { L = t; break; }
     seg_first.push_back((int)i);
     seg_len.push_back(L);
     i += L;

@@ -230,6 +230,10 @@ class NativeMlpLoop:
         self.num_sets = len(sets)
         self._step = 0
 
+    def reset(self) -> None:
+        """Next run()/run_graph() starts at operand set 0 again (same graph decomposition for the same length)."""
+        self._step = 0
+
     def run(self, steps: int) -> None:
         cfg = self.cfg
         bn, bk, bc = cfg.tiles
@@ -267,6 +271,15 @@ class NativeMlpLoop:
 
     PIPE_MODES = {"async": 0, "grouped": 1, "streams": 2, "batch2": 4, "batch3": 5, "batch4": 6, "batch6": 8}
 
+    @classmethod
+    def pipe_mode(cls, mode: str) -> int:
+        """"batchG" for any G >= 1: groups of G steps share one captured graph (mode code 2 + G)."""
+        if mode in cls.PIPE_MODES:
+            return cls.PIPE_MODES[mode]
+        if mode.startswith("batch") and mode[5:].isdigit() and int(mode[5:]) >= 1:
+            return 2 + int(mode[5:])
+        raise KeyError(mode)
+
     def run_e2e_pipelined(self, steps: int, elem_size: int = 2, mode: str = "async") -> int:
         """Throughput form of run_e2e: every operand set is a pipeline slot, so uploads, kernels and downloads
         of neighbouring steps overlap; every step still moves its input and its output across PCIe.
@@ -283,7 +296,7 @@ class NativeMlpLoop:
         graphs, streams = getattr(self, key)
         rc = replay_lib().tpp_replay_mlp_e2e_pipelined(cfg.dtype, cfg.num_layers, self._handles, self._sizes, cfg.batch,
                                                        bn, bk, bc, self._sets, self.num_sets, steps,
-                                                       1 if cfg.bias else 0, elem_size, self.PIPE_MODES[mode], graphs,
+                                                       1 if cfg.bias else 0, elem_size, self.pipe_mode(mode), graphs,
                                                        streams)
         if rc < 0:
             raise RuntimeError("pipelined e2e replay failed (graph capture)")
