@@ -1675,7 +1675,9 @@ constexpr int PC_ROWS = 2 * BLOCK_M;                  // batch rows per work ite
 constexpr int PC_OUT_COLS = 64;                       // columns per TMA store box (128 bytes: one swizzle row)
 constexpr int PC_OUT_BYTES = BLOCK_M * PC_OUT_COLS * 2;   // 16 KiB staging buffer, two of them
 constexpr int PC_BIAS_BYTES = PC_BLOCK_N * 2;         // one tile's bias slice, two of them
-constexpr int PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 2 * PC_OUT_BYTES + 2 * PC_BIAS_BYTES + (2 * PC_STAGES + 5) * 8 + 16 + 1024;
+constexpr int PC_MAX_TILES = 16;                      // output tiles per layer (n <= 4096): one "stored" barrier each
+constexpr int PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 2 * PC_OUT_BYTES + 2 * PC_BIAS_BYTES +
+                        (2 * PC_STAGES + 4 + PC_MAX_TILES) * 8 + 16 + 1024;
 
 struct alignas(128) PcLayer {
   CUtensorMap tmX;          // activations: (k, row, batch element), box 64 x 128
@@ -1724,8 +1726,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
   const uint32_t empty_bar = bar_base + PC_STAGES * 8;                     // per CTA, released by the pair's MMA commits
   const uint32_t acc_full = bar_base + 2 * PC_STAGES * 8;                  // [2] per CTA: accumulator complete
   const uint32_t acc_free = acc_full + 16;                                 // [2] leader's: both epilogues have read it out
-  const uint32_t layer_done = acc_free + 16;                               // per CTA: my rows of the layer output are stored
-  const uint32_t tmem_slot = layer_done + 8;
+  const uint32_t tile_done = acc_free + 16;                                // [PC_MAX_TILES] per CTA: my rows of output tile j are stored
+  const uint32_t tmem_slot = tile_done + 8 * PC_MAX_TILES;
   uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
 
@@ -1742,7 +1744,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
       ptx::mbar_init(acc_full + 8 * b, 1);
       ptx::mbar_init(acc_free + 8 * b, 8);            // one arrival per epilogue warp of both CTAs
     }
-    ptx::mbar_init(layer_done, 1);                    // the epilogue thread that issues (and waits for) the TMA stores
+    for (int j = 0; j < PC_MAX_TILES; ++j) ptx::mbar_init(tile_done + 8 * j, 1);   // the thread that issues the TMA stores
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -1770,7 +1772,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
       const uint64_t pol_first = ptx::l2_policy_evict_first(), pol_last = ptx::l2_policy_evict_last();
       const bool hints = cp.l2_hints != 0;
       int s = 0;
-      uint32_t ph = 0, layer_ph = 0;
+      uint32_t ph = 0, done_ph = 0;                   // done_ph bit j: parity of tile_done[j]'s next phase
       for (int item = pair; item < cp.num_items; item += num_pairs) {
         const PcItem it = cp.items[item];
         const int32_t row0 = it.row0 + (int32_t)peer * BLOCK_M;
@@ -1779,15 +1781,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
           tensormap_acquire(&L->tmX);
           tensormap_acquire(&L->tmW);
           const int32_t k_iters = L->k_iters, total = L->total_iters, n_tiles = L->n_tiles;
-          const int32_t pre = total < PC_STAGES ? total : PC_STAGES;
+          int32_t ready = 0;                          // output tiles of layer l - 1 (my rows) known to be stored
           for (int32_t j = 0; j < n_tiles; ++j) {
             const int32_t wcol = j * PC_BLOCK_N + (int32_t)peer * PC_HALF_N;
-            const bool defer = (l > 0 && j == 0);     // the activations are the previous layer's output
             const uint64_t pol_x = (j + 1 < n_tiles) ? pol_last : pol_first;
             int32_t b = 0, kb = 0;
             for (int32_t i = 0; i < total; ++i) {
               ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
               if (peer == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2 * PC_STAGE_BYTES);   // both CTAs' bytes
+              // the weights depend on nothing: their boxes go out before any wait for the previous layer
 #pragma unroll
               for (int c = 0; c < PC_W_CHUNKS; ++c) {
                 if (hints)
@@ -1797,34 +1799,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
                   ptx::tma_load_3d_pair(smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES, &L->tmW, leader_full + 8 * s,
                                         wcol + c * 64, kb * BLOCK_K, b);
               }
-              if (!(defer && i < pre)) {
-                if (hints)
-                  ptx::tma_load_3d_pair_hint(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, kb * BLOCK_K, row0, b,
-                                             pol_x);
-                else
-                  ptx::tma_load_3d_pair(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, kb * BLOCK_K, row0, b);
-              }
-              if (defer && i == pre - 1) {
-                // my rows of the previous layer's output are stored and fenced: now the activation boxes of the
-                // `pre` slots whose weights are already in flight
-                if (item == pair) pc_stamp(cp, 48 + 2 * l);
-                ptx::mbar_wait(layer_done, layer_ph);
-                asm volatile("fence.proxy.async;" ::: "memory");
-                if (item == pair) pc_stamp(cp, 49 + 2 * l);
-                layer_ph ^= 1;
-                int ss = s - (pre - 1);
-                if (ss < 0) ss += PC_STAGES;
-                int32_t bb = 0, kk = 0;
-                for (int32_t t = 0; t < pre; ++t) {
-                  if (hints)
-                    ptx::tma_load_3d_pair_hint(smem_a + ss * A_STAGE_BYTES, &L->tmX, leader_full + 8 * ss, kk * BLOCK_K, row0,
-                                               bb, pol_x);
-                  else
-                    ptx::tma_load_3d_pair(smem_a + ss * A_STAGE_BYTES, &L->tmX, leader_full + 8 * ss, kk * BLOCK_K, row0, bb);
-                  if (++ss == PC_STAGES) ss = 0;
-                  if (++kk == k_iters) { kk = 0; ++bb; }
+              if (l > 0 && j == 0) {
+                // reduction step i reads columns [64 i, 64 i + 64) of the previous layer's output = its tile i / 4:
+                // only the last four steps of the first tile have to wait for the previous layer's last epilogue
+                const int32_t need = (i * BLOCK_K) / PC_BLOCK_N;
+                while (ready <= need) {
+                  const bool last = ready + 1 == (total * BLOCK_K) / PC_BLOCK_N;
+                  if (last && item == pair) pc_stamp(cp, 48 + 2 * l);
+                  ptx::mbar_wait(tile_done + 8 * ready, (done_ph >> ready) & 1u);
+                  if (last && item == pair) pc_stamp(cp, 49 + 2 * l);
+                  done_ph ^= 1u << ready;
+                  ++ready;
+                  asm volatile("fence.proxy.async;" ::: "memory");
                 }
               }
+              if (hints)
+                ptx::tma_load_3d_pair_hint(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, kb * BLOCK_K, row0, b,
+                                           pol_x);
+              else
+                ptx::tma_load_3d_pair(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, kb * BLOCK_K, row0, b);
               if (++kb == k_iters) { kb = 0; ++b; }
               if (++s == PC_STAGES) { s = 0; ph ^= 1; }
             }
@@ -1969,6 +1962,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
               else ptx::tma_store_3d_hint(&L->tmC, sbuf, j * PC_BLOCK_N + c, row0, 0,
                                           l + 1 < it.num_layers ? pol_last : pol_first);
               ptx::bulk_commit_group();
+              if (c == 0 && j > 0 && l + 1 < it.num_layers) {
+                // every store group but the one just committed is complete: tile j - 1 (my rows) is in L2
+                ptx::bulk_wait_group<1>();
+                ptx::mbar_arrive(tile_done + 8 * (j - 1));
+              }
             }
           }
           // the other half of the bias buffer was last read during tile t - 1: every thread is past that
@@ -1977,9 +1975,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
           if (t < 12 && issuer) pc_stamp(cp, 4 * t + 3);
         }
         if (l + 1 < it.num_layers && issuer) {
-          // my rows of the layer output have been written (TMA stores complete): the producer may fetch them
+          // the layer's last tile: its stores are the only ones outstanding
           ptx::bulk_wait_group<0>();
-          ptx::mbar_arrive(layer_done);
+          ptx::mbar_arrive(tile_done + 8 * (n_tiles - 1));
         }
       }
     }
@@ -2732,7 +2730,7 @@ bool chain_pair_supported(const KernelDesc *const *descs, const GemmArgs *args, 
   if ((d0.m % PC_ROWS) != 0 || d0.m > (1 << 30)) return false;
   for (int l = 0; l < L; ++l) {
     const KernelDesc &d = *descs[l];
-    if ((d.n % PC_BLOCK_N) != 0 || d.n > (1 << 30)) return false;
+    if ((d.n % PC_BLOCK_N) != 0 || d.n > PC_MAX_TILES * PC_BLOCK_N) return false;
     if ((d.k % BLOCK_K) != 0 || args[l].batch < 1 || (d.ldc % 8) != 0) return false;
     if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && args[l].D == nullptr) return false;
     if (d.op == OpClass::FusedBrgemm && d.unary_kind != 0 && d.unary_kind != 5) return false;
