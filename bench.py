@@ -34,7 +34,7 @@ if ROOT not in sys.path:
 
 LAYERS = (1024, 1024, 1024, 1024)
 CHAIN_GROUP = 74        # forward passes per launch group: one per CTA pair of the pair-per-chain kernel (148 SMs / 2)
-PIPE_GROUPS = 3         # launch groups in flight in the end-to-end throughput leg (upload | kernel | download)
+PIPE_GROUPS = int(os.environ.get("TPP_BENCH_PIPE_GROUPS", "3"))   # launch groups in flight in the end-to-end leg (upload | kernel | download)
 BATCH_PER_GPU = 256
 TILES = (256, 1024, 1024)
 L2_BYTES = 126 * 1024 * 1024

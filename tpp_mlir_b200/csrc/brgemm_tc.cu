@@ -1700,6 +1700,7 @@ struct PcParams {
   const PcLayer *layers;
   const PcItem *items;
   int32_t num_items;
+  int32_t prefetch_w;          // L2 prefetch of the next tile's weight boxes (TPP_XSMM_CHAIN_PAIR_PREFETCH=1)
   int32_t l2_hints;            // L2 eviction-priority hints on the TMA loads / stores (TPP_XSMM_CHAIN_PAIR_HINTS=0: off)
   unsigned long long *trace;   // TPP_XSMM_TC_TRACE=4: clock stamps of each CTA's first item (nullptr in normal runs)
 };
@@ -1771,6 +1772,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
       // activations are re-read once per output tile -> evict_last until the layer's last tile, whose read demotes them
       const uint64_t pol_first = ptx::l2_policy_evict_first(), pol_last = ptx::l2_policy_evict_last();
       const bool hints = cp.l2_hints != 0;
+      const bool prefetch_w = cp.prefetch_w != 0;
       int s = 0;
       uint32_t ph = 0, done_ph = 0;                   // done_ph bit j: parity of tile_done[j]'s next phase
       for (int item = pair; item < cp.num_items; item += num_pairs) {
@@ -1798,6 +1800,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
                 else
                   ptx::tma_load_3d_pair(smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES, &L->tmW, leader_full + 8 * s,
                                         wcol + c * 64, kb * BLOCK_K, b);
+              }
+              if (prefetch_w && (j & 1) == 0 && j + 1 < n_tiles) {
+                // the same k-rows of the NEXT tile's weight columns go to L2 now: DRAM sees runs of 1 KiB per row
+                // (this pair's two tiles) instead of 512 B, and the odd tiles' weight loads hit L2
+#pragma unroll
+                for (int c = 0; c < PC_W_CHUNKS; ++c)
+                  ptx::tma_prefetch_3d(&L->tmW, wcol + PC_BLOCK_N + c * 64, kb * BLOCK_K, b);
               }
               if (l > 0 && j == 0) {
                 // reduction step i reads columns [64 i, 64 i + 64) of the previous layer's output = its tile i / 4:
@@ -2828,6 +2837,8 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   cp.num_items = (int32_t)items;
   static const bool hints_on = [] { const char *e = getenv("TPP_XSMM_CHAIN_PAIR_HINTS"); return !(e && e[0] == '0'); }();
   cp.l2_hints = hints_on ? 1 : 0;
+  static const bool prefetch_on = [] { const char *e = getenv("TPP_XSMM_CHAIN_PAIR_PREFETCH"); return e && e[0] == '1'; }();
+  cp.prefetch_w = prefetch_on ? 1 : 0;
   cp.trace = nullptr;
   static const bool pc_trace_on = [] { const char *e = getenv("TPP_XSMM_TC_TRACE"); return e && atoi(e) == 4; }();
   if (pc_trace_on) {
