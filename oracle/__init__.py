@@ -21,6 +21,8 @@ from .pyoracle import (  # noqa: F401
     num_threads,
     set_acc_mode,
     set_num_threads,
+    tensor_pack,
+    tensor_unpack,
     unary,
     use_native,
 )

@@ -177,3 +177,31 @@ class TensorInit:
             lib().ti_destroy(self._h)
         except Exception:
             pass
+
+
+# ---- tensor.pack / tensor.unpack (block layouts) ------------------------------------------------------
+# Restates the semantics of the ops the reference tiles and lowers to per-tile unary TPPs
+# (lib/TPP/Transforms/LowerPacksAndUnpacks.cpp:143-250; benchmarks/mlir/fp32-pack-gemm-operand-{a,b}-512x1024.mlir,
+# fp32-unpack-gemm-operand-a-512x512.mlir): inner_dims_pos = [0, 1], inner_tiles = [bm, bn], optional
+# outer_dims_perm = [1, 0]. Pure data movement: bit-exact for every dtype.
+def tensor_pack(x, bm, bn, outer_perm=(0, 1)):
+    """[M][N] -> [M/bm][N/bn][bm][bn] (outer dims permuted by outer_perm)."""
+    import numpy as np
+
+    m, n = x.shape
+    assert m % bm == 0 and n % bn == 0
+    t = x.reshape(m // bm, bm, n // bn, bn).transpose(0, 2, 1, 3)
+    if tuple(outer_perm) == (1, 0):
+        t = t.transpose(1, 0, 2, 3)
+    return np.ascontiguousarray(t)
+
+
+def tensor_unpack(xp, outer_perm=(0, 1)):
+    """[A][B][bm][bn] -> [M][N], the inverse of tensor_pack."""
+    import numpy as np
+
+    t = xp
+    if tuple(outer_perm) == (1, 0):
+        t = t.transpose(1, 0, 2, 3)
+    mb, nb, bm, bn = t.shape
+    return np.ascontiguousarray(t.transpose(0, 2, 1, 3).reshape(mb * bm, nb * bn))

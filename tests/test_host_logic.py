@@ -55,3 +55,24 @@ def test_replay_offsets_follow_appendix_b(monkeypatch):
     # (iN=1, iK=2): offA = iN*(C/bc)*bn*bc, offB = iK*(C/bc)*bc*bk, offC = (iN*(K/bk)+iK)*bn*bk, offD = iK*bk
     c = inv[1 * 4 + 2]
     assert c[1:] == (2, 77, "x", 1 * 2 * 1024, "W", 2 * 2 * 1024, "y", (1 * 4 + 2) * 1024, "b", 64, 2)
+
+
+def test_tensor_pack_oracle_matches_the_tile_loop():
+    """oracle.tensor_pack / tensor_unpack (numpy reshapes) against the explicit per-tile loop the reference's lowering
+    executes (one 2-D copy per tile, LowerPacksAndUnpacks.cpp:143-250), for both outer-dims permutations."""
+    import numpy as np
+
+    import oracle
+
+    rng = np.random.default_rng(3)
+    for (m, n, bm, bn) in ((64, 96, 32, 32), (24, 40, 12, 8), (512, 1024, 32, 32)):
+        x = rng.integers(0, 1 << 16, size=(m, n), dtype=np.uint16)
+        for perm in ((0, 1), (1, 0)):
+            p = oracle.tensor_pack(x, bm, bn, perm)
+            mb, nb = m // bm, n // bn
+            assert p.shape == ((nb, mb, bm, bn) if perm == (1, 0) else (mb, nb, bm, bn))
+            for i in range(mb):
+                for j in range(nb):
+                    tile = p[j, i] if perm == (1, 0) else p[i, j]
+                    assert np.array_equal(tile, x[i * bm:(i + 1) * bm, j * bn:(j + 1) * bn])
+            assert np.array_equal(oracle.tensor_unpack(p, perm), x)

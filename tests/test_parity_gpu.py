@@ -1007,3 +1007,110 @@ def test_pair_kernel_without_bias_or_relu_and_with_padded_leading_dims():
         for a in acts[1:]:
             assert (a[:, 1024:] == 0x1234).all(), "padding columns were overwritten"
     g.destroy()
+
+
+# ---- tensor.pack / tensor.unpack: per-tile unary TPPs, batched into one kernel under graph capture ----
+PACK_CASES = [
+    # (dtype, M, N, bm, bn, outer_perm, unpack, transpose_tiles)
+    (F32, 512, 1024, 32, 32, (0, 1), False, False),    # benchmarks/mlir/fp32-pack-gemm-operand-a-512x1024.mlir
+    (F32, 1024, 512, 32, 32, (1, 0), False, False),    # fp32-pack-gemm-operand-b-512x1024.mlir
+    (F32, 512, 512, 32, 32, (0, 1), True, False),      # fp32-unpack-gemm-operand-a-512x512.mlir
+    (BF16, 256, 1024, 32, 32, (0, 1), False, False),   # the MLP's activation packing (mlir-gen --tiles=32,32,32)
+    (BF16, 1024, 1024, 32, 32, (1, 0), False, False),  # ... and its weight packing
+    (BF16, 256, 1024, 32, 32, (0, 1), True, False),
+    (F32, 120, 200, 24, 40, (0, 1), False, False),     # rows that are no multiple of 16 bytes apart: scalar path
+    (BF16, 96, 168, 12, 21, (1, 0), True, False),      # odd tile width
+    (BF16, 256, 512, 32, 64, (0, 1), False, True),     # tiles stored transposed (xsmm.unary transpose per tile)
+    (F32, 128, 192, 32, 48, (1, 0), True, True),
+]
+
+
+@pytest.mark.parametrize("case", PACK_CASES, ids=lambda c: f"{'bf16' if c[0] == BF16 else 'f32'}-{c[1]}x{c[2]}-t{c[3]}x{c[4]}-"
+                                                           f"{'perm' if c[5] == (1, 0) else 'id'}-"
+                                                           f"{'unpack' if c[6] else 'pack'}{'-T' if c[7] else ''}")
+def test_tiled_pack_unpack_is_one_batched_kernel_and_bit_exact(case):
+    """The per-tile invoke sequence of a lowered tensor.pack / unpack, issued (a) directly - one launch per tile - and
+    (b) inside a graph capture, where the runtime batches the run into ONE kernel. Both must equal the numpy restatement
+    of the op bit for bit, and bytes outside the destination tiles must stay untouched."""
+    import torch
+
+    from tpp_mlir_b200 import harness, xsmm
+
+    dtype, M, N, bm, bn, perm, unpack, tt = case
+    npdt = np.float32 if dtype == F32 else np.uint16
+    rng = np.random.default_rng(M * 7 + N)
+    flat = (rng.standard_normal((M, N)).astype(np.float32) if dtype == F32
+            else rng.integers(0, 65535, size=(M, N), dtype=np.uint16))
+    packed = oracle.tensor_pack(flat, bm, bn, perm)
+    if tt:
+        packed = np.ascontiguousarray(packed.transpose(0, 1, 3, 2))
+    tdt = torch.float32 if dtype == F32 else torch.int16
+
+    def dev_t(a):
+        return torch.from_numpy(a.view(np.int16) if dtype == BF16 else a).cuda()
+
+    src_np, want = (packed, flat) if unpack else (flat, packed)
+    src = dev_t(src_np)
+    rp = harness.PackReplay(dtype, M, N, bm, bn, perm, unpack=unpack, transpose_tiles=tt)
+    results = []
+    for mode in ("direct", "captured"):
+        dst = torch.zeros(want.size, dtype=tdt, device="cuda")
+        args = (dst, src) if unpack else (src, dst)
+        n0 = xsmm.launch_count()
+        if mode == "direct":
+            rp.run(*args)
+            xsmm.sync()
+            assert xsmm.launch_count() - n0 == rp.num_tiles
+        else:
+            with xsmm.graph_capture() as g:
+                rp.run(*args)
+            assert f"batch{rp.num_tiles}" in xsmm.last_kernel(), xsmm.last_kernel()
+            n0 = xsmm.launch_count()
+            g.launch()
+            xsmm.sync()
+            assert xsmm.launch_count() - n0 == 1, "the tiles of one pack must share one launch"
+            dst.zero_()
+            g.launch()   # replay
+            xsmm.sync()
+            g.destroy()
+        got = dst.cpu().numpy().view(npdt).reshape(want.shape)
+        assert np.array_equal(got, want), f"{mode}: pack/unpack result differs"
+        results.append(got)
+
+
+def test_captured_tile_moves_respect_dependencies():
+    """Tile copies that read what an earlier one wrote (a -> b -> c -> d -> e) or overwrite what an earlier one wrote
+    must not be reordered into one batch; copies into disjoint tiles of ONE matrix (interleaved in address space) still
+    batch. Mixed with BRGEMMs recorded during the same capture."""
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    h = xsmm.unary_dispatch(xsmm.UNARY_IDENTITY, F32, 32, 32, 32, 32, 0)
+    bufs = [torch.zeros(32 * 32, device="cuda") for _ in range(6)]
+    bufs[0].copy_(torch.arange(1024, dtype=torch.float32))
+    other = torch.full((1024,), 5.0, device="cuda")
+    with xsmm.graph_capture() as g:
+        for i in range(5):
+            xsmm.unary_invoke(F32, h, bufs[i], 0, bufs[i + 1], 0)       # chain: each reads the previous output
+        xsmm.unary_invoke(F32, h, other, 0, bufs[1], 0)                  # WAW + WAR on bufs[1]
+    n0 = xsmm.launch_count()
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == 6, "dependent copies must stay separate launches"
+    assert torch.equal(bufs[5], bufs[0]) and torch.equal(bufs[1], other)
+    g.destroy()
+    # 16 tiles of one 128 x 128 matrix copied into another one: bounding ranges interleave, elements are disjoint
+    ht = xsmm.unary_dispatch(xsmm.UNARY_IDENTITY, F32, 32, 32, 128, 128, 0)
+    a = torch.arange(128 * 128, dtype=torch.float32, device="cuda")
+    b = torch.zeros(128 * 128, device="cuda")
+    with xsmm.graph_capture() as g:
+        for i in range(4):
+            for j in range(4):
+                off = i * 32 * 128 + j * 32
+                xsmm.unary_invoke(F32, ht, a, off, b, off)
+    assert "batch16" in xsmm.last_kernel(), xsmm.last_kernel()
+    g.launch()
+    xsmm.sync()
+    assert torch.equal(a, b)
+    g.destroy()

@@ -422,6 +422,73 @@ void launch_transpose(const void *in, void *out, int64_t m, int64_t n, int64_t l
   TPP_CUDA_CHECK(cudaGetLastError());
 }
 
+// ---- batched tile moves (block-layout pack / unpack as ONE kernel) -----------------------------------
+// tensor.pack / tensor.unpack reach the ABI as one xsmm_unary_invoke (identity, or transpose) per tile with the same
+// descriptor (lib/TPP/Transforms/LowerPacksAndUnpacks.cpp:143-250 tiles the pack by one outer tile,
+// ConvertLinalgToXsmm turns each tile's copy / transpose into a unary TPP): hundreds of 2-4 KiB moves. During graph
+// capture the runtime collects such runs and launches this kernel once: CTA t moves tile t, (in, out) pointers come from a
+// device table.
+template <typename V>
+__global__ void __launch_bounds__(256) tile_copy_batch_kernel(const TilePtrs *__restrict__ tiles, int64_t m, int64_t nv,
+                                                              int64_t ldi_v, int64_t ldo_v) {
+  const TilePtrs t = tiles[blockIdx.x];
+  const V *__restrict__ in = static_cast<const V *>(t.in);
+  V *__restrict__ out = static_cast<V *>(t.out);
+  const int64_t total = m * nv;
+  for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.y * blockDim.x) {
+    const int64_t r = e / nv, c = e - r * nv;
+    out[r * ldo_v + c] = in[r * ldi_v + c];
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) tile_transpose_batch_kernel(const TilePtrs *__restrict__ tiles, int64_t m, int64_t n,
+                                                                   int64_t ldi, int64_t ldo) {
+  constexpr int TILE = 32;
+  __shared__ T sm[TILE][TILE + 1];
+  const TilePtrs t = tiles[blockIdx.x];
+  const T *__restrict__ in = static_cast<const T *>(t.in);
+  T *__restrict__ out = static_cast<T *>(t.out);
+  const int64_t tiles_n = (n + TILE - 1) / TILE, tiles_m = (m + TILE - 1) / TILE;
+  const int tx = threadIdx.x % TILE, ty = threadIdx.x / TILE;   // 32 x 8
+  for (int64_t b = blockIdx.y; b < tiles_m * tiles_n; b += gridDim.y) {
+    const int64_t i0 = (b / tiles_n) * TILE, j0 = (b % tiles_n) * TILE;
+#pragma unroll
+    for (int r = ty; r < TILE; r += 8) {
+      const int64_t i = i0 + r, j = j0 + tx;
+      if (i < m && j < n) sm[r][tx] = in[i * ldi + j];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < TILE; r += 8) {
+      const int64_t j = j0 + r, i = i0 + tx;   // out row j, col i
+      if (i < m && j < n) out[j * ldo + i] = sm[tx][r];
+    }
+    __syncthreads();
+  }
+}
+
+void launch_tile_batch(const TilePtrs *dev_tiles, int64_t num_tiles, bool transpose, int64_t m, int64_t n, int64_t ldi,
+                       int64_t ldo, int es, bool vec16_ok, cudaStream_t stream) {
+  if (num_tiles <= 0 || m <= 0 || n <= 0) return;
+  if (transpose) {
+    const int64_t sub = ((m + 31) / 32) * ((n + 31) / 32);
+    dim3 grid((unsigned)num_tiles, (unsigned)(sub < 64 ? sub : 64));
+    if (es == 4) tile_transpose_batch_kernel<uint32_t><<<grid, 256, 0, stream>>>(dev_tiles, m, n, ldi, ldo);
+    else tile_transpose_batch_kernel<uint16_t><<<grid, 256, 0, stream>>>(dev_tiles, m, n, ldi, ldo);
+  } else if (vec16_ok) {
+    const int64_t per = 16 / es, nv = n / per, chunks = (m * nv + 255) / 256;
+    dim3 grid((unsigned)num_tiles, (unsigned)(chunks < 64 ? chunks : 64));
+    tile_copy_batch_kernel<uint4><<<grid, 256, 0, stream>>>(dev_tiles, m, nv, ldi / per, ldo / per);
+  } else {
+    const int64_t chunks = (m * n + 255) / 256;
+    dim3 grid((unsigned)num_tiles, (unsigned)(chunks < 64 ? chunks : 64));
+    if (es == 4) tile_copy_batch_kernel<uint32_t><<<grid, 256, 0, stream>>>(dev_tiles, m, n, ldi, ldo);
+    else tile_copy_batch_kernel<uint16_t><<<grid, 256, 0, stream>>>(dev_tiles, m, n, ldi, ldo);
+  }
+  TPP_CUDA_CHECK(cudaGetLastError());
+}
+
 void launch_vnni2_pack(const void *in, void *out, int64_t m, int64_t n, int64_t ldi, int64_t ldo,
                        cudaStream_t stream) {
   if (m <= 0 || n <= 0) return;

@@ -35,6 +35,16 @@ void launch_vnni2_pack(const void *in, void *out, int64_t m, int64_t n, int64_t 
 void launch_vnni2_unpack(const void *in, void *out, int64_t m, int64_t n, int64_t ldi, int64_t ldo,
                          cudaStream_t stream);
 
+// one tile of a batched tile move (identity copy or transpose, same m / n / ldi / ldo for the whole batch)
+struct TilePtrs {
+  const void *in;
+  void *out;
+};
+// num_tiles moves in ONE launch; dev_tiles is a device array. vec16_ok: every pointer and both row pitches are
+// multiples of 16 bytes and so is a row of n elements (identity only)
+void launch_tile_batch(const TilePtrs *dev_tiles, int64_t num_tiles, bool transpose, int64_t m, int64_t n, int64_t ldi,
+                       int64_t ldo, int es, bool vec16_ok, cudaStream_t stream);
+
 struct GemmArgs {
   const void *A = nullptr;
   const void *B = nullptr;

@@ -86,10 +86,20 @@ struct PendingGemm {
   GemmArgs g;
 };
 
+// a data-movement unary invoke (identity copy or transpose of one tile) recorded during graph capture
+struct PendingTile {
+  const KernelDesc *d;
+  char *in, *out;
+};
+
 struct ThreadCtx {
   // BRGEMM invokes recorded during graph capture and not launched yet: consecutive layers whose C is the next
   // layer's A are fused into one persistent kernel when the sequence is flushed (see flush_pending)
   std::vector<PendingGemm> pending;
+  // run of tile moves with ONE descriptor and no hazards among them (a tensor.pack / unpack lowered tile by tile):
+  // launched as one batched kernel by flush_tiles(). At most one of the two pending lists is non-empty.
+  std::vector<PendingTile> pending_tiles;
+  std::vector<void *> capture_tables;   // device tables baked into the graph being captured (freed with it)
   cudaStream_t stream = nullptr; // legacy default stream unless xsmm_cuda_set_stream was called
   int device = -1;               // device this thread last launched on
   const char *last_kernel = "";
@@ -427,11 +437,14 @@ void issue_gemm(const KernelDesc *d, const GemmArgs &g, cudaStream_t stream) {
 // (C of layer l is A of layer l+1, same m / n, tensor-core eligible) go to the persistent fused kernel
 // ("whole-MLP fusion ... or CUDA-graph capture of the invoke sequence"); everything else is
 // launched exactly as a direct invoke would.
+void flush_tiles();
+
 void flush_pending() {
   if (t_ctx.up_pending) {   // kernels issued from here on see every upload_async issued before them
     TPP_CUDA_CHECK(cudaStreamWaitEvent(t_ctx.stream, t_ctx.ev_up, 0));
     t_ctx.up_pending = false;
   }
+  flush_tiles();
   if (t_ctx.pending.empty()) return;
   std::vector<PendingGemm> list;
   list.swap(t_ctx.pending);
@@ -547,6 +560,7 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
     t_ctx.note_output(ops[2].dev, (size_t)((d->m - 1) * d->ldc + d->n) * es);
   }
   if (t_ctx.capturing && !sc.any_host && d->impl == KernelImpl::BrgemmTC) {
+    flush_tiles();
     t_ctx.pending.push_back({d, g});   // launched (possibly fused with its neighbours) by flush_pending()
     return;
   }
@@ -694,9 +708,108 @@ extern "C" void xsmm_fused_brgemm_invoke(int64_t dtype, int64_t addr, void *alig
                      numBatches);
 }
 
+namespace {
+// launch one unary TPP on resolved device operands
+void launch_unary(const KernelDesc *d, const char *in, char *out, bool use_imm, float imm, cudaStream_t stream) {
+  switch (d->impl) {
+  case KernelImpl::Transpose:
+    launch_transpose(in, out, d->m, d->n, d->ldi, d->ldo, (int)esize(d->dtype), stream);
+    break;
+  case KernelImpl::Vnni2Pack:
+    launch_vnni2_pack(in, out, d->m, d->n, d->ldi, d->ldo, stream);
+    break;
+  case KernelImpl::Vnni2Unpack:
+    launch_vnni2_unpack(in, out, d->m, d->n, d->ldi, d->ldo, stream);
+    break;
+  default: {
+    EltwiseArgs a;
+    a.in0 = in; a.out = out;
+    a.m = d->m; a.n = d->n; a.ld0 = d->ldi; a.ldo = d->ldo;
+    a.mode0 = use_imm ? kBcastImm : bcast_mode_unary(d->flags);
+    a.imm = imm;
+    a.op = d->kind == XSMM_UNARY_ZERO ? kOpZero : d->kind == XSMM_UNARY_RELU ? kOpRelu : kOpIdentity;
+    a.dtype = d->dtype;
+    launch_eltwise(a, stream);
+  }
+  }
+}
+
+// Do two pitched rectangles of bytes share a byte? Exact when both have the same pitch (tiles of one matrix interleave
+// in address space without touching), conservative (bounding ranges) otherwise.
+bool rects_overlap(const char *a, int64_t a_rows, int64_t a_w, int64_t a_ld, const char *b, int64_t b_rows, int64_t b_w,
+                   int64_t b_ld) {
+  const char *a_hi = a + (a_rows - 1) * a_ld + a_w, *b_hi = b + (b_rows - 1) * b_ld + b_w;
+  if (!(a < b_hi && b < a_hi)) return false;
+  if (a_ld != b_ld || a_ld <= 0) return true;
+  if (b < a) { std::swap(a, b); std::swap(a_rows, b_rows); std::swap(a_w, b_w); }
+  const int64_t delta = b - a, dr = delta / a_ld, dc = delta % a_ld;   // b's first byte sits at row dr, column dc of a's grid
+  if (dr < a_rows && dc < a_w) return true;
+  if (dc + b_w > a_ld && dr + 1 < a_rows) return true;                 // b's rows wrap into the next grid row, column 0
+  return false;
+}
+
+struct TileRects { const char *in; char *out; int64_t in_rows, in_w, in_ld, out_rows, out_w, out_ld; };
+TileRects tile_rects(const KernelDesc *d, const char *in, char *out) {
+  const int64_t es = (int64_t)esize(d->dtype);
+  if (d->impl == KernelImpl::Transpose) return {in, out, d->m, d->n * es, d->ldi * es, d->n, d->m * es, d->ldo * es};
+  return {in, out, d->m, d->n * es, d->ldi * es, d->m, d->n * es, d->ldo * es};
+}
+
+// Launch the tile moves recorded during graph capture: four or more become ONE batched kernel reading a device table
+// of (in, out) pointers, fewer are launched as they would have been.
+void flush_tiles() {
+  if (t_ctx.pending_tiles.empty()) return;
+  std::vector<PendingTile> list;
+  list.swap(t_ctx.pending_tiles);
+  cudaStream_t stream = t_ctx.stream;
+  const KernelDesc *d = list[0].d;
+  if (list.size() < 4) {
+    for (const PendingTile &t : list) {
+      launch_unary(d, t.in, t.out, false, 0.f, stream);
+      count_launch();
+    }
+    t_ctx.last_kernel = d->name;
+    return;
+  }
+  const int64_t es = (int64_t)esize(d->dtype);
+  std::vector<TilePtrs> host(list.size());
+  bool vec_ok = d->impl != KernelImpl::Transpose && ((d->n * es) % 16) == 0 && ((d->ldi * es) % 16) == 0 &&
+                ((d->ldo * es) % 16) == 0;
+  for (size_t i = 0; i < list.size(); ++i) {
+    host[i] = {list[i].in, list[i].out};
+    vec_ok = vec_ok && aligned16(list[i].in) && aligned16(list[i].out);
+  }
+  // the table is written now, outside the capture; the graph only holds the kernel that reads it
+  static thread_local cudaStream_t side = nullptr;
+  if (!side) TPP_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+  TilePtrs *table = nullptr;
+  TPP_CUDA_CHECK(cudaMalloc(&table, host.size() * sizeof(TilePtrs)));
+  TPP_CUDA_CHECK(cudaMemcpyAsync(table, host.data(), host.size() * sizeof(TilePtrs), cudaMemcpyHostToDevice, side));
+  TPP_CUDA_CHECK(cudaStreamSynchronize(side));
+  t_ctx.capture_tables.push_back(table);
+  launch_tile_batch(table, (int64_t)host.size(), d->impl == KernelImpl::Transpose, d->m, d->n, d->ldi, d->ldo, (int)es,
+                    vec_ok, stream);
+  static thread_local char name[96];
+  snprintf(name, sizeof(name), "%s_batch%zu", d->name, host.size());
+  t_ctx.last_kernel = name;
+  count_launch();
+}
+}  // namespace
+
 static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int64_t offIn, bool use_imm, float imm,
                               void *pOut, int64_t offOut) {
-  flush_pending();
+  // tile moves (plain identity copy / transpose) issued during graph capture are collected, see flush_tiles()
+  const bool batchable = t_ctx.capturing && !use_imm &&
+                         (d->impl == KernelImpl::Transpose ||
+                          (d->impl == KernelImpl::Eltwise && d->kind == XSMM_UNARY_IDENTITY && d->flags == 0));
+  if (batchable) {
+    std::vector<PendingTile> keep;
+    keep.swap(t_ctx.pending_tiles);   // flush_pending() must not launch the run this invoke may still join
+    flush_pending();
+    keep.swap(t_ctx.pending_tiles);
+  } else {
+    flush_pending();
+  }
   if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
   Operand ops[2];
   const int mode = bcast_mode_unary(d->flags);
@@ -729,27 +842,26 @@ static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int
   cudaStream_t stream = t_ctx.stream;
   StagedCall sc{ops, 2, esize(dtype)};
   stage_in(sc, stream);
-  switch (d->impl) {
-  case KernelImpl::Transpose:
-    launch_transpose(ops[0].dev, ops[1].dev, d->m, d->n, d->ldi, d->ldo, (int)esize(dtype), stream);
-    break;
-  case KernelImpl::Vnni2Pack:
-    launch_vnni2_pack(ops[0].dev, ops[1].dev, d->m, d->n, d->ldi, d->ldo, stream);
-    break;
-  case KernelImpl::Vnni2Unpack:
-    launch_vnni2_unpack(ops[0].dev, ops[1].dev, d->m, d->n, d->ldi, d->ldo, stream);
-    break;
-  default: {
-    EltwiseArgs a;
-    a.in0 = ops[0].dev; a.out = ops[1].dev;
-    a.m = d->m; a.n = d->n; a.ld0 = d->ldi; a.ldo = d->ldo;
-    a.mode0 = use_imm ? kBcastImm : mode;
-    a.imm = imm;
-    a.op = d->kind == XSMM_UNARY_ZERO ? kOpZero : d->kind == XSMM_UNARY_RELU ? kOpRelu : kOpIdentity;
-    a.dtype = dtype;
-    launch_eltwise(a, stream);
+  if (batchable && !sc.any_host) {
+    // joins the pending run if it has the same descriptor and neither reads nor writes anything the run writes (nor
+    // writes anything the run reads); otherwise the run is launched first and this invoke starts a new one
+    const TileRects nr = tile_rects(d, ops[0].dev, ops[1].dev);
+    bool join = t_ctx.pending_tiles.empty() || (t_ctx.pending_tiles[0].d == d && t_ctx.pending_tiles.size() < 8192);
+    for (size_t i = 0; join && i < t_ctx.pending_tiles.size(); ++i) {
+      const TileRects pr = tile_rects(d, t_ctx.pending_tiles[i].in, t_ctx.pending_tiles[i].out);
+      if (rects_overlap(nr.out, nr.out_rows, nr.out_w, nr.out_ld, pr.out, pr.out_rows, pr.out_w, pr.out_ld) ||
+          rects_overlap(nr.out, nr.out_rows, nr.out_w, nr.out_ld, pr.in, pr.in_rows, pr.in_w, pr.in_ld) ||
+          rects_overlap(nr.in, nr.in_rows, nr.in_w, nr.in_ld, pr.out, pr.out_rows, pr.out_w, pr.out_ld))
+        join = false;
+    }
+    if (!join) flush_tiles();
+    t_ctx.pending_tiles.push_back({d, ops[0].dev, ops[1].dev});
+    t_ctx.note_output(ops[1].dev, (size_t)((ops[1].rows - 1) * ops[1].ld + ops[1].width) * esize(dtype));
+    return;
   }
-  }
+  flush_tiles();
+  (void)mode;
+  launch_unary(d, ops[0].dev, ops[1].dev, use_imm, imm, stream);
   t_ctx.note_output(ops[1].dev, (size_t)((ops[1].rows - 1) * ops[1].ld + ops[1].width) * esize(dtype));
   t_ctx.last_kernel = d->name;
   count_launch();
@@ -1028,6 +1140,8 @@ extern "C" int64_t xsmm_cuda_graph_end(void) {
   t_ctx.stream = t_ctx.saved_stream;
   std::vector<void *> tables;
   brgemm_tc_take_capture_allocs(tables);
+  tables.insert(tables.end(), t_ctx.capture_tables.begin(), t_ctx.capture_tables.end());
+  t_ctx.capture_tables.clear();
   if (e != cudaSuccess || !graph) {
     fprintf(stderr, "tpp-xsmm-cuda: graph capture failed: %s\n", cudaGetErrorString(e));
     cudaGetLastError();

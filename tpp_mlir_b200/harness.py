@@ -143,6 +143,43 @@ def bench_loop(fn, n: int):
     return xsmm.perf_stop_timer(t0) / n
 
 
+# ---- tensor.pack / tensor.unpack as the reference lowers them: one unary TPP per tile -------------------
+class PackReplay:
+    """The invoke sequence of a tiled ``tensor.pack`` / ``tensor.unpack`` (inner_dims_pos = [0, 1], inner_tiles =
+    [bm, bn], optional outer_dims_perm = [1, 0]): the reference tiles the op by one outer tile and turns every tile's
+    copy into a ``xsmm.unary identity`` with ldi / ldo (lib/TPP/Transforms/LowerPacksAndUnpacks.cpp:143-250;
+    benchmarks/mlir/fp32-pack-gemm-operand-a-512x1024.mlir). ``transpose_tiles`` replays the variant whose tiles are
+    stored transposed ([..][bn][bm], ``xsmm.unary transpose`` per tile)."""
+
+    def __init__(self, dtype, m, n, bm, bn, outer_perm=(0, 1), unpack=False, transpose_tiles=False):
+        self.dtype, self.m, self.n, self.bm, self.bn = dtype, m, n, bm, bn
+        self.outer_perm, self.unpack, self.transpose_tiles = tuple(outer_perm), unpack, transpose_tiles
+        kind = xsmm.UNARY_TRANSPOSE if transpose_tiles else xsmm.UNARY_IDENTITY
+        if not unpack:       # flat tile (pitch n) -> packed tile (contiguous)
+            self.handle = xsmm.unary_dispatch(kind, dtype, bm, bn, n, bm if transpose_tiles else bn, 0)
+        elif transpose_tiles:   # packed [bn][bm] tile -> flat [bm][bn] tile
+            self.handle = xsmm.unary_dispatch(kind, dtype, bn, bm, bm, n, 0)
+        else:
+            self.handle = xsmm.unary_dispatch(kind, dtype, bm, bn, bn, n, 0)
+
+    @property
+    def num_tiles(self) -> int:
+        return (self.m // self.bm) * (self.n // self.bn)
+
+    def run(self, flat, packed) -> None:
+        """pack: flat -> packed; unpack: packed -> flat. One xsmm_unary_invoke per tile."""
+        mb, nb = self.m // self.bm, self.n // self.bn
+        for i in range(mb):
+            for j in range(nb):
+                off_flat = i * self.bm * self.n + j * self.bn
+                slot = j * mb + i if self.outer_perm == (1, 0) else i * nb + j
+                off_packed = slot * self.bm * self.bn
+                if self.unpack:
+                    xsmm.unary_invoke(self.dtype, self.handle, packed, off_packed, flat, off_flat)
+                else:
+                    xsmm.unary_invoke(self.dtype, self.handle, flat, off_flat, packed, off_packed)
+
+
 # ---- layout helpers (torch; used by tests / bench to build the packed operands) ---------
 def pack_activation(x, bn, bc):
     """[MB][C] -> [MB/bn][C/bc][bn][bc]"""
