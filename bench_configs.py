@@ -6,6 +6,7 @@ measured through the same C-ABI on one B200, each against the roofline that boun
   cfg3b  MLP layer as the strided view k=64 x batch 16 (same math as cfg3)  -> tensor peak
   cfg4   unary vnni_2 4096x4096 bf16 (+ inverse, transpose, relu, bias add) -> HBM bandwidth
   cfg5   MLP 3x1024^2 at batch 2048 on one GPU (what 8 GPUs shard)          -> tensor peak
+  pack   tensor.pack / unpack as per-tile unary TPPs, batched under capture   -> HBM bandwidth
 
 Writes one JSON line per config to stdout (and to --out). Operands rotate over more bytes than the
 126 MiB L2; time = CUDA events on the launch stream after warm-up.
@@ -162,6 +163,48 @@ def eltwise(pk):
     return out
 
 
+def pack(pk):
+    """tensor.pack / unpack lowered to one unary TPP per 32x32 tile (the reference's
+    benchmarks/mlir/fp32-{pack,unpack}-gemm-operand-*.mlir and the bf16 MLP operands), issued (a) as the reference
+    would - one launch per tile - and (b) as a captured graph, where the runtime batches the run into one kernel."""
+    import numpy as np  # noqa: F401
+
+    out = []
+    F32 = xsmm.F32
+    cases = [("fp32 pack operand A 512x1024 (32x32 tiles)", F32, 512, 1024, (0, 1), False),
+             ("fp32 pack operand B 1024x512 (outer_dims_perm [1,0])", F32, 1024, 512, (1, 0), False),
+             ("fp32 unpack 512x512", F32, 512, 512, (0, 1), True),
+             ("bf16 pack 4096x4096 (32x32 tiles, 16384 tiles)", BF16, 4096, 4096, (0, 1), False)]
+    stream = torch.cuda.current_stream()
+    xsmm.set_stream(stream.cuda_stream)
+    for name, dtype, m, n, perm, unpack in cases:
+        es = 4 if dtype == F32 else 2
+        tdt = torch.float32 if dtype == F32 else torch.int16
+        nbytes = m * n * es
+        ns = sets_needed(2 * nbytes)
+        A = [torch.ones(m * n, dtype=tdt, device="cuda") for _ in range(ns)]
+        B = [torch.zeros(m * n, dtype=tdt, device="cuda") for _ in range(ns)]
+        rp = harness.PackReplay(dtype, m, n, 32, 32, perm, unpack=unpack)
+        graphs = []
+        for a, b in zip(A, B):
+            with xsmm.graph_capture() as g:
+                rp.run(*((b, a) if unpack else (a, b)))
+            graphs.append(g)
+        kernel = xsmm.last_kernel()
+        t_batched = timed([g.launch for g in graphs], 20 * ns, warmup=ns)
+        direct_iters = 2 if rp.num_tiles > 4096 else 5
+        t_direct = timed([lambda a=a, b=b: rp.run(*((b, a) if unpack else (a, b))) for a, b in zip(A, B)], direct_iters,
+                         warmup=1)
+        for g in graphs:
+            g.destroy()
+        out.append({"config": f"8f-3 {name}", "kernel": kernel, "tiles": rp.num_tiles, "seconds_batched": t_batched,
+                    "seconds_one_launch_per_tile": t_direct, "speedup": t_direct / t_batched,
+                    "roofline": {"bound": "hbm", "achieved": 2 * nbytes / t_batched / 1e9, "peak": pk["hbm_gbs"],
+                                 "unit": "GB/s", "frac": 2 * nbytes / t_batched / 1e9 / pk["hbm_gbs"],
+                                 "algorithmic_bytes": 2 * nbytes}})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
@@ -181,6 +224,8 @@ def main():
         rows.append(cfg3b(pk))
     if on("cfg4"):
         rows.extend(eltwise(pk))
+    if on("pack"):
+        rows.extend(pack(pk))
     if on("cfg5"):
         rows.append(mlp(pk, 2048, "cfg5 MLP 3x1024^2 batch 2048 on ONE GPU (tiles 2048,1024,1024)", (2048, 1024, 1024)))
         rows.append(mlp(pk, 256, "cfg3 MLP 3x1024^2 batch 256 (graph replay, same as bench.py)", (256, 1024, 1024)))
