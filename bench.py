@@ -407,7 +407,9 @@ def main():
             slot_acts.append([b[j] for b in lvl])
     pipe_loop = harness.NativeMlpLoop(cfg, replay.handles, [(a, h_w, h_b) for a in slot_acts])
     pipe_mode = f"batch{CHAIN_GROUP}"
-    pipe_steps = max(e2e_steps // depth, 2) * depth
+    # enough group iterations that filling and draining the 3-deep pipeline (one upload + kernel + download = ~1.5 ms,
+    # inside the timing) does not dominate: 8 ... 24 rounds over the groups
+    pipe_steps = min(max(args.steps // depth, 8), 24) * depth
     pipe_loop.run_e2e_pipelined(depth, mode=pipe_mode)
     torch.cuda.synchronize(dev)
     for a in slot_acts:
