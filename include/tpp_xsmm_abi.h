@@ -265,6 +265,11 @@ TPP_XSMM_EXPORT const char *xsmm_cuda_handle_kernel(int64_t addr);
 /* Debug: with TPP_XSMM_TC_TRACE=2 in the environment, print the wall-clock timeline of the
  * most recent BRGEMM launches (kernel overlap under PDL / graph replay) to stderr. */
 TPP_XSMM_EXPORT void xsmm_cuda_debug_dump_trace(void);
+/* Debug / test hook (no device needed): the hazard test the capture path uses before it adds a tile move to a
+ * batched run - do two pitched rectangles of bytes (rows x width bytes, pitch ld bytes) share a byte? Exact for
+ * equal pitches (tiles of one matrix interleave in address space without touching), conservative otherwise. */
+TPP_XSMM_EXPORT int64_t xsmm_cuda_debug_rects_overlap(const void *a, int64_t a_rows, int64_t a_width, int64_t a_ld,
+                                                      const void *b, int64_t b_rows, int64_t b_width, int64_t b_ld);
 /* ABI version of this header. */
 TPP_XSMM_EXPORT int64_t xsmm_cuda_abi_version(void);
 

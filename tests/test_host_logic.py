@@ -76,3 +76,49 @@ def test_tensor_pack_oracle_matches_the_tile_loop():
                     tile = p[j, i] if perm == (1, 0) else p[i, j]
                     assert np.array_equal(tile, x[i * bm:(i + 1) * bm, j * bn:(j + 1) * bn])
             assert np.array_equal(oracle.tensor_unpack(p, perm), x)
+
+
+def test_tile_hazard_test_is_exact_for_equal_pitches():
+    """The rectangle-overlap test that guards the batching of captured tile moves (runtime.cu rects_overlap, exported
+    as a debug hook) against a brute-force byte-set comparison: random rectangles of one pitch, including rows that
+    wrap around the pitch; with different pitches it may only err on the safe side."""
+    import ctypes
+
+    import numpy as np
+
+    from tpp_mlir_b200 import _build
+
+    lib = ctypes.CDLL(_build.build())
+    fn = lib.xsmm_cuda_debug_rects_overlap
+    fn.restype = ctypes.c_int64
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64] * 2
+    base = 1 << 20
+
+    def bytes_of(off, rows, width, ld):
+        return {off + r * ld + c for r in range(rows) for c in range(width)}
+
+    rng = np.random.default_rng(11)
+    seen_true = seen_false = 0
+    for _ in range(3000):
+        ld = int(rng.integers(8, 40))
+        ra, wa, rb, wb = (int(rng.integers(1, 6)), int(rng.integers(1, ld + 1)), int(rng.integers(1, 6)),
+                          int(rng.integers(1, ld + 1)))
+        oa, ob = int(rng.integers(0, 6 * ld)), int(rng.integers(0, 6 * ld))
+        want = bool(bytes_of(oa, ra, wa, ld) & bytes_of(ob, rb, wb, ld))
+        got = bool(fn(base + oa, ra, wa, ld, base + ob, rb, wb, ld))
+        assert got == want, (ld, oa, ra, wa, ob, rb, wb)
+        seen_true += want
+        seen_false += not want
+    assert seen_true > 300 and seen_false > 300
+    for _ in range(1000):   # different pitches: never a false negative
+        lda, ldb = int(rng.integers(8, 40)), int(rng.integers(8, 40))
+        ra, wa, rb, wb = (int(rng.integers(1, 6)), int(rng.integers(1, lda + 1)), int(rng.integers(1, 6)),
+                          int(rng.integers(1, ldb + 1)))
+        oa, ob = int(rng.integers(0, 200)), int(rng.integers(0, 200))
+        if bytes_of(oa, ra, wa, lda) & bytes_of(ob, rb, wb, ldb):
+            assert fn(base + oa, ra, wa, lda, base + ob, rb, wb, ldb) == 1
+    # the pack / unpack pattern: 32 x 32 f32 tiles of a 1024-wide matrix are pairwise disjoint
+    ld, w = 1024 * 4, 32 * 4
+    for (i, j) in ((0, 1), (1, 0), (1, 1), (0, 31)):
+        assert fn(base, 32, w, ld, base + i * 32 * ld + j * w, 32, w, ld) == 0
+    assert fn(base, 32, w, ld, base + 31 * ld + w - 1, 32, w, ld) == 1

@@ -1114,3 +1114,47 @@ def test_captured_tile_moves_respect_dependencies():
     xsmm.sync()
     assert torch.equal(a, b)
     g.destroy()
+
+
+def test_pair_kernel_chain_with_layers_of_different_width():
+    """A funnel MLP 1024 -> 512 -> 256 -> 512 (three different dispatches per chain): the number of 256-column output
+    tiles changes from layer to layer, and so does the number of per-tile hand-off barriers each layer boundary uses."""
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    sizes = (1024, 512, 256, 512)
+    n_chains = 14
+    gen = oracle.TensorInit("normal", BF16, 4242)
+
+    def dev_t(a):
+        return torch.from_numpy(a.view(np.int16)).cuda()
+
+    hs = [xsmm.fused_brgemm_dispatch(BF16, 256, n, k, k, n, n, 0, 0, 4, 0, 5, 4, 1) for k, n in zip(sizes[:-1], sizes[1:])]
+    chains = []
+    for _ in range(n_chains):
+        Ws = [gen.fill(k, n) for k, n in zip(sizes[:-1], sizes[1:])]
+        bs = [gen.fill(n) for n in sizes[1:]]
+        x = gen.fill(256, sizes[0])
+        acts = [dev_t(x)] + [torch.zeros(256, n, dtype=torch.int16, device="cuda") for n in sizes[1:]]
+        chains.append((x, Ws, bs, acts, [dev_t(w) for w in Ws], [dev_t(b) for b in bs]))
+    with xsmm.graph_capture() as g:
+        for x, Ws, bs, acts, dW, db in chains:
+            for l, h in enumerate(hs):
+                xsmm.fused_brgemm_invoke(BF16, h, acts[l], 0, dW[l], 0, acts[l + 1], 0, db[l], 0, 1)
+    assert xsmm.last_kernel() == f"mlp_chain_bf16_{n_chains}x3layers_pair256x256", xsmm.last_kernel()
+    for rep in range(2):
+        for c in chains:
+            for a in c[3][1:]:
+                a.fill_(0x7FC0)
+        g.launch()
+        xsmm.sync()
+        for x, Ws, bs, acts, dW, db in chains:
+            ref = x
+            for W, b in zip(Ws, bs):
+                y = np.zeros((256, W.shape[1]), np.uint16)
+                oracle.fused_brgemm(BF16, 256, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4, 0, 5,
+                                    4, 1, ref, W, y, b, 1)
+                ref = y
+            assert_close(BF16, acts[-1].cpu().numpy().view(np.uint16), ref)
+    g.destroy()

@@ -1191,5 +1191,10 @@ extern "C" const char *xsmm_cuda_handle_kernel(int64_t addr) {
   const KernelDesc *d = reinterpret_cast<const KernelDesc *>(addr);
   return (d && d->magic == kDescMagic) ? d->name : "";
 }
+extern "C" int64_t xsmm_cuda_debug_rects_overlap(const void *a, int64_t a_rows, int64_t a_width, int64_t a_ld,
+                                                 const void *b, int64_t b_rows, int64_t b_width, int64_t b_ld) {
+  return rects_overlap(static_cast<const char *>(a), a_rows, a_width, a_ld, static_cast<const char *>(b), b_rows, b_width,
+                       b_ld) ? 1 : 0;
+}
 extern "C" int64_t xsmm_cuda_abi_version(void) { return 1; }
 extern "C" void xsmm_cuda_debug_dump_trace(void) { brgemm_tc_dump_trace(); }
