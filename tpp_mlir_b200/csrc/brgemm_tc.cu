@@ -1656,16 +1656,18 @@ __global__ void __launch_bounds__(F2_THREADS, 1) mlp_chain_fts_kernel(const __gr
 //   * per tile and k-block each CTA stages its 128 activation rows (16 KiB) and HALF of the 256 weight columns (16 KiB);
 //     a layer costs 4 MiB of L2 -> SM traffic per item instead of 16 MiB, every weight byte is fetched exactly once;
 //   * CTA r only ever reads the activation rows it wrote itself (rows 128 r .. 128 r + 127 of the item), so a layer
-//     boundary needs no cross-SM synchronisation at all: the CTA's epilogue warps fence their stores and arrive on a
-//     LOCAL mbarrier, the CTA's producer waits on it before the next layer's first activation box. No counters, no
-//     co-residency assumption, nothing to spin on across SMs;
-//   * the next layer's weights do not depend on anything: their boxes for the first ring slots are issued BEFORE that
-//     wait (same mbarrier, expect_tx covers both operands), so the HBM latency of the weights hides behind the last
-//     epilogue of the previous layer;
-//   * TMEM holds two 256-column accumulators: the epilogue of tile t (tcgen05.ld -> bias -> ReLU -> bf16 -> 16-byte
-//     stores) runs under the MMAs of tile t + 1;
+//     boundary needs no cross-SM synchronisation at all: the epilogue thread that issues the CTA's TMA stores waits
+//     for their completion and arrives on a LOCAL mbarrier per output tile; the CTA's producer waits for tile i / 4
+//     before reduction step i of the next layer's first tile. No counters, no co-residency assumption, nothing to
+//     spin on across SMs; the last epilogue of a layer hides behind 12 of the next tile's 16 reduction steps;
+//   * the next layer's weights do not depend on anything: their box of a ring slot is always issued BEFORE that wait
+//     (same mbarrier, expect_tx covers both operands);
+//   * TMEM holds two 256-column accumulators: the epilogue of tile t (tcgen05.ld -> bias from shared memory -> ReLU ->
+//     bf16 -> swizzled staging buffer -> TMA store) runs under the MMAs of tile t + 1;
+//   * L2 eviction-priority hints keep the activations (re-read once per output tile) resident under the weight stream;
 //   * pairs are independent: the grid is min(items, 74) pairs, pair p takes items p, p + pairs, ...
-// Layer descriptors (two tensor maps + epilogue parameters per layer) live in a device table written once at capture.
+// Layer descriptors (three tensor maps + epilogue parameters per layer) live in a device table written once at capture.
+// History of the measurements that shaped it: profiles/kernel_trace_r1.txt.
 constexpr int PC_STAGES = 6;
 constexpr int PC_BLOCK_N = 256;                       // output columns per tile (UMMA N)
 constexpr int PC_HALF_N = PC_BLOCK_N / 2;             // weight columns staged by each CTA
