@@ -126,6 +126,21 @@ def make_host_data(seed=123):
     return gen, Ws, bs
 
 
+def capture_stdout():
+    """Send everything written to fd 1 from here on (NCCL's version banner, library chatter) to stderr; returns the
+    saved descriptor for restore_stdout(). Rank 0's JSON line must be the ONLY line on stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return saved
+
+
+def restore_stdout(saved):
+    sys.stdout.flush()
+    os.dup2(saved, 1)
+    os.close(saved)
+
+
 def h_out_bits(h_acts, harness, bn, bk):
     """first 8 rows of a host-side output buffer (block-packed) as int32 bf16 bit patterns"""
     import numpy as np
@@ -237,6 +252,7 @@ def main():
     if not torch.cuda.is_available():
         print(json.dumps({"error": "no CUDA device: this backend has no CPU path"}))
         return 1
+    saved_stdout = capture_stdout()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -520,7 +536,9 @@ def main():
                   "parity_rel_err_vs_oracle": rel, "kernel": timed_kernel,
                   "per_layer_kernel": xsmm.handle_kernel(replay.handles[0])},
     }
+    restore_stdout(saved_stdout)
     print(json.dumps(line))
+    sys.stdout.flush()
     if n_gpus > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -122,3 +122,27 @@ def test_tile_hazard_test_is_exact_for_equal_pitches():
     for (i, j) in ((0, 1), (1, 0), (1, 1), (0, 31)):
         assert fn(base, 32, w, ld, base + i * 32 * ld + j * w, 32, w, ld) == 0
     assert fn(base, 32, w, ld, base + 31 * ld + w - 1, 32, w, ld) == 1
+
+
+def test_bench_keeps_library_chatter_off_stdout():
+    """bench.py's stdout contract is ONE JSON line: whatever libraries write to fd 1 while it runs (NCCL prints its
+    version banner there) is diverted to stderr until the line itself is printed."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = "\n".join([
+        "import os, sys",
+        "sys.path.insert(0, %r)" % root,
+        "import bench",
+        "fd = bench.capture_stdout()",
+        "print('python noise')",
+        "os.write(1, b'native noise' + bytes([10]))",
+        "bench.restore_stdout(fd)",
+        "print('{}')",
+    ])
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == "{}\n"
+    assert "python noise" in r.stderr and "native noise" in r.stderr
