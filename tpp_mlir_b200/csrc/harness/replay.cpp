@@ -48,7 +48,8 @@ void tpp_replay_mlp(int64_t dtype, int64_t num_layers, const int64_t *handles, c
 // rotation (num_sets consecutive forward passes, used when `group` != 0 - the loop body unrolled over the
 // rotating operand sets, so the per-graph-launch latency is paid once per rotation). 0 == not captured yet.
 // With `group`, the steps before the first rotation boundary and after the last one are replayed as ONE graph each
-// (captured per (first set, length) on first use), single steps only when one step is left.
+// (captured per (first set, length) on first use), single steps only when one step is left. `graphs` has
+// num_sets + 2 entries: [num_sets + 1] identifies the caller's loop object for those partial graphs.
 __attribute__((visibility("default")))
 int64_t tpp_replay_mlp_graph(int64_t dtype, int64_t num_layers, const int64_t *handles, const int64_t *layer_sizes,
                              int64_t batch, int64_t bn, int64_t bk, int64_t bc, const TppMlpSet *sets,
@@ -73,8 +74,13 @@ int64_t tpp_replay_mlp_graph(int64_t dtype, int64_t num_layers, const int64_t *h
     // (first set, length), so that a run of any length is still a handful of graph launches
     const int64_t chunk = std::min(steps - s, num_sets - idx);
     if (group && chunk >= 2) {
-      static std::map<std::tuple<const void *, const void *, int64_t, int64_t>, int64_t> partial;
-      int64_t &g = partial[std::make_tuple((const void *)sets, (const void *)graphs, idx, chunk)];
+      // keyed by an id that lives in the caller's graphs array (slot num_sets + 1, 0 = not assigned yet), not by
+      // addresses: a later loop object whose arrays land on recycled addresses must not inherit these graphs
+      static std::map<std::tuple<int64_t, int64_t, int64_t>, int64_t> partial;
+      static int64_t next_loop_id = 0;
+      int64_t &loop_id = graphs[num_sets + 1];
+      if (!loop_id) loop_id = ++next_loop_id;
+      int64_t &g = partial[std::make_tuple(loop_id, idx, chunk)];
       if (!g) {
         if (xsmm_cuda_graph_begin() != 0) return -1;
         tpp_replay_mlp(dtype, num_layers, handles, layer_sizes, batch, bn, bk, bc, sets + idx, chunk, 0, chunk, has_bias);

@@ -285,7 +285,7 @@ class NativeMlpLoop:
         cfg = self.cfg
         bn, bk, bc = cfg.tiles
         if not hasattr(self, "_graphs"):
-            self._graphs = (_ct.c_int64 * (self.num_sets + 1))()
+            self._graphs = (_ct.c_int64 * (self.num_sets + 2))()   # per-set graphs, the rotation graph, the loop's id
         rc = replay_lib().tpp_replay_mlp_graph(cfg.dtype, cfg.num_layers, self._handles, self._sizes, cfg.batch, bn,
                                                bk, bc, self._sets, self.num_sets, self._graphs, self._step, steps,
                                                1 if cfg.bias else 0, 1 if group else 0)
