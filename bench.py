@@ -1,29 +1,35 @@
 #!/usr/bin/env python
 """bench.py - fused-BRGEMM MLP (bf16, 3 x 1024^2, batch 256 per GPU) through the xsmm C-ABI.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--global-batch B]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A "step" is one forward pass of the reference's benchmark workload
-(`mlir-gen --kernel=const --bias --relu --float-type=bf16 --batch=256
---layers=1024,1024,1024,1024 --tiles=256,1024,1024`, benchmarks/config/omp/mlir-bf16.json:34-62
-with the GPU tile setting of SURVEY.md Appendix B): 3 x xsmm_fused_brgemm_invoke
-(m=256, n=1024, k=1024, bias add + ReLU fused), issued by the native replay loop
+Workload = the reference's benchmark (`mlir-gen --kernel=const --bias --relu --float-type=bf16 --batch=256
+--layers=1024,1024,1024,1024`, benchmarks/config/omp/mlir-bf16.json:34-62): one FORWARD PASS is 3 x
+xsmm_fused_brgemm_invoke (m=256, n=1024, k=1024, bias add + ReLU fused), issued by the native replay loop
 (tpp_mlir_b200/csrc/harness/replay.cpp) exactly as tpp-run's JIT-compiled loop would.
 
-Metric = the reference's own: BENCH_TOTAL_FLOPS / mean seconds / 1e9 (benchmarks/harness/
-controller.py:187-192), FLOPs counted as mlir-gen does (MLIRGen.cpp:313-334).
+A STEP is STEP_ROTATIONS (2) rotations over the operand sets: 2 x 148 = 296 forward passes in stream order, every
+one on its own copy of weights / biases / activations (1.2 GB >> 126 MiB L2, so every step streams its operands
+from HBM - the "inputs larger than L2" rule). The number of forward passes per launch does NOT depend on --steps:
+one rotation is one captured graph (xsmm_cuda_graph_*), which the runtime turns into one launch of the
+pair-per-chain kernel, so `--steps 20` times 40 full launches.
 
-N > 1: the batch dimension is sharded (weak scaling: 256 rows per GPU, global batch 256*N,
-BASELINE config 5 at N=8); weights/biases are broadcast once from rank 0 over NCCL; there is no
-collective inside the timed loop. Prints ONE JSON line on rank 0.
+Metric = the reference's own: BENCH_TOTAL_FLOPS / mean seconds / 1e9 (benchmarks/harness/controller.py:187-192),
+FLOPs counted as mlir-gen does (MLIRGen.cpp:313-334). The reference's benchmark loop itself re-runs ONE forward pass
+on ONE set of buffers back to back (lib/TPP/Runner/MLIRBench.cpp:265-300): that sequential, L2-hot number is the
+first-class `latency` field, timed with perf_start_timer / perf_stop_timer like tpp-run does.
+
+N > 1: the batch dimension is sharded (default weak scaling: 256 rows per GPU, global batch 256*N = BASELINE
+configs[4] at N=8; --global-batch 2048 runs configs[4] as strong scaling, 2048/N rows per GPU); weights/biases are
+broadcast once from rank 0 over NCCL; no collective inside the timed loop; every rank's output is gathered and
+checked against the oracle on rank 0. Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -33,10 +39,12 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 LAYERS = (1024, 1024, 1024, 1024)
-CHAIN_GROUP = 74        # forward passes per launch group: one per CTA pair of the pair-per-chain kernel (148 SMs / 2)
-PIPE_GROUPS = int(os.environ.get("TPP_BENCH_PIPE_GROUPS", "3"))   # launch groups in flight in the end-to-end leg (upload | kernel | download)
+NUM_PAIRS = 74          # CTA pairs of the pair-per-chain kernel (148 SMs / 2)
+ROW_BLOCK = 256         # batch rows per work item of that kernel
+STEP_ROTATIONS = 2      # rotations over the operand sets per step
+CHAIN_GROUP = NUM_PAIRS  # forward passes per launch group of the end-to-end leg
+PIPE_GROUPS = int(os.environ.get("TPP_BENCH_PIPE_GROUPS", "3"))   # launch groups in flight in the end-to-end leg
 BATCH_PER_GPU = 256
-TILES = (256, 1024, 1024)
 L2_BYTES = 126 * 1024 * 1024
 METRIC = "fused_brgemm_mlp_bf16_3x1024_b256_gflops"
 UNIT = "GFLOP/s"
@@ -126,6 +134,34 @@ def make_host_data(seed=123):
     return gen, Ws, bs
 
 
+def oracle_forward(x, Ws, bs, fast=False):
+    """The pinned oracle (oracle/xsmm_oracle.c) over all layers; bf16 bits in, bf16 bits out."""
+    import numpy as np
+
+    import oracle
+
+    a = np.ascontiguousarray(x)
+    for W, b in zip(Ws, bs):
+        rows = a.shape[0]
+        y = np.empty((rows, W.shape[1]), np.uint16)
+        done = fast and oracle.fused_brgemm_fast(2, rows, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0,
+                                                 0, 4, 5, 4, 1, a, W, y, b, 1)
+        if not done:
+            oracle.fused_brgemm(2, rows, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4, 0, 5, 4,
+                                1, a, W, y, b, 1)
+        a = y
+    return a
+
+
+def rel_err(got_bits, want_bits):
+    import numpy as np
+
+    import oracle
+
+    g, w = oracle.bf16_to_f32(got_bits), oracle.bf16_to_f32(want_bits)
+    return float(np.abs(g - w).max() / max(np.abs(w).max(), 1e-30))
+
+
 def capture_stdout():
     """Send everything written to fd 1 from here on (NCCL's version banner, library chatter) to stderr; returns the
     saved descriptor for restore_stdout(). Rank 0's JSON line must be the ONLY line on stdout."""
@@ -141,20 +177,47 @@ def restore_stdout(saved):
     os.close(saved)
 
 
-def h_out_bits(h_acts, harness, bn, bk):
-    """first 8 rows of a host-side output buffer (block-packed) as int32 bf16 bit patterns"""
+def torch_onednn_proxy(steps=20, warmup=5):
+    """BASELINE.md's second CPU proxy (`cpu_torch_onednn`): PyTorch-CPU bf16 relu(x @ W + b) x 3 (oneDNN picks its
+    AMX / AVX512-BF16 JIT kernels) on the same shapes and data, all usable host threads."""
     import numpy as np
+    import torch
 
-    o = harness.unpack_activation(h_acts[-1].reshape(BATCH_PER_GPU // bn, LAYERS[-1] // bk, bn, bk))[:8].numpy()
-    return o.view(np.uint16).astype(np.int32)
+    _, Ws, bs = make_host_data()
+    gen = make_host_data()[0]
+    x = gen.fill(BATCH_PER_GPU, LAYERS[0])
+
+    def t(a):
+        return torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16)
+
+    tx, tW, tb = t(x), [t(W) for W in Ws], [t(b) for b in bs]
+    best = None
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for nt in sorted({min(avail, v) for v in (8, 16, 32, avail)}):
+        torch.set_num_threads(nt)
+        with torch.no_grad():
+            def fwd():
+                a = tx
+                for W, b in zip(tW, tb):
+                    a = torch.relu(torch.addmm(b, a, W))
+                return a
+            for _ in range(warmup):
+                fwd()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fwd()
+            dt = (time.perf_counter() - t0) / steps
+        if best is None or dt < best[0]:
+            best = (dt, nt)
+    flops = sum(2 * BATCH_PER_GPU * c * k + 2 * BATCH_PER_GPU * k for c, k in zip(LAYERS[:-1], LAYERS[1:]))
+    return {"value": flops / best[0] / 1e9, "unit": UNIT, "cores": best[1], "kind": "proxy (torch CPU bf16, oneDNN)",
+            "ms_per_forward": best[0] * 1e3}
 
 
-def cpu_arm(steps, warmup, total_budget_s, verbose=False):
+def cpu_arm(steps, warmup, total_budget_s):
     """The reference's CPU path for this workload, timed on this box's host cores.
     kind = "port": oracle/ (libxsmm is not buildable offline). Each step is a
     bounded sample: `rows` of the 256 batch rows through all three layers."""
-    import numpy as np
-
     import oracle
 
     oracle.use_native(True)  # -march=native build for the box it is timed on
@@ -163,15 +226,7 @@ def cpu_arm(steps, warmup, total_budget_s, verbose=False):
     x = gen.fill(BATCH_PER_GPU, LAYERS[0])
 
     def forward(rows):
-        a = x[:rows]
-        for W, b in zip(Ws, bs):
-            y = np.empty((rows, W.shape[1]), np.uint16)
-            if not oracle.fused_brgemm_fast(2, rows, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4,
-                                            5, 4, 1, a, W, y, b, 1):
-                oracle.fused_brgemm(2, rows, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4, 0, 5,
-                                    4, 1, a, W, y, b, 1)
-            a = y
-        return a
+        return oracle_forward(x[:rows], Ws, bs, fast=True)
 
     # "all the host threads it can use": the usable count is not os.cpu_count() inside a container with a CPU
     # quota - try a ladder of thread counts on one forward pass each and keep the fastest
@@ -200,7 +255,7 @@ def cpu_arm(steps, warmup, total_budget_s, verbose=False):
     dt = (time.perf_counter() - t) / steps
     flops = sum(2 * rows * c * k + 2 * rows * k for c, k in zip(LAYERS[:-1], LAYERS[1:]))
     return {"value": flops / dt / 1e9, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-            "sample": f"{rows} of {BATCH_PER_GPU} batch rows x 3 layers per step, {steps} steps "
+            "sample": f"{rows} of {BATCH_PER_GPU} batch rows x 3 layers per CPU step, {steps} steps "
                       f"(oracle/xsmm_oracle_fast.c: {oracle.fast_isa()}, OpenMP {oracle.num_threads()} threads, "
                       f"gcc -O3 -march=native; libxsmm itself is not buildable offline)",
             "ms_per_step": dt * 1e3, "rows": rows}
@@ -209,14 +264,21 @@ def cpu_arm(steps, warmup, total_budget_s, verbose=False):
 def reference_main(args, rank):
     if rank != 0:
         return 0
-    res = cpu_arm(args.steps, args.warmup, total_budget_s=150.0)
+    res = cpu_arm(args.steps, args.warmup, total_budget_s=120.0)
+    try:
+        proxy = torch_onednn_proxy()
+    except Exception as e:  # torch CPU bf16 matmul missing on an odd host: the port number stands alone
+        proxy = {"error": repr(e)}
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (TensorInit normal, seed 123)",
         "config": {"workload": "fused_brgemm MLP 3x(256x1024x1024)+bias+relu bf16, batch 256", "layers": list(LAYERS),
-                   "global_batch": BATCH_PER_GPU, "parallelism": "host cores (OpenMP)"},
-        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                   "global_batch": BATCH_PER_GPU, "parallelism": "host cores (OpenMP)",
+                   "step": "one forward pass (a bounded row sample of it, see cpu_baseline.sample); the metric is a "
+                           "rate, so it compares with the GPU arm's 296-forward-pass steps"},
+        "cpu_baseline": {**{k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                         "torch_onednn_proxy": proxy},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -224,18 +286,82 @@ def reference_main(args, rank):
     return 0
 
 
+class MlpWorkload:
+    """`num_sets` operand sets of the 3-layer MLP for `m` batch rows on this rank, the dispatched handles and the
+    native replay loop over them. Set s reads the rank's input rolled by s rows (so every set has its own answer:
+    out_s = roll(out_0, s)); weights / biases are private copies per set (HBM traffic like independent requests)."""
+
+    def __init__(self, m, x_shard, w_dev, b_dev, tiles=None, min_sets=0, vnni=False, max_sets=None):
+        import torch
+
+        from tpp_mlir_b200 import harness
+
+        self.m = m
+        self.tiles = tiles or (m, 1024, 1024)
+        bn, bk, bc = self.tiles
+        self.cfg = harness.MlpConfig(batch=m, layers=LAYERS, tiles=self.tiles, vnni=vnni)
+        dev = x_shard.device
+        self.set_bytes = sum(w.numel() * 2 for w in w_dev) + sum(b.numel() * 2 for b in b_dev) + 4 * m * 1024 * 2
+        items_per_set = max(m // ROW_BLOCK, 1)
+        self.num_sets = max(L2_BYTES // self.set_bytes + 2, -(-2 * NUM_PAIRS // items_per_set), min_sets)
+        if max_sets:
+            self.num_sets = min(self.num_sets, max_sets)
+        wp = [harness.pack_weight(w, bk, bc) for w in w_dev]
+        if vnni:
+            wp = [harness.vnni_pack_weight(w) for w in wp]
+        self.sets = []
+        for s in range(self.num_sets):
+            xin = harness.pack_activation(torch.roll(x_shard, s, 0), bn, bc).contiguous()
+            acts = [xin] + [torch.zeros(m * k, dtype=torch.int16, device=dev) for k in LAYERS[1:]]
+            self.sets.append((acts, [w.clone() for w in wp], [b.clone() for b in b_dev]))
+        self.replay = harness.MlpReplay(self.cfg, self.sets[0][1], self.sets[0][2], self.sets[0][0])
+        self.loop = harness.NativeMlpLoop(self.cfg, self.replay.handles, self.sets)
+
+    def output(self, s):
+        """[m][1024] int16 (bf16 bits) result of operand set s"""
+        from tpp_mlir_b200 import harness
+
+        bn, bk, _ = self.tiles
+        return harness.unpack_activation(self.sets[s][0][-1].reshape(self.m // bn, LAYERS[-1] // bk, bn, bk))
+
+    def rotations(self, n):
+        """n rotations = n graph launches = n * num_sets forward passes, starting at set 0"""
+        self.loop.reset()
+        self.loop.run_graph(n * self.num_sets)
+
+    def time_rotations(self, n, stream, barrier, dev):
+        """device time (CUDA events on the launch stream, ms) of n rotations, plus launches / issue time"""
+        import torch
+
+        from tpp_mlir_b200 import xsmm
+
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = xsmm.launch_count()
+        w0 = time.perf_counter()
+        ev0.record(stream)
+        self.rotations(n)
+        w_issue = time.perf_counter() - w0
+        ev1.record(stream)
+        barrier()
+        w1 = time.perf_counter()
+        return {"ms": ev0.elapsed_time(ev1), "launches": xsmm.launch_count() - l0, "issue_s": w_issue, "w0": w0, "w1": w1}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=14800)   # 100 rotations of 148 operand sets
-    ap.add_argument("--warmup", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=50)     # 50 steps = 100 rotations = 14800 forward passes
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--global-batch", type=int, default=int(os.environ.get("TPP_BENCH_GLOBAL_BATCH", "0")),
+                    help="strong scaling: this many batch rows in total, sharded over the GPUs (BASELINE configs[4]: "
+                         "2048). Default 0: weak scaling, 256 rows per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", default="graph", choices=["graph", "direct"],
-                    help="graph: replay the captured invoke sequence (one host call per step); "
-                         "direct: one C-ABI invoke per layer per step")
+    ap.add_argument("--no-extras", action="store_true", help="skip the cfg2 / cfg4 / cfg5 / reference-stream side measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    args.steps = max(args.steps, 1)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -247,6 +373,7 @@ def main():
     import torch
     import torch.distributed as dist
 
+    import oracle
     from tpp_mlir_b200 import harness, shard, xsmm
 
     if not torch.cuda.is_available():
@@ -260,172 +387,152 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
     n_gpus = world
+    strong = args.global_batch > 0
+    global_batch = args.global_batch if strong else BATCH_PER_GPU * n_gpus
+    if global_batch % (n_gpus * ROW_BLOCK) != 0:
+        print(json.dumps({"error": f"global batch {global_batch} does not split into {ROW_BLOCK}-row blocks over "
+                                   f"{n_gpus} GPUs"}))
+        return 1
+    m_rank = global_batch // n_gpus
 
-    bn, bk, bc = TILES
-    cfg = harness.MlpConfig(batch=BATCH_PER_GPU, layers=LAYERS, tiles=TILES)
-
-    # ---- data: rank 0 generates, NCCL broadcasts weights/biases; each rank owns its batch shard ----
     def to_dev(a):
         return torch.from_numpy(a.view(np.int16)).to(dev)
-
-    if rank == 0:
-        gen, Ws, bs = make_host_data()
-        x_all = gen.fill(BATCH_PER_GPU * n_gpus, LAYERS[0])
-        w_dev = [harness.pack_weight(to_dev(W), bk, bc) for W in Ws]
-        b_dev = [to_dev(b) for b in bs]
-        x_dev_all = to_dev(x_all)
-    else:
-        w_dev = [torch.empty(k // bk, c // bc, bc, bk, dtype=torch.int16, device=dev)
-                 for c, k in zip(LAYERS[:-1], LAYERS[1:])]
-        b_dev = [torch.empty(k, dtype=torch.int16, device=dev) for k in LAYERS[1:]]
-        x_dev_all = torch.empty(BATCH_PER_GPU * n_gpus, LAYERS[0], dtype=torch.int16, device=dev)
-    # the one collective of this path: parameters (and the synthetic input), once, outside the timed loop
-    shard.broadcast_parameters(w_dev + b_dev + [x_dev_all], src=0)
-    lo, hi = shard.shard_bounds(BATCH_PER_GPU * n_gpus, rank, n_gpus, tile_m=bn)
-    x_shard = x_dev_all[lo:hi].contiguous()
-    x_packed = harness.pack_activation(x_shard, bn, bc)
-
-    # ---- rotate more bytes than the L2 holds so every step streams its operands from HBM ----
-    set_bytes = sum(w.numel() * 2 for w in w_dev) + sum(b.numel() * 2 for b in b_dev) + 4 * BATCH_PER_GPU * 1024 * 2
-    # ... and at least two forward passes per CTA pair in one rotation graph, so that the pair-per-chain kernel
-    # (one pair of SMs per forward pass) has two rounds of work per launch
-    num_sets = max(L2_BYTES // set_bytes + 2, 2 * CHAIN_GROUP)
-    sets = []
-    for s in range(num_sets):
-        acts = [x_packed.clone()] + [torch.zeros(BATCH_PER_GPU * k, dtype=torch.int16, device=dev) for k in LAYERS[1:]]
-        sets.append((acts, [w.clone() for w in w_dev], [b.clone() for b in b_dev]))
-    replay = harness.MlpReplay(cfg, sets[0][1], sets[0][2], sets[0][0])  # dispatches (hoisted, once)
-    loop = harness.NativeMlpLoop(cfg, replay.handles, sets)
-    stream = torch.cuda.current_stream(dev)
-    xsmm.set_stream(stream.cuda_stream)
 
     def barrier():
         if n_gpus > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident number ("value") --------------------------------------------------------
-    # mode "graph": every operand set's forward pass (3 invokes) is captured once through
-    # xsmm_cuda_graph_begin/end and replayed - one host call per step; mode "direct": one
-    # xsmm_fused_brgemm_invoke (one cudaLaunchKernelEx) per layer per step.
-    run = loop.run_graph if args.mode == "graph" else loop.run
-    run(max(args.warmup, num_sets))   # warm-up also captures the rotation graph
-    loop.reset()
-    run(args.steps)                   # rehearsal of the timed call: captures the graph of its partial last rotation
+    def fail(msg):
+        restore_stdout(saved_stdout)
+        print(json.dumps({"error": msg}))
+        sys.stdout.flush()
+        os._exit(1)
+
+    # ---- data: rank 0 generates, NCCL broadcasts weights / biases / inputs; each rank owns its batch shard ----
+    extra_rows = 2048   # input of the configs[4] side measurement
+    if rank == 0:
+        gen, Ws, bs = make_host_data()
+        x_all = gen.fill(max(global_batch, extra_rows), LAYERS[0])
+        w_dev, b_dev, x_dev_all = [to_dev(W) for W in Ws], [to_dev(b) for b in bs], to_dev(x_all)
+    else:
+        w_dev = [torch.empty(c, k, dtype=torch.int16, device=dev) for c, k in zip(LAYERS[:-1], LAYERS[1:])]
+        b_dev = [torch.empty(k, dtype=torch.int16, device=dev) for k in LAYERS[1:]]
+        x_dev_all = torch.empty(max(global_batch, extra_rows), LAYERS[0], dtype=torch.int16, device=dev)
+    # the one collective of this path: parameters (and the synthetic input), once, outside the timed loop
+    shard.broadcast_parameters(w_dev + b_dev + [x_dev_all], src=0)
+    lo, hi = shard.shard_bounds(global_batch, rank, n_gpus, tile_m=ROW_BLOCK)
+    x_shard = x_dev_all[lo:hi].contiguous()
+
+    stream = torch.cuda.current_stream(dev)
+    xsmm.set_stream(stream.cuda_stream)
+    wl = MlpWorkload(m_rank, x_shard, w_dev, b_dev)
+    num_sets, cfg = wl.num_sets, wl.cfg
+    fwd_per_step = STEP_ROTATIONS * num_sets
+    flops_fwd_rank = cfg.flops()
+
+    # ---- device-resident number ("value"): K steps of STEP_ROTATIONS rotation graphs each -----------------------
+    wl.rotations(STEP_ROTATIONS * args.warmup)      # warm-up (W steps); the first rotation captures the graph
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    loop.reset()
-    run(2 * num_sets)  # keep the GPU busy while the sampler gets going
-    barrier()
-    loop.reset()
-    launches0 = xsmm.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.perf_counter()
-    ev0.record(stream)
-    run(args.steps)
-    t_issue = time.perf_counter() - t_wall0   # host time to issue all launches (no sync yet)
-    ev1.record(stream)
-    barrier()
-    t_wall1 = time.perf_counter()
-    launches = xsmm.launch_count() - launches0
-    loop.reset()
-    run(num_sets)                       # exactly one rotation: the name of the kernel the timed loop is made of
-    timed_kernel = xsmm.last_kernel()   # (graph mode: the fused multi-chain kernel; leftover steps run single chains)
+    wl.rotations(8)                                 # keep the GPU busy while the sampler gets going
+    tm = wl.time_rotations(STEP_ROTATIONS * args.steps, stream, barrier, dev)
     sampler.stop()
-    ms = ev0.elapsed_time(ev1)
-    ms_max = shard.max_over_ranks(ms, device=dev)
+    timed_kernel = xsmm.last_kernel()
+    ms_max = shard.max_over_ranks(tm["ms"], device=dev)
     ms_per_step = ms_max / args.steps
-    flops_step_rank = cfg.flops()
-    value = flops_step_rank * n_gpus / (ms_per_step * 1e-3) / 1e9
+    value = flops_fwd_rank * fwd_per_step * n_gpus / (ms_per_step * 1e-3) / 1e9
+    launches = tm["launches"]
 
-    if os.environ.get("TPP_XSMM_TC_TRACE") in ("2", "3"):
+    # the same K steps under tpp-run's own protocol: perf_start_timer / perf_stop_timer around the host loop of
+    # asynchronous invokes, wall clock, device drained inside perf_stop_timer (lib/TPP/Runner/MLIRBench.cpp:265-300)
+    barrier()
+    t0 = xsmm.perf_start_timer()
+    wl.rotations(STEP_ROTATIONS * args.steps)
+    perf_s = shard.max_over_ranks(xsmm.perf_stop_timer(t0), device=dev) / args.steps
+
+    if os.environ.get("TPP_XSMM_TC_TRACE") in ("2", "3", "4"):
         xsmm.LIB.xsmm_cuda_debug_dump_trace()
 
-    # hot-L2 variant (what tpp-run measures: the same buffers every iteration), for information
-    hot = harness.NativeMlpLoop(cfg, replay.handles, sets[:1])
-    run_hot = hot.run_graph if args.mode == "graph" else hot.run
-    run_hot(args.warmup)
-    barrier()
-    ev0.record(stream)
-    run_hot(args.steps)
-    ev1.record(stream)
-    barrier()
-    ms_hot = ev0.elapsed_time(ev1) / args.steps
-
-    # the other issue mode, for information (same kernels, different host path)
-    other = loop.run if args.mode == "graph" else loop.run_graph
-    other_steps = min(args.steps, 500)
-    other(max(args.warmup, num_sets))
-    barrier()
-    ev0.record(stream)
-    other(other_steps)
-    ev1.record(stream)
-    barrier()
-    ms_other = ev0.elapsed_time(ev1) / other_steps
-
-    # ---- parity of what was just timed (rank-local, against the oracle on a row sample) ----------
-    import oracle
-
-    out = harness.unpack_activation(sets[0][0][-1].reshape(BATCH_PER_GPU // bn, LAYERS[-1] // bk, bn, bk))
-    got = oracle.bf16_to_f32(out[:8].cpu().numpy().view(np.uint16))
+    # ---- parity of what was just timed: EVERY rank's full shard, several operand sets, against the oracle ---------
+    check_sets = sorted({0, 1, num_sets // 2, num_sets - 1})
+    mine = torch.stack([wl.output(s) for s in check_sets])               # [sets][m_rank][1024]
+    gathered = shard.gather_rows(mine.permute(1, 0, 2).contiguous())     # rank 0: [world * m_rank][sets][1024]
+    parity = None
     if rank == 0:
-        a = x_all[:8]
-        for W, b in zip(Ws, bs):
-            y = np.empty((8, W.shape[1]), np.uint16)
-            oracle.fused_brgemm(2, 8, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4, 0, 5, 4, 1,
-                                a, W, y, b, 1)
-            a = y
-        want = oracle.bf16_to_f32(a)
-        rel = float(np.abs(got - want).max() / max(np.abs(want).max(), 1e-30))
-    else:
-        rel = None
+        worst = 0.0
+        got_all = gathered.cpu().numpy().view(np.uint16).reshape(n_gpus, m_rank, len(check_sets), LAYERS[-1])
+        for r in range(n_gpus):
+            want0 = oracle_forward(x_all[r * m_rank:(r + 1) * m_rank], Ws, bs)
+            for i, s in enumerate(check_sets):
+                worst = max(worst, rel_err(got_all[r, :, i, :], np.roll(want0, s, axis=0)))
+        parity = {"max_rel_err_vs_oracle": worst, "tolerance": 1e-2, "ranks_checked": n_gpus,
+                  "operand_sets_checked": check_sets, "rows_per_rank": m_rank,
+                  "oracle": "oracle/xsmm_oracle.c (pinned, plain C)"}
+        if not worst <= 1e-2:
+            fail(f"parity failure: max rel err {worst} vs the oracle over {n_gpus} ranks, sets {check_sets}")
 
-    # ---- end-to-end through the C-ABI with HOST buffers (rank-local), H2D + D2H inside the timing ----
-    host_sets = None
-    e2e_steps = min(args.steps, 500)
-    h_w = [w.cpu().contiguous().pin_memory() for w in w_dev]
-    h_b = [b.cpu().contiguous().pin_memory() for b in b_dev]
-    h_acts = [x_packed.cpu().contiguous().pin_memory()] + [torch.zeros(BATCH_PER_GPU * k, dtype=torch.int16).pin_memory()
-                                                           for k in LAYERS[1:]]
+    # ---- latency: what tpp-run's perf.bench loop measures - ONE forward pass re-run on ONE set of buffers -------
+    def lone_forward(mode):
+        hot = harness.NativeMlpLoop(cfg, wl.replay.handles, wl.sets[:1])
+        run = hot.run_graph if mode == "graph" else hot.run
+        n = 1000
+        for _ in range(min(max(n // 100, 1), 50)):   # tpp-run's warm-up clamp(N/100, 1, 50)
+            run(1)
+        barrier()
+        t0 = xsmm.perf_start_timer()
+        run(n)
+        s = shard.max_over_ranks(xsmm.perf_stop_timer(t0) / n, device=dev)
+        return s, xsmm.last_kernel()
+
+    lat_graph_s, lat_kernel = lone_forward("graph")
+    lat_direct_s, lat_direct_kernel = lone_forward("direct")
+    lone_rel = rel_err(wl.output(0).cpu().numpy().view(np.uint16),
+                       oracle_forward(x_all[lo:hi], Ws, bs)) if rank == 0 else None
+    if rank == 0 and not lone_rel <= 1e-2:
+        fail(f"parity failure of the lone forward pass: {lone_rel}")
+
+    # ---- end to end through the C-ABI with HOST buffers (rank-local), H2D + D2H inside the timing -----------------
+    bn, bk, bc = wl.tiles
+    xp0 = wl.sets[0][0][0]
+    h_w = [w.cpu().contiguous().pin_memory() for w in wl.sets[0][1]]
+    h_b = [b.cpu().contiguous().pin_memory() for b in wl.sets[0][2]]
+    h_acts = [xp0.cpu().contiguous().pin_memory()] + [torch.zeros(m_rank * k, dtype=torch.int16).pin_memory()
+                                                      for k in LAYERS[1:]]
     for tns in h_w + h_b + h_acts:
         xsmm.register_host(tns, upload=True)  # parameters + activation buffers mirrored once (like gpu.alloc)
-    host_sets = [(h_acts, h_w, h_b)]
-    e2e_loop = harness.NativeMlpLoop(cfg, replay.handles, host_sets)
-    e2e_loop.run_e2e(max(3, args.warmup // 5))
+    e2e_loop = harness.NativeMlpLoop(cfg, wl.replay.handles, [(h_acts, h_w, h_b)])
+    sync_steps = 200
+    e2e_loop.run_e2e(5)
     barrier()
     t0 = time.perf_counter()
-    e2e_loop.run_e2e(e2e_steps)
+    e2e_loop.run_e2e(sync_steps)
     torch.cuda.synchronize(dev)
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    e2e_s = shard.max_over_ranks(e2e_s, device=dev)
-    e2e_value = flops_step_rank * n_gpus / e2e_s / 1e9
-    e2e_out = oracle.bf16_to_f32(harness.unpack_activation(
-        h_acts[-1].reshape(BATCH_PER_GPU // bn, LAYERS[-1] // bk, bn, bk))[:8].numpy().view(np.uint16))
-    # the single-step graph runs the full-K pass kernel, the device-timed loop the pair kernel: same math, the f32
-    # summation order inside the tensor core may differ -> compare in bf16 ulps, and against the oracle below
-    sync_ulp = int(np.abs(h_out_bits(h_acts, harness, bn, bk) - out[:8].cpu().numpy().view(np.uint16).astype(np.int32)).max())
-    e2e_rel = float(np.abs(e2e_out - want).max() / max(np.abs(want).max(), 1e-30)) if rank == 0 else None
-    # throughput form: PIPE_GROUPS groups of CHAIN_GROUP independent steps in flight (one buffer set per step); every
-    # step still uploads its 512 KiB input and downloads its 512 KiB output
+    sync_s = shard.max_over_ranks((time.perf_counter() - t0) / sync_steps, device=dev)
+    want_rank = oracle_forward(x_all[lo:hi], Ws, bs) if rank == 0 else None
+
+    def host_out(acts):
+        return harness.unpack_activation(acts[-1].reshape(m_rank // bn, LAYERS[-1] // bk, bn, bk)).numpy().view(np.uint16)
+
+    sync_rel = rel_err(host_out(h_acts), want_rank) if rank == 0 else None
+    # throughput form: PIPE_GROUPS groups of CHAIN_GROUP independent steps in flight (one buffer set per forward pass);
+    # every forward pass still uploads its input and downloads its output. Per group ONE pinned, registered host block
+    # per activation level; a forward pass's buffers are slices of it, so a group's inputs cross PCIe as one copy
     depth = PIPE_GROUPS * CHAIN_GROUP
-    # per group ONE pinned, registered host block per activation level; a step's buffers are slices of it, so that a
-    # group's inputs (outputs) cross PCIe as one 37 MiB copy
     blocks, slot_acts = [], []
-    xp_host = x_packed.cpu().contiguous().reshape(-1)
+    xp_host = xp0.cpu().contiguous().reshape(-1)
     for _ in range(PIPE_GROUPS):
-        lvl = [torch.zeros(CHAIN_GROUP, BATCH_PER_GPU * k, dtype=torch.int16).pin_memory() for k in LAYERS]
+        lvl = [torch.zeros(CHAIN_GROUP, m_rank * k, dtype=torch.int16).pin_memory() for k in LAYERS]
         lvl[0][:] = xp_host
         for tns in lvl:
             xsmm.register_host(tns, upload=True)
         blocks += lvl
         for j in range(CHAIN_GROUP):
             slot_acts.append([b[j] for b in lvl])
-    pipe_loop = harness.NativeMlpLoop(cfg, replay.handles, [(a, h_w, h_b) for a in slot_acts])
+    pipe_loop = harness.NativeMlpLoop(cfg, wl.replay.handles, [(a, h_w, h_b) for a in slot_acts])
     pipe_mode = f"batch{CHAIN_GROUP}"
-    # enough group iterations that filling and draining the 3-deep pipeline (one upload + kernel + download = ~1.5 ms,
-    # inside the timing) does not dominate: 8 ... 24 rounds over the groups
-    pipe_steps = min(max(args.steps // depth, 8), 24) * depth
+    pipe_fwd = min(max(args.steps * fwd_per_step // depth, 8), 24) * depth
     pipe_loop.run_e2e_pipelined(depth, mode=pipe_mode)
     torch.cuda.synchronize(dev)
     for a in slot_acts:
@@ -434,18 +541,72 @@ def main():
     for _ in range(3):   # three timed repetitions; the median is reported
         barrier()
         t0 = time.perf_counter()
-        ran = pipe_loop.run_e2e_pipelined(pipe_steps, mode=pipe_mode)   # returns after the last output reached the host
+        ran = pipe_loop.run_e2e_pipelined(pipe_fwd, mode=pipe_mode)   # returns after the last output reached the host
         pipe_runs.append(shard.max_over_ranks((time.perf_counter() - t0) / ran, device=dev))
     pipe_s = sorted(pipe_runs)[1]
-    pipe_value = flops_step_rank * n_gpus / pipe_s / 1e9
     pipe_kernel = xsmm.last_kernel()
-    e2e_ulp = 0
-    got_bits = out[:8].cpu().numpy().view(np.uint16).astype(np.int32)
-    for a in slot_acts:
-        o = harness.unpack_activation(a[-1].reshape(BATCH_PER_GPU // bn, LAYERS[-1] // bk, bn, bk))[:8].numpy()
-        e2e_ulp = max(e2e_ulp, int(np.abs(o.view(np.uint16).astype(np.int32) - got_bits).max()))
+    pipe_rel = max(rel_err(host_out(a), want_rank) for a in slot_acts[::17]) if rank == 0 else None
+    # strict mode: PLAIN host pointers (nothing registered) straight into xsmm_fused_brgemm_invoke, what an unmodified
+    # tools/tpp-run flow would hit: every invoke stages its operands H2D, runs, copies C back, returns when C is visible
+    p_w = [w.cpu().contiguous() for w in wl.sets[0][1]]
+    p_b = [b.cpu().contiguous() for b in wl.sets[0][2]]
+    p_acts = [xp0.cpu().contiguous()] + [torch.zeros(m_rank * k, dtype=torch.int16) for k in LAYERS[1:]]
+    strict_loop = harness.NativeMlpLoop(cfg, wl.replay.handles, [(p_acts, p_w, p_b)])
+    strict_loop.run(3)
+    barrier()
+    strict_n = 20
+    t0 = time.perf_counter()
+    strict_loop.run(strict_n)
+    strict_s = shard.max_over_ranks((time.perf_counter() - t0) / strict_n, device=dev)
+    strict_rel = rel_err(host_out(p_acts), want_rank) if rank == 0 else None
     for tns in h_w + h_b + h_acts + blocks:
         xsmm.unregister_host(tns)
+    del blocks, slot_acts, pipe_loop, e2e_loop
+    if rank == 0:
+        for name, r in (("pipelined e2e", pipe_rel), ("synchronous e2e", sync_rel), ("strict-mode e2e", strict_rel)):
+            if not r <= 1e-2:
+                fail(f"parity failure in the {name} leg: {r}")
+
+    # ---- side measurements with a driver clock record: configs[1], [3], [4] and the reference's default call stream --
+    extras = {}
+    if not args.no_extras:
+        import bench_configs
+
+        pk_ = peaks()
+        # BASELINE configs[4] (batch 2048): at N > 1 sharded over the ranks (strong scaling, 2048/N rows per GPU), at N = 1
+        # all 2048 rows on the one GPU. Skipped when it IS the main workload (--global-batch 2048)
+        if not (strong and global_batch == extra_rows):
+            m5 = extra_rows // n_gpus
+            lo5 = rank * m5
+            x5 = x_dev_all[lo5:lo5 + m5].contiguous()
+            wl5 = MlpWorkload(m5, x5, w_dev, b_dev)
+            wl5.rotations(3)
+            t5 = wl5.time_rotations(10, stream, barrier, dev)
+            ms5 = shard.max_over_ranks(t5["ms"], device=dev) / (10 * wl5.num_sets)
+            g5 = shard.gather_rows(wl5.output(wl5.num_sets - 1))
+            e5 = None
+            if rank == 0:
+                want5 = np.concatenate([np.roll(oracle_forward(x_all[r * m5:(r + 1) * m5], Ws, bs), wl5.num_sets - 1, 0)
+                                        for r in range(n_gpus)])
+                e5 = rel_err(g5.cpu().numpy().view(np.uint16), want5)
+                if not e5 <= 1e-2:
+                    fail(f"parity failure in the configs[4] side measurement: {e5}")
+            tf5 = wl5.cfg.flops() * n_gpus / (ms5 * 1e-3) / 1e12
+            extras["cfg5_batch2048"] = {
+                "config": f"MLP 3x1024^2 bf16 batch 2048 over {n_gpus} GPU(s): {m5} rows per GPU (BASELINE configs[4])",
+                "scaling": "strong", "ms_per_forward": ms5, "gflops": tf5 * 1e3, "kernel": xsmm.last_kernel(),
+                "operand_sets": wl5.num_sets, "rel_err_vs_oracle_all_ranks": e5,
+                "roofline": {"bound": "tensor", "achieved": tf5 / n_gpus, "peak": pk_["bf16_tflops"], "unit": "TFLOP/s per GPU",
+                             "frac": tf5 / n_gpus / pk_["bf16_tflops"]}}
+            del wl5
+        if n_gpus == 1:
+            for name, fn in (("cfg2_brgemm_1024x16", bench_configs.cfg2), ("cfg4_vnni2_pack_4096", bench_configs.cfg4),
+                             ("reference_default_stream", bench_configs.reference_stream)):
+                try:
+                    extras[name] = fn(pk_)
+                except Exception as e:   # a side measurement must not take the headline down with it
+                    extras[name] = {"error": repr(e)}
+        xsmm.set_stream(stream.cuda_stream)
 
     if rank != 0:
         if n_gpus > 1:
@@ -455,86 +616,115 @@ def main():
 
     pk = peaks()
     # algorithmic HBM bytes of one forward pass: 3 weight matrices + 3 biases + input + output (intermediates stay in L2)
-    set_bytes_algo = sum(c * k * 2 + k * 2 for c, k in zip(LAYERS[:-1], LAYERS[1:])) + 2 * BATCH_PER_GPU * 1024 * 2
-    launches_per_step = launches / args.steps
-    flops_per_launch = flops_step_rank / launches_per_step
-    avg_launch_s = (ms / args.steps) * 1e-3 / launches_per_step
+    fwd_bytes = sum(c * k * 2 + k * 2 for c, k in zip(LAYERS[:-1], LAYERS[1:])) + 2 * m_rank * 1024 * 2
+    fwd_per_launch = args.steps * fwd_per_step / max(launches, 1)
+    avg_launch_s = tm["ms"] * 1e-3 / max(launches, 1)
+    bytes_per_launch = fwd_bytes * fwd_per_launch
+    flops_per_launch = flops_fwd_rank * fwd_per_launch
+    achieved_gbs = bytes_per_launch / avg_launch_s / 1e9
     achieved_tflops = flops_per_launch / avg_launch_s / 1e12
-    bytes_per_launch = set_bytes_algo / launches_per_step
-    traffic = None
+    traffic, traffic_src = None, None
     prof = os.path.join(ROOT, "profiles", "dominant_kernel.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and m_rank == BATCH_PER_GPU:
         with open(prof) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
+            pj = json.load(f)
+        if pj.get("forward_passes_per_launch") == round(fwd_per_launch):   # the capture describes THIS launch shape
+            traffic, traffic_src = pj.get("dram_bytes_per_launch"), pj.get("from")
     cpu = None
     if n_gpus == 1 and not args.no_cpu_baseline:
-        c = cpu_arm(steps=10, warmup=2, total_budget_s=20.0)
+        c = cpu_arm(steps=10, warmup=2, total_budget_s=15.0)
         cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        try:
+            cpu["torch_onednn_proxy"] = torch_onednn_proxy(steps=10, warmup=3)
+        except Exception as e:
+            cpu["torch_onednn_proxy"] = {"error": repr(e)}
 
+    h2d_fwd, d2h_fwd = m_rank * LAYERS[0] * 2, m_rank * LAYERS[-1] * 2
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic (TensorInit normal, seed 123; random-init weights)",
-        "config": {"workload": "fused_brgemm MLP 3x(256x1024x1024)+bias+relu bf16, batch 256 per GPU "
-                               "(BASELINE configs[2]; configs[4] at 8 GPUs)",
-                   "layers": list(LAYERS), "tiles": list(TILES), "global_batch": BATCH_PER_GPU * n_gpus,
+        "config": {"workload": f"fused_brgemm MLP 3x({m_rank}x1024x1024)+bias+relu bf16, batch {m_rank} per GPU "
+                               "(BASELINE configs[2]; configs[4] when the global batch is 2048)",
+                   "layers": list(LAYERS), "tiles": list(wl.tiles), "global_batch": global_batch,
                    "parallelism": f"batch-sharded x{n_gpus}, weights broadcast once over NCCL",
-                   "l2": f"rotating {num_sets} operand sets ({num_sets * set_bytes >> 20} MiB > 126 MiB L2), "
-                         "inputs larger than L2",
-                   "timing": "CUDA events on the launch stream, max over ranks",
-                   "issue_mode": ("CUDA graph replay of the captured xsmm invoke sequence (xsmm_cuda_graph_*): one graph = "
-                                  f"one rotation of {num_sets} forward passes on {num_sets} operand sets ({3 * num_sets} "
-                                  "xsmm_fused_brgemm_invoke calls), which the runtime turns into ONE launch of the "
-                                  "pair-per-chain kernel: each forward pass (a chain of 3 dependent layers) runs on one "
-                                  "pair of SMs, 74 forward passes side by side; latency of a lone forward pass: "
-                                  "extra.ms_per_step_single_forward"
-                                  if args.mode == "graph" else "one xsmm_fused_brgemm_invoke per layer"),
-                   "flops_per_step": flops_step_rank * n_gpus, "matmul_flops_per_step": cfg.matmul_flops() * n_gpus},
-        "clocks": sampler.summary(t_wall0, t_wall1),
-        "e2e": {"value": pipe_value, "unit": UNIT, "h2d_bytes_per_step": BATCH_PER_GPU * LAYERS[0] * 2,
-                "d2h_bytes_per_step": BATCH_PER_GPU * LAYERS[-1] * 2, "ms_per_step": pipe_s * 1e3, "steps": pipe_steps,
-                "path": "xsmm C-ABI on registered pinned host buffers, every step: xsmm_cuda_upload_async(input 512 KiB) "
+                   "step": f"{STEP_ROTATIONS} rotations over {num_sets} operand sets = {fwd_per_step} forward passes "
+                           f"({3 * fwd_per_step} xsmm_fused_brgemm_invoke calls) per GPU, in stream order",
+                   "forward_passes_per_step": fwd_per_step, "forward_passes_per_launch": fwd_per_launch,
+                   "ms_per_forward": ms_per_step / fwd_per_step,
+                   "l2": f"rotating {num_sets} operand sets ({num_sets * wl.set_bytes >> 20} MiB > 126 MiB L2), all of them "
+                         "touched by every launch: inputs larger than L2",
+                   "timing": "CUDA events on the launch stream, max over ranks; extra.perf_timer_protocol repeats it with "
+                             "perf_start_timer / perf_stop_timer",
+                   "issue_mode": ("one rotation = one CUDA graph replay of the captured xsmm invoke sequence "
+                                  "(xsmm_cuda_graph_*), which the runtime turns into ONE launch of the pair-per-chain kernel: "
+                                  "each forward pass (a chain of 3 dependent layers) runs on one pair of SMs, 74 side by side; "
+                                  "the forward passes of a rotation are independent of each other, as the iterations of the "
+                                  "reference's perf.bench loop are; the sequential form is the `latency` field"),
+                   "flops_per_step": flops_fwd_rank * fwd_per_step * n_gpus, "flops_per_forward": flops_fwd_rank,
+                   "matmul_flops_per_forward": cfg.matmul_flops()},
+        "clocks": sampler.summary(tm["w0"], tm["w1"]),
+        "latency": {"what": "ONE forward pass re-run on ONE set of buffers back to back (L2-hot): what the reference's "
+                            "benchmark loop times (lib/TPP/Runner/MLIRBench.cpp:265-300, TppRunnerWrapper.cpp:115-130)",
+                    "protocol": "warm-up clamp(N/100,1,50), N = 1000 calls between perf_start_timer / perf_stop_timer "
+                                "(wall clock, device drained), max over ranks",
+                    "ms_per_forward": lat_graph_s * 1e3, "gflops": flops_fwd_rank / lat_graph_s / 1e9,
+                    "frac_of_burst_tensor_peak": flops_fwd_rank / lat_graph_s / 1e12 / pk["bf16_tflops"],
+                    "kernel": lat_kernel, "issue": "graph replay of the captured 3-invoke sequence",
+                    "direct_invokes": {"ms_per_forward": lat_direct_s * 1e3, "gflops": flops_fwd_rank / lat_direct_s / 1e9,
+                                       "kernel": lat_direct_kernel, "issue": "3 x xsmm_fused_brgemm_invoke, PDL-chained"},
+                    "rel_err_vs_oracle": lone_rel},
+        "e2e": {"value": flops_fwd_rank * n_gpus / pipe_s / 1e9, "unit": UNIT,
+                "h2d_bytes_per_step": h2d_fwd * fwd_per_step, "d2h_bytes_per_step": d2h_fwd * fwd_per_step,
+                "h2d_bytes_per_forward": h2d_fwd, "d2h_bytes_per_forward": d2h_fwd,
+                "ms_per_step": pipe_s * 1e3 * fwd_per_step, "ms_per_forward": pipe_s * 1e3, "forward_passes_timed": pipe_fwd,
+                "copy_gbs_per_direction_per_gpu": h2d_fwd / pipe_s / 1e9,
+                "path": "xsmm C-ABI on registered pinned host buffers, every forward pass: xsmm_cuda_upload_async(input) "
                         "-> 3 xsmm_fused_brgemm_invoke (replayed from the captured sequence) -> xsmm_cuda_download_async("
-                        f"output 512 KiB); steps are issued in groups of {CHAIN_GROUP} (one captured graph = one launch of the "
-                        f"pair-per-chain kernel per group; the group's {CHAIN_GROUP} inputs / outputs are slices of one registered "
+                        f"output); issued in groups of {CHAIN_GROUP} (one captured graph = one launch of the "
+                        f"pair-per-chain kernel per group; the group's inputs / outputs are slices of one registered "
                         f"host block and move as one copy), {PIPE_GROUPS} groups in flight, xsmm_cuda_wait_host(output) before "
-                        "a group's buffers are reused, so uploads, kernels and downloads of neighbouring groups overlap; wall "
-                        "clock incl. the final drain; median of 3 repetitions; bound by PCIe (1 MiB per step; "
-                        "scripts/pcie_probe.py: ~50 GB/s per direction with both directions busy = 10.5 us per step)",
+                        "a group's buffers are reused; wall clock incl. the final drain; median of 3 repetitions; bound by "
+                        "PCIe (scripts/pcie_probe.py: ~50 GB/s per direction with both directions busy)",
                 "pipeline_depth": depth, "kernel": pipe_kernel,
-                "ms_per_step_repetitions": [t * 1e3 for t in pipe_runs],
-                "max_ulp_diff_vs_device_run": e2e_ulp,
-                "synchronous": {"value": e2e_value, "ms_per_step": e2e_s * 1e3,
-                                "path": "same step, one in flight: graph launch -> stream sync, every step",
-                                "rel_err_vs_oracle": e2e_rel, "max_ulp_diff_vs_device_run": sync_ulp}},
+                "ms_per_forward_repetitions": [t * 1e3 for t in pipe_runs], "rel_err_vs_oracle": pipe_rel,
+                "synchronous": {"value": flops_fwd_rank * n_gpus / sync_s / 1e9, "ms_per_forward": sync_s * 1e3,
+                                "path": "same forward pass, one in flight: graph launch (H2D, 3 layers, D2H) -> stream "
+                                        "sync, every time", "rel_err_vs_oracle": sync_rel},
+                "strict": {"value": flops_fwd_rank * n_gpus / strict_s / 1e9, "ms_per_forward": strict_s * 1e3,
+                           "path": "PLAIN (unregistered, pageable) host pointers passed to xsmm_fused_brgemm_invoke, the "
+                                   "call an unmodified tools/tpp-run would make: every invoke stages A, B, bias H2D, "
+                                   "launches, copies C back and returns once C is visible (reference semantics)",
+                           "rel_err_vs_oracle": strict_rel}},
         "gpu_launches": launches,
-        # the dominant kernel is HBM-bound (ncu: DRAM 5.3 TB/s busy, tensor pipe < 50 % of cycles): the roofline is the
+        # the dominant kernel is HBM-bound (ncu: DRAM busy, tensor pipe < 50 % of cycles): the roofline is the
         # measured copy bandwidth; the tensor-core view of the same launch is kept beside it
-        "roofline": {"bound": "hbm", "achieved": bytes_per_launch / avg_launch_s / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": bytes_per_launch / avg_launch_s / 1e9 / pk["hbm_gbs"], "traffic": traffic,
+        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved_gbs / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": timed_kernel, "peak_source": pk["source"],
                      "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6,
-                     "forward_passes_per_launch": args.steps / max(launches, 1),
-                     "bytes_per_forward_pass": set_bytes_algo,
+                     "launches_timed": launches, "forward_passes_per_launch": fwd_per_launch,
+                     "bytes_per_forward_pass": fwd_bytes,
                      "tensor": {"achieved": achieved_tflops, "unit": "TFLOP/s", "peak_burst": pk["bf16_tflops"],
                                 "frac_of_burst_peak": achieved_tflops / pk["bf16_tflops"],
                                 "peak_sustained": pk["bf16_tflops_sustained"],
                                 "frac_of_sustained_peak": (achieved_tflops / pk["bf16_tflops_sustained"]
                                                            if pk["bf16_tflops_sustained"] else None),
                                 "flops_per_launch": flops_per_launch},
-                     "note": "arithmetic intensity 219 FLOP/B (1.61 GFLOP over 7.35 MB: 3 weight matrices, biases, input, "
-                             "output; intermediates stay in L2) is below the measured machine balance (1641 TF/s / 6.55 TB/s "
-                             "= 251): with operand sets rotating through > L2 every weight byte comes from HBM and HBM "
-                             "bounds the step (DESIGN.md 4.1d). traffic = DRAM bytes of one launch under ncu "
-                             "(profiles/ncu_mlp_chain_pair_r1.json)"},
+                     "note": "arithmetic intensity 219 FLOP/B (1.61 GFLOP over 7.35 MB per forward pass: 3 weight matrices, "
+                             "biases, input, output; intermediates stay in L2) is below the measured machine balance "
+                             "(1641 TF/s / 6.55 TB/s = 251): with operand sets rotating through > L2 every weight byte comes "
+                             "from HBM and HBM bounds the step (DESIGN.md 4.1d). traffic = dram__bytes_read+write of ONE "
+                             "launch of the same shape under ncu (null when profiles/ has no capture of this shape)"},
         "cpu_baseline": cpu,
-        "extra": {"ms_per_step_single_forward": ms_hot,
-                  "single_forward_note": "one operand set replayed back to back (L2-hot, what tpp-run itself measures): "
-                                         "one forward pass per launch, the full-K pass kernel on 128 SMs",
-                  "host_issue_us_per_launch": t_issue / max(launches, 1) * 1e6,
-                  ("ms_per_step_direct_invokes" if args.mode == "graph" else "ms_per_step_graph_replay"): ms_other,
-                  "parity_rel_err_vs_oracle": rel, "kernel": timed_kernel,
-                  "per_layer_kernel": xsmm.handle_kernel(replay.handles[0])},
+        "parity": parity,
+        "extra": {"perf_timer_protocol": {"ms_per_step": perf_s * 1e3,
+                                          "gflops": flops_fwd_rank * fwd_per_step * n_gpus / perf_s / 1e9,
+                                          "what": "the same K steps between perf_start_timer / perf_stop_timer (wall clock)"},
+                  "host_issue_us_per_launch": tm["issue_s"] / max(launches, 1) * 1e6,
+                  "kernel": timed_kernel, "per_layer_kernel": xsmm.handle_kernel(wl.replay.handles[0]),
+                  **extras},
     }
     restore_stdout(saved_stdout)
     print(json.dumps(line))

@@ -125,7 +125,63 @@ def cfg3b(pk):
                          "frac": flops / t / 1e12 / pk["bf16_tflops"]}}
 
 
-def eltwise(pk):
+def cfg4(pk):
+    """BASELINE configs[3]: unary vnni_2 4096x4096 bf16 and its inverse, rotating operands > L2."""
+    rows = eltwise(pk, only=("cfg4 unary vnni_2 pack", "cfg4 inverse"))
+    head = dict(rows[0])
+    head["inverse"] = rows[1]
+    return head
+
+
+def reference_stream(pk):
+    """The reference's DEFAULT benchmark call stream (benchmarks/config/omp/mlir-bf16.json:37: --tiles=32,32,32 --vnni=2):
+    768 xsmm_fused_brgemm_invoke calls of a 32x32x32 x batch-32 VNNI-2 BRGEMM per forward pass on block-packed operands,
+    captured and replayed like bench.py's headline. Reports the throughput of that stream and which kernel ran it."""
+    import numpy as np
+
+    import bench
+
+    gen, Ws, bs = bench.make_host_data()
+    x = gen.fill(256, 1024)
+    dev = torch.device("cuda", torch.cuda.current_device())
+
+    def to_dev(a):
+        return torch.from_numpy(a.view(np.int16)).to(dev)
+
+    stream = torch.cuda.current_stream()
+    xsmm.set_stream(stream.cuda_stream)
+    probe = bench.MlpWorkload(256, to_dev(x), [to_dev(W) for W in Ws], [to_dev(b) for b in bs], tiles=(32, 32, 32),
+                              vnni=True, max_sets=1)
+    probe.rotations(1)
+    torch.cuda.synchronize()
+    fused = "pair" in xsmm.last_kernel() or "chain" in xsmm.last_kernel()
+    del probe
+    # one launch per tile invoke (no regrouping): keep the rotation short, it is ~2 ms per forward pass
+    wl = bench.MlpWorkload(256, to_dev(x), [to_dev(W) for W in Ws], [to_dev(b) for b in bs], tiles=(32, 32, 32), vnni=True,
+                           max_sets=None if fused else 4)
+    wl.rotations(2)
+    torch.cuda.synchronize()
+    n = 10 if fused else 2
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = xsmm.launch_count()
+    e0.record(stream)
+    wl.rotations(n)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / (n * wl.num_sets)
+    launches = (xsmm.launch_count() - l0) / (n * wl.num_sets)
+    s = wl.num_sets - 1
+    rel = bench.rel_err(wl.output(s).cpu().numpy().view(np.uint16), np.roll(bench.oracle_forward(x, Ws, bs), s, 0))
+    flops = wl.cfg.flops()
+    return {"config": "reference default stream: MLP 3x1024^2 bf16 batch 256, --tiles=32,32,32 --vnni=2 "
+                      "(768 invokes of 32x32x32 x batch 32 per forward pass, block-packed, VNNI-2 weights)",
+            "kernel": xsmm.last_kernel(), "seconds_per_forward": t, "gflops": flops / t / 1e9,
+            "kernel_launches_per_forward": launches, "operand_sets": wl.num_sets, "rel_err_vs_oracle": rel,
+            "roofline": {"bound": "hbm", "achieved": 7346176 / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": 7346176 / t / 1e9 / pk["hbm_gbs"], "algorithmic_bytes": 7346176}}
+
+
+def eltwise(pk, only=None):
     out = []
     m = n = 4096
     nbytes = m * n * 2
@@ -135,6 +191,8 @@ def eltwise(pk):
     bias = rnd(n)
 
     def run(name, h, invoke, alg_bytes, iters=60):
+        if only and not any(name.startswith(o) for o in only):
+            return
         t = timed([lambda i=i: invoke(i) for i in range(ns)], iters, warmup=ns)
         out.append({"config": name, "kernel": xsmm.handle_kernel(h), "seconds": t, "gbytes_per_s": alg_bytes / t / 1e9,
                     "reference_convention_gbs(input bytes only)": nbytes / t / 1e9,

@@ -18,6 +18,8 @@ std::vector<Event> g_capture;
 bool g_capturing = false;
 void *g_stream = nullptr;
 int64_t g_streams_created = 0;
+int64_t g_wait_ring = 1 << 30;                  // how many of the most recent downloads wait_host still knows
+std::vector<int64_t> g_downloads;               // hosts of the downloads issued outside captures, in order
 
 void record(const Event &e) { (g_capturing ? g_capture : g_log).push_back(e); }
 }  // namespace
@@ -31,8 +33,18 @@ void xsmm_fused_brgemm_invoke(int64_t dtype, int64_t addr, void *A, int64_t offA
   (void)numBatches;
 }
 int64_t xsmm_cuda_upload_async(void *host, int64_t bytes) { record({2, (int64_t)(intptr_t)host, bytes, 0, 0, 0}); return 0; }
-int64_t xsmm_cuda_download_async(void *host, int64_t bytes) { record({3, (int64_t)(intptr_t)host, bytes, 0, 0, 0}); return 0; }
-int64_t xsmm_cuda_wait_host(void *host) { record({4, (int64_t)(intptr_t)host, 0, 0, 0, 0}); return 0; }
+int64_t xsmm_cuda_download_async(void *host, int64_t bytes) {
+  record({3, (int64_t)(intptr_t)host, bytes, 0, 0, 0});
+  if (!g_capturing) g_downloads.push_back((int64_t)(intptr_t)host);
+  return 0;
+}
+int64_t xsmm_cuda_wait_host(void *host) {
+  record({4, (int64_t)(intptr_t)host, 0, 0, 0, 0});
+  const int64_t n = (int64_t)g_downloads.size();
+  for (int64_t i = n - 1; i >= 0 && i >= n - g_wait_ring; --i)
+    if (g_downloads[(size_t)i] == (int64_t)(intptr_t)host) return 0;
+  return -1;   // like the runtime: no such download on record any more
+}
 void xsmm_cuda_stream_sync(void) { record({5, (int64_t)(intptr_t)g_stream, 0, 0, 0, 0}); }
 int64_t xsmm_cuda_update_device(void *host, int64_t bytes) { record({6, (int64_t)(intptr_t)host, bytes, 0, 0, 0}); return 0; }
 int64_t xsmm_cuda_update_host(void *host, int64_t bytes) { record({7, (int64_t)(intptr_t)host, bytes, 0, 0, 0}); return 0; }
@@ -63,7 +75,10 @@ __attribute__((visibility("default"))) void stub_reset(void) {
   g_graphs.clear();
   g_capture.clear();
   g_capturing = false;
+  g_downloads.clear();
+  g_wait_ring = 1 << 30;
 }
+__attribute__((visibility("default"))) void stub_set_wait_ring(int64_t n) { g_wait_ring = n; }
 __attribute__((visibility("default"))) int64_t stub_log_size(void) { return (int64_t)g_log.size(); }
 __attribute__((visibility("default"))) void stub_log_get(int64_t i, int64_t *out6) {
   const Event &e = g_log[(size_t)i];

@@ -35,6 +35,7 @@ def lib(tmp_path_factory):
     lib.stub_log_size.restype = i64
     lib.stub_log_get.argtypes = [i64, p]
     lib.stub_num_graphs.restype = i64
+    lib.stub_set_wait_ring.argtypes = [i64]
     return lib
 
 
@@ -153,11 +154,24 @@ def test_grouped_e2e_pipeline_orders_copies_launches_and_waits(lib):
     assert lib.stub_num_graphs() == ngrp
 
 
-def test_grouped_e2e_refuses_large_groups_of_scattered_buffers(lib):
-    """xsmm_cuda_wait_host remembers the last 16 downloads: groups of more than 8 steps need one block per group."""
+def test_grouped_e2e_drains_when_a_download_is_no_longer_on_record(lib):
+    """xsmm_cuda_wait_host only remembers the most recent downloads; when it answers -1 the loop must drain the stream
+    (xsmm_cuda_stream_sync) before it reuses the slot - never reuse the buffer blindly (replay.cpp:168)."""
     gsz, ngrp = 12, 2
-    sets = make_sets(gsz * ngrp)   # scattered buffers
+    sets = make_sets(gsz * ngrp)   # scattered buffers: one download per step
     graphs, streams = (i64 * (gsz * ngrp + 1))(), (p * (gsz * ngrp))()
     lib.stub_reset()
+    lib.stub_set_wait_ring(16)     # fewer than the 24 downloads in flight
     assert lib.tpp_replay_mlp_e2e_pipelined(2, 3, HANDLES, SIZES, 256, 256, 1024, 1024, sets, gsz * ngrp, 4 * gsz, 1, 2,
-                                            2 + gsz, graphs, streams) == -1
+                                            2 + gsz, graphs, streams) == 4 * gsz
+    ev = log(lib)
+    waits = [i for i, e in enumerate(ev) if e[0] == 4]
+    assert waits, "slots are reused, so there must be waits"
+    forgotten = 0
+    for i in waits:
+        host = ev[i][1]
+        earlier = [e[1] for e in ev[:i] if e[0] == 3]
+        if host not in earlier[-16:]:
+            forgotten += 1
+            assert ev[i + 1][0] == 5, "a forgotten download must be followed by a stream sync"
+    assert forgotten > 0

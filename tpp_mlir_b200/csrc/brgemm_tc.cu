@@ -2076,6 +2076,9 @@ template <int BLOCK_N, int STAGES, int SPLITK> constexpr int smem_bytes() {
   return STAGES * SmemLayout<BLOCK_N>::kStageBytes + (SPLITK == 1 ? RECV_BYTES : 0) + (2 * STAGES + 1) * 8 + 16 + 1024;
 }
 
+// programmatic dependent launch of the next direct BRGEMM launch (false: plain stream order, see GemmArgs::pdl)
+thread_local int t_pdl_allowed = 1;
+
 template <int BLOCK_N, int STAGES, int SPLITK, int MC = 0>
 void launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, dim3 grid, cudaStream_t stream) {
   constexpr int smem = smem_bytes<BLOCK_N, STAGES, SPLITK>();
@@ -2092,7 +2095,7 @@ void launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &
   cudaLaunchAttribute attrs[2];
   int na = 0;
   attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attrs[na].val.programmaticStreamSerializationAllowed = 1;
+  attrs[na].val.programmaticStreamSerializationAllowed = t_pdl_allowed;
   ++na;
   if (SPLITK || MC) {
     attrs[na].id = cudaLaunchAttributeClusterDimension;
@@ -2121,7 +2124,7 @@ void launch_cfg_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
   cfg.stream = stream;
   cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  attrs[0].val.programmaticStreamSerializationAllowed = t_pdl_allowed;
   attrs[1].id = cudaLaunchAttributeClusterDimension;
   attrs[1].val.clusterDim.x = 2;
   attrs[1].val.clusterDim.y = 1;
@@ -2223,6 +2226,51 @@ static void choose_tile(const KernelDesc &d, int64_t total_iters, int *bn_out, i
 
 thread_local char t_last_name[64] = "brgemm_tc_bf16";
 
+// ---- device memory owned by the graph being captured ----------------------------------------------------------
+// Everything a captured kernel node reads or spins on (descriptor tables, arrival counters, split-K workspaces) is
+// allocated here, written / zeroed on a private non-capturing stream BEFORE the node can ever run, and handed to the
+// graph handle at xsmm_cuda_graph_end (brgemm_tc_take_capture_allocs), which frees it with the graph. Nothing a graph
+// references is shared with direct launches, so no later launch can free or re-zero it under a replay.
+thread_local std::vector<void *> t_capture_allocs;
+cudaStream_t table_stream() {
+  thread_local cudaStream_t st = nullptr;
+  if (!st) TPP_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  return st;
+}
+bool stream_is_capturing(cudaStream_t stream) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cs);
+  return cs != cudaStreamCaptureStatusNone;
+}
+// zero-filled device words, complete (not merely enqueued) when this returns: never a node of somebody's graph
+void *alloc_zeroed(size_t bytes) {
+  void *p = nullptr;
+  TPP_CUDA_CHECK(cudaMalloc(&p, bytes));
+  TPP_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, table_stream()));
+  TPP_CUDA_CHECK(cudaStreamSynchronize(table_stream()));
+  return p;
+}
+void *capture_owned_zeroed(size_t bytes) {
+  void *p = alloc_zeroed(bytes);
+  t_capture_allocs.push_back(p);
+  return p;
+}
+// split-K exchange workspace of the capture in progress: kernels of one captured stream are serialised, so they share
+// it; when a later launch needs more, a new one is allocated and the old one stays alive with the graph
+struct CaptureWs { float *ptr = nullptr; size_t bytes = 0; };
+thread_local CaptureWs t_capture_ws;
+float *capture_owned_ws(size_t need) {
+  if (need > t_capture_ws.bytes) {
+    void *p = nullptr;
+    const size_t want = need < (4u << 20) ? (4u << 20) : need;
+    TPP_CUDA_CHECK(cudaMalloc(&p, want));
+    t_capture_allocs.push_back(p);
+    t_capture_ws.ptr = static_cast<float *>(p);
+    t_capture_ws.bytes = want;
+  }
+  return t_capture_ws.ptr;
+}
+
 // Device scratch of the split-K exchange and the chain kernel's grid counters. One instance per (host thread, stream):
 // launches of one thread on one stream are serialised and may share it; a thread that pipelines work over several
 // streams (xsmm_cuda_stream_create + xsmm_cuda_set_stream) gets a private copy per stream, so kernels that overlap in
@@ -2232,9 +2280,6 @@ struct StreamScratch {
   float *ws = nullptr;
   size_t ws_bytes = 0;
   unsigned int *flags = nullptr;
-  float *chain_ws = nullptr;
-  unsigned int *chain_counters = nullptr;
-  std::vector<std::pair<int, unsigned int *>> ft_counters;   // feature-major chain: (group size, counters)
 };
 StreamScratch &scratch_for(cudaStream_t stream) {
   thread_local std::vector<StreamScratch *> all;
@@ -2255,6 +2300,7 @@ void brgemm_tc_configure(KernelDesc &d) {
 
 bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t stream) {
   if (!aligned16(g.A) || !aligned16(g.B)) return false;
+  t_pdl_allowed = g.pdl ? 1 : 0;
   const int64_t batch = g.batch;
   if (batch > (1ll << 31)) return false;
   const int32_t k_iters = (int32_t)((d.k + BLOCK_K - 1) / BLOCK_K);
@@ -2338,32 +2384,32 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   p.flags = nullptr;
   if (split > 1 && (!xchg_dsmem || block_n != 64)) {
     // per-(thread, stream) workspace: launches on one stream are serialised and may share it
-    StreamScratch &sc = scratch_for(stream);
-    float *&ws = sc.ws;
-    size_t &ws_bytes = sc.ws_bytes;
     const size_t need = (size_t)n_ctas * BLOCK_M * block_n * sizeof(float);
-    if (need > ws_bytes) {
-      cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(stream, &cs);
-      if (cs != cudaStreamCaptureStatusNone && ws_bytes > 0) return false;   // cannot re-allocate inside a capture
-      if (ws) { TPP_CUDA_CHECK(cudaDeviceSynchronize()); TPP_CUDA_CHECK(cudaFree(ws)); }
-      const size_t want = need < (8u << 20) ? (8u << 20) : need;
-      TPP_CUDA_CHECK(cudaMalloc(&ws, want));
-      ws_bytes = want;
-    }
-    p.ws = ws;
-    // arrival counters of the flag-synchronised exchange: zeroed once, only ever incremented; one region per S so
-    // that every counter is a multiple of S between launches
-    unsigned int *&flags = sc.flags;
+    const bool capturing = stream_is_capturing(stream);
     constexpr int kFlagTiles = 4096;
-    if (mc == 2) {
-      if (n_ctas / split > kFlagTiles) return false;
-      if (!flags) {
-        TPP_CUDA_CHECK(cudaMalloc(&flags, sizeof(unsigned int) * 2 * kFlagTiles));
-        // stream-ordered (and capturable: re-zeroing at every graph replay keeps the counters multiples of S)
-        TPP_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(unsigned int) * 2 * kFlagTiles, stream));
+    if (mc == 2 && n_ctas / split > kFlagTiles) return false;
+    if (capturing) {
+      // a captured node never shares scratch with direct launches (which may grow = free theirs): graph-owned memory
+      p.ws = capture_owned_ws(need);
+      if (mc == 2) p.flags = static_cast<unsigned int *>(capture_owned_zeroed(sizeof(unsigned int) * (size_t)(n_ctas / split)));
+    } else {
+      StreamScratch &sc = scratch_for(stream);
+      float *&ws = sc.ws;
+      size_t &ws_bytes = sc.ws_bytes;
+      if (need > ws_bytes) {
+        if (ws) { TPP_CUDA_CHECK(cudaDeviceSynchronize()); TPP_CUDA_CHECK(cudaFree(ws)); }
+        const size_t want = need < (8u << 20) ? (8u << 20) : need;
+        TPP_CUDA_CHECK(cudaMalloc(&ws, want));
+        ws_bytes = want;
       }
-      p.flags = flags + (split == 4 ? kFlagTiles : 0);
+      p.ws = ws;
+      // arrival counters of the flag-synchronised exchange: zeroed once (complete before the first launch), only ever
+      // incremented; one region per S so that every counter is a multiple of S between launches
+      unsigned int *&flags = sc.flags;
+      if (mc == 2) {
+        if (!flags) flags = static_cast<unsigned int *>(alloc_zeroed(sizeof(unsigned int) * 2 * kFlagTiles));
+        p.flags = flags + (split == 4 ? kFlagTiles : 0);
+      }
     }
   }
   if (trace_mode == 1 && n_ctas <= kTraceCtas) {
@@ -2429,6 +2475,40 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
 }
 
 // ---- fused chain launch -------------------------------------------------------------------------------------
+namespace {
+struct ByteRange { const char *lo, *hi; };
+inline bool overlaps(const ByteRange &a, const ByteRange &b) { return a.lo < b.hi && b.lo < a.hi; }
+inline ByteRange bf16_range(const void *p, int64_t elems) {
+  const char *c = static_cast<const char *>(p);
+  return ByteRange{c, c + elems * 2};
+}
+// No layer's weights / bias overlap ANY layer's output, no two outputs overlap, and the chain's input is not one of its
+// outputs (byte ranges, not pointer equality: an operand that starts inside another layer's C is a hazard too).
+bool chain_operands_hazard_free(const KernelDesc *const *descs, const GemmArgs *args, int L) {
+  ByteRange outs[8], bs[8], ds[8];
+  if (L > 8) return false;
+  for (int l = 0; l < L; ++l) {
+    const KernelDesc &d = *descs[l];
+    const int64_t nb = args[l].batch > 0 ? args[l].batch : 1;
+    outs[l] = bf16_range(args[l].C, (d.m - 1) * d.ldc + d.n);
+    bs[l] = bf16_range(args[l].B, (nb - 1) * d.stride_b + (d.k - 1) * d.ldb + d.n);
+    ds[l] = args[l].D ? bf16_range(args[l].D, d.n) : ByteRange{nullptr, nullptr};
+  }
+  const KernelDesc &d0 = *descs[0];
+  const int64_t nb0 = args[0].batch > 0 ? args[0].batch : 1;
+  const ByteRange in0 = bf16_range(args[0].A, (nb0 - 1) * d0.stride_a + (d0.m - 1) * d0.lda + d0.k);
+  for (int l = 0; l < L; ++l)
+    for (int j = 0; j < L; ++j) {
+      if (overlaps(bs[l], outs[j])) return false;
+      if (ds[l].lo && overlaps(ds[l], outs[j])) return false;
+      if (j != l && overlaps(outs[l], outs[j])) return false;
+    }
+  for (int j = 0; j < L; ++j)
+    if (overlaps(in0, outs[j])) return false;
+  return true;
+}
+}  // namespace
+
 // True if layers[0..L) can run in mlp_chain_kernel: every layer is a bf16 tensor-core BRGEMM with beta_0, the same
 // m and n, exactly 4 x CHAIN_IPC (batch x k-block) iterations, and layer l+1 reads layer l's C as its A.
 // Kernel-independent part: layers[0..L) form a chain - every layer a bf16 tensor-core BRGEMM with beta_0 on the same m
@@ -2448,13 +2528,10 @@ bool brgemm_chain_linked(const KernelDesc *const *descs, const GemmArgs *args, i
     if (l > 0) {
       if (args[l].A != args[l - 1].C || d.lda != descs[l - 1]->ldc) return false;
       if (args[l].batch * d.k != descs[l - 1]->n) return false;
-    }
-    for (int j = 0; j < L; ++j) {
-      if (args[l].B == args[j].C || (args[l].D && args[l].D == args[j].C)) return false;
-      if (j != l && args[l].C == args[j].C) return false;
+      if (args[l].batch > 1 && d.stride_a != d.k) return false;   // batch element b = columns [b k, b k + k) of C(l-1)
     }
   }
-  return true;
+  return chain_operands_hazard_free(descs, args, L);
 }
 
 bool brgemm_chain_supported(const KernelDesc *const *descs, const GemmArgs *args, int L) {
@@ -2474,13 +2551,10 @@ bool brgemm_chain_supported(const KernelDesc *const *descs, const GemmArgs *args
       // the chain link: A(l) is exactly C(l-1), viewed with the same leading dimension
       if (args[l].A != args[l - 1].C || d.lda != descs[l - 1]->ldc) return false;
       if (args[l].batch * d.k != descs[l - 1]->n) return false;
-    }
-    for (int j = 0; j < L; ++j) {   // weights / bias must not be produced inside the chain
-      if (args[l].B == args[j].C || (args[l].D && args[l].D == args[j].C)) return false;
-      if (j != l && args[l].C == args[j].C) return false;
+      if (args[l].batch > 1 && d.stride_a != d.k) return false;
     }
   }
-  return true;
+  return chain_operands_hazard_free(descs, args, L);   // weights / bias must not be produced inside the chain
 }
 
 // Feature-major chain (mlp_chain_ft_kernel): additionally needs m % 32 == 0, n % 64 == 0, a reduction of exactly
@@ -2528,8 +2602,6 @@ static int chain_ft_split(const KernelDesc *const *descs, const GemmArgs *args, 
 }
 
 namespace {
-struct ByteRange { const char *lo, *hi; };
-inline bool overlaps(const ByteRange &a, const ByteRange &b) { return a.lo < b.hi && b.lo < a.hi; }
 // operand footprints of one chain: inputs (first layer's A, every layer's B and D) and outputs (every layer's C)
 void chain_ranges(const KernelDesc *const *descs, const GemmArgs *args, int L, std::vector<ByteRange> &in,
                   std::vector<ByteRange> &out) {
@@ -2654,19 +2726,11 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   }
   dim3 grid((unsigned)(d0.n / FT_M), (unsigned)(d0.m / (32 * split)), (unsigned)split);
   const int n_ctas = (int)(grid.x * grid.y * grid.z);
-  StreamScratch &sc = scratch_for(stream);
-  // one counter array per (variant, group size G = grid.x): every counter stays a multiple of G between launches;
-  // the split-K-2 variant's launch epoch (+ exit ticket) lives behind its counters
-  const int ctr_key = (int)grid.x | (split << 16);
-  unsigned int *counters = nullptr;
-  for (auto &e : sc.ft_counters)
-    if (e.first == ctr_key) counters = e.second;
-  if (!counters) {
-    const size_t bytes = sizeof(unsigned int) * (FT_MAX_WAYS * FT_CTR_SLOT + 2 * FT_MAX_WAYS);
-    TPP_CUDA_CHECK(cudaMalloc(&counters, bytes));
-    TPP_CUDA_CHECK(cudaMemsetAsync(counters, 0, bytes, stream));
-    sc.ft_counters.emplace_back(ctr_key, counters);
-  }
+  // arrival counters of THIS kernel node (the chain kernels only ever run inside a capture): zero-filled before the
+  // node exists, owned by the graph, monotonic across its replays - every counter stays a multiple of the group size
+  // between launches; the split-K-2 variant's launch epoch (+ exit ticket) lives behind its counters
+  unsigned int *counters = static_cast<unsigned int *>(
+      capture_owned_zeroed(sizeof(unsigned int) * (FT_MAX_WAYS * FT_CTR_SLOT + 2 * FT_MAX_WAYS)));
   cp.counters = counters;
   cp.epoch = counters + FT_MAX_WAYS * FT_CTR_SLOT;
   for (int sl = 0; sl < FT_MAX_WAYS; ++sl) cp.arrivals_total[sl] = arrivals[sl];
@@ -2730,12 +2794,6 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
 
 // ---- pair-per-chain launch ---------------------------------------------------------------------------------------------
 namespace {
-thread_local std::vector<void *> t_capture_allocs;   // device tables baked into the graph being captured
-cudaStream_t table_stream() {
-  thread_local cudaStream_t st = nullptr;
-  if (!st) TPP_CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  return st;
-}
 bool chain_pair_supported(const KernelDesc *const *descs, const GemmArgs *args, int L) {
   const KernelDesc &d0 = *descs[0];
   if ((d0.m % PC_ROWS) != 0 || d0.m > (1 << 30)) return false;
@@ -2754,6 +2812,7 @@ bool chain_pair_supported(const KernelDesc *const *descs, const GemmArgs *args, 
 void brgemm_tc_take_capture_allocs(std::vector<void *> &out) {
   out.insert(out.end(), t_capture_allocs.begin(), t_capture_allocs.end());
   t_capture_allocs.clear();
+  t_capture_ws = CaptureWs();
 }
 
 // Launch a prefix of chains [0, num_chains) as ONE launch of mlp_chain_pair_kernel: every chain is cut into blocks of
@@ -2897,14 +2956,8 @@ bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, i
   dim3 grid((unsigned)((d0.n + 63) / 64), (unsigned)((d0.m + BLOCK_M - 1) / BLOCK_M), 4);
   const int n_ctas = (int)(grid.x * grid.y * grid.z);
   // per-(thread, stream) exchange workspace + grid counters (same life cycle as the stand-alone kernel's workspace)
-  StreamScratch &sc = scratch_for(stream);
-  float *&ws = sc.chain_ws;
-  unsigned int *&counters = sc.chain_counters;
-  if (!ws) {
-    TPP_CUDA_CHECK(cudaMalloc(&ws, (size_t)148 * BLOCK_M * 64 * sizeof(float)));
-    TPP_CUDA_CHECK(cudaMalloc(&counters, sizeof(unsigned int) * 256));
-    TPP_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 256, stream));
-  }
+  float *ws = capture_owned_ws((size_t)148 * BLOCK_M * 64 * sizeof(float));
+  unsigned int *counters = static_cast<unsigned int *>(capture_owned_zeroed(sizeof(unsigned int) * 256));
   cp.grid_counter = counters + n_ctas;   // one counter per grid size: always a multiple of G between launches
   cp.num_layers = L;
   cp.weights_early = 1;

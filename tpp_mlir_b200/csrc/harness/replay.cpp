@@ -9,9 +9,18 @@
 #include <algorithm>
 #include <cstdint>
 #include <map>
+#include <mutex>
 #include <tuple>
 
 #include "tpp_xsmm_abi.h"
+
+namespace {
+// the slot's previous output has reached the host; a download the runtime no longer remembers (its ring holds the
+// most recent ones) is waited for by draining the thread's streams - never by reusing the buffer blindly
+inline void wait_output(void *host) {
+  if (xsmm_cuda_wait_host(host) != 0) xsmm_cuda_stream_sync();
+}
+}  // namespace
 
 extern "C" {
 
@@ -78,14 +87,21 @@ int64_t tpp_replay_mlp_graph(int64_t dtype, int64_t num_layers, const int64_t *h
       // addresses: a later loop object whose arrays land on recycled addresses must not inherit these graphs
       static std::map<std::tuple<int64_t, int64_t, int64_t>, int64_t> partial;
       static int64_t next_loop_id = 0;
-      int64_t &loop_id = graphs[num_sets + 1];
-      if (!loop_id) loop_id = ++next_loop_id;
-      int64_t &g = partial[std::make_tuple(loop_id, idx, chunk)];
+      static std::mutex partial_mutex;
+      int64_t g = 0;
+      {
+        std::lock_guard<std::mutex> lock(partial_mutex);
+        int64_t &loop_id = graphs[num_sets + 1];
+        if (!loop_id) loop_id = ++next_loop_id;
+        g = partial[std::make_tuple(loop_id, idx, chunk)];
+      }
       if (!g) {
         if (xsmm_cuda_graph_begin() != 0) return -1;
         tpp_replay_mlp(dtype, num_layers, handles, layer_sizes, batch, bn, bk, bc, sets + idx, chunk, 0, chunk, has_bias);
         g = xsmm_cuda_graph_end();
         if (!g) return -1;
+        std::lock_guard<std::mutex> lock(partial_mutex);
+        partial[std::make_tuple(graphs[num_sets + 1], idx, chunk)] = g;
       }
       xsmm_cuda_graph_launch(g);
       s += chunk;
@@ -165,7 +181,7 @@ int64_t tpp_replay_mlp_e2e_pipelined(int64_t dtype, int64_t num_layers, const in
     for (int64_t s = 0; s < steps; ++s) {
       const int64_t d = s % depth;
       void *out = slots[d].acts[num_layers];
-      if (s >= depth) xsmm_cuda_wait_host(out);   // output of step s - depth consumed; the slot is free again
+      if (s >= depth) wait_output(out);   // output of step s - depth consumed; the slot is free again
       xsmm_cuda_upload_async(slots[d].acts[0], in_bytes);
       xsmm_cuda_graph_launch(graphs[d]);
       xsmm_cuda_download_async(out, out_bytes);
@@ -217,11 +233,10 @@ int64_t tpp_replay_mlp_e2e_pipelined(int64_t dtype, int64_t num_layers, const in
       const int64_t grp = it % ngrp;
       const TppMlpSet &g0 = slots[grp * gsz];
       const bool in_block = contiguous(grp, 0, in_bytes), out_block = contiguous(grp, num_layers, out_bytes);
-      if (!out_block && gsz > 8) return -1;   // wait_host remembers the last 16 downloads only
       // previous outputs of this group's slots consumed: the buffers are free again
       if (it >= ngrp) {
-        if (out_block) xsmm_cuda_wait_host(g0.acts[num_layers]);
-        else for (int64_t j = 0; j < gsz; ++j) xsmm_cuda_wait_host(slots[grp * gsz + j].acts[num_layers]);
+        if (out_block) wait_output(g0.acts[num_layers]);
+        else for (int64_t j = 0; j < gsz; ++j) wait_output(slots[grp * gsz + j].acts[num_layers]);
       }
       if (in_block) xsmm_cuda_upload_async(g0.acts[0], gsz * in_bytes);
       else for (int64_t j = 0; j < gsz; ++j) xsmm_cuda_upload_async(slots[grp * gsz + j].acts[0], in_bytes);

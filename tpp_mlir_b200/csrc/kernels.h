@@ -57,7 +57,12 @@ struct GemmArgs {
   // same for A: the fused chain kernel may then fetch its first layer's activations (and run that layer's MMAs,
   // which only touch shared / tensor memory) before the wait; stores always come after it
   bool a_independent = false;
+  // programmatic dependent launch allowed. The runtime clears it once per window of kPdlWindow PDL launches: a launch
+  // in plain stream order waits for EVERYTHING before it, so at most one window of kernels can ever be co-resident and
+  // the "not written by the last kPdlWindow kernels" test behind b_independent / a_independent is a proof, not a hope
+  bool pdl = true;
 };
+constexpr int kPdlWindow = 32;
 
 // generic FFMA BRGEMM (any dtype/ld/stride, VNNI-B), fused epilogue
 void launch_brgemm_simt(const KernelDesc &d, const GemmArgs &g, cudaStream_t stream);

@@ -92,6 +92,8 @@ struct PendingTile {
   char *in, *out;
 };
 
+constexpr int kDownloadRing = 64;   // downloads xsmm_cuda_wait_host can still find (callers fall back to a stream sync)
+
 struct ThreadCtx {
   // BRGEMM invokes recorded during graph capture and not launched yet: consecutive layers whose C is the next
   // layer's A are fused into one persistent kernel when the sequence is flushed (see flush_pending)
@@ -100,6 +102,7 @@ struct ThreadCtx {
   // launched as one batched kernel by flush_tiles(). At most one of the two pending lists is non-empty.
   std::vector<PendingTile> pending_tiles;
   std::vector<void *> capture_tables;   // device tables baked into the graph being captured (freed with it)
+  std::vector<std::pair<cudaStream_t, Staging *>> vnni_scratch;   // VNNI-2 un-interleave scratch, one per stream
   cudaStream_t stream = nullptr; // legacy default stream unless xsmm_cuda_set_stream was called
   int device = -1;               // device this thread last launched on
   const char *last_kernel = "";
@@ -110,10 +113,13 @@ struct ThreadCtx {
   cudaStream_t saved_stream = nullptr;
   int64_t captured_launches = 0;
   // device ranges written by the last few kernels of this thread (dependency tracking for PDL)
-  struct Range { const char *lo = nullptr, *hi = nullptr; } recent_out[8];
+  // kPdlWindow entries: every kernel that can still be running when a new one starts its prologue is in here, because
+  // after kPdlWindow programmatic launches in a row the next one is issued in plain stream order (pdl_run)
+  struct Range { const char *lo = nullptr, *hi = nullptr; } recent_out[kPdlWindow];
   int recent_pos = 0;
+  int pdl_run = 0;               // programmatic launches since the last launch in plain stream order
   void note_output(const char *lo, size_t bytes) {
-    recent_out[recent_pos & 7] = {lo, lo + bytes};
+    recent_out[recent_pos % kPdlWindow] = {lo, lo + bytes};
     ++recent_pos;
   }
   bool recently_written(const char *lo, size_t bytes) const {
@@ -127,7 +133,7 @@ struct ThreadCtx {
   cudaEvent_t ev_up = nullptr, ev_compute = nullptr, ev_fork = nullptr, ev_join = nullptr;
   bool up_pending = false;       // the compute stream must wait for ev_up before its next launch
   bool up_in_capture = false, down_in_capture = false;   // side streams forked into the running capture
-  struct Download { void *host = nullptr; cudaEvent_t ev = nullptr; } downloads[16];
+  struct Download { void *host = nullptr; cudaEvent_t ev = nullptr; } downloads[kDownloadRing];
   int download_pos = 0;
 };
 
@@ -216,6 +222,10 @@ Resolved resolve(const void *base, const void *elem) {
 }
 
 void use_device(int dev) {
+  if (dev < 0 && t_ctx.device < 0) {   // a thread's first launch without a device operand: TPP_XSMM_DEVICE, in EVERY thread
+    static const int env_dev = [] { const char *e = getenv("TPP_XSMM_DEVICE"); return e ? atoi(e) : -1; }();
+    dev = env_dev;
+  }
   if (dev >= 0 && dev != t_ctx.device) {
     TPP_CUDA_CHECK(cudaSetDevice(dev));
     t_ctx.device = dev;
@@ -409,14 +419,28 @@ void issue_gemm(const KernelDesc *d, const GemmArgs &g, cudaStream_t stream) {
     if (launched) t_ctx.last_kernel = brgemm_tc_last_name();
   } else if (d->flat_twin && batch > 0 && (double)d->m * d->n * d->k * batch >= 2097152.0 &&
              (batch == 1 || d->stride_b == d->k * d->ldb) && aligned16(g.B)) {
-    // VNNI-B -> flat B in a per-thread scratch (batches are contiguous: one tall [batch*k][ldb] un-interleave)
-    thread_local Staging vnni_scratch;
+    // VNNI-B -> flat B in a scratch buffer (batches are contiguous: one tall [batch*k][ldb] un-interleave). The scratch
+    // belongs to this (thread, stream): launches of one stream are serialised and may share it, kernels on different
+    // streams never do. A captured launch gets a buffer owned by the graph instead, so that no later, larger direct
+    // invoke can free memory a graph still references.
     const int64_t rows = batch * d->k;
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    cudaStreamIsCapturing(stream, &cs);
     const size_t need = (size_t)rows * d->ldb * 2;
-    if (cs == cudaStreamCaptureStatusNone || need <= vnni_scratch.cap) {
-      void *flat = vnni_scratch.get(need);
+    void *flat = nullptr;
+    if (t_ctx.capturing) {
+      TPP_CUDA_CHECK(cudaMalloc(&flat, need));
+      t_ctx.capture_tables.push_back(flat);
+    } else {
+      Staging *scratch = nullptr;
+      for (auto &e : t_ctx.vnni_scratch)
+        if (e.first == stream) scratch = e.second;
+      if (!scratch) {
+        scratch = new Staging();
+        t_ctx.vnni_scratch.emplace_back(stream, scratch);
+      }
+      if (need > scratch->cap) TPP_CUDA_CHECK(cudaStreamSynchronize(stream));   // the old buffer may still be in use
+      flat = scratch->get(need);
+    }
+    {
       launch_vnni2_unpack(g.B, flat, rows, d->n, d->ldb, d->ldb, stream);
       count_launch();
       GemmArgs gf = g;
@@ -558,6 +582,14 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
     g.b_independent = !t_ctx.recently_written(ops[1].dev, (size_t)ops[1].width * es) &&
                       (!has_d || !t_ctx.recently_written(ops[3].dev, (size_t)((ops[3].rows - 1) * ops[3].ld + ops[3].width) * es));
     t_ctx.note_output(ops[2].dev, (size_t)((d->m - 1) * d->ldc + d->n) * es);
+  }
+  if (d->impl == KernelImpl::BrgemmTC && !t_ctx.capturing) {
+    if (++t_ctx.pdl_run >= kPdlWindow) {   // close the window: this launch waits for everything before it
+      g.pdl = false;
+      t_ctx.pdl_run = 0;
+    }
+  } else {
+    t_ctx.pdl_run = 0;                     // generic kernels / captured work are launched in plain stream order
   }
   if (t_ctx.capturing && !sc.any_host && d->impl == KernelImpl::BrgemmTC) {
     flush_tiles();
@@ -861,6 +893,7 @@ static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int
   }
   flush_tiles();
   (void)mode;
+  t_ctx.pdl_run = 0;   // a plain launch: ordered after everything before it
   launch_unary(d, ops[0].dev, ops[1].dev, use_imm, imm, stream);
   t_ctx.note_output(ops[1].dev, (size_t)((ops[1].rows - 1) * ops[1].ld + ops[1].width) * esize(dtype));
   t_ctx.last_kernel = d->name;
@@ -905,6 +938,7 @@ extern "C" void xsmm_binary_invoke(int64_t dtype, int64_t addr, void *alignedPtr
   a.mode0 = mode0; a.mode1 = mode1;
   a.op = kOpAdd + (int)(d->kind - 1);
   a.dtype = dtype;
+  t_ctx.pdl_run = 0;
   launch_eltwise(a, stream);
   t_ctx.note_output(ops[2].dev, (size_t)((ops[2].rows - 1) * ops[2].ld + ops[2].width) * esize(dtype));
   t_ctx.last_kernel = d->name;
@@ -946,8 +980,10 @@ extern "C" void xsmm_cuda_set_stream(void *stream) {
     t_ctx.saved_stream = static_cast<cudaStream_t>(stream);
     return;
   }
-  if (t_ctx.stream != static_cast<cudaStream_t>(stream))
-    for (auto &r : t_ctx.recent_out) r = {};   // dependency tracking is per stream; cross-stream order is the caller's
+  if (t_ctx.stream != static_cast<cudaStream_t>(stream)) {
+    for (auto &r : t_ctx.recent_out) r = {};
+    t_ctx.pdl_run = kPdlWindow;   // first BRGEMM on the new stream: plain stream order
+  }   // dependency tracking is per stream; cross-stream order is the caller's
   t_ctx.stream = static_cast<cudaStream_t>(stream);
 }
 extern "C" void *xsmm_cuda_get_stream(void) { return t_ctx.stream; }
@@ -1077,7 +1113,7 @@ extern "C" int64_t xsmm_cuda_download_async(void *host, int64_t bytes) {
   TPP_CUDA_CHECK(cudaMemcpyAsync(host, m.dev + (static_cast<char *>(host) - m.host), (size_t)bytes,
                                  cudaMemcpyDeviceToHost, t_ctx.down_stream));
   if (!t_ctx.capturing) {
-    ThreadCtx::Download &d = t_ctx.downloads[t_ctx.download_pos++ & 15];
+    ThreadCtx::Download &d = t_ctx.downloads[t_ctx.download_pos++ % kDownloadRing];
     d.host = host;
     TPP_CUDA_CHECK(cudaEventRecord(d.ev, t_ctx.down_stream));
   }
@@ -1085,10 +1121,11 @@ extern "C" int64_t xsmm_cuda_download_async(void *host, int64_t bytes) {
 }
 
 // Block until the most recent xsmm_cuda_download_async(host, ...) of this thread has delivered its bytes.
-// Returns -1 if the thread has no such download on record (only the last 16 are kept).
+// Returns -1 if the thread has no such download on record (only the last kDownloadRing are kept): the caller must then
+// drain the stream (xsmm_cuda_stream_sync) before it reuses the buffer.
 extern "C" int64_t xsmm_cuda_wait_host(void *host) {
-  for (int i = 1; i <= 16; ++i) {
-    ThreadCtx::Download &d = t_ctx.downloads[(t_ctx.download_pos - i) & 15];
+  for (int i = 1; i <= kDownloadRing && i <= t_ctx.download_pos; ++i) {
+    ThreadCtx::Download &d = t_ctx.downloads[(t_ctx.download_pos - i) % kDownloadRing];
     if (d.host == host && d.ev) {
       TPP_CUDA_CHECK(cudaEventSynchronize(d.ev));
       return 0;
