@@ -1,0 +1,521 @@
+// mlp_chain_pair.cu - pair-per-chain kernel: one CTA pair (tcgen05.mma.cta_group::2, 256 x 256 tiles) walks a whole
+// layer chain for a block of 256 batch rows, many chains side by side. The dominant kernel of bench.py. DESIGN.md 4.1d.
+#include "tc_common.cuh"
+
+namespace tpp {
+using namespace tc;
+
+namespace {
+
+// ---- pair-per-chain kernel: one CTA pair runs a whole layer chain, many chains side by side ---------------------------
+// Third design of the fused chain, for launches that carry MANY independent chains (a captured graph of the
+// benchmark's rotating operand sets, a batch of requests, or the 256-row blocks of a large-batch MLP: rows are
+// independent through all layers). The pass kernels above spread ONE layer over 128 SMs in 64 x 64 tiles: every SM then
+// receives 128 KiB of operands per layer pass, 16 MiB per layer over all SMs for 2.5 MiB of unique data, and the
+// chip-wide L2 -> SM throughput (~6300 B/clk) bounds a pass at ~2700 clk no matter how the latencies are hidden.
+// Here a work item (one chain x one block of 256 batch rows) belongs to ONE pair of CTAs (two SMs of a TPC,
+// tcgen05.mma.cta_group::2, M = 256) which walks the layers and, per layer, the 256-column output tiles:
+//   * per tile and k-block each CTA stages its 128 activation rows (16 KiB) and HALF of the 256 weight columns (16 KiB);
+//     a layer costs 4 MiB of L2 -> SM traffic per item instead of 16 MiB, every weight byte is fetched exactly once;
+//   * CTA r only ever reads the activation rows it wrote itself (rows 128 r .. 128 r + 127 of the item), so a layer
+//     boundary needs no cross-SM synchronisation at all: the epilogue thread that issues the CTA's TMA stores waits
+//     for their completion and arrives on a LOCAL mbarrier per output tile; the CTA's producer waits for tile i / 4
+//     before reduction step i of the next layer's first tile. No counters, no co-residency assumption, nothing to
+//     spin on across SMs; the last epilogue of a layer hides behind 12 of the next tile's 16 reduction steps;
+//   * the next layer's weights do not depend on anything: their box of a ring slot is always issued BEFORE that wait
+//     (same mbarrier, expect_tx covers both operands);
+//   * TMEM holds two 256-column accumulators: the epilogue of tile t (tcgen05.ld -> bias from shared memory -> ReLU ->
+//     bf16 -> swizzled staging buffer -> TMA store) runs under the MMAs of tile t + 1;
+//   * L2 eviction-priority hints keep the activations (re-read once per output tile) resident under the weight stream;
+//   * pairs are independent: the grid is min(items, 74) pairs, pair p takes items p, p + pairs, ...
+// Layer descriptors (three tensor maps + epilogue parameters per layer) live in a device table written once at capture.
+// History of the measurements that shaped it: profiles/kernel_trace_r1.txt.
+constexpr int PC_STAGES = 6;
+constexpr int PC_BLOCK_N = 256;                       // output columns per tile (UMMA N)
+constexpr int PC_HALF_N = PC_BLOCK_N / 2;             // weight columns staged by each CTA
+constexpr int PC_W_CHUNKS = PC_HALF_N / 64;           // 64-column TMA boxes per CTA and k-block
+constexpr int PC_STAGE_BYTES = A_STAGE_BYTES + PC_W_CHUNKS * B_CHUNK_BYTES;   // 32 KiB
+constexpr int PC_ROWS = 2 * BLOCK_M;                  // batch rows per work item
+constexpr int PC_OUT_COLS = 64;                       // columns per TMA store box (128 bytes: one swizzle row)
+constexpr int PC_OUT_BYTES = BLOCK_M * PC_OUT_COLS * 2;   // 16 KiB staging buffer, two of them
+constexpr int PC_BIAS_BYTES = PC_BLOCK_N * 2;         // one tile's bias slice, two of them
+constexpr int PC_MAX_TILES = 16;                      // output tiles per layer (n <= 4096): one "stored" barrier each
+constexpr int PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 2 * PC_OUT_BYTES + 2 * PC_BIAS_BYTES +
+                        (2 * PC_STAGES + 4 + PC_MAX_TILES) * 8 + 16 + 1024;
+
+struct alignas(128) PcLayer {
+  CUtensorMap tmX;          // activations: (k, row, batch element), box 64 x 128
+  CUtensorMap tmW;          // weights: (n, k, batch element), box 64 x 64
+  CUtensorMap tmC;          // output: (n, row, 1), box 64 x 128 (TMA store from the swizzled staging buffer)
+  void *C;
+  const void *D;            // bias vector or nullptr
+  int64_t ldc;
+  int32_t k_iters;          // k-blocks per batch element
+  int32_t total_iters;      // batch x k_iters
+  int32_t n_tiles;          // n / 256
+  int32_t n;
+  int32_t relu;
+  int32_t pad[3];
+};
+struct PcItem {
+  int32_t layer0, num_layers, row0, pad;
+};
+struct PcParams {
+  const PcLayer *layers;
+  const PcItem *items;
+  int32_t num_items;
+  int32_t prefetch_w;          // L2 prefetch of the next tile's weight boxes (TPP_XSMM_CHAIN_PAIR_PREFETCH=1)
+  int32_t l2_hints;            // L2 eviction-priority hints on the TMA loads / stores (TPP_XSMM_CHAIN_PAIR_HINTS=0: off)
+  unsigned long long *trace;   // TPP_XSMM_TC_TRACE=4: clock stamps of each CTA's first item (nullptr in normal runs)
+};
+__device__ __forceinline__ void pc_stamp(const PcParams &cp, int slot) {
+  if (cp.trace) cp.trace[(size_t)blockIdx.x * PC_TRACE_SLOTS + slot] = clock64();
+}
+
+__device__ __forceinline__ void tensormap_acquire(const void *map) {
+  // the table was written by a host copy: make it visible to the tensor-map proxy of this SM before the first use
+  asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const PcParams cp) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = smem_base;                                       // PC_STAGES x 16 KiB
+  const uint32_t smem_w = smem_base + PC_STAGES * A_STAGE_BYTES;           // PC_STAGES x 2 x 8 KiB
+  const uint32_t smem_out = smem_w + PC_STAGES * PC_W_CHUNKS * B_CHUNK_BYTES;   // 2 x 16 KiB output staging
+  const uint32_t smem_bias = smem_out + 2 * PC_OUT_BYTES;                  // 2 x 512 B: bias slice of tile t / t + 1
+  const uint32_t bar_base = smem_bias + 2 * PC_BIAS_BYTES;
+  const uint32_t full_bar = bar_base;                                      // leader's: both CTAs' bytes land on it
+  const uint32_t empty_bar = bar_base + PC_STAGES * 8;                     // per CTA, released by the pair's MMA commits
+  const uint32_t acc_full = bar_base + 2 * PC_STAGES * 8;                  // [2] per CTA: accumulator complete
+  const uint32_t acc_free = acc_full + 16;                                 // [2] leader's: both epilogues have read it out
+  const uint32_t tile_done = acc_free + 16;                                // [PC_MAX_TILES] per CTA: my rows of output tile j are stored
+  const uint32_t tmem_slot = tile_done + 8 * PC_MAX_TILES;
+  uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t peer = ptx::cluster_ctarank();       // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < PC_STAGES; ++s) {
+      ptx::mbar_init(full_bar + 8 * s, 1);
+      ptx::mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(acc_full + 8 * b, 1);
+      ptx::mbar_init(acc_free + 8 * b, 8);            // one arrival per epilogue warp of both CTAs
+    }
+    for (int j = 0; j < PC_MAX_TILES; ++j) ptx::mbar_init(tile_done + 8 * j, 1);   // the thread that issues the TMA stores
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, 2 * PC_BLOCK_N);  // all 512 columns: two accumulators
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before_sync();
+  __syncwarp();
+  ptx::cluster_arrive();   // both CTAs' barriers and TMEM exist before any remote signal / pair MMA
+  ptx::cluster_wait();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_acc = *tmem_slot_ptr;
+
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (threadIdx.x == 0) pc_stamp(cp, 60);
+
+  if (warp == 0) {
+    // ===== TMA producer (both CTAs): own rows / own weight columns into own smem, bytes counted on the LEADER =====
+    if (lane == 0) {
+      const uint32_t leader_full = ptx::mapa(full_bar, 0);
+      // L2 residency (measured with ncu before the hints: 1.34 GB of DRAM reads per launch for 1.01 GB of operands -
+      // the weight stream evicted activations between their four re-reads): weights are used once -> evict_first;
+      // activations are re-read once per output tile -> evict_last until the layer's last tile, whose read demotes them
+      const uint64_t pol_first = ptx::l2_policy_evict_first(), pol_last = ptx::l2_policy_evict_last();
+      const bool hints = cp.l2_hints != 0;
+      const bool prefetch_w = cp.prefetch_w != 0;
+      int s = 0;
+      uint32_t ph = 0, done_ph = 0;                   // done_ph bit j: parity of tile_done[j]'s next phase
+      for (int item = pair; item < cp.num_items; item += num_pairs) {
+        const PcItem it = cp.items[item];
+        const int32_t row0 = it.row0 + (int32_t)peer * BLOCK_M;
+        for (int l = 0; l < it.num_layers; ++l) {
+          const PcLayer *L = cp.layers + it.layer0 + l;
+          tensormap_acquire(&L->tmX);
+          tensormap_acquire(&L->tmW);
+          const int32_t k_iters = L->k_iters, total = L->total_iters, n_tiles = L->n_tiles;
+          int32_t ready = 0;                          // output tiles of layer l - 1 (my rows) known to be stored
+          for (int32_t j = 0; j < n_tiles; ++j) {
+            const int32_t wcol = j * PC_BLOCK_N + (int32_t)peer * PC_HALF_N;
+            const uint64_t pol_x = (j + 1 < n_tiles) ? pol_last : pol_first;
+            int32_t b = 0, kb = 0;
+            for (int32_t i = 0; i < total; ++i) {
+              ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
+              if (peer == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2 * PC_STAGE_BYTES);   // both CTAs' bytes
+              // the weights depend on nothing: their boxes go out before any wait for the previous layer
+#pragma unroll
+              for (int c = 0; c < PC_W_CHUNKS; ++c) {
+                if (hints)
+                  ptx::tma_load_3d_pair_hint(smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES, &L->tmW, leader_full + 8 * s,
+                                             wcol + c * 64, kb * BLOCK_K, b, pol_first);
+                else
+                  ptx::tma_load_3d_pair(smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES, &L->tmW, leader_full + 8 * s,
+                                        wcol + c * 64, kb * BLOCK_K, b);
+              }
+              if (prefetch_w && (j & 1) == 0 && j + 1 < n_tiles) {
+                // the same k-rows of the NEXT tile's weight columns go to L2 now: DRAM sees runs of 1 KiB per row
+                // (this pair's two tiles) instead of 512 B, and the odd tiles' weight loads hit L2
+#pragma unroll
+                for (int c = 0; c < PC_W_CHUNKS; ++c)
+                  ptx::tma_prefetch_3d(&L->tmW, wcol + PC_BLOCK_N + c * 64, kb * BLOCK_K, b);
+              }
+              if (l > 0 && j == 0) {
+                // reduction step i reads columns [64 i, 64 i + 64) of the previous layer's output = its tile i / 4:
+                // only the last four steps of the first tile have to wait for the previous layer's last epilogue
+                const int32_t need = (i * BLOCK_K) / PC_BLOCK_N;
+                while (ready <= need) {
+                  const bool last = ready + 1 == (total * BLOCK_K) / PC_BLOCK_N;
+                  if (last && item == pair) pc_stamp(cp, 48 + 2 * l);
+                  ptx::mbar_wait(tile_done + 8 * ready, (done_ph >> ready) & 1u);
+                  if (last && item == pair) pc_stamp(cp, 49 + 2 * l);
+                  done_ph ^= 1u << ready;
+                  ++ready;
+                  asm volatile("fence.proxy.async;" ::: "memory");
+                }
+              }
+              if (hints)
+                ptx::tma_load_3d_pair_hint(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, kb * BLOCK_K, row0, b,
+                                           pol_x);
+              else
+                ptx::tma_load_3d_pair(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, kb * BLOCK_K, row0, b);
+              if (++kb == k_iters) { kb = 0; ++b; }
+              if (++s == PC_STAGES) { s = 0; ph ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: the leader only =====
+    if (lane == 0 && peer == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(PC_ROWS, PC_BLOCK_N, /*A K-major*/ 0, /*B MN-major*/ 1);
+      const uint16_t pair_mask = 3;
+      int s = 0;
+      uint32_t ph = 0, t = 0;
+      for (int item = pair; item < cp.num_items; item += num_pairs) {
+        const PcItem it = cp.items[item];
+        for (int l = 0; l < it.num_layers; ++l) {
+          const PcLayer *L = cp.layers + it.layer0 + l;
+          const int32_t total = L->total_iters, n_tiles = L->n_tiles;
+          for (int32_t j = 0; j < n_tiles; ++j, ++t) {
+            const uint32_t buf = t & 1;
+            if (t >= 2) {                              // both epilogues have read tile t - 2 out of this accumulator
+              ptx::mbar_wait_cluster(acc_free + 8 * buf, ((t >> 1) - 1) & 1);
+              ptx::tc_fence_after_sync();
+            }
+            const uint32_t acc = tmem_acc + buf * PC_BLOCK_N;
+            if (t < 12) pc_stamp(cp, 4 * t);
+            for (int32_t i = 0; i < total; ++i) {
+              ptx::mbar_wait(full_bar + 8 * s, ph);
+              ptx::tc_fence_after_sync();
+              const uint32_t a_addr = smem_a + s * A_STAGE_BYTES;
+              const uint32_t b_addr = smem_w + s * PC_W_CHUNKS * B_CHUNK_BYTES;
+#pragma unroll
+              for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
+                const uint64_t da = ptx::umma_smem_desc_sw128(a_addr + kk * (UMMA_K * 2), 16, 1024);
+                const uint64_t db = ptx::umma_smem_desc_sw128(b_addr + kk * (UMMA_K * 128), B_CHUNK_BYTES, 1024);
+                ptx::umma_bf16_pair(acc, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
+              }
+              ptx::umma_commit_pair(empty_bar + 8 * s, pair_mask);   // frees the slot in both CTAs
+              if (++s == PC_STAGES) { s = 0; ph ^= 1; }
+            }
+            ptx::umma_commit_pair(acc_full + 8 * buf, pair_mask);    // both epilogues may start
+            if (t < 12) pc_stamp(cp, 4 * t + 1);
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue (both CTAs, each on its own 128 rows / TMEM lanes) =====
+    // TMEM lane = row: a thread owns one output row. Its bf16 results go to a 128-byte-swizzled staging buffer
+    // (64 columns x 128 rows), which one thread hands to TMA as a store box: full 128-byte lines leave the SM instead of
+    // 16-byte pieces of 32 different lines per warp instruction (measured: direct stores cost 15.7k clk per tile, twice
+    // the tile's MMA time).
+    const int q = warp & 3;
+    const int r_in = q * 32 + lane;                   // row within this CTA's 128
+    const uint32_t leader_acc_free = ptx::mapa(acc_free, 0);
+    const uint32_t lane_addr = tmem_acc + (static_cast<uint32_t>(q * 32) << 16);
+    const bool issuer = threadIdx.x == 64;
+    const uint64_t pol_first = ptx::l2_policy_evict_first(), pol_last = ptx::l2_policy_evict_last();
+    const bool hints = cp.l2_hints != 0;
+    const uint32_t row_off = (uint32_t)r_in * 128u;
+    const uint32_t sw = (uint32_t)(r_in & 7);
+    uint32_t t = 0, g = 0;                            // tiles / store boxes handled so far
+    // The bias slice of a tile (256 bf16) is staged in shared memory one tile ahead: thread i fetches columns 2i, 2i+1
+    // of the NEXT tile into a register before it starts on the current one and parks it in the other half of the
+    // buffer afterwards, so no global-load latency (an L2 / HBM miss every time: bias slices are never reused by an SM)
+    // sits inside the column loop. Measured before: 8 exposed misses per tile, epilogue 10-20k clk for 8k clk of MMAs.
+    auto fetch_bias = [&](const void *D, int32_t j) -> uint32_t {
+      return D ? __ldg(reinterpret_cast<const uint32_t *>(static_cast<const uint16_t *>(D) + (size_t)j * PC_BLOCK_N) + r_in) : 0u;
+    };
+    if (pair < cp.num_items) {
+      const PcItem it0 = cp.items[pair];
+      const uint32_t b0 = fetch_bias(cp.layers[it0.layer0].D, 0);
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_bias + (uint32_t)r_in * 4u), "r"(b0) : "memory");
+    }
+    for (int item = pair; item < cp.num_items; item += num_pairs) {
+      const PcItem it = cp.items[item];
+      const int32_t row0 = it.row0 + (int32_t)peer * BLOCK_M;
+      for (int l = 0; l < it.num_layers; ++l) {
+        const PcLayer *L = cp.layers + it.layer0 + l;
+        if (issuer) tensormap_acquire(&L->tmC);
+        const void *Dp = L->D;
+        const bool relu = L->relu != 0;
+        const int32_t n_tiles = L->n_tiles;
+        for (int32_t j = 0; j < n_tiles; ++j, ++t) {
+          const uint32_t buf = t & 1;
+          // next tile's bias: same layer / next layer / first layer of this pair's next item
+          uint32_t bias_next = 0;
+          if (j + 1 < n_tiles) bias_next = fetch_bias(Dp, j + 1);
+          else if (l + 1 < it.num_layers) bias_next = fetch_bias(L[1].D, 0);
+          else if (item + num_pairs < cp.num_items) bias_next = fetch_bias(cp.layers[cp.items[item + num_pairs].layer0].D, 0);
+          ptx::mbar_wait(acc_full + 8 * buf, (t >> 1) & 1);
+          ptx::tc_fence_after_sync();
+          if (t < 12 && issuer) pc_stamp(cp, 4 * t + 2);
+          const uint32_t bias_s = smem_bias + buf * PC_BIAS_BYTES;
+#pragma unroll 1
+          for (int c = 0; c < PC_BLOCK_N; c += PC_OUT_COLS, ++g) {
+            const uint32_t sbuf = smem_out + (g & 1) * PC_OUT_BYTES;
+            // the store box issued two boxes ago has been read out of this staging buffer
+            if (issuer) ptx::bulk_wait_group_read<1>();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+            for (int h = 0; h < PC_OUT_COLS; h += 32) {
+              uint32_t r[32];
+              ptx::tmem_ld_32x32(lane_addr + buf * PC_BLOCK_N + c + h, r);
+              uint32_t bw[16];
+#pragma unroll
+              for (int u = 0; u < 4; ++u)             // warp-uniform address: a broadcast read
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(bw[4 * u]), "=r"(bw[4 * u + 1]), "=r"(bw[4 * u + 2]), "=r"(bw[4 * u + 3])
+                             : "r"(bias_s + (uint32_t)((c + h) * 2 + u * 16)));
+              ptx::tmem_ld_wait();
+              if (c + h == PC_BLOCK_N - 32) {         // the accumulator is in registers: hand it back to the MMA issuer
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive_remote(leader_acc_free + 8 * buf);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                uint32_t o[4];
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                  float lo = __uint_as_float(r[8 * u + 2 * w]), hi = __uint_as_float(r[8 * u + 2 * w + 1]);
+                  if (Dp) {
+                    lo += __uint_as_float(bw[4 * u + w] << 16);
+                    hi += __uint_as_float(bw[4 * u + w] & 0xffff0000u);
+                  }
+                  if (relu) { lo = relu_f32(lo); hi = relu_f32(hi); }
+                  o[w] = pack_bf16x2(lo, hi);
+                }
+                const uint32_t chunk = (uint32_t)(h / 8 + u);   // 16-byte chunk of the 128-byte row
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                             ::"r"(sbuf + row_off + ((chunk ^ sw) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                             : "memory");
+              }
+            }
+            ptx::fence_proxy_async();                 // my shared-memory writes -> the async proxy (TMA store)
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (issuer) {
+              // a layer output that the next layer re-reads four times stays in L2; the chain's result does not
+              if (!hints) ptx::tma_store_3d(&L->tmC, sbuf, j * PC_BLOCK_N + c, row0, 0);
+              else ptx::tma_store_3d_hint(&L->tmC, sbuf, j * PC_BLOCK_N + c, row0, 0,
+                                          l + 1 < it.num_layers ? pol_last : pol_first);
+              ptx::bulk_commit_group();
+              if (c == 0 && j > 0 && l + 1 < it.num_layers) {
+                // every store group but the one just committed is complete: tile j - 1 (my rows) is in L2
+                ptx::bulk_wait_group<1>();
+                ptx::mbar_arrive(tile_done + 8 * (j - 1));
+              }
+            }
+          }
+          // the other half of the bias buffer was last read during tile t - 1: every thread is past that
+          asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_bias + (buf ^ 1u) * PC_BIAS_BYTES + (uint32_t)r_in * 4u), "r"(bias_next)
+                       : "memory");
+          if (t < 12 && issuer) pc_stamp(cp, 4 * t + 3);
+        }
+        if (l + 1 < it.num_layers && issuer) {
+          // the layer's last tile: its stores are the only ones outstanding
+          ptx::bulk_wait_group<0>();
+          ptx::mbar_arrive(tile_done + 8 * (n_tiles - 1));
+        }
+      }
+    }
+    if (issuer) ptx::bulk_wait_group<0>();
+  }
+
+  // the peer must not exit (nor free TMEM) while the leader's MMAs still read its shared memory / write its TMEM
+  ptx::tc_fence_before_sync();
+  __syncwarp();
+  ptx::cluster_arrive();
+  ptx::cluster_wait();
+  if (threadIdx.x == 0) pc_stamp(cp, 61);
+  if (warp == 1) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc_pair(tmem_acc, 2 * PC_BLOCK_N);
+  }
+}
+
+
+} // namespace
+
+// ---- pair-per-chain launch ---------------------------------------------------------------------------------------------
+namespace {
+bool chain_pair_supported(const KernelDesc *const *descs, const GemmArgs *args, int L) {
+  const KernelDesc &d0 = *descs[0];
+  if ((d0.m % PC_ROWS) != 0 || d0.m > (1 << 30)) return false;
+  for (int l = 0; l < L; ++l) {
+    const KernelDesc &d = *descs[l];
+    if ((d.n % PC_BLOCK_N) != 0 || d.n > PC_MAX_TILES * PC_BLOCK_N) return false;
+    if ((d.k % BLOCK_K) != 0 || args[l].batch < 1 || (d.ldc % 8) != 0) return false;
+    if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && args[l].D == nullptr) return false;
+    if (d.op == OpClass::FusedBrgemm && d.unary_kind != 0 && d.unary_kind != 5) return false;
+    if (args[l].D && !aligned16(args[l].D)) return false;   // the epilogue reads the bias in 16-byte words
+  }
+  return true;
+}
+}  // namespace
+
+
+// Launch a prefix of chains [0, num_chains) as ONE launch of mlp_chain_pair_kernel: every chain is cut into blocks of
+// 256 batch rows, every block is a work item of one CTA pair. Taken only when the launch carries enough items to
+// occupy a useful share of the 74 pairs (a single pair needs ~50 us for a 3 x 1024^2 chain; the pass kernels above
+// finish a lone chain in ~11 us). Returns the number of chains launched (0: not applicable).
+int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *args, const int *first, const int *len,
+                              int num_chains, cudaStream_t stream) {
+  static const int min_items = [] {
+    const char *e = getenv("TPP_XSMM_CHAIN_PAIR_MIN");   // 0 disables the kernel
+    return e ? atoi(e) : 12;
+  }();
+  if (min_items <= 0 || num_chains < 1) return 0;
+  int take = 0;
+  int64_t items = 0, layers = 0;
+  {
+    std::vector<ByteRange> in_all, out_all;
+    while (take < num_chains) {
+      const int c = take;
+      if (!chain_pair_supported(descs + first[c], args + first[c], len[c])) break;
+      std::vector<ByteRange> in, out;
+      chain_ranges(descs + first[c], args + first[c], len[c], in, out);
+      bool indep = true;
+      for (const ByteRange &o : out) {
+        for (const ByteRange &x : in_all) indep = indep && !overlaps(o, x);
+        for (const ByteRange &x : out_all) indep = indep && !overlaps(o, x);
+      }
+      for (const ByteRange &i : in)
+        for (const ByteRange &x : out_all) indep = indep && !overlaps(i, x);
+      if (!indep) break;
+      in_all.insert(in_all.end(), in.begin(), in.end());
+      out_all.insert(out_all.end(), out.begin(), out.end());
+      items += descs[first[c]]->m / PC_ROWS;
+      layers += len[c];
+      ++take;
+    }
+  }
+  if (take == 0 || items < min_items) return 0;
+  std::vector<PcLayer> hl((size_t)layers);
+  std::vector<PcItem> hi((size_t)items);
+  size_t nl = 0, ni = 0;
+  for (int c = 0; c < take; ++c) {
+    const int32_t layer0 = (int32_t)nl;
+    for (int l = 0; l < len[c]; ++l) {
+      const KernelDesc &d = *descs[first[c] + l];
+      const GemmArgs &g = args[first[c] + l];
+      PcLayer &pl = hl[nl++];
+      memset(&pl, 0, sizeof(pl));
+      const uint64_t nb = (uint64_t)g.batch;
+      if (!encode_map(&pl.tmX, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, BLOCK_K,
+                      BLOCK_M) ||
+          !encode_map(&pl.tmW, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, 64, BLOCK_K) ||
+          !encode_map(&pl.tmC, g.C, (uint64_t)d.n, (uint64_t)d.m, 1, (uint64_t)d.ldc, 0, PC_OUT_COLS, BLOCK_M))
+        return 0;
+      pl.C = g.C;
+      pl.D = (d.op == OpClass::FusedBrgemm && g.D && d.binary_kind == 1) ? g.D : nullptr;
+      pl.ldc = d.ldc;
+      pl.k_iters = (int32_t)(d.k / BLOCK_K);
+      pl.total_iters = (int32_t)(g.batch * (d.k / BLOCK_K));
+      pl.n_tiles = (int32_t)(d.n / PC_BLOCK_N);
+      pl.n = (int32_t)d.n;
+      pl.relu = (d.op == OpClass::FusedBrgemm && d.unary_kind == 5) ? 1 : 0;
+    }
+    for (int64_t r = 0; r < descs[first[c]]->m; r += PC_ROWS) {
+      PcItem &pi = hi[ni++];
+      pi.layer0 = layer0;
+      pi.num_layers = len[c];
+      pi.row0 = (int32_t)r;
+      pi.pad = 0;
+    }
+  }
+  // the table is written now (not captured): a graph replay only launches the kernel that reads it
+  const size_t lbytes = hl.size() * sizeof(PcLayer), ibytes = (hi.size() * sizeof(PcItem) + 127) & ~(size_t)127;
+  char *table = nullptr;
+  TPP_CUDA_CHECK(cudaMalloc(&table, lbytes + ibytes));
+  TPP_CUDA_CHECK(cudaMemcpyAsync(table, hl.data(), lbytes, cudaMemcpyHostToDevice, table_stream()));
+  TPP_CUDA_CHECK(cudaMemcpyAsync(table + lbytes, hi.data(), hi.size() * sizeof(PcItem), cudaMemcpyHostToDevice, table_stream()));
+  TPP_CUDA_CHECK(cudaStreamSynchronize(table_stream()));
+  capture_adopt(table);
+  PcParams cp;
+  cp.layers = reinterpret_cast<const PcLayer *>(table);
+  cp.items = reinterpret_cast<const PcItem *>(table + lbytes);
+  cp.num_items = (int32_t)items;
+  static const bool hints_on = [] { const char *e = getenv("TPP_XSMM_CHAIN_PAIR_HINTS"); return !(e && e[0] == '0'); }();
+  cp.l2_hints = hints_on ? 1 : 0;
+  static const bool prefetch_on = [] { const char *e = getenv("TPP_XSMM_CHAIN_PAIR_PREFETCH"); return e && e[0] == '1'; }();
+  cp.prefetch_w = prefetch_on ? 1 : 0;
+  cp.trace = nullptr;
+  static const bool pc_trace_on = [] { const char *e = getenv("TPP_XSMM_TC_TRACE"); return e && atoi(e) == 4; }();
+  if (pc_trace_on) {
+    if (!g_pc_trace) {
+      TPP_CUDA_CHECK(cudaMalloc(&g_pc_trace, sizeof(unsigned long long) * 2 * 148 * PC_TRACE_SLOTS));
+      TPP_CUDA_CHECK(cudaMemset(g_pc_trace, 0, sizeof(unsigned long long) * 2 * 148 * PC_TRACE_SLOTS));
+    }
+    cp.trace = g_pc_trace;
+  }
+  static const int max_pairs = [] {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char *e = getenv("TPP_XSMM_CHAIN_PAIRS");
+    const int p = e ? atoi(e) : sms / 2;
+    return p < 1 ? 1 : p;
+  }();
+  // balanced: the fewest pairs that still need the minimal number of rounds
+  const int rounds = (int)((items + max_pairs - 1) / max_pairs);
+  const int pairs = (int)((items + rounds - 1) / rounds);
+  static std::once_flag once;
+  std::call_once(once, [] {
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM));
+  });
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  g_pc_trace_ctas = 2 * pairs;
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = PC_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = 2;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_pair_kernel, cp));
+  set_last_name("mlp_chain_bf16_%dx%dlayers_pair256x256", (int)items, len[0]);
+  return take;
+}
+
+
+} // namespace tpp
