@@ -417,6 +417,135 @@ def test_mlp_replay_blocked_layouts(tiles, vnni):
     assert_close(BF16, got, ref)
 
 
+def _blocked_mlp(tiles, vnni, batch=256, layers=(1024, 1024, 1024), seed=123, n_sets=1):
+    """n_sets operand sets of a block-packed MLP (mlir-gen layouts) on the GPU plus the oracle's
+    answer for each; returns (cfg, replay objects, expected outputs)."""
+    import torch
+
+    from tpp_mlir_b200 import harness
+
+    bn, bk, bc = tiles
+    cfg = harness.MlpConfig(batch=batch, layers=layers, tiles=tiles, vnni=vnni)
+    gen = oracle.TensorInit("normal", BF16, seed)
+
+    def t(a):
+        return torch.from_numpy(a.view(np.int16))
+
+    replays, wants = [], []
+    for _ in range(n_sets):
+        Ws = [gen.fill(c, k) for c, k in zip(layers[:-1], layers[1:])]
+        bs = [gen.fill(k) for k in layers[1:]]
+        x = gen.fill(batch, layers[0])
+        wp = [harness.pack_weight(t(W), bk, bc) for W in Ws]
+        if vnni:
+            wp = [harness.vnni_pack_weight(w) for w in wp]
+        acts = [harness.pack_activation(t(x), bn, bc).cuda()] + [torch.zeros(batch * k, dtype=torch.int16).cuda()
+                                                                   for k in layers[1:]]
+        replays.append(harness.MlpReplay(cfg, [w.cuda() for w in wp], [t(b).cuda() for b in bs], acts))
+        ref = x
+        for W, b in zip(Ws, bs):
+            y = np.zeros((batch, W.shape[1]), np.uint16)
+            oracle.fused_brgemm(BF16, batch, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4, 0, 5, 4,
+                                1, ref, W, y, b, 1)
+            ref = y
+        wants.append(ref)
+    return cfg, replays, wants
+
+
+def _blocked_out(cfg, replay):
+    from tpp_mlir_b200 import harness
+
+    bn, bk, _ = cfg.tiles
+    return harness.unpack_activation(replay.acts[-1].reshape(cfg.batch // bn, cfg.layers[-1] // bk, bn, bk)).cpu().numpy().view(
+        np.uint16)
+
+
+@pytest.mark.parametrize("tiles", [(32, 32, 32), (64, 64, 64), (32, 64, 64), (128, 128, 128), (256, 64, 64), (64, 256, 256)])
+@pytest.mark.parametrize("vnni", [False, True])
+def test_captured_tile_invokes_are_regrouped_onto_the_pair_kernel(tiles, vnni):
+    """The reference's DEFAULT call stream (benchmarks/config/omp/mlir-bf16.json:37: --tiles=32,32,32 --vnni=2; one small
+    BRGEMM per (iN, iK) output block on block-packed operands) captured into a graph must not run as one launch per
+    tile: the runtime folds the invokes of a layer back into one work item and the whole chain runs as ONE launch of
+    the pair-per-chain kernel (4-D tensor maps over the blocked operands, VNNI-2 weights converted in the kernel)."""
+    from tpp_mlir_b200 import xsmm
+
+    cfg, (r,), (want,) = _blocked_mlp(tiles, vnni)
+    n0 = xsmm.launch_count()
+    with xsmm.graph_capture() as g:
+        r.forward()
+    name = xsmm.last_kernel()
+    assert "pair256x256" in name and "_blocked" in name, name
+    assert ("_vnni2" in name) == vnni, name
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == 1, "one kernel for the whole forward pass"
+    assert_close(BF16, _blocked_out(cfg, r), want)
+    # replays are bit-identical
+    first = _blocked_out(cfg, r).copy()
+    r.acts[-1].zero_()
+    g.launch()
+    xsmm.sync()
+    assert (_blocked_out(cfg, r) == first).all()
+    g.destroy()
+
+
+@pytest.mark.parametrize("vnni", [False, True])
+def test_reference_default_stream_many_sets_one_launch(vnni):
+    """14 operand sets of the --tiles=32,32,32 stream (3 layers each, 768 invokes per set) captured in one graph: one
+    launch, every set checked against the oracle."""
+    from tpp_mlir_b200 import xsmm
+
+    cfg, replays, wants = _blocked_mlp((32, 32, 32), vnni, layers=(1024, 1024, 1024, 1024), n_sets=14)
+    n0 = xsmm.launch_count()
+    with xsmm.graph_capture() as g:
+        for r in replays:
+            r.forward()
+    name = xsmm.last_kernel()
+    assert name.startswith("mlp_chain_bf16_14x3layers_pair256x256_blocked"), name
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == 1
+    for r, want in zip(replays, wants):
+        assert_close(BF16, _blocked_out(cfg, r), want)
+    g.destroy()
+
+
+def test_regrouping_keeps_irregular_invoke_streams_as_they_are():
+    """Tile invokes that do NOT walk a regular grid (here: the column blocks of a layer visited in a shuffled order) are
+    launched one by one, in program order - same answer, no fused kernel."""
+    import torch
+
+    from tpp_mlir_b200 import harness, xsmm
+
+    cfg, (r,), (want,) = _blocked_mlp((64, 64, 64), False, layers=(256, 256))
+    bn, bk, bc = cfg.tiles
+    order = [(i, j) for i in range(cfg.batch // bn) for j in (2, 0, 3, 1)]
+    with xsmm.graph_capture() as g:
+        for i_n, i_k in order:
+            xsmm.fused_brgemm_invoke(cfg.dtype, r.handles[0], r.acts[0], i_n * (256 // bc) * bn * bc, r.weights[0],
+                                     i_k * (256 // bc) * bc * bk, r.acts[1], (i_n * (256 // bk) + i_k) * bn * bk, r.biases[0],
+                                     i_k * bk, 256 // bc)
+    assert "pair" not in xsmm.last_kernel(), xsmm.last_kernel()
+    g.launch()
+    xsmm.sync()
+    assert_close(BF16, _blocked_out(cfg, r), want)
+    g.destroy()
+
+
+def test_single_blocked_layer_runs_on_the_pair_kernel():
+    """One layer (no chain) as a grid of tile invokes under capture: still one tensor-core launch."""
+    from tpp_mlir_b200 import xsmm
+
+    cfg, (r,), (want,) = _blocked_mlp((32, 32, 32), True, layers=(512, 768))
+    with xsmm.graph_capture() as g:
+        r.forward()
+    assert "pair256x256_blocked_vnni2" in xsmm.last_kernel(), xsmm.last_kernel()
+    g.launch()
+    xsmm.sync()
+    assert_close(BF16, _blocked_out(cfg, r), want)
+    g.destroy()
+
+
 def test_perf_timer_includes_async_launches():
     import torch
 

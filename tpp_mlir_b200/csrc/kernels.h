@@ -61,6 +61,13 @@ struct GemmArgs {
   // in plain stream order waits for EVERYTHING before it, so at most one window of kernels can ever be co-resident and
   // the "not written by the last kPdlWindow kernels" test behind b_independent / a_independent is a proof, not a hope
   bool pdl = true;
+  // A LAYER regrouped from the invokes recorded during graph capture: grid_n x grid_k invokes of ONE descriptor, tile
+  // (i, j) being the invoke on A + i a_step, B + j b_step, C + i c_step_n + j c_step_k, D + j d_step (steps in elements).
+  // This is what the reference's tiled loop nest emits per layer (block-packed operands, one
+  // BRGEMM per (iN, iK) output block); 1 x 1 is a plain invoke. Only the pair-per-chain kernel takes grids.
+  int32_t grid_n = 1, grid_k = 1;
+  int64_t a_step = 0, b_step = 0, c_step_n = 0, c_step_k = 0, d_step = 0;
+  bool is_grid() const { return grid_n != 1 || grid_k != 1; }
 };
 constexpr int kPdlWindow = 32;
 
@@ -75,6 +82,7 @@ void brgemm_tc_configure(KernelDesc &d);
 bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t stream);
 // L consecutive layers (C of one is A of the next) in one persistent kernel: see brgemm_tc.cu
 bool brgemm_chain_linked(const KernelDesc *const *descs, const GemmArgs *args, int L);      // the layers form a chain
+bool brgemm_layer_chainable(const KernelDesc &d, const GemmArgs &g);   // a layer a chain kernel could take (bf16, beta_0, ...)
 bool brgemm_chain_supported(const KernelDesc *const *descs, const GemmArgs *args, int L);   // ... the pass kernels can run
 bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, int L, cudaStream_t stream);
 // several chains (chain c = layers [first[c], first[c] + len[c]), each accepted by brgemm_chain_supported) as ONE launch
@@ -84,8 +92,10 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
                             int num_chains, cudaStream_t stream);
 // same contract, for launches that carry many independent chains: one CTA pair (cta_group::2, 256 x 256 tiles) walks a
 // whole chain for a block of 256 batch rows; taken when the prefix has at least TPP_XSMM_CHAIN_PAIR_MIN (12) such blocks
+// `force`: take the prefix whatever its size (layers that are grids of small tile invokes or have VNNI-2 weights have no
+// other tensor-core kernel: the alternative is one launch per tile)
 int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *args, const int *first, const int *len,
-                              int num_chains, cudaStream_t stream);
+                              int num_chains, cudaStream_t stream, bool force = false);
 // device tables allocated by chain launches since the last call (owned by the graph being captured)
 void brgemm_tc_take_capture_allocs(std::vector<void *> &out);
 const char *brgemm_tc_last_name();   // tile configuration of this thread's last tcgen05 launch

@@ -187,26 +187,55 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_kernel(const __grid_
 
 // ---- fused chain launch -------------------------------------------------------------------------------------
 
-// True if layers[0..L) can run in mlp_chain_kernel: every layer is a bf16 tensor-core BRGEMM with beta_0, the same
-// m and n, exactly 4 x CHAIN_IPC (batch x k-block) iterations, and layer l+1 reads layer l's C as its A.
-// Kernel-independent part: layers[0..L) form a chain - every layer a bf16 tensor-core BRGEMM with beta_0 on the same m
-// rows, layer l+1 reads exactly layer l's C as its A, no weight / bias / output buffer is written inside the chain.
-// Each chain kernel adds its own shape constraints on top (brgemm_chain_supported, chain_ft_supported,
-// chain_pair_supported); a linked chain that no kernel takes is launched layer by layer.
+// A layer a chain kernel could take: bf16 BRGEMM with beta_0 whose operands TMA can address (the flat descriptor, or a
+// VNNI-2 B descriptor whose flat twin is tensor-core eligible), bias add (bcast_col) / ReLU or no epilogue.
+bool brgemm_layer_chainable(const KernelDesc &d, const GemmArgs &g) {
+  if (d.dtype != kBF16 || !(d.gemm_flags & 4)) return false;
+  if (d.impl != KernelImpl::BrgemmTC && d.flat_twin == nullptr) return false;
+  if (g.batch < 1) return false;
+  if (!aligned16(g.A) || !aligned16(g.B) || !aligned16(g.C) || (d.ldc % 8) != 0) return false;
+  if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && !(d.binary_kind == 1 && (d.binary_flags & 4))) return false;
+  if (d.op == OpClass::FusedBrgemm && d.unary_kind != 0 && d.unary_kind != 5) return false;
+  return true;
+}
+
+namespace {
+// Address (in elements, relative to the operand base) of column `col` of a layer's OUTPUT row 0 ...
+inline int64_t out_col_addr(const KernelDesc &d, const GemmArgs &g, int64_t col) {
+  return (col / d.n) * g.c_step_k + (col % d.n);
+}
+// ... and of reduction index `kcol` of a layer's INPUT row 0 (batch element kcol / k, column kcol % k)
+inline int64_t in_col_addr(const KernelDesc &d, int64_t kcol) { return (kcol / d.k) * d.stride_a + (kcol % d.k); }
+}  // namespace
+
+// Kernel-independent part: layers[0..L) form a chain - every layer a chainable bf16 BRGEMM on the same rows, layer l+1
+// reads exactly layer l's output as its input (same base, same row structure, and every column of C(l) is the
+// reduction index of A(l+1) that lives at the same address - true for the flat link "batch element b = columns
+// [b k, b k + k)" and for the block-packed link "batch element b = output block b"), no weight /
+// bias / output buffer is written inside the chain. Each chain kernel adds its own shape constraints on top
+// (brgemm_chain_supported, chain_ft_supported, chain_pair_supported); a linked chain that no kernel takes is launched
+// layer by layer.
 bool brgemm_chain_linked(const KernelDesc *const *descs, const GemmArgs *args, int L) {
   static const bool off = [] { const char *e = getenv("TPP_XSMM_CHAIN"); return e && e[0] == '0'; }();
   if (off || L < 2 || L > CHAIN_MAX_LAYERS) return false;
   const KernelDesc &d0 = *descs[0];
   for (int l = 0; l < L; ++l) {
     const KernelDesc &d = *descs[l];
-    if (d.impl != KernelImpl::BrgemmTC || !(d.gemm_flags & 4) || d.m != d0.m) return false;
-    if ((d.k % BLOCK_K) != 0 || args[l].batch < 1) return false;
-    if (!aligned16(args[l].A) || !aligned16(args[l].B) || !aligned16(args[l].C) || (d.ldc % 8) != 0) return false;
-    if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && !(d.binary_kind == 1 && (d.binary_flags & 4))) return false;
+    const GemmArgs &g = args[l];
+    if (!brgemm_layer_chainable(d, g) || d.m != d0.m || g.grid_n != args[0].grid_n) return false;
+    if (((g.batch * d.k) % BLOCK_K) != 0) return false;
     if (l > 0) {
-      if (args[l].A != args[l - 1].C || d.lda != descs[l - 1]->ldc) return false;
-      if (args[l].batch * d.k != descs[l - 1]->n) return false;
-      if (args[l].batch > 1 && d.stride_a != d.k) return false;   // batch element b = columns [b k, b k + k) of C(l-1)
+      const KernelDesc &p = *descs[l - 1];
+      const GemmArgs &pg = args[l - 1];
+      if (g.A != pg.C || d.lda != p.ldc) return false;
+      if (g.grid_n > 1 && g.a_step != pg.c_step_n) return false;          // same row blocks
+      const int64_t n_total = (int64_t)pg.grid_k * p.n;
+      if (g.batch * d.k != n_total) return false;
+      // column c of C(l-1) must be reduction index c of A(l): compare the two address maps block by block
+      const int64_t step = p.n < d.k ? p.n : d.k;
+      if ((p.n % step) != 0 || (d.k % step) != 0) return false;
+      for (int64_t c = 0; c < n_total; c += step)
+        if (out_col_addr(p, pg, c) != in_col_addr(d, c)) return false;
     }
   }
   return chain_operands_hazard_free(descs, args, L);
@@ -221,6 +250,7 @@ bool brgemm_chain_supported(const KernelDesc *const *descs, const GemmArgs *args
   for (int l = 0; l < L; ++l) {
     const KernelDesc &d = *descs[l];
     if (d.impl != KernelImpl::BrgemmTC || !(d.gemm_flags & 4) || d.m != d0.m || d.n != d0.n) return false;
+    if (args[l].is_grid()) return false;   // the pass kernels address flat operands only
     const int64_t k_iters = (d.k + BLOCK_K - 1) / BLOCK_K;
     if ((d.k % BLOCK_K) != 0 || args[l].batch * k_iters != 4 * CHAIN_IPC) return false;
     if (!aligned16(args[l].A) || !aligned16(args[l].B) || !aligned16(args[l].C) || (d.ldc % 8) != 0) return false;

@@ -43,19 +43,33 @@ constexpr int PC_MAX_TILES = 16;                      // output tiles per layer 
 constexpr int PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 2 * PC_OUT_BYTES + 2 * PC_BIAS_BYTES +
                         (2 * PC_STAGES + 4 + PC_MAX_TILES) * 8 + 16 + 1024;
 
+// Operand addressing. A layer is a grid of tile BRGEMMs on block-packed operands (GemmArgs::grid_*; 1 x 1 with
+// m = 256 r, k = K is the flat case): all three operands are described by 4-D tensor maps whose box gathers one
+// 128-byte swizzle row from several blocks -
+//   X (k in block | batch element | row in block | row block): box (min(k,64), 64/min(k,64), min(m,128), 128/min(m,128))
+//   W (n in block | column block | k in block | batch element): box (min(n,64), 64/min(n,64), min(k,64), 64/min(k,64))
+//   C (n in block | column block | row in block | row block):   box (min(n,64), 64/min(n,64), min(m,128), 128/min(m,128))
+// so shared memory always receives the canonical K-major (X) / MN-major (W) SWIZZLE_128B tiles the MMA descriptors
+// expect, whatever the tiling of the caller. VNNI-2 weights ([k/2][n][2], the reference's default bf16 layout) are not
+// a canonical UMMA layout and TMA cannot de-interleave 2-byte elements: in the <VNNI = true> instantiation eight
+// converter warps per CTA fetch the weight rows with 16-byte global loads, split the k pairs in registers
+// (2 x LDG.128 -> 8 PRMT -> 2 x STS.128) and write the swizzled tile themselves - no extra pass through HBM, no extra
+// shared-memory traffic; they arrive on the same "full" barrier the activations' TMA bytes are counted on.
 struct alignas(128) PcLayer {
-  CUtensorMap tmX;          // activations: (k, row, batch element), box 64 x 128
-  CUtensorMap tmW;          // weights: (n, k, batch element), box 64 x 64
-  CUtensorMap tmC;          // output: (n, row, 1), box 64 x 128 (TMA store from the swizzled staging buffer)
-  void *C;
+  CUtensorMap tmX;          // activations, box = 64 k x 128 rows
+  CUtensorMap tmW;          // flat weights, box = 64 n x 64 k (unused for VNNI-2 weights)
+  CUtensorMap tmC;          // output, box = 64 n x 128 rows (TMA store from the swizzled staging buffer)
   const void *D;            // bias vector or nullptr
-  int64_t ldc;
-  int32_t k_iters;          // k-blocks per batch element
-  int32_t total_iters;      // batch x k_iters
-  int32_t n_tiles;          // n / 256
-  int32_t n;
+  const void *W;            // VNNI-2 weights: base pointer for the converter warps
+  int64_t w_col_step;       // VNNI-2: elements between column blocks (b_step)
+  int64_t w_batch_step;     // VNNI-2: elements between batch elements (stride_b)
+  int64_t w_ldb;            // VNNI-2: leading dimension in k pairs (elements / 2 per k-pair row = ldb)
+  int32_t m, n, k;          // the tile BRGEMM: rows per row block, columns per column block, k per batch element
+  int32_t k_bstep;          // batch elements per 64-wide k-block (k < 64), else 1
+  int32_t total_iters;      // k-blocks of the whole reduction (batch x k / 64)
+  int32_t n_tiles;          // output columns / 256
   int32_t relu;
-  int32_t pad[3];
+  int32_t vnni;
 };
 struct PcItem {
   int32_t layer0, num_layers, row0, pad;
@@ -64,10 +78,12 @@ struct PcParams {
   const PcLayer *layers;
   const PcItem *items;
   int32_t num_items;
-  int32_t prefetch_w;          // L2 prefetch of the next tile's weight boxes (TPP_XSMM_CHAIN_PAIR_PREFETCH=1)
   int32_t l2_hints;            // L2 eviction-priority hints on the TMA loads / stores (TPP_XSMM_CHAIN_PAIR_HINTS=0: off)
   unsigned long long *trace;   // TPP_XSMM_TC_TRACE=4: clock stamps of each CTA's first item (nullptr in normal runs)
 };
+constexpr int PC_CONV_GROUPS = 2;                     // converter warp groups (VNNI): group g takes k-blocks q % 2 == g
+constexpr int PC_CONV_WARPS = 4;                      // warps per group: 128 threads x 4 units of 32 bytes = 16 KiB
+constexpr int PC_THREADS_VNNI = NUM_THREADS + 32 * PC_CONV_GROUPS * PC_CONV_WARPS;   // 448
 __device__ __forceinline__ void pc_stamp(const PcParams &cp, int slot) {
   if (cp.trace) cp.trace[(size_t)blockIdx.x * PC_TRACE_SLOTS + slot] = clock64();
 }
@@ -77,7 +93,8 @@ __device__ __forceinline__ void tensormap_acquire(const void *map) {
   asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const PcParams cp) {
+template <bool VNNI>
+__global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_chain_pair_kernel(const PcParams cp) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_a = smem_base;                                       // PC_STAGES x 16 KiB
@@ -100,7 +117,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < PC_STAGES; ++s) {
-      ptx::mbar_init(full_bar + 8 * s, 1);
+      // VNNI: besides the producer's expect_tx arrival, the converter warps of BOTH CTAs arrive once their half of the
+      // weight tile is in place (one group of PC_CONV_WARPS warps per CTA handles a given k-block)
+      ptx::mbar_init(full_bar + 8 * s, VNNI ? 1 + 2 * PC_CONV_WARPS : 1);
       ptx::mbar_init(empty_bar + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -134,7 +153,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
       // activations are re-read once per output tile -> evict_last until the layer's last tile, whose read demotes them
       const uint64_t pol_first = ptx::l2_policy_evict_first(), pol_last = ptx::l2_policy_evict_last();
       const bool hints = cp.l2_hints != 0;
-      const bool prefetch_w = cp.prefetch_w != 0;
       int s = 0;
       uint32_t ph = 0, done_ph = 0;                   // done_ph bit j: parity of tile_done[j]'s next phase
       for (int item = pair; item < cp.num_items; item += num_pairs) {
@@ -143,32 +161,38 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
         for (int l = 0; l < it.num_layers; ++l) {
           const PcLayer *L = cp.layers + it.layer0 + l;
           tensormap_acquire(&L->tmX);
-          tensormap_acquire(&L->tmW);
-          const int32_t k_iters = L->k_iters, total = L->total_iters, n_tiles = L->n_tiles;
+          if (!VNNI) tensormap_acquire(&L->tmW);
+          const int32_t total = L->total_iters, n_tiles = L->n_tiles;
+          const int32_t lk = L->k, k_bstep = L->k_bstep, ln = L->n;
+          // my 128 rows: inside one row block (m >= 128) or 128 / m whole row blocks
+          const int32_t xr = L->m >= BLOCK_M ? row0 % L->m : 0, xi = row0 / L->m;
           int32_t ready = 0;                          // output tiles of layer l - 1 (my rows) known to be stored
           for (int32_t j = 0; j < n_tiles; ++j) {
             const int32_t wcol = j * PC_BLOCK_N + (int32_t)peer * PC_HALF_N;
+            int32_t wn[PC_W_CHUNKS], wj[PC_W_CHUNKS];   // my weight columns: (column in block, column block) per 64-column box
+#pragma unroll
+            for (int c = 0; c < PC_W_CHUNKS; ++c) {
+              const int32_t col = wcol + c * 64;
+              wn[c] = ln >= 64 ? col % ln : 0;
+              wj[c] = col / ln;
+            }
             const uint64_t pol_x = (j + 1 < n_tiles) ? pol_last : pol_first;
-            int32_t b = 0, kb = 0;
+            int32_t c0 = 0, c1 = 0;                   // k within the batch element, batch element of this k-block
             for (int32_t i = 0; i < total; ++i) {
               ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
-              if (peer == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2 * PC_STAGE_BYTES);   // both CTAs' bytes
-              // the weights depend on nothing: their boxes go out before any wait for the previous layer
+              // both CTAs' bytes: activations, plus the weights unless the converter warps deliver them
+              if (peer == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, VNNI ? 2 * A_STAGE_BYTES : 2 * PC_STAGE_BYTES);
+              if (!VNNI) {
+                // the weights depend on nothing: their boxes go out before any wait for the previous layer
 #pragma unroll
-              for (int c = 0; c < PC_W_CHUNKS; ++c) {
-                if (hints)
-                  ptx::tma_load_3d_pair_hint(smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES, &L->tmW, leader_full + 8 * s,
-                                             wcol + c * 64, kb * BLOCK_K, b, pol_first);
-                else
-                  ptx::tma_load_3d_pair(smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES, &L->tmW, leader_full + 8 * s,
-                                        wcol + c * 64, kb * BLOCK_K, b);
-              }
-              if (prefetch_w && (j & 1) == 0 && j + 1 < n_tiles) {
-                // the same k-rows of the NEXT tile's weight columns go to L2 now: DRAM sees runs of 1 KiB per row
-                // (this pair's two tiles) instead of 512 B, and the odd tiles' weight loads hit L2
-#pragma unroll
-                for (int c = 0; c < PC_W_CHUNKS; ++c)
-                  ptx::tma_prefetch_3d(&L->tmW, wcol + PC_BLOCK_N + c * 64, kb * BLOCK_K, b);
+                for (int c = 0; c < PC_W_CHUNKS; ++c) {
+                  if (hints)
+                    ptx::tma_load_4d_pair_hint(smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES, &L->tmW, leader_full + 8 * s,
+                                               wn[c], wj[c], c0, c1, pol_first);
+                  else
+                    ptx::tma_load_4d_pair(smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES, &L->tmW, leader_full + 8 * s,
+                                          wn[c], wj[c], c0, c1);
+                }
               }
               if (l > 0 && j == 0) {
                 // reduction step i reads columns [64 i, 64 i + 64) of the previous layer's output = its tile i / 4:
@@ -185,11 +209,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
                 }
               }
               if (hints)
-                ptx::tma_load_3d_pair_hint(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, kb * BLOCK_K, row0, b,
-                                           pol_x);
+                ptx::tma_load_4d_pair_hint(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, c0, c1, xr, xi, pol_x);
               else
-                ptx::tma_load_3d_pair(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, kb * BLOCK_K, row0, b);
-              if (++kb == k_iters) { kb = 0; ++b; }
+                ptx::tma_load_4d_pair(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, c0, c1, xr, xi);
+              c0 += BLOCK_K;
+              if (c0 >= lk) { c0 = 0; c1 += k_bstep; }
               if (++s == PC_STAGES) { s = 0; ph ^= 1; }
             }
           }
@@ -217,7 +241,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
             const uint32_t acc = tmem_acc + buf * PC_BLOCK_N;
             if (t < 12) pc_stamp(cp, 4 * t);
             for (int32_t i = 0; i < total; ++i) {
-              ptx::mbar_wait(full_bar + 8 * s, ph);
+              if (VNNI) ptx::mbar_wait_cluster(full_bar + 8 * s, ph);   // the peer's converter warps arrive remotely
+              else ptx::mbar_wait(full_bar + 8 * s, ph);
               ptx::tc_fence_after_sync();
               const uint32_t a_addr = smem_a + s * A_STAGE_BYTES;
               const uint32_t b_addr = smem_w + s * PC_W_CHUNKS * B_CHUNK_BYTES;
@@ -236,7 +261,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
         }
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ===== epilogue (both CTAs, each on its own 128 rows / TMEM lanes) =====
     // TMEM lane = row: a thread owns one output row. Its bf16 results go to a 128-byte-swizzled staging buffer
     // (64 columns x 128 rows), which one thread hands to TMA as a store box: full 128-byte lines leave the SM instead of
@@ -270,6 +295,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
       for (int l = 0; l < it.num_layers; ++l) {
         const PcLayer *L = cp.layers + it.layer0 + l;
         if (issuer) tensormap_acquire(&L->tmC);
+        const int32_t ln = L->n;
+        const int32_t xr = L->m >= BLOCK_M ? row0 % L->m : 0, xi = row0 / L->m;   // as in the producer
         const void *Dp = L->D;
         const bool relu = L->relu != 0;
         const int32_t n_tiles = L->n_tiles;
@@ -329,9 +356,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (issuer) {
               // a layer output that the next layer re-reads four times stays in L2; the chain's result does not
-              if (!hints) ptx::tma_store_3d(&L->tmC, sbuf, j * PC_BLOCK_N + c, row0, 0);
-              else ptx::tma_store_3d_hint(&L->tmC, sbuf, j * PC_BLOCK_N + c, row0, 0,
-                                          l + 1 < it.num_layers ? pol_last : pol_first);
+              const int32_t col = j * PC_BLOCK_N + c;
+              const int32_t cn = ln >= 64 ? col % ln : 0, cj = col / ln;
+              if (!hints) ptx::tma_store_4d(&L->tmC, sbuf, cn, cj, xr, xi);
+              else ptx::tma_store_4d_hint(&L->tmC, sbuf, cn, cj, xr, xi, l + 1 < it.num_layers ? pol_last : pol_first);
               ptx::bulk_commit_group();
               if (c == 0 && j > 0 && l + 1 < it.num_layers) {
                 // every store group but the one just committed is complete: tile j - 1 (my rows) is in L2
@@ -353,6 +381,76 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
       }
     }
     if (issuer) ptx::bulk_wait_group<0>();
+  } else if (VNNI) {
+    // ===== VNNI-2 weight converters (both CTAs): global [k/2][n][2] -> registers -> swizzled MN-major tile =====
+    // Group g (PC_CONV_WARPS warps) takes the k-blocks whose running index q is g mod PC_CONV_GROUPS, so that
+    // PC_CONV_GROUPS k-blocks of weight loads are in flight per CTA. Per k-block a group moves this CTA's 128 weight
+    // columns x 64 k = 2 chunks x 32 k-pair rows x 64 columns x 2: thread t handles 16-byte chunk (t & 7) of rows
+    // (t >> 3) and (t >> 3) + 16 of both chunks - four units of 32 contiguous global bytes (8 columns x 2 k).
+    const int cw = warp - 6;
+    const int group = cw / PC_CONV_WARPS;
+    const int ct = (cw % PC_CONV_WARPS) * 32 + lane;  // 0 .. 127 within the group
+    const int g8 = ct & 7, r_lo = ct >> 3;
+    const uint32_t leader_full = ptx::mapa(full_bar, 0);
+    const uint64_t pol_first = ptx::l2_policy_evict_first();
+    uint32_t q = 0;                                   // running k-block index of this CTA (all items / layers / tiles)
+    for (int item = pair; item < cp.num_items; item += num_pairs) {
+      const PcItem it = cp.items[item];
+      for (int l = 0; l < it.num_layers; ++l) {
+        const PcLayer *L = cp.layers + it.layer0 + l;
+        const char *Wb = static_cast<const char *>(L->W);
+        const int32_t ln = L->n, lk = L->k, total = L->total_iters, n_tiles = L->n_tiles;
+        const int64_t col_step = L->w_col_step, batch_step = L->w_batch_step, ldb2 = 2 * L->w_ldb;
+        const int32_t half_k = lk >> 1;               // k-pair rows per batch element
+        for (int32_t j = 0; j < n_tiles; ++j) {
+          int64_t col_off[PC_W_CHUNKS];               // element offset of my 8 columns: column block + column in block
+#pragma unroll
+          for (int c = 0; c < PC_W_CHUNKS; ++c) {
+            const int32_t col = j * PC_BLOCK_N + (int32_t)peer * PC_HALF_N + c * 64 + 8 * g8;
+            col_off[c] = (int64_t)(col / ln) * col_step + (int64_t)(col % ln) * 2;
+          }
+          for (int32_t i = 0; i < total; ++i, ++q) {
+            if ((int)(q % PC_CONV_GROUPS) != group) continue;
+            const uint32_t s = q % PC_STAGES, ph = (q / PC_STAGES) & 1u;
+            uint4 v[2 * PC_W_CHUNKS][2];
+#pragma unroll
+            for (int u = 0; u < 2 * PC_W_CHUNKS; ++u) {
+              const int32_t kpg = i * 32 + r_lo + 16 * (u & 1);          // k-pair row within the whole reduction
+              const int32_t b = kpg / half_k, kp = kpg - b * half_k;
+              const char *src = Wb + 2 * (col_off[u >> 1] + (int64_t)b * batch_step + (int64_t)kp * ldb2);
+              v[u][0] = ptx::ldg_v4_hint(src, pol_first);
+              v[u][1] = ptx::ldg_v4_hint(src + 16, pol_first);
+            }
+            ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
+#pragma unroll
+            for (int u = 0; u < 2 * PC_W_CHUNKS; ++u) {
+              const uint32_t w[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
+              uint32_t lo[4], hi[4];                  // k even / k odd of my 8 columns
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                lo[e] = __byte_perm(w[2 * e], w[2 * e + 1], 0x5410);
+                hi[e] = __byte_perm(w[2 * e], w[2 * e + 1], 0x7632);
+              }
+              const uint32_t r0 = 2u * (uint32_t)(r_lo + 16 * (u & 1));     // k row of the 64 x 64 chunk (128-byte rows)
+              const uint32_t base = smem_w + (s * PC_W_CHUNKS + (u >> 1)) * B_CHUNK_BYTES;
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                           ::"r"(base + r0 * 128u + (((uint32_t)g8 ^ (r0 & 7u)) << 4)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3])
+                           : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                           ::"r"(base + (r0 + 1u) * 128u + (((uint32_t)g8 ^ ((r0 + 1u) & 7u)) << 4)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
+                             "r"(hi[3])
+                           : "memory");
+            }
+            ptx::fence_proxy_async();                 // my shared-memory writes -> the async proxy (the pair's MMAs)
+            __syncwarp();
+            if (lane == 0) {
+              if (peer == 0) ptx::mbar_arrive(full_bar + 8 * s);
+              else ptx::mbar_arrive_remote(leader_full + 8 * s);
+            }
+          }
+        }
+      }
+    }
   }
 
   // the peer must not exit (nor free TMEM) while the leader's MMAs still read its shared memory / write its TMEM
@@ -372,28 +470,97 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_pair_kernel(const Pc
 
 // ---- pair-per-chain launch ---------------------------------------------------------------------------------------------
 namespace {
-bool chain_pair_supported(const KernelDesc *const *descs, const GemmArgs *args, int L) {
+inline bool divides_or_multiple(int64_t v, int64_t unit) { return v > 0 && (v <= unit ? unit % v == 0 : v % unit == 0); }
+
+// Shape rules of the kernel (per layer; a layer is a grid of tile BRGEMMs, GemmArgs::grid_*): whole 256-row work items and
+// 256-column tiles; the tile dimensions must divide (or be multiples of) the box extents 128 rows / 64 k / 64 columns so
+// that one TMA box is a whole number of blocks; every stride TMA sees is a multiple of 16 bytes.
+bool chain_pair_supported(const KernelDesc *const *descs, const GemmArgs *args, int L, bool *vnni_out) {
   const KernelDesc &d0 = *descs[0];
-  if ((d0.m % PC_ROWS) != 0 || d0.m > (1 << 30)) return false;
+  const int64_t rows = (int64_t)args[0].grid_n * d0.m;
+  if ((rows % PC_ROWS) != 0 || rows > (1 << 30)) return false;
+  const bool vnni = (d0.gemm_flags & 2048) != 0;
   for (int l = 0; l < L; ++l) {
     const KernelDesc &d = *descs[l];
-    if ((d.n % PC_BLOCK_N) != 0 || d.n > PC_MAX_TILES * PC_BLOCK_N) return false;
-    if ((d.k % BLOCK_K) != 0 || args[l].batch < 1 || (d.ldc % 8) != 0) return false;
-    if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && args[l].D == nullptr) return false;
-    if (d.op == OpClass::FusedBrgemm && d.unary_kind != 0 && d.unary_kind != 5) return false;
-    if (args[l].D && !aligned16(args[l].D)) return false;   // the epilogue reads the bias in 16-byte words
+    const GemmArgs &g = args[l];
+    if (!brgemm_layer_chainable(d, g)) return false;
+    if (((d.gemm_flags & 2048) != 0) != vnni) return false;             // one weight layout per launch
+    const int64_t n_total = (int64_t)g.grid_k * d.n, k_total = g.batch * d.k;
+    if ((n_total % PC_BLOCK_N) != 0 || n_total > PC_MAX_TILES * PC_BLOCK_N) return false;
+    if ((k_total % BLOCK_K) != 0 || k_total > (1 << 24)) return false;
+    if (!divides_or_multiple(d.m, BLOCK_M) || !divides_or_multiple(d.k, BLOCK_K) || !divides_or_multiple(d.n, 64)) return false;
+    if (d.k < 8 || d.n < 8) return false;                               // the inner box extent is at least 16 bytes
+    if ((d.lda % 8) != 0 || (d.ldb % 8) != 0 || (d.ldc % 8) != 0) return false;
+    if (g.batch > 1 && (d.stride_a % 8) != 0) return false;
+    if (g.batch > 1 && (d.stride_b % 8) != 0) return false;
+    if (g.grid_n > 1 && ((g.a_step % 8) != 0 || (g.c_step_n % 8) != 0)) return false;
+    if (g.grid_k > 1 && ((g.b_step % 8) != 0 || (g.c_step_k % 8) != 0)) return false;
+    if (d.k < BLOCK_K && g.batch % (BLOCK_K / d.k) != 0) return false;  // a k-block is a whole number of batch elements
+    if (vnni && ((d.k % 2) != 0 || (d.k < BLOCK_K ? false : (d.k % BLOCK_K) != 0))) return false;
+    if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && g.D == nullptr) return false;
+    if (g.D && !aligned16(g.D)) return false;   // the epilogue reads the bias in 16-byte words
+  }
+  *vnni_out = vnni;
+  return true;
+}
+
+// dims / strides / box of the three operand maps (see the comment above PcLayer); sizes in elements
+bool encode_layer_maps(PcLayer &pl, const KernelDesc &d, const GemmArgs &g, bool vnni) {
+  const uint64_t nb = (uint64_t)g.batch, gn = (uint64_t)g.grid_n, gk = (uint64_t)g.grid_k;
+  // a dimension of size 1 may carry any legal stride
+  const uint64_t sa = nb > 1 ? (uint64_t)d.stride_a : (uint64_t)d.lda, sb = nb > 1 ? (uint64_t)d.stride_b : (uint64_t)d.ldb;
+  const uint64_t a_step = gn > 1 ? (uint64_t)g.a_step : (uint64_t)d.lda, cn_step = gn > 1 ? (uint64_t)g.c_step_n : (uint64_t)d.ldc;
+  const uint64_t b_step = gk > 1 ? (uint64_t)g.b_step : (uint64_t)d.ldb, ck_step = gk > 1 ? (uint64_t)g.c_step_k : (uint64_t)d.ldc;
+  const uint32_t kx = (uint32_t)std::min<int64_t>(d.k, BLOCK_K), rx = (uint32_t)std::min<int64_t>(d.m, BLOCK_M),
+                 nx = (uint32_t)std::min<int64_t>(d.n, 64);
+  {
+    const uint64_t dims[4] = {(uint64_t)d.k, nb, (uint64_t)d.m, gn}, str[3] = {sa, (uint64_t)d.lda, a_step};
+    const uint32_t box[4] = {kx, BLOCK_K / kx, rx, BLOCK_M / rx};
+    if (!encode_map_nd(&pl.tmX, g.A, 4, dims, str, box, true)) return false;
+  }
+  if (!vnni) {
+    const uint64_t dims[4] = {(uint64_t)d.n, gk, (uint64_t)d.k, nb}, str[3] = {b_step, (uint64_t)d.ldb, sb};
+    const uint32_t box[4] = {nx, 64 / nx, kx, BLOCK_K / kx};
+    if (!encode_map_nd(&pl.tmW, g.B, 4, dims, str, box, true)) return false;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)d.n, gk, (uint64_t)d.m, gn}, str[3] = {ck_step, (uint64_t)d.ldc, cn_step};
+    const uint32_t box[4] = {nx, PC_OUT_COLS / nx, rx, BLOCK_M / rx};
+    if (!encode_map_nd(&pl.tmC, g.C, 4, dims, str, box, true)) return false;
   }
   return true;
+}
+
+template <bool VNNI> void launch_pair_kernel(const PcParams &cp, int pairs, cudaStream_t stream) {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<VNNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM));
+  });
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(2 * pairs));
+  cfg.blockDim = dim3(VNNI ? PC_THREADS_VNNI : NUM_THREADS);
+  cfg.dynamicSmemBytes = PC_SMEM;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[0].val.programmaticStreamSerializationAllowed = 1;
+  attrs[1].id = cudaLaunchAttributeClusterDimension;
+  attrs[1].val.clusterDim.x = 2;
+  attrs[1].val.clusterDim.y = 1;
+  attrs[1].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 2;
+  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_pair_kernel<VNNI>, cp));
 }
 }  // namespace
 
 
 // Launch a prefix of chains [0, num_chains) as ONE launch of mlp_chain_pair_kernel: every chain is cut into blocks of
-// 256 batch rows, every block is a work item of one CTA pair. Taken only when the launch carries enough items to
-// occupy a useful share of the 74 pairs (a single pair needs ~50 us for a 3 x 1024^2 chain; the pass kernels above
-// finish a lone chain in ~11 us). Returns the number of chains launched (0: not applicable).
+// 256 batch rows, every block is a work item of one CTA pair. Without `force` it is taken only when the launch carries
+// enough items to occupy a useful share of the 74 pairs (a single pair needs ~50 us for a 3 x 1024^2 chain; the pass
+// kernels finish a lone flat chain in ~11 us). Returns the number of chains launched (0: not applicable).
 int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *args, const int *first, const int *len,
-                              int num_chains, cudaStream_t stream) {
+                              int num_chains, cudaStream_t stream, bool force) {
   static const int min_items = [] {
     const char *e = getenv("TPP_XSMM_CHAIN_PAIR_MIN");   // 0 disables the kernel
     return e ? atoi(e) : 12;
@@ -401,11 +568,15 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   if (min_items <= 0 || num_chains < 1) return 0;
   int take = 0;
   int64_t items = 0, layers = 0;
+  bool vnni = false;
   {
     std::vector<ByteRange> in_all, out_all;
     while (take < num_chains) {
       const int c = take;
-      if (!chain_pair_supported(descs + first[c], args + first[c], len[c])) break;
+      bool v = false;
+      if (!chain_pair_supported(descs + first[c], args + first[c], len[c], &v)) break;
+      if (take > 0 && v != vnni) break;   // one instantiation per launch
+      vnni = v;
       std::vector<ByteRange> in, out;
       chain_ranges(descs + first[c], args + first[c], len[c], in, out);
       bool indep = true;
@@ -418,15 +589,16 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
       if (!indep) break;
       in_all.insert(in_all.end(), in.begin(), in.end());
       out_all.insert(out_all.end(), out.begin(), out.end());
-      items += descs[first[c]]->m / PC_ROWS;
+      items += (int64_t)args[first[c]].grid_n * descs[first[c]]->m / PC_ROWS;
       layers += len[c];
       ++take;
     }
   }
-  if (take == 0 || items < min_items) return 0;
+  if (take == 0 || (!force && items < min_items)) return 0;
   std::vector<PcLayer> hl((size_t)layers);
   std::vector<PcItem> hi((size_t)items);
   size_t nl = 0, ni = 0;
+  bool grids = false;
   for (int c = 0; c < take; ++c) {
     const int32_t layer0 = (int32_t)nl;
     for (int l = 0; l < len[c]; ++l) {
@@ -434,22 +606,22 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
       const GemmArgs &g = args[first[c] + l];
       PcLayer &pl = hl[nl++];
       memset(&pl, 0, sizeof(pl));
-      const uint64_t nb = (uint64_t)g.batch;
-      if (!encode_map(&pl.tmX, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, BLOCK_K,
-                      BLOCK_M) ||
-          !encode_map(&pl.tmW, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, 64, BLOCK_K) ||
-          !encode_map(&pl.tmC, g.C, (uint64_t)d.n, (uint64_t)d.m, 1, (uint64_t)d.ldc, 0, PC_OUT_COLS, BLOCK_M))
-        return 0;
-      pl.C = g.C;
+      if (!encode_layer_maps(pl, d, g, vnni)) return 0;
+      grids = grids || g.is_grid();
       pl.D = (d.op == OpClass::FusedBrgemm && g.D && d.binary_kind == 1) ? g.D : nullptr;
-      pl.ldc = d.ldc;
-      pl.k_iters = (int32_t)(d.k / BLOCK_K);
-      pl.total_iters = (int32_t)(g.batch * (d.k / BLOCK_K));
-      pl.n_tiles = (int32_t)(d.n / PC_BLOCK_N);
-      pl.n = (int32_t)d.n;
+      pl.W = g.B;
+      pl.w_col_step = g.grid_k > 1 ? g.b_step : 0;
+      pl.w_batch_step = g.batch > 1 ? d.stride_b : 0;
+      pl.w_ldb = d.ldb;
+      pl.m = (int32_t)d.m; pl.n = (int32_t)d.n; pl.k = (int32_t)d.k;
+      pl.k_bstep = d.k < BLOCK_K ? (int32_t)(BLOCK_K / d.k) : 1;
+      pl.total_iters = (int32_t)(g.batch * d.k / BLOCK_K);
+      pl.n_tiles = (int32_t)((int64_t)g.grid_k * d.n / PC_BLOCK_N);
       pl.relu = (d.op == OpClass::FusedBrgemm && d.unary_kind == 5) ? 1 : 0;
+      pl.vnni = vnni ? 1 : 0;
     }
-    for (int64_t r = 0; r < descs[first[c]]->m; r += PC_ROWS) {
+    const int64_t rows = (int64_t)args[first[c]].grid_n * descs[first[c]]->m;
+    for (int64_t r = 0; r < rows; r += PC_ROWS) {
       PcItem &pi = hi[ni++];
       pi.layer0 = layer0;
       pi.num_layers = len[c];
@@ -471,8 +643,6 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   cp.num_items = (int32_t)items;
   static const bool hints_on = [] { const char *e = getenv("TPP_XSMM_CHAIN_PAIR_HINTS"); return !(e && e[0] == '0'); }();
   cp.l2_hints = hints_on ? 1 : 0;
-  static const bool prefetch_on = [] { const char *e = getenv("TPP_XSMM_CHAIN_PAIR_PREFETCH"); return e && e[0] == '1'; }();
-  cp.prefetch_w = prefetch_on ? 1 : 0;
   cp.trace = nullptr;
   static const bool pc_trace_on = [] { const char *e = getenv("TPP_XSMM_TC_TRACE"); return e && atoi(e) == 4; }();
   if (pc_trace_on) {
@@ -493,27 +663,10 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   // balanced: the fewest pairs that still need the minimal number of rounds
   const int rounds = (int)((items + max_pairs - 1) / max_pairs);
   const int pairs = (int)((items + rounds - 1) / rounds);
-  static std::once_flag once;
-  std::call_once(once, [] {
-    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM));
-  });
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(2 * pairs));
   g_pc_trace_ctas = 2 * pairs;
-  cfg.blockDim = dim3(NUM_THREADS);
-  cfg.dynamicSmemBytes = PC_SMEM;
-  cfg.stream = stream;
-  cudaLaunchAttribute attrs[2];
-  attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attrs[0].val.programmaticStreamSerializationAllowed = 1;
-  attrs[1].id = cudaLaunchAttributeClusterDimension;
-  attrs[1].val.clusterDim.x = 2;
-  attrs[1].val.clusterDim.y = 1;
-  attrs[1].val.clusterDim.z = 1;
-  cfg.attrs = attrs;
-  cfg.numAttrs = 2;
-  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_pair_kernel, cp));
-  set_last_name("mlp_chain_bf16_%dx%dlayers_pair256x256", (int)items, len[0]);
+  if (vnni) launch_pair_kernel<true>(cp, pairs, stream);
+  else launch_pair_kernel<false>(cp, pairs, stream);
+  set_last_name("mlp_chain_bf16_%dx%dlayers_pair256x256%s%s", (int)items, len[0], grids ? "_blocked" : "", vnni ? "_vnni2" : "");
   return take;
 }
 

@@ -161,6 +161,45 @@ __device__ __forceinline__ void tma_store_3d_hint(const void *map, uint32_t smem
                : "memory");
 }
 
+// 4-D variants for block-packed operands ([row block][k block][rows][k] and friends): one box gathers the pieces of
+// a 128-byte swizzle row from several blocks
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t smem_dst, const void *map, uint32_t bar, int32_t c0, int32_t c1,
+                                                 int32_t c2, int32_t c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair_hint(uint32_t smem_dst, const void *map, uint32_t bar, int32_t c0,
+                                                      int32_t c1, int32_t c2, int32_t c3, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint "
+      "[%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const void *map, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2,
+                                             int32_t c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_4d_hint(const void *map, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2,
+                                                  int32_t c3, uint64_t policy) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group.L2::cache_hint [%0, {%2, %3, %4, %5}], [%1], %6;"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "l"(policy)
+               : "memory");
+}
+// 16 bytes from global memory that are read once (weights): no L1 allocation, L2 eviction priority from `policy`
+__device__ __forceinline__ uint4 ldg_v4_hint(const void *p, uint64_t policy) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.b32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(policy));
+  return v;
+}
+
 // TMA store: a swizzled shared-memory box -> global memory, tracked by the issuing thread's bulk async-group
 __device__ __forceinline__ void tma_store_3d(const void *map, uint32_t smem_src, int32_t c0, int32_t c1, int32_t c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"

@@ -457,10 +457,117 @@ void issue_gemm(const KernelDesc *d, const GemmArgs &g, cudaStream_t stream) {
   count_launch();
 }
 
-// Launch the BRGEMMs recorded during graph capture, in order. Runs of 2..4 consecutive layers that form a chain
-// (C of layer l is A of layer l+1, same m / n, tensor-core eligible) go to the persistent fused kernel
-// ("whole-MLP fusion ... or CUDA-graph capture of the invoke sequence"); everything else is
-// launched exactly as a direct invoke would.
+// ---- regrouping of captured tile invokes into layers ------------------------------------------------------------
+// The reference tiles every layer into (iN, iK) output blocks and emits one small BRGEMM per block on block-packed
+// operands (benchmarks/config/omp/mlir-bf16.json:37 runs --tiles=32,32,32: 256 invokes of a
+// 32 x 32 x 32 x batch-32 BRGEMM per layer, scf.parallel over OpenMP threads). One GPU launch per block is hopeless, so
+// runs of recorded invokes that share ONE descriptor and walk a regular grid - A + i a_step, B + j b_step,
+// C + i c_step_n + j c_step_k, D + j d_step - are folded back into one layer-sized work item (GemmArgs::grid_*), which
+// the pair-per-chain kernel addresses through 4-D tensor maps. Anything irregular stays a plain invoke.
+struct Layer {
+  const KernelDesc *d;
+  GemmArgs g;
+  size_t first, count;   // the invokes of `list` this layer was folded from
+};
+
+inline int64_t elem_diff(const void *a, const void *b) {   // (a - b) in bf16 elements
+  return (static_cast<const char *>(a) - static_cast<const char *>(b)) / 2;
+}
+
+// the longest grid that starts at list[i]; returns the number of invokes folded (>= 1)
+size_t fold_grid(const std::vector<PendingGemm> &list, size_t i, Layer *out) {
+  const PendingGemm &p0 = list[i];
+  out->d = p0.d;
+  out->g = p0.g;
+  out->first = i;
+  out->count = 1;
+  static const bool off = [] { const char *e = getenv("TPP_XSMM_REGROUP"); return e && e[0] == '0'; }();
+  if (off || p0.d->dtype != kBF16) return 1;
+  size_t run = 1;   // invokes with the same descriptor / batch count / bias-ness
+  while (i + run < list.size() && run < (1u << 20) && list[i + run].d == p0.d && list[i + run].g.batch == p0.g.batch &&
+         (list[i + run].g.D != nullptr) == (p0.g.D != nullptr))
+    ++run;
+  if (run < 2) return 1;
+  const GemmArgs &g0 = p0.g, &g1 = list[i + 1].g;
+  // the inner loop runs over output-column blocks (same A, next B) or over row blocks (same B, next A)
+  const bool inner_k = g1.A == g0.A && g1.B != g0.B;
+  const bool inner_n = g1.B == g0.B && g1.A != g0.A;
+  if (!inner_k && !inner_n) return 1;
+  size_t inner = 1;
+  while (inner < run && (inner_k ? list[i + inner].g.A == g0.A : list[i + inner].g.B == g0.B)) ++inner;
+  // steps from the first two invokes of the inner loop and the first invoke of the second outer iteration
+  const int64_t in_a = inner_k ? 0 : elem_diff(g1.A, g0.A), in_b = inner_k ? elem_diff(g1.B, g0.B) : 0;
+  const int64_t in_c = elem_diff(g1.C, g0.C), in_d = g0.D ? elem_diff(g1.D, g0.D) : 0;
+  int64_t out_a = 0, out_b = 0, out_c = 0, out_d = 0;
+  size_t outer = 1;
+  if (inner < run) {
+    const GemmArgs &gn = list[i + inner].g;
+    out_a = elem_diff(gn.A, g0.A); out_b = elem_diff(gn.B, g0.B); out_c = elem_diff(gn.C, g0.C);
+    out_d = g0.D ? elem_diff(gn.D, g0.D) : 0;
+    if (inner_k ? (out_b != 0 || out_a == 0) : (out_a != 0 || out_b == 0)) outer = 1;   // second outer iteration is not one
+    else outer = run / inner;
+  }
+  auto matches = [&](size_t o, size_t t) {
+    const GemmArgs &g = list[i + o * inner + t].g;
+    const int64_t io = (int64_t)o, it = (int64_t)t;
+    return elem_diff(g.A, g0.A) == io * out_a + it * in_a && elem_diff(g.B, g0.B) == io * out_b + it * in_b &&
+           elem_diff(g.C, g0.C) == io * out_c + it * in_c && (!g0.D || elem_diff(g.D, g0.D) == io * out_d + it * in_d);
+  };
+  size_t good_outer = 0;
+  for (size_t o = 0; o < outer; ++o) {
+    bool ok = true;
+    for (size_t t = 0; t < inner && ok; ++t) ok = matches(o, t);
+    if (!ok) break;
+    ++good_outer;
+  }
+  if (good_outer == 0) return 1;   // not even the first inner loop is regular
+  GemmArgs g = g0;
+  if (inner_k) {
+    g.grid_k = (int32_t)inner; g.grid_n = (int32_t)good_outer;
+    g.b_step = in_b; g.c_step_k = in_c; g.d_step = in_d;
+    g.a_step = good_outer > 1 ? out_a : 0; g.c_step_n = good_outer > 1 ? out_c : 0;
+  } else {
+    g.grid_n = (int32_t)inner; g.grid_k = (int32_t)good_outer;
+    g.a_step = in_a; g.c_step_n = in_c;
+    g.b_step = good_outer > 1 ? out_b : 0; g.c_step_k = good_outer > 1 ? out_c : 0; g.d_step = good_outer > 1 ? out_d : 0;
+  }
+  // only forward-walking grids whose tiles cannot touch each other or the layer's inputs
+  const KernelDesc &d = *p0.d;
+  const int64_t c_tile = (d.m - 1) * d.ldc + d.n;
+  bool ok = g.a_step >= 0 && g.b_step >= 0 && g.c_step_n >= 0 && g.c_step_k >= 0 && g.d_step >= 0;
+  if (g.grid_k > 1) ok = ok && g.c_step_k >= d.n && (g.c_step_k >= c_tile || d.ldc >= (g.grid_k - 1) * g.c_step_k + d.n);
+  if (g.grid_n > 1) ok = ok && g.c_step_n >= (g.grid_k - 1) * g.c_step_k + c_tile;
+  if (g.grid_k > 1 && g.D) ok = ok && g.d_step == d.n;   // the bias slices of neighbouring column blocks are contiguous
+  if (ok) {
+    const size_t es = 2;
+    (void)es;
+    // bounding ranges: the outputs of the grid must not overlap anything the grid reads
+    const char *c_lo = static_cast<const char *>(g.C);
+    const char *c_hi = c_lo + ((g.grid_n - 1) * g.c_step_n + (g.grid_k - 1) * g.c_step_k + c_tile) * 2;
+    const int64_t nb = g.batch > 0 ? g.batch : 1;
+    const bool vnni = (d.gemm_flags & XSMM_GEMM_FLAG_ROWMAJOR_B_VNNI) != 0;
+    const char *a_lo = static_cast<const char *>(g.A);
+    const char *a_hi = a_lo + ((g.grid_n - 1) * g.a_step + (nb - 1) * d.stride_a + (d.m - 1) * d.lda + d.k) * 2;
+    const char *b_lo = static_cast<const char *>(g.B);
+    const int64_t b_tile = vnni ? (nb - 1) * d.stride_b + ((d.k / 2 - 1) * d.ldb + d.n) * 2
+                                : (nb - 1) * d.stride_b + (d.k - 1) * d.ldb + d.n;
+    const char *b_hi = b_lo + ((g.grid_k - 1) * g.b_step + b_tile) * 2;
+    ok = !(c_lo < a_hi && a_lo < c_hi) && !(c_lo < b_hi && b_lo < c_hi);
+    if (ok && g.D) {
+      const char *d_lo = static_cast<const char *>(g.D), *d_hi = d_lo + ((g.grid_k - 1) * g.d_step + d.n) * 2;
+      ok = !(c_lo < d_hi && d_lo < c_hi);
+    }
+  }
+  if (!ok) return 1;
+  out->g = g;
+  out->count = inner * good_outer;
+  return out->count;
+}
+
+// Launch the BRGEMMs recorded during graph capture, in order. Tile invokes are first folded into layers (above); runs
+// of 2..4 consecutive layers that form a chain (C of layer l is A of layer l+1) go to the persistent fused kernels
+// ("whole-MLP fusion ... or CUDA-graph capture of the invoke sequence"); everything else is launched
+// exactly as a direct invoke would.
 void flush_tiles();
 
 void flush_pending() {
@@ -473,11 +580,17 @@ void flush_pending() {
   std::vector<PendingGemm> list;
   list.swap(t_ctx.pending);
   cudaStream_t stream = t_ctx.stream;
-  // segment the list: maximal chains (2..4 layers, C of one = A of the next) and single invokes
-  const size_t n = list.size();
+  std::vector<Layer> layers;
+  for (size_t i = 0; i < list.size();) {
+    Layer L;
+    i += fold_grid(list, i, &L);
+    layers.push_back(L);
+  }
+  // segment the layers: maximal chains (2..4 layers, C of one = A of the next) and single layers
+  const size_t n = layers.size();
   std::vector<const KernelDesc *> descs(n);
   std::vector<GemmArgs> args(n);
-  for (size_t k = 0; k < n; ++k) { descs[k] = list[k].d; args[k] = list[k].g; }
+  for (size_t k = 0; k < n; ++k) { descs[k] = layers[k].d; args[k] = layers[k].g; }
   std::vector<int> seg_first, seg_len;     // seg_len 1 = not a chain
   for (size_t i = 0; i < n;) {
     int L = 1;
@@ -487,19 +600,32 @@ void flush_pending() {
     seg_len.push_back(L);
     i += L;
   }
+  // a layer no fused kernel took: its invokes are launched one by one, exactly as they were recorded
+  auto issue_layer = [&](size_t l) {
+    for (size_t k = layers[l].first; k < layers[l].first + layers[l].count; ++k) issue_gemm(list[k].d, list[k].g, stream);
+  };
+  // layers only the pair-per-chain kernel can run on the tensor cores in one launch: grids of tile invokes, VNNI-2 weights
+  auto pair_only = [&](size_t l) {
+    return (args[l].is_grid() || descs[l]->impl != KernelImpl::BrgemmTC) && brgemm_layer_chainable(*descs[l], args[l]);
+  };
   for (size_t sidx = 0; sidx < seg_first.size();) {
-    if (seg_len[sidx] == 1) {
-      issue_gemm(list[seg_first[sidx]].d, list[seg_first[sidx]].g, stream);
+    // a run of consecutive segments of the same kind: chains, or single layers that need the pair kernel
+    const bool chains = seg_len[sidx] > 1;
+    if (!chains && !pair_only((size_t)seg_first[sidx])) {
+      issue_layer((size_t)seg_first[sidx]);
       ++sidx;
       continue;
     }
-    // a run of consecutive chains: as many as possible in one launch of the feature-major kernel
     size_t run = sidx;
-    while (run < seg_first.size() && seg_len[run] > 1) ++run;
+    while (run < seg_first.size() && (chains ? seg_len[run] > 1 : (seg_len[run] == 1 && pair_only((size_t)seg_first[run]))))
+      ++run;
+    bool force = !chains;
+    for (size_t q = sidx; q < run && !force; ++q)
+      for (int l = 0; l < seg_len[q]; ++l) force = force || pair_only((size_t)(seg_first[q] + l));
     // many independent chains: one CTA pair per chain (4x less L2 -> SM traffic per layer than the pass kernels)
     int took = launch_brgemm_chains_pair(descs.data(), args.data(), seg_first.data() + sidx, seg_len.data() + sidx,
-                                         (int)(run - sidx), stream);
-    if (took == 0)
+                                         (int)(run - sidx), stream, force);
+    if (took == 0 && chains)
       took = launch_brgemm_chains_ft(descs.data(), args.data(), seg_first.data() + sidx, seg_len.data() + sidx,
                                      (int)(run - sidx), stream);
     if (took > 0) {
@@ -509,11 +635,11 @@ void flush_pending() {
       continue;
     }
     const int f = seg_first[sidx], L = seg_len[sidx];
-    if (launch_brgemm_chain(descs.data() + f, args.data() + f, L, stream)) {
+    if (chains && launch_brgemm_chain(descs.data() + f, args.data() + f, L, stream)) {
       t_ctx.last_kernel = brgemm_tc_last_name();
       count_launch();
     } else {
-      for (int l = 0; l < L; ++l) issue_gemm(list[f + l].d, list[f + l].g, stream);
+      for (int l = 0; l < L; ++l) issue_layer((size_t)(f + l));
     }
     ++sidx;
   }
@@ -591,7 +717,7 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
   } else {
     t_ctx.pdl_run = 0;                     // generic kernels / captured work are launched in plain stream order
   }
-  if (t_ctx.capturing && !sc.any_host && d->impl == KernelImpl::BrgemmTC) {
+  if (t_ctx.capturing && !sc.any_host && d->dtype == kBF16 && (d->impl == KernelImpl::BrgemmTC || d->flat_twin)) {
     flush_tiles();
     t_ctx.pending.push_back({d, g});   // launched (possibly fused with its neighbours) by flush_pending()
     return;

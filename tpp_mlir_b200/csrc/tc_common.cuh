@@ -160,6 +160,9 @@ inline ByteRange bf16_range(const void *p, int64_t elems) {
   const char *c = static_cast<const char *>(p);
   return ByteRange{c, c + elems * 2};
 }
+// byte ranges one layer (a plain invoke or a grid of tile invokes) reads and writes; B in VNNI-2 layout included
+struct LayerRanges { ByteRange a, b, c, d; };
+LayerRanges layer_ranges(const KernelDesc &d, const GemmArgs &g);
 // operand footprints of one chain: inputs (first layer's A, every layer's B and D) and outputs (every layer's C)
 void chain_ranges(const KernelDesc *const *descs, const GemmArgs *args, int L, std::vector<ByteRange> &in,
                   std::vector<ByteRange> &out);

@@ -176,47 +176,49 @@ unsigned long long *trace_ring() {
   return g_trace_buf;
 }
 
+LayerRanges layer_ranges(const KernelDesc &d, const GemmArgs &g) {
+  const int64_t nb = g.batch > 0 ? g.batch : 1;
+  const bool vnni = (d.gemm_flags & 2048) != 0;
+  const int64_t a_tile = (nb - 1) * d.stride_a + (d.m - 1) * d.lda + d.k;
+  const int64_t b_tile = vnni ? (nb - 1) * d.stride_b + ((d.k / 2 - 1) * d.ldb + d.n) * 2
+                              : (nb - 1) * d.stride_b + (d.k - 1) * d.ldb + d.n;
+  const int64_t c_tile = (d.m - 1) * d.ldc + d.n;
+  LayerRanges r;
+  r.a = bf16_range(g.A, (g.grid_n - 1) * g.a_step + a_tile);
+  r.b = bf16_range(g.B, (g.grid_k - 1) * g.b_step + b_tile);
+  r.c = bf16_range(g.C, (g.grid_n - 1) * g.c_step_n + (g.grid_k - 1) * g.c_step_k + c_tile);
+  r.d = g.D ? bf16_range(g.D, (g.grid_k - 1) * g.d_step + d.n) : ByteRange{nullptr, nullptr};
+  return r;
+}
+
 // operand footprints of one chain: inputs (first layer's A, every layer's B and D) and outputs (every layer's C)
 void chain_ranges(const KernelDesc *const *descs, const GemmArgs *args, int L, std::vector<ByteRange> &in,
                   std::vector<ByteRange> &out) {
   for (int l = 0; l < L; ++l) {
-    const KernelDesc &d = *descs[l];
-    const GemmArgs &g = args[l];
-    const int64_t nb = g.batch > 0 ? g.batch : 1;
-    auto rng = [](const void *p, int64_t elems) { return bf16_range(p, elems); };
-    if (l == 0) in.push_back(rng(g.A, (nb - 1) * d.stride_a + (d.m - 1) * d.lda + d.k));
-    in.push_back(rng(g.B, (nb - 1) * d.stride_b + (d.k - 1) * d.ldb + d.n));
-    if (g.D) in.push_back(rng(g.D, d.n));
-    out.push_back(rng(g.C, (d.m - 1) * d.ldc + d.n));
+    const LayerRanges r = layer_ranges(*descs[l], args[l]);
+    if (l == 0) in.push_back(r.a);
+    in.push_back(r.b);
+    if (r.d.lo) in.push_back(r.d);
+    out.push_back(r.c);
   }
 }
 
 // No layer's weights / bias overlap ANY layer's output, no two outputs overlap, and the chain's input is not one of its
 // outputs (byte ranges, not pointer equality: an operand that starts inside another layer's C is a hazard too).
 bool chain_operands_hazard_free(const KernelDesc *const *descs, const GemmArgs *args, int L) {
-  ByteRange outs[8], bs[8], ds[8];
+  LayerRanges r[8];
   if (L > 8) return false;
-  for (int l = 0; l < L; ++l) {
-    const KernelDesc &d = *descs[l];
-    const int64_t nb = args[l].batch > 0 ? args[l].batch : 1;
-    outs[l] = bf16_range(args[l].C, (d.m - 1) * d.ldc + d.n);
-    bs[l] = bf16_range(args[l].B, (nb - 1) * d.stride_b + (d.k - 1) * d.ldb + d.n);
-    ds[l] = args[l].D ? bf16_range(args[l].D, d.n) : ByteRange{nullptr, nullptr};
-  }
-  const KernelDesc &d0 = *descs[0];
-  const int64_t nb0 = args[0].batch > 0 ? args[0].batch : 1;
-  const ByteRange in0 = bf16_range(args[0].A, (nb0 - 1) * d0.stride_a + (d0.m - 1) * d0.lda + d0.k);
+  for (int l = 0; l < L; ++l) r[l] = layer_ranges(*descs[l], args[l]);
   for (int l = 0; l < L; ++l)
     for (int j = 0; j < L; ++j) {
-      if (overlaps(bs[l], outs[j])) return false;
-      if (ds[l].lo && overlaps(ds[l], outs[j])) return false;
-      if (j != l && overlaps(outs[l], outs[j])) return false;
+      if (overlaps(r[l].b, r[j].c)) return false;
+      if (r[l].d.lo && overlaps(r[l].d, r[j].c)) return false;
+      if (j != l && overlaps(r[l].c, r[j].c)) return false;
     }
   for (int j = 0; j < L; ++j)
-    if (overlaps(in0, outs[j])) return false;
+    if (overlaps(r[0].a, r[j].c)) return false;
   return true;
 }
-
 } // namespace tc
 
 using namespace tc;
