@@ -70,6 +70,12 @@ struct alignas(128) PcLayer {
   int32_t n_tiles;          // output columns / 256
   int32_t relu;
   int32_t vnni;
+  // 32-wide blocks: the innermost contiguous extent of an operand is 64 bytes, half a SWIZZLE_128B row (TMA would pad
+  // every 64-byte piece to its own 128-byte line). Those operands use SWIZZLE_64B instead: a 64-wide k-block of X is
+  // two [128 rows][32 k] sub-tiles (two boxes), a 64-column chunk of W / C two [64 k | 128 rows][32 n] sub-tiles.
+  int32_t x64;              // k == 32
+  int32_t w64;              // n == 32, flat weights
+  int32_t c64;              // n == 32
 };
 struct PcItem {
   int32_t layer0, num_layers, row0, pad;
@@ -164,6 +170,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
           if (!VNNI) tensormap_acquire(&L->tmW);
           const int32_t total = L->total_iters, n_tiles = L->n_tiles;
           const int32_t lk = L->k, k_bstep = L->k_bstep, ln = L->n;
+          const bool x64 = L->x64 != 0, w64 = L->w64 != 0;
           // my 128 rows: inside one row block (m >= 128) or 128 / m whole row blocks
           const int32_t xr = L->m >= BLOCK_M ? row0 % L->m : 0, xi = row0 / L->m;
           int32_t ready = 0;                          // output tiles of layer l - 1 (my rows) known to be stored
@@ -186,12 +193,13 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
                 // the weights depend on nothing: their boxes go out before any wait for the previous layer
 #pragma unroll
                 for (int c = 0; c < PC_W_CHUNKS; ++c) {
-                  if (hints)
-                    ptx::tma_load_4d_pair_hint(smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES, &L->tmW, leader_full + 8 * s,
-                                               wn[c], wj[c], c0, c1, pol_first);
-                  else
-                    ptx::tma_load_4d_pair(smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES, &L->tmW, leader_full + 8 * s,
-                                          wn[c], wj[c], c0, c1);
+                  const uint32_t dst = smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES;
+                  if (hints) ptx::tma_load_4d_pair_hint(dst, &L->tmW, leader_full + 8 * s, wn[c], wj[c], c0, c1, pol_first);
+                  else ptx::tma_load_4d_pair(dst, &L->tmW, leader_full + 8 * s, wn[c], wj[c], c0, c1);
+                  if (w64) {   // the chunk's second 32-column block: its own [64 k][32 n] sub-tile
+                    if (hints) ptx::tma_load_4d_pair_hint(dst + B_CHUNK_BYTES / 2, &L->tmW, leader_full + 8 * s, 0, wj[c] + 1, c0, c1, pol_first);
+                    else ptx::tma_load_4d_pair(dst + B_CHUNK_BYTES / 2, &L->tmW, leader_full + 8 * s, 0, wj[c] + 1, c0, c1);
+                  }
                 }
               }
               if (l > 0 && j == 0) {
@@ -212,6 +220,13 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
                 ptx::tma_load_4d_pair_hint(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, c0, c1, xr, xi, pol_x);
               else
                 ptx::tma_load_4d_pair(smem_a + s * A_STAGE_BYTES, &L->tmX, leader_full + 8 * s, c0, c1, xr, xi);
+              if (x64) {     // k == 32: the k-block's second batch element is its own [128 rows][32 k] sub-tile
+                if (hints)
+                  ptx::tma_load_4d_pair_hint(smem_a + s * A_STAGE_BYTES + A_STAGE_BYTES / 2, &L->tmX, leader_full + 8 * s, 0, c1 + 1,
+                                             xr, xi, pol_x);
+                else
+                  ptx::tma_load_4d_pair(smem_a + s * A_STAGE_BYTES + A_STAGE_BYTES / 2, &L->tmX, leader_full + 8 * s, 0, c1 + 1, xr, xi);
+              }
               c0 += BLOCK_K;
               if (c0 >= lk) { c0 = 0; c1 += k_bstep; }
               if (++s == PC_STAGES) { s = 0; ph ^= 1; }
@@ -232,6 +247,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
         for (int l = 0; l < it.num_layers; ++l) {
           const PcLayer *L = cp.layers + it.layer0 + l;
           const int32_t total = L->total_iters, n_tiles = L->n_tiles;
+          const bool x64 = L->x64 != 0, w64 = L->w64 != 0;
           for (int32_t j = 0; j < n_tiles; ++j, ++t) {
             const uint32_t buf = t & 1;
             if (t >= 2) {                              // both epilogues have read tile t - 2 out of this accumulator
@@ -248,8 +264,13 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
               const uint32_t b_addr = smem_w + s * PC_W_CHUNKS * B_CHUNK_BYTES;
 #pragma unroll
               for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
-                const uint64_t da = ptx::umma_smem_desc_sw128(a_addr + kk * (UMMA_K * 2), 16, 1024);
-                const uint64_t db = ptx::umma_smem_desc_sw128(b_addr + kk * (UMMA_K * 128), B_CHUNK_BYTES, 1024);
+                // SWIZZLE_128B: A rows are 128 bytes (64 k), B atoms 64 columns wide. SWIZZLE_64B (32-wide blocks): A is two
+                // [128 rows][32 k] sub-tiles (k steps 0,1 | 2,3), 8-row atoms of 512 bytes; B atoms are 32 columns wide
+                // (4 KiB apart), 8 k rows = 512 bytes, one k step = 16 rows of 64 bytes
+                const uint64_t da = x64 ? ptx::umma_smem_desc_sw64(a_addr + (kk >> 1) * (A_STAGE_BYTES / 2) + (kk & 1) * (UMMA_K * 2), 16, 512)
+                                        : ptx::umma_smem_desc_sw128(a_addr + kk * (UMMA_K * 2), 16, 1024);
+                const uint64_t db = w64 ? ptx::umma_smem_desc_sw64(b_addr + kk * (UMMA_K * 64), B_CHUNK_BYTES / 2, 512)
+                                        : ptx::umma_smem_desc_sw128(b_addr + kk * (UMMA_K * 128), B_CHUNK_BYTES, 1024);
                 ptx::umma_bf16_pair(acc, da, db, idesc, (i > 0 || kk > 0) ? 1u : 0u);
               }
               ptx::umma_commit_pair(empty_bar + 8 * s, pair_mask);   // frees the slot in both CTAs
@@ -276,6 +297,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
     const bool hints = cp.l2_hints != 0;
     const uint32_t row_off = (uint32_t)r_in * 128u;
     const uint32_t sw = (uint32_t)(r_in & 7);
+    const uint32_t sw64 = (uint32_t)((r_in >> 1) & 3);
     uint32_t t = 0, g = 0;                            // tiles / store boxes handled so far
     // The bias slice of a tile (256 bf16) is staged in shared memory one tile ahead: thread i fetches columns 2i, 2i+1
     // of the NEXT tile into a register before it starts on the current one and parks it in the other half of the
@@ -296,6 +318,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
         const PcLayer *L = cp.layers + it.layer0 + l;
         if (issuer) tensormap_acquire(&L->tmC);
         const int32_t ln = L->n;
+        const bool c64 = L->c64 != 0;
         const int32_t xr = L->m >= BLOCK_M ? row0 % L->m : 0, xi = row0 / L->m;   // as in the producer
         const void *Dp = L->D;
         const bool relu = L->relu != 0;
@@ -347,8 +370,11 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
                   o[w] = pack_bf16x2(lo, hi);
                 }
                 const uint32_t chunk = (uint32_t)(h / 8 + u);   // 16-byte chunk of the 128-byte row
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                             ::"r"(sbuf + row_off + ((chunk ^ sw) << 4)), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
+                // SWIZZLE_128B staging: [128 rows][128 bytes]; SWIZZLE_64B (32-column blocks): two [128 rows][64 bytes]
+                // pieces, one per column block
+                const uint32_t dst = c64 ? sbuf + (chunk >> 2) * (PC_OUT_BYTES / 2) + (uint32_t)r_in * 64u + (((chunk & 3u) ^ sw64) << 4)
+                                         : sbuf + row_off + ((chunk ^ sw) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
                              : "memory");
               }
             }
@@ -360,6 +386,11 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
               const int32_t cn = ln >= 64 ? col % ln : 0, cj = col / ln;
               if (!hints) ptx::tma_store_4d(&L->tmC, sbuf, cn, cj, xr, xi);
               else ptx::tma_store_4d_hint(&L->tmC, sbuf, cn, cj, xr, xi, l + 1 < it.num_layers ? pol_last : pol_first);
+              if (c64) {     // the second 32-column block of this 64-column group
+                if (!hints) ptx::tma_store_4d(&L->tmC, sbuf + PC_OUT_BYTES / 2, 0, cj + 1, xr, xi);
+                else ptx::tma_store_4d_hint(&L->tmC, sbuf + PC_OUT_BYTES / 2, 0, cj + 1, xr, xi,
+                                            l + 1 < it.num_layers ? pol_last : pol_first);
+              }
               ptx::bulk_commit_group();
               if (c == 0 && j > 0 && l + 1 < it.num_layers) {
                 // every store group but the one just committed is complete: tile j - 1 (my rows) is in L2
@@ -489,7 +520,9 @@ bool chain_pair_supported(const KernelDesc *const *descs, const GemmArgs *args, 
     if ((n_total % PC_BLOCK_N) != 0 || n_total > PC_MAX_TILES * PC_BLOCK_N) return false;
     if ((k_total % BLOCK_K) != 0 || k_total > (1 << 24)) return false;
     if (!divides_or_multiple(d.m, BLOCK_M) || !divides_or_multiple(d.k, BLOCK_K) || !divides_or_multiple(d.n, 64)) return false;
-    if (d.k < 8 || d.n < 8) return false;                               // the inner box extent is at least 16 bytes
+    // the innermost contiguous extent of every operand is a whole swizzle row: 128 bytes (SWIZZLE_128B) or 64 bytes
+    // (SWIZZLE_64B); TMA pads anything narrower to its own line
+    if (d.k < 32 || d.n < 32) return false;
     if ((d.lda % 8) != 0 || (d.ldb % 8) != 0 || (d.ldc % 8) != 0) return false;
     if (g.batch > 1 && (d.stride_a % 8) != 0) return false;
     if (g.batch > 1 && (d.stride_b % 8) != 0) return false;
@@ -513,20 +546,25 @@ bool encode_layer_maps(PcLayer &pl, const KernelDesc &d, const GemmArgs &g, bool
   const uint64_t b_step = gk > 1 ? (uint64_t)g.b_step : (uint64_t)d.ldb, ck_step = gk > 1 ? (uint64_t)g.c_step_k : (uint64_t)d.ldc;
   const uint32_t kx = (uint32_t)std::min<int64_t>(d.k, BLOCK_K), rx = (uint32_t)std::min<int64_t>(d.m, BLOCK_M),
                  nx = (uint32_t)std::min<int64_t>(d.n, 64);
+  const bool k32 = kx == 32, n32 = nx == 32;   // 64-byte inner extents: SWIZZLE_64B, one block per box along that dimension
+  pl.x64 = k32 ? 1 : 0;
+  pl.w64 = (n32 && !vnni) ? 1 : 0;
+  pl.c64 = n32 ? 1 : 0;
   {
     const uint64_t dims[4] = {(uint64_t)d.k, nb, (uint64_t)d.m, gn}, str[3] = {sa, (uint64_t)d.lda, a_step};
-    const uint32_t box[4] = {kx, BLOCK_K / kx, rx, BLOCK_M / rx};
-    if (!encode_map_nd(&pl.tmX, g.A, 4, dims, str, box, true)) return false;
+    const uint32_t box[4] = {kx, k32 ? 1u : BLOCK_K / kx, rx, BLOCK_M / rx};
+    if (!encode_map_nd(&pl.tmX, g.A, 4, dims, str, box, k32 ? 64 : 128)) return false;
   }
   if (!vnni) {
+    // k rows of one box: all 64 of the k-block (for k == 32: both batch elements, 32 rows each)
     const uint64_t dims[4] = {(uint64_t)d.n, gk, (uint64_t)d.k, nb}, str[3] = {b_step, (uint64_t)d.ldb, sb};
-    const uint32_t box[4] = {nx, 64 / nx, kx, BLOCK_K / kx};
-    if (!encode_map_nd(&pl.tmW, g.B, 4, dims, str, box, true)) return false;
+    const uint32_t box[4] = {nx, n32 ? 1u : 64 / nx, kx, BLOCK_K / kx};
+    if (!encode_map_nd(&pl.tmW, g.B, 4, dims, str, box, n32 ? 64 : 128)) return false;
   }
   {
     const uint64_t dims[4] = {(uint64_t)d.n, gk, (uint64_t)d.m, gn}, str[3] = {ck_step, (uint64_t)d.ldc, cn_step};
-    const uint32_t box[4] = {nx, PC_OUT_COLS / nx, rx, BLOCK_M / rx};
-    if (!encode_map_nd(&pl.tmC, g.C, 4, dims, str, box, true)) return false;
+    const uint32_t box[4] = {nx, n32 ? 1u : PC_OUT_COLS / nx, rx, BLOCK_M / rx};
+    if (!encode_map_nd(&pl.tmC, g.C, 4, dims, str, box, n32 ? 64 : 128)) return false;
   }
   return true;
 }
@@ -607,6 +645,14 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
       PcLayer &pl = hl[nl++];
       memset(&pl, 0, sizeof(pl));
       if (!encode_layer_maps(pl, d, g, vnni)) return 0;
+      static const bool dbg = getenv("TPP_XSMM_DEBUG") != nullptr;
+      if (dbg)
+        fprintf(stderr, "pair-chain layer: chain %d layer %d tile m=%lld n=%lld k=%lld batch=%lld lda=%lld ldb=%lld ldc=%lld sa=%lld "
+                        "sb=%lld grid %d x %d steps a=%lld b=%lld cn=%lld ck=%lld d=%lld vnni=%d A=%p B=%p C=%p D=%p\n", c, l,
+                (long long)d.m, (long long)d.n, (long long)d.k, (long long)g.batch, (long long)d.lda, (long long)d.ldb,
+                (long long)d.ldc, (long long)d.stride_a, (long long)d.stride_b, g.grid_n, g.grid_k, (long long)g.a_step,
+                (long long)g.b_step, (long long)g.c_step_n, (long long)g.c_step_k, (long long)g.d_step, (int)vnni, g.A, g.B, g.C,
+                g.D);
       grids = grids || g.is_grid();
       pl.D = (d.op == OpClass::FusedBrgemm && g.D && d.binary_kind == 1) ? g.D : nullptr;
       pl.W = g.B;

@@ -310,6 +310,17 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t saddr, uint32_
   d |= 2ull << 61;
   return d;
 }
+// Same descriptor with SWIZZLE_64B (layout type 4): 64-byte rows, 8-row atoms of 512 bytes, 16-byte chunk index XORed
+// with bits [1,3) of the row. Used for operands whose innermost contiguous extent in global memory is 32 bf16.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw64(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((saddr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= 1ull << 46;
+  d |= 4ull << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16 with bf16 A/B, f32 D:
 //   [4,6) D format (1 = f32), [7,10) A format (1 = bf16), [10,13) B format (1 = bf16),
 //   [15] A major (0 = K), [16] B major (1 = MN), [17,23) N >> 3, [24,29) M >> 4

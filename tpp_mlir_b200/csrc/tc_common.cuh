@@ -136,7 +136,7 @@ bool encode_map_x4(CUtensorMap *map, const void *base, uint64_t k, uint64_t rows
                    uint64_t stride, uint32_t box_rows, uint32_t box_kb, uint32_t box_b);
 // generic bf16 tensor map of rank <= 5: dims / strides (elements; strides[0] is the stride of dims[1]) / box
 bool encode_map_nd(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides,
-                   const uint32_t *box, bool swizzle128);
+                   const uint32_t *box, int swizzle_bytes);
 int bin_mode_from_flags(int64_t f);
 
 // Device memory owned by the graph being captured. Everything a captured kernel node reads or spins on (descriptor

@@ -75,7 +75,7 @@ bool encode_map_x4(CUtensorMap *map, const void *base, uint64_t k, uint64_t rows
 
 
 bool encode_map_nd(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides,
-                   const uint32_t *box, bool swizzle128) {
+                   const uint32_t *box, int swizzle_bytes) {
   if (rank < 1 || rank > 5) return false;
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], estr[5];
@@ -83,7 +83,8 @@ bool encode_map_nd(CUtensorMap *map, const void *base, int rank, const uint64_t 
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides[i] * 2;
   CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void *>(base), gd, gs, bx,
                                estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                               swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                                                       : CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
