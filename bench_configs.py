@@ -282,6 +282,8 @@ def main():
         rows.append(cfg3b(pk))
     if on("cfg4"):
         rows.extend(eltwise(pk))
+    if on("refstream"):
+        rows.append(reference_stream(pk))
     if on("pack"):
         rows.extend(pack(pk))
     if on("cfg5"):

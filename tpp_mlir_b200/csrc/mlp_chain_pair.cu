@@ -99,7 +99,8 @@ __device__ __forceinline__ void tensormap_acquire(const void *map) {
   asm volatile("fence.proxy.tensormap::generic.acquire.sys [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
-template <bool VNNI>
+// NARROW: some layer has 32-wide blocks (SWIZZLE_64B operands); false compiles the selects out of the hot loops
+template <bool VNNI, bool NARROW>
 __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_chain_pair_kernel(const PcParams cp) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
           if (!VNNI) tensormap_acquire(&L->tmW);
           const int32_t total = L->total_iters, n_tiles = L->n_tiles;
           const int32_t lk = L->k, k_bstep = L->k_bstep, ln = L->n;
-          const bool x64 = L->x64 != 0, w64 = L->w64 != 0;
+          const bool x64 = NARROW && L->x64 != 0, w64 = NARROW && L->w64 != 0;
           // my 128 rows: inside one row block (m >= 128) or 128 / m whole row blocks
           const int32_t xr = L->m >= BLOCK_M ? row0 % L->m : 0, xi = row0 / L->m;
           int32_t ready = 0;                          // output tiles of layer l - 1 (my rows) known to be stored
@@ -247,7 +248,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
         for (int l = 0; l < it.num_layers; ++l) {
           const PcLayer *L = cp.layers + it.layer0 + l;
           const int32_t total = L->total_iters, n_tiles = L->n_tiles;
-          const bool x64 = L->x64 != 0, w64 = L->w64 != 0;
+          const bool x64 = NARROW && L->x64 != 0, w64 = NARROW && L->w64 != 0;
           for (int32_t j = 0; j < n_tiles; ++j, ++t) {
             const uint32_t buf = t & 1;
             if (t >= 2) {                              // both epilogues have read tile t - 2 out of this accumulator
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
         const PcLayer *L = cp.layers + it.layer0 + l;
         if (issuer) tensormap_acquire(&L->tmC);
         const int32_t ln = L->n;
-        const bool c64 = L->c64 != 0;
+        const bool c64 = NARROW && L->c64 != 0;
         const int32_t xr = L->m >= BLOCK_M ? row0 % L->m : 0, xi = row0 / L->m;   // as in the producer
         const void *Dp = L->D;
         const bool relu = L->relu != 0;
@@ -420,67 +421,115 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
     // (t >> 3) and (t >> 3) + 16 of both chunks - four units of 32 contiguous global bytes (8 columns x 2 k).
     const int cw = warp - 6;
     const int group = cw / PC_CONV_WARPS;
-    const int ct = (cw % PC_CONV_WARPS) * 32 + lane;  // 0 .. 127 within the group
-    const int g8 = ct & 7, r_lo = ct >> 3;
+    // Lane mapping: one warp-wide 16-byte load covers two whole k-pair rows of a chunk (2 x 256 contiguous bytes: every
+    // 32-byte sector is consumed by one instruction - with 32 bytes per lane each load used half of every sector it
+    // touched and the weights crossed the L2 -> SM path twice). Lanes 2p, 2p + 1 hold columns 8p .. 8p + 3 / 8p + 4 .. 8p + 7
+    // of one row (both k of the pair); they swap halves with one shuffle so that the even lane owns the 8 columns of the
+    // even k (one 16-byte chunk of swizzled row 2R) and the odd lane those of the odd k (row 2R + 1).
+    const int wq = cw % PC_CONV_WARPS;                // warp within the group
+    const int row_sub = lane >> 4, g8 = (lane & 15) >> 1, half = lane & 1;
     const uint32_t leader_full = ptx::mapa(full_bar, 0);
     const uint64_t pol_first = ptx::l2_policy_evict_first();
-    uint32_t q = 0;                                   // running k-block index of this CTA (all items / layers / tiles)
-    for (int item = pair; item < cp.num_items; item += num_pairs) {
-      const PcItem it = cp.items[item];
-      for (int l = 0; l < it.num_layers; ++l) {
-        const PcLayer *L = cp.layers + it.layer0 + l;
-        const char *Wb = static_cast<const char *>(L->W);
-        const int32_t ln = L->n, lk = L->k, total = L->total_iters, n_tiles = L->n_tiles;
-        const int64_t col_step = L->w_col_step, batch_step = L->w_batch_step, ldb2 = 2 * L->w_ldb;
-        const int32_t half_k = lk >> 1;               // k-pair rows per batch element
-        for (int32_t j = 0; j < n_tiles; ++j) {
-          int64_t col_off[PC_W_CHUNKS];               // element offset of my 8 columns: column block + column in block
+    // Position in the CTA's flattened k-block sequence (item, layer, tile, k-block) plus what the address needs. Every
+    // thread keeps TWO k-blocks of loads in flight (the one it converts next and the one after: registers va / vb), so
+    // a CTA has 2 x PC_CONV_GROUPS k-blocks = 64 KiB of weight loads outstanding - the converter is a latency pipeline
+    // (measured with one k-block per group in flight: 2100 clk per k-block against 1250 for the TMA-fed flat kernel).
+    struct Cursor {
+      int item, l;
+      int32_t j, i;
+      uint32_t q;
+      bool valid;
+      const char *Wb;
+      int32_t ln, half_k, total, n_tiles, num_layers, layer0;
+      int64_t col_step, batch_step, ldb2, col_off[PC_W_CHUNKS];
+    };
+    auto load_tile = [&](Cursor &c) {
 #pragma unroll
-          for (int c = 0; c < PC_W_CHUNKS; ++c) {
-            const int32_t col = j * PC_BLOCK_N + (int32_t)peer * PC_HALF_N + c * 64 + 8 * g8;
-            col_off[c] = (int64_t)(col / ln) * col_step + (int64_t)(col % ln) * 2;
-          }
-          for (int32_t i = 0; i < total; ++i, ++q) {
-            if ((int)(q % PC_CONV_GROUPS) != group) continue;
-            const uint32_t s = q % PC_STAGES, ph = (q / PC_STAGES) & 1u;
-            uint4 v[2 * PC_W_CHUNKS][2];
-#pragma unroll
-            for (int u = 0; u < 2 * PC_W_CHUNKS; ++u) {
-              const int32_t kpg = i * 32 + r_lo + 16 * (u & 1);          // k-pair row within the whole reduction
-              const int32_t b = kpg / half_k, kp = kpg - b * half_k;
-              const char *src = Wb + 2 * (col_off[u >> 1] + (int64_t)b * batch_step + (int64_t)kp * ldb2);
-              v[u][0] = ptx::ldg_v4_hint(src, pol_first);
-              v[u][1] = ptx::ldg_v4_hint(src + 16, pol_first);
-            }
-            ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
-#pragma unroll
-            for (int u = 0; u < 2 * PC_W_CHUNKS; ++u) {
-              const uint32_t w[8] = {v[u][0].x, v[u][0].y, v[u][0].z, v[u][0].w, v[u][1].x, v[u][1].y, v[u][1].z, v[u][1].w};
-              uint32_t lo[4], hi[4];                  // k even / k odd of my 8 columns
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                lo[e] = __byte_perm(w[2 * e], w[2 * e + 1], 0x5410);
-                hi[e] = __byte_perm(w[2 * e], w[2 * e + 1], 0x7632);
-              }
-              const uint32_t r0 = 2u * (uint32_t)(r_lo + 16 * (u & 1));     // k row of the 64 x 64 chunk (128-byte rows)
-              const uint32_t base = smem_w + (s * PC_W_CHUNKS + (u >> 1)) * B_CHUNK_BYTES;
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                           ::"r"(base + r0 * 128u + (((uint32_t)g8 ^ (r0 & 7u)) << 4)), "r"(lo[0]), "r"(lo[1]), "r"(lo[2]), "r"(lo[3])
-                           : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                           ::"r"(base + (r0 + 1u) * 128u + (((uint32_t)g8 ^ ((r0 + 1u) & 7u)) << 4)), "r"(hi[0]), "r"(hi[1]), "r"(hi[2]),
-                             "r"(hi[3])
-                           : "memory");
-            }
-            ptx::fence_proxy_async();                 // my shared-memory writes -> the async proxy (the pair's MMAs)
-            __syncwarp();
-            if (lane == 0) {
-              if (peer == 0) ptx::mbar_arrive(full_bar + 8 * s);
-              else ptx::mbar_arrive_remote(leader_full + 8 * s);
-            }
-          }
-        }
+      for (int ch = 0; ch < PC_W_CHUNKS; ++ch) {
+        const int32_t col = c.j * PC_BLOCK_N + (int32_t)peer * PC_HALF_N + ch * 64 + 8 * g8 + 4 * half;
+        c.col_off[ch] = (int64_t)(col / c.ln) * c.col_step + (int64_t)(col % c.ln) * 2;
       }
+    };
+    auto load_layer = [&](Cursor &c) {
+      const PcLayer *L = cp.layers + c.layer0 + c.l;
+      c.Wb = static_cast<const char *>(L->W);
+      c.ln = L->n; c.half_k = L->k >> 1; c.total = L->total_iters; c.n_tiles = L->n_tiles;
+      c.col_step = L->w_col_step; c.batch_step = L->w_batch_step; c.ldb2 = 2 * L->w_ldb;
+      load_tile(c);
+    };
+    auto load_item = [&](Cursor &c) {
+      c.valid = c.item < cp.num_items;
+      if (!c.valid) return;
+      const PcItem it = cp.items[c.item];
+      c.layer0 = it.layer0; c.num_layers = it.num_layers;
+      c.l = 0; c.j = 0; c.i = 0;
+      load_layer(c);
+    };
+    auto step = [&](Cursor &c) {   // one k-block forward
+      ++c.q;
+      if (++c.i < c.total) return;
+      c.i = 0;
+      if (++c.j < c.n_tiles) { load_tile(c); return; }
+      c.j = 0;
+      if (++c.l < c.num_layers) { load_layer(c); return; }
+      c.item += num_pairs;
+      load_item(c);
+    };
+    auto advance = [&](Cursor &c) {   // to this group's next k-block
+      for (int n = 0; n < PC_CONV_GROUPS && c.valid; ++n) step(c);
+    };
+    constexpr int UNITS = 4 * PC_W_CHUNKS;            // 16-byte loads per thread and k-block: 4 row groups x 2 chunks
+    auto issue = [&](const Cursor &c, uint4 (&v)[UNITS]) {
+#pragma unroll
+      for (int u = 0; u < UNITS; ++u) {
+        const int32_t kpg = c.i * 32 + (u & 3) * 8 + wq * 2 + row_sub;     // k-pair row within the whole reduction
+        const int32_t b = kpg / c.half_k, kp = kpg - b * c.half_k;
+        const char *src = c.Wb + 2 * (c.col_off[u >> 2] + (int64_t)b * c.batch_step + (int64_t)kp * c.ldb2);
+        v[u] = ptx::ldg_v4_hint(src, pol_first);
+      }
+    };
+    auto finish = [&](const Cursor &c, uint4 (&v)[UNITS]) {
+      const uint32_t s = c.q % PC_STAGES, ph = (c.q / PC_STAGES) & 1u;
+      ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
+#pragma unroll
+      for (int u = 0; u < UNITS; ++u) {
+        // my 4 columns x (k even | k odd) -> 4 columns of k even (lo) and 4 columns of k odd (hi)
+        const uint32_t lo0 = __byte_perm(v[u].x, v[u].y, 0x5410), lo1 = __byte_perm(v[u].z, v[u].w, 0x5410);
+        const uint32_t hi0 = __byte_perm(v[u].x, v[u].y, 0x7632), hi1 = __byte_perm(v[u].z, v[u].w, 0x7632);
+        // the even lane keeps lo and needs its neighbour's lo; the odd lane keeps hi and needs its neighbour's hi
+        const uint32_t r0 = __shfl_xor_sync(0xffffffffu, half ? lo0 : hi0, 1);
+        const uint32_t r1 = __shfl_xor_sync(0xffffffffu, half ? lo1 : hi1, 1);
+        const uint32_t o0 = half ? r0 : lo0, o1 = half ? r1 : lo1, o2 = half ? hi0 : r0, o3 = half ? hi1 : r1;
+        const uint32_t krow = 2u * (uint32_t)((u & 3) * 8 + wq * 2 + row_sub) + (uint32_t)half;   // k row of the 64 x 64 chunk
+        const uint32_t base = smem_w + (s * PC_W_CHUNKS + (u >> 2)) * B_CHUNK_BYTES;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(base + krow * 128u + (((uint32_t)g8 ^ (krow & 7u)) << 4)), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                     : "memory");
+      }
+      ptx::fence_proxy_async();                 // my shared-memory writes -> the async proxy (the pair's MMAs)
+      __syncwarp();
+      if (lane == 0) {
+        if (peer == 0) ptx::mbar_arrive(full_bar + 8 * s);
+        else ptx::mbar_arrive_remote(leader_full + 8 * s);
+      }
+    };
+    Cursor cur;
+    cur.item = pair; cur.q = 0;
+    load_item(cur);
+    for (int n = 0; n < group && cur.valid; ++n) step(cur);   // this group's first k-block
+    uint4 va[UNITS], vb[UNITS];
+    if (cur.valid) issue(cur, va);
+    while (cur.valid) {
+      Cursor nxt = cur;
+      advance(nxt);
+      if (nxt.valid) issue(nxt, vb);
+      finish(cur, va);
+      cur = nxt;
+      if (!cur.valid) break;
+      advance(nxt);
+      if (nxt.valid) issue(nxt, va);
+      finish(cur, vb);
+      cur = nxt;
     }
   }
 
@@ -569,10 +618,10 @@ bool encode_layer_maps(PcLayer &pl, const KernelDesc &d, const GemmArgs &g, bool
   return true;
 }
 
-template <bool VNNI> void launch_pair_kernel(const PcParams &cp, int pairs, cudaStream_t stream) {
+template <bool VNNI, bool NARROW> void launch_pair_kernel(const PcParams &cp, int pairs, cudaStream_t stream) {
   static std::once_flag once;
   std::call_once(once, [] {
-    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<VNNI>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM));
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<VNNI, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM));
   });
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(2 * pairs));
@@ -588,7 +637,7 @@ template <bool VNNI> void launch_pair_kernel(const PcParams &cp, int pairs, cuda
   attrs[1].val.clusterDim.z = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 2;
-  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_pair_kernel<VNNI>, cp));
+  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_pair_kernel<VNNI, NARROW>, cp));
 }
 }  // namespace
 
@@ -637,6 +686,8 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   std::vector<PcItem> hi((size_t)items);
   size_t nl = 0, ni = 0;
   bool grids = false;
+  static const bool force_narrow = [] { const char *e = getenv("TPP_XSMM_PAIR_NARROW"); return e && e[0] == '1'; }();   // A/B
+  bool narrow = force_narrow;
   for (int c = 0; c < take; ++c) {
     const int32_t layer0 = (int32_t)nl;
     for (int l = 0; l < len[c]; ++l) {
@@ -654,6 +705,7 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
                 (long long)g.b_step, (long long)g.c_step_n, (long long)g.c_step_k, (long long)g.d_step, (int)vnni, g.A, g.B, g.C,
                 g.D);
       grids = grids || g.is_grid();
+      narrow = narrow || pl.x64 || pl.w64 || pl.c64;
       pl.D = (d.op == OpClass::FusedBrgemm && g.D && d.binary_kind == 1) ? g.D : nullptr;
       pl.W = g.B;
       pl.w_col_step = g.grid_k > 1 ? g.b_step : 0;
@@ -710,8 +762,10 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   const int rounds = (int)((items + max_pairs - 1) / max_pairs);
   const int pairs = (int)((items + rounds - 1) / rounds);
   g_pc_trace_ctas = 2 * pairs;
-  if (vnni) launch_pair_kernel<true>(cp, pairs, stream);
-  else launch_pair_kernel<false>(cp, pairs, stream);
+  if (vnni && narrow) launch_pair_kernel<true, true>(cp, pairs, stream);
+  else if (vnni) launch_pair_kernel<true, false>(cp, pairs, stream);
+  else if (narrow) launch_pair_kernel<false, true>(cp, pairs, stream);
+  else launch_pair_kernel<false, false>(cp, pairs, stream);
   set_last_name("mlp_chain_bf16_%dx%dlayers_pair256x256%s%s", (int)items, len[0], grids ? "_blocked" : "", vnni ? "_vnni2" : "");
   return take;
 }
