@@ -170,6 +170,8 @@ def reference_stream(pk):
     torch.cuda.synchronize()
     t = e0.elapsed_time(e1) * 1e-3 / (n * wl.num_sets)
     launches = (xsmm.launch_count() - l0) / (n * wl.num_sets)
+    if os.environ.get("TPP_XSMM_TC_TRACE") == "4":
+        xsmm.LIB.xsmm_cuda_debug_dump_trace()
     s = wl.num_sets - 1
     rel = bench.rel_err(wl.output(s).cpu().numpy().view(np.uint16), np.roll(bench.oracle_forward(x, Ws, bs), s, 0))
     flops = wl.cfg.flops()

@@ -41,7 +41,7 @@ constexpr int PC_OUT_BYTES = BLOCK_M * PC_OUT_COLS * 2;   // 16 KiB staging buff
 constexpr int PC_BIAS_BYTES = PC_BLOCK_N * 2;         // one tile's bias slice, two of them
 constexpr int PC_MAX_TILES = 16;                      // output tiles per layer (n <= 4096): one "stored" barrier each
 constexpr int PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 2 * PC_OUT_BYTES + 2 * PC_BIAS_BYTES +
-                        (2 * PC_STAGES + 4 + PC_MAX_TILES) * 8 + 16 + 1024;
+                        (3 * PC_STAGES + 4 + PC_MAX_TILES) * 8 + 16 + 1024;
 
 // Operand addressing. A layer is a grid of tile BRGEMMs on block-packed operands (GemmArgs::grid_*; 1 x 1 with
 // m = 256 r, k = K is the flat case): all three operands are described by 4-D tensor maps whose box gathers one
@@ -50,11 +50,13 @@ constexpr int PC_SMEM = PC_STAGES * PC_STAGE_BYTES + 2 * PC_OUT_BYTES + 2 * PC_B
 //   W (n in block | column block | k in block | batch element): box (min(n,64), 64/min(n,64), min(k,64), 64/min(k,64))
 //   C (n in block | column block | row in block | row block):   box (min(n,64), 64/min(n,64), min(m,128), 128/min(m,128))
 // so shared memory always receives the canonical K-major (X) / MN-major (W) SWIZZLE_128B tiles the MMA descriptors
-// expect, whatever the tiling of the caller. VNNI-2 weights ([k/2][n][2], the reference's default bf16 layout) are not
-// a canonical UMMA layout and TMA cannot de-interleave 2-byte elements: in the <VNNI = true> instantiation eight
-// converter warps per CTA fetch the weight rows with 16-byte global loads, split the k pairs in registers
-// (2 x LDG.128 -> 8 PRMT -> 2 x STS.128) and write the swizzled tile themselves - no extra pass through HBM, no extra
-// shared-memory traffic; they arrive on the same "full" barrier the activations' TMA bytes are counted on.
+// expect, whatever the tiling of the caller. 32-wide blocks (the reference's default --tiles=32,32,32) have 64-byte
+// innermost extents, which TMA would pad to one 128-byte line each under SWIZZLE_128B (scripts/probes/tma_box_probe.cu):
+// those operands use SWIZZLE_64B sub-tiles instead (NARROW instantiations). VNNI-2 weights ([k/2][n][2], the reference's
+// default bf16 layout) are not a canonical UMMA layout and TMA cannot de-interleave 2-byte elements: in the
+// <VNNI = true> instantiations TMA drops the raw rows into the ring slot and eight converter warps per CTA rewrite them
+// IN PLACE into the swizzled MN-major tile (LDS.128 -> 4 PRMT + 2 SHFL -> STS.128) - no extra pass through HBM, no
+// extra shared memory; they arrive on the same "full" barrier the activations' TMA bytes are counted on.
 struct alignas(128) PcLayer {
   CUtensorMap tmX;          // activations, box = 64 k x 128 rows
   CUtensorMap tmW;          // flat weights, box = 64 n x 64 k (unused for VNNI-2 weights)
@@ -114,7 +116,8 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
   const uint32_t acc_full = bar_base + 2 * PC_STAGES * 8;                  // [2] per CTA: accumulator complete
   const uint32_t acc_free = acc_full + 16;                                 // [2] leader's: both epilogues have read it out
   const uint32_t tile_done = acc_free + 16;                                // [PC_MAX_TILES] per CTA: my rows of output tile j are stored
-  const uint32_t tmem_slot = tile_done + 8 * PC_MAX_TILES;
+  const uint32_t raw_full = tile_done + 8 * PC_MAX_TILES;                  // [PC_STAGES] per CTA (VNNI): my raw weight bytes have landed
+  const uint32_t tmem_slot = raw_full + 8 * PC_STAGES;
   uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
 
@@ -128,6 +131,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
       // weight tile is in place (one group of PC_CONV_WARPS warps per CTA handles a given k-block)
       ptx::mbar_init(full_bar + 8 * s, VNNI ? 1 + 2 * PC_CONV_WARPS : 1);
       ptx::mbar_init(empty_bar + 8 * s, 1);
+      ptx::mbar_init(raw_full + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(acc_full + 8 * b, 1);
@@ -168,7 +172,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
         for (int l = 0; l < it.num_layers; ++l) {
           const PcLayer *L = cp.layers + it.layer0 + l;
           tensormap_acquire(&L->tmX);
-          if (!VNNI) tensormap_acquire(&L->tmW);
+          tensormap_acquire(&L->tmW);
           const int32_t total = L->total_iters, n_tiles = L->n_tiles;
           const int32_t lk = L->k, k_bstep = L->k_bstep, ln = L->n;
           const bool x64 = NARROW && L->x64 != 0, w64 = NARROW && L->w64 != 0;
@@ -190,7 +194,18 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
               ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
               // both CTAs' bytes: activations, plus the weights unless the converter warps deliver them
               if (peer == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, VNNI ? 2 * A_STAGE_BYTES : 2 * PC_STAGE_BYTES);
-              if (!VNNI) {
+              if (VNNI) {
+                // VNNI-2 weights: the raw [k/2][n][2] rows of my 128 columns go into the slot as they are (no swizzle),
+                // counted on MY raw barrier; my converter warps rewrite them in place
+                ptx::mbar_arrive_expect_tx(raw_full + 8 * s, PC_W_CHUNKS * B_CHUNK_BYTES);
+#pragma unroll
+                for (int c = 0; c < PC_W_CHUNKS; ++c) {
+                  const uint32_t dst = smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES;
+                  // (element pair in block, column block, k pair in batch element, batch element)
+                  if (hints) ptx::tma_load_4d_hint(dst, &L->tmW, raw_full + 8 * s, 2 * wn[c], wj[c], c0 >> 1, c1, pol_first);
+                  else ptx::tma_load_4d(dst, &L->tmW, raw_full + 8 * s, 2 * wn[c], wj[c], c0 >> 1, c1);
+                }
+              } else {
                 // the weights depend on nothing: their boxes go out before any wait for the previous layer
 #pragma unroll
                 for (int c = 0; c < PC_W_CHUNKS; ++c) {
@@ -414,122 +429,62 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
     }
     if (issuer) ptx::bulk_wait_group<0>();
   } else if (VNNI) {
-    // ===== VNNI-2 weight converters (both CTAs): global [k/2][n][2] -> registers -> swizzled MN-major tile =====
-    // Group g (PC_CONV_WARPS warps) takes the k-blocks whose running index q is g mod PC_CONV_GROUPS, so that
-    // PC_CONV_GROUPS k-blocks of weight loads are in flight per CTA. Per k-block a group moves this CTA's 128 weight
-    // columns x 64 k = 2 chunks x 32 k-pair rows x 64 columns x 2: thread t handles 16-byte chunk (t & 7) of rows
-    // (t >> 3) and (t >> 3) + 16 of both chunks - four units of 32 contiguous global bytes (8 columns x 2 k).
+    // ===== VNNI-2 weight converters (both CTAs): raw [k/2][n][2] rows in the slot -> swizzled MN-major tile, in place =====
+    // The producer's TMA boxes deliver, per 64-column chunk, 32 k-pair rows of 256 bytes (64 columns x 2 k). Row R holds
+    // exactly the bytes of the swizzled tile's rows 2R and 2R + 1 (128 bytes each), so the rewrite is in place: one
+    // warp-wide 16-byte load covers two whole raw rows; lanes 2p, 2p + 1 hold columns 8p .. 8p + 3 / 8p + 4 .. 8p + 7 (both
+    // k of the pair), swap halves with one shuffle, and the even lane writes the 16-byte chunk of the even k row, the odd
+    // lane that of the odd k row (chunk index XOR row & 7: the SWIZZLE_128B pattern TMA would have produced for flat
+    // weights). Group g (PC_CONV_WARPS warps) takes the k-blocks with running index q = g mod PC_CONV_GROUPS.
+    // (First version: the converters fetched the weights themselves with 16-byte global loads - 1720 clk per k-block
+    // however many loads were in flight: the LSU path cannot keep as many bytes outstanding as TMA.)
     const int cw = warp - 6;
     const int group = cw / PC_CONV_WARPS;
-    // Lane mapping: one warp-wide 16-byte load covers two whole k-pair rows of a chunk (2 x 256 contiguous bytes: every
-    // 32-byte sector is consumed by one instruction - with 32 bytes per lane each load used half of every sector it
-    // touched and the weights crossed the L2 -> SM path twice). Lanes 2p, 2p + 1 hold columns 8p .. 8p + 3 / 8p + 4 .. 8p + 7
-    // of one row (both k of the pair); they swap halves with one shuffle so that the even lane owns the 8 columns of the
-    // even k (one 16-byte chunk of swizzled row 2R) and the odd lane those of the odd k (row 2R + 1).
     const int wq = cw % PC_CONV_WARPS;                // warp within the group
     const int row_sub = lane >> 4, g8 = (lane & 15) >> 1, half = lane & 1;
     const uint32_t leader_full = ptx::mapa(full_bar, 0);
-    const uint64_t pol_first = ptx::l2_policy_evict_first();
-    // Position in the CTA's flattened k-block sequence (item, layer, tile, k-block) plus what the address needs. Every
-    // thread keeps TWO k-blocks of loads in flight (the one it converts next and the one after: registers va / vb), so
-    // a CTA has 2 x PC_CONV_GROUPS k-blocks = 64 KiB of weight loads outstanding - the converter is a latency pipeline
-    // (measured with one k-block per group in flight: 2100 clk per k-block against 1250 for the TMA-fed flat kernel).
-    struct Cursor {
-      int item, l;
-      int32_t j, i;
-      uint32_t q;
-      bool valid;
-      const char *Wb;
-      int32_t ln, half_k, total, n_tiles, num_layers, layer0;
-      int64_t col_step, batch_step, ldb2, col_off[PC_W_CHUNKS];
-    };
-    auto load_tile = [&](Cursor &c) {
+    constexpr int UNITS = 4 * PC_W_CHUNKS;            // 16-byte pieces per thread and k-block: 4 row groups x 2 chunks
+    uint32_t q = 0;                                   // running k-block index of this CTA (all items / layers / tiles)
+    for (int item = pair; item < cp.num_items; item += num_pairs) {
+      const PcItem it = cp.items[item];
+      for (int l = 0; l < it.num_layers; ++l) {
+        const PcLayer *L = cp.layers + it.layer0 + l;
+        const uint32_t kblocks = (uint32_t)(L->total_iters * L->n_tiles);
+        for (uint32_t e = 0; e < kblocks; ++e, ++q) {
+          if ((int)(q % PC_CONV_GROUPS) != group) continue;
+          const uint32_t s = q % PC_STAGES, ph = (q / PC_STAGES) & 1u;
+          ptx::mbar_wait(raw_full + 8 * s, ph);
+          uint4 v[UNITS];
 #pragma unroll
-      for (int ch = 0; ch < PC_W_CHUNKS; ++ch) {
-        const int32_t col = c.j * PC_BLOCK_N + (int32_t)peer * PC_HALF_N + ch * 64 + 8 * g8 + 4 * half;
-        c.col_off[ch] = (int64_t)(col / c.ln) * c.col_step + (int64_t)(col % c.ln) * 2;
-      }
-    };
-    auto load_layer = [&](Cursor &c) {
-      const PcLayer *L = cp.layers + c.layer0 + c.l;
-      c.Wb = static_cast<const char *>(L->W);
-      c.ln = L->n; c.half_k = L->k >> 1; c.total = L->total_iters; c.n_tiles = L->n_tiles;
-      c.col_step = L->w_col_step; c.batch_step = L->w_batch_step; c.ldb2 = 2 * L->w_ldb;
-      load_tile(c);
-    };
-    auto load_item = [&](Cursor &c) {
-      c.valid = c.item < cp.num_items;
-      if (!c.valid) return;
-      const PcItem it = cp.items[c.item];
-      c.layer0 = it.layer0; c.num_layers = it.num_layers;
-      c.l = 0; c.j = 0; c.i = 0;
-      load_layer(c);
-    };
-    auto step = [&](Cursor &c) {   // one k-block forward
-      ++c.q;
-      if (++c.i < c.total) return;
-      c.i = 0;
-      if (++c.j < c.n_tiles) { load_tile(c); return; }
-      c.j = 0;
-      if (++c.l < c.num_layers) { load_layer(c); return; }
-      c.item += num_pairs;
-      load_item(c);
-    };
-    auto advance = [&](Cursor &c) {   // to this group's next k-block
-      for (int n = 0; n < PC_CONV_GROUPS && c.valid; ++n) step(c);
-    };
-    constexpr int UNITS = 4 * PC_W_CHUNKS;            // 16-byte loads per thread and k-block: 4 row groups x 2 chunks
-    auto issue = [&](const Cursor &c, uint4 (&v)[UNITS]) {
+          for (int u = 0; u < UNITS; ++u) {
+            const uint32_t R = (uint32_t)((u & 3) * 8 + wq * 2 + row_sub);      // raw row = k pair of the k-block
+            const uint32_t src = smem_w + (s * PC_W_CHUNKS + (u >> 2)) * B_CHUNK_BYTES + R * 256u + (uint32_t)(lane & 15) * 16u;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "r"(src));
+          }
+          __syncwarp();                               // every lane has read its rows before any lane overwrites them
 #pragma unroll
-      for (int u = 0; u < UNITS; ++u) {
-        const int32_t kpg = c.i * 32 + (u & 3) * 8 + wq * 2 + row_sub;     // k-pair row within the whole reduction
-        const int32_t b = kpg / c.half_k, kp = kpg - b * c.half_k;
-        const char *src = c.Wb + 2 * (c.col_off[u >> 2] + (int64_t)b * c.batch_step + (int64_t)kp * c.ldb2);
-        v[u] = ptx::ldg_v4_hint(src, pol_first);
+          for (int u = 0; u < UNITS; ++u) {
+            // my 4 columns x (k even | k odd) -> 4 columns of k even (lo) and 4 columns of k odd (hi)
+            const uint32_t lo0 = __byte_perm(v[u].x, v[u].y, 0x5410), lo1 = __byte_perm(v[u].z, v[u].w, 0x5410);
+            const uint32_t hi0 = __byte_perm(v[u].x, v[u].y, 0x7632), hi1 = __byte_perm(v[u].z, v[u].w, 0x7632);
+            // the even lane keeps lo and needs its neighbour's lo; the odd lane keeps hi and needs its neighbour's hi
+            const uint32_t r0 = __shfl_xor_sync(0xffffffffu, half ? lo0 : hi0, 1);
+            const uint32_t r1 = __shfl_xor_sync(0xffffffffu, half ? lo1 : hi1, 1);
+            const uint32_t o0 = half ? r0 : lo0, o1 = half ? r1 : lo1, o2 = half ? hi0 : r0, o3 = half ? hi1 : r1;
+            const uint32_t krow = 2u * (uint32_t)((u & 3) * 8 + wq * 2 + row_sub) + (uint32_t)half;   // k row of the 64 x 64 chunk
+            const uint32_t base = smem_w + (s * PC_W_CHUNKS + (u >> 2)) * B_CHUNK_BYTES;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                         ::"r"(base + krow * 128u + (((uint32_t)g8 ^ (krow & 7u)) << 4)), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                         : "memory");
+          }
+          ptx::fence_proxy_async();                   // my shared-memory writes -> the async proxy (the pair's MMAs)
+          __syncwarp();
+          if (lane == 0) {
+            if (peer == 0) ptx::mbar_arrive(full_bar + 8 * s);
+            else ptx::mbar_arrive_remote(leader_full + 8 * s);
+          }
+        }
       }
-    };
-    auto finish = [&](const Cursor &c, uint4 (&v)[UNITS]) {
-      const uint32_t s = c.q % PC_STAGES, ph = (c.q / PC_STAGES) & 1u;
-      ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
-#pragma unroll
-      for (int u = 0; u < UNITS; ++u) {
-        // my 4 columns x (k even | k odd) -> 4 columns of k even (lo) and 4 columns of k odd (hi)
-        const uint32_t lo0 = __byte_perm(v[u].x, v[u].y, 0x5410), lo1 = __byte_perm(v[u].z, v[u].w, 0x5410);
-        const uint32_t hi0 = __byte_perm(v[u].x, v[u].y, 0x7632), hi1 = __byte_perm(v[u].z, v[u].w, 0x7632);
-        // the even lane keeps lo and needs its neighbour's lo; the odd lane keeps hi and needs its neighbour's hi
-        const uint32_t r0 = __shfl_xor_sync(0xffffffffu, half ? lo0 : hi0, 1);
-        const uint32_t r1 = __shfl_xor_sync(0xffffffffu, half ? lo1 : hi1, 1);
-        const uint32_t o0 = half ? r0 : lo0, o1 = half ? r1 : lo1, o2 = half ? hi0 : r0, o3 = half ? hi1 : r1;
-        const uint32_t krow = 2u * (uint32_t)((u & 3) * 8 + wq * 2 + row_sub) + (uint32_t)half;   // k row of the 64 x 64 chunk
-        const uint32_t base = smem_w + (s * PC_W_CHUNKS + (u >> 2)) * B_CHUNK_BYTES;
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
-                     ::"r"(base + krow * 128u + (((uint32_t)g8 ^ (krow & 7u)) << 4)), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
-                     : "memory");
-      }
-      ptx::fence_proxy_async();                 // my shared-memory writes -> the async proxy (the pair's MMAs)
-      __syncwarp();
-      if (lane == 0) {
-        if (peer == 0) ptx::mbar_arrive(full_bar + 8 * s);
-        else ptx::mbar_arrive_remote(leader_full + 8 * s);
-      }
-    };
-    Cursor cur;
-    cur.item = pair; cur.q = 0;
-    load_item(cur);
-    for (int n = 0; n < group && cur.valid; ++n) step(cur);   // this group's first k-block
-    uint4 va[UNITS], vb[UNITS];
-    if (cur.valid) issue(cur, va);
-    while (cur.valid) {
-      Cursor nxt = cur;
-      advance(nxt);
-      if (nxt.valid) issue(nxt, vb);
-      finish(cur, va);
-      cur = nxt;
-      if (!cur.valid) break;
-      advance(nxt);
-      if (nxt.valid) issue(nxt, va);
-      finish(cur, vb);
-      cur = nxt;
     }
   }
 
@@ -604,7 +559,14 @@ bool encode_layer_maps(PcLayer &pl, const KernelDesc &d, const GemmArgs &g, bool
     const uint32_t box[4] = {kx, k32 ? 1u : BLOCK_K / kx, rx, BLOCK_M / rx};
     if (!encode_map_nd(&pl.tmX, g.A, 4, dims, str, box, k32 ? 64 : 128)) return false;
   }
-  if (!vnni) {
+  if (vnni) {
+    // raw VNNI-2 rows: (element of the [n][2] row | column block | k pair | batch element); a box is 64 columns x 2 =
+    // 256 contiguous bytes per k pair (two column blocks of 32), 32 k pairs (two batch elements when k == 32); no swizzle
+    const uint32_t ex = 2 * nx, kpx = kx / 2;
+    const uint64_t dims[4] = {2 * (uint64_t)d.n, gk, (uint64_t)d.k / 2, nb}, str[3] = {b_step, 2 * (uint64_t)d.ldb, sb};
+    const uint32_t box[4] = {ex, 128 / ex, kpx, 32 / kpx};
+    if (!encode_map_nd(&pl.tmW, g.B, 4, dims, str, box, 0)) return false;
+  } else {
     // k rows of one box: all 64 of the k-block (for k == 32: both batch elements, 32 rows each)
     const uint64_t dims[4] = {(uint64_t)d.n, gk, (uint64_t)d.k, nb}, str[3] = {b_step, (uint64_t)d.ldb, sb};
     const uint32_t box[4] = {nx, n32 ? 1u : 64 / nx, kx, BLOCK_K / kx};
