@@ -133,7 +133,7 @@ def cfg4(pk):
     return head
 
 
-def reference_stream(pk):
+def reference_stream(pk, tiles=(32, 32, 32), vnni=True):
     """The reference's DEFAULT benchmark call stream (benchmarks/config/omp/mlir-bf16.json:37: --tiles=32,32,32 --vnni=2):
     768 xsmm_fused_brgemm_invoke calls of a 32x32x32 x batch-32 VNNI-2 BRGEMM per forward pass on block-packed operands,
     captured and replayed like bench.py's headline. Reports the throughput of that stream and which kernel ran it."""
@@ -150,14 +150,14 @@ def reference_stream(pk):
 
     stream = torch.cuda.current_stream()
     xsmm.set_stream(stream.cuda_stream)
-    probe = bench.MlpWorkload(256, to_dev(x), [to_dev(W) for W in Ws], [to_dev(b) for b in bs], tiles=(32, 32, 32),
-                              vnni=True, max_sets=1)
+    probe = bench.MlpWorkload(256, to_dev(x), [to_dev(W) for W in Ws], [to_dev(b) for b in bs], tiles=tiles,
+                              vnni=vnni, max_sets=1)
     probe.rotations(1)
     torch.cuda.synchronize()
     fused = "pair" in xsmm.last_kernel() or "chain" in xsmm.last_kernel()
     del probe
     # one launch per tile invoke (no regrouping): keep the rotation short, it is ~2 ms per forward pass
-    wl = bench.MlpWorkload(256, to_dev(x), [to_dev(W) for W in Ws], [to_dev(b) for b in bs], tiles=(32, 32, 32), vnni=True,
+    wl = bench.MlpWorkload(256, to_dev(x), [to_dev(W) for W in Ws], [to_dev(b) for b in bs], tiles=tiles, vnni=vnni,
                            max_sets=None if fused else 4)
     wl.rotations(2)
     torch.cuda.synchronize()
@@ -175,8 +175,11 @@ def reference_stream(pk):
     s = wl.num_sets - 1
     rel = bench.rel_err(wl.output(s).cpu().numpy().view(np.uint16), np.roll(bench.oracle_forward(x, Ws, bs), s, 0))
     flops = wl.cfg.flops()
-    return {"config": "reference default stream: MLP 3x1024^2 bf16 batch 256, --tiles=32,32,32 --vnni=2 "
-                      "(768 invokes of 32x32x32 x batch 32 per forward pass, block-packed, VNNI-2 weights)",
+    bn, bk, bc = tiles
+    invokes = 3 * (256 // bn) * (1024 // bk)
+    return {"config": f"{'reference default stream: ' if tiles == (32, 32, 32) and vnni else ''}MLP 3x1024^2 bf16 batch 256, "
+                      f"--tiles={bn},{bk},{bc}{' --vnni=2' if vnni else ''} ({invokes} invokes of {bn}x{bk}x{bc} x batch "
+                      f"{1024 // bc} per forward pass, block-packed{', VNNI-2 weights' if vnni else ''})",
             "kernel": xsmm.last_kernel(), "seconds_per_forward": t, "gflops": flops / t / 1e9,
             "kernel_launches_per_forward": launches, "operand_sets": wl.num_sets, "rel_err_vs_oracle": rel,
             "roofline": {"bound": "hbm", "achieved": 7346176 / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
@@ -269,6 +272,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=None)
     ap.add_argument("--only", default="")
+    ap.add_argument("--tiles", default="32,32,32")
+    ap.add_argument("--vnni", type=int, default=1)
     args = ap.parse_args()
     pk = peaks()
     torch.cuda.set_device(0)
@@ -285,7 +290,7 @@ def main():
     if on("cfg4"):
         rows.extend(eltwise(pk))
     if on("refstream"):
-        rows.append(reference_stream(pk))
+        rows.append(reference_stream(pk, tuple(int(v) for v in args.tiles.split(",")), bool(args.vnni)))
     if on("pack"):
         rows.extend(pack(pk))
     if on("cfg5"):

@@ -15,8 +15,11 @@ from .pyoracle import (  # noqa: F401
     f32_to_bf16,
     fast_isa,
     fused_brgemm,
+    fused_brgemm_amx,
+    fused_brgemm_amx_grid,
     fused_brgemm_fast,
     gemm,
+    has_amx,
     lib,
     num_threads,
     set_acc_mode,

@@ -76,6 +76,10 @@ def lib(native: bool | None = None):
     L.xo_fused_brgemm_fast.argtypes = [i64] * 13 + [c_void_p] * 4 + [i64]
     L.xo_fused_brgemm_fast.restype = c_int
     L.xo_fast_isa.restype = c_int
+    L.xo_fused_brgemm_amx.argtypes = [i64] * 13 + [c_void_p] * 4 + [i64]
+    L.xo_fused_brgemm_amx.restype = c_int
+    L.xo_fused_brgemm_amx_grid.argtypes = [i64] * 13 + [c_void_p] * 4 + [i64] * 8
+    L.xo_fused_brgemm_amx_grid.restype = c_int
     L.ti_create.argtypes = [c_int, c_int, c_int]
     L.ti_create.restype = c_void_p
     L.ti_destroy.argtypes = [c_void_p]
@@ -141,8 +145,32 @@ def fused_brgemm_fast(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, gemm_fl
                                       binary_flags, binary_kind, _p(A), _p(B), _p(C), _p(D), batch) == 0
 
 
+def fused_brgemm_amx(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, gemm_flags, unary_kind, binary_flags,
+                     binary_kind, A, B_vnni2, C, D, batch) -> bool:
+    """AMX-BF16 tile kernel (tdpbf16ps) for a VNNI-2 packed B (gemm flag 2048) - the instruction and the weight layout
+    libxsmm's JIT uses on Sapphire Rapids and later. False when the build / host / kernel has no AMX or the shape is not
+    a multiple of 32 (caller falls back)."""
+    return lib().xo_fused_brgemm_amx(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, gemm_flags, unary_kind,
+                                     binary_flags, binary_kind, _p(A), _p(B_vnni2), _p(C), _p(D), batch) == 0
+
+
+def fused_brgemm_amx_grid(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, gemm_flags, unary_kind, binary_flags,
+                          binary_kind, A, B_vnni2, C, D, batch, grid_n, grid_k, a_step, b_step, c_step_n, c_step_k,
+                          d_step) -> bool:
+    """A whole layer as the reference runs it: grid_n x grid_k tile BRGEMMs (AMX-BF16) on block-packed operands, the
+    (iN, iK) loop nest shared by the OpenMP threads (scf.parallel in the reference)."""
+    return lib().xo_fused_brgemm_amx_grid(dtype, m, n, k, lda, ldb, ldc, stride_a, stride_b, gemm_flags, unary_kind,
+                                          binary_flags, binary_kind, _p(A), _p(B_vnni2), _p(C), _p(D), batch, grid_n,
+                                          grid_k, a_step, b_step, c_step_n, c_step_k, d_step) == 0
+
+
 def fast_isa() -> str:
-    return {2: "AVX512-BF16 vdpbf16ps 8x32 microkernel", 1: "compiler-vectorised f32 FMA"}[lib().xo_fast_isa()]
+    return {3: "AMX-BF16 tdpbf16ps 32x32 tile block", 2: "AVX512-BF16 vdpbf16ps 8x32 microkernel",
+            1: "compiler-vectorised f32 FMA"}[lib().xo_fast_isa()]
+
+
+def has_amx() -> bool:
+    return lib().xo_fast_isa() == 3
 
 
 def unary(kind, dtype, m, n, ldi, ldo, flags, inp, out):

@@ -74,6 +74,22 @@ int xo_binary(int64_t kind, int64_t dtype, int64_t m, int64_t n, int64_t ldl,
               int64_t ldr, int64_t ldo, int64_t flags, const void *lhs,
               const void *rhs, void *out);
 
+/* xsmm_oracle_fast.c: vectorised / AMX variants for the timed CPU arm; 0 on success, -1 if unsupported here */
+int xo_fused_brgemm_fast(int64_t dtype, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc,
+                         int64_t stride_a, int64_t stride_b, int64_t gemm_flags, int64_t unary_kind,
+                         int64_t binary_flags, int64_t binary_kind, const void *A, const void *B, void *C,
+                         const void *D, int64_t batch);
+int xo_fused_brgemm_amx(int64_t dtype, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc,
+                        int64_t stride_a, int64_t stride_b, int64_t gemm_flags, int64_t unary_kind,
+                        int64_t binary_flags, int64_t binary_kind, const void *A, const void *B, void *C,
+                        const void *D, int64_t batch);
+int xo_fused_brgemm_amx_grid(int64_t dtype, int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc,
+                             int64_t stride_a, int64_t stride_b, int64_t gemm_flags, int64_t unary_kind,
+                             int64_t binary_flags, int64_t binary_kind, const void *A, const void *B, void *C, const void *D,
+                             int64_t batch, int64_t grid_n, int64_t grid_k, int64_t a_step, int64_t b_step, int64_t c_step_n,
+                             int64_t c_step_k, int64_t d_step);
+int xo_fast_isa(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -89,3 +89,16 @@ def _check_fast_kernel():
         np.testing.assert_allclose(f, r, rtol=1e-2, atol=1e-2 * np.abs(r).max())
     # unsupported shapes are refused, not mis-computed
     assert not oracle.fused_brgemm_fast(2, 7, n, k, k, n, n, 0, 0, 4, 5, 4, 1, A, B, c_fast, bias, 1)
+    # the AMX-BF16 tile kernel (VNNI-2 packed B), where the build and the host have AMX
+    if oracle.has_amx():
+        Bv = np.zeros((batch, k // 2, n, 2), np.uint16)
+        for b in range(batch):
+            oracle.unary(28, 2, k, n, n, n, 0, B[b], Bv[b])
+        for gflags in (4, 0):
+            C0 = oracle.f32_to_bf16(rng.uniform(-1, 1, (m, n)).astype(np.float32))
+            c_ref, c_amx = C0.copy(), C0.copy()
+            oracle.fused_brgemm(2, m, n, k, k, n, n, m * k, k * n, gflags, 0, 5, 4, 1, A, B, c_ref, bias, batch)
+            assert oracle.fused_brgemm_amx(2, m, n, k, k, n, n, m * k, k * n, gflags | 2048, 5, 4, 1, A, Bv, c_amx, bias, batch)
+            r, f = oracle.bf16_to_f32(c_ref), oracle.bf16_to_f32(c_amx)
+            np.testing.assert_allclose(f, r, rtol=1e-2, atol=1e-2 * np.abs(r).max())
+        assert not oracle.fused_brgemm_amx(2, m, n, k, k, n, n, 0, 0, 4, 5, 4, 1, A, B, c_fast, bias, 1)   # flat B: refused
