@@ -87,11 +87,12 @@ struct PcParams {
   const PcItem *items;
   int32_t num_items;
   int32_t l2_hints;            // L2 eviction-priority hints on the TMA loads / stores (TPP_XSMM_CHAIN_PAIR_HINTS=0: off)
+  int32_t debug;               // TPP_XSMM_PAIR_DEBUG (timing experiments only, results are wrong): 1 = converters skip the
+                               // rewrite, 2 = converters skip the proxy fence
   unsigned long long *trace;   // TPP_XSMM_TC_TRACE=4: clock stamps of each CTA's first item (nullptr in normal runs)
 };
-constexpr int PC_CONV_GROUPS = 2;                     // converter warp groups (VNNI): group g takes k-blocks q % 2 == g
-constexpr int PC_CONV_WARPS = 4;                      // warps per group: 128 threads x 4 units of 32 bytes = 16 KiB
-constexpr int PC_THREADS_VNNI = NUM_THREADS + 32 * PC_CONV_GROUPS * PC_CONV_WARPS;   // 448
+constexpr int PC_CONV_WARPS = 8;                      // converter warps (VNNI): 256 threads x 4 pieces of 16 bytes = 16 KiB per k-block
+constexpr int PC_THREADS_VNNI = NUM_THREADS + 32 * PC_CONV_WARPS;   // 448
 __device__ __forceinline__ void pc_stamp(const PcParams &cp, int slot) {
   if (cp.trace) cp.trace[(size_t)blockIdx.x * PC_TRACE_SLOTS + slot] = clock64();
 }
@@ -127,8 +128,8 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < PC_STAGES; ++s) {
-      // VNNI: besides the producer's expect_tx arrival, the converter warps of BOTH CTAs arrive once their half of the
-      // weight tile is in place (one group of PC_CONV_WARPS warps per CTA handles a given k-block)
+      // VNNI: besides the producer's expect_tx arrival, the converter warps of BOTH CTAs arrive once their part of the
+      // weight tile is in place
       ptx::mbar_init(full_bar + 8 * s, VNNI ? 1 + 2 * PC_CONV_WARPS : 1);
       ptx::mbar_init(empty_bar + 8 * s, 1);
       ptx::mbar_init(raw_full + 8 * s, 1);
@@ -273,8 +274,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
             const uint32_t acc = tmem_acc + buf * PC_BLOCK_N;
             if (t < 12) pc_stamp(cp, 4 * t);
             for (int32_t i = 0; i < total; ++i) {
-              if (VNNI) ptx::mbar_wait_cluster(full_bar + 8 * s, ph);   // the peer's converter warps arrive remotely
-              else ptx::mbar_wait(full_bar + 8 * s, ph);
+              ptx::mbar_wait(full_bar + 8 * s, ph);
               ptx::tc_fence_after_sync();
               const uint32_t a_addr = smem_a + s * A_STAGE_BYTES;
               const uint32_t b_addr = smem_w + s * PC_W_CHUNKS * B_CHUNK_BYTES;
@@ -435,15 +435,13 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
     // warp-wide 16-byte load covers two whole raw rows; lanes 2p, 2p + 1 hold columns 8p .. 8p + 3 / 8p + 4 .. 8p + 7 (both
     // k of the pair), swap halves with one shuffle, and the even lane writes the 16-byte chunk of the even k row, the odd
     // lane that of the odd k row (chunk index XOR row & 7: the SWIZZLE_128B pattern TMA would have produced for flat
-    // weights). Group g (PC_CONV_WARPS warps) takes the k-blocks with running index q = g mod PC_CONV_GROUPS.
+    // weights). All PC_CONV_WARPS warps share every k-block (4 rows each): the rewrite sits on the ring's round trip.
     // (First version: the converters fetched the weights themselves with 16-byte global loads - 1720 clk per k-block
     // however many loads were in flight: the LSU path cannot keep as many bytes outstanding as TMA.)
-    const int cw = warp - 6;
-    const int group = cw / PC_CONV_WARPS;
-    const int wq = cw % PC_CONV_WARPS;                // warp within the group
+    const int cw = warp - 6;                          // 0 .. PC_CONV_WARPS - 1
     const int row_sub = lane >> 4, g8 = (lane & 15) >> 1, half = lane & 1;
     const uint32_t leader_full = ptx::mapa(full_bar, 0);
-    constexpr int UNITS = 4 * PC_W_CHUNKS;            // 16-byte pieces per thread and k-block: 4 row groups x 2 chunks
+    constexpr int UNITS = 2 * PC_W_CHUNKS;            // 16-byte pieces per thread and k-block: 2 row groups x 2 chunks
     uint32_t q = 0;                                   // running k-block index of this CTA (all items / layers / tiles)
     for (int item = pair; item < cp.num_items; item += num_pairs) {
       const PcItem it = cp.items[item];
@@ -451,14 +449,21 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
         const PcLayer *L = cp.layers + it.layer0 + l;
         const uint32_t kblocks = (uint32_t)(L->total_iters * L->n_tiles);
         for (uint32_t e = 0; e < kblocks; ++e, ++q) {
-          if ((int)(q % PC_CONV_GROUPS) != group) continue;
           const uint32_t s = q % PC_STAGES, ph = (q / PC_STAGES) & 1u;
-          ptx::mbar_wait(raw_full + 8 * s, ph);
+          if (lane == 0) ptx::mbar_wait(raw_full + 8 * s, ph);   // one poller per warp
+          __syncwarp();
+          if (cp.debug & 1) {
+            if (lane == 0) {
+              if (peer == 0) ptx::mbar_arrive(full_bar + 8 * s);
+              else ptx::mbar_arrive_remote_relaxed(leader_full + 8 * s);
+            }
+            continue;
+          }
           uint4 v[UNITS];
 #pragma unroll
           for (int u = 0; u < UNITS; ++u) {
-            const uint32_t R = (uint32_t)((u & 3) * 8 + wq * 2 + row_sub);      // raw row = k pair of the k-block
-            const uint32_t src = smem_w + (s * PC_W_CHUNKS + (u >> 2)) * B_CHUNK_BYTES + R * 256u + (uint32_t)(lane & 15) * 16u;
+            const uint32_t R = (uint32_t)((u & 1) * 16 + cw * 2 + row_sub);     // raw row = k pair of the k-block
+            const uint32_t src = smem_w + (s * PC_W_CHUNKS + (u >> 1)) * B_CHUNK_BYTES + R * 256u + (uint32_t)(lane & 15) * 16u;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "r"(src));
           }
           __syncwarp();                               // every lane has read its rows before any lane overwrites them
@@ -471,17 +476,17 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
             const uint32_t r0 = __shfl_xor_sync(0xffffffffu, half ? lo0 : hi0, 1);
             const uint32_t r1 = __shfl_xor_sync(0xffffffffu, half ? lo1 : hi1, 1);
             const uint32_t o0 = half ? r0 : lo0, o1 = half ? r1 : lo1, o2 = half ? hi0 : r0, o3 = half ? hi1 : r1;
-            const uint32_t krow = 2u * (uint32_t)((u & 3) * 8 + wq * 2 + row_sub) + (uint32_t)half;   // k row of the 64 x 64 chunk
-            const uint32_t base = smem_w + (s * PC_W_CHUNKS + (u >> 2)) * B_CHUNK_BYTES;
+            const uint32_t krow = 2u * (uint32_t)((u & 1) * 16 + cw * 2 + row_sub) + (uint32_t)half;   // k row of the 64 x 64 chunk
+            const uint32_t base = smem_w + (s * PC_W_CHUNKS + (u >> 1)) * B_CHUNK_BYTES;
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
                          ::"r"(base + krow * 128u + (((uint32_t)g8 ^ (krow & 7u)) << 4)), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
                          : "memory");
           }
-          ptx::fence_proxy_async();                   // my shared-memory writes -> the async proxy (the pair's MMAs)
+          if (!(cp.debug & 2)) ptx::fence_proxy_async();   // my shared-memory writes -> the async proxy (the pair's MMAs)
           __syncwarp();
           if (lane == 0) {
             if (peer == 0) ptx::mbar_arrive(full_bar + 8 * s);
-            else ptx::mbar_arrive_remote(leader_full + 8 * s);
+            else ptx::mbar_arrive_remote_relaxed(leader_full + 8 * s);
           }
         }
       }
@@ -703,6 +708,8 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   cp.num_items = (int32_t)items;
   static const bool hints_on = [] { const char *e = getenv("TPP_XSMM_CHAIN_PAIR_HINTS"); return !(e && e[0] == '0'); }();
   cp.l2_hints = hints_on ? 1 : 0;
+  static const int debug = [] { const char *e = getenv("TPP_XSMM_PAIR_DEBUG"); return e ? atoi(e) : 0; }();
+  cp.debug = debug;
   cp.trace = nullptr;
   static const bool pc_trace_on = [] { const char *e = getenv("TPP_XSMM_TC_TRACE"); return e && atoi(e) == 4; }();
   if (pc_trace_on) {

@@ -63,6 +63,11 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_bar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// same without the cluster-scope release: the arrival only signals; data the waiter's MMAs depend on was made visible to the
+// async proxy by the writer's own fence.proxy.async (the pattern CUTLASS' ClusterBarrier::arrive(cta_id) uses)
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 // 16 bytes into a peer CTA's shared memory; their arrival is counted (complete_tx, 16 bytes) on an mbarrier of that
 // same peer CTA - the receiver needs no release/acquire round trip, it waits on its own barrier like for a TMA load
 __device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint32_t cluster_bar, uint32_t a, uint32_t b,
