@@ -327,6 +327,37 @@ def reference_main(args, rank):
     return 0
 
 
+def run_standin():
+    """tpp_mlir_b200/lib/tpp_run_standin: the native program that executes what `mlir-gen ... | tpp-run -n N` would
+    (dispatch hoisted, warm-up clamp, N iterations between perf_start_timer / perf_stop_timer, SURVEY.md Appendix B
+    invoke stream), for the reference's default tiling and the GPU tiling, in the three operand-residency modes."""
+    import subprocess
+
+    from tpp_mlir_b200 import _build
+
+    exe = _build.standin_path()
+    if not os.path.exists(exe):
+        return {"error": "tpp_run_standin is not built"}
+    out = []
+    for tiles, vnni, label in (("32,32,32", 2, "reference default (benchmarks/config/omp/mlir-bf16.json:37)"),
+                               ("256,1024,1024", 0, "GPU tiling (SURVEY.md Appendix B)")):
+        for mode, n in (("strict", 3 if tiles == "32,32,32" else 20), ("device", 10 if tiles == "32,32,32" else 300),
+                        ("graph", 300)):
+            cmd = [exe, "--batch", "256", "--layers", "1024,1024,1024,1024", "--tiles", tiles, "--vnni", str(vnni), "-n",
+                   str(n), "--seed", "123", "--mode", mode]
+            try:
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+                row = json.loads(r.stdout.strip().splitlines()[-1])
+            except Exception as e:   # a side measurement: report, do not fail the headline
+                row = {"mode": mode, "error": repr(e)}
+            row["tiles"], row["vnni"], row["config"] = tiles, vnni, label
+            out.append(row)
+    return {"what": "mean seconds per forward pass as tpp-run would print it; strict = plain host pointers (an unmodified "
+                    "tpp-run), device = arguments registered on the GPU (patches/0004), graph = + the timed body "
+                    "captured and replayed (patches/0005); ONE forward pass on ONE set of buffers, sequential",
+            "runs": out}
+
+
 class MlpWorkload:
     """`num_sets` operand sets of the 3-layer MLP for `m` batch rows on this rank, the dispatched handles and the
     native replay loop over them. Set s reads the rank's input rolled by s rows (so every set has its own answer:
@@ -641,6 +672,7 @@ def main():
                              "frac": tf5 / n_gpus / pk_["bf16_tflops"]}}
             del wl5
         if n_gpus == 1:
+            extras["tpp_run_standin"] = run_standin()
             for name, fn in (("cfg2_brgemm_1024x16", bench_configs.cfg2), ("cfg4_vnni2_pack_4096", bench_configs.cfg4),
                              ("reference_default_stream", bench_configs.reference_stream)):
                 try:

@@ -1,6 +1,8 @@
 """GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle and the
 reference's known-answer vectors. Tolerances (BASELINE.json north_star): bf16 1e-2 rel,
 f32 1e-5 rel, bit-exact for data movement (identity / zero / transpose / VNNI)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -544,6 +546,32 @@ def test_single_blocked_layer_runs_on_the_pair_kernel():
     xsmm.sync()
     assert_close(BF16, _blocked_out(cfg, r), want)
     g.destroy()
+
+
+@pytest.mark.parametrize("tiles,vnni", [("32,32,32", 2), ("64,64,64", 0), ("256,256,256", 0)])
+def test_tpp_run_standin_modes_agree(tiles, vnni):
+    """The native tpp-run stand-in (csrc/harness/tpp_run_standin.cpp) in its three residency modes - plain host pointers,
+    device arguments, captured graph - computes the same forward pass (checksums within the bf16 tolerance) and the
+    graph mode runs it as one fused launch."""
+    import json
+    import subprocess
+
+    from tpp_mlir_b200 import _build
+
+    exe = _build.standin_path()
+    if not os.path.exists(exe):
+        exe = _build.build_standin()
+    rows = {}
+    for mode in ("strict", "device", "graph"):
+        r = subprocess.run([exe, "--batch", "256", "--layers", "256,512,256", "--tiles", tiles, "--vnni", str(vnni), "-n", "2",
+                            "--mode", mode], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        rows[mode] = json.loads(r.stdout.strip().splitlines()[-1])
+    ref = rows["strict"]["checksum"]
+    assert ref > 0
+    for mode in ("device", "graph"):
+        assert abs(rows[mode]["checksum"] - ref) <= 1e-2 * abs(ref), rows
+    assert "pair256x256" in rows["graph"]["kernel"] or "chain" in rows["graph"]["kernel"], rows["graph"]
 
 
 def test_perf_timer_includes_async_launches():

@@ -99,6 +99,28 @@ def build_replay(force: bool = False) -> str:
     return so
 
 
+STANDIN_NAME = "tpp_run_standin"
+
+
+def standin_path() -> str:
+    return os.path.join(LIBDIR, STANDIN_NAME)
+
+
+def build_standin(force: bool = False) -> str:
+    """tpp_run_standin (csrc/harness/tpp_run_standin.cpp): what `mlir-gen ... | tpp-run -n N` executes, as a native
+    program that links only the C-ABI library."""
+    src = os.path.join(CSRC, "harness", "tpp_run_standin.cpp")
+    exe = standin_path()
+    lib = build()
+    if force or _stale(exe, [src, lib, os.path.join(ROOT, "include", "tpp_xsmm_abi.h")]):
+        cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+        cmd = [cxx, "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", exe, "-L", LIBDIR,
+               "-ltpp_xsmm_runner_utils", "-Wl,-rpath,$ORIGIN"]
+        subprocess.run(cmd, check=True)
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True))
     print(build_replay(force="--force" in sys.argv))
+    print(build_standin(force="--force" in sys.argv))
