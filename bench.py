@@ -376,6 +376,11 @@ class MlpWorkload:
         self.set_bytes = sum(w.numel() * 2 for w in w_dev) + sum(b.numel() * 2 for b in b_dev) + 4 * m * 1024 * 2
         items_per_set = max(m // ROW_BLOCK, 1)
         self.num_sets = max(L2_BYTES // self.set_bytes + 2, -(-2 * NUM_PAIRS // items_per_set), min_sets)
+        # a rotation is a whole number of rounds over the 74 CTA pairs (work items = 256-row blocks): no idle tail
+        import math
+
+        per_round = NUM_PAIRS // math.gcd(NUM_PAIRS, items_per_set)
+        self.num_sets = -(-self.num_sets // per_round) * per_round
         if max_sets:
             self.num_sets = min(self.num_sets, max_sets)
         wp = [harness.pack_weight(w, bk, bc) for w in w_dev]
