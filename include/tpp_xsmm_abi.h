@@ -67,8 +67,13 @@ enum {
   XSMM_UNARY_RELU = 5,
   XSMM_UNARY_VNNI2 = 28,
   XSMM_UNARY_TRANSPOSE = 29,
-  /* extension (not in the reference dialect): inverse of VNNI2, [K/2][N][2] -> [K][N] */
-  XSMM_UNARY_UNVNNI2_EXT = 1028
+  /* VNNI-4 pack [K][N] -> [K/4][N][4]: the libxsmm transform the reference runtime accepts (NORM_TO_VNNI4 in the
+   * list of runtime/Xsmm/XsmmRunnerUtils.cpp:45-54; the dialect has no op for it yet, mlir-gen --vnni=4 packs weights at
+   * compile time). 32 follows libxsmm's numbering after NORM_TO_VNNI2 = 28 / NORM_TO_NORMT = 29. */
+  XSMM_UNARY_VNNI4 = 32,
+  /* extensions (not in the reference dialect): inverses, [K/v][N][v] -> [K][N] */
+  XSMM_UNARY_UNVNNI2_EXT = 1028,
+  XSMM_UNARY_UNVNNI4_EXT = 1032
 };
 enum {
   XSMM_UNARY_FLAG_NONE = 0,

@@ -24,6 +24,7 @@ from .pyoracle import (  # noqa: F401
     num_threads,
     set_acc_mode,
     set_num_threads,
+    set_vnni_factor,
     tensor_pack,
     tensor_unpack,
     unary,

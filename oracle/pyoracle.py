@@ -73,6 +73,7 @@ def lib(native: bool | None = None):
     L.xo_set_acc_mode.argtypes = [c_int]
     L.xo_set_num_threads.argtypes = [c_int]
     L.xo_num_threads.restype = c_int
+    L.xo_set_vnni_factor.argtypes = [c_int]
     L.xo_fused_brgemm_fast.argtypes = [i64] * 13 + [c_void_p] * 4 + [i64]
     L.xo_fused_brgemm_fast.restype = c_int
     L.xo_fast_isa.restype = c_int
@@ -117,6 +118,11 @@ def set_acc_mode(mode: int) -> None:
 
 def set_num_threads(n: int) -> None:
     lib().xo_set_num_threads(n)
+
+
+def set_vnni_factor(v: int) -> None:
+    """VNNI blocking factor of B operands carrying gemm flag 2048: 2 (default) or 4 (mlir-gen --vnni=4 layouts)."""
+    lib().xo_set_vnni_factor(v)
 
 
 def num_threads() -> int:

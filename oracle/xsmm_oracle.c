@@ -22,7 +22,15 @@
 #define XO_BF16 2
 
 #define XO_BETA_0 4
-#define XO_B_VNNI 2048 /* row-major B operand is [K/2][N][2] */
+#define XO_B_VNNI 2048 /* row-major B operand is [K/v][N][v] */
+
+/* VNNI blocking factor v of B operands: what libxsmm_cpuid_dot_pack_factor(BF16) answers on the target - 2 on every x86
+ * part the reference's tests run on (and the default here), 4 where mlir-gen --vnni=4 applies
+ * (lib/TPP/Transforms/Utils/VNNIUtils.cpp:25-45; benchmarks/config/omp/mlir-bf16.json:65-125). Process-wide, like the
+ * cpuid answer it stands for. */
+static int64_t g_vnni_factor = 2;
+void xo_set_vnni_factor(int v) { g_vnni_factor = (v == 4) ? 4 : 2; }
+int xo_vnni_factor(void) { return (int)g_vnni_factor; }
 
 static int g_acc_mode = 0;
 static int g_threads = 0;
@@ -112,12 +120,13 @@ static void brgemm_rows_f32acc(int64_t dtype, int64_t i0, int64_t i1, int64_t j0
           memcpy(&brow[j], &u, 4);
         }
       } else {
-        /* B[b][p/2][j][p%2], ldb already divided by the VNNI factor
+        /* B[b][p/v][j][p%v], ldb already divided by the VNNI factor v
          * (ConvertLinalgToXsmm.cpp:1143-1148) */
+        const int64_t v = g_vnni_factor;
         const uint16_t *Bp = (const uint16_t *)B + b * stride_b +
-                             ((p / 2) * ldb + j0) * 2 + (p % 2);
+                             ((p / v) * ldb + j0) * v + (p % v);
         for (int64_t j = 0; j < n; ++j) {
-          uint32_t u = ((uint32_t)Bp[j * 2]) << 16;
+          uint32_t u = ((uint32_t)Bp[j * v]) << 16;
           memcpy(&brow[j], &u, 4);
         }
       }
@@ -138,7 +147,8 @@ static double brgemm_elem_f64(int64_t dtype, int64_t i, int64_t j, int64_t k,
   for (int64_t b = 0; b < batch; ++b)
     for (int64_t p = 0; p < k; ++p) {
       float a = ld(dtype, A, b * stride_a + i * lda + p);
-      float bb = vnni ? ld(dtype, B, b * stride_b + ((p / 2) * ldb + j) * 2 + p % 2)
+      const int64_t v = g_vnni_factor;
+      float bb = vnni ? ld(dtype, B, b * stride_b + ((p / v) * ldb + j) * v + p % v)
                       : ld(dtype, B, b * stride_b + p * ldb + j);
       acc += (double)a * (double)bb;
     }
@@ -267,6 +277,20 @@ int xo_unary(int64_t kind, int64_t dtype, int64_t m, int64_t n, int64_t ldi,
     for (int64_t p = 0; p < m; ++p)
       for (int64_t j = 0; j < n; ++j)
         dst[((p / 2) * ldo + j) * 2 + (p % 2)] = src[p * ldi + j];
+    return 0;
+  }
+  if (kind == 32 || kind == 1032) { /* norm -> VNNI4 ([m/4][n][4]) and its inverse (extension), m x n = the flat dims */
+    if (dtype != XO_BF16 || (m % 4) != 0)
+      return -1;
+    const uint16_t *src = (const uint16_t *)in;
+    uint16_t *dst = (uint16_t *)out;
+    for (int64_t p = 0; p < m; ++p)
+      for (int64_t j = 0; j < n; ++j) {
+        if (kind == 32)
+          dst[((p / 4) * ldo + j) * 4 + (p % 4)] = src[p * ldi + j];
+        else
+          dst[p * ldo + j] = src[((p / 4) * ldi + j) * 4 + (p % 4)];
+      }
     return 0;
   }
   if (kind == 1028) { /* extension: VNNI2 -> norm, m x n are the OUTPUT dims */

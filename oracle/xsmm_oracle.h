@@ -45,6 +45,9 @@ void xo_bf16_to_f32_array(const uint16_t *src, float *dst, int64_t n);
 void xo_set_acc_mode(int mode);
 /* number of OpenMP threads the oracle will use (1 when built without OpenMP) */
 int xo_num_threads(void);
+/* VNNI blocking factor of B operands with gemm flag 2048 (2 by default, 4 for mlir-gen --vnni=4 layouts) */
+void xo_set_vnni_factor(int v);
+int xo_vnni_factor(void);
 void xo_set_num_threads(int n);
 
 /* C (+)= sum_b A_b * B_b ; flags as received by the C-ABI (see tpp_xsmm_abi.h) */

@@ -102,3 +102,29 @@ def _check_fast_kernel():
             r, f = oracle.bf16_to_f32(c_ref), oracle.bf16_to_f32(c_amx)
             np.testing.assert_allclose(f, r, rtol=1e-2, atol=1e-2 * np.abs(r).max())
         assert not oracle.fused_brgemm_amx(2, m, n, k, k, n, n, 0, 0, 4, 5, 4, 1, A, B, c_fast, bias, 1)   # flat B: refused
+
+
+def test_vnni4_layout_of_the_oracle():
+    """VNNI-4 has no golden vector in the reference's tests (parity unpinned for this layout): the oracle is checked
+    against the layout definition itself, B[K/4][N][4] (lib/TPP/Transforms/Utils/VNNIUtils.cpp:75-78 with factor 4), and
+    the VNNI-4 BRGEMM against the flat one on the same numbers."""
+    rng = np.random.default_rng(44)
+    k, n, m = 16, 24, 8
+    B = rng.integers(0, 1 << 15, size=(k, n), dtype=np.uint16)
+    P = np.zeros((k // 4, n, 4), np.uint16)
+    assert oracle.unary(32, 2, k, n, n, n, 0, B, P) is None or True
+    np.testing.assert_array_equal(P, B.reshape(k // 4, 4, n).transpose(0, 2, 1))
+    back = np.zeros((k, n), np.uint16)
+    oracle.unary(1032, 2, k, n, n, n, 0, P, back)
+    np.testing.assert_array_equal(back, B)
+    A = oracle.f32_to_bf16(rng.uniform(-1, 1, (m, k)).astype(np.float32))
+    Bf = oracle.f32_to_bf16(rng.uniform(-1, 1, (k, n)).astype(np.float32))
+    Bv = np.ascontiguousarray(Bf.reshape(k // 4, 4, n).transpose(0, 2, 1))
+    c_flat, c_v4 = np.zeros((m, n), np.uint16), np.zeros((m, n), np.uint16)
+    oracle.brgemm(2, m, n, k, k, n, n, 0, 0, 4, A, Bf, c_flat, 1)
+    oracle.set_vnni_factor(4)
+    try:
+        oracle.brgemm(2, m, n, k, k, n, n, 0, 0, 4 | 2048, A, Bv, c_v4, 1)
+    finally:
+        oracle.set_vnni_factor(2)
+    np.testing.assert_array_equal(c_flat, c_v4)

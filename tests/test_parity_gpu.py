@@ -193,6 +193,60 @@ def test_vnni2_full_size_roundtrip(dev):
     np.testing.assert_array_equal(p[5, 17], x[10:12, 17])
 
 
+@pytest.mark.parametrize("shape", [(4, 1), (16, 16), (32, 32), (64, 1000), (132, 72), (1024, 1024)])
+@pytest.mark.parametrize("pad", [0, 8, 3])
+def test_vnni4_pack_unpack_bit_exact(shape, pad, dev, orc):
+    """VNNI-4 ([K][N] -> [K/4][N][4]; mlir-gen --vnni=4, benchmarks/config/omp/mlir-bf16.json:65-125; the transform kinds
+    runtime/Xsmm/XsmmRunnerUtils.cpp:45-54 lists): bit-exact against the oracle and against numpy's view of the layout."""
+    m, n = shape
+    rng = np.random.default_rng(m * n + pad)
+    inp = rnd(rng, BF16, (m, n + pad))
+    ldo = n + pad
+    g, o = np.zeros((m // 4, ldo, 4), np.uint16), np.zeros((m // 4, ldo, 4), np.uint16)
+    dev.unary(32, BF16, m, n, n + pad, ldo, 0, inp, 0, g, 0)
+    orc.unary(32, BF16, m, n, n + pad, ldo, 0, inp, 0, o, 0)
+    np.testing.assert_array_equal(g, o)
+    np.testing.assert_array_equal(g[:, :n, :], inp[:, :n].reshape(m // 4, 4, n).transpose(0, 2, 1))
+    back = np.zeros((m, n + pad), np.uint16)
+    dev.unary(1032, BF16, m, n, ldo, n + pad, 0, g, 0, back, 0)
+    np.testing.assert_array_equal(back[:, :n], inp[:, :n])
+
+
+def test_vnni4_full_size_roundtrip(dev):
+    rng = np.random.default_rng(4097)
+    x = rng.integers(0, 1 << 16, size=(4096, 4096), dtype=np.uint16)
+    p, back = np.zeros((1024, 4096, 4), np.uint16), np.zeros((4096, 4096), np.uint16)
+    dev.unary(32, BF16, 4096, 4096, 4096, 4096, 0, x, 0, p, 0)
+    dev.unary(1032, BF16, 4096, 4096, 4096, 4096, 0, p, 0, back, 0)
+    np.testing.assert_array_equal(back, x)
+    np.testing.assert_array_equal(p[5, 17], x[20:24, 17])
+
+
+@pytest.mark.parametrize("shape", [(32, 32, 32, 32), (64, 48, 96, 3), (256, 512, 256, 4), (256, 1024, 1024, 1)])
+def test_brgemm_bf16_vnni4_b(shape, dev, orc, monkeypatch):
+    """B operands packed with VNNI factor 4 ([K/4][N][4]): the factor is what libxsmm_cpuid_dot_pack_factor answers
+    (TPP_XSMM_VNNI=4), as in the reference, where the dispatch only carries the vnni_b flag."""
+    m, n, k, batch = shape
+    monkeypatch.setenv("TPP_XSMM_VNNI", "4")
+    oracle.set_vnni_factor(4)
+    try:
+        rng = np.random.default_rng(m + n + k)
+        A = rnd(rng, BF16, (batch, m, k))
+        Bflat = rnd(rng, BF16, (batch, k, n))
+        Bv = np.ascontiguousarray(Bflat.reshape(batch, k // 4, 4, n).transpose(0, 1, 3, 2))
+        g, o, ref = (np.zeros((m, n), np.uint16) for _ in range(3))
+        dev.brgemm(BF16, m, n, k, k, n, n, m * k, k * n, 4 | 2048, A, 0, Bv, 0, g, 0, batch)
+        orc.brgemm(BF16, m, n, k, k, n, n, m * k, k * n, 4 | 2048, A, 0, Bv, 0, o, 0, batch)
+        oracle.set_vnni_factor(2)
+        orc.brgemm(BF16, m, n, k, k, n, n, m * k, k * n, 4, A, 0, Bflat, 0, ref, 0, batch)   # the flat form of the same math
+        np.testing.assert_array_equal(o, ref)
+        assert_close(BF16, g, o)
+        if m * n * k * batch >= 1 << 21:
+            assert dev.kernels[-1] == "vnni4_unpack+brgemm_tc_bf16", dev.kernels[-1]
+    finally:
+        oracle.set_vnni_factor(2)
+
+
 # ---- 4. BRGEMM family ---------------------------------------------------------------------------
 def run_brgemm_pair(dev, orc, dtype, m, n, k, batch, *, lda=None, ldb=None, ldc=None, sa=None, sb=None, flags=4,
                     vnni=False, fused=None, seed=0, lo=-1.0, hi=1.0):
@@ -572,6 +626,62 @@ def test_tpp_run_standin_modes_agree(tiles, vnni):
     for mode in ("device", "graph"):
         assert abs(rows[mode]["checksum"] - ref) <= 1e-2 * abs(ref), rows
     assert "pair256x256" in rows["graph"]["kernel"] or "chain" in rows["graph"]["kernel"], rows["graph"]
+
+
+@pytest.mark.parametrize("tiles", [(256, 1024, 1024), (64, 64, 64), (32, 32, 32)])
+@pytest.mark.parametrize("with_zero", [False, True])
+def test_unfused_layers_are_combined_under_capture(tiles, with_zero):
+    """The UNFUSED form of an MLP layer (what the pipeline emits when CombineXsmmOp does not fire, SURVEY.md Appendix A:
+    [unary zero] -> brgemm -> binary add(bias, bcast_col_in0, in place) -> unary relu(in place)) captured into a graph is
+    combined by the runtime the way lib/TPP/Transforms/CombineXsmmPass.cpp:31-145 would have: add / relu become the
+    BRGEMM's epilogue, a zero overwritten by a beta=1 BRGEMM becomes beta_0, and the two layers still chain into ONE
+    launch. Checked against the oracle's fused op (one rounding) and, within the bf16 tolerance, its unfused sequence."""
+    import torch
+
+    from tpp_mlir_b200 import harness, xsmm
+
+    bn, bk, bc = tiles
+    layers = (1024, 1024, 1024) if bk == 1024 else (512, 512, 512)
+    cfg, (r,), (want,) = _blocked_mlp(tiles, False, layers=layers)
+    gflags = (0 if with_zero else xsmm.GEMM_FLAG_BETA_0) | 64 | 128
+    hb = xsmm.brgemm_dispatch(BF16, bn, bk, bc, bc, bk, bk, bn * bc, bc * bk, gflags)
+    hz = xsmm.unary_dispatch(xsmm.UNARY_ZERO, BF16, bn, bk, bk, bk, 0)
+    ha = xsmm.binary_dispatch(xsmm.BINARY_ADD, BF16, bn, bk, bk, bk, bk, xsmm.BINARY_FLAG_BCAST_COL_IN_0)
+    hr = xsmm.unary_dispatch(xsmm.UNARY_RELU, BF16, bn, bk, bk, bk, 0)
+
+    def forward():
+        for l in range(2):
+            c, k = layers[l], layers[l + 1]
+            nb_c, nb_k = c // bc, k // bk
+            for i_n in range(cfg.batch // bn):
+                for i_k in range(nb_k):
+                    off_c = (i_n * nb_k + i_k) * bn * bk
+                    if with_zero:
+                        xsmm.unary_invoke(BF16, hz, r.acts[l + 1], off_c, r.acts[l + 1], off_c)
+                    xsmm.brgemm_invoke(BF16, hb, r.acts[l], i_n * nb_c * bn * bc, r.weights[l], i_k * nb_c * bc * bk,
+                                       r.acts[l + 1], off_c, nb_c)
+                    xsmm.binary_invoke(BF16, ha, r.biases[l], i_k * bk, r.acts[l + 1], off_c, r.acts[l + 1], off_c)
+                    xsmm.unary_invoke(BF16, hr, r.acts[l + 1], off_c, r.acts[l + 1], off_c)
+
+    n0 = xsmm.launch_count()
+    with xsmm.graph_capture() as g:
+        forward()
+    name = xsmm.last_kernel()
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == 1, (xsmm.launch_count() - n0, name)
+    assert "mlp_chain" in name, name
+    fused = _blocked_out(cfg, r)
+    assert_close(BF16, fused, want)
+    g.destroy()
+    # the same stream issued directly (no capture): every op is its own launch, three roundings per layer
+    for a in r.acts[1:]:
+        a.zero_()
+    n0 = xsmm.launch_count()
+    forward()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 > 2
+    assert_close(BF16, _blocked_out(cfg, r), want)
 
 
 def test_perf_timer_includes_async_launches():

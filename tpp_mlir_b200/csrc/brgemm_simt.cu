@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(256) brgemm_simt_kernel(SimtParams p) {
         const int64_t j = j0 + c, kq = k0 + kk;
         float v = 0.f;
         if (j < p.n && kq < p.k) {
-          v = p.vnni_b ? ldf(Bb, ((kq / 2) * p.ldb + j) * 2 + (kq % 2)) : ldf(Bb, kq * p.ldb + j);
+          v = p.vnni_b ? ldf(Bb, ((kq / p.vnni_b) * p.ldb + j) * p.vnni_b + (kq % p.vnni_b)) : ldf(Bb, kq * p.ldb + j);
         }
         Bs[kk][c] = v;
       }
@@ -128,7 +128,7 @@ void launch_brgemm_simt(const KernelDesc &d, const GemmArgs &g, cudaStream_t str
   p.m = d.m; p.n = d.n; p.k = d.k; p.lda = d.lda; p.ldb = d.ldb; p.ldc = d.ldc;
   p.stride_a = d.stride_a; p.stride_b = d.stride_b; p.batch = g.batch;
   p.beta0 = (d.gemm_flags & 4) != 0;
-  p.vnni_b = (d.gemm_flags & 2048) != 0 && d.dtype == kBF16;
+  p.vnni_b = ((d.gemm_flags & 2048) != 0 && d.dtype == kBF16) ? (d.vnni_factor == 4 ? 4 : 2) : 0;   // VNNI factor, 0 = flat B
   p.bin_kind = (d.op == OpClass::FusedBrgemm && g.D) ? (int)d.binary_kind : 0;
   p.bin_mode = bin_mode_from_flags(d.binary_flags);
   p.relu = d.op == OpClass::FusedBrgemm && d.unary_kind == 5;

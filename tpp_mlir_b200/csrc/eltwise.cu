@@ -367,6 +367,71 @@ __global__ void __launch_bounds__(kThreads) vnni2_unpack_scalar_kernel(const uin
   }
 }
 
+// ---- VNNI-4 pack / unpack ([K][N] <-> [K/4][N][4]) -------------------------------------------------------------
+// pack: out[((p/4)*ldo + j)*4 + p%4] = in[p*ldi + j]. A thread owns 8 columns of one row quad: four 16-byte loads (one
+// per row), four 16-byte stores of 64 contiguous bytes (8 columns x 4 k).
+__global__ void __launch_bounds__(kThreads) vnni4_pack_vec_kernel(const uint16_t *__restrict__ in,
+                                                                 uint16_t *__restrict__ out, int64_t m, int64_t n,
+                                                                 int64_t ldi, int64_t ldo) {
+  const int64_t nv = n / 8, nq = m / 4;
+  const int64_t cv = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  if (cv >= nv) return;
+  const int64_t j = cv * 8;
+  const int ty = threadIdx.x >> 5;
+  for (int64_t q = (int64_t)blockIdx.y * 8 + ty; q < nq; q += (int64_t)gridDim.y * 8) {
+    uint4 r[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) r[v] = *reinterpret_cast<const uint4 *>(in + (4 * q + v) * ldi + j);
+    const uint32_t w[4][4] = {{r[0].x, r[0].y, r[0].z, r[0].w}, {r[1].x, r[1].y, r[1].z, r[1].w},
+                              {r[2].x, r[2].y, r[2].z, r[2].w}, {r[3].x, r[3].y, r[3].z, r[3].w}};
+    uint4 *dst = reinterpret_cast<uint4 *>(out + (q * ldo + j) * 4);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {   // word i of a row holds columns 2i (low half) and 2i + 1 (high half)
+      uint4 o;
+      o.x = __byte_perm(w[0][i], w[1][i], 0x5410); o.y = __byte_perm(w[2][i], w[3][i], 0x5410);   // column 2i: k 0,1 | k 2,3
+      o.z = __byte_perm(w[0][i], w[1][i], 0x7632); o.w = __byte_perm(w[2][i], w[3][i], 0x7632);   // column 2i + 1
+      dst[i] = o;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) vnni4_unpack_vec_kernel(const uint16_t *__restrict__ in,
+                                                                   uint16_t *__restrict__ out, int64_t m, int64_t n,
+                                                                   int64_t ldi, int64_t ldo) {
+  const int64_t nv = n / 8, nq = m / 4;
+  const int64_t cv = (int64_t)blockIdx.x * 32 + (threadIdx.x & 31);
+  if (cv >= nv) return;
+  const int64_t j = cv * 8;
+  const int ty = threadIdx.x >> 5;
+  for (int64_t q = (int64_t)blockIdx.y * 8 + ty; q < nq; q += (int64_t)gridDim.y * 8) {
+    const uint4 *src = reinterpret_cast<const uint4 *>(in + (q * ldi + j) * 4);
+    uint4 a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = src[i];   // a[i] = columns 2i, 2i + 1: (k0 k1 | k2 k3) each
+    uint32_t row[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      row[0][i] = __byte_perm(a[i].x, a[i].z, 0x5410);   // k0 of column 2i | k0 of column 2i + 1
+      row[1][i] = __byte_perm(a[i].x, a[i].z, 0x7632);
+      row[2][i] = __byte_perm(a[i].y, a[i].w, 0x5410);
+      row[3][i] = __byte_perm(a[i].y, a[i].w, 0x7632);
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+      *reinterpret_cast<uint4 *>(out + (4 * q + v) * ldo + j) = make_uint4(row[v][0], row[v][1], row[v][2], row[v][3]);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) vnni4_scalar_kernel(const uint16_t *__restrict__ in, uint16_t *__restrict__ out,
+                                                               int64_t m, int64_t n, int64_t ldi, int64_t ldo, int unpack) {
+  const int64_t total = m * n;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = idx / n, j = idx - p * n;
+    if (unpack) out[p * ldo + j] = in[((p / 4) * ldi + j) * 4 + (p % 4)];
+    else out[((p / 4) * ldo + j) * 4 + (p % 4)] = in[p * ldi + j];
+  }
+}
+
 } // namespace
 
 void launch_eltwise(const EltwiseArgs &a_in, cudaStream_t stream) {
@@ -500,6 +565,26 @@ void launch_vnni2_pack(const void *in, void *out, int64_t m, int64_t n, int64_t 
   else
     vnni2_pack_scalar_kernel<<<grid_for(m * n), kThreads, 0, stream>>>(src, dst, m, n, ldi, ldo);
   TPP_CUDA_CHECK(cudaGetLastError());
+}
+
+void launch_vnni4_pack(const void *in, void *out, int64_t m, int64_t n, int64_t ldi, int64_t ldo, cudaStream_t stream) {
+  if (m <= 0 || n <= 0) return;
+  const uint16_t *src = static_cast<const uint16_t *>(in);
+  uint16_t *dst = static_cast<uint16_t *>(out);
+  if ((n % 8) == 0 && (ldi % 8) == 0 && (ldo % 2) == 0 && aligned16(in) && aligned16(out))
+    vnni4_pack_vec_kernel<<<grid2d(n / 8, m / 4, 8), kThreads, 0, stream>>>(src, dst, m, n, ldi, ldo);
+  else
+    vnni4_scalar_kernel<<<grid_for(m * n), kThreads, 0, stream>>>(src, dst, m, n, ldi, ldo, 0);
+}
+
+void launch_vnni4_unpack(const void *in, void *out, int64_t m, int64_t n, int64_t ldi, int64_t ldo, cudaStream_t stream) {
+  if (m <= 0 || n <= 0) return;
+  const uint16_t *src = static_cast<const uint16_t *>(in);
+  uint16_t *dst = static_cast<uint16_t *>(out);
+  if ((n % 8) == 0 && (ldi % 2) == 0 && (ldo % 8) == 0 && aligned16(in) && aligned16(out))
+    vnni4_unpack_vec_kernel<<<grid2d(n / 8, m / 4, 8), kThreads, 0, stream>>>(src, dst, m, n, ldi, ldo);
+  else
+    vnni4_scalar_kernel<<<grid_for(m * n), kThreads, 0, stream>>>(src, dst, m, n, ldi, ldo, 1);
 }
 
 void launch_vnni2_unpack(const void *in, void *out, int64_t m, int64_t n, int64_t ldi, int64_t ldo,

@@ -22,6 +22,8 @@ enum class KernelImpl : int32_t {
   Vnni2Pack = 5,
   Vnni2Unpack = 6,
   Noop = 7,
+  Vnni4Pack = 8,
+  Vnni4Unpack = 9,
 };
 
 constexpr uint32_t kDescMagic = 0x54505042u; // "TPPB"
@@ -41,6 +43,7 @@ struct KernelDesc {
   int32_t block_n = 0;   // UMMA N (64/128/256)
   int32_t stages = 0;
   int32_t split_k = 1;   // cluster size along the reduction (DSMEM reduce)
+  int32_t vnni_factor = 0;   // B operand [K/v][N][v] (gemm flag 2048): v = 2 or 4, the answer of libxsmm_cpuid_dot_pack_factor at dispatch; 0 = flat
   // VNNI-B descriptors: the same shape with a flat [K][N] B, run on the tcgen05 kernel after B has been
   // un-interleaved into a scratch buffer (nullptr when the shape is not tensor-core eligible)
   const KernelDesc *flat_twin = nullptr;

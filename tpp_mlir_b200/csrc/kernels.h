@@ -34,6 +34,9 @@ void launch_vnni2_pack(const void *in, void *out, int64_t m, int64_t n, int64_t 
                        cudaStream_t stream);
 void launch_vnni2_unpack(const void *in, void *out, int64_t m, int64_t n, int64_t ldi, int64_t ldo,
                          cudaStream_t stream);
+// bf16 [K=m][N=n] (ldi) -> [K/4][N][4] (ldo in quads), and the inverse
+void launch_vnni4_pack(const void *in, void *out, int64_t m, int64_t n, int64_t ldi, int64_t ldo, cudaStream_t stream);
+void launch_vnni4_unpack(const void *in, void *out, int64_t m, int64_t n, int64_t ldi, int64_t ldo, cudaStream_t stream);
 
 // one tile of a batched tile move (identity copy or transpose, same m / n / ldi / ldo for the whole batch)
 struct TilePtrs {

@@ -101,6 +101,8 @@ struct ThreadCtx {
   // run of tile moves with ONE descriptor and no hazards among them (a tensor.pack / unpack lowered tile by tile):
   // launched as one batched kernel by flush_tiles(). At most one of the two pending lists is non-empty.
   std::vector<PendingTile> pending_tiles;
+  // a unary zero(C) recorded during capture and not launched yet (runtime CombineXsmmOp: see pending_producer_of)
+  struct HeldZero { const KernelDesc *d = nullptr; char *out = nullptr; } held_zero;
   std::vector<void *> capture_tables;   // device tables baked into the graph being captured (freed with it)
   std::vector<std::pair<cudaStream_t, Staging *>> vnni_scratch;   // VNNI-2 un-interleave scratch, one per stream
   cudaStream_t stream = nullptr; // legacy default stream unless xsmm_cuda_set_stream was called
@@ -368,7 +370,9 @@ int64_t gemm_family_dispatch(OpClass op, int64_t dtype, int64_t m, int64_t n, in
   const bool vnni_b = (gflags & XSMM_GEMM_FLAG_ROWMAJOR_B_VNNI) != 0;
   // op verifier rules (lib/TPP/Dialect/Xsmm/XsmmOps.cpp:319-344): lda >= k, ldb >= n, ldc >= n
   ok = ok && lda >= k && ldb >= n && ldc >= n && sa >= 0 && sb >= 0;
-  if (vnni_b) ok = ok && dtype == kBF16 && (k % 2) == 0;
+  // VNNI blocking factor of B: what the compiler asked libxsmm_cpuid_dot_pack_factor (2; 4 with TPP_XSMM_VNNI=4)
+  const int64_t vfac = vnni_b ? (int64_t)libxsmm_cpuid_dot_pack_factor((int)kBF16) : 0;
+  if (vnni_b) ok = ok && dtype == kBF16 && (vfac == 2 || vfac == 4) && (k % vfac) == 0;
   if (gflags & XSMM_GEMM_FLAG_VNNI_C) ok = false; // never produced by the pipeline (XsmmVerify.cpp:91-95)
   if (op == OpClass::FusedBrgemm) {
     ok = ok && bkind >= 0 && bkind <= 4 && (ukind == XSMM_UNARY_NONE || ukind == XSMM_UNARY_RELU);
@@ -378,7 +382,7 @@ int64_t gemm_family_dispatch(OpClass op, int64_t dtype, int64_t m, int64_t n, in
     print_gemm_shape(what, dtype, m, n, k, lda, ldb, ldc, sa, sb, gflags);
     exit(-1);
   }
-  Key key{{(int64_t)op, dtype, m, n, k, lda, ldb, ldc, sa, sb, gflags, uflags, ukind, bflags, bkind, 0}};
+  Key key{{(int64_t)op, dtype, m, n, k, lda, ldb, ldc, sa, sb, gflags, uflags, ukind, bflags, bkind, vfac}};
   return cached(key, [&](KernelDesc &d) {
     d.op = op;
     d.dtype = dtype;
@@ -386,6 +390,7 @@ int64_t gemm_family_dispatch(OpClass op, int64_t dtype, int64_t m, int64_t n, in
     d.stride_a = sa; d.stride_b = sb;
     d.gemm_flags = gflags;
     d.unary_flags = uflags; d.unary_kind = ukind; d.binary_flags = bflags; d.binary_kind = bkind;
+    d.vnni_factor = (int32_t)vfac;
     const char *force = getenv("TPP_XSMM_FORCE_SIMT");
     if (brgemm_tc_supported(d) && !(force && force[0] == '1')) {
       d.impl = KernelImpl::BrgemmTC;
@@ -399,6 +404,7 @@ int64_t gemm_family_dispatch(OpClass op, int64_t dtype, int64_t m, int64_t n, in
         // kernel on the flat twin; small ones stay on the generic kernel.
         KernelDesc twin = d;
         twin.gemm_flags &= ~(int64_t)XSMM_GEMM_FLAG_ROWMAJOR_B_VNNI;
+        twin.vnni_factor = 0;
         if (brgemm_tc_supported(twin)) {
           twin.impl = KernelImpl::BrgemmTC;
           brgemm_tc_configure(twin);
@@ -441,13 +447,14 @@ void issue_gemm(const KernelDesc *d, const GemmArgs &g, cudaStream_t stream) {
       flat = scratch->get(need);
     }
     {
-      launch_vnni2_unpack(g.B, flat, rows, d->n, d->ldb, d->ldb, stream);
+      if (d->vnni_factor == 4) launch_vnni4_unpack(g.B, flat, rows, d->n, d->ldb, d->ldb, stream);
+      else launch_vnni2_unpack(g.B, flat, rows, d->n, d->ldb, d->ldb, stream);
       count_launch();
       GemmArgs gf = g;
       gf.B = flat;
       gf.b_independent = false;   // produced by the kernel just launched
       launched = launch_brgemm_tc(*d->flat_twin, gf, stream);
-      if (launched) t_ctx.last_kernel = "vnni2_unpack+brgemm_tc_bf16";
+      if (launched) t_ctx.last_kernel = d->vnni_factor == 4 ? "vnni4_unpack+brgemm_tc_bf16" : "vnni2_unpack+brgemm_tc_bf16";
     }
   }
   if (!launched) {
@@ -569,6 +576,8 @@ size_t fold_grid(const std::vector<PendingGemm> &list, size_t i, Layer *out) {
 // ("whole-MLP fusion ... or CUDA-graph capture of the invoke sequence"); everything else is launched
 // exactly as a direct invoke would.
 void flush_tiles();
+void flush_held_zero();
+const KernelDesc *fused_variant(const KernelDesc *d, bool add_bias, bool relu, bool beta0);
 
 void flush_pending() {
   if (t_ctx.up_pending) {   // kernels issued from here on see every upload_async issued before them
@@ -576,6 +585,8 @@ void flush_pending() {
     t_ctx.up_pending = false;
   }
   flush_tiles();
+  // program order: the pending BRGEMMs were recorded BEFORE a held zero (a zero is held only until the next BRGEMM)
+  struct ZeroLast { ~ZeroLast() { flush_held_zero(); } } zero_last;
   if (t_ctx.pending.empty()) return;
   std::vector<PendingGemm> list;
   list.swap(t_ctx.pending);
@@ -676,7 +687,8 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
   ops[0].is_input = batch > 0;
   ops[1].aligned = pB; ops[1].elem = elem_ptr(dtype, pB, offB);
   ops[1].rows = 1;
-  ops[1].width = vnni_b ? (nb - 1) * d->stride_b + ((d->k / 2 - 1) * d->ldb + d->n) * 2
+  const int64_t vf = d->vnni_factor > 0 ? d->vnni_factor : 2;
+  ops[1].width = vnni_b ? (nb - 1) * d->stride_b + ((d->k / vf - 1) * d->ldb + d->n) * vf
                         : (nb - 1) * d->stride_b + (d->k - 1) * d->ldb + d->n;
   ops[1].ld = ops[1].width;
   ops[1].is_input = batch > 0;
@@ -716,6 +728,16 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
     }
   } else {
     t_ctx.pdl_run = 0;                     // generic kernels / captured work are launched in plain stream order
+  }
+  if (t_ctx.capturing && t_ctx.held_zero.d) {
+    const ThreadCtx::HeldZero z = t_ctx.held_zero;
+    if (!sc.any_host && !beta0 && d->dtype == z.d->dtype && z.out == ops[2].dev && z.d->m == d->m && z.d->n == d->n &&
+        z.d->ldo == d->ldc && t_ctx.pending_tiles.empty()) {
+      t_ctx.held_zero = {};                      // C = 0; C += A B   ==   C = A B
+      d = fused_variant(d, false, false, true);
+    } else {
+      flush_pending();                           // earlier BRGEMMs, then the zero, then this invoke
+    }
   }
   if (t_ctx.capturing && !sc.any_host && d->dtype == kBF16 && (d->impl == KernelImpl::BrgemmTC || d->flat_twin)) {
     flush_tiles();
@@ -782,6 +804,8 @@ extern "C" int64_t xsmm_unary_dispatch(int64_t kind, int64_t dtype, int64_t m, i
   case XSMM_UNARY_TRANSPOSE: impl = KernelImpl::Transpose; name = "unary_transpose_64x64"; ok = ok && flags == 0 && ldi >= n && ldo >= m; break;
   case XSMM_UNARY_VNNI2: impl = KernelImpl::Vnni2Pack; name = "unary_vnni2_pack"; ok = ok && flags == 0 && dtype == kBF16 && (m % 2) == 0 && ldi >= n && ldo >= n; break;
   case XSMM_UNARY_UNVNNI2_EXT: impl = KernelImpl::Vnni2Unpack; name = "unary_vnni2_unpack"; ok = ok && flags == 0 && dtype == kBF16 && (m % 2) == 0 && ldi >= n && ldo >= n; break;
+  case XSMM_UNARY_VNNI4: impl = KernelImpl::Vnni4Pack; name = "unary_vnni4_pack"; ok = ok && flags == 0 && dtype == kBF16 && (m % 4) == 0 && ldi >= n && ldo >= n; break;
+  case XSMM_UNARY_UNVNNI4_EXT: impl = KernelImpl::Vnni4Unpack; name = "unary_vnni4_unpack"; ok = ok && flags == 0 && dtype == kBF16 && (m % 4) == 0 && ldi >= n && ldo >= n; break;
   default: ok = false;
   }
   if (impl == KernelImpl::Eltwise) {
@@ -879,6 +903,12 @@ void launch_unary(const KernelDesc *d, const char *in, char *out, bool use_imm, 
   case KernelImpl::Vnni2Unpack:
     launch_vnni2_unpack(in, out, d->m, d->n, d->ldi, d->ldo, stream);
     break;
+  case KernelImpl::Vnni4Pack:
+    launch_vnni4_pack(in, out, d->m, d->n, d->ldi, d->ldo, stream);
+    break;
+  case KernelImpl::Vnni4Unpack:
+    launch_vnni4_unpack(in, out, d->m, d->n, d->ldi, d->ldo, stream);
+    break;
   default: {
     EltwiseArgs a;
     a.in0 = in; a.out = out;
@@ -911,6 +941,17 @@ TileRects tile_rects(const KernelDesc *d, const char *in, char *out) {
   const int64_t es = (int64_t)esize(d->dtype);
   if (d->impl == KernelImpl::Transpose) return {in, out, d->m, d->n * es, d->ldi * es, d->n, d->m * es, d->ldo * es};
   return {in, out, d->m, d->n * es, d->ldi * es, d->m, d->n * es, d->ldo * es};
+}
+
+// the zero that no BRGEMM absorbed is launched where it was issued
+void flush_held_zero() {
+  if (!t_ctx.held_zero.d) return;
+  const ThreadCtx::HeldZero z = t_ctx.held_zero;
+  t_ctx.held_zero = {};
+  launch_unary(z.d, nullptr, z.out, false, 0.f, t_ctx.stream);
+  t_ctx.note_output(z.out, (size_t)((z.d->m - 1) * z.d->ldo + z.d->n) * esize(z.d->dtype));
+  t_ctx.last_kernel = z.d->name;
+  count_launch();
 }
 
 // Launch the tile moves recorded during graph capture: four or more become ONE batched kernel reading a device table
@@ -954,12 +995,67 @@ void flush_tiles() {
 }
 }  // namespace
 
+namespace {
+// ---- runtime CombineXsmmOp (capture only) --------------------------------------------------------------------
+// When the compiler's fusion pass does not fire (lib/TPP/Transforms/CombineXsmmPass.cpp:31-145 needs the
+// brgemm -> binary add(bcast_col_in0) -> unary relu chain on ONE buffer inside one block), a layer reaches the ABI as
+// [unary zero(C)] -> brgemm(A, B, C) -> binary add(bias, C, C) -> unary relu(C, C): three or four launches and as many
+// trips of C through memory ("unfused MLP layer"). During graph capture the BRGEMM is still
+// pending when its consumers arrive, so the same rewrite is done here: the add / relu are folded into the pending
+// invoke's descriptor (post-ops on the f32 accumulator, ONE rounding - exactly what the compiler's fused op computes,
+// docs/TPPDialect.md:288-300), a zero that is overwritten by a beta=1 BRGEMM of the same tile becomes beta_0.
+// Returns the descriptor of `d` with the given epilogue / beta, from the ordinary dispatch cache.
+const KernelDesc *fused_variant(const KernelDesc *d, bool add_bias, bool relu, bool beta0) {
+  const int64_t gflags = beta0 ? (d->gemm_flags | XSMM_GEMM_FLAG_BETA_0) : d->gemm_flags;
+  const bool bias = add_bias || d->binary_kind == XSMM_BINARY_ADD;
+  const bool act = relu || d->unary_kind == XSMM_UNARY_RELU;
+  const OpClass op = (bias || act) ? OpClass::FusedBrgemm : d->op;
+  const int64_t h = gemm_family_dispatch(op, d->dtype, d->m, d->n, d->k, d->lda, d->ldb, d->ldc, d->stride_a, d->stride_b, gflags,
+                                         0, act ? XSMM_UNARY_RELU : XSMM_UNARY_NONE, bias ? XSMM_BINARY_FLAG_BCAST_COL_IN_0 : 0,
+                                         bias ? XSMM_BINARY_ADD : XSMM_BINARY_NONE);
+  return reinterpret_cast<const KernelDesc *>(h);
+}
+
+// the last pending BRGEMM if its output tile is exactly [C, m x n, pitch ld] of this dtype
+PendingGemm *pending_producer_of(int64_t dtype, const char *C, int64_t m, int64_t n, int64_t ld) {
+  static const bool off = [] { const char *e = getenv("TPP_XSMM_COMBINE"); return e && e[0] == '0'; }();
+  if (off || !t_ctx.capturing || t_ctx.pending.empty() || !t_ctx.pending_tiles.empty()) return nullptr;
+  PendingGemm &p = t_ctx.pending.back();
+  if (p.d->dtype != dtype || static_cast<const char *>(p.g.C) != C || p.d->m != m || p.d->n != n || p.d->ldc != ld) return nullptr;
+  return &p;
+}
+
+}  // namespace
+
 static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int64_t offIn, bool use_imm, float imm,
                               void *pOut, int64_t offOut) {
   // tile moves (plain identity copy / transpose) issued during graph capture are collected, see flush_tiles()
   const bool batchable = t_ctx.capturing && !use_imm &&
                          (d->impl == KernelImpl::Transpose ||
                           (d->impl == KernelImpl::Eltwise && d->kind == XSMM_UNARY_IDENTITY && d->flags == 0));
+  if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
+  if (t_ctx.capturing && !use_imm && d->impl == KernelImpl::Eltwise && d->flags == 0 && d->dtype == kBF16) {
+    if (d->kind == XSMM_UNARY_RELU && pIn == pOut && offIn == offOut && d->ldi == d->ldo) {
+      // relu(C, C) right after the BRGEMM that produces C: becomes that invoke's epilogue
+      Resolved r = resolve(pOut, elem_ptr(dtype, pOut, offOut));
+      PendingGemm *p = r.where != Where::HostPlain ? pending_producer_of(dtype, r.dev, d->m, d->n, d->ldo) : nullptr;
+      if (p && p->d->unary_kind == XSMM_UNARY_NONE && (p->d->op != OpClass::FusedBrgemm || p->d->binary_kind == XSMM_BINARY_NONE ||
+                                                      (p->d->binary_kind == XSMM_BINARY_ADD && (p->d->binary_flags & 4)))) {
+        p->d = fused_variant(p->d, false, true, (p->d->gemm_flags & XSMM_GEMM_FLAG_BETA_0) != 0);
+        return;
+      }
+    }
+    if (d->kind == XSMM_UNARY_ZERO) {
+      // zero(C): held back; dropped if the very next invoke is a beta=1 BRGEMM that overwrites exactly this tile
+      Resolved r = resolve(pOut, elem_ptr(dtype, pOut, offOut));
+      if (r.where != Where::HostPlain) {
+        if (t_ctx.held_zero.d) flush_pending();   // one zero is held at a time (pending BRGEMMs first, then that zero)
+        flush_tiles();
+        t_ctx.held_zero = {d, r.dev};
+        return;
+      }
+    }
+  }
   if (batchable) {
     std::vector<PendingTile> keep;
     keep.swap(t_ctx.pending_tiles);   // flush_pending() must not launch the run this invoke may still join
@@ -968,7 +1064,6 @@ static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int
   } else {
     flush_pending();
   }
-  if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
   Operand ops[2];
   const int mode = bcast_mode_unary(d->flags);
   const bool reads_input = d->kind != XSMM_UNARY_ZERO && !use_imm;
@@ -989,6 +1084,14 @@ static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int
     break;
   case KernelImpl::Vnni2Unpack:
     ops[0].rows = d->m / 2; ops[0].width = 2 * d->n; ops[0].ld = 2 * d->ldi;
+    ops[1].rows = d->m; ops[1].width = d->n; ops[1].ld = d->ldo;
+    break;
+  case KernelImpl::Vnni4Pack:
+    ops[0].rows = d->m; ops[0].width = d->n; ops[0].ld = d->ldi;
+    ops[1].rows = d->m / 4; ops[1].width = 4 * d->n; ops[1].ld = 4 * d->ldo;
+    break;
+  case KernelImpl::Vnni4Unpack:
+    ops[0].rows = d->m / 4; ops[0].width = 4 * d->n; ops[0].ld = 4 * d->ldi;
     ops[1].rows = d->m; ops[1].width = d->n; ops[1].ld = d->ldo;
     break;
   default:
@@ -1044,6 +1147,19 @@ extern "C" void xsmm_binary_invoke(int64_t dtype, int64_t addr, void *alignedPtr
                                    void *alignedPtrRhs, int64_t offsetRhs, void *alignedPtrOut, int64_t offsetOut) {
   const KernelDesc *d = desc_of(addr, OpClass::Binary);
   if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
+  if (t_ctx.capturing && d->dtype == kBF16 && d->kind == XSMM_BINARY_ADD && d->flags == XSMM_BINARY_FLAG_BCAST_COL_IN_0 &&
+      alignedPtrRhs == alignedPtrOut && offsetRhs == offsetOut && d->ldi2 == d->ldo) {
+    // add(bias[bcast_col_in0], C, C) right after the BRGEMM that produces C: becomes that invoke's epilogue
+    Resolved rc = resolve(alignedPtrOut, elem_ptr(dtype, alignedPtrOut, offsetOut));
+    Resolved rb = resolve(alignedPtrLhs, elem_ptr(dtype, alignedPtrLhs, offsetLhs));
+    PendingGemm *p = (rc.where != Where::HostPlain && rb.where != Where::HostPlain)
+                         ? pending_producer_of(dtype, rc.dev, d->m, d->n, d->ldo) : nullptr;
+    if (p && p->d->unary_kind == XSMM_UNARY_NONE && (p->d->op != OpClass::FusedBrgemm || p->d->binary_kind == XSMM_BINARY_NONE)) {
+      p->d = fused_variant(p->d, true, false, (p->d->gemm_flags & XSMM_GEMM_FLAG_BETA_0) != 0);
+      p->g.D = rb.dev;
+      return;
+    }
+  }
   flush_pending();
   const int64_t f = d->flags;
   const int mode0 = (f & 1) ? kBcastRow : (f & 4) ? kBcastCol : (f & 16) ? kBcastScalar : kBcastNone;
@@ -1096,6 +1212,7 @@ extern "C" int libxsmm_cpuid_dot_pack_factor(int datatype) {
   if (datatype != (int)kBF16) return 1;
   const char *env = getenv("TPP_XSMM_VNNI");
   if (env && env[0] == '0') return 0; // odd factors disable VNNI packing (VNNIUtils.cpp:41-43)
+  if (env && env[0] == '4') return 4; // mlir-gen --vnni=4 layouts ([K/4][N][4]; benchmarks/config/omp/mlir-bf16.json:65-125)
   return 2;
 }
 

@@ -181,7 +181,8 @@ LayerRanges layer_ranges(const KernelDesc &d, const GemmArgs &g) {
   const int64_t nb = g.batch > 0 ? g.batch : 1;
   const bool vnni = (d.gemm_flags & 2048) != 0;
   const int64_t a_tile = (nb - 1) * d.stride_a + (d.m - 1) * d.lda + d.k;
-  const int64_t b_tile = vnni ? (nb - 1) * d.stride_b + ((d.k / 2 - 1) * d.ldb + d.n) * 2
+  const int64_t vf = d.vnni_factor > 0 ? d.vnni_factor : 2;
+  const int64_t b_tile = vnni ? (nb - 1) * d.stride_b + ((d.k / vf - 1) * d.ldb + d.n) * vf
                               : (nb - 1) * d.stride_b + (d.k - 1) * d.ldb + d.n;
   const int64_t c_tile = (d.m - 1) * d.ldc + d.n;
   LayerRanges r;

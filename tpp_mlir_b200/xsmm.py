@@ -26,6 +26,7 @@ F32, BF16 = 1, 2
 BINARY_NONE, BINARY_ADD, BINARY_MUL, BINARY_SUB, BINARY_DIV = 0, 1, 2, 3, 4
 UNARY_NONE, UNARY_IDENTITY, UNARY_ZERO, UNARY_RELU, UNARY_VNNI2, UNARY_TRANSPOSE = 0, 1, 2, 5, 28, 29
 UNARY_UNVNNI2_EXT = 1028
+UNARY_VNNI4, UNARY_UNVNNI4_EXT = 32, 1032   # [K][N] <-> [K/4][N][4]
 UNARY_FLAG_NONE, UNARY_FLAG_BCAST_ROW, UNARY_FLAG_BCAST_COL, UNARY_FLAG_BCAST_SCALAR = 0, 2, 4, 8
 BINARY_FLAG_NONE = 0
 BINARY_FLAG_BCAST_ROW_IN_0, BINARY_FLAG_BCAST_ROW_IN_1 = 1, 2
