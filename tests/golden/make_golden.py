@@ -154,6 +154,17 @@ def main():
     d = dense_blocks(t)
     add("strided_gemm1", "test/Integration/xsmm-strided-brgemm1.mlir:15-100", A=d[0], B=d[1], expected=flat_checks(t))
 
+    for i in (2, 3):
+        t = read(f"test/Integration/xsmm-strided-brgemm{i}.mlir")
+        d = dense_blocks(t)
+        add(f"strided_gemm{i}", f"test/Integration/xsmm-strided-brgemm{i}.mlir", A=d[0], B=d[1], expected=flat_checks(t))
+
+    t = read("test/BF16/Integration/mlir-gen-bf16.mlir")
+    mm = re.search(r"GEN-MATMUL-BF16: \(([^)]*)\)", t)
+    fc = re.search(r"GEN-FC-BF16: \(([^)]*)\)", t)
+    add("mlir_gen_bf16", "test/BF16/Integration/mlir-gen-bf16.mlir:9-26", matmul_row=nums(mm.group(1)), fc_row=nums(fc.group(1)),
+        batch=16, layers=[16, 16])
+
     t = read("test/BF16/Integration/mlp-all-bf16-tpprun.mlir")
     m = re.search(r"%c4 = arith.constant (" + NUM + ")", t)
     thr = re.search(r"%threshold = arith.constant (" + NUM + ")", t)

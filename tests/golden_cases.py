@@ -236,6 +236,48 @@ def case_strided_gemm1(be):
     return C, np.array(g["expected"], np.float32), 5e-3 * 10
 
 
+def case_strided_gemm2(be):
+    # test/Integration/xsmm-strided-brgemm2.mlir:35: xsmm_gemm_dispatch(1,2,8,4,8,16,8,4) (beta_0 folded in):
+    # C_exp[b][h][i][j] = sum_k A_exp[b][i][h][k] * B_exp[b][k][h][j] with A(4x8) -> (2,2,2,4), B(8x16) -> (2,4,2,8),
+    # C(4x16) -> (2,2,2,8): one gemm per (b,h) on A rows at pitch 8, B rows at pitch 16, a 2x8 tile of C at pitch 8
+    g = golden()["strided_gemm2"]
+    A, B = np.array(g["A"], np.float32), np.array(g["B"], np.float32)
+    C = np.zeros(64, np.float32)
+    for b in range(2):
+        for h in range(2):
+            be.gemm(F32, 2, 8, 4, 8, 16, 8, 4, A, b * 16 + h * 4, B, b * 64 + h * 8, C, (b * 2 + h) * 16)
+    return C, np.array(g["expected"], np.float32), 5e-3 * 10   # printed with up to 5 significant digits
+
+
+def case_strided_gemm3(be):
+    # test/Integration/xsmm-strided-brgemm3.mlir:34-35: ONE xsmm_unary_dispatch (transpose of the A slice) and
+    # xsmm_gemm_dispatch(1,8,2,4,8,2,2,4): C_exp[b][h][j][i] = sum_k A_exp[b][i][h][k] * B_exp[b][j][h][k] with B(16x8) ->
+    # (2,8,2,4), C(4x16) -> (2,2,8,2): per (b,h) the 8x4 slice of B is the row-major A operand (pitch 8), the transposed
+    # 2x4 slice of A the B operand (4x2), the result an 8x2 tile of C
+    g = golden()["strided_gemm3"]
+    A, B = np.array(g["A"], np.float32), np.array(g["B"], np.float32)
+    C = np.zeros(64, np.float32)
+    for b in range(2):
+        for h in range(2):
+            T = np.zeros(8, np.float32)
+            be.unary(29, F32, 2, 4, 8, 2, 0, A, b * 16 + h * 4, T, 0)          # 2x4 (pitch 8) -> 4x2
+            be.gemm(F32, 8, 2, 4, 8, 2, 2, 4, B, b * 64 + h * 4, T, 0, C, (b * 2 + h) * 16)
+    return C, np.array(g["expected"], np.float32), 5e-3 * 10
+
+
+def case_mlir_gen_bf16(be):
+    # test/BF16/Integration/mlir-gen-bf16.mlir:9-26: mlir-gen --kernel=args --float-type=bf16 --batch=16 --layers=16,16
+    # (all-ones init): matmul accumulating into C = 1 prints rows of 17; with --bias --relu rows of 18. VNNI-2 weights, as
+    # the bf16 pipeline packs them.
+    g = golden()["mlir_gen_bf16"]
+    x, W, bias = const(BF16, (16, 16)), const(BF16, (8, 16, 2)), const(BF16, (16,))
+    c_mm, c_fc = const(BF16, (16, 16)), const(BF16, (16, 16))
+    be.gemm(BF16, 16, 16, 16, 16, 16, 16, 2048, x, 0, W, 0, c_mm, 0)
+    be.fused_brgemm(BF16, 16, 16, 16, 16, 16, 16, 0, 0, 2048, 0, 5, 4, 1, x, 0, W, 0, c_fc, 0, bias, 0, 1)
+    got = np.concatenate([to_f32(BF16, c_mm)[0], to_f32(BF16, c_fc)[0]])
+    return got, np.array(g["matmul_row"] + g["fc_row"], np.float32), 0.0
+
+
 def case_matmul_64x64x64_f32(be):
     # test/Integration/matmul_64x64x64.mlir:11,16 (cfg1): default 32x32x32 packing -> per output block one
     # xsmm_brgemm_dispatch(1,32,32,32,32,32,32,1024,1024,0) invoke with 2 batches, C initialised to 1 => 65
