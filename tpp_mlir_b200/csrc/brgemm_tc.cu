@@ -469,7 +469,7 @@ void launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &
 }
 
 template <int BLOCK_N, int STAGES, int SPLITK>
-void launch_cfg_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, dim3 grid, cudaStream_t stream) {
+bool launch_cfg_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, dim3 grid, cudaStream_t stream) {
   constexpr int smem = STAGES * (A_STAGE_BYTES + (BLOCK_N / 128) * B_CHUNK_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
   static std::once_flag once;
   std::call_once(once, [] {
@@ -490,7 +490,14 @@ void launch_cfg_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
   attrs[1].val.clusterDim.z = SPLITK == 2 ? (unsigned)p.split_k : 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 2;
+  if (SPLITK == 3) {
+    // the k-slices of a tile meet at an arrival counter in global memory: all CTAs must be resident. The launcher keeps
+    // such grids within one wave; the cooperative launch makes that a guarantee (other streams may hold SMs)
+    if (!prepare_resident_launch(reinterpret_cast<const void *>(brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK>), &cfg, attrs))
+      return false;
+  }
   TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK>, tmA, tmB, p));
+  return true;
 }
 
 
@@ -729,12 +736,17 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   set_last_name("brgemm_tc_bf16_%dx%dx64%s%s", mc == 2 ? 256 : 128, block_n,
            split == 1 ? "" : split == 2 ? "_splitk2" : "_splitk4", mc == 1 ? "_mc2x2" : mc == 2 ? "_2cta" : "");
   if (mc == 2) {
-    if (block_n == 256) {
-      if (split > 1) launch_cfg_pair<256, 6, 3>(tmA, tmB, p, grid, stream);
-      else launch_cfg_pair<256, 6, 0>(tmA, tmB, p, grid, stream);
-    } else {
-      if (split > 1) launch_cfg_pair<128, 8, 3>(tmA, tmB, p, grid, stream);
+    bool ok = true;
+    if (split > 1) ok = block_n == 256 ? launch_cfg_pair<256, 6, 3>(tmA, tmB, p, grid, stream)
+                                       : launch_cfg_pair<128, 8, 3>(tmA, tmB, p, grid, stream);
+    if (split == 1 || !ok) {   // no split, or the split grid cannot be co-resident here: one CTA pair per tile, whole reduction
+      p.split_k = 1;
+      grid.z = 1;
+      p.ws = nullptr;
+      p.flags = nullptr;
+      if (block_n == 256) launch_cfg_pair<256, 6, 0>(tmA, tmB, p, grid, stream);
       else launch_cfg_pair<128, 8, 0>(tmA, tmB, p, grid, stream);
+      if (!ok) set_last_name("brgemm_tc_bf16_256x%dx64_2cta", block_n);
     }
   } else
   switch (block_n) {

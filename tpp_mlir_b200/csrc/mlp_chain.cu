@@ -343,6 +343,7 @@ bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, i
     g_chain_trace_ctas = n_ctas;
     g_chain_trace_layers = L;
   }
+  if (!prepare_resident_launch(reinterpret_cast<const void *>(mlp_chain_kernel), &cfg, attrs)) return false;   // grid barrier per layer
   TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_kernel, cp));
   set_last_name("mlp_chain_bf16_%dlayers_128x64x64_splitk4", L);
   return true;

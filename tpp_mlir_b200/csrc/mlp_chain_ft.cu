@@ -886,6 +886,11 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     g_chain_trace_layers = np;
     g_chain_trace_ft = true;
   }
+  // the passes wait for each other through arrival counters: every CTA must be resident (cooperative launch)
+  const void *kfn = split == 4 ? reinterpret_cast<const void *>(mlp_chain_fts_kernel<4>)
+                    : split == 2 ? reinterpret_cast<const void *>(mlp_chain_fts_kernel<2>)
+                                 : reinterpret_cast<const void *>(mlp_chain_ft_kernel);
+  if (!prepare_resident_launch(kfn, &cfg, attrs)) return 0;
   if (split == 4) TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_fts_kernel<4>, cp));
   else if (split == 2) TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_fts_kernel<2>, cp));
   else TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_ft_kernel, cp));

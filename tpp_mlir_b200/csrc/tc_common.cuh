@@ -152,6 +152,14 @@ void capture_adopt(void *p);                   // a device allocation the caller
 void *capture_owned_table(const void *host, size_t bytes);   // device copy of a host table, complete on return
 float *capture_owned_ws(size_t need);          // split-K exchange workspace of the capture in progress
 
+// Kernels whose CTAs wait for each other through global-memory counters (flag-synchronised split-K, the chain kernels'
+// layer barriers) need every CTA of the grid resident at once. They are launched COOPERATIVELY - the driver then
+// guarantees co-residency even when other streams hold SMs, instead of a spin that could only trap - after an occupancy
+// query has shown that the grid fits; when it does not, the caller takes a path without cross-CTA waits.
+// prepare_resident_launch: puts the cooperative attribute into attrs[0] (replacing programmatic serialisation, the two do
+// not combine) unless TPP_XSMM_COOP=0, and returns false if the grid cannot be co-resident on this device.
+bool prepare_resident_launch(const void *kernel, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attrs);
+
 void set_last_name(const char *fmt, ...);      // this thread's last tcgen05 launch (xsmm_cuda_last_kernel)
 
 struct ByteRange { const char *lo, *hi; };

@@ -169,6 +169,36 @@ void *capture_owned_table(const void *host, size_t bytes) {
   return p;
 }
 
+bool prepare_resident_launch(const void *kernel, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attrs) {
+  static const bool coop = [] { const char *e = getenv("TPP_XSMM_COOP"); return !(e && e[0] == '0'); }();
+  const size_t ctas = (size_t)cfg->gridDim.x * cfg->gridDim.y * cfg->gridDim.z;
+  size_t cluster = 1;
+  for (unsigned i = 0; i < cfg->numAttrs; ++i)
+    if (cfg->attrs[i].id == cudaLaunchAttributeClusterDimension)
+      cluster = (size_t)cfg->attrs[i].val.clusterDim.x * cfg->attrs[i].val.clusterDim.y * cfg->attrs[i].val.clusterDim.z;
+  size_t capacity = 0;
+  if (cluster > 1) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kernel, cfg) != cudaSuccess) { cudaGetLastError(); return false; }
+    capacity = (size_t)n * cluster;
+  } else {
+    int per_sm = 0, dev = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, (int)cfg->blockDim.x, cfg->dynamicSmemBytes) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    capacity = (size_t)per_sm * sms;
+  }
+  if (capacity < ctas) return false;
+  if (coop && attrs[0].id == cudaLaunchAttributeProgrammaticStreamSerialization) {
+    attrs[0].id = cudaLaunchAttributeCooperative;
+    attrs[0].val.cooperative = 1;
+  }
+  return true;
+}
+
 unsigned long long *trace_ring() {
   if (!g_trace_buf) {
     const size_t bytes = sizeof(unsigned long long) * kTraceRing * kTraceRingCtas * TRACE_SLOTS;
