@@ -451,7 +451,7 @@ void launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[2];
+  cudaLaunchAttribute attrs[3];
   int na = 0;
   attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[na].val.programmaticStreamSerializationAllowed = t_pdl_allowed;
@@ -481,7 +481,7 @@ bool launch_cfg_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[2];
+  cudaLaunchAttribute attrs[3];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = t_pdl_allowed;
   attrs[1].id = cudaLaunchAttributeClusterDimension;
@@ -493,7 +493,8 @@ bool launch_cfg_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
   if (SPLITK == 3) {
     // the k-slices of a tile meet at an arrival counter in global memory: all CTAs must be resident. The launcher keeps
     // such grids within one wave; the cooperative launch makes that a guarantee (other streams may hold SMs)
-    if (!prepare_resident_launch(reinterpret_cast<const void *>(brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK>), &cfg, attrs))
+    if (!prepare_resident_launch(reinterpret_cast<const void *>(brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK>), &cfg, attrs,
+                                 /*only_if_concurrent=*/true))
       return false;
   }
   TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK>, tmA, tmB, p));

@@ -320,7 +320,7 @@ bool launch_brgemm_chain(const KernelDesc *const *descs, const GemmArgs *args, i
   cfg.blockDim = dim3(NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[2];
+  cudaLaunchAttribute attrs[3];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   attrs[1].id = cudaLaunchAttributeClusterDimension;

@@ -858,7 +858,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   cfg.blockDim = dim3(split2 ? F2_THREADS : NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[2];
+  cudaLaunchAttribute attrs[3];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;

@@ -158,7 +158,11 @@ float *capture_owned_ws(size_t need);          // split-K exchange workspace of 
 // query has shown that the grid fits; when it does not, the caller takes a path without cross-CTA waits.
 // prepare_resident_launch: puts the cooperative attribute into attrs[0] (replacing programmatic serialisation, the two do
 // not combine) unless TPP_XSMM_COOP=0, and returns false if the grid cannot be co-resident on this device.
-bool prepare_resident_launch(const void *kernel, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attrs);
+// `only_if_concurrent`: keep the ordinary (programmatic) launch while this process has only ever launched on ONE
+// (thread, stream) - nothing else of ours can hold SMs then, and back-to-back launches keep their PDL overlap (a
+// cooperative launch serialises them: cfg2 1130 -> 1037 TF/s) - and go cooperative from the first sign of a second one.
+bool prepare_resident_launch(const void *kernel, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attrs,
+                             bool only_if_concurrent = false);
 
 void set_last_name(const char *fmt, ...);      // this thread's last tcgen05 launch (xsmm_cuda_last_kernel)
 

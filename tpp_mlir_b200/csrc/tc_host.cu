@@ -1,7 +1,9 @@
 // tc_host.cu - host-side helpers shared by the tcgen05 kernel families (declared in tc_common.cuh): tensor-map
 // encoding through the driver entry point, device memory owned by the graph being captured, operand-hazard tests of
 // layer chains, the name of the last launch, and the debug trace dump.
+#include <atomic>
 #include <cstdarg>
+#include <utility>
 
 #include "tc_common.cuh"
 
@@ -169,8 +171,31 @@ void *capture_owned_table(const void *host, size_t bytes) {
   return p;
 }
 
-bool prepare_resident_launch(const void *kernel, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attrs) {
-  static const bool coop = [] { const char *e = getenv("TPP_XSMM_COOP"); return !(e && e[0] == '0'); }();
+namespace {
+// has this process launched through the library on more than one (thread, stream)?
+bool concurrent_launchers_seen(cudaStream_t stream) {
+  static std::mutex mu;
+  static std::vector<std::pair<size_t, cudaStream_t>> seen;
+  static std::atomic<bool> many{false};
+  if (many.load(std::memory_order_relaxed)) return true;
+  thread_local size_t me = 0;
+  thread_local cudaStream_t last = reinterpret_cast<cudaStream_t>(~(uintptr_t)0);
+  if (me != 0 && last == stream) return false;   // fast path: same launcher as last time
+  std::lock_guard<std::mutex> lock(mu);
+  if (me == 0) { static size_t next_id = 0; me = ++next_id; }
+  last = stream;
+  bool known = false;
+  for (auto &e : seen) known = known || (e.first == me && e.second == stream);
+  if (!known) seen.emplace_back(me, stream);
+  if (seen.size() > 1) many.store(true);
+  return seen.size() > 1;
+}
+}  // namespace
+
+bool prepare_resident_launch(const void *kernel, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attrs, bool only_if_concurrent) {
+  static const int coop_env = [] { const char *e = getenv("TPP_XSMM_COOP"); return e ? atoi(e) : -1; }();   // 0 never, 1 always
+  const bool concurrent = concurrent_launchers_seen(cfg->stream);
+  const bool coop = coop_env == 0 ? false : coop_env == 1 ? true : (!only_if_concurrent || concurrent);
   const size_t ctas = (size_t)cfg->gridDim.x * cfg->gridDim.y * cfg->gridDim.z;
   size_t cluster = 1;
   for (unsigned i = 0; i < cfg->numAttrs; ++i)
@@ -192,6 +217,7 @@ bool prepare_resident_launch(const void *kernel, cudaLaunchConfig_t *cfg, cudaLa
     capacity = (size_t)per_sm * sms;
   }
   if (capacity < ctas) return false;
+  // (the driver accepts programmatic serialisation + cooperative together, but the launches do not overlap: measured)
   if (coop && attrs[0].id == cudaLaunchAttributeProgrammaticStreamSerialization) {
     attrs[0].id = cudaLaunchAttributeCooperative;
     attrs[0].val.cooperative = 1;
