@@ -782,6 +782,12 @@ def main():
                      "frac": achieved_gbs / pk["hbm_gbs"], "traffic": traffic, "traffic_source": traffic_src,
                      "kernel": timed_kernel, "peak_source": pk["source"],
                      "algorithmic_bytes_per_launch": bytes_per_launch, "avg_launch_us": avg_launch_s * 1e6,
+                     # every layer's C is an output buffer of its invoke (reference semantics): counting the two
+                     # intermediate activations the DRAM has to absorb as well
+                     "incl_intermediate_outputs": {
+                         "bytes_per_forward_pass": fwd_bytes + 2 * m_rank * 1024 * 2,
+                         "achieved": (fwd_bytes + 2 * m_rank * 1024 * 2) * fwd_per_launch / avg_launch_s / 1e9,
+                         "frac": (fwd_bytes + 2 * m_rank * 1024 * 2) * fwd_per_launch / avg_launch_s / 1e9 / pk["hbm_gbs"]},
                      "launches_timed": launches, "forward_passes_per_launch": fwd_per_launch,
                      "bytes_per_forward_pass": fwd_bytes,
                      "tensor": {"achieved": achieved_tflops, "unit": "TFLOP/s", "peak_burst": pk["bf16_tflops"],
