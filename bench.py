@@ -342,7 +342,7 @@ def run_standin():
     for tiles, vnni, label in (("32,32,32", 2, "reference default (benchmarks/config/omp/mlir-bf16.json:37)"),
                                ("256,1024,1024", 0, "GPU tiling (SURVEY.md Appendix B)")):
         for mode, n in (("strict", 3 if tiles == "32,32,32" else 20), ("device", 10 if tiles == "32,32,32" else 300),
-                        ("graph", 300)):
+                        ("lazy", 100), ("graph", 300)):
             cmd = [exe, "--batch", "256", "--layers", "1024,1024,1024,1024", "--tiles", tiles, "--vnni", str(vnni), "-n",
                    str(n), "--seed", "123", "--mode", mode]
             try:
@@ -353,8 +353,9 @@ def run_standin():
             row["tiles"], row["vnni"], row["config"] = tiles, vnni, label
             out.append(row)
     return {"what": "mean seconds per forward pass as tpp-run would print it; strict = plain host pointers (an unmodified "
-                    "tpp-run), device = arguments registered on the GPU (patches/0004), graph = + the timed body "
-                    "captured and replayed (patches/0005); ONE forward pass on ONE set of buffers, sequential",
+                    "tpp-run), device = arguments registered on the GPU (patches/0004), lazy = device + xsmm_cuda_set_lazy (the same "
+                    "invoke loop, queued and launched fused at the timer), graph = device + the timed body captured and "
+                    "replayed (patches/0005); ONE forward pass on ONE set of buffers, sequential",
             "runs": out}
 
 

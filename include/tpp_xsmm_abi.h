@@ -260,6 +260,16 @@ TPP_XSMM_EXPORT int64_t xsmm_cuda_graph_end(void);
 TPP_XSMM_EXPORT void xsmm_cuda_graph_launch(int64_t graph);
 TPP_XSMM_EXPORT void xsmm_cuda_graph_destroy(int64_t graph);
 
+/* Lazy mode (per thread; TPP_XSMM_LAZY=1 turns it on for every thread): outside a graph capture, BRGEMM and tile-move
+ * invokes on device / registered operands are QUEUED instead of launched and go out - folded into layers, chained and
+ * batched exactly as a captured sequence would be - at the next flush point: xsmm_cuda_sync, xsmm_cuda_stream_sync,
+ * perf_start_timer / perf_stop_timer, the update / upload / download calls, xsmm_cuda_set_stream, xsmm_cuda_graph_*, an
+ * invoke that cannot be queued (plain host operands, f32, ...), or 16384 queued invokes. An invoke loop without any
+ * graph call (tools/tpp-run with device arguments, patches/0004) then runs on the fused kernels. Contract: drain through
+ * one of those calls before operands are read, written or freed by any other means (cudaMemcpy, cudaFree, another
+ * stream). Turning it off flushes. */
+TPP_XSMM_EXPORT void xsmm_cuda_set_lazy(int64_t on);
+
 /* Introspection used by the tests and by bench.py's "gpu_launches". */
 TPP_XSMM_EXPORT int64_t xsmm_cuda_launch_count(void);
 /* Name of the kernel variant the last invoke on this thread launched

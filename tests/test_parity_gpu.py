@@ -616,16 +616,18 @@ def test_tpp_run_standin_modes_agree(tiles, vnni):
     if not os.path.exists(exe):
         exe = _build.build_standin()
     rows = {}
-    for mode in ("strict", "device", "graph"):
+    for mode in ("strict", "device", "lazy", "graph"):
         r = subprocess.run([exe, "--batch", "256", "--layers", "256,512,256", "--tiles", tiles, "--vnni", str(vnni), "-n", "2",
                             "--mode", mode], capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, r.stderr
         rows[mode] = json.loads(r.stdout.strip().splitlines()[-1])
     ref = rows["strict"]["checksum"]
     assert ref > 0
-    for mode in ("device", "graph"):
+    for mode in ("device", "lazy", "graph"):
         assert abs(rows[mode]["checksum"] - ref) <= 1e-2 * abs(ref), rows
-    assert "pair256x256" in rows["graph"]["kernel"] or "chain" in rows["graph"]["kernel"], rows["graph"]
+    for mode in ("lazy", "graph"):
+        assert "pair256x256" in rows[mode]["kernel"] or "chain" in rows[mode]["kernel"], rows[mode]
+    assert rows["lazy"]["launches"] < rows["device"]["launches"], rows
 
 
 @pytest.mark.parametrize("tiles", [(256, 1024, 1024), (64, 64, 64), (32, 32, 32)])
@@ -682,6 +684,39 @@ def test_unfused_layers_are_combined_under_capture(tiles, with_zero):
     xsmm.sync()
     assert xsmm.launch_count() - n0 > 2
     assert_close(BF16, _blocked_out(cfg, r), want)
+
+
+def test_lazy_mode_queues_invokes_and_keeps_program_order():
+    """Lazy mode (xsmm_cuda_set_lazy): the uncaptured tile-invoke stream of a 2-layer block-packed MLP is queued and goes
+    out as one fused launch at sync(); ops that cannot be queued (a unary relu on another buffer, a binary op) flush the
+    queue first, so program order is kept; turning lazy mode off flushes."""
+    import torch
+
+    from tpp_mlir_b200 import xsmm
+
+    cfg, (r,), (want,) = _blocked_mlp((32, 32, 32), True)
+    xsmm.set_lazy(True)
+    try:
+        n0 = xsmm.launch_count()
+        r.forward()
+        assert xsmm.launch_count() == n0, "nothing is launched before a flush point"
+        xsmm.sync()
+        assert xsmm.launch_count() - n0 == 1, xsmm.launch_count() - n0
+        assert "pair256x256_blocked_vnni2" in xsmm.last_kernel(), xsmm.last_kernel()
+        assert_close(BF16, _blocked_out(cfg, r), want)
+        # program order against a consumer that is not a BRGEMM: out2 = relu(result) must see the NEW result
+        for a in r.acts[1:]:
+            a.zero_()
+        out2 = torch.zeros_like(r.acts[-1])
+        hr = xsmm.unary_dispatch(xsmm.UNARY_RELU, BF16, 256, 1024, 1024, 1024, 0)
+        r.forward()
+        xsmm.unary_invoke(BF16, hr, r.acts[-1], 0, out2, 0)   # flushes the queued layers first
+        xsmm.set_lazy(False)
+        xsmm.sync()
+        np.testing.assert_array_equal(out2.cpu().numpy(), r.acts[-1].cpu().numpy())
+        assert_close(BF16, _blocked_out(cfg, r), want)
+    finally:
+        xsmm.set_lazy(False)
 
 
 def test_perf_timer_includes_async_launches():

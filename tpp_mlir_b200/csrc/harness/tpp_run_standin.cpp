@@ -11,10 +11,12 @@
 //   --mode strict   plain host pointers, nothing registered: an UNMODIFIED tpp-run linked against this library
 //   --mode device   arguments live on the device (what MLIRBench::registerOnGpu gives the patched runner,
 //                   patches/0004): invokes take the in-place path, one launch per invoke
+//   --mode lazy     device arguments + xsmm_cuda_set_lazy(1): the same invoke loop, no graph calls; invokes are queued and
+//                   launched fused at perf_stop_timer (what TPP_XSMM_LAZY=1 gives the patched runner WITHOUT patches/0005)
 //   --mode graph    device arguments + the timed body recorded once and replayed (patches/0005)
 //
 //   tpp_run_standin [--batch 256] [--layers 1024,1024,1024,1024] [--tiles 32,32,32] [--vnni 2] [-n 100] [--seed 123]
-//                   [--mode strict|device|graph]
+//                   [--mode strict|device|lazy|graph]
 // prints: seconds per iteration (mean), GFLOP/s by mlir-gen's flop count, and a checksum of the output.
 #include <algorithm>
 #include <cmath>
@@ -124,6 +126,7 @@ int main(int argc, char **argv) {
     }
   }
 
+  if (mode == "lazy") xsmm_cuda_set_lazy(1);
   char amx_state[64];
   auto kernel = [&]() {   // the loop nest the pipeline emits (scf.parallel serialised on one stream)
     for (int64_t l = 0; l < L; ++l) {

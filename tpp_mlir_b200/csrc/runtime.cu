@@ -92,6 +92,7 @@ struct PendingTile {
   char *in, *out;
 };
 
+constexpr size_t kLazyQueueMax = 16384;   // lazy mode: invokes queued before a flush is forced
 constexpr int kDownloadRing = 64;   // downloads xsmm_cuda_wait_host can still find (callers fall back to a stream sync)
 
 struct ThreadCtx {
@@ -109,6 +110,24 @@ struct ThreadCtx {
   int device = -1;               // device this thread last launched on
   const char *last_kernel = "";
   Staging stage[4];
+  // lazy mode (xsmm_cuda_set_lazy / TPP_XSMM_LAZY=1): outside a capture BRGEMM / tile-move invokes on device operands are
+  // queued exactly as during a capture and launched - folded into layers, chained, batched - at the next flush point:
+  // any sync entry point, a host-visible operation of this ABI, an invoke that cannot be queued, a full queue. An
+  // unmodified invoke loop (no graph calls) then gets the fused kernels. The caller must drain through this ABI
+  // (xsmm_cuda_sync / perf_stop_timer / xsmm_cuda_update_host ...) before it reads or frees operands by other means.
+  bool lazy = false;
+  bool lazy_init = false;
+  bool recording() {
+    if (!lazy_init) {
+      lazy_init = true;
+      const char *e = getenv("TPP_XSMM_LAZY");
+      lazy = e && e[0] == '1';
+    }
+    return capturing || lazy;
+  }
+  // device tables of lazily launched fused kernels: freed once the event recorded after their launch has completed
+  struct Retired { cudaEvent_t ev = nullptr; std::vector<void *> ptrs; };
+  std::vector<Retired> retired;
   // graph capture (xsmm_cuda_graph_begin/end)
   bool capturing = false;
   cudaStream_t capture_stream = nullptr;   // internal stream used when the thread is on the legacy stream
@@ -579,7 +598,9 @@ void flush_tiles();
 void flush_held_zero();
 const KernelDesc *fused_variant(const KernelDesc *d, bool add_bias, bool relu, bool beta0);
 
-void flush_pending() {
+void retire_lazy_allocs(bool all_done);
+
+void flush_pending_impl() {
   if (t_ctx.up_pending) {   // kernels issued from here on see every upload_async issued before them
     TPP_CUDA_CHECK(cudaStreamWaitEvent(t_ctx.stream, t_ctx.ev_up, 0));
     t_ctx.up_pending = false;
@@ -656,6 +677,41 @@ void flush_pending() {
   }
 }
 
+// Device tables the fused kernels of a LAZY flush read (outside a capture nothing owns them): parked with an event and
+// freed when it has completed; all_done = the device has been drained.
+void retire_lazy_allocs(bool all_done) {
+  for (size_t i = 0; i < t_ctx.retired.size();) {
+    ThreadCtx::Retired &r = t_ctx.retired[i];
+    if (all_done || cudaEventQuery(r.ev) == cudaSuccess) {
+      for (void *p : r.ptrs) cudaFree(p);
+      cudaEventDestroy(r.ev);
+      t_ctx.retired[i] = std::move(t_ctx.retired.back());
+      t_ctx.retired.pop_back();
+    } else {
+      ++i;
+    }
+  }
+  cudaGetLastError();   // cudaEventQuery's cudaErrorNotReady is not an error
+}
+
+void flush_pending() {
+  flush_pending_impl();
+  if (t_ctx.capturing) return;
+  // lazy mode: whatever the launches allocated belongs to nobody - retire it behind an event
+  std::vector<void *> tables;
+  brgemm_tc_take_capture_allocs(tables);
+  tables.insert(tables.end(), t_ctx.capture_tables.begin(), t_ctx.capture_tables.end());
+  t_ctx.capture_tables.clear();
+  if (!tables.empty()) {
+    ThreadCtx::Retired r;
+    TPP_CUDA_CHECK(cudaEventCreateWithFlags(&r.ev, cudaEventDisableTiming));
+    TPP_CUDA_CHECK(cudaEventRecord(r.ev, t_ctx.stream));
+    r.ptrs.swap(tables);
+    t_ctx.retired.push_back(std::move(r));
+  }
+  if (!t_ctx.retired.empty()) retire_lazy_allocs(false);
+}
+
 // TPP_XSMM_HOST_PROFILE=1: where the host time of a BRGEMM invoke goes (printed at thread exit)
 const bool g_host_prof = getenv("TPP_XSMM_HOST_PROFILE") != nullptr;
 struct HostProf {
@@ -729,7 +785,7 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
   } else {
     t_ctx.pdl_run = 0;                     // generic kernels / captured work are launched in plain stream order
   }
-  if (t_ctx.capturing && t_ctx.held_zero.d) {
+  if (t_ctx.recording() && t_ctx.held_zero.d) {
     const ThreadCtx::HeldZero z = t_ctx.held_zero;
     if (!sc.any_host && !beta0 && d->dtype == z.d->dtype && z.out == ops[2].dev && z.d->m == d->m && z.d->n == d->n &&
         z.d->ldo == d->ldc && t_ctx.pending_tiles.empty()) {
@@ -739,9 +795,10 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
       flush_pending();                           // earlier BRGEMMs, then the zero, then this invoke
     }
   }
-  if (t_ctx.capturing && !sc.any_host && d->dtype == kBF16 && (d->impl == KernelImpl::BrgemmTC || d->flat_twin)) {
+  if (t_ctx.recording() && !sc.any_host && d->dtype == kBF16 && (d->impl == KernelImpl::BrgemmTC || d->flat_twin)) {
     flush_tiles();
     t_ctx.pending.push_back({d, g});   // launched (possibly fused with its neighbours) by flush_pending()
+    if (!t_ctx.capturing && t_ctx.pending.size() >= kLazyQueueMax) flush_pending();   // lazy mode: bounded queue
     return;
   }
   flush_pending();
@@ -1019,7 +1076,7 @@ const KernelDesc *fused_variant(const KernelDesc *d, bool add_bias, bool relu, b
 // the last pending BRGEMM if its output tile is exactly [C, m x n, pitch ld] of this dtype
 PendingGemm *pending_producer_of(int64_t dtype, const char *C, int64_t m, int64_t n, int64_t ld) {
   static const bool off = [] { const char *e = getenv("TPP_XSMM_COMBINE"); return e && e[0] == '0'; }();
-  if (off || !t_ctx.capturing || t_ctx.pending.empty() || !t_ctx.pending_tiles.empty()) return nullptr;
+  if (off || !t_ctx.recording() || t_ctx.pending.empty() || !t_ctx.pending_tiles.empty()) return nullptr;
   PendingGemm &p = t_ctx.pending.back();
   if (p.d->dtype != dtype || static_cast<const char *>(p.g.C) != C || p.d->m != m || p.d->n != n || p.d->ldc != ld) return nullptr;
   return &p;
@@ -1030,11 +1087,11 @@ PendingGemm *pending_producer_of(int64_t dtype, const char *C, int64_t m, int64_
 static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int64_t offIn, bool use_imm, float imm,
                               void *pOut, int64_t offOut) {
   // tile moves (plain identity copy / transpose) issued during graph capture are collected, see flush_tiles()
-  const bool batchable = t_ctx.capturing && !use_imm &&
+  const bool batchable = t_ctx.recording() && !use_imm &&
                          (d->impl == KernelImpl::Transpose ||
                           (d->impl == KernelImpl::Eltwise && d->kind == XSMM_UNARY_IDENTITY && d->flags == 0));
   if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
-  if (t_ctx.capturing && !use_imm && d->impl == KernelImpl::Eltwise && d->flags == 0 && d->dtype == kBF16) {
+  if (t_ctx.recording() && !use_imm && d->impl == KernelImpl::Eltwise && d->flags == 0 && d->dtype == kBF16) {
     if (d->kind == XSMM_UNARY_RELU && pIn == pOut && offIn == offOut && d->ldi == d->ldo) {
       // relu(C, C) right after the BRGEMM that produces C: becomes that invoke's epilogue
       Resolved r = resolve(pOut, elem_ptr(dtype, pOut, offOut));
@@ -1147,7 +1204,7 @@ extern "C" void xsmm_binary_invoke(int64_t dtype, int64_t addr, void *alignedPtr
                                    void *alignedPtrRhs, int64_t offsetRhs, void *alignedPtrOut, int64_t offsetOut) {
   const KernelDesc *d = desc_of(addr, OpClass::Binary);
   if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
-  if (t_ctx.capturing && d->dtype == kBF16 && d->kind == XSMM_BINARY_ADD && d->flags == XSMM_BINARY_FLAG_BCAST_COL_IN_0 &&
+  if (t_ctx.recording() && d->dtype == kBF16 && d->kind == XSMM_BINARY_ADD && d->flags == XSMM_BINARY_FLAG_BCAST_COL_IN_0 &&
       alignedPtrRhs == alignedPtrOut && offsetRhs == offsetOut && d->ldi2 == d->ldo) {
     // add(bias[bcast_col_in0], C, C) right after the BRGEMM that produces C: becomes that invoke's epilogue
     Resolved rc = resolve(alignedPtrOut, elem_ptr(dtype, alignedPtrOut, offsetOut));
@@ -1195,13 +1252,21 @@ extern "C" void xsmm_intel_amx_tile_config_invoke(int64_t dtype, int64_t addr, v
 // ================================ perf timers ========================================
 
 extern "C" int64_t perf_start_timer(void) {
-  if (g_cuda_ready.load()) TPP_CUDA_CHECK(cudaDeviceSynchronize()); // earlier async work is not ours to time
+  if (g_cuda_ready.load() && !t_ctx.capturing) {   // earlier async (or lazily queued) work is not ours to time
+    flush_pending();
+    TPP_CUDA_CHECK(cudaDeviceSynchronize());
+    retire_lazy_allocs(true);
+  }
   auto timestamp = std::chrono::high_resolution_clock::now();
   return timestamp.time_since_epoch().count();
 }
 
 extern "C" double perf_stop_timer(int64_t startTimestamp) {
-  if (g_cuda_ready.load()) TPP_CUDA_CHECK(cudaDeviceSynchronize()); // invokes are asynchronous launches
+  if (g_cuda_ready.load() && !t_ctx.capturing) {   // invokes are asynchronous launches (lazy mode: possibly still queued)
+    flush_pending();
+    TPP_CUDA_CHECK(cudaDeviceSynchronize());
+    retire_lazy_allocs(true);
+  }
   auto stop = std::chrono::high_resolution_clock::now();
   std::chrono::high_resolution_clock::time_point start{std::chrono::high_resolution_clock::duration{startTimestamp}};
   return std::chrono::duration_cast<std::chrono::duration<double>>(stop - start).count();
@@ -1224,6 +1289,7 @@ extern "C" void xsmm_cuda_set_stream(void *stream) {
     return;
   }
   if (t_ctx.stream != static_cast<cudaStream_t>(stream)) {
+    flush_pending();   // lazy mode: what was queued belongs to the old stream
     for (auto &r : t_ctx.recent_out) r = {};
     t_ctx.pdl_run = kPdlWindow;   // first BRGEMM on the new stream: plain stream order
   }   // dependency tracking is per stream; cross-stream order is the caller's
@@ -1245,11 +1311,21 @@ extern "C" void xsmm_cuda_stream_destroy(void *stream) {
 }
 
 extern "C" void xsmm_cuda_sync(void) {
-  if (g_cuda_ready.load()) TPP_CUDA_CHECK(cudaDeviceSynchronize());
+  if (!g_cuda_ready.load()) return;
+  if (!t_ctx.capturing) flush_pending();   // lazy mode: queued invokes are launched first
+  TPP_CUDA_CHECK(cudaDeviceSynchronize());
+  if (!t_ctx.capturing) retire_lazy_allocs(true);
+}
+
+extern "C" void xsmm_cuda_set_lazy(int64_t on) {
+  if (!t_ctx.capturing && !on) flush_pending();
+  t_ctx.lazy_init = true;
+  t_ctx.lazy = on != 0;
 }
 
 extern "C" void xsmm_cuda_stream_sync(void) {
   if (!g_cuda_ready.load()) return;
+  if (!t_ctx.capturing) flush_pending();
   TPP_CUDA_CHECK(cudaStreamSynchronize(t_ctx.stream));
   if (t_ctx.up_stream && !t_ctx.capturing) {   // everything this thread issued, asynchronous copies included
     TPP_CUDA_CHECK(cudaStreamSynchronize(t_ctx.up_stream));
@@ -1386,6 +1462,7 @@ extern "C" void *xsmm_cuda_device_ptr(void *host) {
 extern "C" int64_t xsmm_cuda_graph_begin(void) {
   ensure_cuda();
   if (t_ctx.capturing) return -1;
+  flush_pending();   // lazy mode: earlier invokes are not part of the graph
   t_ctx.saved_stream = t_ctx.stream;
   if (t_ctx.stream == nullptr) { // the legacy default stream cannot be captured
     if (!t_ctx.capture_stream) TPP_CUDA_CHECK(cudaStreamCreateWithFlags(&t_ctx.capture_stream, cudaStreamNonBlocking));

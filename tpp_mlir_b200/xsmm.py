@@ -73,6 +73,7 @@ EXPORTS = {
     "xsmm_cuda_graph_end": (c_int64, []),
     "xsmm_cuda_graph_launch": (None, [c_int64]),
     "xsmm_cuda_graph_destroy": (None, [c_int64]),
+    "xsmm_cuda_set_lazy": (None, [c_int64]),
     "xsmm_cuda_launch_count": (c_int64, []),
     "xsmm_cuda_last_kernel": (c_char_p, []),
     "xsmm_cuda_handle_kernel": (c_char_p, [c_int64]),
@@ -200,6 +201,12 @@ def perf_stop_timer(t0: int) -> float:
 
 def sync() -> None:
     LIB.xsmm_cuda_sync()
+
+
+def set_lazy(on: bool) -> None:
+    """Lazy mode of the calling thread: invokes on device operands are queued and launched fused at the next flush
+    point (sync(), perf timers, update_* ...). Turning it off flushes."""
+    LIB.xsmm_cuda_set_lazy(1 if on else 0)
 
 
 def set_stream(stream_ptr: int | None) -> None:
