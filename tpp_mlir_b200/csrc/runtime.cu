@@ -657,7 +657,9 @@ void flush_pending_impl() {
     // many independent chains: one CTA pair per chain (4x less L2 -> SM traffic per layer than the pass kernels)
     int took = launch_brgemm_chains_pair(descs.data(), args.data(), seg_first.data() + sidx, seg_len.data() + sidx,
                                          (int)(run - sidx), stream, force);
-    if (took == 0 && chains)
+    // (the few-chain kernels own per-launch counters: an allocation and a sync each time, which only a captured graph
+    // amortises - a lazily flushed lone chain goes out as PDL-chained per-layer launches instead)
+    if (took == 0 && chains && t_ctx.capturing)
       took = launch_brgemm_chains_ft(descs.data(), args.data(), seg_first.data() + sidx, seg_len.data() + sidx,
                                      (int)(run - sidx), stream);
     if (took > 0) {
@@ -667,7 +669,7 @@ void flush_pending_impl() {
       continue;
     }
     const int f = seg_first[sidx], L = seg_len[sidx];
-    if (chains && launch_brgemm_chain(descs.data() + f, args.data() + f, L, stream)) {
+    if (chains && t_ctx.capturing && launch_brgemm_chain(descs.data() + f, args.data() + f, L, stream)) {
       t_ctx.last_kernel = brgemm_tc_last_name();
       count_launch();
     } else {
