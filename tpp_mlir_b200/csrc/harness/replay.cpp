@@ -119,6 +119,34 @@ int64_t tpp_replay_mlp_graph(int64_t dtype, int64_t num_layers, const int64_t *h
   return 0;
 }
 
+// The benchmark loop of tpp-run itself: `steps` forward passes on ONE set of buffers, back to back. graphs[0] replays
+// `unroll` consecutive forward passes captured as one graph (the loop body unrolled before capture: the runtime runs the
+// exact repeats as one launch, a plain sequence of layer passes), graphs[1] one forward pass (the remainder).
+__attribute__((visibility("default")))
+int64_t tpp_replay_mlp_graph_unrolled(int64_t dtype, int64_t num_layers, const int64_t *handles, const int64_t *layer_sizes,
+                                      int64_t batch, int64_t bn, int64_t bk, int64_t bc, const TppMlpSet *set,
+                                      int64_t *graphs, int64_t unroll, int64_t steps, int64_t has_bias) {
+  if (unroll < 1) unroll = 1;
+  int64_t s = 0;
+  if (unroll > 1 && steps >= unroll) {
+    if (!graphs[0]) {
+      if (xsmm_cuda_graph_begin() != 0) return -1;
+      tpp_replay_mlp(dtype, num_layers, handles, layer_sizes, batch, bn, bk, bc, set, 1, 0, unroll, has_bias);
+      if (!(graphs[0] = xsmm_cuda_graph_end())) return -1;
+    }
+    for (; s + unroll <= steps; s += unroll) xsmm_cuda_graph_launch(graphs[0]);
+  }
+  if (s < steps) {
+    if (!graphs[1]) {
+      if (xsmm_cuda_graph_begin() != 0) return -1;
+      tpp_replay_mlp(dtype, num_layers, handles, layer_sizes, batch, bn, bk, bc, set, 1, 0, 1, has_bias);
+      if (!(graphs[1] = xsmm_cuda_graph_end())) return -1;
+    }
+    for (; s < steps; ++s) xsmm_cuda_graph_launch(graphs[1]);
+  }
+  return 0;
+}
+
 // One forward on host buffers that were registered with xsmm_cuda_register_host: upload the
 // step's input, run the layers on the mirrors, download the step's output, wait for it.
 // use_graph != 0: the whole step (H2D copy, invokes, D2H copy) is captured once with

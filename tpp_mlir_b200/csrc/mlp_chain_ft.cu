@@ -736,6 +736,25 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   const KernelDesc &d0 = *descs[first[0]];
   int split = chain_ft_split(descs + first[0], args + first[0], len[0]);
   // ---- which chains go into this launch ----
+  // `sequential`: the following chains are EXACT REPEATS of the first one (same descriptors, same buffers: the unrolled
+  // iterations of a benchmark loop, lib/TPP/Runner/MLIRBench.cpp:265-300). They depend on each other, but only through
+  // buffers every CTA group (one 32-row batch tile) partitions the same way, so they can share one launch as a plain
+  // sequence of passes: a repeat's first layer reads the never-written input (no wait, it overlaps the previous
+  // repeat's last layer), its stores to an intermediate buffer come after every CTA of the row tile has passed the
+  // barrier behind the previous repeat's reader of that buffer (barriers are cumulative and no CTA runs more than one
+  // arrival ahead), and the final output is rewritten by the same CTA in order. What this removes is the ~5 us between
+  // two graph launches that a one-forward-per-graph replay pays.
+  bool sequential = false;
+  auto is_repeat = [&](int c) {
+    if (len[c] != len[c - 1]) return false;
+    for (int l = 0; l < len[c]; ++l) {
+      const GemmArgs &a = args[first[c] + l], &b = args[first[c - 1] + l];
+      if (descs[first[c] + l] != descs[first[c - 1] + l] || a.A != b.A || a.B != b.B || a.C != b.C || a.D != b.D ||
+          a.batch != b.batch)
+        return false;
+    }
+    return true;
+  };
   int take = 1, passes = len[0];
   {
     std::vector<ByteRange> in_all, out_all;
@@ -757,7 +776,12 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
       }
       for (const ByteRange &i : in)
         for (const ByteRange &x : out_all) indep = indep && !overlaps(i, x);
-      if (!indep) break;
+      if (!indep) {
+        if ((take == 1 || sequential) && is_repeat(c)) sequential = true;   // a run of exact repeats
+        else break;
+      } else if (sequential) {
+        break;                                                            // do not mix the two kinds in one pass list
+      }
       in_all.insert(in_all.end(), in.begin(), in.end());
       out_all.insert(out_all.end(), out.begin(), out.end());
       passes += len[c];
@@ -766,7 +790,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   }
   // one or two chains per launch have nothing to hide the exchange latency behind: the full-K kernel is faster there
   // (11.0 vs 14.7 us for a single forward); every split-K shape is also a full-K shape
-  if (take < 3) split = 1;
+  if (take < 3 || sequential) split = 1;
   const bool split2 = split > 1;
   // ---- the pass list: `ways` chains at a time interleaved layer by layer; a chain's counter slot is its position in
   // the tuple. One chain's layer-to-layer latency (store, fence, counter, poll, TMA: ~5000 clk) is longer than one
@@ -813,6 +837,10 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     return true;
   };
   bool ok = true;
+  if (sequential) {
+    for (int c = 0; c < take && ok; ++c)
+      for (int l = 0; l < len[c] && ok; ++l) ok = add_pass(c, l, 0);
+  } else
   for (int c = 0; c < take && ok; c += ways) {
     const int nc = std::min(ways, take - c);
     int maxL = 0;
@@ -896,7 +924,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   else TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_ft_kernel, cp));
   const char *tile = split == 4 ? "ft64x128_splitk4" : split == 2 ? "ft64x64_splitk2" : "ft64x32_fullk";
   if (take == 1) set_last_name("mlp_chain_bf16_%dlayers_%s", len[0], tile);
-  else set_last_name("mlp_chain_bf16_%dx%dlayers_%s", take, len[0], tile);
+  else set_last_name("mlp_chain_bf16_%dx%dlayers_%s%s", take, len[0], tile, sequential ? "_seq" : "");
   return take;
 }
 

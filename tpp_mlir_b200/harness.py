@@ -239,6 +239,8 @@ def replay_lib():
         lib.tpp_replay_mlp_e2e_pipelined.restype = i64
         lib.tpp_replay_mlp_graph.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, i64, p, i64, i64, i64, i64]
         lib.tpp_replay_mlp_graph.restype = i64
+        lib.tpp_replay_mlp_graph_unrolled.argtypes = [i64, i64, p, p, i64, i64, i64, i64, p, p, i64, i64, i64]
+        lib.tpp_replay_mlp_graph_unrolled.restype = i64
         _replay_lib = lib
     return _replay_lib
 
@@ -292,6 +294,20 @@ class NativeMlpLoop:
         if rc != 0:
             raise RuntimeError("CUDA graph capture of the MLP forward failed")
         self._step += steps
+
+    def run_graph_unrolled(self, steps: int, unroll: int = 16) -> None:
+        """tpp-run's own benchmark loop: `steps` forward passes on operand set 0, back to back, replayed from a graph
+        that holds `unroll` consecutive forward passes (the loop body unrolled before capture)."""
+        cfg = self.cfg
+        bn, bk, bc = cfg.tiles
+        key = f"_unrolled_{unroll}"
+        if not hasattr(self, key):
+            setattr(self, key, (_ct.c_int64 * 2)())
+        rc = replay_lib().tpp_replay_mlp_graph_unrolled(cfg.dtype, cfg.num_layers, self._handles, self._sizes, cfg.batch, bn,
+                                                        bk, bc, self._sets, getattr(self, key), unroll, steps,
+                                                        1 if cfg.bias else 0)
+        if rc != 0:
+            raise RuntimeError("CUDA graph capture of the unrolled MLP loop failed")
 
     def run_e2e(self, steps: int, elem_size: int = 2, graph: bool = True) -> None:
         """Host buffers registered with xsmm.register_host: per step H2D(input), layers, D2H(output), stream
