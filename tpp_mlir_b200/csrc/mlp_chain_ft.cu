@@ -41,6 +41,7 @@ constexpr int FT_GROUP = 4;                       // k-blocks per TMA box / barr
 constexpr int FT_NG = FT_KB / FT_GROUP;
 constexpr int FT_X_BYTES = FT_N * BLOCK_K * 2;    // 4 KiB
 constexpr int FT_W_BYTES = BLOCK_K * FT_M * 2;    // 8 KiB
+constexpr int FT_OUT_BYTES = FT_N * FT_M * 2;     // 4 KiB output staging (transposed back to row-major before it leaves the SM)
 constexpr int FT_CTR_STRIDE = 32;                 // one 128-byte line per batch-tile counter
 constexpr int FT_CTR_SLOT = 160 * FT_CTR_STRIDE;  // counters of chain slot s start at s * FT_CTR_SLOT
 constexpr int FT_MAX_WAYS = 4;                    // chains interleaved in one launch (= counter slots)
@@ -98,7 +99,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_x = smem_base;                                   // FT_KB x 4 KiB
   const uint32_t smem_w = smem_base + FT_KB * FT_X_BYTES;              // FT_KB x 8 KiB
-  const uint32_t bar_base = smem_w + FT_KB * FT_W_BYTES;
+  const uint32_t smem_out = smem_w + FT_KB * FT_W_BYTES;               // 4 KiB: the output tile, [32 rows][64 features]
+  const uint32_t bar_base = smem_out + FT_OUT_BYTES;
   const uint32_t x_full = bar_base;                                    // [FT_NG]
   const uint32_t w_full = bar_base + 8 * FT_NG;                        // [FT_NG]
   const uint32_t w_empty = bar_base + 16 * FT_NG;                      // [FT_NG] group's X and W slots consumed
@@ -311,14 +313,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(acc_free + 8 * par);
+      // TMEM lane = feature, column = batch row: the tile is transposed back through shared memory so that it leaves
+      // the SM as 16-byte pieces of row-major rows (2 store instructions per thread instead of 32 two-byte stores whose
+      // acknowledgements the release fence below then had to wait for: stored -> arrived was 1100-1500 clk)
       if (active) {
-        uint16_t *out = static_cast<uint16_t *>(ps.C) + (int64_t)m0 * ps.ldc + n0 + f;
-        if (ps.relu) {
+        const uint32_t dst = smem_out + (uint32_t)f * 2u;
 #pragma unroll
-          for (int j = 0; j < FT_N; ++j) out[(int64_t)j * ps.ldc] = f32_to_bf16_bits(relu_f32(__uint_as_float(r[j]) + bias));
-        } else {
+        for (int j = 0; j < FT_N; ++j) {
+          const float v = __uint_as_float(r[j]) + bias;
+          const uint16_t h = f32_to_bf16_bits(ps.relu ? relu_f32(v) : v);
+          asm volatile("st.shared.u16 [%0], %1;" ::"r"(dst + (uint32_t)j * (FT_M * 2)), "h"(h) : "memory");
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // the whole tile is staged
+      {
+        const int et = (int)threadIdx.x - ep_tid0;          // 0 .. 127
+        uint16_t *crow = static_cast<uint16_t *>(ps.C) + (int64_t)m0 * ps.ldc + n0;
 #pragma unroll
-          for (int j = 0; j < FT_N; ++j) out[(int64_t)j * ps.ldc] = f32_to_bf16_bits(__uint_as_float(r[j]) + bias);
+        for (int c = et; c < FT_N * FT_M * 2 / 16; c += 128) {
+          const int row = c >> 3, col16 = c & 7;
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                       : "r"(smem_out + (uint32_t)c * 16u));
+          *reinterpret_cast<uint4 *>(crow + (int64_t)row * ps.ldc + col16 * 8) = v;
         }
       }
       if (threadIdx.x == ep_tid0) ft_stamp_pass(cp.trace, p, 4);
@@ -330,6 +347,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
           asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter0 + (int)ps.slot * FT_CTR_SLOT) : "memory");
           ft_stamp_pass(cp.trace, p, 5);
         }
+      } else {
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // the staging buffer is free for the next pass
       }
     }
   }
@@ -873,7 +892,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   // data that other SMs fenced to L2 (TMA reads L2); TPP_XSMM_CHAIN_PROXY_FENCE=1 turns it on
   static const bool pf = [] { const char *e = getenv("TPP_XSMM_CHAIN_PROXY_FENCE"); return e && e[0] == '1'; }();
   cp.proxy_fence = pf ? 1 : 0;
-  constexpr int smem1 = FT_KB * (FT_X_BYTES + FT_W_BYTES) + (3 * FT_NG + 4) * 8 + 16 + 1024;
+  constexpr int smem1 = FT_KB * (FT_X_BYTES + FT_W_BYTES) + FT_OUT_BYTES + (3 * FT_NG + 4) * 8 + 16 + 1024;
   const int smem = split == 4 ? FS<4>::SMEM : split == 2 ? FS<2>::SMEM : smem1;
   static std::once_flag once;
   std::call_once(once, [] {
