@@ -285,6 +285,13 @@ TPP_XSMM_EXPORT void xsmm_cuda_debug_dump_trace(void);
  * equal pitches (tiles of one matrix interleave in address space without touching), conservative otherwise. */
 TPP_XSMM_EXPORT int64_t xsmm_cuda_debug_rects_overlap(const void *a, int64_t a_rows, int64_t a_width, int64_t a_ld,
                                                       const void *b, int64_t b_rows, int64_t b_width, int64_t b_ld);
+/* Debug / test hook (no device needed): the layer the capture path folds a run of `num` bf16 tile invokes into (one
+ * descriptor, operand offsets in elements per invoke; d_off may be NULL). out[0..7] = grid_n, grid_k, a_step, b_step,
+ * c_step_n, c_step_k, d_step, invokes folded into the first layer (1 = not a grid). */
+TPP_XSMM_EXPORT int64_t xsmm_cuda_debug_fold_grid(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc,
+                                                  int64_t stride_a, int64_t stride_b, int64_t flags, int64_t batch,
+                                                  int64_t num, const int64_t *a_off, const int64_t *b_off,
+                                                  const int64_t *c_off, const int64_t *d_off, int64_t *out);
 /* ABI version of this header. */
 TPP_XSMM_EXPORT int64_t xsmm_cuda_abi_version(void);
 

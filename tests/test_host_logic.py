@@ -146,3 +146,60 @@ def test_bench_keeps_library_chatter_off_stdout():
     assert r.returncode == 0, r.stderr
     assert r.stdout == "{}\n"
     assert "python noise" in r.stderr and "native noise" in r.stderr
+
+
+# ---- folding of captured tile invokes into layers (runtime.cu: fold_grid), no GPU needed --------------------------------
+def _fold(m, n, k, lda, ldb, ldc, sa, sb, flags, batch, invokes, with_bias=True):
+    import ctypes
+
+    from tpp_mlir_b200 import xsmm
+
+    num = len(invokes)
+    arr = lambda col: (ctypes.c_int64 * num)(*[inv[col] for inv in invokes])   # noqa: E731
+    out = (ctypes.c_int64 * 8)()
+    xsmm.LIB.xsmm_cuda_debug_fold_grid(m, n, k, lda, ldb, ldc, sa, sb, flags, batch, num, arr(0), arr(1), arr(2),
+                                       arr(3) if with_bias else None, out)
+    return dict(zip(("grid_n", "grid_k", "a_step", "b_step", "c_step_n", "c_step_k", "d_step", "folded"), out))
+
+
+def _appendix_b_invokes(mb, c, kk, bn, bk, bc, order="nk"):
+    """operand offsets of one layer of the block-packed MLP, (iN outer, iK inner) or reversed"""
+    nb_c, nb_k = c // bc, kk // bk
+    pairs = [(i, j) for i in range(mb // bn) for j in range(nb_k)] if order == "nk" else \
+            [(i, j) for j in range(nb_k) for i in range(mb // bn)]
+    return [(i * nb_c * bn * bc, j * nb_c * bc * bk, (i * nb_k + j) * bn * bk, j * bk) for i, j in pairs]
+
+
+def test_fold_reference_default_layer():
+    """benchmarks/config/omp/mlir-bf16.json:37 (--tiles=32,32,32): 256 invokes per layer fold into an 8 x 32 grid"""
+    inv = _appendix_b_invokes(256, 1024, 1024, 32, 32, 32)
+    r = _fold(32, 32, 32, 32, 32, 32, 1024, 1024, 4 | 2048, 32, inv)
+    assert r == {"grid_n": 8, "grid_k": 32, "a_step": 32 * 1024, "b_step": 32 * 1024, "c_step_n": 32 * 1024, "c_step_k": 1024,
+                 "d_step": 32, "folded": 256}
+
+
+def test_fold_stops_at_the_layer_boundary_and_handles_both_loop_orders():
+    layer0 = _appendix_b_invokes(256, 512, 512, 64, 64, 64)
+    # the next layer reads what this one wrote (different A / B / C bases): must not be folded into the same grid
+    layer1 = [(a + 10_000_000, b + 20_000_000, c + 30_000_000, d + 5_000) for a, b, c, d in layer0]
+    r = _fold(64, 64, 64, 64, 64, 64, 4096, 4096, 4, 8, layer0 + layer1)
+    assert (r["grid_n"], r["grid_k"], r["folded"]) == (4, 8, 32)
+    r = _fold(64, 64, 64, 64, 64, 64, 4096, 4096, 4, 8, _appendix_b_invokes(256, 512, 512, 64, 64, 64, order="kn"))
+    assert (r["grid_n"], r["grid_k"], r["folded"]) == (4, 8, 32)
+    assert r["a_step"] == 8 * 4096 and r["b_step"] == 8 * 4096 and r["c_step_k"] == 4096 and r["c_step_n"] == 8 * 4096
+
+
+def test_fold_refuses_irregular_or_hazardous_walks():
+    inv = _appendix_b_invokes(256, 512, 512, 64, 64, 64)
+    shuffled = [inv[i] for i in (2, 0, 3, 1)] + inv[4:]
+    assert _fold(64, 64, 64, 64, 64, 64, 4096, 4096, 4, 8, shuffled)["folded"] == 1
+    # output tiles that overlap each other (c step smaller than a tile): not a layer
+    bad = [(a, b, c // 2, d) for a, b, c, d in inv]
+    assert _fold(64, 64, 64, 64, 64, 64, 4096, 4096, 4, 8, bad)["folded"] == 1
+    # a single invoke, and two invokes that share neither A nor B
+    assert _fold(256, 1024, 1024, 1024, 1024, 1024, 0, 0, 4, 1, [(0, 0, 0, 0)])["folded"] == 1
+    assert _fold(64, 64, 64, 64, 64, 64, 4096, 4096, 4, 8, [(0, 0, 0, 0), (4096 * 8, 4096 * 8, 4096, 64)])["folded"] == 1
+    # flat layouts tiled along n only (one row block): interleaved output tiles of one matrix are fine
+    flat = [(0, j * 64, j * 64, j * 64) for j in range(8)]
+    r = _fold(256, 64, 512, 512, 512, 512, 0, 0, 4, 1, flat)
+    assert (r["grid_n"], r["grid_k"], r["c_step_k"], r["folded"]) == (1, 8, 64, 8)

@@ -1555,5 +1555,36 @@ extern "C" int64_t xsmm_cuda_debug_rects_overlap(const void *a, int64_t a_rows, 
   return rects_overlap(static_cast<const char *>(a), a_rows, a_width, a_ld, static_cast<const char *>(b), b_rows, b_width,
                        b_ld) ? 1 : 0;
 }
+// Debug / test hook (no device needed): what the capture path folds a run of tile invokes into. The invokes share one
+// bf16 descriptor (m, n, k, lda, ldb, ldc, stride_a, stride_b, flags) and batch count; invoke t uses operand offsets
+// a_off[t], b_off[t], c_off[t], d_off[t] (elements; d_off may be NULL). out[0..7] = grid_n, grid_k, a_step, b_step,
+// c_step_n, c_step_k, d_step, number of invokes folded into the first layer.
+extern "C" int64_t xsmm_cuda_debug_fold_grid(int64_t m, int64_t n, int64_t k, int64_t lda, int64_t ldb, int64_t ldc,
+                                             int64_t stride_a, int64_t stride_b, int64_t flags, int64_t batch, int64_t num,
+                                             const int64_t *a_off, const int64_t *b_off, const int64_t *c_off,
+                                             const int64_t *d_off, int64_t *out) {
+  KernelDesc d;
+  d.op = OpClass::FusedBrgemm;
+  d.impl = KernelImpl::BrgemmTC;
+  d.dtype = kBF16;
+  d.m = m; d.n = n; d.k = k; d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.stride_a = stride_a; d.stride_b = stride_b;
+  d.gemm_flags = flags;
+  d.vnni_factor = (flags & XSMM_GEMM_FLAG_ROWMAJOR_B_VNNI) ? 2 : 0;
+  char *const A = reinterpret_cast<char *>(0x100000000ull), *const B = reinterpret_cast<char *>(0x200000000ull),
+             *const C = reinterpret_cast<char *>(0x300000000ull), *const D = reinterpret_cast<char *>(0x400000000ull);
+  std::vector<PendingGemm> list((size_t)num);
+  for (int64_t t = 0; t < num; ++t) {
+    list[(size_t)t].d = &d;
+    GemmArgs &g = list[(size_t)t].g;
+    g.A = A + 2 * a_off[t]; g.B = B + 2 * b_off[t]; g.C = C + 2 * c_off[t];
+    g.D = d_off ? D + 2 * d_off[t] : nullptr;
+    g.batch = batch;
+  }
+  Layer L;
+  const size_t folded = num > 0 ? fold_grid(list, 0, &L) : 0;
+  out[0] = L.g.grid_n; out[1] = L.g.grid_k; out[2] = L.g.a_step; out[3] = L.g.b_step; out[4] = L.g.c_step_n;
+  out[5] = L.g.c_step_k; out[6] = L.g.d_step; out[7] = (int64_t)folded;
+  return 0;
+}
 extern "C" int64_t xsmm_cuda_abi_version(void) { return 1; }
 extern "C" void xsmm_cuda_debug_dump_trace(void) { brgemm_tc_dump_trace(); }

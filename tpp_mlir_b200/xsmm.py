@@ -74,6 +74,7 @@ EXPORTS = {
     "xsmm_cuda_graph_launch": (None, [c_int64]),
     "xsmm_cuda_graph_destroy": (None, [c_int64]),
     "xsmm_cuda_set_lazy": (None, [c_int64]),
+    "xsmm_cuda_debug_fold_grid": (c_int64, [c_int64] * 11 + [c_void_p] * 5),
     "xsmm_cuda_launch_count": (c_int64, []),
     "xsmm_cuda_last_kernel": (c_char_p, []),
     "xsmm_cuda_handle_kernel": (c_char_p, [c_int64]),
