@@ -79,14 +79,26 @@ struct alignas(128) PcLayer {
   int32_t w64;              // n == 32, flat weights
   int32_t c64;              // n == 32
 };
+// A work item: rows [row0, row0 + 256) of one chain. In a launch with FEW row blocks (a lone forward pass) the output
+// tiles of every layer are dealt out to `nslices` pairs instead - pair `slice` takes tiles slice, slice + nslices, ... - so
+// that one chain occupies several SM pairs; the layer boundary then crosses SMs and goes through per-tile flags in
+// global memory (flag_base, see PcParams::flags) instead of the CTA-local barriers.
 struct PcItem {
-  int32_t layer0, num_layers, row0, pad;
+  int32_t layer0, num_layers, row0;
+  int32_t slice, nslices;   // 0, 1: the whole row block belongs to one pair
+  int32_t flag_base;        // first flag word of this row block: [layer][tile][CTA of the pair]
+  int32_t pad[2];
 };
 struct PcParams {
   const PcLayer *layers;
   const PcItem *items;
   int32_t num_items;
   int32_t l2_hints;            // L2 eviction-priority hints on the TMA loads / stores (TPP_XSMM_CHAIN_PAIR_HINTS=0: off)
+  // column-split items only: flags[flag_base + (l * PC_MAX_TILES + j) * 2 + r] = epoch + 1 once rows 128 r .. of output
+  // tile j of layer l are in L2; epoch[0] = launches completed so far on this table (read at kernel start, bumped by the
+  // last CTA to leave - flags are never reset), epoch[1] = exit ticket
+  unsigned int *flags;
+  unsigned int *epoch;
   int32_t debug;               // TPP_XSMM_PAIR_DEBUG (timing experiments only, results are wrong): 1 = converters skip the
                                // rewrite, 2 = converters skip the proxy fence
   unsigned long long *trace;   // TPP_XSMM_TC_TRACE=4: clock stamps of each CTA's first item (nullptr in normal runs)
@@ -167,6 +179,11 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
       const bool hints = cp.l2_hints != 0;
       int s = 0;
       uint32_t ph = 0, done_ph = 0;                   // done_ph bit j: parity of tile_done[j]'s next phase
+      unsigned int epoch1 = 0;                        // the flag value of THIS launch (column-split items)
+      if (cp.epoch) {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(epoch1) : "l"(cp.epoch) : "memory");
+        ++epoch1;
+      }
       for (int item = pair; item < cp.num_items; item += num_pairs) {
         const PcItem it = cp.items[item];
         const int32_t row0 = it.row0 + (int32_t)peer * BLOCK_M;
@@ -180,7 +197,9 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
           // my 128 rows: inside one row block (m >= 128) or 128 / m whole row blocks
           const int32_t xr = L->m >= BLOCK_M ? row0 % L->m : 0, xi = row0 / L->m;
           int32_t ready = 0;                          // output tiles of layer l - 1 (my rows) known to be stored
-          for (int32_t j = 0; j < n_tiles; ++j) {
+          const bool split = it.nslices > 1;
+          const unsigned int *prev_flags = split && l > 0 ? cp.flags + it.flag_base + (l - 1) * PC_MAX_TILES * 2 + (int)peer : nullptr;
+          for (int32_t j = it.slice; j < n_tiles; j += it.nslices) {
             const int32_t wcol = j * PC_BLOCK_N + (int32_t)peer * PC_HALF_N;
             int32_t wn[PC_W_CHUNKS], wj[PC_W_CHUNKS];   // my weight columns: (column in block, column block) per 64-column box
 #pragma unroll
@@ -189,7 +208,8 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
               wn[c] = ln >= 64 ? col % ln : 0;
               wj[c] = col / ln;
             }
-            const uint64_t pol_x = (j + 1 < n_tiles) ? pol_last : pol_first;
+            // (column-split items: other pairs re-read these rows too, nobody knows who is last - keep them resident)
+            const uint64_t pol_x = (split || j + 1 < n_tiles) ? pol_last : pol_first;
             int32_t c0 = 0, c1 = 0;                   // k within the batch element, batch element of this k-block
             for (int32_t i = 0; i < total; ++i) {
               ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
@@ -219,16 +239,25 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
                   }
                 }
               }
-              if (l > 0 && j == 0) {
+              if (l > 0 && j == it.slice) {
                 // reduction step i reads columns [64 i, 64 i + 64) of the previous layer's output = its tile i / 4:
                 // only the last four steps of the first tile have to wait for the previous layer's last epilogue
                 const int32_t need = (i * BLOCK_K) / PC_BLOCK_N;
                 while (ready <= need) {
                   const bool last = ready + 1 == (total * BLOCK_K) / PC_BLOCK_N;
                   if (last && item == pair) pc_stamp(cp, 48 + 2 * l);
-                  ptx::mbar_wait(tile_done + 8 * ready, (done_ph >> ready) & 1u);
+                  if (!split) {
+                    ptx::mbar_wait(tile_done + 8 * ready, (done_ph >> ready) & 1u);
+                    done_ph ^= 1u << ready;
+                  } else {
+                    // tile `ready` of the previous layer was produced by another pair: its flag in global memory
+                    unsigned int seen, spins = 0;
+                    do {
+                      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(prev_flags + ready * 2) : "memory");
+                      if (++spins > (1u << 24)) __trap();   // cooperative launch: all pairs are resident; never hang silently
+                    } while (seen != epoch1);
+                  }
                   if (last && item == pair) pc_stamp(cp, 49 + 2 * l);
-                  done_ph ^= 1u << ready;
                   ++ready;
                   asm volatile("fence.proxy.async;" ::: "memory");
                 }
@@ -265,7 +294,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
           const PcLayer *L = cp.layers + it.layer0 + l;
           const int32_t total = L->total_iters, n_tiles = L->n_tiles;
           const bool x64 = NARROW && L->x64 != 0, w64 = NARROW && L->w64 != 0;
-          for (int32_t j = 0; j < n_tiles; ++j, ++t) {
+          for (int32_t j = it.slice; j < n_tiles; j += it.nslices, ++t) {
             const uint32_t buf = t & 1;
             if (t >= 2) {                              // both epilogues have read tile t - 2 out of this accumulator
               ptx::mbar_wait_cluster(acc_free + 8 * buf, ((t >> 1) - 1) & 1);
@@ -322,9 +351,26 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
     auto fetch_bias = [&](const void *D, int32_t j) -> uint32_t {
       return D ? __ldg(reinterpret_cast<const uint32_t *>(static_cast<const uint16_t *>(D) + (size_t)j * PC_BLOCK_N) + r_in) : 0u;
     };
+    unsigned int epoch1 = 0;                          // the flag value of THIS launch (column-split items)
+    if (cp.epoch && issuer) {
+      asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(epoch1) : "l"(cp.epoch) : "memory");
+      ++epoch1;
+    }
+    // my rows of output tile j of layer l are complete in L2: tell whoever reads them next
+    auto publish = [&](const PcItem &it, int l, int32_t j) {
+      if (it.nslices == 1) {
+        ptx::mbar_arrive(tile_done + 8 * j);
+      } else {
+        // the TMA stores of the tile have completed (bulk wait by this thread): order them before the flag, device-wide
+        asm volatile("fence.proxy.async;" ::: "memory");
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(cp.flags + it.flag_base + (l * PC_MAX_TILES + j) * 2 + (int)peer),
+                     "r"(epoch1) : "memory");
+      }
+    };
     if (pair < cp.num_items) {
       const PcItem it0 = cp.items[pair];
-      const uint32_t b0 = fetch_bias(cp.layers[it0.layer0].D, 0);
+      const uint32_t b0 = fetch_bias(cp.layers[it0.layer0].D, it0.slice);
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_bias + (uint32_t)r_in * 4u), "r"(b0) : "memory");
     }
     for (int item = pair; item < cp.num_items; item += num_pairs) {
@@ -339,13 +385,18 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
         const void *Dp = L->D;
         const bool relu = L->relu != 0;
         const int32_t n_tiles = L->n_tiles;
-        for (int32_t j = 0; j < n_tiles; ++j, ++t) {
+        int32_t prev_tile = -1;                         // my previous tile of this layer (its stores may still be in flight)
+        for (int32_t j = it.slice; j < n_tiles; j += it.nslices, ++t) {
           const uint32_t buf = t & 1;
-          // next tile's bias: same layer / next layer / first layer of this pair's next item
+          // next tile's bias: same layer / next layer / first layer of this pair's next item (every slice has a tile in
+          // every layer: the launcher only splits when the slice count divides all tile counts)
           uint32_t bias_next = 0;
-          if (j + 1 < n_tiles) bias_next = fetch_bias(Dp, j + 1);
-          else if (l + 1 < it.num_layers) bias_next = fetch_bias(L[1].D, 0);
-          else if (item + num_pairs < cp.num_items) bias_next = fetch_bias(cp.layers[cp.items[item + num_pairs].layer0].D, 0);
+          if (j + it.nslices < n_tiles) bias_next = fetch_bias(Dp, j + it.nslices);
+          else if (l + 1 < it.num_layers) bias_next = fetch_bias(L[1].D, it.slice);
+          else if (item + num_pairs < cp.num_items) {
+            const PcItem nx = cp.items[item + num_pairs];
+            bias_next = fetch_bias(cp.layers[nx.layer0].D, nx.slice);
+          }
           ptx::mbar_wait(acc_full + 8 * buf, (t >> 1) & 1);
           ptx::tc_fence_after_sync();
           if (t < 12 && issuer) pc_stamp(cp, 4 * t + 2);
@@ -408,22 +459,23 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
                                             l + 1 < it.num_layers ? pol_last : pol_first);
               }
               ptx::bulk_commit_group();
-              if (c == 0 && j > 0 && l + 1 < it.num_layers) {
-                // every store group but the one just committed is complete: tile j - 1 (my rows) is in L2
+              if (c == 0 && prev_tile >= 0 && l + 1 < it.num_layers) {
+                // every store group but the one just committed is complete: my previous tile (my rows) is in L2
                 ptx::bulk_wait_group<1>();
-                ptx::mbar_arrive(tile_done + 8 * (j - 1));
+                publish(it, l, prev_tile);
               }
             }
           }
+          prev_tile = j;
           // the other half of the bias buffer was last read during tile t - 1: every thread is past that
           asm volatile("st.shared.b32 [%0], %1;" ::"r"(smem_bias + (buf ^ 1u) * PC_BIAS_BYTES + (uint32_t)r_in * 4u), "r"(bias_next)
                        : "memory");
           if (t < 12 && issuer) pc_stamp(cp, 4 * t + 3);
         }
-        if (l + 1 < it.num_layers && issuer) {
+        if (l + 1 < it.num_layers && issuer && prev_tile >= 0) {
           // the layer's last tile: its stores are the only ones outstanding
           ptx::bulk_wait_group<0>();
-          ptx::mbar_arrive(tile_done + 8 * (n_tiles - 1));
+          publish(it, l, prev_tile);
         }
       }
     }
@@ -447,7 +499,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
       const PcItem it = cp.items[item];
       for (int l = 0; l < it.num_layers; ++l) {
         const PcLayer *L = cp.layers + it.layer0 + l;
-        const uint32_t kblocks = (uint32_t)(L->total_iters * L->n_tiles);
+        const uint32_t kblocks = (uint32_t)(L->total_iters * ((L->n_tiles - it.slice + it.nslices - 1) / it.nslices));   // my tiles
         for (uint32_t e = 0; e < kblocks; ++e, ++q) {
           const uint32_t s = q % PC_STAGES, ph = (q / PC_STAGES) & 1u;
           if (lane == 0) ptx::mbar_wait(raw_full + 8 * s, ph);   // one poller per warp
@@ -499,6 +551,17 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
   ptx::cluster_arrive();
   ptx::cluster_wait();
   if (threadIdx.x == 0) pc_stamp(cp, 61);
+  if (cp.epoch && threadIdx.x == 0) {
+    // the last CTA to leave closes the launch: flags of this launch (epoch + 1) become stale values for the next one
+    unsigned int e;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(cp.epoch) : "memory");
+    __threadfence();
+    if (atomicAdd(cp.epoch + 1, 1u) == gridDim.x - 1) {
+      cp.epoch[1] = 0;
+      __threadfence();
+      asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(cp.epoch), "r"(e + 1) : "memory");
+    }
+  }
   if (warp == 1) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc_pair(tmem_acc, 2 * PC_BLOCK_N);
@@ -585,7 +648,7 @@ bool encode_layer_maps(PcLayer &pl, const KernelDesc &d, const GemmArgs &g, bool
   return true;
 }
 
-template <bool VNNI, bool NARROW> void launch_pair_kernel(const PcParams &cp, int pairs, cudaStream_t stream) {
+template <bool VNNI, bool NARROW> bool launch_pair_kernel(const PcParams &cp, int pairs, cudaStream_t stream) {
   static std::once_flag once;
   std::call_once(once, [] {
     TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_pair_kernel<VNNI, NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, PC_SMEM));
@@ -595,7 +658,7 @@ template <bool VNNI, bool NARROW> void launch_pair_kernel(const PcParams &cp, in
   cfg.blockDim = dim3(VNNI ? PC_THREADS_VNNI : NUM_THREADS);
   cfg.dynamicSmemBytes = PC_SMEM;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[2];
+  cudaLaunchAttribute attrs[3];
   attrs[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attrs[0].val.programmaticStreamSerializationAllowed = 1;
   attrs[1].id = cudaLaunchAttributeClusterDimension;
@@ -604,7 +667,11 @@ template <bool VNNI, bool NARROW> void launch_pair_kernel(const PcParams &cp, in
   attrs[1].val.clusterDim.z = 1;
   cfg.attrs = attrs;
   cfg.numAttrs = 2;
+  // column-split items wait for each other's tiles through flags in global memory: every pair must be resident
+  if (cp.flags && !prepare_resident_launch(reinterpret_cast<const void *>(mlp_chain_pair_kernel<VNNI, NARROW>), &cfg, attrs))
+    return false;
   TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_pair_kernel<VNNI, NARROW>, cp));
+  return true;
 }
 }  // namespace
 
@@ -649,9 +716,36 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
     }
   }
   if (take == 0 || (!force && items < min_items)) return 0;
+  static const int max_pairs = [] {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char *e = getenv("TPP_XSMM_CHAIN_PAIRS");
+    const int p = e ? atoi(e) : sms / 2;
+    return p < 1 ? 1 : p;
+  }();
+  // Few row blocks (a lone forward pass is ONE): deal the output tiles of every layer out to `nslices` pairs per row
+  // block, the largest power of two that divides every layer's tile count and still fits one round of resident pairs
+  // (the slices wait for each other, so they must all be on the machine at once).
+  static const int split_max = [] { const char *e = getenv("TPP_XSMM_PAIR_SPLIT"); return e ? atoi(e) : 16; }();
+  constexpr int kFlagsPerRowBlock = CHAIN_MAX_LAYERS * PC_MAX_TILES * 2;
+  int nslices = 1;
+  for (int d = 16; d >= 2; d /= 2) {
+    if (d > split_max || items * d > max_pairs) continue;
+    bool ok = true;
+    for (int c = 0; c < take && ok; ++c)
+      for (int l = 0; l < len[c] && ok; ++l) {
+        const int64_t nt = (int64_t)args[first[c] + l].grid_k * descs[first[c] + l]->n / PC_BLOCK_N;
+        ok = (nt % d) == 0;
+      }
+    if (ok) { nslices = d; break; }
+  }
+  const int64_t row_blocks = items;
+  items *= nslices;
   std::vector<PcLayer> hl((size_t)layers);
   std::vector<PcItem> hi((size_t)items);
   size_t nl = 0, ni = 0;
+  int32_t row_block = 0;
   bool grids = false;
   static const bool force_narrow = [] { const char *e = getenv("TPP_XSMM_PAIR_NARROW"); return e && e[0] == '1'; }();   // A/B
   bool narrow = force_narrow;
@@ -686,12 +780,17 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
       pl.vnni = vnni ? 1 : 0;
     }
     const int64_t rows = (int64_t)args[first[c]].grid_n * descs[first[c]]->m;
-    for (int64_t r = 0; r < rows; r += PC_ROWS) {
-      PcItem &pi = hi[ni++];
-      pi.layer0 = layer0;
-      pi.num_layers = len[c];
-      pi.row0 = (int32_t)r;
-      pi.pad = 0;
+    for (int64_t r = 0; r < rows; r += PC_ROWS, ++row_block) {
+      for (int sl = 0; sl < nslices; ++sl) {      // the slices of a row block sit on neighbouring pairs (shared input rows)
+        PcItem &pi = hi[ni++];
+        memset(&pi, 0, sizeof(pi));
+        pi.layer0 = layer0;
+        pi.num_layers = len[c];
+        pi.row0 = (int32_t)r;
+        pi.slice = sl;
+        pi.nslices = nslices;
+        pi.flag_base = row_block * kFlagsPerRowBlock;
+      }
     }
   }
   // the table is written now (not captured): a graph replay only launches the kernel that reads it
@@ -706,6 +805,13 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   cp.layers = reinterpret_cast<const PcLayer *>(table);
   cp.items = reinterpret_cast<const PcItem *>(table + lbytes);
   cp.num_items = (int32_t)items;
+  cp.flags = nullptr;
+  cp.epoch = nullptr;
+  if (nslices > 1) {
+    const size_t words = (size_t)row_blocks * kFlagsPerRowBlock + 2;
+    cp.flags = static_cast<unsigned int *>(capture_owned_zeroed(words * sizeof(unsigned int)));
+    cp.epoch = cp.flags + (size_t)row_blocks * kFlagsPerRowBlock;
+  }
   static const bool hints_on = [] { const char *e = getenv("TPP_XSMM_CHAIN_PAIR_HINTS"); return !(e && e[0] == '0'); }();
   cp.l2_hints = hints_on ? 1 : 0;
   static const int debug = [] { const char *e = getenv("TPP_XSMM_PAIR_DEBUG"); return e ? atoi(e) : 0; }();
@@ -719,23 +825,19 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
     }
     cp.trace = g_pc_trace;
   }
-  static const int max_pairs = [] {
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const char *e = getenv("TPP_XSMM_CHAIN_PAIRS");
-    const int p = e ? atoi(e) : sms / 2;
-    return p < 1 ? 1 : p;
-  }();
   // balanced: the fewest pairs that still need the minimal number of rounds
   const int rounds = (int)((items + max_pairs - 1) / max_pairs);
   const int pairs = (int)((items + rounds - 1) / rounds);
   g_pc_trace_ctas = 2 * pairs;
-  if (vnni && narrow) launch_pair_kernel<true, true>(cp, pairs, stream);
-  else if (vnni) launch_pair_kernel<true, false>(cp, pairs, stream);
-  else if (narrow) launch_pair_kernel<false, true>(cp, pairs, stream);
-  else launch_pair_kernel<false, false>(cp, pairs, stream);
-  set_last_name("mlp_chain_bf16_%dx%dlayers_pair256x256%s%s", (int)items, len[0], grids ? "_blocked" : "", vnni ? "_vnni2" : "");
+  const bool launched = vnni && narrow ? launch_pair_kernel<true, true>(cp, pairs, stream)
+                        : vnni         ? launch_pair_kernel<true, false>(cp, pairs, stream)
+                        : narrow       ? launch_pair_kernel<false, true>(cp, pairs, stream)
+                                       : launch_pair_kernel<false, false>(cp, pairs, stream);
+  if (!launched) return 0;
+  char split_tag[16] = "";
+  if (nslices > 1) snprintf(split_tag, sizeof(split_tag), "_split%d", nslices);
+  set_last_name("mlp_chain_bf16_%dx%dlayers_pair256x256%s%s%s", (int)row_blocks, len[0], grids ? "_blocked" : "",
+                vnni ? "_vnni2" : "", split_tag);
   return take;
 }
 
