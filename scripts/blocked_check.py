@@ -40,3 +40,15 @@ print("tiles", tiles, "vnni", vnni, "max rel err", err.max() / np.abs(w32).max()
 if err.max() > 1e-2 * np.abs(w32).max():
     bad = np.argwhere(err > 1e-2 * np.abs(w32).max())
     print("first bad", bad[:8].tolist(), "rows bad", np.unique(bad[:, 0])[:16], "cols bad", np.unique(bad[:, 1])[:32])
+# replay timing (same buffers, L2-hot: what tpp-run's loop measures) and, with TPP_XSMM_TC_TRACE=4, the pair kernel's stamps
+reps = int(os.environ.get("REPS", "200"))
+for _ in range(10):
+    g.launch()
+xsmm.sync()
+t0 = xsmm.perf_start_timer()
+for _ in range(reps):
+    g.launch()
+dt = xsmm.perf_stop_timer(t0) / reps
+print(f"replay: {dt * 1e6:.2f} us per forward ({cfg.flops() / dt / 1e12:.1f} TF/s)")
+if os.environ.get("TPP_XSMM_TC_TRACE"):
+    xsmm.LIB.xsmm_cuda_debug_dump_trace()

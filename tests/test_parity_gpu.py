@@ -1145,6 +1145,14 @@ def test_pipelined_steps_keep_apart(mode):
 
 
 # ---- pair-per-chain kernel (mlp_chain_pair_kernel): many independent chains in one captured graph -----------------
+def _is_pair_kernel(name, base):
+    """`base`, optionally with the column-split tag: launches with few row blocks deal every layer's output tiles out to
+    2 / 4 / 8 / 16 SM pairs per row block (mlp_chain_pair.cu: PcItem::nslices)."""
+    import re
+
+    return re.fullmatch(re.escape(base) + r"(_split(2|4|8|16))?", name) is not None
+
+
 def _oracle_mlp(x, Ws, bs, m=256, relu=5, bias=True):
     ref = x
     for W, b in zip(Ws, bs):
@@ -1201,7 +1209,7 @@ def test_many_captured_chains_run_on_cta_pairs(n_chains, layers, view):
     with xsmm.graph_capture() as g:
         for c in chains:
             forward(c)
-    assert xsmm.last_kernel() == f"mlp_chain_bf16_{n_chains}x{layers}layers_pair256x256", xsmm.last_kernel()
+    assert _is_pair_kernel(xsmm.last_kernel(), f"mlp_chain_bf16_{n_chains}x{layers}layers_pair256x256"), xsmm.last_kernel()
     first = None
     for rep in range(3):
         for c in chains:
@@ -1253,7 +1261,7 @@ def test_large_batch_chain_is_cut_into_row_blocks_for_the_pairs():
         for m, h, x, hW, hb, acts, dW, db in specs:
             for l in range(layers):
                 xsmm.fused_brgemm_invoke(BF16, h, acts[l], 0, dW[l], 0, acts[l + 1], 0, db[l], 0, 1)
-    assert xsmm.last_kernel() == "mlp_chain_bf16_12x3layers_pair256x256", xsmm.last_kernel()
+    assert _is_pair_kernel(xsmm.last_kernel(), "mlp_chain_bf16_12x3layers_pair256x256"), xsmm.last_kernel()
     n0 = xsmm.launch_count()
     g.launch()
     xsmm.sync()
@@ -1295,7 +1303,7 @@ def test_pair_kernel_without_bias_or_relu_and_with_padded_leading_dims():
         for acts in chains:
             for l in range(layers):
                 xsmm.brgemm_invoke(BF16, h, acts[l], 0, dW[l], 0, acts[l + 1], 0, 1)
-    assert xsmm.last_kernel() == f"mlp_chain_bf16_{n_chains}x{layers}layers_pair256x256", xsmm.last_kernel()
+    assert _is_pair_kernel(xsmm.last_kernel(), f"mlp_chain_bf16_{n_chains}x{layers}layers_pair256x256"), xsmm.last_kernel()
     g.launch()
     xsmm.sync()
     for x, acts in zip(xs, chains):
@@ -1444,7 +1452,7 @@ def test_pair_kernel_chain_with_layers_of_different_width():
         for x, Ws, bs, acts, dW, db in chains:
             for l, h in enumerate(hs):
                 xsmm.fused_brgemm_invoke(BF16, h, acts[l], 0, dW[l], 0, acts[l + 1], 0, db[l], 0, 1)
-    assert xsmm.last_kernel() == f"mlp_chain_bf16_{n_chains}x3layers_pair256x256", xsmm.last_kernel()
+    assert _is_pair_kernel(xsmm.last_kernel(), f"mlp_chain_bf16_{n_chains}x3layers_pair256x256"), xsmm.last_kernel()
     for rep in range(2):
         for c in chains:
             for a in c[3][1:]:
