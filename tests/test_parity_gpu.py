@@ -516,9 +516,22 @@ def _blocked_out(cfg, replay):
         np.uint16)
 
 
+@pytest.fixture
+def pair_kernel_only():
+    """Lone block-packed / VNNI-2 chains normally run on the pass kernel's GEN instantiations (mlp_chain_ft.cu);
+    TPP_XSMM_CHAIN_FTG=0 keeps them on the pair-per-chain kernel (column-split items), which these tests then cover."""
+    old = os.environ.get("TPP_XSMM_CHAIN_FTG")
+    os.environ["TPP_XSMM_CHAIN_FTG"] = "0"
+    yield
+    if old is None:
+        del os.environ["TPP_XSMM_CHAIN_FTG"]
+    else:
+        os.environ["TPP_XSMM_CHAIN_FTG"] = old
+
+
 @pytest.mark.parametrize("tiles", [(32, 32, 32), (64, 64, 64), (32, 64, 64), (128, 128, 128), (256, 64, 64), (64, 256, 256)])
 @pytest.mark.parametrize("vnni", [False, True])
-def test_captured_tile_invokes_are_regrouped_onto_the_pair_kernel(tiles, vnni):
+def test_captured_tile_invokes_are_regrouped_onto_the_pair_kernel(tiles, vnni, pair_kernel_only):
     """The reference's DEFAULT call stream (benchmarks/config/omp/mlir-bf16.json:37: --tiles=32,32,32 --vnni=2; one small
     BRGEMM per (iN, iK) output block on block-packed operands) captured into a graph must not run as one launch per
     tile: the runtime folds the invokes of a layer back into one work item and the whole chain runs as ONE launch of
@@ -543,6 +556,87 @@ def test_captured_tile_invokes_are_regrouped_onto_the_pair_kernel(tiles, vnni):
     xsmm.sync()
     assert (_blocked_out(cfg, r) == first).all()
     g.destroy()
+
+
+@pytest.mark.parametrize("tiles", [(32, 32, 32), (64, 64, 64), (32, 64, 64), (128, 128, 128), (256, 64, 64), (64, 256, 256),
+                                   (256, 1024, 1024)])
+@pytest.mark.parametrize("vnni", [False, True])
+def test_lone_blocked_forward_runs_on_the_pass_kernel(tiles, vnni):
+    """ONE forward pass of the reference's call stream (what `tpp-run -n` re-runs on one set of buffers): the layers folded
+    from the tile invokes go to the GEN instantiations of the feature-major pass kernel - 128 CTAs of 32 rows x 64
+    features, 5-D / 4-D tensor maps over the block-packed operands, SWIZZLE_64B sub-tiles for 32-wide k blocks, VNNI-2
+    weights rewritten in shared memory - instead of a single SM pair. 3 layers; every layer's output is checked against
+    the oracle, replays with poisoned intermediates are bit-identical. Flat non-VNNI weights keep the flat kernel; 32-wide
+    non-VNNI weight blocks stay on the pair kernel."""
+    import torch
+
+    from tpp_mlir_b200 import harness, xsmm
+
+    cfg, (r,), (want,) = _blocked_mlp(tiles, vnni, layers=(1024, 1024, 1024, 1024))
+    n0 = xsmm.launch_count()
+    with xsmm.graph_capture() as g:
+        r.forward()
+    name = xsmm.last_kernel()
+    bn, bk, bc = tiles
+    if bk == 32 and not vnni:
+        assert "pair256x256_blocked" in name, name
+    else:
+        assert "ft64x32_fullk" in name, name
+        assert ("_blocked" in name) == (tiles != (256, 1024, 1024)), name
+    assert ("_vnni2" in name) == vnni, name
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == 1, "one kernel for the whole forward pass"
+    assert_close(BF16, _blocked_out(cfg, r), want)
+    first = [a.clone() for a in r.acts[1:]]
+    for rep in range(3):
+        for a in r.acts[1:]:
+            a.fill_(0x7FC0)
+        g.launch()
+        xsmm.sync()
+        for a, f in zip(r.acts[1:], first):
+            assert torch.equal(a, f), "a layer ran ahead of its input"
+    g.destroy()
+
+
+@pytest.mark.parametrize("tiles,vnni", [((32, 32, 32), True), ((64, 64, 64), False)])
+def test_few_blocked_chains_share_one_pass_kernel_launch(tiles, vnni):
+    """Three operand sets of the block-packed stream in one graph: one launch of the pass kernel, the three chains
+    interleaved layer by layer; seven sets: the pair-per-chain kernel (column-split items)."""
+    from tpp_mlir_b200 import xsmm
+
+    for n_sets, kernel in ((3, "3x3layers_ft64x32_fullk_blocked"), (7, "7x3layers_pair256x256_blocked")):
+        cfg, replays, wants = _blocked_mlp(tiles, vnni, layers=(1024, 1024, 1024, 1024), n_sets=n_sets, seed=77 + n_sets)
+        n0 = xsmm.launch_count()
+        with xsmm.graph_capture() as g:
+            for r in replays:
+                r.forward()
+        assert kernel in xsmm.last_kernel(), xsmm.last_kernel()
+        g.launch()
+        xsmm.sync()
+        assert xsmm.launch_count() - n0 == 1
+        for r, want in zip(replays, wants):
+            assert_close(BF16, _blocked_out(cfg, r), want)
+        g.destroy()
+
+
+@pytest.mark.parametrize("tiles,vnni", [((32, 32, 32), True), ((64, 64, 64), True), ((64, 64, 64), False)])
+def test_unrolled_blocked_loop_is_one_sequential_launch(tiles, vnni):
+    """The benchmark loop of tpp-run unrolled 4x before capture (patches/0005), on the reference's own operands: the exact
+    repeats of the chain run as one launch of the pass kernel (a plain sequence of dependent passes)."""
+    import torch
+
+    from tpp_mlir_b200 import harness, xsmm
+
+    cfg, (r,), (want,) = _blocked_mlp(tiles, vnni, layers=(1024, 1024, 1024, 1024))
+    stream = torch.cuda.current_stream()
+    xsmm.set_stream(stream.cuda_stream)
+    loop = harness.NativeMlpLoop(cfg, r.handles, [(r.acts, r.weights, r.biases)])
+    loop.run_graph_unrolled(8, 4)
+    xsmm.sync()
+    assert "4x3layers_ft64x32_fullk_blocked" in xsmm.last_kernel() and xsmm.last_kernel().endswith("_seq"), xsmm.last_kernel()
+    assert_close(BF16, _blocked_out(cfg, r), want)
+    xsmm.set_stream(0)
 
 
 @pytest.mark.parametrize("vnni", [False, True])

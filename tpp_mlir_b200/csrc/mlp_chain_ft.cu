@@ -60,6 +60,12 @@ struct alignas(64) FtPass {
   uint8_t slot;             // chain slot (< FT_MAX_WAYS) = which counter set this pass's chain uses
   uint8_t pad[3];
   uint32_t wait_arrivals;   // arrivals per CTA on the slot's counter (this launch) that must be visible before X loads
+  // GEN instantiations only (layers that are grids of tile invokes on block-packed operands / have VNNI-2 weights): the
+  // tile BRGEMM's m and n, the steps between output blocks, and per group of 4 k-blocks the box coordinates
+  // (k-block within the batch element, batch element) of its first k-block
+  int32_t m, n;
+  int64_t c_step_n, c_step_k;
+  int16_t grp_kb[4], grp_be[4];
 };
 
 struct FtParams {
@@ -94,7 +100,18 @@ __device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p) {
   return v;
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __grid_constant__ FtParams cp) {
+// GEN: the layers are grids of tile BRGEMMs on block-packed operands (GemmArgs::grid_*; what the reference's default
+// --tiles=32,32,32 emits) - X comes through a 5-D map (k in block | row in block | k-block in batch
+// element | batch element | row block), W through a 4-D map (n in block | k in block | batch element | column block), the
+// output tile is stored block by block. NARROW: 32-wide k blocks, whose 64-byte rows use SWIZZLE_64B sub-tiles (a k-block
+// slot holds two [32 rows][32 k] sub-tiles). VNNI: VNNI-2 weights ([k/2][n][2]); TMA drops the raw rows of a group into
+// its slots (row R of a k-block holds exactly the bytes of rows 2R, 2R+1 of the swizzled tile) and FT_CONV_WARPS converter
+// warps rewrite them in place, the same scheme as the pair kernel's (mlp_chain_pair.cu). <false, false, false> is the
+// flat kernel of rounds 1-2, unchanged.
+constexpr int FT_CONV_WARPS = 8;
+constexpr int FT_THREADS_VNNI = NUM_THREADS + 32 * FT_CONV_WARPS;
+template <bool GEN, bool VNNI, bool NARROW>
+__global__ void __launch_bounds__(VNNI ? FT_THREADS_VNNI : NUM_THREADS, 1) mlp_chain_ft_kernel(const __grid_constant__ FtParams cp) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t smem_x = smem_base;                                   // FT_KB x 4 KiB
@@ -106,7 +123,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
   const uint32_t w_empty = bar_base + 16 * FT_NG;                      // [FT_NG] group's X and W slots consumed
   const uint32_t acc_full = bar_base + 24 * FT_NG;                     // [2] accumulator (pass parity) complete
   const uint32_t acc_free = acc_full + 16;                             // [2] accumulator read out by the epilogue
-  const uint32_t tmem_slot = acc_free + 16;
+  const uint32_t raw_full = acc_free + 16;                             // [FT_NG] (VNNI) the group's raw weight rows have landed
+  const uint32_t tmem_slot = raw_full + 8 * FT_NG;
   uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
 
@@ -122,8 +140,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
     ptx::prefetch_tensormap(&cp.pass[0].tmW);
     for (int g = 0; g < FT_NG; ++g) {
       ptx::mbar_init(x_full + 8 * g, 1);
-      ptx::mbar_init(w_full + 8 * g, 1);
+      ptx::mbar_init(w_full + 8 * g, VNNI ? FT_CONV_WARPS : 1);   // VNNI: one arrival per converter warp, no TMA bytes
       ptx::mbar_init(w_empty + 8 * g, cp.w_multicast ? 2 : 1);   // multicast: both CTAs of the cluster retire a group
+      ptx::mbar_init(raw_full + 8 * g, 1);
     }
     for (int b = 0; b < 2; ++b) {
       ptx::mbar_init(acc_full + 8 * b, 1);
@@ -156,6 +175,23 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
     };
     auto issue_w = [&](int p, int g) {
       const FtPass &ps = cp.pass[p];
+      if constexpr (GEN) {
+        // my 64 features: column block n0 / n, column n0 % n in it (n == 32: two column blocks per box, VNNI only)
+        const int32_t cb = n0 / ps.n, n_in = n0 - cb * ps.n;
+        const int32_t kb = ps.grp_kb[g], be = ps.grp_be[g];
+        if (ptx::elect_one()) {
+          if constexpr (VNNI) {
+            // raw [k/2][n][2] rows: (element of the row | column block | k pair | batch element), counted on raw_full
+            ptx::mbar_arrive_expect_tx(raw_full + 8 * g, FT_GROUP * FT_W_BYTES);
+            ptx::tma_load_4d(smem_w + g * (FT_GROUP * FT_W_BYTES), &ps.tmW, raw_full + 8 * g, 2 * n_in, cb, kb * (BLOCK_K / 2), be);
+          } else {
+            ptx::mbar_arrive_expect_tx(w_full + 8 * g, FT_GROUP * FT_W_BYTES);
+            ptx::tma_load_4d(smem_w + g * (FT_GROUP * FT_W_BYTES), &ps.tmW, w_full + 8 * g, n_in, kb * BLOCK_K, be, cb);
+          }
+        }
+        __syncwarp();
+        return;
+      }
       int32_t b, kb;
       group_coords(ps, g, b, kb);
       if (ptx::elect_one()) {
@@ -172,6 +208,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
     };
     auto issue_x = [&](int p, int g) {
       const FtPass &ps = cp.pass[p];
+      if constexpr (GEN) {
+        const int32_t rb = m0 / ps.m, r_in = m0 - rb * ps.m;     // my 32 rows lie inside one row block
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(x_full + 8 * g, FT_GROUP * FT_X_BYTES);
+          ptx::tma_load_5d(smem_x + g * (FT_GROUP * FT_X_BYTES), &ps.tmX, x_full + 8 * g, 0, r_in, ps.grp_kb[g], ps.grp_be[g], rb);
+        }
+        __syncwarp();
+        return;
+      }
       int32_t b, kb;
       group_coords(ps, g, b, kb);
       if (ptx::elect_one()) {
@@ -187,13 +232,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
         if (x0_early) issue_x(0, g);
       }
       // the next passes' weights: this CTA's share of the feature tile's slice goes to L2 now
-      for (int p = 1; p < P && p < 3; ++p) {
-        const FtPass &ps = cp.pass[p];
-        for (int g = (int)blockIdx.y; g < ps.groups; g += (int)gridDim.y) {
-          int32_t b, kb;
-          group_coords(ps, g, b, kb);
-          if (ptx::elect_one()) ptx::tma_prefetch_3d(&ps.tmW, n0, kb * BLOCK_K, b);
-          __syncwarp();
+      if constexpr (!GEN) {
+        for (int p = 1; p < P && p < 3; ++p) {
+          const FtPass &ps = cp.pass[p];
+          for (int g = (int)blockIdx.y; g < ps.groups; g += (int)gridDim.y) {
+            int32_t b, kb;
+            group_coords(ps, g, b, kb);
+            if (ptx::elect_one()) ptx::tma_prefetch_3d(&ps.tmW, n0, kb * BLOCK_K, b);
+            __syncwarp();
+          }
         }
       }
     };
@@ -249,7 +296,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(FT_M, FT_N, 1, 0);     // A (weights) MN-major, B (X) K-major
     // descriptors of slot 0 / k-step 0; every other (slot, k-step) is a constant added to the 14-bit address field
     const uint64_t da0 = ptx::umma_smem_desc_sw128(smem_w, FT_W_BYTES, 1024);
-    const uint64_t db0 = ptx::umma_smem_desc_sw128(smem_x, 16, 1024);
+    // NARROW: a k-block slot of X is two [32 rows][32 k] SWIZZLE_64B sub-tiles (k steps 0,1 | 2,3), 8-row atoms of 512 bytes
+    const uint64_t db0 = NARROW ? ptx::umma_smem_desc_sw64(smem_x, 16, 512) : ptx::umma_smem_desc_sw128(smem_x, 16, 1024);
     for (int p = 0; p < P; ++p) {
       const int NG = cp.pass[p].groups;
       const uint32_t par = p & 1;
@@ -271,7 +319,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
 #pragma unroll
               for (int kk = 0; kk < BLOCK_K / UMMA_K; ++kk) {
                 const uint64_t da = da0 + (uint64_t)(((g * FT_GROUP + j) * FT_W_BYTES + kk * (UMMA_K * 128)) >> 4);
-                const uint64_t db = db0 + (uint64_t)(((g * FT_GROUP + j) * FT_X_BYTES + kk * (UMMA_K * 2)) >> 4);
+                const uint64_t db = db0 + (uint64_t)(((g * FT_GROUP + j) * FT_X_BYTES +
+                                                      (NARROW ? (kk >> 1) * (FT_X_BYTES / 2) + (kk & 1) * (UMMA_K * 2) : kk * (UMMA_K * 2))) >> 4);
                 ptx::umma_bf16(acc, da, db, idesc, (g > 0 || j > 0 || kk > 0) ? 1u : 0u);
               }
             }
@@ -284,7 +333,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
         }
       }
     }
-  } else {
+  } else if (warp < 6) {
     // ===== epilogue: TMEM lanes 32q + (0..15) hold features 16q + (0..15); columns = the 32 batch rows =====
     const int q = warp & 3;
     const int f = 16 * q + (lane & 15);
@@ -329,6 +378,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
       {
         const int et = (int)threadIdx.x - ep_tid0;          // 0 .. 127
         uint16_t *crow = static_cast<uint16_t *>(ps.C) + (int64_t)m0 * ps.ldc + n0;
+        if constexpr (GEN) {
+          // block-packed output: row block m0 / m, this thread's 8 features (the same for both of its pieces) lie in
+          // column block col / n
+          const int32_t rb = m0 / ps.m, r_in = m0 - rb * ps.m;
+          const int32_t col = n0 + (et & 7) * 8, cb = col / ps.n, n_in = col - cb * ps.n;
+          crow = static_cast<uint16_t *>(ps.C) + (int64_t)rb * ps.c_step_n + (int64_t)cb * ps.c_step_k + (int64_t)r_in * ps.ldc +
+                 n_in - (et & 7) * 8;
+        }
 #pragma unroll
         for (int c = et; c < FT_N * FT_M * 2 / 16; c += 128) {
           const int row = c >> 3, col16 = c & 7;
@@ -349,6 +406,46 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_ft_kernel(const __gr
         }
       } else {
         asm volatile("bar.sync 1, 128;" ::: "memory");     // the staging buffer is free for the next pass
+      }
+    }
+  } else if (VNNI) {
+    // ===== VNNI-2 weight converters: raw [k/2][n][2] rows of a group's four k-block slots -> swizzled MN-major tiles, in
+    // place. A slot holds 32 k-pair rows of 256 bytes (64 features x 2 k); row R is exactly the bytes of the tile's rows
+    // 2R and 2R + 1 (128 bytes each). One warp-wide 16-byte load covers two raw rows; lanes 2p, 2p + 1 hold features
+    // 8p .. 8p + 3 / 8p + 4 .. 8p + 7 (both k of the pair), swap halves with one shuffle, the even lane writes the chunk
+    // of the even k row, the odd lane that of the odd k row (chunk index XOR row & 7: what TMA's SWIZZLE_128B would have
+    // produced for flat weights). Only shared memory is touched: the converters may run ahead of the PDL wait. =====
+    const int cw = warp - 6;                          // 0 .. FT_CONV_WARPS - 1
+    const int row_sub = lane >> 4, g8 = (lane & 15) >> 1, half = lane & 1;
+    for (int p = 0; p < P; ++p) {
+      const int NG = cp.pass[p].groups;
+      for (int g = 0; g < NG; ++g) {
+        if (lane == 0) ptx::mbar_wait(raw_full + 8 * g, p & 1);   // one poller per warp
+        __syncwarp();
+        uint4 v[2 * FT_GROUP];
+#pragma unroll
+        for (int u = 0; u < 2 * FT_GROUP; ++u) {
+          const uint32_t R = (uint32_t)((u & 1) * 16 + cw * 2 + row_sub);     // raw row = k pair of the k-block
+          const uint32_t src = smem_w + (uint32_t)(g * FT_GROUP + (u >> 1)) * FT_W_BYTES + R * 256u + (uint32_t)(lane & 15) * 16u;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "r"(src));
+        }
+        __syncwarp();                                 // every lane has read its rows before any lane overwrites them
+#pragma unroll
+        for (int u = 0; u < 2 * FT_GROUP; ++u) {
+          const uint32_t lo0 = __byte_perm(v[u].x, v[u].y, 0x5410), lo1 = __byte_perm(v[u].z, v[u].w, 0x5410);
+          const uint32_t hi0 = __byte_perm(v[u].x, v[u].y, 0x7632), hi1 = __byte_perm(v[u].z, v[u].w, 0x7632);
+          const uint32_t r0 = __shfl_xor_sync(0xffffffffu, half ? lo0 : hi0, 1);
+          const uint32_t r1 = __shfl_xor_sync(0xffffffffu, half ? lo1 : hi1, 1);
+          const uint32_t o0 = half ? r0 : lo0, o1 = half ? r1 : lo1, o2 = half ? hi0 : r0, o3 = half ? hi1 : r1;
+          const uint32_t krow = 2u * (uint32_t)((u & 1) * 16 + cw * 2 + row_sub) + (uint32_t)half;   // k row of the 64 x 64 tile
+          const uint32_t base = smem_w + (uint32_t)(g * FT_GROUP + (u >> 1)) * FT_W_BYTES;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                       ::"r"(base + krow * 128u + (((uint32_t)g8 ^ (krow & 7u)) << 4)), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                       : "memory");
+        }
+        ptx::fence_proxy_async();                     // my shared-memory writes -> the async proxy (the MMAs)
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(w_full + 8 * g);
       }
     }
   }
@@ -717,6 +814,79 @@ static bool chain_ft_supported(const KernelDesc *const *descs, const GemmArgs *a
   return true;
 }
 
+// The GEN instantiations of the full-K kernel: layers that are grids of tile BRGEMMs on block-packed operands and / or
+// have VNNI-2 weights (the reference's default --tiles=32,32,32 --vnni=2 stream after the runtime has folded the tile
+// invokes into layers). Same tiling as the flat kernel - 32 batch rows x 64 features per CTA, a reduction of exactly
+// FT_KB k-blocks - so every layer is 1024 wide; tile sizes must let one TMA box be a whole number of blocks.
+static bool chain_ftg_supported(const KernelDesc *const *descs, const GemmArgs *args, int L, bool *vnni_out, bool *narrow_out) {
+  // TPP_XSMM_CHAIN_FTG=0 (read per capture, so that tests can switch it): such chains stay on the pair-per-chain kernel
+  const char *env = getenv("TPP_XSMM_CHAIN_FTG");
+  if ((env && env[0] == '0') || L < 2 || L > CHAIN_MAX_LAYERS) return false;
+  const KernelDesc &d0 = *descs[0];
+  const int64_t rows = (int64_t)args[0].grid_n * d0.m, n_total0 = (int64_t)args[0].grid_k * d0.n;
+  if ((rows % FT_N) != 0 || (n_total0 % FT_M) != 0 || (rows / FT_N) * (n_total0 / FT_M) > 148) return false;
+  const bool vnni = (d0.gemm_flags & 2048) != 0, narrow = d0.k == 32;
+  for (int l = 0; l < L; ++l) {
+    const KernelDesc &d = *descs[l];
+    const GemmArgs &g = args[l];
+    if (!brgemm_layer_chainable(d, g)) return false;
+    if (((d.gemm_flags & 2048) != 0) != vnni || (d.k == 32) != narrow) return false;   // one instantiation per launch
+    if ((int64_t)g.grid_n * d.m != rows || (int64_t)g.grid_k * d.n != n_total0) return false;
+    if (g.batch * d.k != (int64_t)FT_KB * BLOCK_K) return false;
+    if ((d.m % FT_N) != 0) return false;                                                 // a CTA's 32 rows lie in one row block
+    if (!(d.k == 32 || d.k == 64 || d.k == 128 || (d.k % 256) == 0)) return false;       // a group of 4 k-blocks is one box
+    if (vnni ? !(d.n == 32 || (d.n % FT_M) == 0) : (d.n % FT_M) != 0) return false;
+    if ((d.lda % 8) != 0 || (d.ldb % 8) != 0 || (d.ldc % 8) != 0) return false;
+    if (g.batch > 1 && ((d.stride_a % 8) != 0 || (d.stride_b % 8) != 0)) return false;
+    if (g.grid_n > 1 && ((g.a_step % 8) != 0 || (g.c_step_n % 8) != 0)) return false;
+    if (g.grid_k > 1 && ((g.b_step % 8) != 0 || (g.c_step_k % 8) != 0)) return false;
+    if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && g.D == nullptr) return false;
+  }
+  *vnni_out = vnni;
+  *narrow_out = narrow;
+  return true;
+}
+
+// tensor maps of a GEN pass (see the kernel's header comment); sizes in elements
+static bool encode_ftg_maps(FtPass &ps, const KernelDesc &d, const GemmArgs &g, bool vnni) {
+  const uint64_t nb = (uint64_t)g.batch, gn = (uint64_t)g.grid_n, gk = (uint64_t)g.grid_k;
+  // a dimension of size 1 may carry any legal stride
+  const uint64_t sa = nb > 1 ? (uint64_t)d.stride_a : (uint64_t)d.lda, sb = nb > 1 ? (uint64_t)d.stride_b : (uint64_t)d.ldb;
+  const uint64_t a_step = gn > 1 ? (uint64_t)g.a_step : (uint64_t)d.lda, b_step = gk > 1 ? (uint64_t)g.b_step : (uint64_t)d.ldb;
+  const uint32_t kx = (uint32_t)std::min<int64_t>(d.k, BLOCK_K);          // 32 or 64
+  const uint32_t kbs = (uint32_t)std::max<int64_t>(d.k / BLOCK_K, 1);     // k-blocks per batch element
+  const uint32_t box_kb = std::min<uint32_t>(kbs, FT_GROUP);              // k-blocks of one batch element per box
+  const uint32_t box_be = FT_GROUP * BLOCK_K / (kx * box_kb);             // batch elements per box: 256 k in all
+  {
+    const uint64_t dims[5] = {kx, (uint64_t)d.m, kbs, nb, gn}, str[4] = {(uint64_t)d.lda, BLOCK_K, sa, a_step};
+    const uint32_t box[5] = {kx, FT_N, box_kb, box_be, 1};
+    if (!encode_map_nd(&ps.tmX, g.A, 5, dims, str, box, kx == 32 ? 64 : 128)) return false;
+  }
+  if (vnni) {
+    // raw VNNI-2 rows: (element of the [n][2] row | column block | k pair | batch element); 64 features x 2 = 256 bytes
+    // per k pair (two column blocks when n == 32), 128 k pairs per box; no swizzle
+    const uint32_t ex = 2 * (uint32_t)std::min<int64_t>(d.n, FT_M), kpx = (uint32_t)std::min<int64_t>(d.k / 2, FT_GROUP * BLOCK_K / 2);
+    const uint64_t dims[4] = {2 * (uint64_t)d.n, gk, (uint64_t)d.k / 2, nb}, str[3] = {b_step, 2 * (uint64_t)d.ldb, sb};
+    const uint32_t box[4] = {ex, 2 * FT_M / ex, kpx, FT_GROUP * BLOCK_K / 2 / kpx};
+    if (!encode_map_nd(&ps.tmW, g.B, 4, dims, str, box, 0)) return false;
+  } else {
+    const uint32_t kw = (uint32_t)std::min<int64_t>(d.k, FT_GROUP * BLOCK_K);
+    const uint64_t dims[4] = {(uint64_t)d.n, (uint64_t)d.k, nb, gk}, str[3] = {(uint64_t)d.ldb, sb, b_step};
+    const uint32_t box[4] = {FT_M, kw, FT_GROUP * BLOCK_K / kw, 1};
+    if (!encode_map_nd(&ps.tmW, g.B, 4, dims, str, box, 128)) return false;
+  }
+  ps.m = (int32_t)d.m;
+  ps.n = (int32_t)d.n;
+  ps.c_step_n = gn > 1 ? g.c_step_n : 0;
+  ps.c_step_k = gk > 1 ? g.c_step_k : 0;
+  for (int gq = 0; gq < FT_NG; ++gq) {
+    const int64_t k0 = (int64_t)gq * FT_GROUP * BLOCK_K;     // first reduction index of the group
+    ps.grp_be[gq] = (int16_t)(k0 / d.k);
+    ps.grp_kb[gq] = (int16_t)((k0 % d.k) / BLOCK_K);
+  }
+  return true;
+}
+
 // split-K variants (mlp_chain_fts_kernel<S>): 32 S-row batch tiles, a multiple of S feature tiles, and a reduction
 // whose S slices are made of whole TMA boxes. Returns the largest usable S in {4, 2}, or 1.
 static int chain_ft_split(const KernelDesc *const *descs, const GemmArgs *args, int L) {
@@ -748,12 +918,25 @@ static int chain_ft_split(const KernelDesc *const *descs, const GemmArgs *args, 
 // independent, identically tiled chains is taken. Returns the number of chains launched (0: not applicable).
 int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args, const int *first, const int *len,
                             int num_chains, cudaStream_t stream) {
-  if (num_chains < 1 || !brgemm_chain_supported(descs + first[0], args + first[0], len[0]) ||
-      !chain_ft_supported(descs + first[0], args + first[0], len[0]))
-    return 0;
+  if (num_chains < 1) return 0;
+  // flat chains: the kernels of rounds 1-2; grids of tile invokes / VNNI-2 weights: the GEN instantiations (full K only)
+  bool gen = false, gen_vnni = false, gen_narrow = false;
+  if (!brgemm_chain_supported(descs + first[0], args + first[0], len[0]) ||
+      !chain_ft_supported(descs + first[0], args + first[0], len[0])) {
+    if (!chain_ftg_supported(descs + first[0], args + first[0], len[0], &gen_vnni, &gen_narrow)) return 0;
+    gen = true;
+  }
+  auto chain_ok = [&](int c) {
+    if (!gen)
+      return brgemm_chain_supported(descs + first[c], args + first[c], len[c]) &&
+             chain_ft_supported(descs + first[c], args + first[c], len[c]);
+    bool v = false, nr = false;
+    return chain_ftg_supported(descs + first[c], args + first[c], len[c], &v, &nr) && v == gen_vnni && nr == gen_narrow;
+  };
   static const bool multi_off = [] { const char *e = getenv("TPP_XSMM_CHAIN_MULTI"); return e && e[0] == '0'; }();
   const KernelDesc &d0 = *descs[first[0]];
-  int split = chain_ft_split(descs + first[0], args + first[0], len[0]);
+  const int64_t rows0 = (int64_t)args[first[0]].grid_n * d0.m, ncols0 = (int64_t)args[first[0]].grid_k * d0.n;
+  int split = gen ? 1 : chain_ft_split(descs + first[0], args + first[0], len[0]);
   // ---- which chains go into this launch ----
   // `sequential`: the following chains are EXACT REPEATS of the first one (same descriptors, same buffers: the unrolled
   // iterations of a benchmark loop, lib/TPP/Runner/MLIRBench.cpp:265-300). They depend on each other, but only through
@@ -781,11 +964,11 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     while (!multi_off && take < num_chains) {
       const int c = take;
       const KernelDesc &d = *descs[first[c]];
-      if (d.m != d0.m || d.n != d0.n || passes + len[c] > FT_MAX_PASSES) break;
-      if (!brgemm_chain_supported(descs + first[c], args + first[c], len[c]) ||
-          !chain_ft_supported(descs + first[c], args + first[c], len[c]))
+      if ((int64_t)args[first[c]].grid_n * d.m != rows0 || (int64_t)args[first[c]].grid_k * d.n != ncols0 ||
+          passes + len[c] > FT_MAX_PASSES)
         break;
-      if (chain_ft_split(descs + first[c], args + first[c], len[c]) != split) break;
+      if (!chain_ok(c)) break;
+      if (!gen && chain_ft_split(descs + first[c], args + first[c], len[c]) != split) break;
       std::vector<ByteRange> in, out;
       chain_ranges(descs + first[c], args + first[c], len[c], in, out);
       bool indep = true;
@@ -833,11 +1016,13 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     const uint64_t nb = (uint64_t)g.batch;
     const uint32_t k_iters = (uint32_t)(d.k / BLOCK_K);
     const uint32_t grp = split == 4 ? FS<4>::GROUP : split == 2 ? FS<2>::GROUP : FT_GROUP;
-    const uint32_t gk = k_iters >= grp ? grp : k_iters, gb = grp / gk;   // box = gk k-blocks x gb batch elements
-    if (!encode_map_x4(&ps.tmX, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a,
-                       32 * split, gk, gb) ||
-        !encode_map(&ps.tmW, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, FT_M,
-                    BLOCK_K * gk, gb))
+    const uint32_t gk = k_iters >= grp ? grp : (k_iters ? k_iters : 1), gb = grp / gk;   // box = gk k-blocks x gb batch elements
+    if (gen) {
+      if (!encode_ftg_maps(ps, d, g, gen_vnni)) return false;
+    } else if (!encode_map_x4(&ps.tmX, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a,
+                              32 * split, gk, gb) ||
+               !encode_map(&ps.tmW, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, FT_M,
+                           BLOCK_K * gk, gb))
       return false;
     ps.C = g.C;
     ps.D = g.D;
@@ -874,7 +1059,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     warned = true;
     return 0;
   }
-  dim3 grid((unsigned)(d0.n / FT_M), (unsigned)(d0.m / (32 * split)), (unsigned)split);
+  dim3 grid((unsigned)(ncols0 / FT_M), (unsigned)(rows0 / (32 * split)), (unsigned)split);
   const int n_ctas = (int)(grid.x * grid.y * grid.z);
   // arrival counters of THIS kernel node (the chain kernels only ever run inside a capture): zero-filled before the
   // node exists, owned by the graph, monotonic across its replays - every counter stays a multiple of the group size
@@ -892,17 +1077,28 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   // data that other SMs fenced to L2 (TMA reads L2); TPP_XSMM_CHAIN_PROXY_FENCE=1 turns it on
   static const bool pf = [] { const char *e = getenv("TPP_XSMM_CHAIN_PROXY_FENCE"); return e && e[0] == '1'; }();
   cp.proxy_fence = pf ? 1 : 0;
-  constexpr int smem1 = FT_KB * (FT_X_BYTES + FT_W_BYTES) + FT_OUT_BYTES + (3 * FT_NG + 4) * 8 + 16 + 1024;
+  constexpr int smem1 = FT_KB * (FT_X_BYTES + FT_W_BYTES) + FT_OUT_BYTES + (4 * FT_NG + 4) * 8 + 16 + 1024;
   const int smem = split == 4 ? FS<4>::SMEM : split == 2 ? FS<2>::SMEM : smem1;
+  // the kernel this launch runs (full-K instantiations; the split-K variants are set below)
+  using FtKernel = void (*)(const FtParams);
+  const FtKernel ft_kernel = !gen                      ? mlp_chain_ft_kernel<false, false, false>
+                             : gen_vnni && gen_narrow ? mlp_chain_ft_kernel<true, true, true>
+                             : gen_vnni               ? mlp_chain_ft_kernel<true, true, false>
+                             : gen_narrow             ? mlp_chain_ft_kernel<true, false, true>
+                                                      : mlp_chain_ft_kernel<true, false, false>;
   static std::once_flag once;
   std::call_once(once, [] {
-    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_ft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_ft_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_ft_kernel<true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_ft_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_ft_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_ft_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem1));
     TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_fts_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS<2>::SMEM));
     TPP_CUDA_CHECK(cudaFuncSetAttribute(mlp_chain_fts_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FS<4>::SMEM));
   });
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(split2 ? F2_THREADS : NUM_THREADS);
+  cfg.blockDim = dim3(split2 ? F2_THREADS : (gen && gen_vnni) ? FT_THREADS_VNNI : NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[3];
@@ -914,7 +1110,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   // the weights but not the bytes each SM receives, and a pass is bound by the latter (~47-53 B/clk per SM):
   // measured 7.15 us (multicast) vs 7.12 us (unicast) per forward, so it stays off by default.
   static const bool mc_on = [] { const char *e = getenv("TPP_XSMM_CHAIN_MC"); return e && e[0] == '1'; }();
-  cp.w_multicast = (!split2 && mc_on && (grid.y % 2) == 0) ? 1 : 0;
+  cp.w_multicast = (!split2 && !gen && mc_on && (grid.y % 2) == 0) ? 1 : 0;
   if (cp.w_multicast || split2) {
     attrs[1].id = cudaLaunchAttributeClusterDimension;
     attrs[1].val.clusterDim.x = 1;
@@ -936,14 +1132,16 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   // the passes wait for each other through arrival counters: every CTA must be resident (cooperative launch)
   const void *kfn = split == 4 ? reinterpret_cast<const void *>(mlp_chain_fts_kernel<4>)
                     : split == 2 ? reinterpret_cast<const void *>(mlp_chain_fts_kernel<2>)
-                                 : reinterpret_cast<const void *>(mlp_chain_ft_kernel);
+                                 : reinterpret_cast<const void *>(ft_kernel);
   if (!prepare_resident_launch(kfn, &cfg, attrs)) return 0;
   if (split == 4) TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_fts_kernel<4>, cp));
   else if (split == 2) TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_fts_kernel<2>, cp));
-  else TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_ft_kernel, cp));
+  else TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ft_kernel, cp));
   const char *tile = split == 4 ? "ft64x128_splitk4" : split == 2 ? "ft64x64_splitk2" : "ft64x32_fullk";
-  if (take == 1) set_last_name("mlp_chain_bf16_%dlayers_%s", len[0], tile);
-  else set_last_name("mlp_chain_bf16_%dx%dlayers_%s%s", take, len[0], tile, sequential ? "_seq" : "");
+  char tag[24] = "";
+  if (gen) snprintf(tag, sizeof(tag), "%s%s", args[first[0]].is_grid() ? "_blocked" : "", gen_vnni ? "_vnni2" : "");
+  if (take == 1) set_last_name("mlp_chain_bf16_%dlayers_%s%s", len[0], tile, tag);
+  else set_last_name("mlp_chain_bf16_%dx%dlayers_%s%s%s", take, len[0], tile, tag, sequential ? "_seq" : "");
   return take;
 }
 

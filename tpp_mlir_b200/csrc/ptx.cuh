@@ -120,6 +120,14 @@ __device__ __forceinline__ void tma_load_4d_hint(uint32_t smem_dst, const void *
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(uint32_t smem_dst, const void *map, uint32_t bar, int32_t c0, int32_t c1,
+                                            int32_t c2, int32_t c3, int32_t c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 // L2 prefetch of the box a later tma_load_3d with the same coordinates will fetch
 __device__ __forceinline__ void tma_prefetch_3d(const void *map, int32_t c0, int32_t c1, int32_t c2) {
   asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];"
