@@ -763,6 +763,9 @@ def main():
                                               "issue": "graph replay of the captured 3-invoke sequence, one launch per forward"},
                     "direct_invokes": {"ms_per_forward": lat_direct_s * 1e3, "gflops": flops_fwd_rank / lat_direct_s / 1e9,
                                        "kernel": lat_direct_kernel, "issue": "3 x xsmm_fused_brgemm_invoke, PDL-chained"},
+                    # the same protocol on the reference's own operands (--tiles=32,32,32 --vnni=2: 768 tile invokes per
+                    # forward pass, block-packed, VNNI-2 weights), measured by bench_configs.reference_stream
+                    "reference_default_stream": (extras.get("reference_default_stream") or {}).get("lone_forward"),
                     "rel_err_vs_oracle": lone_rel},
         "e2e": {"value": flops_fwd_rank * n_gpus / pipe_s / 1e9, "unit": UNIT,
                 "h2d_bytes_per_step": h2d_fwd * fwd_per_step, "d2h_bytes_per_step": d2h_fwd * fwd_per_step,

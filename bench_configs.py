@@ -173,15 +173,33 @@ def reference_stream(pk, tiles=(32, 32, 32), vnni=True):
     if os.environ.get("TPP_XSMM_TC_TRACE") == "4":
         xsmm.LIB.xsmm_cuda_debug_dump_trace()
     s = wl.num_sets - 1
+    stream_kernel = xsmm.last_kernel()
     rel = bench.rel_err(wl.output(s).cpu().numpy().view(np.uint16), np.roll(bench.oracle_forward(x, Ws, bs), s, 0))
     flops = wl.cfg.flops()
     bn, bk, bc = tiles
     invokes = 3 * (256 // bn) * (1024 // bk)
+    # the same stream as tpp-run's own loop runs it: ONE forward pass re-run on ONE set of buffers (bench.py: latency)
+    lone = None
+    if fused:
+        from tpp_mlir_b200 import harness
+
+        hot = harness.NativeMlpLoop(wl.cfg, wl.replay.handles, wl.sets[:1])
+        lone = {}
+        for label, run in (("unrolled16", lambda k: hot.run_graph_unrolled(k, 16)), ("one_forward_per_graph", hot.run_graph)):
+            for _ in range(10):
+                run(1)
+            torch.cuda.synchronize()
+            t0 = xsmm.perf_start_timer()
+            run(1024)
+            dt = xsmm.perf_stop_timer(t0) / 1024
+            lone[label] = {"ms_per_forward": dt * 1e3, "gflops": flops / dt / 1e9, "kernel": xsmm.last_kernel()}
+        lone["rel_err_vs_oracle"] = bench.rel_err(wl.output(0).cpu().numpy().view(np.uint16), bench.oracle_forward(x, Ws, bs))
     return {"config": f"{'reference default stream: ' if tiles == (32, 32, 32) and vnni else ''}MLP 3x1024^2 bf16 batch 256, "
                       f"--tiles={bn},{bk},{bc}{' --vnni=2' if vnni else ''} ({invokes} invokes of {bn}x{bk}x{bc} x batch "
                       f"{1024 // bc} per forward pass, block-packed{', VNNI-2 weights' if vnni else ''})",
-            "kernel": xsmm.last_kernel(), "seconds_per_forward": t, "gflops": flops / t / 1e9,
+            "kernel": stream_kernel, "seconds_per_forward": t, "gflops": flops / t / 1e9,
             "kernel_launches_per_forward": launches, "operand_sets": wl.num_sets, "rel_err_vs_oracle": rel,
+            "lone_forward": lone,
             "roofline": {"bound": "hbm", "achieved": 7346176 / t / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                          "frac": 7346176 / t / 1e9 / pk["hbm_gbs"], "algorithmic_bytes": 7346176}}
 

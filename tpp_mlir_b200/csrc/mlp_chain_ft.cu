@@ -416,7 +416,10 @@ __global__ void __launch_bounds__(VNNI ? FT_THREADS_VNNI : NUM_THREADS, 1) mlp_c
     // of the even k row, the odd lane that of the odd k row (chunk index XOR row & 7: what TMA's SWIZZLE_128B would have
     // produced for flat weights). Only shared memory is touched: the converters may run ahead of the PDL wait. =====
     const int cw = warp - 6;                          // 0 .. FT_CONV_WARPS - 1
-    const int row_sub = lane >> 4, g8 = (lane & 15) >> 1, half = lane & 1;
+    // (which 8-feature group a lane pair takes: within a quarter-warp the four pairs take groups {0,5,2,7} / {4,1,6,3}, so
+    // that the quarter's eight 16-byte loads AND its eight 16-byte stores - two tile rows whose chunk positions differ
+    // in bit 0 only - each cover all 32 banks once)
+    const int row_sub = lane >> 4, half = lane & 1, g8 = vnni_group_of_lane(lane);
     for (int p = 0; p < P; ++p) {
       const int NG = cp.pass[p].groups;
       for (int g = 0; g < NG; ++g) {
@@ -426,7 +429,7 @@ __global__ void __launch_bounds__(VNNI ? FT_THREADS_VNNI : NUM_THREADS, 1) mlp_c
 #pragma unroll
         for (int u = 0; u < 2 * FT_GROUP; ++u) {
           const uint32_t R = (uint32_t)((u & 1) * 16 + cw * 2 + row_sub);     // raw row = k pair of the k-block
-          const uint32_t src = smem_w + (uint32_t)(g * FT_GROUP + (u >> 1)) * FT_W_BYTES + R * 256u + (uint32_t)(lane & 15) * 16u;
+          const uint32_t src = smem_w + (uint32_t)(g * FT_GROUP + (u >> 1)) * FT_W_BYTES + R * 256u + (uint32_t)(2 * g8 + half) * 16u;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "r"(src));
         }
         __syncwarp();                                 // every lane has read its rows before any lane overwrites them
@@ -821,7 +824,14 @@ static bool chain_ft_supported(const KernelDesc *const *descs, const GemmArgs *a
 static bool chain_ftg_supported(const KernelDesc *const *descs, const GemmArgs *args, int L, bool *vnni_out, bool *narrow_out) {
   // TPP_XSMM_CHAIN_FTG=0 (read per capture, so that tests can switch it): such chains stay on the pair-per-chain kernel
   const char *env = getenv("TPP_XSMM_CHAIN_FTG");
-  if ((env && env[0] == '0') || L < 2 || L > CHAIN_MAX_LAYERS) return false;
+  static const bool chains_off = [] { const char *e = getenv("TPP_XSMM_CHAIN"); return e && (e[0] == 's' || e[0] == '0'); }();
+  if ((env && env[0] == '0') || chains_off || L < 2 || L > CHAIN_MAX_LAYERS) return false;
+  {
+    // flat chains with flat weights belong to the flat kernels (or to whatever the caller tries next)
+    bool special = (descs[0]->gemm_flags & 2048) != 0;
+    for (int l = 0; l < L; ++l) special = special || args[l].is_grid();
+    if (!special) return false;
+  }
   const KernelDesc &d0 = *descs[0];
   const int64_t rows = (int64_t)args[0].grid_n * d0.m, n_total0 = (int64_t)args[0].grid_k * d0.n;
   if ((rows % FT_N) != 0 || (n_total0 % FT_M) != 0 || (rows / FT_N) * (n_total0 / FT_M) > 148) return false;
@@ -990,6 +1000,10 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
       ++take;
     }
   }
+  // more than a handful of independent block-packed / VNNI-2 chains: the pair-per-chain kernel with column-split items is
+  // faster (measured: ~47 us per launch up to 18 row blocks against ~7 us per chain here); exact repeats stay here
+  constexpr int kFtGenMax = 6;
+  if (gen && !sequential && take > kFtGenMax) return 0;
   // one or two chains per launch have nothing to hide the exchange latency behind: the full-K kernel is faster there
   // (11.0 vs 14.7 us for a single forward); every split-K shape is also a full-K shape
   if (take < 3 || sequential) split = 1;
@@ -1071,6 +1085,9 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   for (int sl = 0; sl < FT_MAX_WAYS; ++sl) cp.arrivals_total[sl] = arrivals[sl];
   cp.num_passes = np;
   cp.weights_early = weights_early ? 1 : 0;
+  if (getenv("TPP_XSMM_DEBUG"))
+    fprintf(stderr, "ft-chain: %d chains, %d passes, gen=%d vnni=%d narrow=%d sequential=%d weights_early=%d a_independent=%d\n", take, np,
+            (int)gen, (int)gen_vnni, (int)gen_narrow, (int)sequential, (int)weights_early, (int)args[first[0]].a_independent);
   static const bool x0_off = [] { const char *e = getenv("TPP_XSMM_CHAIN_X0"); return e && e[0] == '0'; }();
   cp.x0_early = (args[first[0]].a_independent && !x0_off) ? 1 : 0;
   // fence.proxy.async between the flag observation and the TMA reads costs ~0.3 us per layer and is not needed for

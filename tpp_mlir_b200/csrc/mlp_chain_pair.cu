@@ -491,7 +491,10 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
     // (First version: the converters fetched the weights themselves with 16-byte global loads - 1720 clk per k-block
     // however many loads were in flight: the LSU path cannot keep as many bytes outstanding as TMA.)
     const int cw = warp - 6;                          // 0 .. PC_CONV_WARPS - 1
-    const int row_sub = lane >> 4, g8 = (lane & 15) >> 1, half = lane & 1;
+    // (which 8-column group a lane pair takes: within a quarter-warp the four pairs take groups {0,5,2,7} / {4,1,6,3}, so
+    // that the quarter's eight 16-byte loads AND its eight 16-byte stores - two tile rows whose chunk positions differ
+    // in bit 0 only - each cover all 32 banks once; the plain order 0..3 made every store a 2-way bank conflict)
+    const int row_sub = lane >> 4, half = lane & 1, g8 = vnni_group_of_lane(lane);
     const uint32_t leader_full = ptx::mapa(full_bar, 0);
     constexpr int UNITS = 2 * PC_W_CHUNKS;            // 16-byte pieces per thread and k-block: 2 row groups x 2 chunks
     uint32_t q = 0;                                   // running k-block index of this CTA (all items / layers / tiles)
@@ -515,7 +518,7 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
 #pragma unroll
           for (int u = 0; u < UNITS; ++u) {
             const uint32_t R = (uint32_t)((u & 1) * 16 + cw * 2 + row_sub);     // raw row = k pair of the k-block
-            const uint32_t src = smem_w + (s * PC_W_CHUNKS + (u >> 1)) * B_CHUNK_BYTES + R * 256u + (uint32_t)(lane & 15) * 16u;
+            const uint32_t src = smem_w + (s * PC_W_CHUNKS + (u >> 1)) * B_CHUNK_BYTES + R * 256u + (uint32_t)(2 * g8 + half) * 16u;
             asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "r"(src));
           }
           __syncwarp();                               // every lane has read its rows before any lane overwrites them

@@ -657,13 +657,12 @@ void flush_pending_impl() {
     // many independent chains: one CTA pair per chain (4x less L2 -> SM traffic per layer than the pass kernels)
     int took = launch_brgemm_chains_pair(descs.data(), args.data(), seg_first.data() + sidx, seg_len.data() + sidx,
                                          (int)(run - sidx), stream, /*force=*/false);
-    // few chains (a lone forward pass above all): the pass kernels spread ONE layer over 128 SMs. Flat chains always;
-    // block-packed / VNNI-2 chains (GEN instantiations) up to kFtGenMax of them - beyond that the pair kernel with
-    // column-split items is faster (measured: ~47 us per launch up to 18 row blocks against ~7 us per chain here).
+    // few chains (a lone forward pass above all, or the exact repeats of an unrolled loop): the pass kernels spread ONE
+    // layer over 128 SMs. Flat chains always; block-packed / VNNI-2 chains (GEN instantiations) decline more than a
+    // handful of independent chains - the pair kernel with column-split items is faster there.
     // (the few-chain kernels own per-launch counters: an allocation and a sync each time, which only a captured graph
     // amortises - a lazily flushed lone chain goes out as PDL-chained per-layer launches instead)
-    constexpr size_t kFtGenMax = 6;
-    if (took == 0 && chains && t_ctx.capturing && (!force || run - sidx <= kFtGenMax))
+    if (took == 0 && chains && t_ctx.capturing)
       took = launch_brgemm_chains_ft(descs.data(), args.data(), seg_first.data() + sidx, seg_len.data() + sidx,
                                      (int)(run - sidx), stream);
     if (took == 0 && force)

@@ -127,6 +127,14 @@ __device__ __forceinline__ void epilogue_store(float (&v)[NC], const TcParams &p
   }
 }
 
+// VNNI-2 converter warps (mlp_chain_pair.cu, mlp_chain_ft.cu): lanes 2p, 2p + 1 of a half-warp rewrite the 8 columns
+// [8 g, 8 g + 8) of one raw k-pair row (pieces 2 g, 2 g + 1 of its sixteen 16-byte pieces) into chunk g of two swizzled
+// tile rows. g as a function of the lane: pair j of quarter Q takes j + 4 ((j & 1) ^ Q) - {0,5,2,7} and {4,1,6,3}.
+__device__ __forceinline__ int vnni_group_of_lane(int lane) {
+  const int j = (lane >> 1) & 3, q = (lane >> 3) & 1;
+  return j + 4 * ((j & 1) ^ q);
+}
+
 // ---- host helpers (tc_host.cu) ---------------------------------------------------------------------------------
 // 3-D bf16 tensor map: dims (inner, rows, batch), strides in elements for rows and batch; 128-byte swizzle
 bool encode_map(CUtensorMap *map, const void *base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t ld,
