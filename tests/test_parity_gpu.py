@@ -1482,6 +1482,37 @@ def test_tiled_pack_unpack_is_one_batched_kernel_and_bit_exact(case):
         results.append(got)
 
 
+def test_full_size_pack_unpack_round_trip_is_one_tma_copy_each():
+    """BASELINE-sized check of the batched tile moves: a 4096 x 4096 bf16 matrix packed into 32 x 32 tiles (16384 unary
+    identity invokes) and unpacked again under capture. Each direction is ONE launch of the TMA-to-TMA grid copy
+    (tile_grid.cu: the run walks a regular grid, no pointer table); packed == the numpy restatement, unpack(pack(x)) == x."""
+    import torch
+
+    from tpp_mlir_b200 import harness, xsmm
+
+    M = N = 4096
+    rng = np.random.default_rng(11)
+    flat = rng.integers(0, 65535, size=(M, N), dtype=np.uint16)
+    src = torch.from_numpy(flat.view(np.int16)).cuda()
+    packed = torch.zeros(M * N, dtype=torch.int16, device="cuda")
+    back = torch.zeros(M * N, dtype=torch.int16, device="cuda")
+    fwd = harness.PackReplay(BF16, M, N, 32, 32, (0, 1))
+    inv = harness.PackReplay(BF16, M, N, 32, 32, (0, 1), unpack=True)
+    with xsmm.graph_capture() as g:
+        fwd.run(src, packed)
+        inv.run(back, packed)
+    k_unpack = xsmm.last_kernel()
+    assert "batch16384_tma128x128" in k_unpack, k_unpack
+    n0 = xsmm.launch_count()
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == 2, "one launch per direction"
+    assert np.array_equal(packed.cpu().numpy().view(np.uint16).reshape(M // 32, N // 32, 32, 32),
+                          oracle.tensor_pack(flat, 32, 32, (0, 1)))
+    assert torch.equal(back.reshape(M, N), src)
+    g.destroy()
+
+
 def test_captured_tile_moves_respect_dependencies():
     """Tile copies that read what an earlier one wrote (a -> b -> c -> d -> e) or overwrite what an earlier one wrote
     must not be reordered into one batch; copies into disjoint tiles of ONE matrix (interleaved in address space) still

@@ -48,6 +48,12 @@ struct TilePtrs {
 void launch_tile_batch(const TilePtrs *dev_tiles, int64_t num_tiles, bool transpose, int64_t m, int64_t n, int64_t ldi,
                        int64_t ldo, int es, bool vec16_ok, cudaStream_t stream);
 
+// a run of tile copies that walks a regular grid - tile t = i * J + j reads in0 + i * in_outer + j * in_inner and writes
+// out0 + i * out_outer + j * out_inner (byte steps) - as ONE TMA-to-TMA copy kernel (tile_grid.cu); false = TMA cannot
+// express the run (nothing launched)
+bool launch_tile_grid(const void *in0, void *out0, int64_t J, int64_t I, int64_t in_inner, int64_t in_outer, int64_t out_inner,
+                      int64_t out_outer, int64_t m, int64_t n, int64_t ldi, int64_t ldo, int es, cudaStream_t stream);
+
 struct GemmArgs {
   const void *A = nullptr;
   const void *B = nullptr;

@@ -102,6 +102,9 @@ struct ThreadCtx {
   // run of tile moves with ONE descriptor and no hazards among them (a tensor.pack / unpack lowered tile by tile):
   // launched as one batched kernel by flush_tiles(). At most one of the two pending lists is non-empty.
   std::vector<PendingTile> pending_tiles;
+  // the run's source / destination rectangles by first byte (every tile of a run has the same extents): a new tile is
+  // tested only against the tiles whose byte range can reach its own - O(tiles of one row block) instead of O(run)
+  std::multimap<const char *, uint32_t> tiles_by_in, tiles_by_out;
   // a unary zero(C) recorded during capture and not launched yet (runtime CombineXsmmOp: see pending_producer_of)
   struct HeldZero { const KernelDesc *d = nullptr; char *out = nullptr; } held_zero;
   std::vector<void *> capture_tables;   // device tables baked into the graph being captured (freed with it)
@@ -1025,6 +1028,8 @@ void flush_tiles() {
   if (t_ctx.pending_tiles.empty()) return;
   std::vector<PendingTile> list;
   list.swap(t_ctx.pending_tiles);
+  t_ctx.tiles_by_in.clear();
+  t_ctx.tiles_by_out.clear();
   cudaStream_t stream = t_ctx.stream;
   const KernelDesc *d = list[0].d;
   if (list.size() < 4) {
@@ -1042,6 +1047,31 @@ void flush_tiles() {
   for (size_t i = 0; i < list.size(); ++i) {
     host[i] = {list[i].in, list[i].out};
     vec_ok = vec_ok && aligned16(list[i].in) && aligned16(list[i].out);
+  }
+  // A run that walks a regular grid (tile t = i * J + j at in0 + i * in_outer + j * in_inner -> out0 + i * out_outer +
+  // j * out_inner: what a lowered tensor.pack / unpack emits) needs no table at all: source and destination are one
+  // rank-4 tensor each and the copy is TMA to TMA (tile_grid.cu)
+  static const bool grid_off = [] { const char *e = getenv("TPP_XSMM_TILE_GRID"); return e && e[0] == '0'; }();
+  if (vec_ok && !grid_off) {
+    const int64_t n_t = (int64_t)list.size();
+    const int64_t in_inner = list[1].in - list[0].in, out_inner = list[1].out - list[0].out;
+    int64_t J = n_t;
+    for (int64_t i = 1; i < n_t; ++i)
+      if (list[i].in - list[i - 1].in != in_inner || list[i].out - list[i - 1].out != out_inner) { J = i; break; }
+    bool regular = (n_t % J) == 0;
+    const int64_t I = regular ? n_t / J : 0;
+    const int64_t in_outer = I > 1 ? list[J].in - list[0].in : 0, out_outer = I > 1 ? list[J].out - list[0].out : 0;
+    for (int64_t t = 0; regular && t < n_t; ++t)
+      regular = list[t].in == list[0].in + (t / J) * in_outer + (t % J) * in_inner &&
+                list[t].out == list[0].out + (t / J) * out_outer + (t % J) * out_inner;
+    if (regular && launch_tile_grid(list[0].in, list[0].out, J, I, in_inner, in_outer, out_inner, out_outer, d->m, d->n, d->ldi,
+                                    d->ldo, (int)es, stream)) {
+      static thread_local char gname[96];
+      snprintf(gname, sizeof(gname), "%s_batch%zu_tma%lldx%lld", d->name, list.size(), (long long)I, (long long)J);
+      t_ctx.last_kernel = gname;
+      count_launch();
+      return;
+    }
   }
   // the table is written now, outside the capture; the graph only holds the kernel that reads it
   static thread_local cudaStream_t side = nullptr;
@@ -1172,15 +1202,31 @@ static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int
     // joins the pending run if it has the same descriptor and neither reads nor writes anything the run writes (nor
     // writes anything the run reads); otherwise the run is launched first and this invoke starts a new one
     const TileRects nr = tile_rects(d, ops[0].dev, ops[1].dev);
-    bool join = t_ctx.pending_tiles.empty() || (t_ctx.pending_tiles[0].d == d && t_ctx.pending_tiles.size() < 8192);
-    for (size_t i = 0; join && i < t_ctx.pending_tiles.size(); ++i) {
-      const TileRects pr = tile_rects(d, t_ctx.pending_tiles[i].in, t_ctx.pending_tiles[i].out);
-      if (rects_overlap(nr.out, nr.out_rows, nr.out_w, nr.out_ld, pr.out, pr.out_rows, pr.out_w, pr.out_ld) ||
-          rects_overlap(nr.out, nr.out_rows, nr.out_w, nr.out_ld, pr.in, pr.in_rows, pr.in_w, pr.in_ld) ||
-          rects_overlap(nr.in, nr.in_rows, nr.in_w, nr.in_ld, pr.out, pr.out_rows, pr.out_w, pr.out_ld))
-        join = false;
+    constexpr size_t kMaxRun = 1u << 17;
+    bool join = t_ctx.pending_tiles.empty() || (t_ctx.pending_tiles[0].d == d && t_ctx.pending_tiles.size() < kMaxRun);
+    if (join && !t_ctx.pending_tiles.empty()) {
+      // byte extents of a source / destination rectangle of this descriptor; a recorded rectangle starting at `lo` can
+      // only touch [a, a_hi) if lo lies in (a - extent, a_hi)
+      const int64_t in_ext = (nr.in_rows - 1) * nr.in_ld + nr.in_w, out_ext = (nr.out_rows - 1) * nr.out_ld + nr.out_w;
+      auto hits = [&](const std::multimap<const char *, uint32_t> &index, int64_t ext, bool index_is_out, const char *a,
+                      int64_t a_rows, int64_t a_w, int64_t a_ld) {
+        const char *a_hi = a + (a_rows - 1) * a_ld + a_w;
+        for (auto it = index.upper_bound(a - ext); it != index.end() && it->first < a_hi; ++it) {
+          const PendingTile &pt = t_ctx.pending_tiles[it->second];
+          const TileRects pr = tile_rects(d, pt.in, pt.out);
+          if (index_is_out ? rects_overlap(a, a_rows, a_w, a_ld, pr.out, pr.out_rows, pr.out_w, pr.out_ld)
+                           : rects_overlap(a, a_rows, a_w, a_ld, pr.in, pr.in_rows, pr.in_w, pr.in_ld))
+            return true;
+        }
+        return false;
+      };
+      join = !hits(t_ctx.tiles_by_out, out_ext, true, nr.out, nr.out_rows, nr.out_w, nr.out_ld) &&    // write after write
+             !hits(t_ctx.tiles_by_in, in_ext, false, nr.out, nr.out_rows, nr.out_w, nr.out_ld) &&     // write after read
+             !hits(t_ctx.tiles_by_out, out_ext, true, nr.in, nr.in_rows, nr.in_w, nr.in_ld);          // read after write
     }
     if (!join) flush_tiles();
+    t_ctx.tiles_by_in.emplace(ops[0].dev, (uint32_t)t_ctx.pending_tiles.size());
+    t_ctx.tiles_by_out.emplace(ops[1].dev, (uint32_t)t_ctx.pending_tiles.size());
     t_ctx.pending_tiles.push_back({d, ops[0].dev, ops[1].dev});
     t_ctx.note_output(ops[1].dev, (size_t)((ops[1].rows - 1) * ops[1].ld + ops[1].width) * esize(dtype));
     return;

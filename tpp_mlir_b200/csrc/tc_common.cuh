@@ -145,6 +145,9 @@ bool encode_map_x4(CUtensorMap *map, const void *base, uint64_t k, uint64_t rows
 // generic bf16 tensor map of rank <= 5: dims / strides (elements; strides[0] is the stride of dims[1]) / box
 bool encode_map_nd(CUtensorMap *map, const void *base, int rank, const uint64_t *dims, const uint64_t *strides,
                    const uint32_t *box, int swizzle_bytes);
+// rank-4 map over 4-byte units (dtype-agnostic data movement): dims[0] in 4-byte units, strides in BYTES, no swizzle
+bool encode_map_u32_4d(CUtensorMap *map, const void *base, const uint64_t *dims, const uint64_t *strides_bytes,
+                       const uint32_t *box);
 int bin_mode_from_flags(int64_t f);
 
 // Device memory owned by the graph being captured. Everything a captured kernel node reads or spins on (descriptor

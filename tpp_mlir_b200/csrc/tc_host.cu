@@ -91,6 +91,19 @@ bool encode_map_nd(CUtensorMap *map, const void *base, int rank, const uint64_t 
   return r == CUDA_SUCCESS;
 }
 
+// rank-4 map over 4-byte units (dtype-agnostic data movement): dims[0] in 4-byte units, strides in BYTES, no swizzle
+bool encode_map_u32_4d(CUtensorMap *map, const void *base, const uint64_t *dims, const uint64_t *strides_bytes,
+                       const uint32_t *box) {
+  cuuint64_t gd[4], gs[3];
+  cuuint32_t bx[4], estr[4];
+  for (int i = 0; i < 4; ++i) { gd[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i < 3; ++i) gs[i] = strides_bytes[i];
+  CUresult r = get_encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, const_cast<void *>(base), gd, gs, bx, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
 int bin_mode_from_flags(int64_t f) {
   if (f & 4) return kBcastCol;
   if (f & 1) return kBcastRow;
