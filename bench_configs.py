@@ -186,6 +186,7 @@ def reference_stream(pk, tiles=(32, 32, 32), vnni=True):
         hot = harness.NativeMlpLoop(wl.cfg, wl.replay.handles, wl.sets[:1])
         lone = {}
         for label, run in (("unrolled16", lambda k: hot.run_graph_unrolled(k, 16)), ("one_forward_per_graph", hot.run_graph)):
+            run(16)              # both graphs (16 forwards / 1 forward) are captured here, outside the timed region
             for _ in range(10):
                 run(1)
             torch.cuda.synchronize()

@@ -52,3 +52,18 @@ dt = xsmm.perf_stop_timer(t0) / reps
 print(f"replay: {dt * 1e6:.2f} us per forward ({cfg.flops() / dt / 1e12:.1f} TF/s)")
 if os.environ.get("TPP_XSMM_TC_TRACE"):
     xsmm.LIB.xsmm_cuda_debug_dump_trace()
+# UNROLL=k: tpp-run's loop unrolled k times before capture (exact repeats -> one sequential pass list)
+unroll = int(os.environ.get("UNROLL", "0"))
+if unroll > 1:
+    stream = torch.cuda.current_stream()
+    xsmm.set_stream(stream.cuda_stream)
+    loop = harness.NativeMlpLoop(cfg, r.handles, [(r.acts, r.weights, r.biases)])
+    loop.run_graph_unrolled(unroll * 4, unroll)
+    xsmm.sync()
+    n = unroll * 32
+    t0 = xsmm.perf_start_timer()
+    loop.run_graph_unrolled(n, unroll)
+    dt = xsmm.perf_stop_timer(t0) / n
+    print(f"unrolled x{unroll}: kernel {xsmm.last_kernel()}: {dt * 1e6:.2f} us per forward")
+    if os.environ.get("TPP_XSMM_TC_TRACE"):
+        xsmm.LIB.xsmm_cuda_debug_dump_trace()

@@ -108,6 +108,7 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
 // device tables allocated by chain launches since the last call (owned by the graph being captured)
 void brgemm_tc_take_capture_allocs(std::vector<void *> &out);
 const char *brgemm_tc_last_name();   // tile configuration of this thread's last tcgen05 launch
+int brgemm_tc_take_extra_launches();   // helper kernels the last chain launches put in front of themselves (since the last call)
 void brgemm_tc_dump_trace();   // debug, TPP_XSMM_TC_TRACE=2
 
 } // namespace tpp

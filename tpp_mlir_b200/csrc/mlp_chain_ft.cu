@@ -66,6 +66,9 @@ struct alignas(64) FtPass {
   int32_t m, n;
   int64_t c_step_n, c_step_k;
   int16_t grp_kb[4], grp_be[4];
+  // the same for the weights, which may be addressed differently from the activations (a flat copy of VNNI-2 weights)
+  int32_t w_n;
+  int16_t w_kb[4], w_be[4];
 };
 
 struct FtParams {
@@ -177,8 +180,8 @@ __global__ void __launch_bounds__(VNNI ? FT_THREADS_VNNI : NUM_THREADS, 1) mlp_c
       const FtPass &ps = cp.pass[p];
       if constexpr (GEN) {
         // my 64 features: column block n0 / n, column n0 % n in it (n == 32: two column blocks per box, VNNI only)
-        const int32_t cb = n0 / ps.n, n_in = n0 - cb * ps.n;
-        const int32_t kb = ps.grp_kb[g], be = ps.grp_be[g];
+        const int32_t cb = n0 / ps.w_n, n_in = n0 - cb * ps.w_n;
+        const int32_t kb = ps.w_kb[g], be = ps.w_be[g];
         if (ptx::elect_one()) {
           if constexpr (VNNI) {
             // raw [k/2][n][2] rows: (element of the row | column block | k pair | batch element), counted on raw_full
@@ -857,8 +860,61 @@ static bool chain_ftg_supported(const KernelDesc *const *descs, const GemmArgs *
   return true;
 }
 
-// tensor maps of a GEN pass (see the kernel's header comment); sizes in elements
-static bool encode_ftg_maps(FtPass &ps, const KernelDesc &d, const GemmArgs &g, bool vnni) {
+// ---- VNNI-2 weights of a lone chain: one flat copy per graph launch ---------------------------------------------------
+// The in-kernel converter warps double the shared-memory traffic of a pass (raw rows in, rewritten rows out), and in the
+// pass kernels shared memory is the bound: measured +4.4 us per forward (18.4 against 14.0 us), every CTA of a feature
+// tile's eight row tiles redoing the same rewrite. Weights do not change inside a chain (hazard-tested), so the launcher
+// instead puts ONE small kernel in front of the chain kernel that un-interleaves (and un-blocks) every layer's weights
+// into a graph-owned scratch [K][N] - 12 MiB of L2-resident traffic per graph launch, shared by all exact repeats of the
+// chain in that launch - and the chain kernel reads the flat copy through the ordinary weight map. Every replay of the
+// graph converts again: weights the caller changed between two launches are seen. TPP_XSMM_FT_VNNI_SCRATCH=0 keeps the
+// converter warps.
+struct WFlatLayer {
+  const uint16_t *src;   // [gk column blocks][nb batch elements][k/2][ldb][2]
+  uint16_t *dst;         // [nb * k][gk * n]
+  int64_t ldb, stride_b, b_step;
+  int32_t n, k, nb, gk;
+};
+struct WFlatParams {
+  WFlatLayer layer[16];
+};
+__global__ void __launch_bounds__(256) vnni2_weights_to_flat_kernel(const __grid_constant__ WFlatParams p) {
+  const WFlatLayer L = p.layer[blockIdx.y];
+  const int64_t n_total = (int64_t)L.gk * L.n, k_total = (int64_t)L.nb * L.k;
+  const int64_t c8s = n_total / 8, units = (k_total / 2) * c8s;   // a unit: one k pair x 8 columns (32 bytes in, 2 x 16 out)
+  for (int64_t u0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; u0 < units; u0 += (int64_t)gridDim.x * blockDim.x * 2) {
+    uint4 a[2], b[2];
+    int64_t kg[2], col[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int64_t u = u0 + i;
+      if (u < units) {
+        const int64_t kp = u / c8s;
+        col[i] = (u - kp * c8s) * 8;
+        kg[i] = 2 * kp;
+        const int64_t j = col[i] / L.n, nn = col[i] - j * L.n, be = kg[i] / L.k, kk = kg[i] - be * L.k;
+        const uint4 *src = reinterpret_cast<const uint4 *>(L.src + j * L.b_step + be * L.stride_b + ((kk / 2) * L.ldb + nn) * 2);
+        a[i] = __ldg(src);
+        b[i] = __ldg(src + 1);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (u0 + i >= units) continue;
+      uint4 r0, r1;
+      r0.x = __byte_perm(a[i].x, a[i].y, 0x5410); r1.x = __byte_perm(a[i].x, a[i].y, 0x7632);
+      r0.y = __byte_perm(a[i].z, a[i].w, 0x5410); r1.y = __byte_perm(a[i].z, a[i].w, 0x7632);
+      r0.z = __byte_perm(b[i].x, b[i].y, 0x5410); r1.z = __byte_perm(b[i].x, b[i].y, 0x7632);
+      r0.w = __byte_perm(b[i].z, b[i].w, 0x5410); r1.w = __byte_perm(b[i].z, b[i].w, 0x7632);
+      *reinterpret_cast<uint4 *>(L.dst + kg[i] * n_total + col[i]) = r0;
+      *reinterpret_cast<uint4 *>(L.dst + (kg[i] + 1) * n_total + col[i]) = r1;
+    }
+  }
+}
+
+// tensor maps of a GEN pass (see the kernel's header comment); sizes in elements. w_flat: a flat [K][N] copy of the
+// layer's VNNI-2 weights (above) to read instead of g.B
+static bool encode_ftg_maps(FtPass &ps, const KernelDesc &d, const GemmArgs &g, bool vnni, const void *w_flat = nullptr) {
   const uint64_t nb = (uint64_t)g.batch, gn = (uint64_t)g.grid_n, gk = (uint64_t)g.grid_k;
   // a dimension of size 1 may carry any legal stride
   const uint64_t sa = nb > 1 ? (uint64_t)d.stride_a : (uint64_t)d.lda, sb = nb > 1 ? (uint64_t)d.stride_b : (uint64_t)d.ldb;
@@ -872,7 +928,15 @@ static bool encode_ftg_maps(FtPass &ps, const KernelDesc &d, const GemmArgs &g, 
     const uint32_t box[5] = {kx, FT_N, box_kb, box_be, 1};
     if (!encode_map_nd(&ps.tmX, g.A, 5, dims, str, box, kx == 32 ? 64 : 128)) return false;
   }
-  if (vnni) {
+  ps.w_n = (int32_t)d.n;
+  if (w_flat) {
+    // the flat copy: one [K][N] matrix, 64 features x 256 k per box
+    const uint64_t n_total = gk * (uint64_t)d.n, k_total = nb * (uint64_t)d.k;
+    const uint64_t dims[4] = {n_total, k_total, 1, 1}, str[3] = {n_total, n_total, n_total};
+    const uint32_t box[4] = {FT_M, FT_GROUP * BLOCK_K, 1, 1};
+    if (!encode_map_nd(&ps.tmW, w_flat, 4, dims, str, box, 128)) return false;
+    ps.w_n = (int32_t)n_total;
+  } else if (vnni) {
     // raw VNNI-2 rows: (element of the [n][2] row | column block | k pair | batch element); 64 features x 2 = 256 bytes
     // per k pair (two column blocks when n == 32), 128 k pairs per box; no swizzle
     const uint32_t ex = 2 * (uint32_t)std::min<int64_t>(d.n, FT_M), kpx = (uint32_t)std::min<int64_t>(d.k / 2, FT_GROUP * BLOCK_K / 2);
@@ -893,6 +957,8 @@ static bool encode_ftg_maps(FtPass &ps, const KernelDesc &d, const GemmArgs &g, 
     const int64_t k0 = (int64_t)gq * FT_GROUP * BLOCK_K;     // first reduction index of the group
     ps.grp_be[gq] = (int16_t)(k0 / d.k);
     ps.grp_kb[gq] = (int16_t)((k0 % d.k) / BLOCK_K);
+    ps.w_be[gq] = w_flat ? (int16_t)0 : ps.grp_be[gq];
+    ps.w_kb[gq] = w_flat ? (int16_t)(k0 / BLOCK_K) : ps.grp_kb[gq];
   }
   return true;
 }
@@ -1023,6 +1089,47 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   uint32_t arrivals[FT_MAX_WAYS] = {0, 0, 0, 0};
   int np = 0;
   bool weights_early = true;
+  // VNNI-2 weights: flat copies made by one kernel in front of this one (see vnni2_weights_to_flat_kernel); a weight
+  // buffer shared by several passes (exact repeats) is converted once. More than 16 distinct buffers, or column blocks /
+  // row pitches the 16-byte path cannot take: the converter warps of the <VNNI> instantiations do the job instead.
+  static const bool scratch_off = [] { const char *e = getenv("TPP_XSMM_FT_VNNI_SCRATCH"); return e && e[0] == '0'; }();
+  bool w_scratch = gen && gen_vnni && !scratch_off;
+  WFlatParams wf;
+  memset(&wf, 0, sizeof(wf));
+  int n_wf = 0;
+  std::vector<std::pair<const void *, int>> wf_index;   // (weights, layer shape id) -> entry of wf
+  if (w_scratch) {
+    for (int c = 0; c < take && w_scratch; ++c)
+      for (int l = 0; l < len[c] && w_scratch; ++l) {
+        const KernelDesc &d = *descs[first[c] + l];
+        const GemmArgs &g = args[first[c] + l];
+        bool seen = false;
+        for (const auto &e : wf_index) seen = seen || e.first == g.B;
+        if (seen) continue;
+        if (n_wf == 16 || (d.n % 8) != 0 || (d.k % 2) != 0 || (d.ldb % 4) != 0 || (d.stride_b % 8) != 0 || (g.b_step % 8) != 0) {
+          w_scratch = false;
+          break;
+        }
+        wf_index.push_back({g.B, n_wf});
+        WFlatLayer &wl = wf.layer[n_wf++];
+        wl.src = static_cast<const uint16_t *>(g.B);
+        wl.ldb = d.ldb; wl.stride_b = g.batch > 1 ? d.stride_b : 0; wl.b_step = g.grid_k > 1 ? g.b_step : 0;
+        wl.n = (int32_t)d.n; wl.k = (int32_t)d.k; wl.nb = (int32_t)g.batch; wl.gk = g.grid_k;
+      }
+    if (w_scratch)
+      for (int i = 0; i < n_wf; ++i) {
+        WFlatLayer &wl = wf.layer[i];
+        void *buf = nullptr;
+        TPP_CUDA_CHECK(cudaMalloc(&buf, (size_t)wl.nb * wl.k * wl.gk * wl.n * sizeof(uint16_t)));
+        capture_adopt(buf);   // owned by the graph being captured
+        wl.dst = static_cast<uint16_t *>(buf);
+      }
+  }
+  auto flat_copy_of = [&](const void *B) -> const void * {
+    for (const auto &e : wf_index)
+      if (e.first == B) return wf.layer[e.second].dst;
+    return nullptr;
+  };
   auto add_pass = [&](int c, int l, int slot) -> bool {
     const KernelDesc &d = *descs[first[c] + l];
     const GemmArgs &g = args[first[c] + l];
@@ -1032,7 +1139,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     const uint32_t grp = split == 4 ? FS<4>::GROUP : split == 2 ? FS<2>::GROUP : FT_GROUP;
     const uint32_t gk = k_iters >= grp ? grp : (k_iters ? k_iters : 1), gb = grp / gk;   // box = gk k-blocks x gb batch elements
     if (gen) {
-      if (!encode_ftg_maps(ps, d, g, gen_vnni)) return false;
+      if (!encode_ftg_maps(ps, d, g, gen_vnni, w_scratch ? flat_copy_of(g.B) : nullptr)) return false;
     } else if (!encode_map_x4(&ps.tmX, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a,
                               32 * split, gk, gb) ||
                !encode_map(&ps.tmW, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, FT_M,
@@ -1050,7 +1157,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
     ps.wait_arrivals = arrivals[ps.slot];
     ps.arrive = l + 1 < len[c] ? 1 : 0;
     if (ps.arrive) ++arrivals[ps.slot];
-    if (!g.b_independent) weights_early = false;
+    if (!g.b_independent || w_scratch) weights_early = false;   // the flat copies are written by the kernel just before
     ++np;
     return true;
   };
@@ -1098,9 +1205,10 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   const int smem = split == 4 ? FS<4>::SMEM : split == 2 ? FS<2>::SMEM : smem1;
   // the kernel this launch runs (full-K instantiations; the split-K variants are set below)
   using FtKernel = void (*)(const FtParams);
-  const FtKernel ft_kernel = !gen                      ? mlp_chain_ft_kernel<false, false, false>
-                             : gen_vnni && gen_narrow ? mlp_chain_ft_kernel<true, true, true>
-                             : gen_vnni               ? mlp_chain_ft_kernel<true, true, false>
+  const bool conv_warps = gen && gen_vnni && !w_scratch;   // VNNI-2 weights rewritten inside the kernel
+  const FtKernel ft_kernel = !gen                        ? mlp_chain_ft_kernel<false, false, false>
+                             : conv_warps && gen_narrow ? mlp_chain_ft_kernel<true, true, true>
+                             : conv_warps               ? mlp_chain_ft_kernel<true, true, false>
                              : gen_narrow             ? mlp_chain_ft_kernel<true, false, true>
                                                       : mlp_chain_ft_kernel<true, false, false>;
   static std::once_flag once;
@@ -1115,7 +1223,7 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   });
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(split2 ? F2_THREADS : (gen && gen_vnni) ? FT_THREADS_VNNI : NUM_THREADS);
+  cfg.blockDim = dim3(split2 ? F2_THREADS : conv_warps ? FT_THREADS_VNNI : NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[3];
@@ -1151,6 +1259,12 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
                     : split == 2 ? reinterpret_cast<const void *>(mlp_chain_fts_kernel<2>)
                                  : reinterpret_cast<const void *>(ft_kernel);
   if (!prepare_resident_launch(kfn, &cfg, attrs)) return 0;
+  if (w_scratch && n_wf > 0) {
+    // 74 CTAs x 256 threads x 2 units per layer and sweep; a layer of 1024 x 1024 has 65536 units
+    vnni2_weights_to_flat_kernel<<<dim3(128, (unsigned)n_wf), 256, 0, stream>>>(wf);
+    TPP_CUDA_CHECK(cudaGetLastError());
+    note_extra_launch();
+  }
   if (split == 4) TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_fts_kernel<4>, cp));
   else if (split == 2) TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_fts_kernel<2>, cp));
   else TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ft_kernel, cp));

@@ -674,6 +674,7 @@ void flush_pending_impl() {
     if (took > 0) {
       t_ctx.last_kernel = brgemm_tc_last_name();
       count_launch();
+      for (int x = brgemm_tc_take_extra_launches(); x > 0; --x) count_launch();   // e.g. the VNNI-2 -> flat weight copy
       sidx += took;
       continue;
     }

@@ -176,6 +176,7 @@ bool prepare_resident_launch(const void *kernel, cudaLaunchConfig_t *cfg, cudaLa
                              bool only_if_concurrent = false);
 
 void set_last_name(const char *fmt, ...);      // this thread's last tcgen05 launch (xsmm_cuda_last_kernel)
+void note_extra_launch();                      // a helper kernel launched besides the one the caller counts
 
 struct ByteRange { const char *lo, *hi; };
 inline bool overlaps(const ByteRange &a, const ByteRange &b) { return a.lo < b.hi && b.lo < a.hi; }

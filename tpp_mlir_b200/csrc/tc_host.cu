@@ -115,7 +115,9 @@ int bin_mode_from_flags(int64_t f) {
 // ---- the name of this thread's last tcgen05 launch ----------------------------------------------------------------
 namespace {
 thread_local char t_last_name[96] = "brgemm_tc_bf16";
+thread_local int t_extra_launches = 0;
 }
+void note_extra_launch() { ++t_extra_launches; }
 void set_last_name(const char *fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
@@ -295,6 +297,11 @@ bool chain_operands_hazard_free(const KernelDesc *const *descs, const GemmArgs *
 using namespace tc;
 
 const char *brgemm_tc_last_name() { return t_last_name; }
+int brgemm_tc_take_extra_launches() {
+  const int n = t_extra_launches;
+  t_extra_launches = 0;
+  return n;
+}
 
 void brgemm_tc_take_capture_allocs(std::vector<void *> &out) {
   out.insert(out.end(), t_capture_allocs.begin(), t_capture_allocs.end());
