@@ -228,7 +228,9 @@ __global__ void __launch_bounds__(VNNI ? FT_THREADS_VNNI : NUM_THREADS, 1) mlp_c
       }
       __syncwarp();
     };
-    const bool x0_early = cp.weights_early && cp.x0_early && !cp.pass[0].x_dep;
+    // pass 0's activations go out group by group with its weights when they are not produced by in-flight kernels - or
+    // when the loads are issued behind the wait anyway
+    const bool x0_early = !cp.pass[0].x_dep && (cp.weights_early ? cp.x0_early != 0 : true);
     auto early_loads = [&]() {
       for (int g = 0; g < cp.pass[0].groups; ++g) {  // group by group: the MMAs start on the first 48 KiB
         issue_w(0, g);
@@ -1093,7 +1095,10 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   // buffer shared by several passes (exact repeats) is converted once. More than 16 distinct buffers, or column blocks /
   // row pitches the 16-byte path cannot take: the converter warps of the <VNNI> instantiations do the job instead.
   static const bool scratch_off = [] { const char *e = getenv("TPP_XSMM_FT_VNNI_SCRATCH"); return e && e[0] == '0'; }();
-  bool w_scratch = gen && gen_vnni && !scratch_off;
+  // (one conversion kernel per graph launch pays off when the launch re-reads the weights - the exact repeats of an unrolled
+  // loop: 10.2 against 15.7 us per forward; a single forward pass per launch is faster with the converter warps, 18.4
+  // against 20.5 us: the extra kernel node costs more than the rewrite it saves)
+  bool w_scratch = gen && gen_vnni && !scratch_off && sequential;
   WFlatParams wf;
   memset(&wf, 0, sizeof(wf));
   int n_wf = 0;
