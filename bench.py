@@ -654,8 +654,6 @@ def main():
     # ---- side measurements with a driver clock record: configs[1], [3], [4] and the reference's default call stream --
     extras = {}
     if not args.no_extras:
-        import bench_configs
-
         pk_ = peaks()
         # BASELINE configs[4] (batch 2048): at N > 1 sharded over the ranks (strong scaling, 2048/N rows per GPU), at N = 1
         # all 2048 rows on the one GPU. Skipped when it IS the main workload (--global-batch 2048)
@@ -685,12 +683,17 @@ def main():
             del wl5
         if n_gpus == 1:
             extras["tpp_run_standin"] = run_standin()
-            for name, fn in (("cfg2_brgemm_1024x16", bench_configs.cfg2), ("cfg4_vnni2_pack_4096", bench_configs.cfg4),
-                             ("reference_default_stream", bench_configs.reference_stream)):
-                try:
-                    extras[name] = fn(pk_)
-                except Exception as e:   # a side measurement must not take the headline down with it
-                    extras[name] = {"error": repr(e)}
+            # configs[1], configs[3], the reference's default stream and the tile-wise pack: measured in a process of their
+            # own, as a program that only does that would see them (this process has launched from several streams by now,
+            # which switches the flag-synchronised split-K GEMM to cooperative launches: cfg2 1040 instead of 1120-1140 TF/s)
+            import subprocess
+
+            try:
+                r = subprocess.run([sys.executable, os.path.join(ROOT, "bench_configs.py"), "--bench-extras"], capture_output=True,
+                                   text=True, timeout=600, cwd=ROOT)
+                extras.update(json.loads(r.stdout.strip().splitlines()[-1]))
+            except Exception as e:   # a side measurement must not take the headline down with it
+                extras["side_measurements"] = {"error": repr(e)}
         xsmm.set_stream(stream.cuda_stream)
 
     if rank != 0:
