@@ -174,6 +174,21 @@ def main():
     t = read("test/Integration/matmul_64x64x64.mlir")
     add("matmul_64x64x64_f32", "test/Integration/matmul_64x64x64.mlir:1-16", raw_checks=check_lines(t))
 
+    # round 2, second batch: more of the reference's tests that end in xsmm invokes of this path
+    t = read("test/Integration/xsmm-ternary.mlir")
+    add("brgemm_f32_ternary", "test/Integration/xsmm-ternary.mlir:5-16", expected=flat_checks(t))
+    for name in ("matmul_48x64x96", "matmul_64x48x96"):
+        t = read(f"test/Integration/{name}.mlir")
+        add(f"{name}_f32", f"test/Integration/{name}.mlir", raw_checks=check_lines(t))
+    t = read("test/Integration/tpp-brgemm-non-unit-batch.mlir")
+    d = dense_blocks(t)
+    add("brgemm_f32_non_unit_batch", "test/Integration/tpp-brgemm-non-unit-batch.mlir:12-66", A=d[0], B=d[1],
+        expected=flat_checks(t))
+    t = read("test/Integration/transpose-fp32.mlir")
+    add("transpose_f32_seed123", "test/Integration/transpose-fp32.mlir:1-25", expected=flat_checks(t))
+    t = read("test/Integration/mlp-fp32-1layer-512.mlir")
+    add("mlp_fp32_1layer_512", "test/Integration/mlp-fp32-1layer-512.mlir:8-31", raw_checks=check_lines(t))
+
     with open(OUT, "w") as f:
         json.dump(g, f, indent=1, sort_keys=True)
     print(f"wrote {OUT}: {len(g)} vectors, {os.path.getsize(OUT)} bytes")

@@ -308,4 +308,60 @@ def case_mlp_all_ones_bf16(be):
     return to_f32(BF16, x).reshape(-1), expect, g["threshold"]
 
 
+def case_brgemm_f32_ternary(be):
+    # test/Integration/xsmm-ternary.mlir:7: dispatch [3,3,4,4,3,3,12,12] flags none, batch 2, all ones: 1 + 2*4 = 9
+    A, B, C = const(F32, (2, 3, 4)), const(F32, (2, 4, 3)), const(F32, (9,))
+    be.brgemm(F32, 3, 3, 4, 4, 3, 3, 12, 12, 0, A, 0, B, 0, C, 0, 2)
+    return C, np.array(golden()["brgemm_f32_ternary"]["expected"], np.float32), 0.0
+
+
+def _case_whole_matmul(be, key, m, n, k):
+    # M or N no multiple of the default 32 x 32 x 32 packing: the pipeline keeps ONE xsmm_gemm_invoke on the whole
+    # matrices (the IR check of the test), all ones, C initialised to 1 => k + 1
+    A, B, C = const(F32, (m, k)), const(F32, (k, n)), const(F32, (m * n,))
+    be.gemm(F32, m, n, k, k, n, n, 0, A, 0, B, 0, C, 0)
+    rows = golden()[key]["raw_checks"]
+    assert sum(r["repeat"] for r in rows) == m and all(len(r["values"]) == n for r in rows)
+    return C, np.concatenate([np.tile(np.array(r["values"], np.float32), r["repeat"]) for r in rows]), 0.0
+
+
+def case_matmul_48x64x96_f32(be):
+    # test/Integration/matmul_48x64x96.mlir:8-15
+    return _case_whole_matmul(be, "matmul_48x64x96_f32", 48, 64, 96)
+
+
+def case_matmul_64x48x96_f32(be):
+    # test/Integration/matmul_64x48x96.mlir:8-15
+    return _case_whole_matmul(be, "matmul_64x48x96_f32", 64, 48, 96)
+
+
+def case_brgemm_f32_non_unit_batch(be):
+    # test/Integration/tpp-brgemm-non-unit-batch.mlir:12-16: linalg.batch_reduce_matmul 2x4x8 . 2x8x4 into a zero 4x4
+    # -> xsmm_brgemm_dispatch(1, 4, 4, 8, 8, 4, 4, 32, 32, 0), batch 2; non-trivial operands (dense<> literals)
+    g = golden()["brgemm_f32_non_unit_batch"]
+    A, B, C = np.array(g["A"], np.float32), np.array(g["B"], np.float32), np.zeros(16, np.float32)
+    be.brgemm(F32, 4, 4, 8, 8, 4, 4, 32, 32, 0, A, 0, B, 0, C, 0, 2)
+    return C, np.array(g["expected"], np.float32), 6e-3   # 6 printed digits of values around 1e3
+
+
+def case_transpose_f32_seed123(be):
+    # test/Integration/transpose-fp32.mlir:7-8 (--seed 123): 3x5 f32 from tpp-run's normal TensorInit -> 5x3; pins the
+    # f32 stream of the RNG restatement
+    inp = oracle.TensorInit("normal", F32, 123).fill(3, 5)
+    out = np.zeros(15, np.float32)
+    be.unary(29, F32, 3, 5, 5, 3, 0, inp, 0, out, 0)
+    return out, np.array(golden()["transpose_f32_seed123"]["expected"], np.float32), 1e-6
+
+
+def case_mlp_fp32_1layer_512(be):
+    # test/Integration/mlp-fp32-1layer-512.mlir:8-20: relu(x[128x256] . W[256x512] + bias), all ones => 257; first row
+    # printed. As the fused op of the layer (beta_0, add bcast_col_in0, relu)
+    x, W, b = const(F32, (128, 256)), const(F32, (256, 512)), const(F32, (512,))
+    y = np.zeros(128 * 512, np.float32)
+    be.fused_brgemm(F32, 128, 512, 256, 256, 512, 512, 0, 0, 4, 0, 5, 4, 1, x, 0, W, 0, y, 0, b, 0, 1)
+    row = golden()["mlp_fp32_1layer_512"]["raw_checks"][0]["values"]
+    assert len(row) == 512
+    return y[:512], np.array(row, np.float32), 0.0
+
+
 CASES = {name[len("case_"):]: fn for name, fn in sorted(globals().items()) if name.startswith("case_")}
