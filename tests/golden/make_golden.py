@@ -186,6 +186,11 @@ def main():
         expected=flat_checks(t))
     t = read("test/Integration/transpose-fp32.mlir")
     add("transpose_f32_seed123", "test/Integration/transpose-fp32.mlir:1-25", expected=flat_checks(t))
+    t = read("test/BF16/Integration/matmul-pbf16.mlir")
+    add("matmul_pbf16", "test/BF16/Integration/matmul-pbf16.mlir:9-41", expected=flat_checks(t))
+    t = read("test/BF16/Integration/mlp-single-layer-blocked-bf16.mlir")
+    add("mlp_single_layer_blocked_bf16", "test/BF16/Integration/mlp-single-layer-blocked-bf16.mlir:11-57",
+        expected=flat_checks(t))
     t = read("test/Integration/mlp-fp32-1layer-512.mlir")
     add("mlp_fp32_1layer_512", "test/Integration/mlp-fp32-1layer-512.mlir:8-31", raw_checks=check_lines(t))
 

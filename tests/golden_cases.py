@@ -353,6 +353,24 @@ def case_transpose_f32_seed123(be):
     return out, np.array(golden()["transpose_f32_seed123"]["expected"], np.float32), 1e-6
 
 
+def case_matmul_pbf16(be):
+    # test/BF16/Integration/matmul-pbf16.mlir:9-41: A 4x8 ones, B already VNNI-packed [4][4][2] ones, C zeros, plain
+    # accumulation: gemm [4,4,8,8,4,4] (vnni_b) => 8
+    A, B, C = const(BF16, (4, 8)), const(BF16, (4, 4, 2)), np.zeros(16, np.uint16)
+    be.gemm(BF16, 4, 4, 8, 8, 4, 4, 2048, A, 0, B, 0, C, 0)
+    return to_f32(BF16, C), np.array(golden()["matmul_pbf16"]["expected"], np.float32), 0.0
+
+
+def case_mlp_single_layer_blocked_bf16(be):
+    # test/BF16/Integration/mlp-single-layer-blocked-bf16.mlir:22-52: per output block a BRGEMM over 64 blocks of 4x4x4
+    # (A block stride 16, VNNI-2 B block stride 16) accumulated onto C = 1, then relu in place: 1 + 64*4 = 257 -> 256 in
+    # bf16. One (row block, column block) of the test's loop nest; every block prints the same tile
+    A, B, C = const(BF16, (64, 4, 4)), const(BF16, (64, 2, 4, 2)), const(BF16, (16,))
+    be.brgemm(BF16, 4, 4, 4, 4, 4, 4, 16, 16, 2048, A, 0, B, 0, C, 0, 64)
+    be.unary(5, BF16, 4, 4, 4, 4, 0, C, 0, C, 0)
+    return to_f32(BF16, C), np.array(golden()["mlp_single_layer_blocked_bf16"]["expected"], np.float32), 0.0
+
+
 def case_mlp_fp32_1layer_512(be):
     # test/Integration/mlp-fp32-1layer-512.mlir:8-20: relu(x[128x256] . W[256x512] + bias), all ones => 257; first row
     # printed. As the fused op of the layer (beta_0, add bcast_col_in0, relu)
