@@ -376,11 +376,42 @@ def test_brgemm_bf16_vnni_b(shape, dev, orc):
     m, n, k, batch = shape
     g, o, kern = run_brgemm_pair(dev, orc, BF16, m, n, k, batch, vnni=True, fused=(5, 4, 1), seed=m)
     assert_close(BF16, g, o)
-    # VNNI-2 weights reach the tensor cores through an un-interleave pass once the problem is big enough
+    # VNNI-2 weights reach the tensor cores once the problem is big enough: rewritten in shared memory by the CTA-pair
+    # kernel (short reductions) or through one un-interleave pass in front of the flat kernel
     if m * n * k * batch >= 1 << 21:
-        assert kern == "vnni2_unpack+brgemm_tc_bf16", kern
+        assert kern == "vnni2_unpack+brgemm_tc_bf16" or (kern.startswith("brgemm_tc_bf16_256x") and kern.endswith("_vnni2")), kern
     else:
         assert kern.startswith("brgemm_simt_bf16"), kern
+
+
+@pytest.mark.parametrize("shape", [(256, 1024, 1024, 1), (1024, 1024, 64, 16), (512, 768, 128, 3), (300, 520, 192, 2)])
+@pytest.mark.parametrize("native", ["1", "0"])
+def test_brgemm_bf16_vnni_b_native_and_unpack_paths_agree(shape, native):
+    """VNNI-2 B on the tensor cores, both ways (TPP_XSMM_VNNI_NATIVE is read once per process, hence the subprocess): the
+    CTA-pair kernel's in-kernel rewrite (incl. the flag-synchronised split-K variant) and the un-interleave pass + flat
+    kernel give the oracle's answer."""
+    import subprocess
+    import sys
+
+    m, n, k, batch = shape
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = f"""
+import sys; sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})
+import numpy as np, oracle, backends
+from test_parity_gpu import run_brgemm_pair, assert_close
+dev, orc = backends.AbiBackend('device'), backends.OracleBackend()
+g, o, kern = run_brgemm_pair(dev, orc, 2, {m}, {n}, {k}, {batch}, vnni=True, fused=(5, 4, 1), seed={m})
+assert_close(2, g, o)
+print('KERNEL', kern)
+"""
+    out = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, TPP_XSMM_VNNI_NATIVE=native), capture_output=True,
+                         text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    kern = out.stdout.split("KERNEL")[-1].strip()
+    if native == "0":
+        assert kern == "vnni2_unpack+brgemm_tc_bf16", kern
+    else:   # the in-kernel path needs the CTA-pair tiling; shapes the cost model gives to other tilings keep the pass
+        assert kern == "vnni2_unpack+brgemm_tc_bf16" or kern.endswith("_vnni2"), kern
 
 
 def test_brgemm_unaligned_falls_back_to_generic_kernel(dev, orc):

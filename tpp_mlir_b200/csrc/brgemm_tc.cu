@@ -277,8 +277,14 @@ brgemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // 16 KiB + BLOCK_N*128 B: for BLOCK_N = 256 that is 32 KiB per 512 MMA clocks = 62 B/clk, inside what the SM<->L2
 // link delivers, where the single-CTA 128 x 256 tile needs 94 B/clk (measured 61 % of tensor peak, link-bound).
 // Cluster = (2, 1, S): the pair along x, optional split-K along z with the L2 workspace exchange.
-template <int BLOCK_N, int STAGES, int SPLITK>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// VNNI: B is VNNI-2 packed ([k/2][n][2], what the compiler emits for bf16 by default). TMA drops the raw rows of the
+// CTA's columns into the stage (no swizzle, counted on a per-CTA "raw" barrier) and eight converter warps rewrite them in
+// place into the swizzled MN-major tile - the scheme of the pair-per-chain kernel (mlp_chain_pair.cu) - and arrive on the
+// leader's "full" barrier: no un-interleave pass through HBM in front of the GEMM.
+constexpr int TC2_CONV_WARPS = 8;
+constexpr int TC2_THREADS_VNNI = NUM_THREADS + 32 * TC2_CONV_WARPS;
+template <int BLOCK_N, int STAGES, int SPLITK, bool VNNI = false>
+__global__ void __launch_bounds__(VNNI ? TC2_THREADS_VNNI : NUM_THREADS, 1)
 brgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcParams p) {
   constexpr int HALF_N = BLOCK_N / 2;                 // B columns staged by each CTA
   constexpr int kBChunks = HALF_N / 64;
@@ -291,7 +297,8 @@ brgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   const uint32_t full_bar = bar_base;                 // used in the leader only (both CTAs' bytes land on it)
   const uint32_t empty_bar = bar_base + STAGES * 8;   // one per CTA, released by the pair's MMA commits
   const uint32_t accum_bar = bar_base + 2 * STAGES * 8;
-  const uint32_t tmem_slot = accum_bar + 8;
+  const uint32_t raw_full = accum_bar + 8;            // [STAGES] per CTA (VNNI): my raw B rows have landed
+  const uint32_t tmem_slot = raw_full + STAGES * 8;
   uint8_t *smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   volatile uint32_t *tmem_slot_ptr = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - smem_base));
 
@@ -316,8 +323,10 @@ brgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     ptx::prefetch_tensormap(&tmA);
     ptx::prefetch_tensormap(&tmB);
     for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(full_bar + 8 * s, 1);
+      // VNNI: besides the producer's expect_tx arrival, the converter warps of BOTH CTAs arrive once their part is in place
+      ptx::mbar_init(full_bar + 8 * s, VNNI ? 1 + 2 * TC2_CONV_WARPS : 1);
       ptx::mbar_init(empty_bar + 8 * s, 1);
+      ptx::mbar_init(raw_full + 8 * s, 1);
     }
     ptx::mbar_init(accum_bar, 1);
     ptx::fence_mbar_init();
@@ -346,12 +355,22 @@ brgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const uint32_t ph = (i / STAGES) & 1;
         const int32_t b = it / p.k_iters, kb = it - b * p.k_iters;
         ptx::mbar_wait(empty_bar + 8 * s, ph ^ 1);
-        if (peer == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, 2 * kStageBytes);   // both CTAs' bytes
+        // both CTAs' bytes: A, plus B unless the converter warps deliver it
+        if (peer == 0) ptx::mbar_arrive_expect_tx(full_bar + 8 * s, VNNI ? 2 * A_STAGE_BYTES : 2 * kStageBytes);
         ptx::tma_load_3d_pair(smem_a + s * A_STAGE_BYTES, &tmA, leader_full + 8 * s, kb * BLOCK_K, m0, b);
+        if constexpr (VNNI) {
+          // raw [k/2][n][2] rows of my columns: (element of the row | k pair | batch element), counted on MY raw barrier
+          ptx::mbar_arrive_expect_tx(raw_full + 8 * s, kBChunks * B_CHUNK_BYTES);
 #pragma unroll
-        for (int c = 0; c < kBChunks; ++c)
-          ptx::tma_load_3d_pair(smem_b + (s * kBChunks + c) * B_CHUNK_BYTES, &tmB, leader_full + 8 * s,
-                                n0 + (int32_t)peer * HALF_N + c * 64, kb * BLOCK_K, b);
+          for (int c = 0; c < kBChunks; ++c)
+            ptx::tma_load_3d(smem_b + (s * kBChunks + c) * B_CHUNK_BYTES, &tmB, raw_full + 8 * s,
+                             2 * (n0 + (int32_t)peer * HALF_N + c * 64), kb * (BLOCK_K / 2), b);
+        } else {
+#pragma unroll
+          for (int c = 0; c < kBChunks; ++c)
+            ptx::tma_load_3d_pair(smem_b + (s * kBChunks + c) * B_CHUNK_BYTES, &tmB, leader_full + 8 * s,
+                                  n0 + (int32_t)peer * HALF_N + c * 64, kb * BLOCK_K, b);
+        }
       }
     }
   } else if (warp == 1) {
@@ -374,6 +393,53 @@ brgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         ptx::umma_commit_pair(empty_bar + 8 * s, pair_mask);   // frees the slot in both CTAs
       }
       if (num_iters > 0) ptx::umma_commit_pair(accum_bar, pair_mask);   // both epilogues may start
+    }
+  } else if (VNNI && warp >= 6) {
+    // ===== VNNI-2 converters (both CTAs): raw rows in the stage -> swizzled MN-major tile, in place (see mlp_chain_pair.cu) =====
+    const int cw = warp - 6;
+    const int row_sub = lane >> 4, half = lane & 1, g8 = vnni_group_of_lane(lane);
+    const uint32_t leader_full = ptx::mapa(full_bar, leader_rank);
+    constexpr int UNITS = 2 * kBChunks;               // 16-byte pieces per thread and k-block: 2 row groups x chunks
+    // software pipeline: the raw rows of k-block i + 1 are fetched into registers before k-block i is rewritten, fenced
+    // and signalled, so that the next stage's load latency hides behind this stage's store -> fence -> arrive
+    uint4 v[UNITS], vn[UNITS];
+    auto fetch = [&](int32_t i, uint4 (&dst)[UNITS]) {
+      const uint32_t s = (uint32_t)(i % STAGES), ph = (uint32_t)(i / STAGES) & 1u;
+      if (lane == 0) ptx::mbar_wait(raw_full + 8 * s, ph);   // one poller per warp
+      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < UNITS; ++u) {
+        const uint32_t R = (uint32_t)((u & 1) * 16 + cw * 2 + row_sub);     // raw row = k pair of the k-block
+        const uint32_t src = smem_b + (s * kBChunks + (u >> 1)) * B_CHUNK_BYTES + R * 256u + (uint32_t)(2 * g8 + half) * 16u;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(dst[u].x), "=r"(dst[u].y), "=r"(dst[u].z), "=r"(dst[u].w) : "r"(src));
+      }
+    };
+    if (num_iters > 0) fetch(0, vn);
+    for (int32_t i = 0; i < num_iters; ++i) {
+      const uint32_t s = (uint32_t)(i % STAGES);
+#pragma unroll
+      for (int u = 0; u < UNITS; ++u) v[u] = vn[u];
+      __syncwarp();                                   // every lane has read its rows before any lane overwrites them
+      if (i + 1 < num_iters) fetch(i + 1, vn);        // a different stage: nothing this warp still has to write
+#pragma unroll
+      for (int u = 0; u < UNITS; ++u) {
+        const uint32_t lo0 = __byte_perm(v[u].x, v[u].y, 0x5410), lo1 = __byte_perm(v[u].z, v[u].w, 0x5410);
+        const uint32_t hi0 = __byte_perm(v[u].x, v[u].y, 0x7632), hi1 = __byte_perm(v[u].z, v[u].w, 0x7632);
+        const uint32_t r0 = __shfl_xor_sync(0xffffffffu, half ? lo0 : hi0, 1);
+        const uint32_t r1 = __shfl_xor_sync(0xffffffffu, half ? lo1 : hi1, 1);
+        const uint32_t o0 = half ? r0 : lo0, o1 = half ? r1 : lo1, o2 = half ? hi0 : r0, o3 = half ? hi1 : r1;
+        const uint32_t krow = 2u * (uint32_t)((u & 1) * 16 + cw * 2 + row_sub) + (uint32_t)half;   // k row of the 64 x 64 chunk
+        const uint32_t base = smem_b + (s * kBChunks + (u >> 1)) * B_CHUNK_BYTES;
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};"
+                     ::"r"(base + krow * 128u + (((uint32_t)g8 ^ (krow & 7u)) << 4)), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                     : "memory");
+      }
+      ptx::fence_proxy_async();                       // my shared-memory writes -> the async proxy (the pair's MMAs)
+      __syncwarp();
+      if (lane == 0) {
+        if (peer == 0) ptx::mbar_arrive(full_bar + 8 * s);
+        else ptx::mbar_arrive_remote_relaxed(leader_full + 8 * s);
+      }
     }
   } else {
     // ===== epilogue (both CTAs, each on its own 128 rows of TMEM) =====
@@ -407,7 +473,7 @@ brgemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 
   if constexpr (SPLITK) {
-    if (warp >= 2) {
+    if (warp >= 2 && warp < 6) {
       const int q = warp & 3;
       splitk_epilogue_l2_wide<BLOCK_N>(p, tmem_acc, q, lane, m0, n0, rank, num_iters > 0, blockIdx.x, gridDim.x,
                                        blockIdx.y, /*flag_sync=*/SPLITK == 3);
@@ -468,17 +534,17 @@ void launch_cfg(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &
   TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, brgemm_tc_kernel<BLOCK_N, STAGES, SPLITK, MC>, tmA, tmB, p));
 }
 
-template <int BLOCK_N, int STAGES, int SPLITK>
+template <int BLOCK_N, int STAGES, int SPLITK, bool VNNI = false>
 bool launch_cfg_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &p, dim3 grid, cudaStream_t stream) {
-  constexpr int smem = STAGES * (A_STAGE_BYTES + (BLOCK_N / 128) * B_CHUNK_BYTES) + (2 * STAGES + 1) * 8 + 16 + 1024;
+  constexpr int smem = STAGES * (A_STAGE_BYTES + (BLOCK_N / 128) * B_CHUNK_BYTES) + (3 * STAGES + 1) * 8 + 16 + 1024;
   static std::once_flag once;
   std::call_once(once, [] {
-    TPP_CUDA_CHECK(cudaFuncSetAttribute(brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK>,
+    TPP_CUDA_CHECK(cudaFuncSetAttribute(brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK, VNNI>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   });
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(VNNI ? TC2_THREADS_VNNI : NUM_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attrs[3];
@@ -493,11 +559,11 @@ bool launch_cfg_pair(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcPar
   if (SPLITK == 3) {
     // the k-slices of a tile meet at an arrival counter in global memory: all CTAs must be resident. The launcher keeps
     // such grids within one wave; the cooperative launch makes that a guarantee (other streams may hold SMs)
-    if (!prepare_resident_launch(reinterpret_cast<const void *>(brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK>), &cfg, attrs,
+    if (!prepare_resident_launch(reinterpret_cast<const void *>(brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK, VNNI>), &cfg, attrs,
                                  /*only_if_concurrent=*/true))
       return false;
   }
-  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK>, tmA, tmB, p));
+  TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, brgemm_tc2_kernel<BLOCK_N, STAGES, SPLITK, VNNI>, tmA, tmB, p));
   return true;
 }
 
@@ -632,6 +698,19 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
     if (split != 2 && split != 4) split = 1;
     if (mc == 1 && split > 2) split = 2;
   }
+  // VNNI-2 packed B (g.B points at [batch][k/2][ldb][2], `d` is the flat twin of the caller's descriptor): only the CTA-pair
+  // kernel converts it in shared memory; whole k-blocks of k pairs, raw rows on 16-byte boundaries. Otherwise the
+  // caller un-interleaves B into a scratch buffer first.
+  // The rewrite adds 32 KiB of shared-memory traffic to the 80 KiB a k-block already moves and shared memory is this
+  // kernel's bound (measured on 1024^3 x 16: 980 instead of 575 clocks per k-block, 43.7 us against 30.4 us flat), so a long
+  // reduction is cheaper with ONE un-interleave pass through HBM in front (43.5 us); the in-kernel path is for the short
+  // ones, where that extra launch is what costs (TPP_XSMM_VNNI_NATIVE=1: always, =0: never).
+  const bool vnni = g.b_vnni2;
+  if (vnni) {
+    static const int native_mode = [] { const char *e = getenv("TPP_XSMM_VNNI_NATIVE"); return e ? atoi(e) : -1; }();
+    if (mc != 2 || (d.k % BLOCK_K) != 0 || (d.ldb % 4) != 0 || (d.stride_b % 8) != 0 || (d.n % 8) != 0) return false;
+    if (native_mode == 0 || (native_mode < 0 && batch * k_iters / split > 24)) return false;
+  }
   // A tensor map is a pure function of (descriptor, operand address, batch, box): cache the encoded
   // pair per thread so steady-state invokes (the same memrefs over and over) skip the driver call.
   struct MapCacheEntry {
@@ -646,14 +725,23 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
   thread_local MapCacheEntry t_maps[kMapCache];
   const uintptr_t ha = reinterpret_cast<uintptr_t>(g.A), hb = reinterpret_cast<uintptr_t>(g.B);
   MapCacheEntry &e = t_maps[((ha >> 7) ^ (ha >> 19) ^ (hb >> 9) ^ (hb >> 23) ^ (uintptr_t)batch) & (kMapCache - 1)];
-  if (e.desc != &d || e.A != g.A || e.B != g.B || e.batch != batch || e.mc != mc) {
+  const int map_kind = vnni ? 3 : mc;
+  if (e.desc != &d || e.A != g.A || e.B != g.B || e.batch != batch || e.mc != map_kind) {
     const uint64_t nb = batch > 0 ? (uint64_t)batch : 1;
-    e.desc = &d; e.A = g.A; e.B = g.B; e.batch = batch; e.mc = mc;
+    e.desc = &d; e.A = g.A; e.B = g.B; e.batch = batch; e.mc = map_kind;
     // with multicast every CTA fetches one 64-row half of the A stage
     e.ok = encode_map(&e.tmA, g.A, (uint64_t)d.k, (uint64_t)d.m, nb, (uint64_t)d.lda, (uint64_t)d.stride_a, BLOCK_K,
-                      mc == 1 ? BLOCK_M / 2 : BLOCK_M) &&
-           encode_map(&e.tmB, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, 64,
-                      BLOCK_K);
+                      mc == 1 ? BLOCK_M / 2 : BLOCK_M);
+    if (e.ok && vnni) {
+      // raw VNNI-2 rows: (element of the [n][2] row | k pair | batch element); a box is 64 columns x 2 = 256 bytes per k
+      // pair, 32 k pairs; no swizzle (the converter warps produce the swizzled tile)
+      const uint64_t dims[3] = {2 * (uint64_t)d.n, (uint64_t)d.k / 2, nb};
+      const uint64_t str[2] = {2 * (uint64_t)d.ldb, nb > 1 ? (uint64_t)d.stride_b : 2 * (uint64_t)d.ldb};
+      const uint32_t box[3] = {128, BLOCK_K / 2, 1};
+      e.ok = encode_map_nd(&e.tmB, g.B, 3, dims, str, box, 0);
+    } else if (e.ok) {
+      e.ok = encode_map(&e.tmB, g.B, (uint64_t)d.n, (uint64_t)d.k, nb, (uint64_t)d.ldb, (uint64_t)d.stride_b, 64, BLOCK_K);
+    }
   }
   if (!e.ok) return false;
   const CUtensorMap &tmA = e.tmA, &tmB = e.tmB;
@@ -734,20 +822,27 @@ bool launch_brgemm_tc(const KernelDesc &d, const GemmArgs &g, cudaStream_t strea
     g_trace_ctas[slot] = n_ctas;
     p.trace = trace_buf + (size_t)slot * kTraceCtas * TRACE_SLOTS;
   }
-  set_last_name("brgemm_tc_bf16_%dx%dx64%s%s", mc == 2 ? 256 : 128, block_n,
-           split == 1 ? "" : split == 2 ? "_splitk2" : "_splitk4", mc == 1 ? "_mc2x2" : mc == 2 ? "_2cta" : "");
+  set_last_name("brgemm_tc_bf16_%dx%dx64%s%s%s", mc == 2 ? 256 : 128, block_n,
+           split == 1 ? "" : split == 2 ? "_splitk2" : "_splitk4", mc == 1 ? "_mc2x2" : mc == 2 ? "_2cta" : "",
+           vnni ? "_vnni2" : "");
   if (mc == 2) {
     bool ok = true;
-    if (split > 1) ok = block_n == 256 ? launch_cfg_pair<256, 6, 3>(tmA, tmB, p, grid, stream)
-                                       : launch_cfg_pair<128, 8, 3>(tmA, tmB, p, grid, stream);
+    if (split > 1)
+      ok = vnni ? (block_n == 256 ? launch_cfg_pair<256, 6, 3, true>(tmA, tmB, p, grid, stream)
+                                  : launch_cfg_pair<128, 8, 3, true>(tmA, tmB, p, grid, stream))
+                : (block_n == 256 ? launch_cfg_pair<256, 6, 3>(tmA, tmB, p, grid, stream)
+                                  : launch_cfg_pair<128, 8, 3>(tmA, tmB, p, grid, stream));
     if (split == 1 || !ok) {   // no split, or the split grid cannot be co-resident here: one CTA pair per tile, whole reduction
       p.split_k = 1;
       grid.z = 1;
       p.ws = nullptr;
       p.flags = nullptr;
-      if (block_n == 256) launch_cfg_pair<256, 6, 0>(tmA, tmB, p, grid, stream);
+      if (vnni) {
+        if (block_n == 256) launch_cfg_pair<256, 6, 0, true>(tmA, tmB, p, grid, stream);
+        else launch_cfg_pair<128, 8, 0, true>(tmA, tmB, p, grid, stream);
+      } else if (block_n == 256) launch_cfg_pair<256, 6, 0>(tmA, tmB, p, grid, stream);
       else launch_cfg_pair<128, 8, 0>(tmA, tmB, p, grid, stream);
-      if (!ok) set_last_name("brgemm_tc_bf16_256x%dx64_2cta", block_n);
+      if (!ok) set_last_name("brgemm_tc_bf16_256x%dx64_2cta%s", block_n, vnni ? "_vnni2" : "");
     }
   } else
   switch (block_n) {

@@ -70,6 +70,9 @@ struct GemmArgs {
   // in plain stream order waits for EVERYTHING before it, so at most one window of kernels can ever be co-resident and
   // the "not written by the last kPdlWindow kernels" test behind b_independent / a_independent is a proof, not a hope
   bool pdl = true;
+  // B is VNNI-2 packed ([batch][k/2][ldb][2]) although the descriptor passed to launch_brgemm_tc is the flat twin: the
+  // CTA-pair kernel converts it in shared memory (launch_brgemm_tc returns false when it would pick another kernel)
+  bool b_vnni2 = false;
   // A LAYER regrouped from the invokes recorded during graph capture: grid_n x grid_k invokes of ONE descriptor, tile
   // (i, j) being the invoke on A + i a_step, B + j b_step, C + i c_step_n + j c_step_k, D + j d_step (steps in elements).
   // This is what the reference's tiled loop nest emits per layer (block-packed operands, one

@@ -445,6 +445,16 @@ void issue_gemm(const KernelDesc *d, const GemmArgs &g, cudaStream_t stream) {
   if (d->impl == KernelImpl::BrgemmTC) {
     launched = launch_brgemm_tc(*d, g, stream);
     if (launched) t_ctx.last_kernel = brgemm_tc_last_name();
+  } else if (d->flat_twin && d->vnni_factor == 2 && batch > 0 && (double)d->m * d->n * d->k * batch >= 2097152.0 && aligned16(g.B) &&
+             [&] {
+               // VNNI-2 B consumed as it is: the CTA-pair kernel rewrites the raw rows in shared memory (short reductions;
+               // launch_brgemm_tc declines the long ones)
+               GemmArgs gv = g;
+               gv.b_vnni2 = true;
+               return launch_brgemm_tc(*d->flat_twin, gv, stream);
+             }()) {
+    launched = true;
+    t_ctx.last_kernel = brgemm_tc_last_name();
   } else if (d->flat_twin && batch > 0 && (double)d->m * d->n * d->k * batch >= 2097152.0 &&
              (batch == 1 || d->stride_b == d->k * d->ldb) && aligned16(g.B)) {
     // VNNI-B -> flat B in a scratch buffer (batches are contiguous: one tall [batch*k][ldb] un-interleave). The scratch
@@ -643,16 +653,20 @@ void flush_pending_impl() {
   auto pair_only = [&](size_t l) {
     return (args[l].is_grid() || descs[l]->impl != KernelImpl::BrgemmTC) && brgemm_layer_chainable(*descs[l], args[l]);
   };
+  // a single layer (no chain) goes to the pair-per-chain kernel only when it is a grid of tile invokes (the alternative is
+  // one launch per tile); a plain invoke with VNNI-2 weights has the per-layer kernels (issue_gemm: the CTA-pair GEMM
+  // converts VNNI-2 B in shared memory), which spread one big layer over the whole machine
+  auto single_pair = [&](size_t l) { return args[l].is_grid() && brgemm_layer_chainable(*descs[l], args[l]); };
   for (size_t sidx = 0; sidx < seg_first.size();) {
     // a run of consecutive segments of the same kind: chains, or single layers that need the pair kernel
     const bool chains = seg_len[sidx] > 1;
-    if (!chains && !pair_only((size_t)seg_first[sidx])) {
+    if (!chains && !single_pair((size_t)seg_first[sidx])) {
       issue_layer((size_t)seg_first[sidx]);
       ++sidx;
       continue;
     }
     size_t run = sidx;
-    while (run < seg_first.size() && (chains ? seg_len[run] > 1 : (seg_len[run] == 1 && pair_only((size_t)seg_first[run]))))
+    while (run < seg_first.size() && (chains ? seg_len[run] > 1 : (seg_len[run] == 1 && single_pair((size_t)seg_first[run]))))
       ++run;
     bool force = !chains;
     for (size_t q = sidx; q < run && !force; ++q)
