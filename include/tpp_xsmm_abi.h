@@ -270,6 +270,18 @@ TPP_XSMM_EXPORT void xsmm_cuda_graph_destroy(int64_t graph);
  * stream). Turning it off flushes. */
 TPP_XSMM_EXPORT void xsmm_cuda_set_lazy(int64_t on);
 
+/* Function-local temporaries. The reference's generated MLP keeps every layer's output except the last in a buffer that
+ * lives and dies inside the kernel function (tools/mlir-gen/MLIRGen.cpp:255-261, 821-827: tensor.empty + fill inside
+ * `entry`, memref.alloc / dealloc after bufferisation): nobody outside the function can observe it. A caller that marks such
+ * a buffer (device pointer, or a host range registered with xsmm_cuda_register_host; the patched runner does it next to
+ * the allocation) allows the runtime to treat its CONTENTS as dead once the last invoke that
+ * reads them inside a fused launch has done so: the pair-per-chain kernel then drops those cache lines from L2
+ * (discard.global.L2) instead of letting them be written back to HBM. Results of the invokes that consume the buffer are
+ * unchanged; what a later read of the buffer itself returns is unspecified. Unmark before the memory is freed or reused
+ * as something observable. Marks only take effect in launches captured / queued after the call. */
+TPP_XSMM_EXPORT void xsmm_cuda_mark_temporary(void *ptr, int64_t bytes);
+TPP_XSMM_EXPORT void xsmm_cuda_unmark_temporary(void *ptr);
+
 /* Introspection used by the tests and by bench.py's "gpu_launches". */
 TPP_XSMM_EXPORT int64_t xsmm_cuda_launch_count(void);
 /* Name of the kernel variant the last invoke on this thread launched

@@ -694,6 +694,48 @@ def test_reference_default_stream_many_sets_one_launch(vnni):
     g.destroy()
 
 
+@pytest.mark.parametrize("tiles,vnni", [((256, 1024, 1024), False), ((32, 32, 32), True), ((64, 64, 64), False)])
+def test_marked_temporaries_do_not_change_results(tiles, vnni):
+    """xsmm_cuda_mark_temporary on the intermediate activations (function-local buffers of the reference's generated
+    kernel): the pair-per-chain kernel drops them from L2 after the next layer has consumed them. The final outputs must be
+    bit-identical to the unmarked run and match the oracle; replays too (a discard issued before the last read would
+    show up here)."""
+    from tpp_mlir_b200 import xsmm
+
+    n_sets = 14
+    cfg, replays, wants = _blocked_mlp(tiles, vnni, layers=(1024, 1024, 1024, 1024), n_sets=n_sets, seed=31)
+    with xsmm.graph_capture() as g0:
+        for r in replays:
+            r.forward()
+    assert "pair256x256" in xsmm.last_kernel(), xsmm.last_kernel()
+    g0.launch()
+    xsmm.sync()
+    plain = [_blocked_out(cfg, r).copy() for r in replays]
+    for r in replays:
+        for a in r.acts[1:-1]:
+            xsmm.mark_temporary(a)
+    try:
+        with xsmm.graph_capture() as g1:
+            for r in replays:
+                r.forward()
+        for rep in range(3):
+            for r in replays:
+                for a in r.acts[1:]:
+                    a.fill_(0x7FC0)
+            g1.launch()
+            xsmm.sync()
+            for r, want, p in zip(replays, wants, plain):
+                got = _blocked_out(cfg, r)
+                assert np.array_equal(got, p), "marked temporaries changed the result"
+                assert_close(BF16, got, want)
+        g1.destroy()
+    finally:
+        for r in replays:
+            for a in r.acts[1:-1]:
+                xsmm.unmark_temporary(a)
+    g0.destroy()
+
+
 def test_regrouping_keeps_irregular_invoke_streams_as_they_are():
     """Tile invokes that do NOT walk a regular grid (here: the column blocks of a layer visited in a shuffled order) are
     launched one by one, in program order - same answer, no fused kernel."""

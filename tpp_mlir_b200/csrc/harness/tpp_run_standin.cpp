@@ -123,6 +123,9 @@ int main(int argc, char **argv) {
     for (int64_t l = 0; l <= L; ++l) {
       xsmm_cuda_register_host(act[l], batch * layers[l] * 2, 1);
       dact[l] = static_cast<uint16_t *>(xsmm_cuda_device_ptr(act[l]));
+      // the outputs of all layers but the last are buffers the generated kernel allocates and frees itself
+      // (patches/0006 marks them)
+      if (l > 0 && l < L) xsmm_cuda_mark_temporary(dact[l], batch * layers[l] * 2);
     }
   }
 

@@ -54,6 +54,9 @@ void launch_tile_batch(const TilePtrs *dev_tiles, int64_t num_tiles, bool transp
 bool launch_tile_grid(const void *in0, void *out0, int64_t J, int64_t I, int64_t in_inner, int64_t in_outer, int64_t out_inner,
                       int64_t out_outer, int64_t m, int64_t n, int64_t ldi, int64_t ldo, int es, cudaStream_t stream);
 
+// [p, p + bytes) lies inside a range the caller marked with xsmm_cuda_mark_temporary (runtime.cu)
+bool range_is_temporary(const void *p, size_t bytes);
+
 struct GemmArgs {
   const void *A = nullptr;
   const void *B = nullptr;

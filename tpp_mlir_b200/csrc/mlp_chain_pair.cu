@@ -78,6 +78,14 @@ struct alignas(128) PcLayer {
   int32_t x64;              // k == 32
   int32_t w64;              // n == 32, flat weights
   int32_t c64;              // n == 32
+  // The layer's OUTPUT is a function-local temporary (xsmm_cuda_mark_temporary) whose only reader is the next layer of
+  // this chain: once a CTA has finished that layer, the 128 output rows it wrote and re-read are dead and it drops their
+  // cache lines from L2 (discard.global.L2) - they never travel to HBM. A CTA's rows of the output are d_nrb x d_gk
+  // contiguous chunks of d_lines 128-byte lines (block-packed outputs: one chunk per (row block, column block); flat:
+  // one chunk); 0 lines: not a temporary / not expressible, nothing is discarded.
+  const char *d_base;       // output base address (bytes)
+  int64_t d_step_n, d_step_k, d_row_bytes;   // bytes between row blocks / column blocks / rows inside a block
+  int32_t d_lines, d_nrb, d_gk;
 };
 // A work item: rows [row0, row0 + 256) of one chain. In a launch with FEW row blocks (a lone forward pass) the output
 // tiles of every layer are dealt out to `nslices` pairs instead - pair `slice` takes tiles slice, slice + nslices, ... - so
@@ -400,6 +408,20 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
           ptx::mbar_wait(acc_full + 8 * buf, (t >> 1) & 1);
           ptx::tc_fence_after_sync();
           if (t < 12 && issuer) pc_stamp(cp, 4 * t + 2);
+          if (l > 0 && j + it.nslices >= n_tiles && it.nslices == 1 && L[-1].d_lines > 0) {
+            // this layer's last accumulator is complete: every load of my rows of the previous layer's output has been
+            // consumed, nobody else reads them (CTA r only ever reads the rows it wrote) and the caller declared the
+            // buffer a temporary - drop the lines from L2 before they are written back
+            const PcLayer *P = L - 1;
+            const int32_t lines = P->d_lines, total = lines * P->d_nrb * P->d_gk;
+            const int32_t pm = P->m, rb0 = row0 / pm, rin0 = pm >= BLOCK_M ? row0 - rb0 * pm : 0;
+            const char *base0 = P->d_base + (int64_t)rb0 * P->d_step_n + (int64_t)rin0 * P->d_row_bytes;
+            for (int32_t idx = r_in; idx < total; idx += BLOCK_M) {
+              const int32_t chunk = idx / lines, li = idx - chunk * lines, ci = chunk / P->d_gk, cj = chunk - ci * P->d_gk;
+              const char *a = base0 + (int64_t)ci * P->d_step_n + (int64_t)cj * P->d_step_k + (int64_t)li * 128;
+              asm volatile("discard.global.L2 [%0], 128;" ::"l"(a) : "memory");
+            }
+          }
           const uint32_t bias_s = smem_bias + buf * PC_BIAS_BYTES;
 #pragma unroll 1
           for (int c = 0; c < PC_BLOCK_N; c += PC_OUT_COLS, ++g) {
@@ -781,6 +803,27 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
       pl.n_tiles = (int32_t)((int64_t)g.grid_k * d.n / PC_BLOCK_N);
       pl.relu = (d.op == OpClass::FusedBrgemm && d.unary_kind == 5) ? 1 : 0;
       pl.vnni = vnni ? 1 : 0;
+      // a temporary the next layer of the chain consumes: geometry of one CTA's 128 rows as contiguous chunks of lines
+      pl.d_lines = 0;
+      static const bool discard_off = [] { const char *e = getenv("TPP_XSMM_DISCARD"); return e && e[0] == '0'; }();
+      if (!discard_off && l + 1 < len[c] && nslices == 1) {
+        const LayerRanges lr = layer_ranges(d, g);
+        const int64_t rows_blk = std::min<int64_t>(d.m, BLOCK_M);          // my rows inside one row block
+        const int64_t chunk_bytes = rows_blk * d.n * 2;                      // contiguous when the block's rows are packed
+        const bool packed = d.ldc == d.n;
+        const int64_t step_n = (g.grid_n > 1 ? g.c_step_n : 0) * 2, step_k = (g.grid_k > 1 ? g.c_step_k : 0) * 2;
+        if (packed && range_is_temporary(lr.c.lo, (size_t)(lr.c.hi - lr.c.lo)) && (reinterpret_cast<uintptr_t>(g.C) % 128) == 0 &&
+            (chunk_bytes % 128) == 0 && (step_n % 128) == 0 && (step_k % 128) == 0 && ((int64_t)BLOCK_M * d.ldc * 2) % 128 == 0 &&
+            chunk_bytes / 128 < (1 << 20)) {
+          pl.d_base = static_cast<const char *>(g.C);
+          pl.d_step_n = step_n;
+          pl.d_step_k = step_k;
+          pl.d_row_bytes = d.ldc * 2;
+          pl.d_lines = (int32_t)(chunk_bytes / 128);
+          pl.d_nrb = (int32_t)(BLOCK_M / rows_blk);
+          pl.d_gk = g.grid_k;
+        }
+      }
     }
     const int64_t rows = (int64_t)args[first[c]].grid_n * descs[first[c]]->m;
     for (int64_t r = 0; r < rows; r += PC_ROWS, ++row_block) {

@@ -1386,6 +1386,45 @@ extern "C" void xsmm_cuda_sync(void) {
   if (!t_ctx.capturing) retire_lazy_allocs(true);
 }
 
+// ---- function-local temporaries (xsmm_cuda_mark_temporary) ------------------------------------------------------------
+namespace {
+std::shared_mutex g_temp_mutex;
+std::vector<std::pair<const char *, const char *>> g_temporaries;   // device byte ranges [lo, hi)
+}  // namespace
+
+namespace tpp {
+bool range_is_temporary(const void *p, size_t bytes) {
+  const char *lo = static_cast<const char *>(p), *hi = lo + bytes;
+  std::shared_lock<std::shared_mutex> lock(g_temp_mutex);
+  for (const auto &r : g_temporaries)
+    if (r.first <= lo && hi <= r.second) return true;
+  return false;
+}
+}  // namespace tpp
+
+extern "C" void xsmm_cuda_mark_temporary(void *ptr, int64_t bytes) {
+  if (!ptr || bytes <= 0) return;
+  const Resolved r = resolve(ptr, ptr);
+  if (r.where == Where::HostPlain) return;   // plain host memory never reaches a fused kernel: nothing to mark
+  std::unique_lock<std::shared_mutex> lock(g_temp_mutex);
+  for (auto &e : g_temporaries)
+    if (e.first == r.dev) { e.second = r.dev + bytes; return; }
+  g_temporaries.emplace_back(r.dev, r.dev + bytes);
+}
+
+extern "C" void xsmm_cuda_unmark_temporary(void *ptr) {
+  if (!ptr) return;
+  const Resolved r = resolve(ptr, ptr);
+  if (r.where == Where::HostPlain) return;
+  std::unique_lock<std::shared_mutex> lock(g_temp_mutex);
+  for (size_t i = 0; i < g_temporaries.size(); ++i)
+    if (g_temporaries[i].first == r.dev) {
+      g_temporaries[i] = g_temporaries.back();
+      g_temporaries.pop_back();
+      return;
+    }
+}
+
 extern "C" void xsmm_cuda_set_lazy(int64_t on) {
   if (!t_ctx.capturing && !on) flush_pending();
   t_ctx.lazy_init = true;

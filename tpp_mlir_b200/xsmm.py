@@ -74,6 +74,8 @@ EXPORTS = {
     "xsmm_cuda_graph_launch": (None, [c_int64]),
     "xsmm_cuda_graph_destroy": (None, [c_int64]),
     "xsmm_cuda_set_lazy": (None, [c_int64]),
+    "xsmm_cuda_mark_temporary": (None, [c_void_p, c_int64]),
+    "xsmm_cuda_unmark_temporary": (None, [c_void_p]),
     "xsmm_cuda_debug_fold_grid": (c_int64, [c_int64] * 11 + [c_void_p] * 5),
     "xsmm_cuda_launch_count": (c_int64, []),
     "xsmm_cuda_last_kernel": (c_char_p, []),
@@ -208,6 +210,17 @@ def set_lazy(on: bool) -> None:
     """Lazy mode of the calling thread: invokes on device operands are queued and launched fused at the next flush
     point (sync(), perf timers, update_* ...). Turning it off flushes."""
     LIB.xsmm_cuda_set_lazy(1 if on else 0)
+
+
+def mark_temporary(t) -> None:
+    """The tensor's memory is a function-local temporary of the program being replayed (see the ABI header): fused
+    launches may drop its contents after their last use instead of writing them back to HBM."""
+    nbytes = t.numel() * t.element_size() if hasattr(t, "element_size") else t.nbytes
+    LIB.xsmm_cuda_mark_temporary(_ptr(t), nbytes)
+
+
+def unmark_temporary(t) -> None:
+    LIB.xsmm_cuda_unmark_temporary(_ptr(t))
 
 
 def set_stream(stream_ptr: int | None) -> None:
