@@ -277,8 +277,10 @@ TPP_XSMM_EXPORT void xsmm_cuda_set_lazy(int64_t on);
  * the allocation) allows the runtime to treat its CONTENTS as dead once the last invoke that
  * reads them inside a fused launch has done so: the pair-per-chain kernel then drops those cache lines from L2
  * (discard.global.L2) instead of letting them be written back to HBM. Results of the invokes that consume the buffer are
- * unchanged; what a later read of the buffer itself returns is unspecified. Unmark before the memory is freed or reused
- * as something observable. Marks only take effect in launches captured / queued after the call. */
+ * unchanged; what a later read of the buffer itself returns is unspecified - so mark only buffers whose ONLY reader is the
+ * invoke that directly follows their producer (the inter-layer activations of an MLP; not a buffer that also feeds a skip
+ * connection or is read again by a later launch). Unmark before the memory is freed or reused as something observable.
+ * Marks only take effect in launches captured / queued after the call. */
 TPP_XSMM_EXPORT void xsmm_cuda_mark_temporary(void *ptr, int64_t bytes);
 TPP_XSMM_EXPORT void xsmm_cuda_unmark_temporary(void *ptr);
 
