@@ -280,7 +280,8 @@ TPP_XSMM_EXPORT void xsmm_cuda_set_lazy(int64_t on);
  * unchanged; what a later read of the buffer itself returns is unspecified - so mark only buffers whose ONLY reader is the
  * invoke that directly follows their producer (the inter-layer activations of an MLP; not a buffer that also feeds a skip
  * connection or is read again by a later launch). Unmark before the memory is freed or reused as something observable.
- * Marks only take effect in launches captured / queued after the call. */
+ * Marks only take effect in launches captured / queued after the call, and a captured graph keeps the treatment it was
+ * captured with: destroy graphs that were recorded while a buffer was marked before giving the buffer another role. */
 TPP_XSMM_EXPORT void xsmm_cuda_mark_temporary(void *ptr, int64_t bytes);
 TPP_XSMM_EXPORT void xsmm_cuda_unmark_temporary(void *ptr);
 
