@@ -13,7 +13,10 @@ A STEP is STEP_ROTATIONS (2) rotations over the operand sets: 2 x 148 = 296 forw
 one on its own copy of weights / biases / activations (1.2 GB >> 126 MiB L2, so every step streams its operands
 from HBM - the "inputs larger than L2" rule). The number of forward passes per launch does NOT depend on --steps:
 one rotation is one captured graph (xsmm_cuda_graph_*), which the runtime turns into one launch of the
-pair-per-chain kernel, so `--steps 20` times 40 full launches.
+pair-per-chain kernel, so `--steps 20` times 40 full launches. As in the reference's generated kernel, where the outputs
+of layers 1 and 2 are buffers allocated and freed inside the function (only layer 3's output is returned), those two
+buffers are registered as function-local temporaries (xsmm_cuda_mark_temporary): the kernel drops them from L2 after
+their last use; `extra.without_temporary_marks` times the same loop with ordinary buffers.
 
 Metric = the reference's own: BENCH_TOTAL_FLOPS / mean seconds / 1e9 (benchmarks/harness/controller.py:187-192),
 FLOPs counted as mlir-gen does (MLIRGen.cpp:313-334). The reference's benchmark loop itself re-runs ONE forward pass
