@@ -389,7 +389,9 @@ class MlpWorkload:
             self.num_sets = min(self.num_sets, max_sets)
         wp = [harness.pack_weight(w, bk, bc) for w in w_dev]
         if vnni:
-            wp = [harness.vnni_pack_weight(w) for w in wp]
+            # the packing factor is what libxsmm_cpuid_dot_pack_factor answers: 2, or 4 with TPP_XSMM_VNNI=4 (mlir-gen --vnni=4)
+            factor = 4 if os.environ.get("TPP_XSMM_VNNI") == "4" else 2
+            wp = [harness.vnni_pack_weight(w, factor) for w in wp]
         self.sets = []
         for s in range(self.num_sets):
             xin = harness.pack_activation(torch.roll(x_shard, s, 0), bn, bc).contiguous()

@@ -504,7 +504,7 @@ def test_mlp_replay_blocked_layouts(tiles, vnni):
     assert_close(BF16, got, ref)
 
 
-def _blocked_mlp(tiles, vnni, batch=256, layers=(1024, 1024, 1024), seed=123, n_sets=1):
+def _blocked_mlp(tiles, vnni, batch=256, layers=(1024, 1024, 1024), seed=123, n_sets=1, vnni_factor=2):
     """n_sets operand sets of a block-packed MLP (mlir-gen layouts) on the GPU plus the oracle's
     answer for each; returns (cfg, replay objects, expected outputs)."""
     import torch
@@ -525,7 +525,7 @@ def _blocked_mlp(tiles, vnni, batch=256, layers=(1024, 1024, 1024), seed=123, n_
         x = gen.fill(batch, layers[0])
         wp = [harness.pack_weight(t(W), bk, bc) for W in Ws]
         if vnni:
-            wp = [harness.vnni_pack_weight(w) for w in wp]
+            wp = [harness.vnni_pack_weight(w, vnni_factor) for w in wp]
         acts = [harness.pack_activation(t(x), bn, bc).cuda()] + [torch.zeros(batch * k, dtype=torch.int16).cuda()
                                                                    for k in layers[1:]]
         replays.append(harness.MlpReplay(cfg, [w.cuda() for w in wp], [t(b).cuda() for b in bs], acts))
@@ -627,6 +627,35 @@ def test_lone_blocked_forward_runs_on_the_pass_kernel(tiles, vnni):
         xsmm.sync()
         for a, f in zip(r.acts[1:], first):
             assert torch.equal(a, f), "a layer ran ahead of its input"
+    g.destroy()
+
+
+@pytest.mark.parametrize("tiles", [(32, 32, 32), (64, 64, 64), (256, 1024, 1024)])
+@pytest.mark.parametrize("n_sets", [1, 14])
+def test_vnni4_chains_run_on_the_fused_kernels(tiles, n_sets, monkeypatch):
+    """mlir-gen --vnni=4 (benchmarks/config/omp/mlir-bf16.json:65-125): weights packed [k/4][n][4], the factor being what
+    libxsmm_cpuid_dot_pack_factor answers (TPP_XSMM_VNNI=4). A captured chain reads flat copies of the weights that one
+    small kernel in front of the chain kernel makes (vnni_flat.cu): a lone forward pass on the pass kernel, many on the
+    pair-per-chain kernel - not one generic launch per tile."""
+    from tpp_mlir_b200 import xsmm
+
+    monkeypatch.setenv("TPP_XSMM_VNNI", "4")
+    cfg, replays, wants = _blocked_mlp(tiles, True, layers=(1024, 1024, 1024, 1024), n_sets=n_sets, seed=5 + n_sets, vnni_factor=4)
+    n0 = xsmm.launch_count()
+    with xsmm.graph_capture() as g:
+        for r in replays:
+            r.forward()
+    name = xsmm.last_kernel()
+    assert name.endswith("_vnni4") or "_vnni4_" in name, name
+    assert ("ft64x32_fullk" in name) if n_sets == 1 else ("pair256x256" in name), name
+    for rep in range(2):
+        for r in replays:
+            r.acts[-1].zero_()
+        g.launch()
+        xsmm.sync()
+        for r, want in zip(replays, wants):
+            assert_close(BF16, _blocked_out(cfg, r), want)
+    assert xsmm.launch_count() - n0 == 4, "two replays of (weight copy + chain kernel)"
     g.destroy()
 
 

@@ -21,7 +21,7 @@ OBJDIR = os.path.join(LIBDIR, "obj")
 LIBNAME = "libtpp_xsmm_runner_utils.so"
 
 SOURCES = ["runtime.cu", "eltwise.cu", "brgemm_simt.cu", "tc_host.cu", "brgemm_tc.cu", "mlp_chain.cu", "mlp_chain_ft.cu",
-           "mlp_chain_pair.cu", "tile_grid.cu"]
+           "mlp_chain_pair.cu", "tile_grid.cu", "vnni_flat.cu"]
 HEADERS = ["common.cuh", "kernels.h", "kernel_desc.h", "ptx.cuh", "tc_common.cuh", "tc_splitk.cuh", os.path.join(ROOT, "include", "tpp_xsmm_abi.h")]
 
 NVCC_FLAGS = [

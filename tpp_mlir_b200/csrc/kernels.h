@@ -111,6 +111,16 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
 // other tensor-core kernel: the alternative is one launch per tile)
 int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *args, const int *first, const int *len,
                               int num_chains, cudaStream_t stream, bool force = false);
+// flat [K][N] copies of VNNI-packed (factor 2 or 4) weights, made by one kernel in front of a chain kernel (vnni_flat.cu)
+struct VnniFlatJob {
+  const void *src;   // [gk column blocks][nb batch elements][k / v][ldb][v]
+  void *dst;         // [nb * k][gk * n]
+  int64_t ldb, stride_b, b_step;
+  int32_t n, k, nb, gk, v;
+};
+bool vnni_flat_job_ok(const KernelDesc &d, const GemmArgs &g);
+VnniFlatJob vnni_flat_job(const KernelDesc &d, const GemmArgs &g, void *dst);
+void launch_vnni_weights_to_flat(const VnniFlatJob *jobs, int count, cudaStream_t stream);
 // device tables allocated by chain launches since the last call (owned by the graph being captured)
 void brgemm_tc_take_capture_allocs(std::vector<void *> &out);
 const char *brgemm_tc_last_name();   // tile configuration of this thread's last tcgen05 launch

@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 1) mlp_chain_kernel(const __grid_
 bool brgemm_layer_chainable(const KernelDesc &d, const GemmArgs &g) {
   if (d.dtype != kBF16 || !(d.gemm_flags & 4)) return false;
   if (d.impl != KernelImpl::BrgemmTC && d.flat_twin == nullptr) return false;
-  if ((d.gemm_flags & 2048) && d.vnni_factor != 2) return false;   // the in-kernel converter rewrites VNNI-2 only
+  // VNNI-2: rewritten in shared memory by the chain kernels' converter warps; VNNI-4: through a flat copy (vnni_flat.cu)
+  if ((d.gemm_flags & 2048) && d.vnni_factor != 2 && d.vnni_factor != 4) return false;
   if (g.batch < 1) return false;
   if (!aligned16(g.A) || !aligned16(g.B) || !aligned16(g.C) || (d.ldc % 8) != 0) return false;
   if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && !(d.binary_kind == 1 && (d.binary_flags & 4))) return false;

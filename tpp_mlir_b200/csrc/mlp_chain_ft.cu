@@ -867,53 +867,11 @@ static bool chain_ftg_supported(const KernelDesc *const *descs, const GemmArgs *
 // pass kernels shared memory is the bound: measured +4.4 us per forward (18.4 against 14.0 us), every CTA of a feature
 // tile's eight row tiles redoing the same rewrite. Weights do not change inside a chain (hazard-tested), so the launcher
 // instead puts ONE small kernel in front of the chain kernel that un-interleaves (and un-blocks) every layer's weights
-// into a graph-owned scratch [K][N] - 12 MiB of L2-resident traffic per graph launch, shared by all exact repeats of the
-// chain in that launch - and the chain kernel reads the flat copy through the ordinary weight map. Every replay of the
-// graph converts again: weights the caller changed between two launches are seen. TPP_XSMM_FT_VNNI_SCRATCH=0 keeps the
-// converter warps.
-struct WFlatLayer {
-  const uint16_t *src;   // [gk column blocks][nb batch elements][k/2][ldb][2]
-  uint16_t *dst;         // [nb * k][gk * n]
-  int64_t ldb, stride_b, b_step;
-  int32_t n, k, nb, gk;
-};
-struct WFlatParams {
-  WFlatLayer layer[16];
-};
-__global__ void __launch_bounds__(256) vnni2_weights_to_flat_kernel(const __grid_constant__ WFlatParams p) {
-  const WFlatLayer L = p.layer[blockIdx.y];
-  const int64_t n_total = (int64_t)L.gk * L.n, k_total = (int64_t)L.nb * L.k;
-  const int64_t c8s = n_total / 8, units = (k_total / 2) * c8s;   // a unit: one k pair x 8 columns (32 bytes in, 2 x 16 out)
-  for (int64_t u0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; u0 < units; u0 += (int64_t)gridDim.x * blockDim.x * 2) {
-    uint4 a[2], b[2];
-    int64_t kg[2], col[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int64_t u = u0 + i;
-      if (u < units) {
-        const int64_t kp = u / c8s;
-        col[i] = (u - kp * c8s) * 8;
-        kg[i] = 2 * kp;
-        const int64_t j = col[i] / L.n, nn = col[i] - j * L.n, be = kg[i] / L.k, kk = kg[i] - be * L.k;
-        const uint4 *src = reinterpret_cast<const uint4 *>(L.src + j * L.b_step + be * L.stride_b + ((kk / 2) * L.ldb + nn) * 2);
-        a[i] = __ldg(src);
-        b[i] = __ldg(src + 1);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      if (u0 + i >= units) continue;
-      uint4 r0, r1;
-      r0.x = __byte_perm(a[i].x, a[i].y, 0x5410); r1.x = __byte_perm(a[i].x, a[i].y, 0x7632);
-      r0.y = __byte_perm(a[i].z, a[i].w, 0x5410); r1.y = __byte_perm(a[i].z, a[i].w, 0x7632);
-      r0.z = __byte_perm(b[i].x, b[i].y, 0x5410); r1.z = __byte_perm(b[i].x, b[i].y, 0x7632);
-      r0.w = __byte_perm(b[i].z, b[i].w, 0x5410); r1.w = __byte_perm(b[i].z, b[i].w, 0x7632);
-      *reinterpret_cast<uint4 *>(L.dst + kg[i] * n_total + col[i]) = r0;
-      *reinterpret_cast<uint4 *>(L.dst + (kg[i] + 1) * n_total + col[i]) = r1;
-    }
-  }
-}
-
+// into a graph-owned scratch [K][N] (vnni_flat.cu) - 12 MiB of L2-resident traffic per graph launch, shared by all exact
+// repeats of the chain in that launch - and the chain kernel reads the flat copy through the ordinary weight map. Every
+// replay of the graph converts again: weights the caller changed between two launches are seen.
+// TPP_XSMM_FT_VNNI_SCRATCH=0 keeps the converter warps. VNNI-4 weights (mlir-gen --vnni=4) always take the flat copy: the
+// converter warps rewrite factor 2 only.
 // tensor maps of a GEN pass (see the kernel's header comment); sizes in elements. w_flat: a flat [K][N] copy of the
 // layer's VNNI-2 weights (above) to read instead of g.B
 static bool encode_ftg_maps(FtPass &ps, const KernelDesc &d, const GemmArgs &g, bool vnni, const void *w_flat = nullptr) {
@@ -1096,43 +1054,34 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
   // row pitches the 16-byte path cannot take: the converter warps of the <VNNI> instantiations do the job instead.
   static const bool scratch_off = [] { const char *e = getenv("TPP_XSMM_FT_VNNI_SCRATCH"); return e && e[0] == '0'; }();
   // (one conversion kernel per graph launch pays off when the launch re-reads the weights - the exact repeats of an unrolled
-  // loop: 10.2 against 15.7 us per forward; a single forward pass per launch is faster with the converter warps, 18.4
+  // loop: 10.2 against 15.7 us per forward; a single forward per launch is faster with the converter warps, 18.4
   // against 20.5 us: the extra kernel node costs more than the rewrite it saves)
-  bool w_scratch = gen && gen_vnni && !scratch_off && sequential;
-  WFlatParams wf;
-  memset(&wf, 0, sizeof(wf));
-  int n_wf = 0;
-  std::vector<std::pair<const void *, int>> wf_index;   // (weights, layer shape id) -> entry of wf
+  const bool vnni4 = gen && gen_vnni && descs[first[0]]->vnni_factor == 4;
+  bool w_scratch = gen && gen_vnni && (vnni4 || (!scratch_off && sequential));
+  std::vector<VnniFlatJob> wf;
   if (w_scratch) {
     for (int c = 0; c < take && w_scratch; ++c)
       for (int l = 0; l < len[c] && w_scratch; ++l) {
         const KernelDesc &d = *descs[first[c] + l];
         const GemmArgs &g = args[first[c] + l];
         bool seen = false;
-        for (const auto &e : wf_index) seen = seen || e.first == g.B;
+        for (const VnniFlatJob &e : wf) seen = seen || e.src == g.B;
         if (seen) continue;
-        if (n_wf == 16 || (d.n % 8) != 0 || (d.k % 2) != 0 || (d.ldb % 4) != 0 || (d.stride_b % 8) != 0 || (g.b_step % 8) != 0) {
-          w_scratch = false;
-          break;
-        }
-        wf_index.push_back({g.B, n_wf});
-        WFlatLayer &wl = wf.layer[n_wf++];
-        wl.src = static_cast<const uint16_t *>(g.B);
-        wl.ldb = d.ldb; wl.stride_b = g.batch > 1 ? d.stride_b : 0; wl.b_step = g.grid_k > 1 ? g.b_step : 0;
-        wl.n = (int32_t)d.n; wl.k = (int32_t)d.k; wl.nb = (int32_t)g.batch; wl.gk = g.grid_k;
+        if (!vnni_flat_job_ok(d, g)) { w_scratch = false; break; }
+        wf.push_back(vnni_flat_job(d, g, nullptr));
       }
+    if (!w_scratch && vnni4) return 0;   // no converter warps for factor 4: somebody else's chain
     if (w_scratch)
-      for (int i = 0; i < n_wf; ++i) {
-        WFlatLayer &wl = wf.layer[i];
+      for (VnniFlatJob &wl : wf) {
         void *buf = nullptr;
         TPP_CUDA_CHECK(cudaMalloc(&buf, (size_t)wl.nb * wl.k * wl.gk * wl.n * sizeof(uint16_t)));
         capture_adopt(buf);   // owned by the graph being captured
-        wl.dst = static_cast<uint16_t *>(buf);
+        wl.dst = buf;
       }
   }
   auto flat_copy_of = [&](const void *B) -> const void * {
-    for (const auto &e : wf_index)
-      if (e.first == B) return wf.layer[e.second].dst;
+    for (const VnniFlatJob &e : wf)
+      if (e.src == B) return e.dst;
     return nullptr;
   };
   auto add_pass = [&](int c, int l, int slot) -> bool {
@@ -1264,18 +1213,13 @@ int launch_brgemm_chains_ft(const KernelDesc *const *descs, const GemmArgs *args
                     : split == 2 ? reinterpret_cast<const void *>(mlp_chain_fts_kernel<2>)
                                  : reinterpret_cast<const void *>(ft_kernel);
   if (!prepare_resident_launch(kfn, &cfg, attrs)) return 0;
-  if (w_scratch && n_wf > 0) {
-    // 74 CTAs x 256 threads x 2 units per layer and sweep; a layer of 1024 x 1024 has 65536 units
-    vnni2_weights_to_flat_kernel<<<dim3(128, (unsigned)n_wf), 256, 0, stream>>>(wf);
-    TPP_CUDA_CHECK(cudaGetLastError());
-    note_extra_launch();
-  }
+  if (w_scratch) launch_vnni_weights_to_flat(wf.data(), (int)wf.size(), stream);
   if (split == 4) TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_fts_kernel<4>, cp));
   else if (split == 2) TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, mlp_chain_fts_kernel<2>, cp));
   else TPP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, ft_kernel, cp));
   const char *tile = split == 4 ? "ft64x128_splitk4" : split == 2 ? "ft64x64_splitk2" : "ft64x32_fullk";
   char tag[24] = "";
-  if (gen) snprintf(tag, sizeof(tag), "%s%s", args[first[0]].is_grid() ? "_blocked" : "", gen_vnni ? "_vnni2" : "");
+  if (gen) snprintf(tag, sizeof(tag), "%s%s", args[first[0]].is_grid() ? "_blocked" : "", vnni4 ? "_vnni4" : gen_vnni ? "_vnni2" : "");
   if (take == 1) set_last_name("mlp_chain_bf16_%dlayers_%s%s", len[0], tile, tag);
   else set_last_name("mlp_chain_bf16_%dx%dlayers_%s%s%s", take, len[0], tile, tag, sequential ? "_seq" : "");
   return take;

@@ -78,6 +78,7 @@ struct alignas(128) PcLayer {
   int32_t x64;              // k == 32
   int32_t w64;              // n == 32, flat weights
   int32_t c64;              // n == 32
+  int32_t w_flat;           // tmW describes a flat [K][N] copy of the weights (vnni_flat.cu): coordinates (column, 0, k, 0)
   // The layer's OUTPUT is a function-local temporary (xsmm_cuda_mark_temporary) whose only reader is the next layer of
   // this chain: once a CTA has finished that layer, the 128 output rows it wrote and re-read are dead and it drops their
   // cache lines from L2 (discard.global.L2) - they never travel to HBM. A CTA's rows of the output are d_nrb x d_gk
@@ -200,7 +201,9 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
           tensormap_acquire(&L->tmX);
           tensormap_acquire(&L->tmW);
           const int32_t total = L->total_iters, n_tiles = L->n_tiles;
-          const int32_t lk = L->k, k_bstep = L->k_bstep, ln = L->n;
+          const int32_t lk = L->k, k_bstep = L->k_bstep;
+          const bool w_flat = !VNNI && L->w_flat != 0;   // weights come from a flat [K][N] copy: one "block" as wide as the layer
+          const int32_t ln = w_flat ? n_tiles * PC_BLOCK_N : L->n;
           const bool x64 = NARROW && L->x64 != 0, w64 = NARROW && L->w64 != 0;
           // my 128 rows: inside one row block (m >= 128) or 128 / m whole row blocks
           const int32_t xr = L->m >= BLOCK_M ? row0 % L->m : 0, xi = row0 / L->m;
@@ -239,8 +242,9 @@ __global__ void __launch_bounds__(VNNI ? PC_THREADS_VNNI : NUM_THREADS, 1) mlp_c
 #pragma unroll
                 for (int c = 0; c < PC_W_CHUNKS; ++c) {
                   const uint32_t dst = smem_w + (s * PC_W_CHUNKS + c) * B_CHUNK_BYTES;
-                  if (hints) ptx::tma_load_4d_pair_hint(dst, &L->tmW, leader_full + 8 * s, wn[c], wj[c], c0, c1, pol_first);
-                  else ptx::tma_load_4d_pair(dst, &L->tmW, leader_full + 8 * s, wn[c], wj[c], c0, c1);
+                  const int32_t wk = w_flat ? i * BLOCK_K : c0, wb = w_flat ? 0 : c1;   // k inside the batch element, batch element
+                  if (hints) ptx::tma_load_4d_pair_hint(dst, &L->tmW, leader_full + 8 * s, wn[c], wj[c], wk, wb, pol_first);
+                  else ptx::tma_load_4d_pair(dst, &L->tmW, leader_full + 8 * s, wn[c], wj[c], wk, wb);
                   if (w64) {   // the chunk's second 32-column block: its own [64 k][32 n] sub-tile
                     if (hints) ptx::tma_load_4d_pair_hint(dst + B_CHUNK_BYTES / 2, &L->tmW, leader_full + 8 * s, 0, wj[c] + 1, c0, c1, pol_first);
                     else ptx::tma_load_4d_pair(dst + B_CHUNK_BYTES / 2, &L->tmW, leader_full + 8 * s, 0, wj[c] + 1, c0, c1);
@@ -626,7 +630,9 @@ bool chain_pair_supported(const KernelDesc *const *descs, const GemmArgs *args, 
     if (g.grid_n > 1 && ((g.a_step % 8) != 0 || (g.c_step_n % 8) != 0)) return false;
     if (g.grid_k > 1 && ((g.b_step % 8) != 0 || (g.c_step_k % 8) != 0)) return false;
     if (d.k < BLOCK_K && g.batch % (BLOCK_K / d.k) != 0) return false;  // a k-block is a whole number of batch elements
-    if (vnni && ((d.k % 2) != 0 || (d.k < BLOCK_K ? false : (d.k % BLOCK_K) != 0))) return false;
+    if (vnni && d.vnni_factor != d0.vnni_factor) return false;
+    if (vnni && d.vnni_factor == 2 && ((d.k % 2) != 0 || (d.k < BLOCK_K ? false : (d.k % BLOCK_K) != 0))) return false;
+    if (vnni && d.vnni_factor != 2 && !vnni_flat_job_ok(d, g)) return false;   // VNNI-4: through a flat copy
     if (d.op == OpClass::FusedBrgemm && d.binary_kind != 0 && g.D == nullptr) return false;
     if (g.D && !aligned16(g.D)) return false;   // the epilogue reads the bias in 16-byte words
   }
@@ -635,7 +641,7 @@ bool chain_pair_supported(const KernelDesc *const *descs, const GemmArgs *args, 
 }
 
 // dims / strides / box of the three operand maps (see the comment above PcLayer); sizes in elements
-bool encode_layer_maps(PcLayer &pl, const KernelDesc &d, const GemmArgs &g, bool vnni) {
+bool encode_layer_maps(PcLayer &pl, const KernelDesc &d, const GemmArgs &g, bool vnni, const void *w_flat = nullptr) {
   const uint64_t nb = (uint64_t)g.batch, gn = (uint64_t)g.grid_n, gk = (uint64_t)g.grid_k;
   // a dimension of size 1 may carry any legal stride
   const uint64_t sa = nb > 1 ? (uint64_t)d.stride_a : (uint64_t)d.lda, sb = nb > 1 ? (uint64_t)d.stride_b : (uint64_t)d.ldb;
@@ -645,14 +651,21 @@ bool encode_layer_maps(PcLayer &pl, const KernelDesc &d, const GemmArgs &g, bool
                  nx = (uint32_t)std::min<int64_t>(d.n, 64);
   const bool k32 = kx == 32, n32 = nx == 32;   // 64-byte inner extents: SWIZZLE_64B, one block per box along that dimension
   pl.x64 = k32 ? 1 : 0;
-  pl.w64 = (n32 && !vnni) ? 1 : 0;
+  pl.w64 = (n32 && !vnni && !w_flat) ? 1 : 0;
   pl.c64 = n32 ? 1 : 0;
+  pl.w_flat = w_flat ? 1 : 0;
   {
     const uint64_t dims[4] = {(uint64_t)d.k, nb, (uint64_t)d.m, gn}, str[3] = {sa, (uint64_t)d.lda, a_step};
     const uint32_t box[4] = {kx, k32 ? 1u : BLOCK_K / kx, rx, BLOCK_M / rx};
     if (!encode_map_nd(&pl.tmX, g.A, 4, dims, str, box, k32 ? 64 : 128)) return false;
   }
-  if (vnni) {
+  if (w_flat) {
+    // the flat copy: one [K][N] matrix, the ordinary 64-column x 64-k box
+    const uint64_t n_total = gk * (uint64_t)d.n, k_total = nb * (uint64_t)d.k;
+    const uint64_t dims[4] = {n_total, 1, k_total, 1}, str[3] = {n_total, n_total, n_total};
+    const uint32_t box[4] = {64, 1, BLOCK_K, 1};
+    if (!encode_map_nd(&pl.tmW, w_flat, 4, dims, str, box, 128)) return false;
+  } else if (vnni) {
     // raw VNNI-2 rows: (element of the [n][2] row | column block | k pair | batch element); a box is 64 columns x 2 =
     // 256 contiguous bytes per k pair (two column blocks of 32), 32 k pairs (two batch elements when k == 32); no swizzle
     const uint32_t ex = 2 * nx, kpx = kx / 2;
@@ -774,6 +787,21 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   bool grids = false;
   static const bool force_narrow = [] { const char *e = getenv("TPP_XSMM_PAIR_NARROW"); return e && e[0] == '1'; }();   // A/B
   bool narrow = force_narrow;
+  // VNNI-4 weights (mlir-gen --vnni=4): the converter warps rewrite factor 2 only, so every distinct weight buffer of the
+  // launch gets a flat [K][N] copy made by one kernel in front of this one (vnni_flat.cu; graph-owned scratch, rebuilt by
+  // every replay) and the layers read the copies with the flat-weight instantiation
+  const bool w_flat = vnni && descs[first[0]]->vnni_factor != 2;
+  std::vector<VnniFlatJob> wf;
+  auto flat_copy_of = [&](const KernelDesc &d, const GemmArgs &g) -> const void * {
+    for (const VnniFlatJob &e : wf)
+      if (e.src == g.B) return e.dst;
+    void *buf = nullptr;
+    TPP_CUDA_CHECK(cudaMalloc(&buf, (size_t)g.batch * d.k * g.grid_k * d.n * sizeof(uint16_t)));
+    capture_adopt(buf);
+    wf.push_back(vnni_flat_job(d, g, buf));
+    return buf;
+  };
+  if (w_flat) vnni = false;   // kernel instantiation: flat weights
   for (int c = 0; c < take; ++c) {
     const int32_t layer0 = (int32_t)nl;
     for (int l = 0; l < len[c]; ++l) {
@@ -781,7 +809,7 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
       const GemmArgs &g = args[first[c] + l];
       PcLayer &pl = hl[nl++];
       memset(&pl, 0, sizeof(pl));
-      if (!encode_layer_maps(pl, d, g, vnni)) return 0;
+      if (!encode_layer_maps(pl, d, g, vnni, w_flat ? flat_copy_of(d, g) : nullptr)) return 0;
       static const bool dbg = getenv("TPP_XSMM_DEBUG") != nullptr;
       if (dbg)
         fprintf(stderr, "pair-chain layer: chain %d layer %d tile m=%lld n=%lld k=%lld batch=%lld lda=%lld ldb=%lld ldc=%lld sa=%lld "
@@ -875,6 +903,7 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   const int rounds = (int)((items + max_pairs - 1) / max_pairs);
   const int pairs = (int)((items + rounds - 1) / rounds);
   g_pc_trace_ctas = 2 * pairs;
+  if (w_flat) launch_vnni_weights_to_flat(wf.data(), (int)wf.size(), stream);
   const bool launched = vnni && narrow ? launch_pair_kernel<true, true>(cp, pairs, stream)
                         : vnni         ? launch_pair_kernel<true, false>(cp, pairs, stream)
                         : narrow       ? launch_pair_kernel<false, true>(cp, pairs, stream)
@@ -883,7 +912,7 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   char split_tag[16] = "";
   if (nslices > 1) snprintf(split_tag, sizeof(split_tag), "_split%d", nslices);
   set_last_name("mlp_chain_bf16_%dx%dlayers_pair256x256%s%s%s", (int)row_blocks, len[0], grids ? "_blocked" : "",
-                vnni ? "_vnni2" : "", split_tag);
+                vnni ? "_vnni2" : w_flat ? "_vnni4" : "", split_tag);
   return take;
 }
 

@@ -199,10 +199,10 @@ def pack_weight(w, bk, bc):
     return w.reshape(c // bc, bc, k // bk, bk).permute(2, 0, 1, 3).contiguous()
 
 
-def vnni_pack_weight(wp):
-    """[K/bk][C/bc][bc][bk] -> [K/bk][C/bc][bc/2][bk][2]"""
+def vnni_pack_weight(wp, factor=2):
+    """[K/bk][C/bc][bc][bk] -> [K/bk][C/bc][bc/v][bk][v] (v = 2, or 4 for mlir-gen --vnni=4)"""
     kb, cb, bc, bk = wp.shape
-    return wp.reshape(kb, cb, bc // 2, 2, bk).permute(0, 1, 2, 4, 3).contiguous()
+    return wp.reshape(kb, cb, bc // factor, factor, bk).permute(0, 1, 2, 4, 3).contiguous()
 
 
 # ---- native replay loop (csrc/harness/replay.cpp) ---------------------------------------------
