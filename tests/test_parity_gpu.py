@@ -765,6 +765,56 @@ def test_marked_temporaries_do_not_change_results(tiles, vnni):
     g0.destroy()
 
 
+@pytest.mark.parametrize("dtype,batch,layers,tiles", [(F32, 256, (1024, 1024, 1024), (32, 32, 32)),
+                                                      (F32, 128, (512, 352), (32, 32, 32)),
+                                                      (BF16, 128, (1024, 4096), (64, 64, 64)),
+                                                      (BF16, 96, (256, 512, 256), (32, 32, 32))])
+def test_grids_no_fused_kernel_takes_run_as_one_generic_launch_per_layer(dtype, batch, layers, tiles):
+    """Tile invokes the tcgen05 chain kernels do not take - f32 (the reference's fp32 MLP configs,
+    benchmarks/config/base/base.json), a batch that is no multiple of 256 rows (benchmarks/config/fc: --batch=128) - are
+    still folded into layers under capture and go out as ONE launch of the generic kernel per layer (one z-slice per tile)
+    instead of one launch per tile. Checked against the oracle (f32: f64-accumulate mode, 1e-5)."""
+    import torch
+
+    from tpp_mlir_b200 import harness, xsmm
+
+    bn, bk, bc = tiles
+    cfg = harness.MlpConfig(batch=batch, layers=layers, tiles=tiles, dtype=dtype)
+    gen = oracle.TensorInit("normal", dtype, 77)
+    Ws = [gen.fill(c, k) for c, k in zip(layers[:-1], layers[1:])]
+    bs = [gen.fill(k) for k in layers[1:]]
+    x = gen.fill(batch, layers[0])
+    tdt = torch.float32 if dtype == F32 else torch.int16
+
+    def t(a):
+        return torch.from_numpy(a if dtype == F32 else a.view(np.int16))
+
+    wp = [harness.pack_weight(t(W), bk, bc).cuda() for W in Ws]
+    acts = [harness.pack_activation(t(x), bn, bc).cuda()] + [torch.zeros(batch * k, dtype=tdt).cuda() for k in layers[1:]]
+    r = harness.MlpReplay(cfg, wp, [t(b).cuda() for b in bs], acts)
+    n0 = xsmm.launch_count()
+    with xsmm.graph_capture() as g:
+        r.forward()
+    assert "_grid" in xsmm.last_kernel() and "simt" in xsmm.last_kernel(), xsmm.last_kernel()
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == len(layers) - 1, "one launch per layer"
+    oracle.set_acc_mode(1 if dtype == F32 else 0)
+    try:
+        ref = x
+        for W, b in zip(Ws, bs):
+            y = np.zeros((batch, W.shape[1]), np.float32 if dtype == F32 else np.uint16)
+            oracle.fused_brgemm(dtype, batch, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4, 0, 5, 4, 1, ref, W,
+                                y, b, 1)
+            ref = y
+    finally:
+        oracle.set_acc_mode(0)
+    got = harness.unpack_activation(acts[-1].reshape(batch // bn, layers[-1] // bk, bn, bk)).cpu().numpy()
+    got = got if dtype == F32 else got.view(np.uint16)
+    assert_close(dtype, got, ref)
+    g.destroy()
+
+
 def test_regrouping_keeps_irregular_invoke_streams_as_they_are():
     """Tile invokes that do NOT walk a regular grid (here: the column blocks of a layer visited in a shuffled order) are
     launched one by one, in program order - same answer, no fused kernel."""

@@ -10,6 +10,8 @@
 // Semantics: SURVEY.md Appendix A / runtime/Xsmm/XsmmRunnerUtils.cpp:288-457.
 // f32 accumulation over all batches and k, post-ops on the accumulator, a single
 // rounding at the store.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -24,6 +26,10 @@ struct SimtParams {
   void *C;
   int64_t m, n, k, lda, ldb, ldc, stride_a, stride_b, batch;
   int beta0, vnni_b, bin_kind, bin_mode, relu;
+  // a grid of tile BRGEMMs in one launch (GemmArgs::grid_*): blockIdx.z = tile index, tile (i, j) of the grid works on
+  // A + i a_step, B + j b_step, C + i c_step_n + j c_step_k, D + j d_step (elements); 1 x 1: a plain invoke
+  int grid_k;
+  int64_t a_step, b_step, c_step_n, c_step_k, d_step, tile0;
 };
 
 template <typename T> __device__ __forceinline__ float ldf(const T *p, int64_t i) {
@@ -34,8 +40,9 @@ template <typename T>
 __global__ void __launch_bounds__(256) brgemm_simt_kernel(SimtParams p) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
-  const T *A = static_cast<const T *>(p.A);
-  const T *B = static_cast<const T *>(p.B);
+  const int64_t tile = p.tile0 + blockIdx.z, ti = tile / p.grid_k, tj = tile - ti * p.grid_k;
+  const T *A = static_cast<const T *>(p.A) + ti * p.a_step;
+  const T *B = static_cast<const T *>(p.B) + tj * p.b_step;
   const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
   const int64_t i0 = (int64_t)blockIdx.y * BM, j0 = (int64_t)blockIdx.x * BN;
 
@@ -86,8 +93,8 @@ __global__ void __launch_bounds__(256) brgemm_simt_kernel(SimtParams p) {
     }
   }
 
-  T *C = static_cast<T *>(p.C);
-  const T *D = static_cast<const T *>(p.D);
+  T *C = static_cast<T *>(p.C) + ti * p.c_step_n + tj * p.c_step_k;
+  const T *D = p.D ? static_cast<const T *>(p.D) + tj * p.d_step : nullptr;
 #pragma unroll
   for (int r = 0; r < TM; ++r) {
     const int64_t i = i0 + ty * TM + r;
@@ -132,10 +139,21 @@ void launch_brgemm_simt(const KernelDesc &d, const GemmArgs &g, cudaStream_t str
   p.bin_kind = (d.op == OpClass::FusedBrgemm && g.D) ? (int)d.binary_kind : 0;
   p.bin_mode = bin_mode_from_flags(d.binary_flags);
   p.relu = d.op == OpClass::FusedBrgemm && d.unary_kind == 5;
-  dim3 grid((unsigned)((d.n + BN - 1) / BN), (unsigned)((d.m + BM - 1) / BM));
-  if (d.dtype == kF32) brgemm_simt_kernel<float><<<grid, 256, 0, stream>>>(p);
-  else brgemm_simt_kernel<uint16_t><<<grid, 256, 0, stream>>>(p);
-  TPP_CUDA_CHECK(cudaGetLastError());
+  // a layer folded from a regular grid of tile invokes runs as ONE launch, one z-slice per tile
+  const int64_t tiles = (int64_t)g.grid_n * g.grid_k;
+  p.grid_k = g.grid_k;
+  p.a_step = g.grid_n > 1 ? g.a_step : 0;
+  p.b_step = g.grid_k > 1 ? g.b_step : 0;
+  p.c_step_n = g.grid_n > 1 ? g.c_step_n : 0;
+  p.c_step_k = g.grid_k > 1 ? g.c_step_k : 0;
+  p.d_step = g.grid_k > 1 ? g.d_step : 0;
+  for (int64_t t0 = 0; t0 < tiles; t0 += 65535) {
+    p.tile0 = t0;
+    dim3 grid((unsigned)((d.n + BN - 1) / BN), (unsigned)((d.m + BM - 1) / BM), (unsigned)std::min<int64_t>(tiles - t0, 65535));
+    if (d.dtype == kF32) brgemm_simt_kernel<float><<<grid, 256, 0, stream>>>(p);
+    else brgemm_simt_kernel<uint16_t><<<grid, 256, 0, stream>>>(p);
+    TPP_CUDA_CHECK(cudaGetLastError());
+  }
 }
 
 } // namespace tpp

@@ -509,8 +509,8 @@ struct Layer {
   size_t first, count;   // the invokes of `list` this layer was folded from
 };
 
-inline int64_t elem_diff(const void *a, const void *b) {   // (a - b) in bf16 elements
-  return (static_cast<const char *>(a) - static_cast<const char *>(b)) / 2;
+inline int64_t elem_diff(const void *a, const void *b, int64_t es) {   // (a - b) in elements of es bytes
+  return (static_cast<const char *>(a) - static_cast<const char *>(b)) / es;
 }
 
 // the longest grid that starts at list[i]; returns the number of invokes folded (>= 1)
@@ -521,7 +521,9 @@ size_t fold_grid(const std::vector<PendingGemm> &list, size_t i, Layer *out) {
   out->first = i;
   out->count = 1;
   static const bool off = [] { const char *e = getenv("TPP_XSMM_REGROUP"); return e && e[0] == '0'; }();
-  if (off || p0.d->dtype != kBF16) return 1;
+  if (off) return 1;
+  const int64_t es = (int64_t)esize(p0.d->dtype);
+  auto elem_diff = [es](const void *a, const void *b) { return ::elem_diff(a, b, es); };
   size_t run = 1;   // invokes with the same descriptor / batch count / bias-ness
   while (i + run < list.size() && run < (1u << 20) && list[i + run].d == p0.d && list[i + run].g.batch == p0.g.batch &&
          (list[i + run].g.D != nullptr) == (p0.g.D != nullptr))
@@ -578,22 +580,22 @@ size_t fold_grid(const std::vector<PendingGemm> &list, size_t i, Layer *out) {
   if (g.grid_n > 1) ok = ok && g.c_step_n >= (g.grid_k - 1) * g.c_step_k + c_tile;
   if (g.grid_k > 1 && g.D) ok = ok && g.d_step == d.n;   // the bias slices of neighbouring column blocks are contiguous
   if (ok) {
-    const size_t es = 2;
-    (void)es;
+
     // bounding ranges: the outputs of the grid must not overlap anything the grid reads
     const char *c_lo = static_cast<const char *>(g.C);
-    const char *c_hi = c_lo + ((g.grid_n - 1) * g.c_step_n + (g.grid_k - 1) * g.c_step_k + c_tile) * 2;
+    const char *c_hi = c_lo + ((g.grid_n - 1) * g.c_step_n + (g.grid_k - 1) * g.c_step_k + c_tile) * es;
     const int64_t nb = g.batch > 0 ? g.batch : 1;
     const bool vnni = (d.gemm_flags & XSMM_GEMM_FLAG_ROWMAJOR_B_VNNI) != 0;
     const char *a_lo = static_cast<const char *>(g.A);
-    const char *a_hi = a_lo + ((g.grid_n - 1) * g.a_step + (nb - 1) * d.stride_a + (d.m - 1) * d.lda + d.k) * 2;
+    const char *a_hi = a_lo + ((g.grid_n - 1) * g.a_step + (nb - 1) * d.stride_a + (d.m - 1) * d.lda + d.k) * es;
     const char *b_lo = static_cast<const char *>(g.B);
-    const int64_t b_tile = vnni ? (nb - 1) * d.stride_b + ((d.k / 2 - 1) * d.ldb + d.n) * 2
+    const int64_t vf = d.vnni_factor > 0 ? d.vnni_factor : 2;
+    const int64_t b_tile = vnni ? (nb - 1) * d.stride_b + ((d.k / vf - 1) * d.ldb + d.n) * vf
                                 : (nb - 1) * d.stride_b + (d.k - 1) * d.ldb + d.n;
-    const char *b_hi = b_lo + ((g.grid_k - 1) * g.b_step + b_tile) * 2;
+    const char *b_hi = b_lo + ((g.grid_k - 1) * g.b_step + b_tile) * es;
     ok = !(c_lo < a_hi && a_lo < c_hi) && !(c_lo < b_hi && b_lo < c_hi);
     if (ok && g.D) {
-      const char *d_lo = static_cast<const char *>(g.D), *d_hi = d_lo + ((g.grid_k - 1) * g.d_step + d.n) * 2;
+      const char *d_lo = static_cast<const char *>(g.D), *d_hi = d_lo + ((g.grid_k - 1) * g.d_step + d.n) * es;
       ok = !(c_lo < d_hi && d_lo < c_hi);
     }
   }
@@ -645,8 +647,22 @@ void flush_pending_impl() {
     seg_len.push_back(L);
     i += L;
   }
-  // a layer no fused kernel took: its invokes are launched one by one, exactly as they were recorded
+  // a layer no fused kernel took. A grid of SMALL tile invokes (f32 tiles, shapes the tcgen05 chain kernels do not take:
+  // a batch that is no multiple of 256 rows, odd widths, ...) still goes out as ONE launch of the generic kernel, one
+  // z-slice per tile, instead of hundreds of launches of a few microseconds each; big tiles and plain invokes are launched
+  // one by one, exactly as they were recorded (the per-layer tcgen05 kernels)
+  static const bool batch_off = [] { const char *e = getenv("TPP_XSMM_GRID_SIMT"); return e && e[0] == '0'; }();
   auto issue_layer = [&](size_t l) {
+    const KernelDesc *d = descs[l];
+    const GemmArgs &g = args[l];
+    if (!batch_off && g.is_grid() && g.batch > 0 && (double)d->m * d->n * d->k * g.batch < 16777216.0) {
+      launch_brgemm_simt(*d, g, stream);
+      static thread_local char name[96];
+      snprintf(name, sizeof(name), "brgemm_simt_%s_64x64x16_grid%dx%d", d->dtype == kF32 ? "f32" : "bf16", g.grid_n, g.grid_k);
+      t_ctx.last_kernel = name;
+      count_launch();
+      return;
+    }
     for (size_t k = layers[l].first; k < layers[l].first + layers[l].count; ++k) issue_gemm(list[k].d, list[k].g, stream);
   };
   // layers only the pair-per-chain kernel can run on the tensor cores in one launch: grids of tile invokes, VNNI-2 weights
@@ -821,7 +837,9 @@ void gemm_family_invoke(const KernelDesc *d, int64_t dtype, void *pA, int64_t of
       flush_pending();                           // earlier BRGEMMs, then the zero, then this invoke
     }
   }
-  if (t_ctx.recording() && !sc.any_host && d->dtype == kBF16 && (d->impl == KernelImpl::BrgemmTC || d->flat_twin)) {
+  // (bf16 invokes the tensor-core kernels can take are fused by flush_pending(); everything else - f32, shapes only the
+  // generic kernel takes - is recorded too, so that a regular grid of such tile invokes becomes one batched launch)
+  if (t_ctx.recording() && !sc.any_host && batch > 0) {
     flush_tiles();
     t_ctx.pending.push_back({d, g});   // launched (possibly fused with its neighbours) by flush_pending()
     if (!t_ctx.capturing && t_ctx.pending.size() >= kLazyQueueMax) flush_pending();   // lazy mode: bounded queue
