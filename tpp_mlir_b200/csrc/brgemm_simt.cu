@@ -19,7 +19,8 @@ namespace tpp {
 
 namespace {
 
-constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+constexpr int BK = 16;   // k per shared-memory step; the CTA tile BM x BN is a template parameter (64 x 64, or 32 x 32 for
+                         // the 32-wide tiles of the reference's default tiling: a 64 x 64 CTA would idle on 3/4 of it)
 
 struct SimtParams {
   const void *A, *B, *D;
@@ -36,8 +37,9 @@ template <typename T> __device__ __forceinline__ float ldf(const T *p, int64_t i
   if constexpr (sizeof(T) == 4) return p[i]; else return bf16_bits_to_f32(p[i]);
 }
 
-template <typename T>
+template <typename T, int BM, int BN>
 __global__ void __launch_bounds__(256) brgemm_simt_kernel(SimtParams p) {
+  constexpr int TM = BM / 16, TN = BN / 16;          // outputs per thread (16 x 16 threads)
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int64_t tile = p.tile0 + blockIdx.z, ti = tile / p.grid_k, tj = tile - ti * p.grid_k;
@@ -56,17 +58,17 @@ __global__ void __launch_bounds__(256) brgemm_simt_kernel(SimtParams p) {
     const T *Ab = A + b * p.stride_a;
     const T *Bb = B + b * p.stride_b;
     for (int64_t k0 = 0; k0 < p.k; k0 += BK) {
-      // A tile: 64 rows x 16 k; thread loads 4 elements, k fastest (coalesced on k)
+      // A tile: BM rows x 16 k; thread loads BM / 16 elements, k fastest (coalesced on k)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < BM / 16; ++e) {
         const int lin = tid + e * 256;
         const int r = lin / BK, kk = lin % BK;
         const int64_t i = i0 + r, kq = k0 + kk;
         As[kk][r] = (i < p.m && kq < p.k) ? ldf(Ab, i * p.lda + kq) : 0.f;
       }
-      // B tile: 16 k x 64 cols; j fastest
+      // B tile: 16 k x BN cols; j fastest
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
+      for (int e = 0; e < BN / 16; ++e) {
         const int lin = tid + e * 256;
         const int kk = lin / BN, c = lin % BN;
         const int64_t j = j0 + c, kq = k0 + kk;
@@ -149,9 +151,16 @@ void launch_brgemm_simt(const KernelDesc &d, const GemmArgs &g, cudaStream_t str
   p.d_step = g.grid_k > 1 ? g.d_step : 0;
   for (int64_t t0 = 0; t0 < tiles; t0 += 65535) {
     p.tile0 = t0;
-    dim3 grid((unsigned)((d.n + BN - 1) / BN), (unsigned)((d.m + BM - 1) / BM), (unsigned)std::min<int64_t>(tiles - t0, 65535));
-    if (d.dtype == kF32) brgemm_simt_kernel<float><<<grid, 256, 0, stream>>>(p);
-    else brgemm_simt_kernel<uint16_t><<<grid, 256, 0, stream>>>(p);
+    const bool small = d.m <= 32 && d.n <= 32;
+    const int bm = small ? 32 : 64, bn = small ? 32 : 64;
+    dim3 grid((unsigned)((d.n + bn - 1) / bn), (unsigned)((d.m + bm - 1) / bm), (unsigned)std::min<int64_t>(tiles - t0, 65535));
+    if (d.dtype == kF32) {
+      if (small) brgemm_simt_kernel<float, 32, 32><<<grid, 256, 0, stream>>>(p);
+      else brgemm_simt_kernel<float, 64, 64><<<grid, 256, 0, stream>>>(p);
+    } else {
+      if (small) brgemm_simt_kernel<uint16_t, 32, 32><<<grid, 256, 0, stream>>>(p);
+      else brgemm_simt_kernel<uint16_t, 64, 64><<<grid, 256, 0, stream>>>(p);
+    }
     TPP_CUDA_CHECK(cudaGetLastError());
   }
 }

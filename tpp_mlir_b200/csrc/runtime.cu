@@ -658,7 +658,8 @@ void flush_pending_impl() {
     if (!batch_off && g.is_grid() && g.batch > 0 && (double)d->m * d->n * d->k * g.batch < 16777216.0) {
       launch_brgemm_simt(*d, g, stream);
       static thread_local char name[96];
-      snprintf(name, sizeof(name), "brgemm_simt_%s_64x64x16_grid%dx%d", d->dtype == kF32 ? "f32" : "bf16", g.grid_n, g.grid_k);
+      const int ct = (d->m <= 32 && d->n <= 32) ? 32 : 64;   // CTA tile of the generic kernel (brgemm_simt.cu)
+      snprintf(name, sizeof(name), "brgemm_simt_%s_%dx%dx16_grid%dx%d", d->dtype == kF32 ? "f32" : "bf16", ct, ct, g.grid_n, g.grid_k);
       t_ctx.last_kernel = name;
       count_launch();
       return;
