@@ -767,13 +767,14 @@ def test_marked_temporaries_do_not_change_results(tiles, vnni):
 
 @pytest.mark.parametrize("dtype,batch,layers,tiles", [(F32, 256, (1024, 1024, 1024), (32, 32, 32)),
                                                       (F32, 128, (512, 352), (32, 32, 32)),
-                                                      (BF16, 128, (1024, 4096), (64, 64, 64)),
+                                                      (BF16, 128, (1024, 2304), (64, 48, 64)),
                                                       (BF16, 96, (256, 512, 256), (32, 32, 32))])
 def test_grids_no_fused_kernel_takes_run_as_one_generic_launch_per_layer(dtype, batch, layers, tiles):
     """Tile invokes the tcgen05 chain kernels do not take - f32 (the reference's fp32 MLP configs,
     benchmarks/config/base/base.json), a batch that is no multiple of 256 rows (benchmarks/config/fc: --batch=128) - are
     still folded into layers under capture and go out as ONE launch of the generic kernel per layer (one z-slice per tile)
-    instead of one launch per tile. Checked against the oracle (f32: f64-accumulate mode, 1e-5)."""
+    instead of one launch per tile; so are 48-wide tiles (benchmarks/config/fc: --tiles=64,48,64) and batches that are no
+    multiple of 128 rows. Checked against the oracle (f32: f64-accumulate mode, 1e-5)."""
     import torch
 
     from tpp_mlir_b200 import harness, xsmm
@@ -812,6 +813,57 @@ def test_grids_no_fused_kernel_takes_run_as_one_generic_launch_per_layer(dtype, 
     got = harness.unpack_activation(acts[-1].reshape(batch // bn, layers[-1] // bk, bn, bk)).cpu().numpy()
     got = got if dtype == F32 else got.view(np.uint16)
     assert_close(dtype, got, ref)
+    g.destroy()
+
+
+@pytest.mark.parametrize("batch,layers,tiles,vnni", [(128, (1024, 4096), (64, 64, 64), False), (128, (768, 768), (32, 32, 32), True),
+                                                      (384, (1024, 1024, 1024), (64, 64, 64), False),
+                                                      (128, (768, 3072), (128, 256, 64), False)])
+def test_batches_of_128_rows_run_on_the_pair_kernel(batch, layers, tiles, vnni):
+    """benchmarks/config/fc and matmul run --batch=128 (and any batch that is an odd number of 128-row halves): the last
+    work item of the pair-per-chain kernel then has 128 rows only; its second CTA works on rows beyond the operands, which
+    TMA zero-fills on loads and drops on stores. One launch, the oracle's answer, nothing written outside the output."""
+    import torch
+
+    from tpp_mlir_b200 import harness, xsmm
+
+    bn, bk, bc = tiles
+    cfg = harness.MlpConfig(batch=batch, layers=layers, tiles=tiles, vnni=vnni)
+    gen = oracle.TensorInit("normal", BF16, 99)
+    Ws = [gen.fill(c, k) for c, k in zip(layers[:-1], layers[1:])]
+    bs = [gen.fill(k) for k in layers[1:]]
+    x = gen.fill(batch, layers[0])
+
+    def t(a):
+        return torch.from_numpy(a.view(np.int16))
+
+    wp = [harness.pack_weight(t(W), bk, bc) for W in Ws]
+    if vnni:
+        wp = [harness.vnni_pack_weight(w) for w in wp]
+    guard = 4096
+    acts = [harness.pack_activation(t(x), bn, bc).cuda()]
+    raw = []
+    for k in layers[1:]:   # outputs with a guard band behind them
+        buf = torch.full((batch * k + guard,), 0x1234, dtype=torch.int16, device="cuda")
+        raw.append(buf)
+        acts.append(buf[:batch * k])
+    r = harness.MlpReplay(cfg, [w.cuda() for w in wp], [t(b).cuda() for b in bs], acts)
+    n0 = xsmm.launch_count()
+    with xsmm.graph_capture() as g:
+        r.forward()
+    assert "pair256x256" in xsmm.last_kernel() or "ft64x32" in xsmm.last_kernel(), xsmm.last_kernel()
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == 1
+    ref = x
+    for W, b in zip(Ws, bs):
+        y = np.zeros((batch, W.shape[1]), np.uint16)
+        oracle.fused_brgemm(BF16, batch, W.shape[1], W.shape[0], W.shape[0], W.shape[1], W.shape[1], 0, 0, 4, 0, 5, 4, 1, ref, W, y, b, 1)
+        ref = y
+    got = harness.unpack_activation(acts[-1].reshape(batch // bn, layers[-1] // bk, bn, bk)).cpu().numpy().view(np.uint16)
+    assert_close(BF16, got, ref)
+    for buf, k in zip(raw, layers[1:]):
+        assert (buf[batch * k:] == 0x1234).all(), "rows beyond the batch were written"
     g.destroy()
 
 

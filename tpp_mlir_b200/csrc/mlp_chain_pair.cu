@@ -610,7 +610,9 @@ inline bool divides_or_multiple(int64_t v, int64_t unit) { return v > 0 && (v <=
 bool chain_pair_supported(const KernelDesc *const *descs, const GemmArgs *args, int L, bool *vnni_out) {
   const KernelDesc &d0 = *descs[0];
   const int64_t rows = (int64_t)args[0].grid_n * d0.m;
-  if ((rows % PC_ROWS) != 0 || rows > (1 << 30)) return false;
+  // whole 128-row halves: a last work item with 128 rows only runs with its second CTA on rows beyond the operands
+  // (TMA fills out-of-range rows with zeros on loads and drops them on stores)
+  if ((rows % BLOCK_M) != 0 || rows > (1 << 30)) return false;
   const bool vnni = (d0.gemm_flags & 2048) != 0;
   for (int l = 0; l < L; ++l) {
     const KernelDesc &d = *descs[l];
@@ -748,7 +750,7 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
       if (!indep) break;
       in_all.insert(in_all.end(), in.begin(), in.end());
       out_all.insert(out_all.end(), out.begin(), out.end());
-      items += (int64_t)args[first[c]].grid_n * descs[first[c]]->m / PC_ROWS;
+      items += ((int64_t)args[first[c]].grid_n * descs[first[c]]->m + PC_ROWS - 1) / PC_ROWS;
       layers += len[c];
       ++take;
     }
@@ -834,7 +836,7 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
       // a temporary the next layer of the chain consumes: geometry of one CTA's 128 rows as contiguous chunks of lines
       pl.d_lines = 0;
       static const bool discard_off = [] { const char *e = getenv("TPP_XSMM_DISCARD"); return e && e[0] == '0'; }();
-      if (!discard_off && l + 1 < len[c] && nslices == 1) {
+      if (!discard_off && l + 1 < len[c] && nslices == 1 && ((int64_t)g.grid_n * d.m) % PC_ROWS == 0) {
         const LayerRanges lr = layer_ranges(d, g);
         const int64_t rows_blk = std::min<int64_t>(d.m, BLOCK_M);          // my rows inside one row block
         const int64_t chunk_bytes = rows_blk * d.n * 2;                      // contiguous when the block's rows are packed
