@@ -307,6 +307,11 @@ TPP_XSMM_EXPORT int64_t xsmm_cuda_debug_fold_grid(int64_t m, int64_t n, int64_t 
                                                   int64_t stride_a, int64_t stride_b, int64_t flags, int64_t batch,
                                                   int64_t num, const int64_t *a_off, const int64_t *b_off,
                                                   const int64_t *c_off, const int64_t *d_off, int64_t *out);
+/* Debug / test hook (no device needed): does a run of `num` tile moves (byte offsets of source / destination per move)
+ * walk a regular grid, i.e. can it be one TMA-to-TMA copy (tile_grid.cu)? Returns 1 and out[0..5] = J (inner count), I,
+ * in_inner, in_outer, out_inner, out_outer (byte steps), or 0. In xsmm_cuda_debug_fold_grid, bit 40 of `flags` makes the
+ * invokes f32 (4-byte elements). */
+TPP_XSMM_EXPORT int64_t xsmm_cuda_debug_tile_grid(int64_t num, const int64_t *in_off, const int64_t *out_off, int64_t *out);
 /* ABI version of this header. */
 TPP_XSMM_EXPORT int64_t xsmm_cuda_abi_version(void);
 

@@ -203,3 +203,47 @@ def test_fold_refuses_irregular_or_hazardous_walks():
     flat = [(0, j * 64, j * 64, j * 64) for j in range(8)]
     r = _fold(256, 64, 512, 512, 512, 512, 0, 0, 4, 1, flat)
     assert (r["grid_n"], r["grid_k"], r["c_step_k"], r["folded"]) == (1, 8, 64, 8)
+
+
+def test_fold_f32_tile_invokes():
+    """fp32 tile invokes (the reference's fp32 MLP configs) fold into the same 8 x 32 grid: steps are in 4-byte elements"""
+    inv = _appendix_b_invokes(256, 1024, 1024, 32, 32, 32)
+    r = _fold(32, 32, 32, 32, 32, 32, 1024, 1024, 4 | (1 << 40), 32, inv)
+    assert r == {"grid_n": 8, "grid_k": 32, "a_step": 32 * 1024, "b_step": 32 * 1024, "c_step_n": 32 * 1024, "c_step_k": 1024,
+                 "d_step": 32, "folded": 256}
+
+
+def _tile_grid(moves):
+    import ctypes
+
+    from tpp_mlir_b200 import xsmm
+
+    num = len(moves)
+    a = (ctypes.c_int64 * num)(*[m[0] for m in moves])
+    b = (ctypes.c_int64 * num)(*[m[1] for m in moves])
+    out = (ctypes.c_int64 * 6)()
+    ok = xsmm.LIB.xsmm_cuda_debug_tile_grid(num, a, b, out)
+    return bool(ok), dict(zip(("J", "I", "in_inner", "in_outer", "out_inner", "out_outer"), out))
+
+
+def test_tile_runs_of_a_lowered_pack_are_regular_grids():
+    """tensor.pack of a 256 x 1024 bf16 matrix into 32 x 32 tiles, tile by tile (harness.PackReplay order): the run is a
+    regular 8 x 32 grid for the TMA-to-TMA copy - also with outer_dims_perm = [1, 0] and for the unpack direction; a
+    shuffled run is not."""
+    M, N, bm, bn, es = 256, 1024, 32, 32, 2
+    mb, nb = M // bm, N // bn
+    flat = lambda i, j: (i * bm * N + j * bn) * es            # noqa: E731
+    packed = lambda i, j: (i * nb + j) * bm * bn * es         # noqa: E731
+    packed_t = lambda i, j: (j * mb + i) * bm * bn * es       # noqa: E731
+    order = [(i, j) for i in range(mb) for j in range(nb)]
+    ok, g = _tile_grid([(flat(i, j), packed(i, j)) for i, j in order])
+    assert ok and g == {"J": 32, "I": 8, "in_inner": 64, "in_outer": 32 * 2048, "out_inner": 2048, "out_outer": 32 * 2048}
+    ok, g = _tile_grid([(flat(i, j), packed_t(i, j)) for i, j in order])
+    assert ok and (g["J"], g["I"], g["out_inner"], g["out_outer"]) == (32, 8, mb * 2048, 2048)
+    ok, g = _tile_grid([(packed(i, j), flat(i, j)) for i, j in order])
+    assert ok and (g["J"], g["I"], g["in_inner"], g["out_inner"]) == (32, 8, 2048, 64)
+    shuffled = [order[k] for k in (1, 0, 2, 3)] + order[4:]
+    assert not _tile_grid([(flat(i, j), packed(i, j)) for i, j in shuffled])[0]
+    # one row of tiles only: J = the whole run, I = 1
+    ok, g = _tile_grid([(flat(0, j), packed(0, j)) for j in range(nb)])
+    assert ok and (g["J"], g["I"]) == (32, 1)

@@ -1056,6 +1056,27 @@ void flush_held_zero() {
   count_launch();
 }
 
+// Does a run of tile moves walk a regular grid - tile t = i * J + j at in0 + i * in_outer + j * in_inner ->
+// out0 + i * out_outer + j * out_inner (byte steps)? J = the length of the first stretch of constant steps.
+struct TileGrid { int64_t J, I, in_inner, in_outer, out_inner, out_outer; };
+bool detect_tile_grid(const std::vector<PendingTile> &list, TileGrid *tg) {
+  const int64_t n_t = (int64_t)list.size();
+  if (n_t < 2) return false;
+  const int64_t in_inner = list[1].in - list[0].in, out_inner = list[1].out - list[0].out;
+  int64_t J = n_t;
+  for (int64_t i = 1; i < n_t; ++i)
+    if (list[i].in - list[i - 1].in != in_inner || list[i].out - list[i - 1].out != out_inner) { J = i; break; }
+  if ((n_t % J) != 0) return false;
+  const int64_t I = n_t / J;
+  const int64_t in_outer = I > 1 ? list[J].in - list[0].in : 0, out_outer = I > 1 ? list[J].out - list[0].out : 0;
+  for (int64_t t = 0; t < n_t; ++t)
+    if (list[t].in != list[0].in + (t / J) * in_outer + (t % J) * in_inner ||
+        list[t].out != list[0].out + (t / J) * out_outer + (t % J) * out_inner)
+      return false;
+  *tg = {J, I, in_inner, in_outer, out_inner, out_outer};
+  return true;
+}
+
 // Launch the tile moves recorded during graph capture: four or more become ONE batched kernel reading a device table
 // of (in, out) pointers, fewer are launched as they would have been.
 void flush_tiles() {
@@ -1087,19 +1108,10 @@ void flush_tiles() {
   // rank-4 tensor each and the copy is TMA to TMA (tile_grid.cu)
   static const bool grid_off = [] { const char *e = getenv("TPP_XSMM_TILE_GRID"); return e && e[0] == '0'; }();
   if (vec_ok && !grid_off) {
-    const int64_t n_t = (int64_t)list.size();
-    const int64_t in_inner = list[1].in - list[0].in, out_inner = list[1].out - list[0].out;
-    int64_t J = n_t;
-    for (int64_t i = 1; i < n_t; ++i)
-      if (list[i].in - list[i - 1].in != in_inner || list[i].out - list[i - 1].out != out_inner) { J = i; break; }
-    bool regular = (n_t % J) == 0;
-    const int64_t I = regular ? n_t / J : 0;
-    const int64_t in_outer = I > 1 ? list[J].in - list[0].in : 0, out_outer = I > 1 ? list[J].out - list[0].out : 0;
-    for (int64_t t = 0; regular && t < n_t; ++t)
-      regular = list[t].in == list[0].in + (t / J) * in_outer + (t % J) * in_inner &&
-                list[t].out == list[0].out + (t / J) * out_outer + (t % J) * out_inner;
-    if (regular && launch_tile_grid(list[0].in, list[0].out, J, I, in_inner, in_outer, out_inner, out_outer, d->m, d->n, d->ldi,
-                                    d->ldo, (int)es, stream)) {
+    TileGrid tg;
+    if (detect_tile_grid(list, &tg) && launch_tile_grid(list[0].in, list[0].out, tg.J, tg.I, tg.in_inner, tg.in_outer, tg.out_inner,
+                                                        tg.out_outer, d->m, d->n, d->ldi, d->ldo, (int)es, stream)) {
+      const int64_t I = tg.I, J = tg.J;
       static thread_local char gname[96];
       snprintf(gname, sizeof(gname), "%s_batch%zu_tma%lldx%lld", d->name, list.size(), (long long)I, (long long)J);
       t_ctx.last_kernel = gname;
@@ -1691,18 +1703,21 @@ extern "C" int64_t xsmm_cuda_debug_fold_grid(int64_t m, int64_t n, int64_t k, in
   KernelDesc d;
   d.op = OpClass::FusedBrgemm;
   d.impl = KernelImpl::BrgemmTC;
-  d.dtype = kBF16;
+  const bool f32 = (flags & (1ll << 40)) != 0;   // hook-only bit: fold f32 invokes (4-byte elements)
+  flags &= ~(1ll << 40);
+  d.dtype = f32 ? kF32 : kBF16;
   d.m = m; d.n = n; d.k = k; d.lda = lda; d.ldb = ldb; d.ldc = ldc; d.stride_a = stride_a; d.stride_b = stride_b;
   d.gemm_flags = flags;
   d.vnni_factor = (flags & XSMM_GEMM_FLAG_ROWMAJOR_B_VNNI) ? 2 : 0;
+  const int64_t hes = f32 ? 4 : 2;
   char *const A = reinterpret_cast<char *>(0x100000000ull), *const B = reinterpret_cast<char *>(0x200000000ull),
              *const C = reinterpret_cast<char *>(0x300000000ull), *const D = reinterpret_cast<char *>(0x400000000ull);
   std::vector<PendingGemm> list((size_t)num);
   for (int64_t t = 0; t < num; ++t) {
     list[(size_t)t].d = &d;
     GemmArgs &g = list[(size_t)t].g;
-    g.A = A + 2 * a_off[t]; g.B = B + 2 * b_off[t]; g.C = C + 2 * c_off[t];
-    g.D = d_off ? D + 2 * d_off[t] : nullptr;
+    g.A = A + hes * a_off[t]; g.B = B + hes * b_off[t]; g.C = C + hes * c_off[t];
+    g.D = d_off ? D + hes * d_off[t] : nullptr;
     g.batch = batch;
   }
   Layer L;
@@ -1710,6 +1725,15 @@ extern "C" int64_t xsmm_cuda_debug_fold_grid(int64_t m, int64_t n, int64_t k, in
   out[0] = L.g.grid_n; out[1] = L.g.grid_k; out[2] = L.g.a_step; out[3] = L.g.b_step; out[4] = L.g.c_step_n;
   out[5] = L.g.c_step_k; out[6] = L.g.d_step; out[7] = (int64_t)folded;
   return 0;
+}
+extern "C" int64_t xsmm_cuda_debug_tile_grid(int64_t num, const int64_t *in_off, const int64_t *out_off, int64_t *out) {
+  char *const in = reinterpret_cast<char *>(0x100000000ull), *const o = reinterpret_cast<char *>(0x200000000ull);
+  std::vector<PendingTile> list((size_t)num);
+  for (int64_t t = 0; t < num; ++t) list[(size_t)t] = {nullptr, in + in_off[t], o + out_off[t]};
+  TileGrid tg{};
+  const bool ok = detect_tile_grid(list, &tg);
+  out[0] = tg.J; out[1] = tg.I; out[2] = tg.in_inner; out[3] = tg.in_outer; out[4] = tg.out_inner; out[5] = tg.out_outer;
+  return ok ? 1 : 0;
 }
 extern "C" int64_t xsmm_cuda_abi_version(void) { return 1; }
 extern "C" void xsmm_cuda_debug_dump_trace(void) { brgemm_tc_dump_trace(); }

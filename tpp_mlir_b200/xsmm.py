@@ -82,6 +82,7 @@ EXPORTS = {
     "xsmm_cuda_handle_kernel": (c_char_p, [c_int64]),
     "xsmm_cuda_abi_version": (c_int64, []),
     "xsmm_cuda_debug_dump_trace": (None, []),
+    "xsmm_cuda_debug_tile_grid": (c_int64, [c_int64, c_void_p, c_void_p, c_void_p]),
     "xsmm_cuda_debug_rects_overlap": (c_int64, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_int64, c_int64]),
 }
 
