@@ -723,6 +723,34 @@ def test_reference_default_stream_many_sets_one_launch(vnni):
     g.destroy()
 
 
+@pytest.mark.parametrize("n_sets", [3, 8])
+def test_marked_temporaries_are_ignored_where_rows_are_shared(n_sets):
+    """Marks on launches that cannot honour them: 3 block-packed chains run on the pass kernel (which never discards),
+    8 on the pair kernel with column-split items (other pairs read a pair's rows: no discard). Results as unmarked."""
+    from tpp_mlir_b200 import xsmm
+
+    cfg, replays, wants = _blocked_mlp((64, 64, 64), False, layers=(1024, 1024, 1024, 1024), n_sets=n_sets, seed=41)
+    for r in replays:
+        for a in r.acts[1:-1]:
+            xsmm.mark_temporary(a)
+    try:
+        with xsmm.graph_capture() as g:
+            for r in replays:
+                r.forward()
+        name = xsmm.last_kernel()
+        assert ("ft64x32" in name) if n_sets == 3 else ("_split" in name), name
+        for rep in range(2):
+            g.launch()
+            xsmm.sync()
+            for r, want in zip(replays, wants):
+                assert_close(BF16, _blocked_out(cfg, r), want)
+        g.destroy()
+    finally:
+        for r in replays:
+            for a in r.acts[1:-1]:
+                xsmm.unmark_temporary(a)
+
+
 @pytest.mark.parametrize("tiles,vnni", [((256, 1024, 1024), False), ((32, 32, 32), True), ((64, 64, 64), False)])
 def test_marked_temporaries_do_not_change_results(tiles, vnni):
     """xsmm_cuda_mark_temporary on the intermediate activations (function-local buffers of the reference's generated
@@ -1631,6 +1659,8 @@ PACK_CASES = [
     (BF16, 256, 1024, 32, 32, (0, 1), True, False),
     (F32, 120, 200, 24, 40, (0, 1), False, False),     # rows that are no multiple of 16 bytes apart: scalar path
     (BF16, 96, 168, 12, 21, (1, 0), True, False),      # odd tile width
+    (F32, 1024, 64, 512, 32, (0, 1), False, False),    # tall tiles: several TMA boxes along the rows of one tile
+    (BF16, 64, 2048, 32, 1024, (0, 1), True, False),   # 2 KiB tile rows: wider than a TMA box, pointer-table kernel
     (BF16, 256, 512, 32, 64, (0, 1), False, True),     # tiles stored transposed (xsmm.unary transpose per tile)
     (F32, 128, 192, 32, 48, (1, 0), True, True),
 ]
