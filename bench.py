@@ -367,7 +367,8 @@ class MlpWorkload:
     native replay loop over them. Set s reads the rank's input rolled by s rows (so every set has its own answer:
     out_s = roll(out_0, s)); weights / biases are private copies per set (HBM traffic like independent requests)."""
 
-    def __init__(self, m, x_shard, w_dev, b_dev, tiles=None, min_sets=0, vnni=False, max_sets=None, temporaries=True):
+    def __init__(self, m, x_shard, w_dev, b_dev, tiles=None, min_sets=0, vnni=False, max_sets=None, temporaries=True,
+                 shared_weights=False):
         import torch
 
         from tpp_mlir_b200 import harness, xsmm
@@ -396,7 +397,9 @@ class MlpWorkload:
         for s in range(self.num_sets):
             xin = harness.pack_activation(torch.roll(x_shard, s, 0), bn, bc).contiguous()
             acts = [xin] + [torch.zeros(m * k, dtype=torch.int16, device=dev) for k in LAYERS[1:]]
-            self.sets.append((acts, [w.clone() for w in wp], [b.clone() for b in b_dev]))
+            # shared_weights: every operand set is another input batch of ONE model (parameters stay L2-resident)
+            self.sets.append((acts, wp if shared_weights else [w.clone() for w in wp],
+                              b_dev if shared_weights else [b.clone() for b in b_dev]))
             if temporaries:
                 # the outputs of all layers but the last are function-local temporaries of the reference's generated
                 # kernel (mlir-gen --kernel=const: tensor.empty + fill inside `entry`, tools/mlir-gen/MLIRGen.cpp:255-261,
@@ -575,6 +578,32 @@ def main():
                     "what": "intermediate activations are ordinary buffers (no xsmm_cuda_mark_temporary): each layer's "
                             "output is written back to HBM, 8.39 MB per forward pass instead of 7.35 MB"}
         del wl_u
+
+    # ---- the served-model form of the same workload: the 148 forward passes of a rotation are 148 input batches of ONE
+    # model (one set of weights / biases, L2-resident like in any inference server; inputs and outputs still rotate
+    # through more bytes than the L2 holds). Tensor-bound instead of HBM-bound ------------------------------------------
+    shared = None
+    if not args.no_extras:
+        wl_s = MlpWorkload(m_rank, x_shard, w_dev, b_dev, shared_weights=True, min_sets=2 * (L2_BYTES // (4 * m_rank * 1024 * 2)))
+        wl_s.rotations(3)
+        t_s = wl_s.time_rotations(10, stream, barrier, dev)
+        ms_s = shard.max_over_ranks(t_s["ms"], device=dev) / (10 * wl_s.num_sets)
+        got_s = shard.gather_rows(wl_s.output(wl_s.num_sets - 1))
+        err_s = None
+        if rank == 0:
+            want_s = np.concatenate([np.roll(oracle_forward(x_all[r * m_rank:(r + 1) * m_rank], Ws, bs), wl_s.num_sets - 1, 0)
+                                     for r in range(n_gpus)])
+            err_s = rel_err(got_s.cpu().numpy().view(np.uint16), want_s)
+            if not err_s <= 1e-2:
+                fail(f"parity failure in the shared-weights side measurement: {err_s}")
+        tf_s = flops_fwd_rank * n_gpus / (ms_s * 1e-3) / 1e12
+        shared = {"what": f"{wl_s.num_sets} forward passes of batch {m_rank} per launch on ONE set of weights / biases (a served "
+                          "model: parameters L2-resident), inputs / outputs rotating through more bytes than the L2 holds",
+                  "ms_per_forward": ms_s, "gflops": tf_s * 1e3, "kernel": xsmm.last_kernel(), "operand_sets": wl_s.num_sets,
+                  "rel_err_vs_oracle_all_ranks": err_s,
+                  "roofline": {"bound": "tensor", "achieved": tf_s / n_gpus, "peak": peaks()["bf16_tflops"],
+                               "unit": "TFLOP/s per GPU", "frac": tf_s / n_gpus / peaks()["bf16_tflops"]}}
+        del wl_s
 
     # ---- latency: what tpp-run's perf.bench loop measures - ONE forward pass re-run on ONE set of buffers -------
     LONE_UNROLL = 16
@@ -856,6 +885,7 @@ def main():
                                           "gflops": flops_fwd_rank * fwd_per_step * n_gpus / perf_s / 1e9,
                                           "what": "the same K steps between perf_start_timer / perf_stop_timer (wall clock)"},
                   "without_temporary_marks": unmarked,
+                  "shared_weights_batch256": shared,
                   "host_issue_us_per_launch": tm["issue_s"] / max(launches, 1) * 1e6,
                   "kernel": timed_kernel, "per_layer_kernel": xsmm.handle_kernel(wl.replay.handles[0]),
                   **extras},
