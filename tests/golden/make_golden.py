@@ -191,6 +191,14 @@ def main():
     t = read("test/BF16/Integration/mlp-single-layer-blocked-bf16.mlir")
     add("mlp_single_layer_blocked_bf16", "test/BF16/Integration/mlp-single-layer-blocked-bf16.mlir:11-57",
         expected=flat_checks(t))
+    t = read("test/Integration/tpp-matmul.mlir")
+    d = dense_blocks(t)
+    add("tpp_matmul_f32", "test/Integration/tpp-matmul.mlir:13-58", A=d[0], B=d[1], expected=flat_checks(t))
+    t = read("test/Integration/tpp-relu.mlir")
+    add("tpp_relu_f32", "test/Integration/tpp-relu.mlir:14-54", input=dense_blocks(t)[0], expected=flat_checks(t))
+    t = read("test/Integration/copy.mlir")
+    d = dense_blocks(t)
+    add("copy_broadcasts_f32", "test/Integration/copy.mlir:18-146", row=d[0], col=d[1], scalar=d[-1], expected_all=flat_checks(t))
     t = read("test/Integration/mlp-fp32-1layer-512.mlir")
     add("mlp_fp32_1layer_512", "test/Integration/mlp-fp32-1layer-512.mlir:8-31", raw_checks=check_lines(t))
 

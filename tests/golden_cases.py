@@ -371,6 +371,37 @@ def case_mlp_single_layer_blocked_bf16(be):
     return to_f32(BF16, C), np.array(golden()["mlp_single_layer_blocked_bf16"]["expected"], np.float32), 0.0
 
 
+def case_tpp_matmul_f32(be):
+    # test/Integration/tpp-matmul.mlir:13-58: a 4x8 . 8x4 contraction with non-trivial dense operands into a zero C
+    # -> one xsmm gemm [4,4,8,8,4,4]
+    g = golden()["tpp_matmul_f32"]
+    A, B, C = np.array(g["A"], np.float32), np.array(g["B"], np.float32), np.zeros(16, np.float32)
+    be.gemm(F32, 4, 4, 8, 8, 4, 4, 0, A, 0, B, 0, C, 0)
+    return C, np.array(g["expected"], np.float32), 6e-3   # 6 printed digits of values around 5e2
+
+
+def case_tpp_relu_f32(be):
+    # test/Integration/tpp-relu.mlir:14-54: relu of a 9x6 matrix with a block of negative entries, unary relu [9,6,6,6]
+    g = golden()["tpp_relu_f32"]
+    inp, out = np.array(g["input"], np.float32), np.zeros(54, np.float32)
+    be.unary(5, F32, 9, 6, 6, 6, 0, inp, 0, out, 0)
+    return out, np.array(g["expected"], np.float32), 1e-6
+
+
+def case_copy_broadcasts_f32(be):
+    # test/Integration/copy.mlir: identity with the three broadcast flags - a 1x6 row into 9x6 (bcast_col = 4: in[0][j]),
+    # a 6x1 column into 6x9 (bcast_row = 2: in[i][0], ldi = 1), a 1x1 scalar into 6x9 (bcast_scalar = 8). The third print
+    # of the test (23.1) is a linalg.fill, not an xsmm op.
+    g = golden()["copy_broadcasts_f32"]
+    exp = np.array(g["expected_all"], np.float32)
+    assert exp.size == 4 * 54
+    o1, o2, o3 = np.zeros(54, np.float32), np.zeros(54, np.float32), np.zeros(54, np.float32)
+    be.unary(1, F32, 9, 6, 6, 6, 4, np.array(g["row"], np.float32), 0, o1, 0)
+    be.unary(1, F32, 6, 9, 1, 9, 2, np.array(g["col"], np.float32), 0, o2, 0)
+    be.unary(1, F32, 6, 9, 1, 9, 8, np.array(g["scalar"], np.float32), 0, o3, 0)
+    return np.concatenate([o1, o2, o3]), np.concatenate([exp[:54], exp[54:108], exp[162:216]]), 1e-6
+
+
 def case_mlp_fp32_1layer_512(be):
     # test/Integration/mlp-fp32-1layer-512.mlir:8-20: relu(x[128x256] . W[256x512] + bias), all ones => 257; first row
     # printed. As the fused op of the layer (beta_0, add bcast_col_in0, relu)
