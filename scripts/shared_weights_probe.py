@@ -14,7 +14,11 @@ dev = torch.device("cuda", 0)
 to_dev = lambda a: torch.from_numpy(a.view(np.int16)).to(dev)
 stream = torch.cuda.current_stream()
 xsmm.set_stream(stream.cuda_stream)
-wl = bench.MlpWorkload(256, to_dev(x), [to_dev(W) for W in Ws], [to_dev(b) for b in bs], shared_weights=True, min_sets=126)
+# argv: [tiles "bn,bk,bc"] [vnni 0|1], e.g. "32,32,32 1" = the reference's default stream as a served model
+tiles = tuple(int(v) for v in sys.argv[1].split(",")) if len(sys.argv) > 1 else None
+vnni = len(sys.argv) > 2 and sys.argv[2] == "1"
+wl = bench.MlpWorkload(256, to_dev(x), [to_dev(W) for W in Ws], [to_dev(b) for b in bs], shared_weights=True, min_sets=126,
+                       tiles=tiles, vnni=vnni)
 wl.rotations(3)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
