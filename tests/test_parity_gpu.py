@@ -723,6 +723,26 @@ def test_reference_default_stream_many_sets_one_launch(vnni):
     g.destroy()
 
 
+def test_shared_vnni2_weights_are_converted_once_per_launch():
+    """A batch of 2048 rows (8 work items per layer chain) on the reference's default layout: every item would rewrite the
+    same VNNI-2 weights in shared memory, so the launch takes one flat copy of them instead (vnni_flat.cu) and the items
+    run the flat-weight instantiation. Same answer as the oracle; 2 launches per replay (copy + chain kernel)."""
+    from tpp_mlir_b200 import xsmm
+
+    cfg, replays, wants = _blocked_mlp((32, 32, 32), True, batch=2048, layers=(1024, 1024, 1024, 1024), n_sets=2, seed=61)
+    with xsmm.graph_capture() as g:
+        for r in replays:
+            r.forward()
+    assert "16x3layers_pair256x256_blocked_vnni2" in xsmm.last_kernel(), xsmm.last_kernel()
+    n0 = xsmm.launch_count()
+    g.launch()
+    xsmm.sync()
+    assert xsmm.launch_count() - n0 == 2, "weight copy + chain kernel"
+    for r, want in zip(replays, wants):
+        assert_close(BF16, _blocked_out(cfg, r), want)
+    g.destroy()
+
+
 @pytest.mark.parametrize("n_sets", [3, 8])
 def test_marked_temporaries_are_ignored_where_rows_are_shared(n_sets):
     """Marks on launches that cannot honour them: 3 block-packed chains run on the pass kernel (which never discards),

@@ -792,7 +792,28 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   // VNNI-4 weights (mlir-gen --vnni=4): the converter warps rewrite factor 2 only, so every distinct weight buffer of the
   // launch gets a flat [K][N] copy made by one kernel in front of this one (vnni_flat.cu; graph-owned scratch, rebuilt by
   // every replay) and the layers read the copies with the flat-weight instantiation
-  const bool w_flat = vnni && descs[first[0]]->vnni_factor != 2;
+  // VNNI-2 weights that MANY work items of the launch share (a served model: one set of weights for all the input
+  // batches of the launch, or the row blocks of a large batch) take the flat copy too: the in-place rewrite costs every
+  // item 32 KiB of shared-memory traffic per k-block (982 against 1285 TF/s with L2-resident weights), the copy costs the
+  // launch 4 bytes per weight element once
+  const int vfactor = vnni ? descs[first[0]]->vnni_factor : 0;
+  bool w_flat = vnni && vfactor != 2;
+  if (vnni && vfactor == 2) {
+    static const int min_reuse = [] { const char *e = getenv("TPP_XSMM_PAIR_FLATW_REUSE"); return e ? atoi(e) : 4; }();
+    std::vector<const void *> distinct;
+    int64_t uses = 0;
+    bool ok = min_reuse > 0;
+    for (int c = 0; c < take && ok; ++c) {
+      const int64_t blocks = ((int64_t)args[first[c]].grid_n * descs[first[c]]->m + PC_ROWS - 1) / PC_ROWS;
+      for (int l = 0; l < len[c] && ok; ++l) {
+        const GemmArgs &g = args[first[c] + l];
+        ok = vnni_flat_job_ok(*descs[first[c] + l], g);
+        uses += blocks;
+        if (std::find(distinct.begin(), distinct.end(), g.B) == distinct.end()) distinct.push_back(g.B);
+      }
+    }
+    w_flat = ok && !distinct.empty() && uses >= (int64_t)min_reuse * (int64_t)distinct.size();
+  }
   std::vector<VnniFlatJob> wf;
   auto flat_copy_of = [&](const KernelDesc &d, const GemmArgs &g) -> const void * {
     for (const VnniFlatJob &e : wf)
@@ -914,7 +935,7 @@ int launch_brgemm_chains_pair(const KernelDesc *const *descs, const GemmArgs *ar
   char split_tag[16] = "";
   if (nslices > 1) snprintf(split_tag, sizeof(split_tag), "_split%d", nslices);
   set_last_name("mlp_chain_bf16_%dx%dlayers_pair256x256%s%s%s", (int)row_blocks, len[0], grids ? "_blocked" : "",
-                vnni ? "_vnni2" : w_flat ? "_vnni4" : "", split_tag);
+                vfactor == 2 ? "_vnni2" : vfactor == 4 ? "_vnni4" : "", split_tag);
   return take;
 }
 
