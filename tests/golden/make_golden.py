@@ -202,6 +202,40 @@ def main():
     t = read("test/Integration/mlp-fp32-1layer-512.mlir")
     add("mlp_fp32_1layer_512", "test/Integration/mlp-fp32-1layer-512.mlir:8-31", raw_checks=check_lines(t))
 
+    # round 2, third batch: tests whose operands are dense literals / fills and whose printed tensors are the
+    # answers of gemm, bias + relu, binary add, relu and tile-wise pack / unpack sequences
+    t = read("test/Integration/tpp-brgemm.mlir")
+    d = dense_blocks(t)
+    add("tpp_brgemm_f32", "test/Integration/tpp-brgemm.mlir:12-57", A=d[0], B=d[1], expected=flat_checks(t))
+    t = read("test/Integration/simple-gemm.mlir")
+    add("simple_gemm_f32", "test/Integration/simple-gemm.mlir:5-11", expected=flat_checks(t))
+    t = read("test/Integration/packed-matmul.mlir")
+    d = dense_blocks(t)
+    add("packed_matmul_f32", "test/Integration/packed-matmul.mlir:25-87", A=d[0], B=d[1], bias=d[2],
+        expected=flat_checks(t))
+    t = read("test/Integration/tpp-run-xsmm-path.mlir")
+    add("xsmm_path_add_f32", "test/Integration/tpp-run-xsmm-path.mlir:8-38", expected=flat_checks(t))
+    t = read("test/Integration/matmul-tpp-with-print.mlir")
+    add("matmul_tpp_with_print_f32", "test/Integration/matmul-tpp-with-print.mlir:17-59", expected=flat_checks(t))
+    t = read("test/Integration/result-out-arg.mlir")
+    d = dense_blocks(t)
+    add("result_out_arg_f32", "test/Integration/result-out-arg.mlir:9-48", A=d[0], B=d[1], expected=flat_checks(t))
+    t = read("test/Integration/tpp-pack-unpack.mlir")
+    # this file writes some literals with parentheses: take everything between `dense<` and `> : tensor`
+    lits = [nums(m.group(1)) for m in re.finditer(r"dense\s*<\s*(.*?)>\s*:\s*tensor", t, re.S)]
+    add("tpp_pack_unpack_f32", "test/Integration/tpp-pack-unpack.mlir:3-91", pack1_in=lits[0], pack2_in=lits[1],
+        unpack1_in=lits[3], unpack2_in=lits[4], expected_all=flat_checks(t))
+    t = read("test/Integration/tiling-add.mlir")
+    d = dense_blocks(t)
+    add("tiling_add_f32", "test/Integration/tiling-add.mlir:14-140", A=d[0], B=d[1], expected=flat_checks(t))
+    t = read("test/Integration/tiling-relu.mlir")
+    add("tiling_relu_f32", "test/Integration/tiling-relu.mlir:14-105", input=dense_blocks(t)[0], expected=flat_checks(t))
+    t = read("test/BF16/Integration/mlp-single-layer-bf16.mlir")
+    m = re.search(r"%c256 = arith.constant (" + NUM + ")", t)
+    thr = re.search(r"%threshold = arith.constant (" + NUM + ")", t)
+    add("mlp_single_layer_bf16", "test/BF16/Integration/mlp-single-layer-bf16.mlir:11-55", expected_fill=float(m.group(1)),
+        threshold=float(thr.group(1)))
+
     with open(OUT, "w") as f:
         json.dump(g, f, indent=1, sort_keys=True)
     print(f"wrote {OUT}: {len(g)} vectors, {os.path.getsize(OUT)} bytes")

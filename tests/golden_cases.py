@@ -413,4 +413,135 @@ def case_mlp_fp32_1layer_512(be):
     return y[:512], np.array(row, np.float32), 0.0
 
 
+def case_tpp_brgemm_f32(be):
+    # test/Integration/tpp-brgemm.mlir:12-16: linalg.batch_reduce_matmul with ONE batch element, 1x4x8 . 1x8x4 into a zero
+    # 4x4; the IR check expects xsmm_gemm_invoke -> gemm [4,4,8,8,4,4]
+    g = golden()["tpp_brgemm_f32"]
+    A, B, C = np.array(g["A"], np.float32), np.array(g["B"], np.float32), np.zeros(16, np.float32)
+    be.gemm(F32, 4, 4, 8, 8, 4, 4, 0, A, 0, B, 0, C, 0)
+    return C, np.array(g["expected"], np.float32), 6e-3   # 5 printed digits of values around 5e2
+
+
+def case_simple_gemm_f32(be):
+    # test/Integration/simple-gemm.mlir:5-11: kernel arguments filled by tpp-run's default init (all 1.0, C included):
+    # gemm [4,4,8,8,4,4] accumulating => 9
+    A, B, C = const(F32, (4, 8)), const(F32, (8, 4)), const(F32, (16,))
+    be.gemm(F32, 4, 4, 8, 8, 4, 4, 0, A, 0, B, 0, C, 0)
+    return C, np.array(golden()["simple_gemm_f32"]["expected"], np.float32), 0.0
+
+
+def case_packed_matmul_f32(be):
+    # test/Integration/packed-matmul.mlir:25-49: C = bias broadcast over rows; C += A(4x8) . B(8x16); relu(C) in place.
+    # (1) unpacked: unary identity [4,16,16,16] (bcast_col) -> gemm [4,16,8,8,16,16] -> unary relu [4,16,16,16];
+    # (2) the third RUN line, -pack-matmul="block-factors=2,2,2": operands block-packed to [M/2][K/2][2][2],
+    #     [N/2][K/2][2][2] (relayout done here in numpy), per 2x2 output block the same three ops with a BRGEMM over the
+    #     4 K blocks: brgemm [2,2,2,2,2,2,4,4]. Both must print the same tensor.
+    g = golden()["packed_matmul_f32"]
+    A, B, bias = (np.array(g[x], np.float32) for x in ("A", "B", "bias"))
+    C = np.zeros(64, np.float32)
+    be.unary(1, F32, 4, 16, 16, 16, 4, bias, 0, C, 0)
+    be.gemm(F32, 4, 16, 8, 8, 16, 16, 0, A, 0, B, 0, C, 0)
+    be.unary(5, F32, 4, 16, 16, 16, 0, C, 0, C, 0)
+    Ap = np.ascontiguousarray(A.reshape(2, 2, 4, 2).transpose(0, 2, 1, 3)).reshape(-1)    # [i][k][ii][kk]
+    Bp = np.ascontiguousarray(B.reshape(4, 2, 8, 2).transpose(2, 0, 1, 3)).reshape(-1)    # [j][k][kk][jj]
+    Cp = np.zeros(64, np.float32)                                                         # [i][j][ii][jj]
+    for i in range(2):
+        for j in range(8):
+            off = (i * 8 + j) * 4
+            be.unary(1, F32, 2, 2, 2, 2, 4, bias, 2 * j, Cp, off)
+            be.brgemm(F32, 2, 2, 2, 2, 2, 2, 4, 4, 0, Ap, i * 16, Bp, j * 16, Cp, off, 4)
+            be.unary(5, F32, 2, 2, 2, 2, 0, Cp, off, Cp, off)
+    unpacked = Cp.reshape(2, 8, 2, 2).transpose(0, 2, 1, 3).reshape(-1)
+    exp = np.array(g["expected"], np.float32)
+    return np.concatenate([C, unpacked]), np.concatenate([exp, exp]), 6e-3   # 5 printed digits of values up to 7e2
+
+
+def case_xsmm_path_add_f32(be):
+    # test/Integration/tpp-run-xsmm-path.mlir:8-38: binary add [2,2,2,2,2] of a 1.0 fill and a 2.0 fill, written over the
+    # second operand (outs(%arg1)) => 3
+    a, b = const(F32, (4,), 1.0), const(F32, (4,), 2.0)
+    be.binary(1, F32, 2, 2, 2, 2, 2, 0, a, 0, b, 0, b, 0)
+    return b, np.array(golden()["xsmm_path_add_f32"]["expected"], np.float32), 0.0
+
+
+def case_matmul_tpp_with_print_f32(be):
+    # test/Integration/matmul-tpp-with-print.mlir:33-59: fills 1.0 / 2.0 / 0.0, then gemm [4,4,8,8,4,4]: the zero fill
+    # of C as its own xsmm zero op [4,4,4,4] followed by the accumulating gemm (the pair fuseZeroWithGemmOrBrgemm folds,
+    # ConvertLinalgToXsmm.cpp:962-993) => 16
+    A, B, C = const(F32, (4, 8), 1.0), const(F32, (8, 4), 2.0), const(F32, (16,), 7.0)
+    be.unary(2, F32, 4, 4, 4, 4, 0, C, 0, C, 0)
+    be.gemm(F32, 4, 4, 8, 8, 4, 4, 0, A, 0, B, 0, C, 0)
+    return C, np.array(golden()["matmul_tpp_with_print_f32"]["expected"], np.float32), 0.0
+
+
+def case_result_out_arg_f32(be):
+    # test/Integration/result-out-arg.mlir:9-48: out (a kernel argument, default-initialised to 1.0) is zeroed, then
+    # gemm [2,2,2,2,2,2] of two 2x2 literals => ( 4, 5 ), ( 10, 11 )
+    g = golden()["result_out_arg_f32"]
+    A, B, C = np.array(g["A"], np.float32), np.array(g["B"], np.float32), const(F32, (4,))
+    be.unary(2, F32, 2, 2, 2, 2, 0, C, 0, C, 0)
+    be.gemm(F32, 2, 2, 2, 2, 2, 2, 0, A, 0, B, 0, C, 0)
+    return C, np.array(g["expected"], np.float32), 0.0
+
+
+def case_tpp_pack_unpack_f32(be):
+    # test/Integration/tpp-pack-unpack.mlir:3-91, tile by tile as identity copies (what tensor.pack / unpack lower to,
+    # LowerPacksAndUnpacks.cpp:143-250): pack1 4x4 -> [2][2][2][2] (tiles of 2x2: identity [2,2,4,2]); pack2 1x2x2x4 ->
+    # [1][2][2][2][2] (outer_dims_perm [0,3,1,2], inner tile 2 of the last dim: per half of the last dim a 4x2 copy,
+    # identity [4,2,4,2]); unpack1 / unpack2 are the inverses. (pack3 is a CHECK-NOT in the test.)
+    g = golden()["tpp_pack_unpack_f32"]
+    outs = []
+    src, dst = np.array(g["pack1_in"], np.float32), np.zeros(16, np.float32)
+    for i in range(2):
+        for j in range(2):
+            be.unary(1, F32, 2, 2, 4, 2, 0, src, i * 8 + j * 2, dst, (i * 2 + j) * 4)
+    outs.append(dst)
+    src, dst = np.array(g["pack2_in"], np.float32), np.zeros(16, np.float32)
+    for dd in range(2):
+        be.unary(1, F32, 4, 2, 4, 2, 0, src, dd * 2, dst, dd * 8)
+    outs.append(dst)
+    src, dst = np.array(g["unpack1_in"], np.float32), np.zeros(16, np.float32)
+    for i in range(2):
+        for j in range(2):
+            be.unary(1, F32, 2, 2, 2, 4, 0, src, (i * 2 + j) * 4, dst, i * 8 + j * 2)
+    outs.append(dst)
+    src, dst = np.array(g["unpack2_in"], np.float32), np.zeros(16, np.float32)
+    for dd in range(2):
+        be.unary(1, F32, 4, 2, 2, 4, 0, src, dd * 8, dst, dd * 2)
+    outs.append(dst)
+    exp = np.array(g["expected_all"], np.float32)
+    assert exp.size == 64
+    return np.concatenate(outs), exp, 0.0
+
+
+def case_tiling_add_f32(be):
+    # test/Integration/tiling-add.mlir:14-24: B += A on 32x16 dense literals -> binary add [32,16,16,16,16], result over
+    # the second operand
+    g = golden()["tiling_add_f32"]
+    A, B = np.array(g["A"], np.float32), np.array(g["B"], np.float32)
+    be.binary(1, F32, 32, 16, 16, 16, 16, 0, A, 0, B, 0, B, 0)
+    return B, np.array(g["expected"], np.float32), 2e-5   # up to 4 printed digits, f32 sums of decimal literals
+
+
+def case_tiling_relu_f32(be):
+    # test/Integration/tiling-relu.mlir:14-24: relu in place on a 32x16 dense literal -> unary relu [32,16,16,16]
+    g = golden()["tiling_relu_f32"]
+    x = np.array(g["input"], np.float32)
+    be.unary(5, F32, 32, 16, 16, 16, 0, x, 0, x, 0)
+    return x, np.array(g["expected"], np.float32), 1e-6
+
+
+def case_mlp_single_layer_bf16(be):
+    # test/BF16/Integration/mlp-single-layer-bf16.mlir:11-55: C(128x512) = bias broadcast (identity bcast_col); C += x . W
+    # with x = 128x128x2 (collapsed: 128x256) and VNNI-2 weights 128x512x2 -> gemm [128,512,256,256,512,512] (vnni_b);
+    # relu in place; all ones: 1 + 256 = 257 -> 256 in bf16 (expected 256, threshold 1.0)
+    g = golden()["mlp_single_layer_bf16"]
+    x, W, bias = const(BF16, (128, 256)), const(BF16, (128, 512, 2)), const(BF16, (512,))
+    C = np.zeros(128 * 512, np.uint16)
+    be.unary(1, BF16, 128, 512, 512, 512, 4, bias, 0, C, 0)
+    be.gemm(BF16, 128, 512, 256, 256, 512, 512, 2048, x, 0, W, 0, C, 0)
+    be.unary(5, BF16, 128, 512, 512, 512, 0, C, 0, C, 0)
+    return to_f32(BF16, C), np.full(C.size, g["expected_fill"], np.float32), g["threshold"]
+
+
 CASES = {name[len("case_"):]: fn for name, fn in sorted(globals().items()) if name.startswith("case_")}
