@@ -236,6 +236,22 @@ def main():
     add("mlp_single_layer_bf16", "test/BF16/Integration/mlp-single-layer-bf16.mlir:11-55", expected_fill=float(m.group(1)),
         threshold=float(thr.group(1)))
 
+    # round 2, fourth batch: block relayouts done as tile copies around tile gemms, the smoke-test matmul, a seeded
+    # row broadcast, convolutions rewritten to matmuls over strided image windows
+    t = read("test/Integration/broadcast-row-1d.mlir")
+    add("broadcast_row_1d_f32_seed123", "test/Integration/broadcast-row-1d.mlir:5-26", expected=flat_checks(t))
+    t = read("test/Integration/relayout-gemm.mlir")
+    d = dense_blocks(t)
+    add("relayout_gemm_f32", "test/Integration/relayout-gemm.mlir:30-133", A=d[0], B=d[1], expected=flat_checks(t))
+    t = read("test/Integration/relayout-more-interesting.mlir")
+    add("relayout_block_copy_f32", "test/Integration/relayout-more-interesting.mlir:22-105", input=dense_blocks(t)[0],
+        expected_all=flat_checks(t))
+    t = read("test/Integration/smoke.mlir")
+    d = dense_blocks(t)
+    add("smoke_matmul_f32", "test/Integration/smoke.mlir:13-59", A=d[0], B=d[1], expected=flat_checks(t))
+    t = read("test/Integration/conv-to-matmul.mlir")
+    add("conv_to_matmul_f32", "test/Integration/conv-to-matmul.mlir:28-152", expected_all=flat_checks(t))
+
     with open(OUT, "w") as f:
         json.dump(g, f, indent=1, sort_keys=True)
     print(f"wrote {OUT}: {len(g)} vectors, {os.path.getsize(OUT)} bytes")

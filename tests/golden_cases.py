@@ -544,4 +544,88 @@ def case_mlp_single_layer_bf16(be):
     return to_f32(BF16, C), np.full(C.size, g["expected_fill"], np.float32), g["threshold"]
 
 
+def case_broadcast_row_1d_f32_seed123(be):
+    # test/Integration/broadcast-row-1d.mlir:5-21 (--seed 123): dispatch (1,1,4,2,1,2,2) = identity, f32, [4,2,1,2],
+    # bcast_row; kernel args filled in order (arg0 4x1, arg1 4x2) from one normal generator, arg1 overwritten
+    gen = oracle.TensorInit("normal", F32, 123)
+    src, dst = gen.fill(4, 1), gen.fill(4, 2)
+    be.unary(1, F32, 4, 2, 1, 2, 2, src, 0, dst, 0)
+    return dst.reshape(-1), np.array(golden()["broadcast_row_1d_f32_seed123"]["expected"], np.float32), 1e-6   # 6 printed digits
+
+
+def _to_blocks(be, src, rows, cols, dst):
+    # "to-block-layout" of relayout-gemm.mlir:9-18 / relayout-more-interesting.mlir:8-17 with 2x2 blocks: block (i,j) of
+    # a rows x cols matrix -> dst[i][j][2][2], one identity copy [2,2,cols,2] per block
+    for i in range(rows // 2):
+        for j in range(cols // 2):
+            be.unary(1, F32, 2, 2, cols, 2, 0, src, i * 2 * cols + j * 2, dst, (i * (cols // 2) + j) * 4)
+
+
+def case_relayout_gemm_f32(be):
+    # test/Integration/relayout-gemm.mlir:30-95: A(6x8), B(8x16), C(6x16, zero) relaid out to 2x2 blocks, per output
+    # block (p1,p2) and K block r1 a gemm [2,2,2,2,2,2] accumulating into the block, then "from-block-layout"
+    # (identity [2,2,2,16] per block) back into C
+    g = golden()["relayout_gemm_f32"]
+    A, B, C = np.array(g["A"], np.float32), np.array(g["B"], np.float32), np.zeros(96, np.float32)
+    Ab, Bb, Cb = np.zeros(48, np.float32), np.zeros(128, np.float32), np.full(96, 7.0, np.float32)
+    _to_blocks(be, C, 6, 16, Cb)
+    _to_blocks(be, A, 6, 8, Ab)
+    _to_blocks(be, B, 8, 16, Bb)
+    for p1 in range(3):
+        for p2 in range(8):
+            for r1 in range(4):
+                be.gemm(F32, 2, 2, 2, 2, 2, 2, 0, Ab, (p1 * 4 + r1) * 4, Bb, (r1 * 8 + p2) * 4, Cb, (p1 * 8 + p2) * 4)
+    for i in range(3):
+        for j in range(8):
+            be.unary(1, F32, 2, 2, 2, 16, 0, Cb, (i * 8 + j) * 4, C, i * 32 + j * 2)
+    return C, np.array(g["expected"], np.float32), 6e-3   # 5 printed digits of values up to 7e2
+
+
+def case_relayout_block_copy_f32(be):
+    # test/Integration/relayout-more-interesting.mlir:22-105: (1) 6x16 -> [3][8][2][2] by block copies, (2) linalg.copy of
+    # the whole matrix (identity [6,16,16,16]) viewed as [3][8][2][2] by a pure reshape - the two printed tensors differ
+    g = golden()["relayout_block_copy_f32"]
+    d = np.array(g["input"], np.float32)
+    blocked, copied = np.zeros(96, np.float32), np.zeros(96, np.float32)
+    _to_blocks(be, d, 6, 16, blocked)
+    be.unary(1, F32, 6, 16, 16, 16, 0, d, 0, copied, 0)
+    exp = np.array(g["expected_all"], np.float32)
+    assert exp.size == 192
+    return np.concatenate([blocked, copied]), exp, 0.0
+
+
+def case_smoke_matmul_f32(be):
+    # test/Integration/smoke.mlir:13-59: C (dense<0.0>) += A(4x8) . B(8x4): gemm [4,4,8,8,4,4]
+    g = golden()["smoke_matmul_f32"]
+    A, B, C = np.array(g["A"], np.float32), np.array(g["B"], np.float32), np.zeros(16, np.float32)
+    be.gemm(F32, 4, 4, 8, 8, 4, 4, 0, A, 0, B, 0, C, 0)
+    return C, np.array(g["expected"], np.float32), 6e-3   # 5 printed digits of values up to 5e2
+
+
+def _conv_as_gemms(be, H, W, KH, KW, stride):
+    # test/Integration/conv-to-matmul.mlir:28-45 after -rewrite-conv-to-matmul-or-brgemm (IR: linalg.matmul): NHWC image
+    # 1xHxWx3 (value = channel index), HWCF filter KHxKWx3x8 (value = filter index), output 1xOHxOWx8 preloaded with the
+    # filter index; per (oh, kh, kw) one accumulating gemm over an output row: [OW, 8, 3, lda = stride*3, 8, 8] on the
+    # image window that starts at pixel (oh*stride + kh, kw)
+    OH, OW = (H - KH) // stride + 1, (W - KW) // stride + 1
+    img = np.tile(np.arange(3, dtype=np.float32), H * W)
+    flt = np.tile(np.arange(8, dtype=np.float32), KH * KW * 3)
+    out = np.tile(np.arange(8, dtype=np.float32), OH * OW)
+    for oh in range(OH):
+        for kh in range(KH):
+            for kw in range(KW):
+                be.gemm(F32, OW, 8, 3, stride * 3, 8, 8, 0, img, ((oh * stride + kh) * W + kw) * 3,
+                        flt, (kh * KW + kw) * 24, out, oh * OW * 8)
+    return out
+
+
+def case_conv_to_matmul_f32(be):
+    # test/Integration/conv-to-matmul.mlir:47-152: 1x1 filter on 4x4 (=> 4 f), 3x3 filter on 5x5 (=> 28 f), the same with
+    # stride 2 (=> 28 f on a 2x2 output)
+    outs = [_conv_as_gemms(be, 4, 4, 1, 1, 1), _conv_as_gemms(be, 5, 5, 3, 3, 1), _conv_as_gemms(be, 5, 5, 3, 3, 2)]
+    exp = np.array(golden()["conv_to_matmul_f32"]["expected_all"], np.float32)
+    assert exp.size == 128 + 72 + 32
+    return np.concatenate(outs), exp, 0.0
+
+
 CASES = {name[len("case_"):]: fn for name, fn in sorted(globals().items()) if name.startswith("case_")}
