@@ -305,9 +305,19 @@ def cpu_arm(steps, warmup, total_budget_s):
             "ms_per_step": dt * 1e3, "rows": rows}
 
 
+def workload_text(m_rank):
+    """config.workload, the same string in both arms"""
+    return (f"fused_brgemm MLP 3x({m_rank}x1024x1024)+bias+relu bf16, batch {m_rank} per GPU "
+            "(BASELINE configs[2]; configs[4] when the global batch is 2048)")
+
+
 def reference_main(args, rank):
     if rank != 0:
         return 0
+    # the GPU arm's workload at this N: 256 rows per GPU (weak), or --global-batch rows over the GPUs (strong)
+    strong = args.global_batch > 0
+    global_batch = args.global_batch if strong else BATCH_PER_GPU * args.gpus
+    m_rank = global_batch // max(args.gpus, 1)
     res = cpu_arm(args.steps, args.warmup, total_budget_s=120.0)
     try:
         proxy = torch_onednn_proxy()
@@ -316,11 +326,13 @@ def reference_main(args, rank):
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic (TensorInit normal, seed 123)",
-        "config": {"workload": "fused_brgemm MLP 3x(256x1024x1024)+bias+relu bf16, batch 256", "layers": list(LAYERS),
-                   "global_batch": BATCH_PER_GPU, "parallelism": "host cores (OpenMP)",
-                   "step": "one forward pass (a bounded row sample of it, see cpu_baseline.sample); the metric is a "
-                           "rate, so it compares with the GPU arm's 296-forward-pass steps"},
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic (TensorInit normal, seed 123; random-init weights)",
+        "config": {"workload": workload_text(m_rank), "layers": list(LAYERS), "tiles": [32, 32, 32],
+                   "global_batch": global_batch, "parallelism": "host cores (OpenMP), one host whatever --gpus is",
+                   "step": f"one forward pass over {BATCH_PER_GPU} batch rows of the workload (a bounded sample of it, see "
+                           "cpu_baseline.sample); the metric is a rate, so it compares with the GPU arm's "
+                           "296-forward-pass steps"},
         "cpu_baseline": {**{k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
                          "torch_onednn_proxy": proxy},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -788,8 +800,7 @@ def main():
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak",
         "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic (TensorInit normal, seed 123; random-init weights)",
-        "config": {"workload": f"fused_brgemm MLP 3x({m_rank}x1024x1024)+bias+relu bf16, batch {m_rank} per GPU "
-                               "(BASELINE configs[2]; configs[4] when the global batch is 2048)",
+        "config": {"workload": workload_text(m_rank),
                    "layers": list(LAYERS), "tiles": list(wl.tiles), "global_batch": global_batch,
                    "parallelism": f"batch-sharded x{n_gpus}, weights broadcast once over NCCL",
                    "step": f"{STEP_ROTATIONS} rotations over {num_sets} operand sets = {fwd_per_step} forward passes "

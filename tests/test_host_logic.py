@@ -148,6 +148,37 @@ def test_bench_keeps_library_chatter_off_stdout():
     assert "python noise" in r.stderr and "native noise" in r.stderr
 
 
+def test_bench_reference_arm_prints_the_contract_line_on_rank_0_only():
+    """`bench.py --impl reference` (the driver's CPU arm): rank 0 prints ONE JSON line with the GPU arm's metric, unit and
+    workload string, its own cpu_baseline / e2e objects and zero device copies; other ranks print nothing and exit 0."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    import bench
+
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "2", "--warmup", "3"]
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0 and r.stdout == "", (r.stdout, r.stderr)
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="2")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr
+    lines = r.stdout.strip().splitlines()
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == bench.METRIC and d["unit"] == bench.UNIT
+    assert d["n_gpus"] == 2 and d["steps"] == 2 and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["config"]["workload"] == bench.workload_text(bench.BATCH_PER_GPU) and d["config"]["global_batch"] == 512
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port"
+    assert d["cpu_baseline"]["cores"] >= 1 and "rows" in d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
+
+
 # ---- folding of captured tile invokes into layers (runtime.cu: fold_grid), no GPU needed --------------------------------
 def _fold(m, n, k, lda, ldb, ldc, sa, sb, flags, batch, invokes, with_bias=True):
     import ctypes
