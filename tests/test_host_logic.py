@@ -15,6 +15,35 @@ def test_flops_match_reference_convention():
     assert cfg8.flops() == 8 * 1_612_185_600
 
 
+def test_layouts_and_flops_match_the_reference_mlir_gen_tests():
+    """The reference pins mlir-gen's operand types and BENCH_TOTAL_FLOPS in its own tests; the harness must build the
+    same block-packed shapes and count the same FLOPs."""
+    # test/Integration/mlir-gen-matmul.mlir:1-11, test/BF16/Integration/mlir-gen-matmul-bf16.mlir:1-40 and the -fc twins
+    # (mlir-gen-fc.mlir:1-11, mlir-gen-fc-bf16.mlir:1-56): --batch=128 --layers=2304,768 --tiles=64,48,64
+    bn, bk, bc = 64, 48, 64
+    x, w = torch.zeros(128, 2304), torch.zeros(2304, 768)
+    xp, wp = harness.pack_activation(x, bn, bc), harness.pack_weight(w, bk, bc)
+    assert tuple(xp.shape) == (2, 36, 64, 64)                                  # %arg0: tensor<2x36x64x64x..>
+    assert tuple(wp.shape) == (16, 36, 64, 48)                                 # %arg1: tensor<16x36x64x48x..>
+    assert tuple(harness.vnni_pack_weight(wp, 2).shape) == (16, 36, 32, 48, 2)   # DP2: tensor<16x36x32x48x2xbf16>
+    assert tuple(harness.vnni_pack_weight(wp, 4).shape) == (16, 36, 16, 48, 4)   # DP4: tensor<16x36x16x48x4xbf16>
+    out = torch.zeros(2, 16, 64, 48)                                           # result: tensor<2x16x64x48x..>, bias 16x48
+    assert tuple(harness.unpack_activation(out).shape) == (128, 768)
+    mm = harness.MlpConfig(batch=128, layers=(2304, 768), tiles=(bn, bk, bc), bias=False, relu=False)
+    fc = harness.MlpConfig(batch=128, layers=(2304, 768), tiles=(bn, bk, bc))
+    assert mm.flops() == 452984832 and fc.flops() == 453181440
+    # test/Integration/mlir-gen-flops.mlir:2-50
+    def flops(batch, layers, fused):
+        t = (1, 1, 1)
+        return harness.MlpConfig(batch=batch, layers=layers, tiles=t, dtype=1, bias=fused, relu=fused).flops()
+
+    assert flops(1, (1, 1), False) == 2 and flops(1, (1, 1), True) == 4                       # MATMUL-UNIT, FC-UNIT / MLP-UNIT
+    assert flops(8, (4, 16), False) == 1024 and flops(8, (4, 16), True) == 1280               # MATMUL-SMALL, FC-SMALL
+    assert flops(8, (4, 8, 16), True) == 2944                                                 # MLP-SMALL
+    assert flops(128, (1024, 4096), False) == 1073741824 and flops(128, (1024, 4096), True) == 1074790400   # *-LARGE
+    assert flops(128, (1024, 1024, 1024), True) == 537395200                                  # MLP-LARGE
+
+
 def test_config_validation():
     with pytest.raises(ValueError):
         harness.MlpConfig(batch=100, tiles=(32, 32, 32))

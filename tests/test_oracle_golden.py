@@ -128,3 +128,42 @@ def test_vnni4_layout_of_the_oracle():
     finally:
         oracle.set_vnni_factor(2)
     np.testing.assert_array_equal(c_flat, c_v4)
+
+
+def test_xsmm_semantics_agree_with_the_loops_path_like_the_reference_checks():
+    """test/BF16/Integration/vnni-xsmm-vs-loops.mlir:1-13: the reference runs
+    `mlir-gen --kernel=const --bias --relu --seed=123 --batch=16 --layers=16,16 --tiles=16,16,16 --float-type=bf16`
+    once through the xsmm path and once with -linalg-to-loops and accepts `fpcmp -r 0.01` between the two printed
+    tensors. The loops path is independent of libxsmm: the linalg.generic bodies are plain arith.mulf / arith.addf in
+    bf16 (every product and every partial sum rounded to bf16), then bias add and max(x, 0) in bf16. Restated here in
+    numpy and compared with the oracle (f32 accumulation, one rounding) under fpcmp's rule |a / b - 1| <= 0.01
+    (tools/fpcmp/fpcmp.c:198-205) - the same independent cross-check of the oracle's semantics the reference applies to
+    libxsmm. Data: weights from TensorInit(normal, seed 123), bias from the seed mlir-gen draws next (rand() after
+    srand(123): tools/mlir-gen/MLIRGen.cpp:131-134, 256-259, 812-818), input from tpp-run's own seed-123 generator."""
+    import ctypes
+
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(123)
+    bias_seed = libc.rand()
+    m = n = k = 16
+    W = oracle.TensorInit("normal", oracle.BF16, 123).fill(k, n)
+    bias = oracle.TensorInit("normal", oracle.BF16, bias_seed).fill(n)
+    x = oracle.TensorInit("normal", oracle.BF16, 123).fill(m, k)
+
+    got = np.zeros((m, n), np.uint16)
+    oracle.fused_brgemm(2, m, n, k, k, n, n, 0, 0, 4, 0, 5, 4, 1, x, W, got, bias, 1)
+    xsmm_path = oracle.bf16_to_f32(got)
+
+    def r(a):   # one bf16 rounding
+        return oracle.bf16_to_f32(oracle.f32_to_bf16(np.ascontiguousarray(a, dtype=np.float32)))
+
+    xf, wf, bf = oracle.bf16_to_f32(x), oracle.bf16_to_f32(W), oracle.bf16_to_f32(bias)
+    acc = np.zeros((m, n), np.float32)
+    for c in range(k):   # reduction loop of the generic: out = out + in0 * in1, both ops in bf16
+        acc = r(acc + r(np.outer(xf[:, c], wf[c, :])))
+    loops_path = np.maximum(r(acc + bf[None, :]), 0.0)
+
+    assert (loops_path > 0).any()
+    both_zero = (xsmm_path == 0) & (loops_path == 0)
+    ratio = np.where(both_zero, 1.0, xsmm_path / np.where(loops_path == 0, 1e-30, loops_path))
+    assert np.abs(ratio - 1.0).max() <= 0.01, np.abs(ratio - 1.0).max()
