@@ -92,3 +92,46 @@ def test_dispatch_without_gpu_fails_loudly():
     assert p.returncode != 0
     assert "SURVIVED" not in p.stdout
     assert "no CUDA device" in p.stderr
+
+
+def _param_class(p):
+    p = p.strip()
+    if "*" in p:
+        return "ptr"
+    if re.match(r"(const\s+)?float\b", p):
+        return "float"
+    return "i64"   # int64_t and the libxsmm enums the lowering passes as i64 (ConvertXsmmToFunc.cpp:37-78)
+
+
+def _param_name(p):
+    m = re.search(r"(\w+)$", p.strip())
+    return m.group(1) if m and not re.match(r"(int64_t|float|libxsmm_\w+)$", m.group(1)) else None
+
+
+def test_prototypes_follow_the_reference_header_and_the_pinned_call_order():
+    """Every one of the 13 xsmm_* entry points has the reference's result type, parameter count and parameter classes
+    (i64 / pointer / float, in order; runtime/Xsmm/XsmmRunnerUtils.h:22-83, extracted into
+    tests/golden/reference_abi_calls.json) and, where the reference names a parameter, the same name; the argument counts
+    the lowering's FileCheck lines pin (test/Conversion/XsmmToFunc/xsmm-to-func.mlir) agree too."""
+    import json
+
+    with open(os.path.join(ROOT, "tests", "golden", "reference_abi_calls.json")) as f:
+        ref = json.load(f)
+    text = open(os.path.join(ROOT, "include", "tpp_xsmm_abi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    ours = {}
+    for m in re.finditer(r"TPP_XSMM_EXPORT\s+(\w+)\s+(\w+)\s*\(([^;]*?)\)\s*;", text, re.S):
+        ours[m.group(2)] = (m.group(1), [re.sub(r"\s+", " ", p.strip()) for p in m.group(3).split(",") if p.strip()])
+    assert len(ref["header"]) == 13
+    for name, proto in ref["header"].items():
+        assert name in ours, name
+        result, params = ours[name]
+        assert result == proto["result"], name
+        assert [_param_class(p) for p in params] == [_param_class(p) for p in proto["params"]], name
+        for mine, theirs in zip(params, proto["params"]):
+            want = _param_name(theirs)
+            if want and want not in ("dType", "data_type", "unary_op_type", "binary_op_type"):
+                assert _param_name(mine) == want, (name, mine, theirs)
+    for name, lines in ref["calls"].items():
+        for c in lines:
+            assert c["num_args"] == len(ours[name][1]), (name, c["line"])
