@@ -17,7 +17,7 @@ with open(os.path.join(ROOT, "tests", "golden", "reference_bench_shapes.json")) 
 
 @pytest.fixture(scope="module")
 def exe(tmp_path_factory):
-    out = tmp_path_factory.mktemp("standin_stub") / "tpp_run_standin_stub"
+    out = tmp_path_factory.mktemp("standin_stub") / "tpp_run_standin"   # the name bench_driver --build looks for
     cmd = ["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"),
            os.path.join(ROOT, "tpp_mlir_b200", "csrc", "harness", "tpp_run_standin.cpp"),
            os.path.join(ROOT, "tests", "stubs", "xsmm_abi_stub_standin.cpp"), "-o", str(out)]
@@ -143,3 +143,77 @@ def test_flops_follow_the_reference_count(exe, tmp_path):
 def test_bad_command_lines_are_refused(args, exe, tmp_path):
     rc, _, _ = run(exe, tmp_path, *args)
     assert rc == 2
+
+
+# ---- tpp_mlir_b200/bench_driver.py: the reference's benchmarks/driver.py contract on top of the stand-in -------------------
+DRIVER_CONFIG = [
+    {"mlp_bf16_dp2_mlir": {
+        "bf16_dp2_3x1024_omp_16_mlir": {   # benchmarks/config/omp/mlir-bf16.json:34-62
+            "type": "IR-GEN",
+            "benchmark": ["mlir-gen", "--kernel=const --bias --relu --float-type=bf16 --vnni=2 --batch=256 "
+                                      "--layers=1024,1024,1024,1024 --tiles=32,32,32"],
+            "environment": {"OMP_NUM_THREADS": "16"},
+            "flags": ["-n", "100", "-run-args='-def-parallel'"],
+            "extensions": [],
+        },
+        "never_on_this_host": {
+            "type": "IR-GEN",
+            "benchmark": ["mlir-gen", "--kernel=const --float-type=bf16 --batch=256 --layers=1024,1024"],
+            "environment": {}, "flags": ["-n", "100"], "extensions": ["(no_such_cpu_flag)"],
+        }}},
+    {"fc_1024x352x512": {
+        "fc_fp32_single_dnn": {   # benchmarks/config/fc/1024x352x512.json
+            "type": "XSMM-DNN", "benchmark": "xsmm_dnn_mlp", "environment": {"OMP_NUM_THREADS": "1"},
+            "flags": ["100", "1024", "3", "F", "32", "32", "32", "0", "1", "512", "352"], "extensions": [],
+        },
+        "fc_fp32_single_mlir": {
+            "type": "IR-GEN",
+            "benchmark": ["mlir-gen", "--kernel=args --bias --relu --float-type=f32 --batch=1024 --layers=512,352 --tiles=32,32,32"],
+            "environment": {"OMP_NUM_THREADS": "1"}, "flags": ["-n", "100"], "extensions": [],
+        },
+        "from_a_file": {
+            "type": "MLIR", "benchmark": "fp32-mha-tensorflow.mlir", "environment": {}, "flags": ["-n", "100"], "extensions": [],
+        }}},
+]
+
+
+def _drive(exe, tmp_path, config, *extra):
+    import sys
+
+    path = tmp_path / "config.json"
+    path.write_text(json.dumps(config))
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    return subprocess.run([sys.executable, "-m", "tpp_mlir_b200.bench_driver", "-c", str(path), "--build", os.path.dirname(exe),
+                           *extra], capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
+
+
+def test_bench_driver_prints_the_reference_report(exe, tmp_path):
+    """`Benchmark: <name>` / `<run:28>: <%9.3f> gflops` / blank line (benchmarks/driver.py:498-515, controller.py:316);
+    entries whose extensions the host lacks are dropped, run types that need the reference's toolchain are skipped; the
+    stub's timer reports 1 s for the timed loop, so gflops = FLOPs * n / 1e9."""
+    r = _drive(exe, tmp_path, DRIVER_CONFIG, "-n", "10")
+    assert r.returncode == 0, r.stderr
+    assert r.stdout == ("Benchmark: mlp_bf16_dp2_mlir\n"
+                        f"{'bf16_dp2_3x1024_omp_16_mlir':28}: {1612185600 * 10 / 1e9:9.3f} gflops\n"
+                        "\n"
+                        "Benchmark: fc_1024x352x512\n"
+                        f"{'fc_fp32_single_mlir':28}: {(2 * 1024 * 512 * 352 + 2 * 1024 * 352) * 10 / 1e9:9.3f} gflops\n"
+                        "\n")
+
+
+def test_bench_driver_iterations_modes_and_json(exe, tmp_path):
+    r = _drive(exe, tmp_path, DRIVER_CONFIG[:1], "--json", "--mode", "device", "--ignore-extensions")
+    assert r.returncode == 0, r.stderr
+    rows = [json.loads(line) for line in r.stdout.splitlines() if line.startswith("{")]
+    assert [row["run"] for row in rows] == ["bf16_dp2_3x1024_omp_16_mlir", "never_on_this_host"]
+    assert all(row["mode"] == "device" and row["iterations"] == 100 for row in rows)   # -n from the entry's own flags
+    assert rows[1]["float_type"] == "bf16" and rows[1]["vnni"] == 2 and rows[1]["bias"] == 0   # mlir-gen's defaults
+
+
+def test_bench_driver_errors(exe, tmp_path):
+    bad = [{"broken": {"run": {"type": "IR-GEN", "benchmark": ["mlir-gen", "--batch=100 --layers=64,64"], "environment": {},
+                               "flags": [], "extensions": []}}}]
+    assert _drive(exe, tmp_path, bad).returncode == 1
+    r = _drive(exe, tmp_path, bad, "--ignore-errors")
+    assert r.returncode == 0 and r.stdout == "Benchmark: broken\n\n"
+    assert _drive(exe, tmp_path, [{"a": {}, "b": {}}]).returncode == 1   # one benchmark per list element
