@@ -135,3 +135,24 @@ def test_prototypes_follow_the_reference_header_and_the_pinned_call_order():
     for name, lines in ref["calls"].items():
         for c in lines:
             assert c["num_args"] == len(ours[name][1]), (name, c["line"])
+
+
+def test_nvtx_ranges_need_no_profiler_and_no_gpu():
+    """TPP_XSMM_NVTX=1 wraps every invoke entry in an NVTX range (runtime.cu: NvtxRange). Without a profiler attached the
+    NVTX calls are no-ops: an invoke with a bogus handle must end the way it does without the variable - the reference's
+    error convention (message on stderr, exit(-1): XsmmRunnerUtils.cpp:132-137) - not in a crash."""
+    code = "\n".join([
+        "import ctypes, sys",
+        "sys.path.insert(0, %r)" % ROOT,
+        "from tpp_mlir_b200 import _build",
+        "lib = ctypes.CDLL(_build.lib_path())",
+        "lib.xsmm_unary_invoke.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64]",
+        "lib.xsmm_unary_invoke(1, 0, None, 0, None, 0)",
+    ])
+    outs = []
+    for nvtx in ("0", "1"):
+        env = dict(os.environ, TPP_XSMM_NVTX=nvtx)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=env)
+        outs.append((r.returncode, r.stderr.strip().splitlines()[-1]))
+    assert outs[0] == outs[1]
+    assert outs[0][0] == 255 and "handle" in outs[0][1]

@@ -17,6 +17,8 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "common.cuh"
 #include "kernel_desc.h"
 #include "kernels.h"
@@ -174,6 +176,21 @@ inline void count_launch() {
   if (t_ctx.capturing) ++t_ctx.captured_launches;   // recorded, not executed yet
   else g_launches.fetch_add(1, std::memory_order_relaxed);
 }
+
+// NVTX range per ABI entry (TPP_XSMM_NVTX=1; off by default: one predictable branch per invoke). The range names are the
+// invoke kinds, so `ncu --nvtx --nvtx-include "xsmm_fused_brgemm_invoke/"` (or an nsys timeline) selects the launches of
+// one kind of TPP; without a profiler attached the NVTX calls are no-ops of the header-only library.
+struct NvtxRange {
+  static bool enabled() {
+    static const bool on = [] { const char *e = getenv("TPP_XSMM_NVTX"); return e && e[0] == '1'; }();
+    return on;
+  }
+  const bool on;
+  explicit NvtxRange(const char *name) : on(enabled()) { if (on) nvtxRangePushA(name); }
+  ~NvtxRange() { if (on) nvtxRangePop(); }
+  NvtxRange(const NvtxRange &) = delete;
+  NvtxRange &operator=(const NvtxRange &) = delete;
+};
 
 // ---- registered host ranges -> device mirrors -----------------------------------
 struct Mirror {
@@ -976,12 +993,14 @@ extern "C" int64_t xsmm_intel_amx_tile_config_dispatch(int64_t dtype, int64_t m,
 
 extern "C" void xsmm_gemm_invoke(int64_t dtype, int64_t addr, void *alignedPtrA, int64_t offsetA, void *alignedPtrB,
                                  int64_t offsetB, void *alignedPtrC, int64_t offsetC) {
+  NvtxRange nvtx("xsmm_gemm_invoke");
   const KernelDesc *d = desc_of(addr, OpClass::Gemm);
   gemm_family_invoke(d, dtype, alignedPtrA, offsetA, alignedPtrB, offsetB, alignedPtrC, offsetC, nullptr, 0, 1);
 }
 
 extern "C" void xsmm_brgemm_invoke(int64_t dtype, int64_t addr, void *alignedPtrA, int64_t offsetA, void *alignedPtrB,
                                    int64_t offsetB, void *alignedPtrC, int64_t offsetC, int64_t numBatches) {
+  NvtxRange nvtx("xsmm_brgemm_invoke");
   const KernelDesc *d = desc_of(addr, OpClass::Brgemm, OpClass::Gemm);
   gemm_family_invoke(d, dtype, alignedPtrA, offsetA, alignedPtrB, offsetB, alignedPtrC, offsetC, nullptr, 0,
                      numBatches);
@@ -990,6 +1009,7 @@ extern "C" void xsmm_brgemm_invoke(int64_t dtype, int64_t addr, void *alignedPtr
 extern "C" void xsmm_fused_brgemm_invoke(int64_t dtype, int64_t addr, void *alignedPtrA, int64_t offsetA,
                                          void *alignedPtrB, int64_t offsetB, void *alignedPtrC, int64_t offsetC,
                                          void *alignedPtrD, int64_t offsetD, int64_t numBatches) {
+  NvtxRange nvtx("xsmm_fused_brgemm_invoke");
   const KernelDesc *d = desc_of(addr, OpClass::FusedBrgemm);
   gemm_family_invoke(d, dtype, alignedPtrA, offsetA, alignedPtrB, offsetB, alignedPtrC, offsetC, alignedPtrD, offsetD,
                      numBatches);
@@ -1292,12 +1312,14 @@ static void unary_invoke_impl(const KernelDesc *d, int64_t dtype, void *pIn, int
 
 extern "C" void xsmm_unary_invoke(int64_t dtype, int64_t addr, void *alignedPtrIn, int64_t offsetIn,
                                   void *alignedPtrOut, int64_t offsetOut) {
+  NvtxRange nvtx("xsmm_unary_invoke");
   const KernelDesc *d = desc_of(addr, OpClass::Unary);
   unary_invoke_impl(d, dtype, alignedPtrIn, offsetIn, false, 0.f, alignedPtrOut, offsetOut);
 }
 
 extern "C" void xsmm_unary_scalar_invoke(int64_t dtype, int64_t addr, float scalar, void *alignedPtrOut,
                                          int64_t offsetOut) {
+  NvtxRange nvtx("xsmm_unary_scalar_invoke");
   const KernelDesc *d = desc_of(addr, OpClass::Unary);
   if (d->impl != KernelImpl::Eltwise) fail("xsmm_unary_scalar_invoke: only identity/zero/relu take a scalar input");
   unary_invoke_impl(d, dtype, nullptr, 0, true, scalar, alignedPtrOut, offsetOut);
@@ -1305,6 +1327,7 @@ extern "C" void xsmm_unary_scalar_invoke(int64_t dtype, int64_t addr, float scal
 
 extern "C" void xsmm_binary_invoke(int64_t dtype, int64_t addr, void *alignedPtrLhs, int64_t offsetLhs,
                                    void *alignedPtrRhs, int64_t offsetRhs, void *alignedPtrOut, int64_t offsetOut) {
+  NvtxRange nvtx("xsmm_binary_invoke");
   const KernelDesc *d = desc_of(addr, OpClass::Binary);
   if (dtype != d->dtype) fail("invoke data type does not match the dispatched kernel");
   if (t_ctx.recording() && d->dtype == kBF16 && d->kind == XSMM_BINARY_ADD && d->flags == XSMM_BINARY_FLAG_BCAST_COL_IN_0 &&
@@ -1663,6 +1686,7 @@ extern "C" int64_t xsmm_cuda_graph_end(void) {
 }
 
 extern "C" void xsmm_cuda_graph_launch(int64_t graph) {
+  NvtxRange nvtx("xsmm_cuda_graph_launch");
   GraphHandle *gh = reinterpret_cast<GraphHandle *>(graph);
   if (!gh || gh->magic != 0x47525048u) fail("xsmm_cuda_graph_launch: not a graph handle");
   flush_pending();   // orders the launch after this thread's pending upload_async
