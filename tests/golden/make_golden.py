@@ -252,6 +252,16 @@ def main():
     t = read("test/Integration/conv-to-matmul.mlir")
     add("conv_to_matmul_f32", "test/Integration/conv-to-matmul.mlir:28-152", expected_all=flat_checks(t))
 
+    # round 2, fifth batch: seeded column broadcast, an add written into slices of a larger tensor, scalar fills of subviews
+    t = read("test/Integration/broadcast-2d.mlir")
+    add("broadcast_col_2d_f32_seed123", "test/Integration/broadcast-2d.mlir:7-33", expected=flat_checks(t, "COLUMNBROADCAST"))
+    t = read("test/Integration/tpp-add.mlir")
+    m = re.search(r"EXE-COUNT-(\d+):\s*\(([^)]*)\)", t)
+    add("tpp_add_slices_f32", "test/Integration/tpp-add.mlir:23-71", repeat=int(m.group(1)), row=nums(m.group(2)))
+    t = read("test/Integration/subview-on-tensor.mlir")
+    add("fill_subviews_f32", "test/Integration/subview-on-tensor.mlir:11-57", expected=flat_checks(t),
+        fills=[float(x) for x in re.findall(r"%cst1? = arith.constant (" + NUM + ") : f32", t)])
+
     with open(OUT, "w") as f:
         json.dump(g, f, indent=1, sort_keys=True)
     print(f"wrote {OUT}: {len(g)} vectors, {os.path.getsize(OUT)} bytes")

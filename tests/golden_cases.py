@@ -628,4 +628,38 @@ def case_conv_to_matmul_f32(be):
     return np.concatenate(outs), exp, 0.0
 
 
+def case_broadcast_col_2d_f32_seed123(be):
+    # test/Integration/broadcast-2d.mlir:7-15 (--seed 123): an 8-vector broadcast over the rows of a 2x4x8 tensor ->
+    # identity [8, 8, 8, 8] with bcast_col; kernel args filled in order (arg0 8, arg1 2x4x8) from one normal generator
+    gen = oracle.TensorInit("normal", F32, 123)
+    src, dst = gen.fill(8), gen.fill(2, 4, 8)
+    be.unary(1, F32, 8, 8, 8, 8, 4, src, 0, dst, 0)
+    return dst.reshape(-1), np.array(golden()["broadcast_col_2d_f32_seed123"]["expected"], np.float32), 1e-6
+
+
+def case_tpp_add_slices_f32(be):
+    # test/Integration/tpp-add.mlir:23-71: b0 = rows of 0..31 (56x32); per (i, j) of a 2x56x56x32 tensor the slice
+    # [i, j, :, :] = b0 + b0: binary add [56,32,32,32,32] with the output at offset (i*56 + j) * 56*32; every one of the
+    # 6272 printed rows is 0, 2, ..., 62
+    g = golden()["tpp_add_slices_f32"]
+    b0 = np.ascontiguousarray(np.tile(np.arange(32, dtype=np.float32), (56, 1)))
+    out = np.full(2 * 56 * 56 * 32, -1.0, np.float32)
+    for i in range(2):
+        for j in range(56):
+            be.binary(1, F32, 56, 32, 32, 32, 32, 0, b0, 0, b0, 0, out, (i * 56 + j) * 56 * 32)
+    assert g["repeat"] * len(g["row"]) == out.size
+    return out, np.tile(np.array(g["row"], np.float32), g["repeat"]), 0.0
+
+
+def case_fill_subviews_f32(be):
+    # test/Integration/subview-on-tensor.mlir:11-57: linalg.fill of the 3x3 subviews [0,0] and [1,1] of a zero 2x2x3x3
+    # tensor with 5.0 / 6.0 -> identity [3,3,1,3] with bcast_scalar, the scalar passed by value
+    # (xsmm_unary_scalar_invoke), outputs at offsets 0 and 27
+    g = golden()["fill_subviews_f32"]
+    A = np.zeros(36, np.float32)
+    for value, slot in zip(g["fills"], (0, 1)):
+        be.unary_scalar(1, F32, 3, 3, 1, 3, 8, value, A, (slot * 2 + slot) * 9)
+    return A, np.array(g["expected"], np.float32), 0.0
+
+
 CASES = {name[len("case_"):]: fn for name, fn in sorted(globals().items()) if name.startswith("case_")}
